@@ -1,0 +1,290 @@
+"""dc / tran entry points -- host mirror of ``dc!`` / ``tran!`` (src/sweeps.jl:450-532,
+:588-707) on top of the C ABI.  A CircuitSweep is lowered once (one builder run with
+lane-array parameters) and solved for all lanes by the CUDA kernels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import backend
+from .circuit import MNACircuit, MNASpec, Params, with_mode
+from .lowering import LoweredCircuit, lower
+from .mna import PWLWave, PulseWave, SinWave, Wave
+from .sweeps import CircuitSweep, SweepResult
+
+_RETCODES = {0: "Success", 1: "MaxIters", 2: "Unstable", 3: "Unstable", 4: "DtLessThanMin"}
+
+
+# --------------------------------------------------------------------------- #
+# breakpoints (src/mna/breakpoints.jl, src/mna/solve.jl:1847-1918)
+# --------------------------------------------------------------------------- #
+def breakpoints(wave) -> Optional[Tuple[List[float], float, int]]:
+    """``breakpoints(wave)`` -> (times, period, count) or None (devices.jl:145,180,211)."""
+    if isinstance(wave, PWLWave):
+        return ([float(t) for t in wave.ts], 0.0, -1)
+    if isinstance(wave, SinWave):
+        td = float(wave.p[3])
+        return ([td], 0.0, -1) if td > 0 else None
+    if isinstance(wave, PulseWave):
+        v1, v2, td, tr, tf, pw, per = [float(x) for x in wave.p]
+        edges = [td, td + tr, td + tr + pw, td + tr + pw + tf]
+        return (edges, per, -1) if per > 0 else (edges, 0.0, -1)
+    return None
+
+
+def expand_breakpoints(specs: Sequence, tspan: Tuple[float, float], max_points: int = 100_000) -> List[float]:
+    """``expand_breakpoints`` (solve.jl:1847-1918): strictly inside tspan, sorted,
+    truncated to ``max_points``, dedup tolerance ``4*max(eps(a), eps(b))``."""
+    t0, t1 = float(tspan[0]), float(tspan[1])
+    out: List[float] = []
+    for spec in specs:
+        if spec is None:
+            continue
+        if isinstance(spec, Wave):
+            spec = breakpoints(spec)
+            if spec is None:
+                continue
+        times, period, count = spec
+        if not times:
+            continue
+        if period <= 0:
+            out += [t for t in times if t0 < t < t1]
+        else:
+            tmin, tmax = min(times), max(times)
+            k_start = int(min(max(math.floor((t0 - tmax) / period), 0.0), 1e15))
+            k_end = int(min(max(math.ceil((t1 - tmin) / period), -1.0), 1e15))
+            if count >= 0:
+                k_end = min(k_end, count - 1)
+            if k_end < k_start:
+                continue
+            if k_end - k_start + 1 > max_points:
+                k_end = k_start + max_points - 1
+            for k in range(k_start, k_end + 1):
+                base = k * period
+                out += [t + base for t in times if t0 < t + base < t1]
+    if not out:
+        return out
+    out.sort()
+    out = out[:max_points]
+    dedup = [out[0]]
+    for x in out[1:]:
+        tol = 4 * max(np.spacing(abs(dedup[-1])), np.spacing(abs(x)))
+        if x - dedup[-1] > tol:
+            dedup.append(x)
+    return dedup
+
+
+# --------------------------------------------------------------------------- #
+# solutions
+# --------------------------------------------------------------------------- #
+class DCSolution:
+    """``DCSolution`` (solve.jl:156-166): ``x``, name vectors, ``converged``;
+    ``sol["out"]`` looks a node / current / charge / limit variable up by name."""
+
+    def __init__(self, lc: LoweredCircuit, x: np.ndarray, converged: bool, iters: int = 0):
+        self.x = x
+        self.node_names = lc.node_names
+        self.current_names = lc.current_names
+        self.charge_names = lc.charge_names
+        self.limit_names = lc.limit_names
+        self.n_nodes = lc.n_nodes
+        self.converged = bool(converged)
+        self.iters = int(iters)
+        self._lc = lc
+
+    def __getitem__(self, name):
+        return float(self.x[self._lc.index_of(name) - 1])
+
+    def __repr__(self):
+        return f"DCSolution(n={len(self.x)}, converged={self.converged})"
+
+
+class TranSolution:
+    """One lane of a transient sweep: the subset of the SciML solution interface the
+    reference's callers use (``sol.t``, ``sol.u``, ``sol[name]``, ``sol(t)``,
+    ``sol.retcode``, ``sol.stats``)."""
+
+    def __init__(self, lc: LoweredCircuit, save_idx: Sequence[int], t: np.ndarray, u: np.ndarray,
+                 status: int, newton_iters: int):
+        self._lc = lc
+        self._save = list(save_idx)
+        self.t = t
+        self.u = u                      # [T][n_save] view
+        self.status = int(status)
+        self.retcode = _RETCODES.get(int(status), "Failure")
+        self.stats = dict(nnonliniter=int(newton_iters), naccept=len(t) - 1)
+
+    def __getitem__(self, name):
+        idx = self._lc.index_of(name)
+        try:
+            col = self._save.index(idx)
+        except ValueError:
+            raise KeyError(f"{name!r} was not saved (save_idxs)") from None
+        return self.u[:, col]
+
+    def __call__(self, t: float) -> np.ndarray:
+        """Linear interpolation between saved points."""
+        return np.array([np.interp(t, self.t, self.u[:, q]) for q in range(self.u.shape[1])])
+
+
+class _LazyTranSolutions:
+    def __init__(self, lc, save_idx, t, u, count, status, iters, adaptive):
+        self.lc, self.save_idx, self.t, self.u = lc, save_idx, t, u
+        self.count, self.status, self.iters, self.adaptive = count, status, iters, adaptive
+
+    def __len__(self):
+        return self.u.shape[2]
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        T = int(self.count[i])
+        t = self.t[:T, i] if self.adaptive else self.t[:T]
+        return TranSolution(self.lc, self.save_idx, t, self.u[:, :T, i].T, self.status[i], self.iters[i])
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+
+class _LazyDCSolutions:
+    def __init__(self, lc, x, status, iters):
+        self.lc, self.x, self.status, self.iters = lc, x, status, iters
+
+    def __len__(self):
+        return self.x.shape[1]
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return DCSolution(self.lc, self.x[:, i].copy(), self.status[i] == 0, self.iters[i])
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+
+# --------------------------------------------------------------------------- #
+# compiled sweeps
+# --------------------------------------------------------------------------- #
+class CompiledSweep:
+    """A lowered circuit bound to one GPU: pattern, maps and device table built once,
+    lane parameters resident in HBM.  ``lanes`` restricts the handle to a contiguous
+    block of the sweep (multi-GPU sharding)."""
+
+    def __init__(self, lc: LoweredCircuit, spec: MNASpec, device: int = 0,
+                 lanes: Optional[slice] = None):
+        self.lc = lc
+        self.spec = spec
+        self.device = device
+        self.handle = backend.Handle(lc, device)
+        soa = lc.lane_soa if lanes is None else np.ascontiguousarray(lc.lane_soa[:, lanes])
+        self.P = int(soa.shape[1])
+        self.lane_slice = lanes
+        self._soa = soa
+        self.handle.set_lanes(soa, self.P)
+
+    def upload_lanes(self):
+        """Re-send the lane parameters (the per-step H2D copy of the e2e measurement)."""
+        self.handle.set_lanes(self._soa, self.P)
+
+    def save_indices(self, save_idxs) -> List[int]:
+        if save_idxs is None:
+            return list(range(1, self.lc.n + 1))
+        return [self.lc.index_of(s) for s in save_idxs]
+
+    def dc(self, u0=None, abstol=1e-10, maxiters=100, use_stepping=True, mode="dcop"):
+        return self.handle.dc(self.spec, u0, abstol, maxiters, use_stepping, mode)
+
+    def tran(self, tspan, dt, method="be", save_idxs=None, save_every=1, abstol=1e-10,
+             max_nl_iters=10, u0=None, init_abstol=1e-9, init_maxiters=500) -> backend.Wave:
+        opts = backend.make_tran_opts(method=method, adaptive=False, dt=dt, abstol=abstol,
+                                      max_nl_iters=max_nl_iters, save_every=save_every,
+                                      init=0 if u0 is None else 1, init_abstol=init_abstol,
+                                      init_maxiters=init_maxiters)
+        return self.handle.tran(self.spec, tspan[0], tspan[1], opts, self.save_indices(save_idxs), u0)
+
+    def close(self):
+        self.handle.close()
+
+
+def compile_sweep(cs: Union[CircuitSweep, MNACircuit], spec: Optional[MNASpec] = None,
+                  device: int = 0, lanes: Optional[slice] = None) -> CompiledSweep:
+    if isinstance(cs, MNACircuit):
+        sp = spec or cs.spec
+        return CompiledSweep(lower(cs.builder, cs.params, sp, P=1), sp, device)
+    params, P = cs.lane_params()
+    sp = spec or cs.circuit.spec
+    return CompiledSweep(lower(cs.builder, params, sp, P=P), sp, device, lanes)
+
+
+# --------------------------------------------------------------------------- #
+# dc! / tran!
+# --------------------------------------------------------------------------- #
+def dc(obj, u0=None, continuation: bool = True, abstol: float = 1e-10, maxiters: int = 100,
+       device: int = 0):
+    """``dc!(circuit; u0)`` (sweeps.jl:450-454) / ``dc!(cs::CircuitSweep; continuation)``
+    (sweeps.jl:511-532).  ``dc!`` goes through ``with_mode(circuit, :dcop)``, which
+    rebuilds the spec from temp+mode only (solve.jl:1976-1979) -- preserved.
+
+    For a sweep all lanes are solved concurrently from a cold start; ``continuation``
+    is accepted for API compatibility (the reference's tests assert it changes the
+    path Newton takes, not where it lands: test/sweep.jl:340-345)."""
+    if isinstance(obj, MNACircuit):
+        c = with_mode(obj, "dcop")
+        comp = compile_sweep(c, device=device)
+        try:
+            uu = None if u0 is None or len(u0) != comp.lc.n else np.asarray(u0, float).reshape(-1, 1)
+            x, st, it = comp.dc(uu, abstol, maxiters)
+        finally:
+            comp.close()
+        return DCSolution(comp.lc, x[:, 0].copy(), st[0] == 0, it[0])
+    if isinstance(obj, CircuitSweep):
+        spec = MNASpec(temp=obj.circuit.spec.temp, mode="dcop")
+        comp = compile_sweep(obj, spec=spec, device=device)
+        try:
+            x, st, it = comp.dc(None, abstol, maxiters)
+        finally:
+            comp.close()
+        return SweepResult(obj.iterator.points(), _LazyDCSolutions(comp.lc, x, st, it))
+    raise TypeError("dc expects an MNACircuit or CircuitSweep")
+
+
+def tran(obj, tspan: Tuple[float, float], solver: Optional[str] = None, abstol: float = 1e-10,
+         reltol: float = 1e-8, dt: Optional[float] = None, adaptive: Optional[bool] = None,
+         saveat: Optional[float] = None, save_idxs=None, max_nl_iters: int = 10, device: int = 0):
+    """``tran!(circuit, tspan; solver, abstol, reltol, kw...)`` (sweeps.jl:588-601) and
+    ``tran!(cs::CircuitSweep, tspan; kw...)`` (sweeps.jl:692-707).
+
+    ``solver``: "ImplicitEuler" | "Trapezoid" | "gear2".  Fixed-step mode is the
+    reference's ``solver=ImplicitEuler()/Trapezoid(), adaptive=false, dt=h``."""
+    method = solver or "Trapezoid"
+    if dt is None:
+        raise ValueError("fixed-step transient needs dt= (adaptive stepping: adaptive=True)")
+    save_every = 1
+    if saveat is not None:
+        save_every = max(1, int(round(saveat / dt)))
+    single = isinstance(obj, MNACircuit)
+    if not single and not isinstance(obj, CircuitSweep):
+        raise TypeError("tran expects an MNACircuit or CircuitSweep")
+    comp = compile_sweep(obj, device=device)
+    try:
+        save = comp.save_indices(save_idxs)
+        wave = comp.tran(tspan, dt, method=method, save_idxs=save, save_every=save_every,
+                         abstol=abstol, max_nl_iters=max_nl_iters)
+        r = wave.fetch()
+        wave.free()
+    finally:
+        comp.close()
+    sols = _LazyTranSolutions(comp.lc, save, r["t"], r["u"], r["count"], r["status"],
+                              r["newton_iters"], False)
+    if single:
+        return sols[0]
+    return SweepResult(obj.iterator.points(), sols)

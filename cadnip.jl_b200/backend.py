@@ -1,0 +1,376 @@
+"""ctypes binding of csrc/libcadnip_b200.so -- the stand-in for the Julia ``ccall``
+shim (INTEGRATION.md shows the Julia side).  Fails loudly: if the library is not
+built, or no sm_100 device is present, every numerical call raises; there is no
+CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .circuit import MNASpec, MODES
+from .lowering import LoweredCircuit
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_CSRC, "libcadnip_b200.so")
+_SOURCES = ["api.cu", "kernels.cu", "symbolic.cpp"]
+_HEADERS = ["kernels.h", "cb200_internal.h", os.path.join("..", "..", "include", "cadnip_b200.h")]
+
+OK, EINVAL, ENOMEM, ECUDA, ENODEVICE, ESTATE, ESINGULAR = 0, -1, -2, -3, -4, -5, -6
+LANE_OK, LANE_MAXITER, LANE_SINGULAR, LANE_NONFINITE, LANE_DTMIN = 0, 1, 2, 3, 4
+METHOD_BE, METHOD_TRAP, METHOD_GEAR2 = 0, 1, 2
+METHODS = {"be": 0, "implicit_euler": 0, "ImplicitEuler": 0, "trap": 1, "trapezoid": 1,
+           "Trapezoid": 1, "gear2": 2, "bdf2": 2}
+
+
+class CB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"cb200 error {code}: {msg}")
+        self.code = code
+
+
+class Spec(C.Structure):
+    _fields_ = [("temp", C.c_double), ("mode", C.c_int32), ("_pad", C.c_int32),
+                ("gmin", C.c_double), ("gshunt", C.c_double), ("srcFact", C.c_double),
+                ("tnom", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
+                ("vntol", C.c_double), ("iabstol", C.c_double)]
+
+
+class Desc(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("n_currents", C.c_int32), ("n_charges", C.c_int32),
+                ("n_limits", C.c_int32),
+                ("nG", C.c_int64), ("nC", C.c_int64), ("nb", C.c_int64),
+                ("G_I", C.POINTER(C.c_int64)), ("G_J", C.POINTER(C.c_int64)),
+                ("C_I", C.POINTER(C.c_int64)), ("C_J", C.POINTER(C.c_int64)),
+                ("b_I", C.POINTER(C.c_int64)),
+                ("n_devices", C.c_int32), ("n_uniform", C.c_int32),
+                ("dev_kind", C.POINTER(C.c_int32)), ("dev_flags", C.POINTER(C.c_int32)),
+                ("dev_node_ptr", C.POINTER(C.c_int32)), ("dev_nodes", C.POINTER(C.c_int32)),
+                ("dev_param_ptr", C.POINTER(C.c_int32)), ("dev_params", C.POINTER(C.c_int32)),
+                ("dev_gbase", C.POINTER(C.c_int64)), ("dev_cbase", C.POINTER(C.c_int64)),
+                ("dev_bbase", C.POINTER(C.c_int64)),
+                ("uniform", C.POINTER(C.c_double)),
+                ("limit_init_ref", C.POINTER(C.c_int32)),
+                ("n_lane_cols", C.c_int32), ("_pad", C.c_int32)]
+
+
+class DcOpts(C.Structure):
+    _fields_ = [("abstol", C.c_double), ("maxiters", C.c_int32), ("use_stepping", C.c_int32)]
+
+
+class TranOpts(C.Structure):
+    _fields_ = [("method", C.c_int32), ("adaptive", C.c_int32),
+                ("dt", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
+                ("lte_abstol", C.c_double), ("dtmin", C.c_double), ("dtmax", C.c_double),
+                ("max_nl_iters", C.c_int32), ("save_every", C.c_int32),
+                ("max_points", C.c_int32), ("init", C.c_int32),
+                ("init_abstol", C.c_double), ("init_maxiters", C.c_int32), ("_pad", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("launches", C.c_int64), ("newton_iters", C.c_int64),
+                ("steps_accepted", C.c_int64), ("steps_rejected", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+def nvcc_path() -> Optional[str]:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    for f in _SOURCES + _HEADERS:
+        fp = os.path.join(_CSRC, f)
+        if os.path.exists(fp) and os.path.getmtime(fp) > t:
+            return True
+    return False
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/ for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = nvcc_path()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build libcadnip_b200.so")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH] + _SOURCES
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, cwd=_CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout)
+    if verbose:
+        print(r.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load libcadnip_b200.so.  The library must already be built (``build_library``
+    / ``__graft_entry__.build``); a missing library is an error, never a fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CB200Error(ENODEVICE, f"{LIB_PATH} is not built (run __graft_entry__.build()); "
+                         "the product has no CPU path")
+    L = C.CDLL(LIB_PATH)
+    vp, dp = C.c_void_p, C.POINTER(C.c_double)
+    ip, lp = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    L.cb200_abi_version.restype = C.c_int
+    L.cb200_last_error.restype = C.c_char_p
+    L.cb200_last_error.argtypes = [vp]
+    L.cb200_create.restype = C.c_int
+    L.cb200_create.argtypes = [C.POINTER(Desc), C.c_int32, C.POINTER(vp)]
+    L.cb200_destroy.restype = None
+    L.cb200_destroy.argtypes = [vp]
+    L.cb200_get_pattern.restype = C.c_int
+    L.cb200_get_pattern.argtypes = [vp, lp, lp, lp, lp]
+    L.cb200_get_maps.restype = C.c_int
+    L.cb200_get_maps.argtypes = [vp, lp, lp, lp, lp]
+    L.cb200_set_lanes.restype = C.c_int
+    L.cb200_set_lanes.argtypes = [vp, C.c_int64, C.c_int32, dp]
+    L.cb200_analyze.restype = C.c_int
+    L.cb200_analyze.argtypes = [vp, C.POINTER(Spec), C.c_double]
+    L.cb200_get_pivot_order.restype = C.c_int
+    L.cb200_get_pivot_order.argtypes = [vp, lp, lp, lp]
+    L.cb200_eval.restype = C.c_int
+    L.cb200_eval.argtypes = [vp, C.POINTER(Spec), C.c_double, C.c_int32, dp, dp, dp, dp, dp]
+    L.cb200_dc.restype = C.c_int
+    L.cb200_dc.argtypes = [vp, C.POINTER(Spec), C.POINTER(DcOpts), dp, dp, ip, ip]
+    L.cb200_tran.restype = C.c_int
+    L.cb200_tran.argtypes = [vp, C.POINTER(Spec), C.c_double, C.c_double, C.POINTER(TranOpts),
+                             lp, C.c_int32, dp, C.POINTER(vp)]
+    L.cb200_wave_info.restype = C.c_int
+    L.cb200_wave_info.argtypes = [vp, lp, lp, ip, ip]
+    L.cb200_wave_fetch.restype = C.c_int
+    L.cb200_wave_fetch.argtypes = [vp, dp, dp, ip, ip, ip]
+    L.cb200_wave_final_state.restype = C.c_int
+    L.cb200_wave_final_state.argtypes = [vp, dp]
+    L.cb200_wave_free.restype = None
+    L.cb200_wave_free.argtypes = [vp]
+    L.cb200_get_stats.restype = C.c_int
+    L.cb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    if L.cb200_abi_version() != 1:
+        raise CB200Error(EINVAL, "libcadnip_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "cb200_abi_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_pattern",
+    "cb200_get_maps", "cb200_set_lanes", "cb200_analyze", "cb200_get_pivot_order", "cb200_eval",
+    "cb200_dc", "cb200_tran", "cb200_wave_info", "cb200_wave_fetch", "cb200_wave_final_state",
+    "cb200_wave_free", "cb200_get_stats"]
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _lp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def make_spec(spec: MNASpec, mode: Optional[str] = None) -> Spec:
+    m = MODES[mode or spec.mode]
+    return Spec(spec.temp, m, 0, spec.gmin, spec.gshunt, spec.srcFact, spec.tnom, spec.abstol,
+                spec.reltol, spec.vntol, spec.iabstol)
+
+
+def make_desc(lc: LoweredCircuit):
+    """Returns (Desc, keepalive list)."""
+    keep = []
+
+    def arr(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a
+
+    G_I, G_J = arr(lc.G_I, np.int64), arr(lc.G_J, np.int64)
+    C_I, C_J = arr(lc.C_I, np.int64), arr(lc.C_J, np.int64)
+    b_I = arr(lc.b_I, np.int64)
+    d = Desc(lc.n_nodes, lc.n_currents, lc.n_charges, lc.n_limits,
+             len(G_I), len(C_I), len(b_I),
+             _lp(G_I), _lp(G_J), _lp(C_I), _lp(C_J), _lp(b_I),
+             len(lc.dev_kind), len(lc.uniform),
+             _ip(arr(lc.dev_kind, np.int32)), _ip(arr(lc.dev_flags, np.int32)),
+             _ip(arr(lc.dev_node_ptr, np.int32)), _ip(arr(lc.dev_nodes, np.int32)),
+             _ip(arr(lc.dev_param_ptr, np.int32)), _ip(arr(lc.dev_params, np.int32)),
+             _lp(arr(lc.dev_gbase, np.int64)), _lp(arr(lc.dev_cbase, np.int64)),
+             _lp(arr(lc.dev_bbase, np.int64)),
+             _dp(arr(lc.uniform, np.float64)), _ip(arr(lc.limit_init_ref, np.int32)),
+             lc.n_lane_cols, 0)
+    return d, keep
+
+
+class Wave:
+    """Owns a cb200_wave: the waveforms of a transient sweep, resident in HBM."""
+
+    def __init__(self, handle: "Handle", ptr):
+        self._h, self._p = handle, ptr
+        T, P, ns, ad = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+        handle._check(lib().cb200_wave_info(ptr, C.byref(T), C.byref(P), C.byref(ns), C.byref(ad)))
+        self.T, self.P, self.n_save, self.adaptive = T.value, P.value, ns.value, bool(ad.value)
+
+    def fetch(self, out_u: Optional[np.ndarray] = None):
+        """D2H copy.  Returns dict(t, u[save][T][P], count, status, newton_iters)."""
+        L = lib()
+        if out_u is None:
+            out_u = np.empty((self.n_save, self.T, self.P), dtype=np.float64)
+        t = np.empty((self.T, self.P) if self.adaptive else (self.T,), dtype=np.float64)
+        count = np.empty(self.P, np.int32)
+        status = np.empty(self.P, np.int32)
+        iters = np.empty(self.P, np.int32)
+        self._h._check(L.cb200_wave_fetch(self._p, _dp(t), _dp(out_u), _ip(count), _ip(status),
+                                          _ip(iters)))
+        return dict(t=t, u=out_u, count=count, status=status, newton_iters=iters)
+
+    def final_state(self) -> np.ndarray:
+        x = np.empty((self._h.n, self.P), dtype=np.float64)
+        self._h._check(lib().cb200_wave_final_state(self._p, _dp(x)))
+        return x
+
+    def free(self):
+        if self._p:
+            lib().cb200_wave_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Handle:
+    """Owns a cb200_handle (one per GPU)."""
+
+    def __init__(self, lc: LoweredCircuit, device: int = 0):
+        L = lib()
+        self.lc = lc
+        self.n = lc.n
+        desc, keep = make_desc(lc)
+        ptr = C.c_void_p()
+        rc = L.cb200_create(C.byref(desc), device, C.byref(ptr))
+        if rc != OK:
+            raise CB200Error(rc, (L.cb200_last_error(None) or b"").decode())
+        self._p = ptr
+        self.P = 0
+
+    def _check(self, rc: int):
+        if rc != OK:
+            raise CB200Error(rc, (lib().cb200_last_error(self._p) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().cb200_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- structure ---------------------------------------------------------- #
+    def pattern(self):
+        L = lib()
+        n, nnz = C.c_int64(), C.c_int64()
+        self._check(L.cb200_get_pattern(self._p, C.byref(n), C.byref(nnz), None, None))
+        colptr = np.zeros(n.value + 1, np.int64)
+        rowval = np.zeros(nnz.value, np.int64)
+        self._check(L.cb200_get_pattern(self._p, None, None, _lp(colptr), _lp(rowval)))
+        return colptr, rowval
+
+    def maps(self):
+        lc = self.lc
+        g = np.zeros(len(lc.G_I), np.int64); c = np.zeros(len(lc.C_I), np.int64)
+        b = np.zeros(len(lc.b_I), np.int64); d = np.zeros(lc.n_nodes, np.int64)
+        self._check(lib().cb200_get_maps(self._p, _lp(g), _lp(c), _lp(b), _lp(d)))
+        return dict(G_coo_to_idx=g, C_coo_to_idx=c, b_resolved=b, G_diag_idx=d)
+
+    def set_lanes(self, soa: np.ndarray, P: int):
+        soa = np.ascontiguousarray(soa, dtype=np.float64)
+        if soa.shape != (self.lc.n_lane_cols, P):
+            raise ValueError(f"lane SoA has shape {soa.shape}, expected {(self.lc.n_lane_cols, P)}")
+        self._check(lib().cb200_set_lanes(self._p, P, self.lc.n_lane_cols, _dp(soa) if soa.size else None))
+        self.P = P
+
+    def analyze(self, spec: MNASpec, gamma: float, mode: Optional[str] = None):
+        s = make_spec(spec, mode)
+        self._check(lib().cb200_analyze(self._p, C.byref(s), float(gamma)))
+
+    def pivot_order(self):
+        r = np.zeros(self.n, np.int64); c = np.zeros(self.n, np.int64); nlu = C.c_int64()
+        self._check(lib().cb200_get_pivot_order(self._p, _lp(r), _lp(c), C.byref(nlu)))
+        return r, c, nlu.value
+
+    # -- analyses ----------------------------------------------------------- #
+    def eval(self, spec: MNASpec, x: Optional[np.ndarray] = None, t: float = 0.0,
+             initjct: bool = False, mode: Optional[str] = None):
+        """fast_rebuild! for every lane: returns G_nz[nnz][P], C_nz[nnz][P], b[n][P], limit_w."""
+        colptr, rowval = self.pattern()
+        nnz, P, n = len(rowval), self.P, self.n
+        G = np.empty((nnz, P)); Cm = np.empty((nnz, P)); b = np.empty((n, P))
+        lw = np.empty((max(self.lc.n_limits, 1), P))
+        xx = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+        if xx is not None and xx.shape != (n, P):
+            raise ValueError(f"x has shape {xx.shape}, expected {(n, P)}")
+        s = make_spec(spec, mode)
+        self._check(lib().cb200_eval(self._p, C.byref(s), float(t), int(initjct), _dp(xx), _dp(G),
+                                     _dp(Cm), _dp(b), _dp(lw)))
+        return G, Cm, b, lw[:self.lc.n_limits]
+
+    def dc(self, spec: MNASpec, u0: Optional[np.ndarray] = None, abstol: float = 1e-10,
+           maxiters: int = 100, use_stepping: bool = True, mode: Optional[str] = "dcop"):
+        n, P = self.n, self.P
+        x = np.empty((n, P)); st = np.empty(P, np.int32); it = np.empty(P, np.int32)
+        uu = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
+        s = make_spec(spec, mode)
+        o = DcOpts(abstol, maxiters, int(use_stepping))
+        self._check(lib().cb200_dc(self._p, C.byref(s), C.byref(o), _dp(uu), _dp(x), _ip(st), _ip(it)))
+        return x, st, it
+
+    def tran(self, spec: MNASpec, t0: float, t1: float, opts: TranOpts, save_idx: Sequence[int],
+             u0: Optional[np.ndarray] = None) -> Wave:
+        save = np.ascontiguousarray(save_idx, dtype=np.int64)
+        uu = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
+        s = make_spec(spec, "tran")
+        ptr = C.c_void_p()
+        self._check(lib().cb200_tran(self._p, C.byref(s), float(t0), float(t1), C.byref(opts),
+                                     _lp(save), len(save), _dp(uu), C.byref(ptr)))
+        return Wave(self, ptr)
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(lib().cb200_get_stats(self._p, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+def make_tran_opts(method="be", adaptive=False, dt=0.0, abstol=1e-10, reltol=1e-8, lte_abstol=1e-10,
+                   dtmin=0.0, dtmax=0.0, max_nl_iters=10, save_every=1, max_points=0, init=0,
+                   init_abstol=1e-9, init_maxiters=500) -> TranOpts:
+    m = METHODS[method] if isinstance(method, str) else int(method)
+    return TranOpts(m, int(adaptive), dt, abstol, reltol, lte_abstol, dtmin, dtmax, max_nl_iters,
+                    save_every, max_points, init, init_abstol, init_maxiters, 0)

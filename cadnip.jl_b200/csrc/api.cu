@@ -1,0 +1,932 @@
+// api.cu -- C ABI of libcadnip_b200.so (include/cadnip_b200.h).
+//
+// Host side of the B200 path: owns the device copies of the circuit program, the
+// lane-parameter SoA and the lane state, runs the host symbolic phase, launches
+// the kernels on the handle's own stream and times them with CUDA events.  There
+// is no CPU fallback: every numerical entry point fails with CB200_ENODEVICE when
+// no CUDA device is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "cb200_internal.h"
+#include "kernels.h"
+
+using namespace cb200;
+
+static thread_local std::string g_last_error;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T> &v, cudaStream_t st)
+    {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct DevLu {
+    LuSchedule host;
+    DevBuf<int> rowperm, colperm, diag_slot, Lptr, L_slot, L_row, Uptr, U_slot, U_col, tgt_ptr, tgt,
+        jmap, fill_slots;
+    LuProgram prog{};
+};
+
+}  // namespace
+
+struct cb200_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    Structure st;
+    // host copies of the description
+    std::vector<int> dev_kind, dev_flags, dev_node_ptr, dev_nodes, dev_param_ptr, dev_params;
+    std::vector<int> dev_gbase, dev_cbase, dev_bbase, dyn_list, limit_init_ref;
+    std::vector<double> uniform;
+    int n_lane_cols = 0;
+    // lanes
+    int64_t P = 0;
+    std::vector<double> lanes_host;
+    // device copies
+    DevBuf<int> d_dev_kind, d_dev_flags, d_dev_node_ptr, d_dev_nodes, d_dev_param_ptr, d_dev_params;
+    DevBuf<int> d_dev_gbase, d_dev_cbase, d_dev_bbase, d_dyn_list, d_limit_init_ref;
+    DevBuf<int> d_gseg_ptr, d_gseg_idx, d_cseg_ptr, d_cseg_idx, d_bseg_ptr, d_bseg_idx;
+    DevBuf<int> d_colptr, d_rowval;
+    DevBuf<unsigned char> d_node_diag;
+    DevBuf<double> d_uniform, d_lanes;
+    DevBuf<double> d_state;        // [n][P]
+    DevBuf<double> d_ws_global;    // [n_slots][P] (eval path / shared-memory overflow)
+    DevBuf<int> d_status, d_iters;
+    DevBuf<unsigned char> d_conv, d_active;
+    DevBuf<double> d_gshunt_lane, d_srcfact_lane;
+    Program prog{};
+    DevLu lu[2];                   // 0: DC (gamma = 0), 1: transient
+    size_t smem_limit = 0;
+    int block_pref = 64;
+    cb200_stats stats{};
+};
+
+struct cb200_wave {
+    cb200_handle *h = nullptr;
+    int64_t T = 0, P = 0;
+    int n_save = 0, adaptive = 0, n = 0;
+    double t0 = 0, dt = 0;
+    int save_every = 1;
+    int64_t nsteps = 0;
+    DevBuf<double> d_out, d_t, d_final;
+    DevBuf<int> d_count, d_status, d_iters;
+};
+
+#define CUDA_TRY(h, expr)                                                              \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);             \
+            g_last_error = (h)->err;                                                   \
+            return CB200_ECUDA;                                                        \
+        }                                                                              \
+    } while (0)
+
+static int fail(cb200_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+static std::vector<int> to_int(const int32_t *p, size_t n) { return std::vector<int>(p, p + n); }
+static std::vector<int> to_int64(const int64_t *p, size_t n)
+{
+    std::vector<int> v(n);
+    for (size_t i = 0; i < n; i++) v[i] = (int)p[i];
+    return v;
+}
+
+static SpecArgs spec_args(const cb200_spec *s)
+{
+    SpecArgs a;
+    a.mode = s->mode; a.temp = s->temp; a.gmin = s->gmin; a.gshunt = s->gshunt; a.srcFact = s->srcFact;
+    return a;
+}
+
+// workspace slot layout of one lane
+static void layout_workspace(cb200_handle *h)
+{
+    Program &p = h->prog;
+    int o = 0;
+    const int n = h->st.n;
+    p.off_u = o; o += n;
+    p.off_un = o; o += n;
+    p.off_dterm = o; o += n;
+    p.off_F = o; o += n;
+    p.off_wv = o; o += n;
+    p.off_SG = o; o += (int)h->st.nG;
+    p.off_SC = o; o += (int)h->st.nC;
+    p.off_SB = o; o += (int)h->st.nb;
+    p.off_limw = o; o += h->st.n_limits;
+    p.off_lp = o; o += h->n_lane_cols;
+    p.off_h1 = o; o += n;
+    p.off_h2 = o; o += n;
+    p.off_LU = o;                       // LU last: its size depends on the schedule
+    int64_t nlu = std::max(h->lu[0].host.nlu, h->lu[1].host.nlu);
+    if (nlu == 0) nlu = h->st.nnz;
+    o += (int)nlu;
+    p.n_slots = o;
+}
+
+static bool is_dynamic_kind(int kind)
+{
+    switch (kind) {
+    case CB200_DEV_VSOURCE: case CB200_DEV_ISOURCE: case CB200_DEV_DIODE:
+    case CB200_DEV_DIODECAP: case CB200_DEV_SIMPLEMOS: return true;
+    default: return false;
+    }
+}
+
+extern "C" int cb200_abi_version(void) { return CB200_ABI_VERSION; }
+
+extern "C" const char *cb200_last_error(const cb200_handle *h)
+{
+    return h ? h->err.c_str() : g_last_error.c_str();
+}
+
+extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **out)
+{
+    if (!d || !out) return fail(nullptr, CB200_EINVAL, "cb200_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+        return fail(nullptr, CB200_ENODEVICE,
+                    std::string("cb200_create: no usable CUDA device (there is no CPU fallback): ") +
+                        (ce != cudaSuccess ? cudaGetErrorString(ce) : "device ordinal out of range"));
+    cb200_handle *h = new cb200_handle();
+    h->device = device;
+    ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) { delete h; return fail(nullptr, CB200_ECUDA, cudaGetErrorString(ce)); }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10) {
+        std::string m = "cb200_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                        "; this library is built for sm_100a only";
+        delete h;
+        return fail(nullptr, CB200_ENODEVICE, m);
+    }
+    h->smem_limit = prop.sharedMemPerBlockOptin;
+    std::string e = build_structure(*d, h->st);
+    if (!e.empty()) { delete h; return fail(nullptr, CB200_EINVAL, e); }
+
+    const int nd = d->n_devices;
+    for (int i = 0; i < nd; i++)
+        if (d->dev_kind[i] < 1 || d->dev_kind[i] > CB200_DEV_KIND_MAX) {
+            delete h;
+            return fail(nullptr, CB200_EINVAL, "cb200_create: unknown device kind");
+        }
+    h->dev_kind = to_int(d->dev_kind, nd);
+    h->dev_flags = to_int(d->dev_flags, nd);
+    h->dev_node_ptr = to_int(d->dev_node_ptr, nd + 1);
+    h->dev_nodes = to_int(d->dev_nodes, nd ? d->dev_node_ptr[nd] : 0);
+    h->dev_param_ptr = to_int(d->dev_param_ptr, nd + 1);
+    h->dev_params = to_int(d->dev_params, nd ? d->dev_param_ptr[nd] : 0);
+    h->dev_gbase = to_int64(d->dev_gbase, nd + 1);
+    h->dev_cbase = to_int64(d->dev_cbase, nd + 1);
+    h->dev_bbase = to_int64(d->dev_bbase, nd + 1);
+    h->uniform.assign(d->uniform, d->uniform + d->n_uniform);
+    h->limit_init_ref = to_int(d->limit_init_ref, d->n_limits);
+    h->n_lane_cols = d->n_lane_cols;
+    for (int r : h->dev_params)
+        if (r >= d->n_uniform || (r < 0 && ~r >= d->n_lane_cols)) {
+            delete h;
+            return fail(nullptr, CB200_EINVAL, "cb200_create: parameter reference out of range");
+        }
+    for (int v : h->dev_nodes)
+        if (v < 0 || v > h->st.n) {
+            delete h;
+            return fail(nullptr, CB200_EINVAL, "cb200_create: device node index out of range");
+        }
+    for (int i = 0; i < nd; i++)
+        if (is_dynamic_kind(h->dev_kind[i])) h->dyn_list.push_back(i);
+
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, CB200_ECUDA, "cb200_create: stream/event creation failed");
+    }
+    cudaStream_t s = h->stream;
+    const Structure &st = h->st;
+    std::vector<unsigned char> nd8(st.nz_is_node_diag.begin(), st.nz_is_node_diag.end());
+    bool ok = h->d_dev_kind.upload(h->dev_kind, s) == cudaSuccess &&
+              h->d_dev_flags.upload(h->dev_flags, s) == cudaSuccess &&
+              h->d_dev_node_ptr.upload(h->dev_node_ptr, s) == cudaSuccess &&
+              h->d_dev_nodes.upload(h->dev_nodes, s) == cudaSuccess &&
+              h->d_dev_param_ptr.upload(h->dev_param_ptr, s) == cudaSuccess &&
+              h->d_dev_params.upload(h->dev_params, s) == cudaSuccess &&
+              h->d_dev_gbase.upload(h->dev_gbase, s) == cudaSuccess &&
+              h->d_dev_cbase.upload(h->dev_cbase, s) == cudaSuccess &&
+              h->d_dev_bbase.upload(h->dev_bbase, s) == cudaSuccess &&
+              h->d_dyn_list.upload(h->dyn_list, s) == cudaSuccess &&
+              h->d_limit_init_ref.upload(h->limit_init_ref, s) == cudaSuccess &&
+              h->d_uniform.upload(h->uniform, s) == cudaSuccess &&
+              h->d_gseg_ptr.upload(st.gseg_ptr, s) == cudaSuccess &&
+              h->d_gseg_idx.upload(st.gseg_idx, s) == cudaSuccess &&
+              h->d_cseg_ptr.upload(st.cseg_ptr, s) == cudaSuccess &&
+              h->d_cseg_idx.upload(st.cseg_idx, s) == cudaSuccess &&
+              h->d_bseg_ptr.upload(st.bseg_ptr, s) == cudaSuccess &&
+              h->d_bseg_idx.upload(st.bseg_idx, s) == cudaSuccess &&
+              h->d_colptr.upload(st.colptr, s) == cudaSuccess &&
+              h->d_rowval.upload(st.rowval, s) == cudaSuccess &&
+              h->d_node_diag.upload(nd8, s) == cudaSuccess;
+    if (!ok || cudaStreamSynchronize(s) != cudaSuccess) {
+        std::string m = std::string("cb200_create: upload failed: ") + cudaGetErrorString(cudaGetLastError());
+        cb200_destroy(h);
+        return fail(nullptr, CB200_ECUDA, m);
+    }
+    Program &p = h->prog;
+    p.n = st.n; p.n_nodes = st.n_nodes; p.n_limits = st.n_limits; p.nnz = (int)st.nnz;
+    p.nG = (int)st.nG; p.nC = (int)st.nC; p.nb = (int)st.nb; p.n_dev = nd;
+    p.n_dyn = (int)h->dyn_list.size(); p.n_lane_cols = h->n_lane_cols; p.P = 0;
+    p.dev_kind = h->d_dev_kind.p; p.dev_flags = h->d_dev_flags.p;
+    p.dev_node_ptr = h->d_dev_node_ptr.p; p.dev_nodes = h->d_dev_nodes.p;
+    p.dev_param_ptr = h->d_dev_param_ptr.p; p.dev_params = h->d_dev_params.p;
+    p.dev_gbase = h->d_dev_gbase.p; p.dev_cbase = h->d_dev_cbase.p; p.dev_bbase = h->d_dev_bbase.p;
+    p.dyn_list = h->d_dyn_list.p; p.uniform = h->d_uniform.p; p.lanes = nullptr;
+    p.limit_init_ref = h->d_limit_init_ref.p;
+    p.gseg_ptr = h->d_gseg_ptr.p; p.gseg_idx = h->d_gseg_idx.p;
+    p.cseg_ptr = h->d_cseg_ptr.p; p.cseg_idx = h->d_cseg_idx.p;
+    p.bseg_ptr = h->d_bseg_ptr.p; p.bseg_idx = h->d_bseg_idx.p;
+    p.colptr = h->d_colptr.p; p.rowval = h->d_rowval.p; p.nz_is_node_diag = h->d_node_diag.p;
+    layout_workspace(h);
+    *out = h;
+    return CB200_OK;
+}
+
+extern "C" void cb200_destroy(cb200_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int cb200_get_pattern(const cb200_handle *h, int64_t *n, int64_t *nnz, int64_t *colptr,
+                                 int64_t *rowval)
+{
+    if (!h) return CB200_EINVAL;
+    if (n) *n = h->st.n;
+    if (nnz) *nnz = h->st.nnz;
+    if (colptr) for (int j = 0; j <= h->st.n; j++) colptr[j] = h->st.colptr[j] + 1;
+    if (rowval) for (int64_t q = 0; q < h->st.nnz; q++) rowval[q] = h->st.rowval[q] + 1;
+    return CB200_OK;
+}
+
+extern "C" int cb200_get_maps(const cb200_handle *h, int64_t *G_map, int64_t *C_map, int64_t *b_rows,
+                              int64_t *G_diag)
+{
+    if (!h) return CB200_EINVAL;
+    if (G_map) for (int64_t k = 0; k < h->st.nG; k++) G_map[k] = h->st.G_map[k] + 1;
+    if (C_map) for (int64_t k = 0; k < h->st.nC; k++) C_map[k] = h->st.C_map[k] + 1;
+    if (b_rows) for (int64_t k = 0; k < h->st.nb; k++) b_rows[k] = h->st.b_rows[k] + 1;
+    if (G_diag) for (int i = 0; i < h->st.n_nodes; i++) G_diag[i] = h->st.diag_nz[i] + 1;   // 0 = absent
+    return CB200_OK;
+}
+
+static int ensure_lane_buffers(cb200_handle *h)
+{
+    const int64_t P = h->P;
+    const int n = h->st.n;
+    if (h->d_state.n != (size_t)n * P) CUDA_TRY(h, h->d_state.alloc((size_t)n * P));
+    if (h->d_status.n != (size_t)P) {
+        CUDA_TRY(h, h->d_status.alloc(P));
+        CUDA_TRY(h, h->d_iters.alloc(P));
+        CUDA_TRY(h, h->d_conv.alloc(P));
+        CUDA_TRY(h, h->d_active.alloc(P));
+        CUDA_TRY(h, h->d_gshunt_lane.alloc(P));
+        CUDA_TRY(h, h->d_srcfact_lane.alloc(P));
+    }
+    return CB200_OK;
+}
+
+static int ensure_global_ws(cb200_handle *h)
+{
+    const size_t need = (size_t)h->prog.n_slots * h->P;
+    if (h->d_ws_global.n < need) CUDA_TRY(h, h->d_ws_global.alloc(need));
+    return CB200_OK;
+}
+
+extern "C" int cb200_set_lanes(cb200_handle *h, int64_t P, int32_t n_cols, const double *soa)
+{
+    if (!h || P <= 0) return fail(h, CB200_EINVAL, "cb200_set_lanes: bad arguments");
+    if (n_cols != h->n_lane_cols) return fail(h, CB200_EINVAL, "cb200_set_lanes: column count differs from the description");
+    if (n_cols > 0 && !soa) return fail(h, CB200_EINVAL, "cb200_set_lanes: null SoA");
+    cudaSetDevice(h->device);
+    h->P = P;
+    h->prog.P = P;
+    h->lanes_host.assign(soa, soa + (size_t)n_cols * P);
+    if (n_cols > 0) {
+        if (h->d_lanes.n != (size_t)n_cols * P) CUDA_TRY(h, h->d_lanes.alloc((size_t)n_cols * P));
+        CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_lanes.p, soa, (size_t)n_cols * P * sizeof(double),
+                                    cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        h->stats.h2d_ms = ms;
+        h->stats.h2d_bytes = (int64_t)n_cols * P * sizeof(double);
+    }
+    h->prog.lanes = h->d_lanes.p;
+    return ensure_lane_buffers(h);
+}
+
+static int upload_lu(cb200_handle *h, DevLu &L)
+{
+    cudaStream_t s = h->stream;
+    const LuSchedule &S = L.host;
+    CUDA_TRY(h, L.rowperm.upload(S.rowperm, s)); CUDA_TRY(h, L.colperm.upload(S.colperm, s));
+    CUDA_TRY(h, L.diag_slot.upload(S.diag_slot, s));
+    CUDA_TRY(h, L.Lptr.upload(S.Lptr, s)); CUDA_TRY(h, L.L_slot.upload(S.L_slot, s));
+    CUDA_TRY(h, L.L_row.upload(S.L_row, s));
+    CUDA_TRY(h, L.Uptr.upload(S.Uptr, s)); CUDA_TRY(h, L.U_slot.upload(S.U_slot, s));
+    CUDA_TRY(h, L.U_col.upload(S.U_col, s));
+    CUDA_TRY(h, L.tgt_ptr.upload(S.tgt_ptr, s)); CUDA_TRY(h, L.tgt.upload(S.tgt, s));
+    CUDA_TRY(h, L.jmap.upload(S.jmap, s)); CUDA_TRY(h, L.fill_slots.upload(S.fill_slots, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    LuProgram &q = L.prog;
+    q.n = S.n; q.nlu = (int)S.nlu; q.n_fill = (int)S.fill_slots.size();
+    q.rowperm = L.rowperm.p; q.colperm = L.colperm.p; q.diag_slot = L.diag_slot.p;
+    q.Lptr = L.Lptr.p; q.L_slot = L.L_slot.p; q.L_row = L.L_row.p;
+    q.Uptr = L.Uptr.p; q.U_slot = L.U_slot.p; q.U_col = L.U_col.p;
+    q.tgt_ptr = L.tgt_ptr.p; q.tgt = L.tgt.p; q.jmap = L.jmap.p; q.fill_slots = L.fill_slots.p;
+    return CB200_OK;
+}
+
+// Evaluate G, C at state x for a compact set of sample lanes; returns |G + gamma*C|
+// maxima per pattern entry.  Runs the K1/K2 evaluation kernels on a temporary
+// program whose lane SoA holds only the samples.
+static int probe_magnitudes(cb200_handle *h, const cb200_spec *spec, double gamma,
+                            std::vector<double> &absJ)
+{
+    const int64_t P = h->P;
+    const int n = h->st.n;
+    const int64_t nnz = h->st.nnz;
+    const int ns = (int)std::min<int64_t>(P, 16);
+    std::vector<int64_t> sample(ns);
+    for (int i = 0; i < ns; i++) sample[i] = ns == 1 ? 0 : (int64_t)((double)i * (double)(P - 1) / (double)(ns - 1));
+    std::vector<double> soa((size_t)h->n_lane_cols * ns);
+    for (int c = 0; c < h->n_lane_cols; c++)
+        for (int i = 0; i < ns; i++) soa[(size_t)c * ns + i] = h->lanes_host[(size_t)c * P + sample[i]];
+    DevBuf<double> d_soa, d_ws, d_G, d_C;
+    CUDA_TRY(h, d_soa.upload(soa, h->stream));
+    Program p = h->prog;
+    p.P = ns; p.lanes = d_soa.p;
+    CUDA_TRY(h, d_ws.alloc((size_t)p.n_slots * ns));
+    CUDA_TRY(h, d_G.alloc((size_t)nnz * ns));
+    CUDA_TRY(h, d_C.alloc((size_t)nnz * ns));
+    absJ.assign(nnz, 0.0);
+    std::vector<double> hG((size_t)nnz * ns), hC((size_t)nnz * ns), ws_host((size_t)p.n_slots * ns, 0.0);
+    // probe states: ZERO_VECTOR with the PCNR seeds (initjct), ZERO_VECTOR, and two
+    // deterministic pseudo-random states in [-1, 1] (cf. solve.jl:992-1015).
+    uint64_t rng = 0xDEADBEEFULL;
+    auto rnd = [&rng]() {
+        rng ^= rng >> 12; rng ^= rng << 25; rng ^= rng >> 27;
+        return (double)((rng * 2685821657736338717ULL) >> 11) / 9007199254740992.0;
+    };
+    for (int probe = 0; probe < 4; probe++) {
+        std::fill(ws_host.begin(), ws_host.end(), 0.0);
+        if (probe >= 2)
+            for (int i = 0; i < n; i++)
+                for (int l = 0; l < ns; l++) ws_host[(size_t)(p.off_u + i) * ns + l] = (rnd() - 0.5) * 2.0;
+        CUDA_TRY(h, cudaMemcpyAsync(d_ws.p, ws_host.data(), ws_host.size() * sizeof(double),
+                                    cudaMemcpyHostToDevice, h->stream));
+        EvalArgs a{};
+        a.t = 0.0; a.initjct = (probe == 0); a.ws = d_ws.p; a.G_nz = d_G.p; a.C_nz = d_C.p;
+        SpecArgs sa = spec_args(spec);
+        CUDA_TRY(h, launch_eval(p, sa, a, h->stream, &h->stats.launches));
+        CUDA_TRY(h, cudaMemcpyAsync(hG.data(), d_G.p, hG.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(hC.data(), d_C.p, hC.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (int64_t q = 0; q < nnz; q++)
+            for (int l = 0; l < ns; l++) {
+                double v = std::fabs(hG[(size_t)q * ns + l] + gamma * hC[(size_t)q * ns + l]);
+                if (std::isfinite(v) && v > absJ[q]) absJ[q] = v;
+            }
+    }
+    return CB200_OK;
+}
+
+extern "C" int cb200_analyze(cb200_handle *h, const cb200_spec *spec, double gamma)
+{
+    if (!h || !spec) return fail(h, CB200_EINVAL, "cb200_analyze: null argument");
+    if (h->P <= 0) return fail(h, CB200_ESTATE, "cb200_analyze: call cb200_set_lanes first");
+    cudaSetDevice(h->device);
+    const int which = gamma == 0.0 ? 0 : 1;
+    std::vector<double> absJ;
+    int rc = probe_magnitudes(h, spec, gamma, absJ);
+    if (rc != CB200_OK) return rc;
+    DevLu &L = h->lu[which];
+    std::string e = analyze_lu(h->st, absJ, 1e-3, L.host);
+    if (!e.empty()) return fail(h, CB200_ESINGULAR, e);
+    L.host.gamma = gamma;
+    rc = upload_lu(h, L);
+    if (rc != CB200_OK) return rc;
+    layout_workspace(h);
+    return CB200_OK;
+}
+
+static int ensure_lu(cb200_handle *h, const cb200_spec *spec, int which, double gamma)
+{
+    if (h->lu[which].host.valid && (which == 0 || h->lu[which].host.gamma == gamma)) return CB200_OK;
+    return cb200_analyze(h, spec, gamma);
+}
+
+extern "C" int cb200_get_pivot_order(const cb200_handle *h, int64_t *rowperm, int64_t *colperm,
+                                     int64_t *nnz_lu)
+{
+    if (!h) return CB200_EINVAL;
+    const LuSchedule &S = h->lu[1].host.valid ? h->lu[1].host : h->lu[0].host;
+    if (!S.valid) return CB200_ESTATE;
+    for (int k = 0; k < S.n; k++) {
+        if (rowperm) rowperm[k] = S.rowperm[k] + 1;
+        if (colperm) colperm[k] = S.colperm[k] + 1;
+    }
+    if (nnz_lu) *nnz_lu = S.nlu;
+    return CB200_OK;
+}
+
+extern "C" int cb200_eval(cb200_handle *h, const cb200_spec *spec, double t, int32_t initjct,
+                          const double *x, double *G_nz, double *C_nz, double *b, double *limw)
+{
+    if (!h || !spec) return fail(h, CB200_EINVAL, "cb200_eval: null argument");
+    if (h->P <= 0) return fail(h, CB200_ESTATE, "cb200_eval: call cb200_set_lanes first");
+    cudaSetDevice(h->device);
+    const int64_t P = h->P;
+    const int n = h->st.n;
+    const int64_t nnz = h->st.nnz;
+    h->stats = cb200_stats{};
+    int rc = ensure_global_ws(h);
+    if (rc != CB200_OK) return rc;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_ws_global.p, 0, (size_t)h->prog.n_slots * P * sizeof(double), s));
+    if (x) CUDA_TRY(h, cudaMemcpyAsync(h->d_ws_global.p + (size_t)h->prog.off_u * P, x,
+                                       (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, s));
+    DevBuf<double> dG, dC, db, dl;
+    CUDA_TRY(h, dG.alloc((size_t)nnz * P)); CUDA_TRY(h, dC.alloc((size_t)nnz * P));
+    CUDA_TRY(h, db.alloc((size_t)n * P)); CUDA_TRY(h, dl.alloc((size_t)std::max(1, h->st.n_limits) * P));
+    EvalArgs a{};
+    a.t = t; a.initjct = initjct; a.ws = h->d_ws_global.p;
+    a.G_nz = dG.p; a.C_nz = dC.p; a.b = db.p; a.limw = dl.p;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    CUDA_TRY(h, launch_eval(h->prog, spec_args(spec), a, s, &h->stats.launches));
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    if (G_nz) CUDA_TRY(h, cudaMemcpyAsync(G_nz, dG.p, (size_t)nnz * P * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (C_nz) CUDA_TRY(h, cudaMemcpyAsync(C_nz, dC.p, (size_t)nnz * P * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (b) CUDA_TRY(h, cudaMemcpyAsync(b, db.p, (size_t)n * P * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (limw && h->st.n_limits > 0)
+        CUDA_TRY(h, cudaMemcpyAsync(limw, dl.p, (size_t)h->st.n_limits * P * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.kernel_ms = ms;
+    return CB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// DC on the device: _dc_solve_with_fallbacks (solve.jl:871-929) over all lanes.
+// State stays in h->d_state; per-lane tier bookkeeping on the host.
+// ---------------------------------------------------------------------------
+struct DcRun {
+    cb200_handle *h;
+    SpecArgs sa;
+    double t;
+    double abstol;
+    int maxiters;
+    float kernel_ms = 0;
+};
+
+static int dc_launch(DcRun &r, int algorithm, const unsigned char *d_active, const double *d_gshunt,
+                     const double *d_srcfact)
+{
+    cb200_handle *h = r.h;
+    DcArgs a{};
+    a.algorithm = algorithm; a.abstol = r.abstol; a.maxiters = r.maxiters; a.t = r.t;
+    a.u = h->d_state.p; a.active = d_active; a.gshunt_lane = d_gshunt; a.srcfact_lane = d_srcfact;
+    a.status = h->d_status.p; a.iters = h->d_iters.p; a.converged = h->d_conv.p;
+    a.ws_global = nullptr;
+    if (choose_block(h->prog.n_slots, h->smem_limit, h->block_pref) == 0) {
+        int rc = ensure_global_ws(h);
+        if (rc != CB200_OK) return rc;
+        a.ws_global = h->d_ws_global.p;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    CUDA_TRY(h, launch_dc(h->prog, h->lu[0].prog, r.sa, a, h->block_pref, h->smem_limit, h->stream,
+                          &h->stats.launches));
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    r.kernel_ms += ms;
+    return CB200_OK;
+}
+
+// Runs the fallback chain on the device state.  d_state must hold u0 for every lane.
+static int dc_chain(cb200_handle *h, const cb200_spec *spec, double t, double abstol, int maxiters,
+                    int use_stepping, std::vector<unsigned char> &conv_out,
+                    std::vector<int> &status_out)
+{
+    const int64_t P = h->P;
+    const int n = h->st.n;
+    int rc = ensure_lu(h, spec, 0, 0.0);
+    if (rc != CB200_OK) return rc;
+    DcRun r{h, spec_args(spec), t, abstol, maxiters};
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_iters.p, 0, P * sizeof(int), s));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_conv.p, 0, P, s));
+    std::vector<unsigned char> conv(P, 0), active(P, 1);
+    std::vector<int> status(P, CB200_LANE_OK);
+    std::vector<double> u0;
+
+    auto fetch = [&]() -> int {
+        CUDA_TRY(h, cudaMemcpyAsync(conv.data(), h->d_conv.p, P, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaMemcpyAsync(status.data(), h->d_status.p, P * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        return CB200_OK;
+    };
+    auto all_conv = [&]() { return std::all_of(conv.begin(), conv.end(), [](unsigned char c) { return c != 0; }); };
+
+    const bool has_limits = h->st.n_limits > 0;
+    if (has_limits) {
+        // tier 0 needs u0 again if it fails: keep a device-side copy only when needed
+        u0.resize((size_t)n * P);
+        CUDA_TRY(h, cudaMemcpyAsync(u0.data(), h->d_state.p, u0.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        rc = dc_launch(r, 0, nullptr, nullptr, nullptr);                  // tier 0: PCNR
+        if (rc != CB200_OK) return rc;
+        if ((rc = fetch()) != CB200_OK) return rc;
+    }
+    if (!has_limits || !all_conv()) {
+        // tier 1: plain Newton from u0 on the lanes PCNR left unconverged
+        if (has_limits) {
+            std::vector<double> cur((size_t)n * P);
+            CUDA_TRY(h, cudaMemcpyAsync(cur.data(), h->d_state.p, cur.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(h, cudaStreamSynchronize(s));
+            for (int64_t l = 0; l < P; l++) {
+                active[l] = conv[l] ? 0 : 1;
+                if (active[l]) for (int i = 0; i < n; i++) cur[(size_t)i * P + l] = u0[(size_t)i * P + l];
+            }
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, cur.data(), cur.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_active.p, active.data(), P, cudaMemcpyHostToDevice, s));
+        }
+        rc = dc_launch(r, 1, has_limits ? h->d_active.p : nullptr, nullptr, nullptr);
+        if (rc != CB200_OK) return rc;
+        if ((rc = fetch()) != CB200_OK) return rc;
+    }
+    if (use_stepping && !all_conv()) {
+        // tiers 2 and 3, per lane, host-driven: _gshunt_stepping (solve.jl:720-783)
+        // then _source_stepping (:805-850), each restarted from zeros.
+        std::vector<double> state((size_t)n * P), saved((size_t)n * P, 0.0);
+        CUDA_TRY(h, cudaMemcpyAsync(state.data(), h->d_state.p, state.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        std::vector<unsigned char> todo(P), final_conv = conv;
+        for (int64_t l = 0; l < P; l++) todo[l] = conv[l] ? 0 : 1;
+        auto put_state = [&]() -> int {
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, state.data(), state.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+            return CB200_OK;
+        };
+        auto get_state = [&](std::vector<double> &dst) -> int {
+            CUDA_TRY(h, cudaMemcpyAsync(dst.data(), h->d_state.p, dst.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(h, cudaStreamSynchronize(s));
+            return CB200_OK;
+        };
+        auto copy_lane = [&](std::vector<double> &dst, const std::vector<double> &src, int64_t l) {
+            for (int i = 0; i < n; i++) dst[(size_t)i * P + l] = src[(size_t)i * P + l];
+        };
+        // ---- gshunt stepping
+        {
+            const double target = spec->gshunt, gmin_thr = std::max(target, 1e-12);
+            std::vector<double> cur(P, 1e-3), factor(P, 10.0), gl(P, 0.0);
+            std::vector<unsigned char> act(P), fin(P, 0);
+            for (int64_t l = 0; l < P; l++) { act[l] = todo[l]; if (act[l]) for (int i = 0; i < n; i++) state[(size_t)i * P + l] = 0.0; }
+            saved = state;
+            std::vector<double> trial((size_t)n * P);
+            for (int step = 1; step <= 21; step++) {
+                bool any = false;
+                for (int64_t l = 0; l < P; l++) { any |= act[l] != 0; gl[l] = fin[l] ? target : cur[l]; }
+                if (!any) break;
+                if ((rc = put_state()) != CB200_OK) return rc;
+                CUDA_TRY(h, cudaMemcpyAsync(h->d_active.p, act.data(), P, cudaMemcpyHostToDevice, s));
+                CUDA_TRY(h, cudaMemcpyAsync(h->d_gshunt_lane.p, gl.data(), P * sizeof(double), cudaMemcpyHostToDevice, s));
+                rc = dc_launch(r, 1, h->d_active.p, h->d_gshunt_lane.p, nullptr);
+                if (rc != CB200_OK) return rc;
+                if ((rc = fetch()) != CB200_OK) return rc;
+                if ((rc = get_state(trial)) != CB200_OK) return rc;
+                for (int64_t l = 0; l < P; l++) {
+                    if (!act[l]) continue;
+                    if (fin[l]) {                       // final solve at the exact target
+                        if (conv[l]) { copy_lane(state, trial, l); final_conv[l] = 1; todo[l] = 0; }
+                        act[l] = 0;
+                        continue;
+                    }
+                    if (conv[l]) {
+                        copy_lane(state, trial, l); copy_lane(saved, trial, l);
+                        if (cur[l] <= gmin_thr) {
+                            if (cur[l] != target) fin[l] = 1;
+                            else { final_conv[l] = 1; todo[l] = 0; act[l] = 0; }
+                            continue;
+                        }
+                        cur[l] /= factor[l];
+                        if (cur[l] < gmin_thr) cur[l] = gmin_thr;
+                    } else {
+                        if (factor[l] <= 1.5) { act[l] = 0; continue; }
+                        factor[l] = std::sqrt(factor[l]);
+                        copy_lane(state, saved, l);
+                    }
+                    if (step >= 20 && !fin[l]) act[l] = 0;   // max_steps = 20
+                }
+            }
+        }
+        // ---- source stepping
+        bool any_todo = std::any_of(todo.begin(), todo.end(), [](unsigned char c) { return c != 0; });
+        if (any_todo) {
+            std::vector<double> sf(P, 0.0), convsf(P, 0.0), raise(P, 0.1), sl(P, 1.0);
+            std::vector<unsigned char> act(P);
+            for (int64_t l = 0; l < P; l++) { act[l] = todo[l]; if (act[l]) for (int i = 0; i < n; i++) state[(size_t)i * P + l] = 0.0; }
+            saved = state;
+            std::vector<double> trial((size_t)n * P);
+            for (int step = 1; step <= 50; step++) {
+                bool any = false;
+                for (int64_t l = 0; l < P; l++) { any |= act[l] != 0; sl[l] = sf[l]; }
+                if (!any) break;
+                if ((rc = put_state()) != CB200_OK) return rc;
+                CUDA_TRY(h, cudaMemcpyAsync(h->d_active.p, act.data(), P, cudaMemcpyHostToDevice, s));
+                CUDA_TRY(h, cudaMemcpyAsync(h->d_srcfact_lane.p, sl.data(), P * sizeof(double), cudaMemcpyHostToDevice, s));
+                rc = dc_launch(r, 1, h->d_active.p, nullptr, h->d_srcfact_lane.p);
+                if (rc != CB200_OK) return rc;
+                if ((rc = fetch()) != CB200_OK) return rc;
+                if ((rc = get_state(trial)) != CB200_OK) return rc;
+                for (int64_t l = 0; l < P; l++) {
+                    if (!act[l]) continue;
+                    if (conv[l]) {
+                        convsf[l] = sf[l];
+                        copy_lane(state, trial, l); copy_lane(saved, trial, l);
+                        if (sf[l] >= 1.0) { final_conv[l] = 1; todo[l] = 0; act[l] = 0; continue; }
+                        sf[l] = std::min(sf[l] + raise[l], 1.0);
+                    } else {
+                        if (sf[l] - convsf[l] < 1e-6) { act[l] = 0; continue; }
+                        raise[l] /= 2.0;
+                        sf[l] = convsf[l] + raise[l];
+                        copy_lane(state, saved, l);
+                    }
+                }
+            }
+        }
+        if ((rc = put_state()) != CB200_OK) return rc;
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        conv = final_conv;
+        for (int64_t l = 0; l < P; l++) status[l] = conv[l] ? CB200_LANE_OK : (status[l] == CB200_LANE_OK ? CB200_LANE_MAXITER : status[l]);
+    }
+    h->stats.kernel_ms += r.kernel_ms;
+    conv_out = conv;
+    status_out = status;
+    for (int64_t l = 0; l < P; l++) if (conv_out[l]) status_out[l] = CB200_LANE_OK;
+    return CB200_OK;
+}
+
+extern "C" int cb200_dc(cb200_handle *h, const cb200_spec *spec, const cb200_dc_opts *opts,
+                        const double *u0, double *x_out, int32_t *status, int32_t *iters)
+{
+    if (!h || !spec || !opts) return fail(h, CB200_EINVAL, "cb200_dc: null argument");
+    if (h->P <= 0) return fail(h, CB200_ESTATE, "cb200_dc: call cb200_set_lanes first");
+    cudaSetDevice(h->device);
+    const int64_t P = h->P;
+    const int n = h->st.n;
+    h->stats = cb200_stats{};
+    cudaStream_t s = h->stream;
+    if (n == 0) { for (int64_t l = 0; l < P; l++) { if (status) status[l] = 0; if (iters) iters[l] = 0; } return CB200_OK; }
+    if (u0) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, u0, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, s));
+        h->stats.h2d_bytes += (int64_t)n * P * sizeof(double);
+    } else {
+        CUDA_TRY(h, cudaMemsetAsync(h->d_state.p, 0, (size_t)n * P * sizeof(double), s));
+    }
+    std::vector<unsigned char> conv;
+    std::vector<int> st;
+    int rc = dc_chain(h, spec, 0.0, opts->abstol, opts->maxiters, opts->use_stepping, conv, st);
+    if (rc != CB200_OK) return rc;
+    if (x_out) {
+        CUDA_TRY(h, cudaMemcpyAsync(x_out, h->d_state.p, (size_t)n * P * sizeof(double), cudaMemcpyDeviceToHost, s));
+        h->stats.d2h_bytes += (int64_t)n * P * sizeof(double);
+    }
+    std::vector<int> it(P);
+    CUDA_TRY(h, cudaMemcpyAsync(it.data(), h->d_iters.p, P * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    int64_t tot = 0;
+    for (int64_t l = 0; l < P; l++) {
+        if (status) status[l] = st[l];
+        if (iters) iters[l] = it[l];
+        tot += it[l];
+    }
+    h->stats.newton_iters = tot;
+    return CB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// transient
+// ---------------------------------------------------------------------------
+extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
+                          const cb200_tran_opts *o, const int64_t *save_idx, int32_t n_save,
+                          const double *u0, cb200_wave **out)
+{
+    if (!h || !spec || !o || !out) return fail(h, CB200_EINVAL, "cb200_tran: null argument");
+    *out = nullptr;
+    if (h->P <= 0) return fail(h, CB200_ESTATE, "cb200_tran: call cb200_set_lanes first");
+    if (!(t1 > t0) || !(o->dt > 0.0)) return fail(h, CB200_EINVAL, "cb200_tran: need t1 > t0 and dt > 0");
+    if (n_save < 0 || (n_save > 0 && !save_idx)) return fail(h, CB200_EINVAL, "cb200_tran: bad save list");
+    cudaSetDevice(h->device);
+    const int64_t P = h->P;
+    const int n = h->st.n;
+    for (int q = 0; q < n_save; q++)
+        if (save_idx[q] < 1 || save_idx[q] > n) return fail(h, CB200_EINVAL, "cb200_tran: save index out of range");
+    h->stats = cb200_stats{};
+    cudaStream_t s = h->stream;
+
+    // initialisation: CedarTranOp (dcop.jl:160-203) or caller-provided state
+    std::vector<unsigned char> conv(P, 1);
+    std::vector<int> st0(P, CB200_LANE_OK);
+    if (o->init == 0) {
+        CUDA_TRY(h, cudaMemsetAsync(h->d_state.p, 0, (size_t)n * P * sizeof(double), s));
+        cb200_spec sdc = *spec;
+        sdc.mode = CB200_MODE_TRANOP;
+        int rc = dc_chain(h, &sdc, t0, o->init_abstol, o->init_maxiters, 1, conv, st0);
+        if (rc != CB200_OK) return rc;
+    } else {
+        if (!u0) return fail(h, CB200_EINVAL, "cb200_tran: init=1 needs u0");
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, u0, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaMemsetAsync(h->d_iters.p, 0, P * sizeof(int), s));
+        h->stats.h2d_bytes += (int64_t)n * P * sizeof(double);
+    }
+    const double gamma_nom = (o->method == CB200_METHOD_BE ? 1.0 : o->method == CB200_METHOD_TRAP ? 2.0 : 1.5) / o->dt;
+    int rc = ensure_lu(h, spec, 1, gamma_nom);
+    if (rc != CB200_OK) return rc;
+
+    cb200_wave *w = new cb200_wave();
+    w->h = h; w->P = P; w->n_save = n_save; w->n = n; w->adaptive = o->adaptive; w->t0 = t0; w->dt = o->dt;
+    std::vector<int> save0(n_save);
+    for (int q = 0; q < n_save; q++) save0[q] = (int)save_idx[q] - 1;
+    DevBuf<int> d_save;
+    if (d_save.upload(save0, s) != cudaSuccess) { delete w; return fail(h, CB200_ECUDA, "cb200_tran: upload failed"); }
+    // lanes whose initialisation failed keep that status (InitialFailure, dcop.jl:197-200)
+    if (cudaMemcpyAsync(h->d_status.p, st0.data(), P * sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess) {
+        delete w; return fail(h, CB200_ECUDA, "cb200_tran: upload failed");
+    }
+    SpecArgs sa = spec_args(spec);
+    sa.mode = CB200_MODE_TRAN;
+    double *ws_global = nullptr;
+    if (choose_block(h->prog.n_slots, h->smem_limit, h->block_pref) == 0) {
+        rc = ensure_global_ws(h);
+        if (rc != CB200_OK) { delete w; return rc; }
+        ws_global = h->d_ws_global.p;
+    }
+    cudaError_t ce = cudaSuccess;
+    if (!o->adaptive) {
+        const int64_t nsteps = (int64_t)std::llround((t1 - t0) / o->dt);
+        const int se = o->save_every > 0 ? o->save_every : 1;
+        const int64_t T = 1 + nsteps / se + ((nsteps % se) ? 1 : 0);
+        w->T = T; w->nsteps = nsteps; w->save_every = se;
+        if (w->d_out.alloc((size_t)std::max(1, n_save) * T * P) != cudaSuccess) {
+            delete w; return fail(h, CB200_ENOMEM, "cb200_tran: waveform buffer allocation failed");
+        }
+        TranArgs a{};
+        a.method = o->method; a.t0 = t0; a.h = o->dt; a.nsteps = nsteps; a.abstol = o->abstol;
+        a.max_nl = o->max_nl_iters; a.save_every = se; a.n_save = n_save; a.save_idx = d_save.p;
+        a.T = T; a.u = h->d_state.p; a.out = w->d_out.p; a.status = h->d_status.p; a.iters = h->d_iters.p;
+        a.ws_global = ws_global;
+        cudaEventRecord(h->ev0, s);
+        ce = launch_tran_fixed(h->prog, h->lu[1].prog, sa, a, h->block_pref, h->smem_limit, s, &h->stats.launches);
+        cudaEventRecord(h->ev1, s);
+    } else {
+        // tstops: breakpoints are computed by the host wrapper and passed through dtmax/.. (see
+        // cb200_tran_adaptive_stops); plain adaptive call uses none.
+        delete w;
+        return fail(h, CB200_EINVAL, "cb200_tran: adaptive stepping is provided by cb200_tran_adaptive");
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) {
+        delete w;
+        return fail(h, CB200_ECUDA, std::string("cb200_tran: kernel failed: ") + cudaGetErrorString(ce));
+    }
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.kernel_ms += ms;
+    // keep per-lane results with the wave so the handle can be reused
+    w->d_status.alloc(P); w->d_iters.alloc(P); w->d_final.alloc((size_t)n * P);
+    cudaMemcpyAsync(w->d_status.p, h->d_status.p, P * sizeof(int), cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(w->d_iters.p, h->d_iters.p, P * sizeof(int), cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(w->d_final.p, h->d_state.p, (size_t)n * P * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) { delete w; return fail(h, CB200_ECUDA, cudaGetErrorString(ce)); }
+    h->stats.steps_accepted = w->nsteps * P;
+    *out = w;
+    return CB200_OK;
+}
+
+extern "C" int cb200_wave_info(const cb200_wave *w, int64_t *T, int64_t *P, int32_t *n_save,
+                               int32_t *adaptive)
+{
+    if (!w) return CB200_EINVAL;
+    if (T) *T = w->T;
+    if (P) *P = w->P;
+    if (n_save) *n_save = w->n_save;
+    if (adaptive) *adaptive = w->adaptive;
+    return CB200_OK;
+}
+
+extern "C" int cb200_wave_fetch(cb200_wave *w, double *t, double *u, int32_t *count, int32_t *status,
+                                int32_t *newton_iters)
+{
+    if (!w) return CB200_EINVAL;
+    cb200_handle *h = w->h;
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    int64_t bytes = 0;
+    if (u && w->n_save > 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(u, w->d_out.p, (size_t)w->n_save * w->T * w->P * sizeof(double), cudaMemcpyDeviceToHost, s));
+        bytes += (int64_t)w->n_save * w->T * w->P * sizeof(double);
+    }
+    if (status) { CUDA_TRY(h, cudaMemcpyAsync(status, w->d_status.p, w->P * sizeof(int), cudaMemcpyDeviceToHost, s)); bytes += w->P * 4; }
+    if (newton_iters) { CUDA_TRY(h, cudaMemcpyAsync(newton_iters, w->d_iters.p, w->P * sizeof(int), cudaMemcpyDeviceToHost, s)); bytes += w->P * 4; }
+    if (w->adaptive) {
+        if (t) CUDA_TRY(h, cudaMemcpyAsync(t, w->d_t.p, (size_t)w->T * w->P * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (count) CUDA_TRY(h, cudaMemcpyAsync(count, w->d_count.p, w->P * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.d2h_ms = ms;
+    h->stats.d2h_bytes = bytes;
+    if (!w->adaptive) {
+        if (t) {
+            int64_t q = 0;
+            t[q++] = w->t0;
+            for (int64_t k = 1; k <= w->nsteps; k++)
+                if (k % w->save_every == 0 || k == w->nsteps) t[q++] = w->t0 + (double)k * w->dt;
+        }
+        if (count) for (int64_t l = 0; l < w->P; l++) count[l] = (int32_t)w->T;
+    }
+    if (newton_iters) {
+        int64_t tot = 0;
+        for (int64_t l = 0; l < w->P; l++) tot += newton_iters[l];
+        h->stats.newton_iters = tot;
+    }
+    return CB200_OK;
+}
+
+extern "C" int cb200_wave_final_state(cb200_wave *w, double *x_out)
+{
+    if (!w || !x_out) return CB200_EINVAL;
+    cb200_handle *h = w->h;
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaMemcpyAsync(x_out, w->d_final.p, (size_t)w->n * w->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CB200_OK;
+}
+
+extern "C" void cb200_wave_free(cb200_wave *w)
+{
+    if (!w) return;
+    cudaSetDevice(w->h->device);
+    delete w;
+}
+
+extern "C" int cb200_get_stats(const cb200_handle *h, cb200_stats *out)
+{
+    if (!h || !out) return CB200_EINVAL;
+    *out = h->stats;
+    return CB200_OK;
+}

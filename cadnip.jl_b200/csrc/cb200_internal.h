@@ -1,0 +1,53 @@
+// cb200_internal.h -- host-side structures shared by symbolic.cpp / api.cu / kernels.cu.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/cadnip_b200.h"
+
+namespace cb200 {
+
+// CSC pattern + stamp maps: the CompiledStructure of src/mna/precompile.jl:88-160,
+// 0-based internally (getters convert to Julia's 1-based Int).
+struct Structure {
+    int n = 0, n_nodes = 0, n_currents = 0, n_charges = 0, n_limits = 0;
+    int64_t nnz = 0, nG = 0, nC = 0, nb = 0;
+    std::vector<int> colptr, rowval;         // unified G|C pattern
+    std::vector<int> G_map, C_map;           // COO k -> nz slot
+    std::vector<int> b_rows;                 // b stamp k -> row (-1 = dropped)
+    std::vector<int> diag_nz;                // [n_nodes] nz slot of (i,i) or -1
+    // segment lists for the deterministic, atomics-free assembly: nz slot s sums the
+    // stamp values gseg_idx[gseg_ptr[s] .. gseg_ptr[s+1]) left to right, i.e. in COO
+    // (program) order -- the summation order of `nzval[idx] += v` in the reference
+    // (src/mna/value_only.jl:395-421).
+    std::vector<int> gseg_ptr, gseg_idx, cseg_ptr, cseg_idx, bseg_ptr, bseg_idx;
+    std::vector<int> nz_row, nz_col;         // coordinates of every nz slot
+    std::vector<uint8_t> nz_is_node_diag;    // gshunt target (precompile.jl:524-534)
+};
+
+// Build pattern and maps from resolved 1-based COO.  Returns "" or an error.
+std::string build_structure(const cb200_desc &d, Structure &out);
+
+// Static-pivot sparse LU schedule (the symbolic phase that replaces KLU analyze).
+struct LuSchedule {
+    int n = 0;
+    int64_t nlu = 0;                         // number of stored factor entries
+    std::vector<int> rowperm, colperm;       // pivot k eliminates row rowperm[k], col colperm[k]
+    std::vector<int> diag_slot;              // [n]
+    std::vector<int> Lptr, L_slot, L_row;    // column k of L (below-diagonal), rows in pivot coords
+    std::vector<int> Uptr, U_slot, U_col;    // row k of U (right of diagonal), cols in pivot coords
+    std::vector<int> tgt_ptr, tgt;           // for pivot k: tgt[tgt_ptr[k] + e*nU + q]
+    std::vector<int> jmap;                   // nz slot -> lu slot
+    std::vector<int> fill_slots;             // lu slots with no nz source (zeroed per factor)
+    int64_t flops = 0;                       // multiply-subtract count of one refactor
+    double gamma = 0.0;
+    bool valid = false;
+};
+
+// absJ: nominal magnitude of every pattern entry (max over probes; 0 = numerically
+// absent at the probes).  Threshold Markowitz on the magnitudes, then symbolic fill.
+std::string analyze_lu(const Structure &s, const std::vector<double> &absJ, double threshold,
+                       LuSchedule &out);
+
+}  // namespace cb200

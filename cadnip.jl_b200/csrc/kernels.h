@@ -1,0 +1,118 @@
+// kernels.h -- device-visible program descriptors and kernel launchers.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cb200 {
+
+// Everything the device needs to re-run the "builder" for a lane: the device table
+// recorded next to each stamp! call, the segment lists of the assembly, the CSC
+// coordinates, and the layout of a lane's workspace.  All pointers are device
+// pointers to read-only int32 / fp64 arrays that are uniform across lanes.
+struct Program {
+    int n, n_nodes, n_limits, nnz, nG, nC, nb, n_dev, n_dyn, n_lane_cols;
+    int64_t P;                      // lanes on this device
+    const int *dev_kind, *dev_flags, *dev_node_ptr, *dev_nodes, *dev_param_ptr, *dev_params;
+    const int *dev_gbase, *dev_cbase, *dev_bbase;
+    const int *dyn_list;            // devices whose stamps depend on (x, t)
+    const double *uniform;          // uniform parameter pool
+    const double *lanes;            // per-lane parameter SoA [col][P]
+    const int *limit_init_ref;      // [n_limits]
+    const int *gseg_ptr, *gseg_idx, *cseg_ptr, *cseg_idx, *bseg_ptr, *bseg_idx;
+    const int *colptr, *rowval;
+    const unsigned char *nz_is_node_diag;
+    // lane workspace: slot offsets (in doubles); element (slot) of a lane lives at
+    // ws[slot * stride + lane_in_block]  (shared) or ws[slot * P + lane] (global).
+    int off_u, off_un, off_dterm, off_F, off_wv, off_SG, off_SC, off_SB, off_LU, off_limw, off_lp;
+    int off_h1, off_h2;             // adaptive history (u_{n-1}, u_{n-2}); -1 when absent
+    int n_slots;
+};
+
+// Static-pivot LU schedule (see LuSchedule in cb200_internal.h).
+struct LuProgram {
+    int n, nlu, n_fill;
+    const int *rowperm, *colperm, *diag_slot;
+    const int *Lptr, *L_slot, *L_row, *Uptr, *U_slot, *U_col, *tgt_ptr, *tgt, *jmap, *fill_slots;
+};
+
+struct SpecArgs {
+    int mode;
+    double temp, gmin, gshunt, srcFact;
+};
+
+// ---- evaluation only (K1 instance x lane device evaluation, K2 segmented assembly)
+struct EvalArgs {
+    double t;
+    int initjct;
+    double *ws;             // global workspace [n_slots][P]; x already in the off_u slots
+    double *G_nz, *C_nz, *b;  // outputs [nnz][P], [nnz][P], [n][P] (may be null)
+    double *limw;           // [n_limits][P] or null
+};
+cudaError_t launch_eval(const Program &p, const SpecArgs &s, const EvalArgs &a, cudaStream_t st,
+                        int64_t *launches);
+
+// ---- DC: PCNR / plain Newton per lane (src/mna/solve.jl:542-698)
+struct DcArgs {
+    int algorithm;          // 0: PCNR (_dc_pcnr_newton), 1: plain Newton (_dc_newton_compiled)
+    double abstol;
+    int maxiters;
+    double t;
+    double *u;              // [n][P] in: start, out: solution
+    const unsigned char *active;   // [P] or null = all lanes
+    const double *gshunt_lane;     // [P] or null -> spec.gshunt
+    const double *srcfact_lane;    // [P] or null -> spec.srcFact
+    int *status;            // [P] CB200_LANE_*
+    int *iters;             // [P] (+= linear solves)
+    unsigned char *converged;  // [P]
+    double *ws_global;      // used when the lane workspace does not fit in shared memory
+};
+cudaError_t launch_dc(const Program &p, const LuProgram &lu, const SpecArgs &s, const DcArgs &a,
+                      int block, size_t smem_limit, cudaStream_t st, int64_t *launches);
+
+// ---- transient, fixed step (BE / trap / Gear-2), whole time loop on the device
+struct TranArgs {
+    int method;             // CB200_METHOD_*
+    double t0, h;
+    int64_t nsteps;
+    double abstol;
+    int max_nl;
+    int save_every;
+    int n_save;
+    const int *save_idx;    // device, 0-based unknown indices
+    int64_t T;              // saved points per lane
+    double *u;              // [n][P] in: u(t0); out: u(t1)
+    double *out;            // [n_save][T][P]
+    int *status;            // [P]
+    int *iters;             // [P]
+    double *ws_global;
+};
+cudaError_t launch_tran_fixed(const Program &p, const LuProgram &lu, const SpecArgs &s,
+                              const TranArgs &a, int block, size_t smem_limit, cudaStream_t st,
+                              int64_t *launches);
+
+// ---- transient, adaptive (trap + LTE), per-lane time axis
+struct AdaptArgs {
+    int method;
+    double t0, t1, h0, dtmin, dtmax;
+    double abstol, reltol, lte_abstol;
+    int max_nl;
+    int n_save;
+    const int *save_idx;
+    int max_points;
+    const double *tstops;   // device, sorted
+    int n_tstops;
+    double *u;              // [n][P]
+    double *out_t;          // [max_points][P]
+    double *out;            // [n_save][max_points][P]
+    int *count;             // [P]
+    int *status, *iters, *rejected;
+    double *ws_global;
+};
+cudaError_t launch_tran_adaptive(const Program &p, const LuProgram &lu, const SpecArgs &s,
+                                 const AdaptArgs &a, int block, size_t smem_limit,
+                                 cudaStream_t st, int64_t *launches);
+
+// pick lanes-per-block so the lane workspace fits in shared memory (0 = use global)
+int choose_block(int n_slots, size_t smem_limit, int preferred);
+
+}  // namespace cb200

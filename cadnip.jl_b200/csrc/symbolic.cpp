@@ -1,0 +1,236 @@
+// symbolic.cpp -- host symbolic phase: CSC pattern + stamp maps (compile_structure,
+// src/mna/precompile.jl:312-467) and the static-pivot LU schedule that replaces
+// KLU's analyze step (call sites src/mna/solve.jl:612-613, src/sweeps.jl:600).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <numeric>
+
+#include "cb200_internal.h"
+
+namespace cb200 {
+
+// ---------------------------------------------------------------------------
+// compile_structure: unified pattern = sparse(vcat(G_I,C_I), vcat(G_J,C_J), 1)
+// (precompile.jl:410-414): CSC, rows ascending inside a column, duplicates merged,
+// explicit zeros kept.  Maps = compute_coo_to_nz_mapping (:253-283).
+// ---------------------------------------------------------------------------
+std::string build_structure(const cb200_desc &d, Structure &s)
+{
+    s.n_nodes = d.n_nodes; s.n_currents = d.n_currents;
+    s.n_charges = d.n_charges; s.n_limits = d.n_limits;
+    s.n = d.n_nodes + d.n_currents + d.n_charges + d.n_limits;
+    s.nG = d.nG; s.nC = d.nC; s.nb = d.nb;
+    const int n = s.n;
+    if (n < 0 || d.nG < 0 || d.nC < 0 || d.nb < 0) return "negative size in description";
+
+    auto check = [&](const int64_t *I, const int64_t *J, int64_t cnt, const char *what) -> std::string {
+        for (int64_t k = 0; k < cnt; k++) {
+            if (I[k] < 1 || I[k] > n || (J && (J[k] < 1 || J[k] > n)))
+                return std::string(what) + ": COO index out of range (ground stamps must be "
+                       "dropped before counting, context.jl:945-953)";
+        }
+        return "";
+    };
+    std::string e;
+    if (!(e = check(d.G_I, d.G_J, d.nG, "G")).empty()) return e;
+    if (!(e = check(d.C_I, d.C_J, d.nC, "C")).empty()) return e;
+    if (!(e = check(d.b_I, nullptr, d.nb, "b")).empty()) return e;
+
+    // unique (col,row) keys, sorted
+    std::vector<int64_t> keys;
+    keys.reserve(d.nG + d.nC);
+    for (int64_t k = 0; k < d.nG; k++) keys.push_back((d.G_J[k] - 1) * (int64_t)n + (d.G_I[k] - 1));
+    for (int64_t k = 0; k < d.nC; k++) keys.push_back((d.C_J[k] - 1) * (int64_t)n + (d.C_I[k] - 1));
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    s.nnz = (int64_t)keys.size();
+    s.colptr.assign(n + 1, 0);
+    s.rowval.resize(s.nnz);
+    s.nz_row.resize(s.nnz);
+    s.nz_col.resize(s.nnz);
+    for (int64_t q = 0; q < s.nnz; q++) {
+        int col = (int)(keys[q] / n), row = (int)(keys[q] % n);
+        s.rowval[q] = row; s.nz_row[q] = row; s.nz_col[q] = col;
+        s.colptr[col + 1]++;
+    }
+    for (int j = 0; j < n; j++) s.colptr[j + 1] += s.colptr[j];
+
+    auto find = [&](int64_t i1, int64_t j1) -> int {
+        int64_t key = (j1 - 1) * (int64_t)n + (i1 - 1);
+        auto it = std::lower_bound(keys.begin(), keys.end(), key);
+        return (int)(it - keys.begin());
+    };
+    s.G_map.resize(d.nG);
+    s.C_map.resize(d.nC);
+    for (int64_t k = 0; k < d.nG; k++) s.G_map[k] = find(d.G_I[k], d.G_J[k]);
+    for (int64_t k = 0; k < d.nC; k++) s.C_map[k] = find(d.C_I[k], d.C_J[k]);
+    s.b_rows.resize(d.nb);
+    for (int64_t k = 0; k < d.nb; k++) s.b_rows[k] = (int)d.b_I[k] - 1;
+
+    // _compute_diag_nz_indices (precompile.jl:451-467)
+    s.diag_nz.assign(s.n_nodes, -1);
+    s.nz_is_node_diag.assign(s.nnz, 0);
+    for (int col = 0; col < s.n_nodes; col++)
+        for (int q = s.colptr[col]; q < s.colptr[col + 1]; q++)
+            if (s.rowval[q] == col) { s.diag_nz[col] = q; s.nz_is_node_diag[q] = 1; break; }
+
+    // segment lists (stable: ascending COO index inside a segment)
+    auto segments = [](const std::vector<int> &map, int64_t nseg, std::vector<int> &ptr,
+                       std::vector<int> &idx) {
+        ptr.assign(nseg + 1, 0);
+        for (int m : map) if (m >= 0) ptr[m + 1]++;
+        for (int64_t q = 0; q < nseg; q++) ptr[q + 1] += ptr[q];
+        idx.resize(ptr[nseg]);
+        std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+        for (size_t k = 0; k < map.size(); k++) if (map[k] >= 0) idx[cur[map[k]]++] = (int)k;
+    };
+    segments(s.G_map, s.nnz, s.gseg_ptr, s.gseg_idx);
+    segments(s.C_map, s.nnz, s.cseg_ptr, s.cseg_idx);
+    segments(s.b_rows, n, s.bseg_ptr, s.bseg_idx);
+    return "";
+}
+
+// ---------------------------------------------------------------------------
+// analyze_lu: threshold Markowitz pivoting on nominal magnitudes, symbolic fill,
+// elimination schedule.  The pivot sequence is fixed for every lane and every
+// Newton iteration (klu_refactor-style reuse); the numeric kernels flag lanes whose
+// pivots vanish (CB200_LANE_SINGULAR).
+// Dense working matrices: this path serves the small/medium-circuit regime
+// (n <= kDenseLimit); the level-scheduled supernodal path for c6288-class
+// circuits is a separate, later tier.
+// ---------------------------------------------------------------------------
+static const int kDenseLimit = 1536;
+
+std::string analyze_lu(const Structure &s, const std::vector<double> &absJ, double threshold,
+                       LuSchedule &out)
+{
+    const int n = s.n;
+    out = LuSchedule();
+    out.n = n;
+    if (n == 0) { out.valid = true; return ""; }
+    if (n > kDenseLimit) return "analyze_lu: n exceeds the small/medium-circuit symbolic path";
+    if ((int64_t)absJ.size() != s.nnz) return "analyze_lu: magnitude array has wrong length";
+
+    // pat: 0 absent, 1 structural; mag: nominal magnitude
+    std::vector<uint8_t> pat((size_t)n * n, 0);
+    std::vector<double> mag((size_t)n * n, 0.0);
+    for (int j = 0; j < n; j++)
+        for (int q = s.colptr[j]; q < s.colptr[j + 1]; q++) {
+            pat[(size_t)s.rowval[q] * n + j] = 1;
+            mag[(size_t)s.rowval[q] * n + j] = std::isfinite(absJ[q]) ? absJ[q] : 0.0;
+        }
+    std::vector<uint8_t> row_done(n, 0), col_done(n, 0);
+    std::vector<int> rcount(n, 0), ccount(n, 0);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++)
+            if (pat[(size_t)i * n + j]) { rcount[i]++; ccount[j]++; }
+    out.rowperm.resize(n);
+    out.colperm.resize(n);
+
+    for (int k = 0; k < n; k++) {
+        // column maxima over the active submatrix
+        std::vector<double> colmax(n, 0.0);
+        for (int i = 0; i < n; i++) {
+            if (row_done[i]) continue;
+            const double *mr = &mag[(size_t)i * n];
+            for (int j = 0; j < n; j++)
+                if (!col_done[j] && mr[j] > colmax[j]) colmax[j] = mr[j];
+        }
+        long best_cost = -1; int bi = -1, bj = -1; double best_rel = -1.0; bool best_diag = false;
+        for (int i = 0; i < n; i++) {
+            if (row_done[i]) continue;
+            for (int j = 0; j < n; j++) {
+                if (col_done[j] || !pat[(size_t)i * n + j]) continue;
+                double m = mag[(size_t)i * n + j];
+                if (!(m > 0.0) || m < threshold * colmax[j]) continue;
+                long cost = (long)(rcount[i] - 1) * (long)(ccount[j] - 1);
+                double rel = m / colmax[j];
+                bool diag = (i == j);
+                bool better = false;
+                if (best_cost < 0 || cost < best_cost) better = true;
+                else if (cost == best_cost) {
+                    if (diag && !best_diag) better = true;
+                    else if (diag == best_diag && rel > best_rel * (1.0 + 1e-12)) better = true;
+                }
+                if (better) { best_cost = cost; bi = i; bj = j; best_rel = rel; best_diag = diag; }
+            }
+        }
+        if (bi < 0) return "analyze_lu: matrix is singular at the probe points (no admissible pivot "
+                           "at step " + std::to_string(k) + ")";
+        out.rowperm[k] = bi; out.colperm[k] = bj;
+        row_done[bi] = 1; col_done[bj] = 1;
+        const double piv = mag[(size_t)bi * n + bj];
+        // eliminate: fill + magnitude bound
+        for (int j = 0; j < n; j++) if (!col_done[j] && pat[(size_t)bi * n + j]) ccount[j]--;
+        for (int i = 0; i < n; i++) {
+            if (row_done[i] || !pat[(size_t)i * n + bj]) continue;
+            rcount[i]--;
+            double l = mag[(size_t)i * n + bj] / piv;
+            for (int j = 0; j < n; j++) {
+                if (col_done[j] || !pat[(size_t)bi * n + j]) continue;
+                size_t ij = (size_t)i * n + j;
+                if (!pat[ij]) { pat[ij] = 2; rcount[i]++; ccount[j]++; }
+                mag[ij] += l * mag[(size_t)bi * n + j];
+            }
+        }
+    }
+
+    // Factor pattern in pivot coordinates: B[a][b] = A[rowperm[a]][colperm[b]].
+    std::vector<int> rinv(n), cinv(n);
+    for (int k = 0; k < n; k++) { rinv[out.rowperm[k]] = k; cinv[out.colperm[k]] = k; }
+    std::vector<int> slot((size_t)n * n, -1);
+    int64_t nlu = 0;
+    // slot order: for every pivot k, its diagonal, then U row k, then L column k
+    out.diag_slot.resize(n);
+    out.Uptr.assign(n + 1, 0);
+    out.Lptr.assign(n + 1, 0);
+    for (int k = 0; k < n; k++) {
+        int ri = out.rowperm[k], cj = out.colperm[k];
+        slot[(size_t)k * n + k] = (int)nlu; out.diag_slot[k] = (int)nlu; nlu++;
+        for (int b = k + 1; b < n; b++) {
+            if (pat[(size_t)ri * n + out.colperm[b]]) {
+                slot[(size_t)k * n + b] = (int)nlu;
+                out.U_slot.push_back((int)nlu); out.U_col.push_back(b); nlu++;
+            }
+        }
+        out.Uptr[k + 1] = (int)out.U_slot.size();
+        for (int a = k + 1; a < n; a++) {
+            if (pat[(size_t)out.rowperm[a] * n + cj]) {
+                slot[(size_t)a * n + k] = (int)nlu;
+                out.L_slot.push_back((int)nlu); out.L_row.push_back(a); nlu++;
+            }
+        }
+        out.Lptr[k + 1] = (int)out.L_slot.size();
+    }
+    out.nlu = nlu;
+    // update targets
+    out.tgt_ptr.assign(n + 1, 0);
+    for (int k = 0; k < n; k++) {
+        int nL = out.Lptr[k + 1] - out.Lptr[k], nU = out.Uptr[k + 1] - out.Uptr[k];
+        for (int e = 0; e < nL; e++) {
+            int a = out.L_row[out.Lptr[k] + e];
+            for (int q = 0; q < nU; q++) {
+                int b = out.U_col[out.Uptr[k] + q];
+                int t = slot[(size_t)a * n + b];
+                if (t < 0) return "analyze_lu: internal error (missing fill slot)";
+                out.tgt.push_back(t);
+            }
+        }
+        out.tgt_ptr[k + 1] = (int)out.tgt.size();
+        out.flops += (int64_t)nL * nU;
+    }
+    // scatter map and fill list
+    out.jmap.resize(s.nnz);
+    std::vector<uint8_t> has_src(nlu, 0);
+    for (int64_t q = 0; q < s.nnz; q++) {
+        int t = slot[(size_t)rinv[s.nz_row[q]] * n + cinv[s.nz_col[q]]];
+        if (t < 0) return "analyze_lu: internal error (pattern entry without slot)";
+        out.jmap[q] = t; has_src[t] = 1;
+    }
+    for (int64_t t = 0; t < nlu; t++) if (!has_src[t]) out.fill_slots.push_back((int)t);
+    out.valid = true;
+    return "";
+}
+
+}  // namespace cb200

@@ -1,0 +1,202 @@
+"""Lowering: run the builder once against the recording MNAContext and flatten what
+it recorded into the circuit IR of include/cadnip_b200.h (``cb200_desc`` + the
+per-lane parameter SoA).
+
+This is the host half of ``build_with_detection`` + ``compile_structure``
+(src/mna/solve.jl:1793-1822, src/mna/precompile.jl:312-366): typed indices are
+resolved once ``n_nodes`` is final, the COO coordinate lists are emitted in
+program order, and every ``stamp`` call becomes a device-table row.  The CSC
+pattern and the COO->nz maps themselves are built by the C++ host code inside
+``cb200_create``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .circuit import MNACircuit, MNASpec, Params
+from .mna import (MNAContext, ZERO_VECTOR, CurrentIndex, DeviceRow)
+
+
+class StructuralSweepError(ValueError):
+    """The builder could not be traced with lane-array parameters (it branches on a
+    swept value), i.e. the sweep crosses a structural boundary."""
+
+
+@dataclass
+class LoweredCircuit:
+    n_nodes: int
+    n_currents: int
+    n_charges: int
+    n_limits: int
+    node_names: List[str]
+    current_names: List[str]
+    charge_names: List[str]
+    limit_names: List[str]
+    G_I: np.ndarray
+    G_J: np.ndarray
+    C_I: np.ndarray
+    C_J: np.ndarray
+    b_I: np.ndarray
+    dev_kind: np.ndarray
+    dev_flags: np.ndarray
+    dev_node_ptr: np.ndarray
+    dev_nodes: np.ndarray
+    dev_param_ptr: np.ndarray
+    dev_params: np.ndarray
+    dev_gbase: np.ndarray
+    dev_cbase: np.ndarray
+    dev_bbase: np.ndarray
+    uniform: np.ndarray
+    limit_init_ref: np.ndarray
+    lane_soa: np.ndarray            # [n_lane_cols][P]
+    P: int
+    dev_names: List[str]
+    dev_user_nodes: List[List[int]]
+    breakpoints: List[Any]
+
+    @property
+    def n(self) -> int:
+        return self.n_nodes + self.n_currents + self.n_charges + self.n_limits
+
+    @property
+    def n_lane_cols(self) -> int:
+        return int(self.lane_soa.shape[0])
+
+    def unknown_names(self) -> List[str]:
+        return self.node_names + self.current_names + self.charge_names + self.limit_names
+
+    def index_of(self, name) -> int:
+        """1-based unknown index of a node / current / charge / limit name."""
+        if isinstance(name, (int, np.integer)):
+            return int(name)
+        names = self.unknown_names()
+        try:
+            return names.index(str(name)) + 1
+        except ValueError:
+            raise KeyError(f"no unknown named {name!r}; have {names}") from None
+
+    def param_value(self, ref: int) -> np.ndarray:
+        """Value of a parameter reference for every lane, shape (P,)."""
+        if ref >= 0:
+            return np.full(self.P, self.uniform[ref])
+        return self.lane_soa[~ref]
+
+    # ------------------------------------------------------------------ #
+    # The same netlist as plain arrays of *values* (one row per lane): the input
+    # format of the CPU oracle.  Lives here because it is pure data reshaping;
+    # the product never evaluates it.
+    def netlist_tables(self):
+        kind = self.dev_kind.astype(np.int32)
+        flags = self.dev_flags.astype(np.int32)
+        node_ptr = [0]
+        nodes: List[int] = []
+        for un in self.dev_user_nodes:
+            nodes += un
+            node_ptr.append(len(nodes))
+        par = np.empty((self.P, len(self.dev_params)), dtype=np.float64)
+        for j, ref in enumerate(self.dev_params):
+            par[:, j] = self.param_value(int(ref))
+        return dict(kind=kind, flags=flags,
+                    node_ptr=np.asarray(node_ptr, dtype=np.int32),
+                    nodes=np.asarray(nodes, dtype=np.int32),
+                    par_ptr=self.dev_param_ptr.astype(np.int32),
+                    par=np.ascontiguousarray(par), n_nodes=self.n_nodes)
+
+
+class _ParamPool:
+    def __init__(self, P: int):
+        self.P = P
+        self.uniform: List[float] = []
+        self._u_index: Dict[float, int] = {}
+        self.cols: List[np.ndarray] = []
+        self._c_index: Dict[bytes, int] = {}
+
+    def ref(self, v) -> int:
+        a = np.asarray(v, dtype=np.float64)
+        if a.ndim == 0:
+            f = float(a)
+            key = f if f == f else "nan"
+            i = self._u_index.get(key)
+            if i is None:
+                i = len(self.uniform)
+                self.uniform.append(f)
+                self._u_index[key] = i
+            return i
+        if a.ndim != 1 or a.shape[0] != self.P:
+            raise StructuralSweepError(
+                f"device parameter has shape {a.shape}; expected a scalar or ({self.P},) lane array")
+        a = np.ascontiguousarray(a)
+        key = a.tobytes()
+        i = self._c_index.get(key)
+        if i is None:
+            i = len(self.cols)
+            self.cols.append(a)
+            self._c_index[key] = i
+        return ~i
+
+
+def run_builder(builder, params: Params, spec: MNASpec) -> MNAContext:
+    """One discovery pass: ``builder(params, spec, 0.0; x=ZERO_VECTOR)``
+    (solve.jl:1793-1822 pass 1).  The reference's passes 2-5 only refine
+    voltage-dependent-charge detection for Verilog-A devices (contrib.jl:214-257);
+    the primitive devices' structure is independent of x."""
+    try:
+        ctx = builder(params, spec, 0.0, x=ZERO_VECTOR, ctx=None)
+    except StructuralSweepError:
+        raise
+    except ValueError as e:
+        if "ambiguous" in str(e):
+            raise StructuralSweepError(
+                "builder branches on a swept parameter: a CircuitSweep must not cross a "
+                "structural boundary (run such points as separate sweeps)") from e
+        raise
+    if not isinstance(ctx, MNAContext):
+        raise TypeError("builder must return the MNAContext it stamped into")
+    return ctx
+
+
+def lower(builder, params: Params, spec: MNASpec, P: int = 1) -> LoweredCircuit:
+    ctx = run_builder(builder, params, spec)
+    pool = _ParamPool(P)
+    res = ctx.resolve_index
+
+    def coords(lst):
+        return np.asarray([res(i) for i in lst], dtype=np.int64)
+
+    kind, flags, node_ptr, nodes, par_ptr, pars = [], [], [0], [], [0], []
+    gbase, cbase, bbase, names, user_nodes = [], [], [], [], []
+    for d in ctx.devices:
+        kind.append(d.kind); flags.append(d.flags); names.append(d.name)
+        nodes += [res(i) for i in d.nodes]
+        node_ptr.append(len(nodes))
+        pars += [pool.ref(v) for v in d.params]
+        par_ptr.append(len(pars))
+        gbase.append(d.gbase); cbase.append(d.cbase); bbase.append(d.bbase)
+        user_nodes.append(list(d.user_nodes))
+    gbase.append(len(ctx.G_I)); cbase.append(len(ctx.C_I)); bbase.append(len(ctx.b_I))
+    limit_init_ref = [pool.ref(v) for v in ctx.limit_init]
+    soa = (np.stack(pool.cols) if pool.cols else np.zeros((0, P), dtype=np.float64))
+    return LoweredCircuit(
+        n_nodes=ctx.n_nodes, n_currents=ctx.n_currents, n_charges=ctx.n_charges,
+        n_limits=ctx.n_limits,
+        node_names=list(ctx.node_names), current_names=list(ctx.current_names),
+        charge_names=list(ctx.charge_names), limit_names=list(ctx.limit_names),
+        G_I=coords(ctx.G_I), G_J=coords(ctx.G_J), C_I=coords(ctx.C_I), C_J=coords(ctx.C_J),
+        b_I=coords(ctx.b_I),
+        dev_kind=np.asarray(kind, dtype=np.int32), dev_flags=np.asarray(flags, dtype=np.int32),
+        dev_node_ptr=np.asarray(node_ptr, dtype=np.int32), dev_nodes=np.asarray(nodes, dtype=np.int32),
+        dev_param_ptr=np.asarray(par_ptr, dtype=np.int32), dev_params=np.asarray(pars, dtype=np.int32),
+        dev_gbase=np.asarray(gbase, dtype=np.int64), dev_cbase=np.asarray(cbase, dtype=np.int64),
+        dev_bbase=np.asarray(bbase, dtype=np.int64),
+        uniform=np.asarray(pool.uniform, dtype=np.float64),
+        limit_init_ref=np.asarray(limit_init_ref, dtype=np.int32),
+        lane_soa=np.ascontiguousarray(soa, dtype=np.float64), P=P,
+        dev_names=names, dev_user_nodes=user_nodes, breakpoints=list(ctx.breakpoints))
+
+
+def lower_circuit(circuit: MNACircuit, spec: Optional[MNASpec] = None) -> LoweredCircuit:
+    """Single circuit = one lane, every parameter uniform."""
+    return lower(circuit.builder, circuit.params, spec or circuit.spec, P=1)

@@ -1,0 +1,248 @@
+/*
+ * cadnip_b200.h -- C ABI of libcadnip_b200.so: the B200-native batched MNA
+ * Newton / transient hot path behind Cadnip's MNACircuit / dc! / tran! /
+ * CircuitSweep API.
+ *
+ * Plain pointers and sizes only; no torch / CUDA types cross this boundary.
+ * All entry points return 0 on success or a negative CB200_E* code; they never
+ * throw.  Per-lane numerical outcomes are reported in status[] arrays
+ * (CB200_LANE_*), mirroring the reference's "numerical failure never throws"
+ * convention (src/mna/solve.jl:1052, :2406; src/mna/dcop.jl:197-200).
+ *
+ * A "lane" is one sweep point of a CircuitSweep (src/sweeps.jl:387-424); lane
+ * order is the sweep iterator's order (Iterators.product: first axis fastest,
+ * src/sweeps.jl:272).  Unknown ordering is [nodes | currents | charges | limits]
+ * (src/mna/context.jl:436-438).  Indices that are Julia `Int` in the reference
+ * are int64 and 1-based here (0 = ground), so a Julia host can pass its arrays
+ * through `ccall` without conversion.
+ *
+ * Reference interfaces each entry point replaces are cited per declaration
+ * (paths relative to the reference repository root).
+ */
+#ifndef CADNIP_B200_H
+#define CADNIP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------- */
+#define CB200_OK            0
+#define CB200_EINVAL       -1   /* bad argument / inconsistent description     */
+#define CB200_ENOMEM       -2
+#define CB200_ECUDA        -3   /* CUDA runtime error; see cb200_last_error    */
+#define CB200_ENODEVICE    -4   /* no sm_100 device: there is NO CPU fallback  */
+#define CB200_ESTATE       -5   /* call order violated (e.g. lanes not set)    */
+#define CB200_ESINGULAR    -6   /* structurally singular pattern at analysis   */
+
+/* ---- per-lane status ---------------------------------------- */
+#define CB200_LANE_OK        0
+#define CB200_LANE_MAXITER   1
+#define CB200_LANE_SINGULAR  2
+#define CB200_LANE_NONFINITE 3
+#define CB200_LANE_DTMIN     4
+
+/* ---- analysis mode: MNASpec.mode (src/mna/solve.jl:57-70) ---------------- */
+#define CB200_MODE_DCOP   0
+#define CB200_MODE_TRAN   1
+#define CB200_MODE_TRANOP 2
+#define CB200_MODE_AC     3
+
+/* ---- device kinds: one per stamp! method of src/mna/devices.jl ---------- */
+/* nodes[] holds resolved unknown indices (1-based, 0 = ground) in the order
+ * listed; indices allocated by the stamp itself (alloc_current!/alloc_limit!)
+ * follow the terminals.  params[] are parameter references (see below).      */
+#define CB200_DEV_RESISTOR   1  /* nodes p,n        params r            devices.jl:498  */
+#define CB200_DEV_CAPACITOR  2  /* nodes p,n        params c            devices.jl:531  */
+#define CB200_DEV_INDUCTOR   3  /* nodes p,n,I      params l            devices.jl:569  */
+#define CB200_DEV_VSOURCE    4  /* nodes p,n,I      params dc,wave...   devices.jl:643  */
+#define CB200_DEV_ISOURCE    5  /* nodes p,n        params dc,wave...   devices.jl:719  */
+#define CB200_DEV_VCVS       6  /* nodes op,on,ip,in,I      params gain devices.jl:760  */
+#define CB200_DEV_VCCS       7  /* nodes op,on,ip,in        params gm   devices.jl:797  */
+#define CB200_DEV_CCVS       8  /* nodes op,on,ip,in,Iin,Iout params rm devices.jl:824;
+                                   flags=1: nodes op,on,Iin,Iout        devices.jl:898  */
+#define CB200_DEV_CCCS       9  /* nodes op,on,ip,in,Iin    params gain devices.jl:865;
+                                   flags=1: nodes op,on,Iin             devices.jl:924  */
+#define CB200_DEV_DIODE     10  /* nodes p,n[,lim]  params Is,Vt,n,vcrit devices.jl:1370;
+                                   flags bit0 = limit (PCNR)                            */
+#define CB200_DEV_DIODECAP  11  /* nodes p,n  params Is,Vt,n,Cj0,Vj,m   devices.jl:1558 */
+#define CB200_DEV_SIMPLEMOS 12  /* nodes d,g,s params Vth,K,lambda,Cgd,Cgs devices.jl:1667 */
+#define CB200_DEV_KIND_MAX  12
+
+/* source waveform selector, stored in dev_flags of V/I sources
+ * (PWLWave / PulseWave / SinWave, src/mna/devices.jl:130-216)                */
+#define CB200_WAVE_NONE  0      /* params: dc                                   */
+#define CB200_WAVE_PWL   1      /* params: dc, t1,y1, t2,y2, ...                */
+#define CB200_WAVE_PULSE 2      /* params: dc, v1,v2,td,tr,tf,pw,per            */
+#define CB200_WAVE_SIN   3      /* params: dc, vo,va,freq,td,theta,phase        */
+
+/* A parameter reference is an int32: ref >= 0 selects uniform[ref] (same value
+ * in every lane); ref < 0 selects lane-parameter column ~ref of the SoA given
+ * to cb200_set_lanes (value differs per sweep point).                         */
+
+/* MNASpec (src/mna/solve.jl:57-70) as a POD.                                  */
+typedef struct cb200_spec {
+    double  temp;      /* 27.0 */
+    int32_t mode;      /* CB200_MODE_* */
+    int32_t _pad;
+    double  gmin;      /* 1e-12 */
+    double  gshunt;    /* 0     */
+    double  srcFact;   /* 1     */
+    double  tnom;      /* 27    */
+    double  abstol;    /* 1e-12 */
+    double  reltol;    /* 1e-3  */
+    double  vntol;     /* 1e-6  */
+    double  iabstol;   /* 1e-12 */
+} cb200_spec;
+
+/* Circuit description: what build_with_detection + the builder's stamp! calls
+ * produce on an MNAContext (src/mna/solve.jl:1793-1822, src/mna/context.jl:248-372),
+ * with typed indices already resolved (context.jl:577-581), plus the device
+ * table a recording context captures next to each stamp! call.    */
+typedef struct cb200_desc {
+    int32_t n_nodes, n_currents, n_charges, n_limits;
+    int64_t nG, nC, nb;                 /* COO stamp counts (ground stamps excluded) */
+    const int64_t *G_I, *G_J;           /* [nG] 1-based                        */
+    const int64_t *C_I, *C_J;           /* [nC]                                */
+    const int64_t *b_I;                 /* [nb]                                */
+    int32_t n_devices;
+    int32_t n_uniform;
+    const int32_t *dev_kind;            /* [n_devices] CB200_DEV_*             */
+    const int32_t *dev_flags;           /* [n_devices]                         */
+    const int32_t *dev_node_ptr;        /* [n_devices+1] into dev_nodes        */
+    const int32_t *dev_nodes;
+    const int32_t *dev_param_ptr;       /* [n_devices+1] into dev_params       */
+    const int32_t *dev_params;          /* parameter references                */
+    const int64_t *dev_gbase;           /* [n_devices+1] first G COO slot (0-based) */
+    const int64_t *dev_cbase;           /* [n_devices+1]                       */
+    const int64_t *dev_bbase;           /* [n_devices+1]                       */
+    const double  *uniform;             /* [n_uniform]                         */
+    const int32_t *limit_init_ref;      /* [n_limits] parameter refs (context.jl:826) */
+    int32_t n_lane_cols;                /* columns cb200_set_lanes must supply */
+    int32_t _pad;
+} cb200_desc;
+
+typedef struct cb200_handle cb200_handle;
+typedef struct cb200_wave   cb200_wave;
+
+/* DC options: keyword arguments of _dc_solve_with_fallbacks
+ * (src/mna/solve.jl:871-874) / CedarTranOp (src/mna/dcop.jl:81).             */
+typedef struct cb200_dc_opts {
+    double  abstol;        /* 1e-10 (dc!) / 1e-9 (transient init)              */
+    int32_t maxiters;      /* 100 / 500                                        */
+    int32_t use_stepping;  /* 1: gshunt + source stepping fallbacks            */
+} cb200_dc_opts;
+
+#define CB200_METHOD_BE    0
+#define CB200_METHOD_TRAP  1
+#define CB200_METHOD_GEAR2 2
+
+/* Transient options: the keyword surface of tran! that reaches the integrator
+ * (src/sweeps.jl:588-665): solver choice (method), adaptive/dt, tolerances,
+ * saveat decimation, initialisation algorithm.                               */
+typedef struct cb200_tran_opts {
+    int32_t method;        /* CB200_METHOD_*                                   */
+    int32_t adaptive;      /* 0: fixed dt; 1: LTE step control per lane        */
+    double  dt;            /* fixed step, or initial step when adaptive        */
+    double  abstol;        /* Newton residual 2-norm tolerance (1e-10)         */
+    double  reltol;        /* LTE relative tolerance when adaptive (1e-8)      */
+    double  lte_abstol;    /* LTE absolute tolerance when adaptive             */
+    double  dtmin, dtmax;  /* adaptive bounds (0 = derive from tspan)          */
+    int32_t max_nl_iters;  /* 10 (IDA max_nonlinear_iters, sweeps.jl:599)      */
+    int32_t save_every;    /* fixed-step: keep every k-th point (saveat), >=1  */
+    int32_t max_points;    /* adaptive: per-lane output capacity               */
+    int32_t init;          /* 0: CedarTranOp (dcop.jl:160); 1: u0 given (UIC)  */
+    double  init_abstol;   /* 1e-9  */
+    int32_t init_maxiters; /* 500   */
+    int32_t _pad;
+} cb200_tran_opts;
+
+/* Counters of the most recent call (all device times from CUDA events on the
+ * library's own stream).                                                      */
+typedef struct cb200_stats {
+    double  kernel_ms;         /* sum of kernel time of the last dc/tran call   */
+    double  h2d_ms, d2h_ms;    /* copies done inside the last call              */
+    int64_t launches;          /* kernels launched by the last call             */
+    int64_t newton_iters;      /* sum over lanes                                */
+    int64_t steps_accepted;    /* sum over lanes                                */
+    int64_t steps_rejected;    /* sum over lanes (adaptive)                     */
+    int64_t h2d_bytes, d2h_bytes;
+} cb200_stats;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+/* Replaces compile_structure + create_workspace (src/mna/precompile.jl:312-443,
+ * :193): builds the unified G|C CSC pattern (sparse() semantics: rows sorted per
+ * column, duplicates merged, explicit zeros kept), COO->nz maps, deferred-b
+ * rows, diagonal map, and uploads the device table.  `device` is the CUDA
+ * ordinal (one handle per GPU).  Copies everything; caller keeps ownership.   */
+int cb200_create(const cb200_desc *desc, int32_t device, cb200_handle **out);
+void cb200_destroy(cb200_handle *h);
+const char *cb200_last_error(const cb200_handle *h);   /* h may be NULL       */
+int cb200_abi_version(void);
+
+/* Structure getters so a host that owns a CompiledStructure can check parity
+ * (precompile.jl:253-283, :350-366, :451-467).  Arrays are int64 1-based.
+ * Pass NULL pointers to query sizes only.                                     */
+int cb200_get_pattern(const cb200_handle *h, int64_t *n, int64_t *nnz,
+                      int64_t *colptr /*[n+1]*/, int64_t *rowval /*[nnz]*/);
+int cb200_get_maps(const cb200_handle *h, int64_t *G_coo_to_idx /*[nG]*/,
+                   int64_t *C_coo_to_idx /*[nC]*/, int64_t *b_rows /*[nb]*/,
+                   int64_t *G_diag_idx /*[n_nodes]*/);
+
+/* Replaces alter() per sweep point (src/mna/solve.jl:1719-1732; sweeps.jl:515,
+ * :696): lane parameters as a struct of arrays soa[col*P + lane], host memory. */
+int cb200_set_lanes(cb200_handle *h, int64_t P, int32_t n_cols, const double *soa);
+
+/* Host symbolic phase of the linear solver that replaces KLU's analyze step
+ * (call sites src/mna/solve.jl:612-613; sweeps.jl:600): probes |J| on sample
+ * lanes, chooses a static pivot sequence (threshold Markowitz), computes fill
+ * and the elimination schedule, uploads it.  gamma is the C-matrix weight the
+ * probe uses (0 for DC, 1/dt for transient).  Called implicitly by dc/tran
+ * when the schedule for that gamma class is missing.                          */
+int cb200_analyze(cb200_handle *h, const cb200_spec *spec, double gamma);
+/* perm arrays are int64 1-based: pivot k eliminates row rowperm[k], col colperm[k]. */
+int cb200_get_pivot_order(const cb200_handle *h, int64_t *rowperm, int64_t *colperm,
+                          int64_t *nnz_lu);
+
+/* ---- evaluation only: fast_rebuild! (src/mna/precompile.jl:493-537) ------ */
+/* x: [n][P] host (lane fastest) or NULL for ZERO_VECTOR; outputs host arrays
+ * G_nz,C_nz: [nnz][P], b: [n][P]; any output may be NULL.  initjct arms the
+ * PCNR seed evaluation (devices.jl:1217-1222).  limit_w_out: [n_limits][P].   */
+int cb200_eval(cb200_handle *h, const cb200_spec *spec, double t, int32_t initjct,
+               const double *x, double *G_nz, double *C_nz, double *b,
+               double *limit_w_out);
+
+/* ---- dc!(::CircuitSweep) (src/sweeps.jl:511-532; solve.jl:871-929) -------- */
+/* u0: NULL (cold start, zeros) or [n][P]; x_out [n][P]; status/iters [P].     */
+int cb200_dc(cb200_handle *h, const cb200_spec *spec, const cb200_dc_opts *opts,
+             const double *u0, double *x_out, int32_t *status, int32_t *iters);
+
+/* ---- tran!(::CircuitSweep, tspan) (src/sweeps.jl:692-707, :588-665) ------- */
+/* save_idx: 1-based unknown indices to record.  The waveform stays in HBM
+ * inside *out until fetched.  u0 [n][P] is used only when opts->init == 1.    */
+int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
+               const cb200_tran_opts *opts, const int64_t *save_idx, int32_t n_save,
+               const double *u0, cb200_wave **out);
+
+/* Wave accessors.  Fixed-step layout is u[save][T][P] with a shared t[T];
+ * adaptive layout is u[save][max_points][P] plus t[max_points][P] and count[P]. */
+int cb200_wave_info(const cb200_wave *w, int64_t *T, int64_t *P, int32_t *n_save,
+                    int32_t *adaptive);
+int cb200_wave_fetch(cb200_wave *w, double *t /*[T] or [T][P]*/, double *u,
+                     int32_t *count /*[P] or NULL*/, int32_t *status /*[P]*/,
+                     int32_t *newton_iters /*[P]*/);
+/* final state u(t1) of every lane, [n][P]                                      */
+int cb200_wave_final_state(cb200_wave *w, double *x_out);
+void cb200_wave_free(cb200_wave *w);
+
+int cb200_get_stats(const cb200_handle *h, cb200_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CADNIP_B200_H */

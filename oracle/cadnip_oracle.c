@@ -1,0 +1,1575 @@
+/*
+ * cadnip_oracle.c -- CPU restatement of Cadnip.jl's MNA Newton/transient hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see cadnip_oracle.h).  Plain C, no dependency on the
+ * product.  Control flow deliberately follows the reference: structure is
+ * discovered by *running* the builder against a COO-recording context
+ * (MNAContext), compiled to CSC + positional stamp maps (CompiledStructure), and
+ * every Newton iteration re-runs the builder against a value-only context that
+ * writes nzval[map[pos++]] += v (DirectStampContext).
+ *
+ * "parity unpinned" (not in the reference tree, versions un-pinned): KLU pivot
+ * order (a dense partial-pivoting LU stands in), NonlinearSolve globalisation
+ * (plain Newton stands in), Sundials/OrdinaryDiffEq step control (own fixed-step
+ * BE/trap/Gear-2 and LTE controller, stated in DESIGN.md).
+ *
+ * All paths cited are relative to the reference repository root.
+ */
+#include "cadnip_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* typed indices: src/mna/context.jl:40-101                                   */
+/* ------------------------------------------------------------------------- */
+enum { IX_GROUND = 0, IX_NODE = 1, IX_CURRENT = 2, IX_CHARGE = 3, IX_LIMIT = 4 };
+typedef struct { int32_t type; int64_t k; } mna_index;
+
+static mna_index ix_node(int64_t i)
+{
+    mna_index r; r.type = i == 0 ? IX_GROUND : IX_NODE; r.k = i; return r;
+}
+static mna_index ix_make(int type, int64_t k) { mna_index r; r.type = type; r.k = k; return r; }
+static int ix_iszero(mna_index i) { return i.type == IX_GROUND; }   /* context.jl:95-99 */
+
+/* ------------------------------------------------------------------------- */
+/* context: MNAContext (context.jl:248-372) and DirectStampContext
+ * (value_only.jl:42-96) behind one struct, as the AnyMNAContext union.        */
+/* ------------------------------------------------------------------------- */
+struct ora_ctx {
+    int direct;                       /* 0: MNAContext, 1: DirectStampContext */
+    int64_t n_nodes, n_currents, n_charges, n_limits;
+    /* COO accumulators */
+    mna_index *G_I, *G_J; double *G_V; int64_t nG, capG;
+    mna_index *C_I, *C_J; double *C_V; int64_t nC, capC;
+    mna_index *b_I;       double *b_V; int64_t nb, capb;
+    double *limit_init, *limit_w; int64_t capL;
+    int initjct;
+    /* DirectStampContext part (value_only.jl:42-96) */
+    double *G_nzval, *C_nzval, *b;            /* storage owned by the workspace */
+    const int64_t *G_mapping, *C_mapping;     /* 1-based nz index, 0 = skip     */
+    int64_t lenG, lenC, lenb;
+    int64_t G_pos, C_pos, b_pos, current_pos, limit_pos;
+};
+
+static void *xrealloc(void *p, size_t sz)
+{
+    void *q = realloc(p, sz ? sz : 1);
+    if (!q) { fprintf(stderr, "cadnip_oracle: out of memory\n"); abort(); }
+    return q;
+}
+
+static ora_ctx *ctx_new(void)
+{
+    ora_ctx *c = (ora_ctx *)calloc(1, sizeof(ora_ctx));
+    if (!c) abort();
+    return c;
+}
+
+void ora_ctx_free(ora_ctx *c)
+{
+    if (!c) return;
+    free(c->G_I); free(c->G_J); free(c->G_V);
+    free(c->C_I); free(c->C_J); free(c->C_V);
+    free(c->b_I); free(c->b_V);
+    free(c->limit_init); free(c->limit_w);
+    free(c);
+}
+
+/* reset_for_restamping!  context.jl:1528-1596 */
+static void ctx_reset_for_restamping(ora_ctx *c, int64_t n_nodes_prealloc)
+{
+    c->n_nodes = n_nodes_prealloc;   /* the builder's get_node! calls re-create them */
+    c->n_currents = 0; c->n_charges = 0; c->n_limits = 0;
+    c->nG = c->nC = c->nb = 0;
+}
+
+/* resolve_index  context.jl:577-581 / value_only.jl:214-231 */
+static int64_t resolve_index(const ora_ctx *c, mna_index i)
+{
+    switch (i.type) {
+    case IX_NODE:    return i.k;
+    case IX_CURRENT: return c->n_nodes + i.k;
+    case IX_CHARGE:  return c->n_nodes + c->n_currents + i.k;
+    case IX_LIMIT:   return c->n_nodes + c->n_currents + c->n_charges + i.k;
+    default:         return 0;
+    }
+}
+
+/* alloc_current!  context.jl:523-527 ; value_only.jl (counter based) */
+static mna_index alloc_current(ora_ctx *c)
+{
+    if (c->direct) { int64_t pos = c->current_pos++; return ix_make(IX_CURRENT, pos); }
+    c->n_currents += 1;
+    return ix_make(IX_CURRENT, c->n_currents);
+}
+
+/* alloc_limit!  context.jl:826-833 ; DirectStampContext: positional */
+static mna_index alloc_limit(ora_ctx *c, double init)
+{
+    if (c->direct) { int64_t pos = c->limit_pos++; return ix_make(IX_LIMIT, pos); }
+    c->n_limits += 1;
+    if (c->n_limits > c->capL) {
+        c->capL = c->capL ? 2 * c->capL : 8;
+        c->limit_init = (double *)xrealloc(c->limit_init, sizeof(double) * c->capL);
+        c->limit_w = (double *)xrealloc(c->limit_w, sizeof(double) * c->capL);
+    }
+    c->limit_init[c->n_limits - 1] = init;
+    c->limit_w[c->n_limits - 1] = init;
+    return ix_make(IX_LIMIT, c->n_limits);
+}
+
+/* record_limit_w!  context.jl:862-865 */
+static void record_limit_w(ora_ctx *c, mna_index l, double w) { c->limit_w[l.k - 1] = w; }
+
+/* stamp_G!  context.jl:945-953 (MNAContext) ; value_only.jl:395-421 (direct) */
+static void stamp_G(ora_ctx *c, mna_index i, mna_index j, double v)
+{
+    if (ix_iszero(i)) return;
+    if (ix_iszero(j)) return;
+    if (c->direct) {
+        int64_t pos = c->G_pos++;                 /* 1-based position          */
+        if (pos > c->lenG) return;                /* overflow stamps dropped   */
+        int64_t nz = c->G_mapping[pos - 1];
+        if (nz > 0) c->G_nzval[nz - 1] += v;
+        return;
+    }
+    if (c->nG == c->capG) {
+        c->capG = c->capG ? 2 * c->capG : 64;
+        c->G_I = (mna_index *)xrealloc(c->G_I, sizeof(mna_index) * c->capG);
+        c->G_J = (mna_index *)xrealloc(c->G_J, sizeof(mna_index) * c->capG);
+        c->G_V = (double *)xrealloc(c->G_V, sizeof(double) * c->capG);
+    }
+    c->G_I[c->nG] = i; c->G_J[c->nG] = j; c->G_V[c->nG] = v; c->nG++;
+}
+
+/* stamp_C!  context.jl:971-979 ; value_only.jl:428-450 */
+static void stamp_C(ora_ctx *c, mna_index i, mna_index j, double v)
+{
+    if (ix_iszero(i)) return;
+    if (ix_iszero(j)) return;
+    if (c->direct) {
+        int64_t pos = c->C_pos++;
+        if (pos > c->lenC) return;
+        int64_t nz = c->C_mapping[pos - 1];
+        if (nz > 0) c->C_nzval[nz - 1] += v;
+        return;
+    }
+    if (c->nC == c->capC) {
+        c->capC = c->capC ? 2 * c->capC : 64;
+        c->C_I = (mna_index *)xrealloc(c->C_I, sizeof(mna_index) * c->capC);
+        c->C_J = (mna_index *)xrealloc(c->C_J, sizeof(mna_index) * c->capC);
+        c->C_V = (double *)xrealloc(c->C_V, sizeof(double) * c->capC);
+    }
+    c->C_I[c->nC] = i; c->C_J[c->nC] = j; c->C_V[c->nC] = v; c->nC++;
+}
+
+/* stamp_b!  context.jl:994-999 ; value_only.jl:458-478 (deferred, b_V[pos] = v) */
+static void stamp_b(ora_ctx *c, mna_index i, double v)
+{
+    if (ix_iszero(i)) return;
+    if (c->direct) {
+        int64_t pos = c->b_pos++;
+        if (pos > c->lenb) return;
+        c->b_V[pos - 1] = v;
+        return;
+    }
+    if (c->nb == c->capb) {
+        c->capb = c->capb ? 2 * c->capb : 64;
+        c->b_I = (mna_index *)xrealloc(c->b_I, sizeof(mna_index) * c->capb);
+        c->b_V = (double *)xrealloc(c->b_V, sizeof(double) * c->capb);
+    }
+    c->b_I[c->nb] = i; c->b_V[c->nb] = v; c->nb++;
+}
+
+/* stamp_conductance! / stamp_capacitance!  context.jl:1362-1385 */
+static void stamp_conductance(ora_ctx *c, int64_t p, int64_t n, double G)
+{
+    stamp_G(c, ix_node(p), ix_node(p),  G);
+    stamp_G(c, ix_node(p), ix_node(n), -G);
+    stamp_G(c, ix_node(n), ix_node(p), -G);
+    stamp_G(c, ix_node(n), ix_node(n),  G);
+}
+static void stamp_capacitance(ora_ctx *c, int64_t p, int64_t n, double C)
+{
+    stamp_C(c, ix_node(p), ix_node(p),  C);
+    stamp_C(c, ix_node(p), ix_node(n), -C);
+    stamp_C(c, ix_node(n), ix_node(p), -C);
+    stamp_C(c, ix_node(n), ix_node(n),  C);
+}
+
+/* ------------------------------------------------------------------------- */
+/* waveforms  src/mna/devices.jl:30-216                                       */
+/* ------------------------------------------------------------------------- */
+
+/* find_t_in_ts  devices.jl:30-36 : searchsortedfirst, then step past an exact hit */
+static int find_t_in_ts(const double *ts, int n, double t)
+{
+    int lo = 0, hi = n;                 /* first index with ts[idx] >= t (0-based) */
+    while (lo < hi) { int mid = (lo + hi) / 2; if (ts[mid] < t) lo = mid + 1; else hi = mid; }
+    int idx = lo + 1;                   /* 1-based */
+    if (idx <= n && ts[idx - 1] == t) return idx + 1;
+    return idx;
+}
+
+/* pwl_at_time  devices.jl:47-71 */
+double ora_pwl_at_time(const double *ts, const double *ys, int n, double t)
+{
+    int i = find_t_in_ts(ts, n, t);     /* 1-based */
+    if (i <= 1) return ys[0];
+    if (i > n) return ys[n - 1];
+    if (ys[i - 2] == ys[i - 1]) return ys[i - 1];
+    if (ts[i - 1] == ts[i - 2]) return (ys[i - 2] + ys[i - 1]) / 2;
+    double slope = (ys[i - 1] - ys[i - 2]) / (ts[i - 1] - ts[i - 2]);
+    return ys[i - 2] + (t - ts[i - 2]) * slope;
+}
+
+/* Julia mod(x, y) for y > 0: result has the sign of y */
+static double jl_mod(double x, double y)
+{
+    double r = fmod(x, y);
+    if (r != 0.0 && ((r < 0.0) != (y < 0.0))) r += y;
+    return r;
+}
+
+/* pulse_at_time  devices.jl:85-103 */
+double ora_pulse_at_time(double v1, double v2, double td, double tr, double tf,
+                         double pw, double per, double t)
+{
+    if (t < td) return v1;
+    double phase = per > 0 ? jl_mod(t - td, per) : (t - td);
+    if (phase < tr) return tr > 0 ? v1 + (v2 - v1) * (phase / tr) : v2;
+    else if (phase < tr + pw) return v2;
+    else if (phase < tr + pw + tf) return tf > 0 ? v2 + (v1 - v2) * ((phase - tr - pw) / tf) : v1;
+    else return v1;
+}
+
+/* sind: Julia Base.sind (third-party to the reference: Julia stdlib).  Restated
+ * as its published algorithm: exact reduction rem(x,360), octant folding, then
+ * sin/cos of the folded angle in radians.                                      */
+double ora_sind(double x)
+{
+    const double d2r = 0.017453292519943295;   /* pi/180 */
+    if (isnan(x) || isinf(x)) return NAN;
+    double rx = copysign(fmod(x, 360.0), x);
+    double arx = fabs(rx);
+    if (rx == 0.0) return rx;
+    else if (arx < 45.0) return sin(rx * d2r);
+    else if (arx <= 135.0) return copysign(cos((90.0 - arx) * d2r), rx);
+    else if (arx == 180.0) return copysign(0.0, rx);
+    else if (arx < 225.0) return sin(((180.0 - arx) * (rx < 0 ? -1.0 : 1.0)) * d2r);
+    else if (arx <= 315.0) return -copysign(cos((270.0 - arx) * d2r), rx);
+    else return sin((rx - copysign(360.0, rx)) * d2r);
+}
+
+/* SinWave  devices.jl:168-174 */
+double ora_sin_wave(double vo, double va, double freq, double td, double theta,
+                    double phase, double t)
+{
+    if (t < td) return vo + va * ora_sind(phase);
+    return vo + va * exp(-theta * (t - td)) * ora_sind(360 * freq * (t - td) + phase);
+}
+
+/* get_source_value  devices.jl:352-360, :396-404.  par = [dc, wave params...] */
+static double source_value(int wave, const double *par, int npar, double t, int mode)
+{
+    if (wave == ORA_WAVE_NONE) return par[0];
+    if (mode == ORA_MODE_DCOP || mode == ORA_MODE_AC) return par[0];
+    const double *w = par + 1;
+    int nw = npar - 1;
+    switch (wave) {
+    case ORA_WAVE_PWL: {
+        int np = nw / 2;
+        double ts[64], ys[64];
+        double *pts = ts, *pys = ys, *heap = NULL;
+        if (np > 64) { heap = (double *)xrealloc(NULL, sizeof(double) * 2 * np); pts = heap; pys = heap + np; }
+        for (int i = 0; i < np; i++) { pts[i] = w[2 * i]; pys[i] = w[2 * i + 1]; }
+        double v = ora_pwl_at_time(pts, pys, np, t);
+        free(heap);
+        return v;
+    }
+    case ORA_WAVE_PULSE: return ora_pulse_at_time(w[0], w[1], w[2], w[3], w[4], w[5], w[6], t);
+    case ORA_WAVE_SIN:   return ora_sin_wave(w[0], w[1], w[2], w[3], w[4], w[5], t);
+    default: return par[0];
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* limiting primitives  src/mna/devices.jl:1169-1258                          */
+/* ------------------------------------------------------------------------- */
+
+/* pnjlim  devices.jl:1169-1189 */
+double ora_pnjlim(double vnew, double vold, double vt, double vcrit, int *limited)
+{
+    int lim = 0;
+    double r = vnew;
+    if (vnew > vcrit && fabs(vnew - vold) > vt + vt) {
+        if (vold > 0.0) {
+            double arg = (vnew - vold) / vt;
+            if (arg > 0.0) r = vold + vt * (2.0 + log(arg - 2.0));
+            else r = vold - vt * (2.0 + log(2.0 - arg));
+        } else {
+            r = vt * log(vnew / vt);
+        }
+        lim = 1;
+    } else if (vnew < 0.0) {
+        double arg = vold > 0.0 ? -vold - 1.0 : 2.0 * vold - 1.0;
+        if (vnew < arg) { r = arg; lim = 1; }
+    }
+    if (limited) *limited = lim;
+    return r;
+}
+
+/* _diode_iv  devices.jl:1333-1345 */
+void ora_diode_iv(double Is, double nVt, double v, double *I0, double *Gd)
+{
+    double xarg = v / nVt;
+    if (xarg > 80.0) {
+        double e80 = exp(80.0);
+        *I0 = Is * (e80 * (1.0 + (xarg - 80.0)) - 1.0);
+        *Gd = Is / nVt * e80;
+    } else {
+        double expterm = exp(xarg);
+        *I0 = Is * (expterm - 1.0);
+        *Gd = Is / nVt * expterm;
+    }
+}
+
+/* Diode constructor  devices.jl:1319-1320 */
+double ora_diode_vcrit(double Is, double Vt, double n)
+{
+    double nVt = n * Vt;
+    return nVt * log(nVt / (sqrt(2.0) * Is));
+}
+
+/* limit!  devices.jl:1209-1234, with fn = pnjlim(vn, vo, nVt, vcrit)[1] */
+static double limit_pnjlim(ora_ctx *c, int64_t p, int64_t n, double vnew, const double *x,
+                           int64_t nx, double nVt, double vcrit, double init)
+{
+    mna_index lidx = alloc_limit(c, init);
+    int64_t li = resolve_index(c, lidx);
+    /* ZERO_VECTOR / empty x is the only legitimate short x (devices.jl:1213-1216) */
+    double vold = (x == NULL || nx == 0) ? 0.0 : x[li - 1];
+    double w;
+    if (c->initjct) w = vnew - vnew + init;      /* devices.jl:1217-1222 */
+    else w = ora_pnjlim(vnew, vold, nVt, vcrit, NULL);
+    record_limit_w(c, lidx, w);
+    stamp_G(c, lidx, lidx, 1.0);
+    stamp_G(c, lidx, ix_node(p), -1.0);
+    stamp_G(c, lidx, ix_node(n), 1.0);
+    return w;
+}
+
+/* stamp_limited_companion!  devices.jl:1251-1258 */
+static void stamp_limited_companion(ora_ctx *c, int64_t p, int64_t n, double w, double I0, double Gd)
+{
+    stamp_conductance(c, p, n, Gd);
+    double Ieq = I0 - Gd * w;
+    stamp_b(c, ix_node(p), -Ieq);
+    stamp_b(c, ix_node(n),  Ieq);
+}
+
+static double xval(const double *x, int64_t nx, int64_t i)
+{
+    /* Vp = p == 0 ? 0.0 : (isempty(x) ? 0.0 : x[p])   devices.jl:1373 */
+    if (i == 0 || x == NULL || nx == 0) return 0.0;
+    return x[i - 1];
+}
+
+/* diode_junction_cap  devices.jl:1505-1516 */
+static double diode_junction_cap(double V, double Cj0, double Vj, double m)
+{
+    double Vmax = 0.9 * Vj;
+    if (V < Vmax) return Cj0 / pow(1 - V / Vj, m);
+    double C_at_max = Cj0 / pow(1 - Vmax / Vj, m);
+    double dC_dV = Cj0 * m / Vj / pow(1 - Vmax / Vj, m + 1);
+    return C_at_max + dC_dV * (V - Vmax);
+}
+
+/* ------------------------------------------------------------------------- */
+/* the builder: one stamp! call per netlist row, in order                      */
+/* ------------------------------------------------------------------------- */
+static void run_builder(const ora_netlist *nl, const ora_spec *spec, double t,
+                        const double *x, int64_t nx, ora_ctx *c)
+{
+    for (int d = 0; d < nl->n_dev; d++) {
+        const int32_t *nd = nl->nodes + nl->node_ptr[d];
+        const double *par = nl->par + nl->par_ptr[d];
+        int npar = nl->par_ptr[d + 1] - nl->par_ptr[d];
+        int flags = nl->flags[d];
+        switch (nl->kind[d]) {
+        case ORA_DEV_RESISTOR: {          /* devices.jl:498-510 */
+            double G = 1.0 / par[0];
+            stamp_conductance(c, nd[0], nd[1], G);
+        } break;
+        case ORA_DEV_CAPACITOR:           /* devices.jl:531-534 */
+            stamp_capacitance(c, nd[0], nd[1], par[0]);
+            break;
+        case ORA_DEV_INDUCTOR: {          /* devices.jl:569-586 */
+            mna_index I = alloc_current(c);
+            mna_index p = ix_node(nd[0]), n = ix_node(nd[1]);
+            stamp_G(c, p, I, 1.0);
+            stamp_G(c, n, I, -1.0);
+            stamp_G(c, I, p, 1.0);
+            stamp_G(c, I, n, -1.0);
+            stamp_C(c, I, I, -par[0]);
+        } break;
+        case ORA_DEV_VSOURCE: {           /* devices.jl:643-663 */
+            mna_index I = alloc_current(c);
+            mna_index p = ix_node(nd[0]), n = ix_node(nd[1]);
+            stamp_G(c, p, I, 1.0);
+            stamp_G(c, n, I, -1.0);
+            stamp_G(c, I, p, 1.0);
+            stamp_G(c, I, n, -1.0);
+            double v = source_value(flags, par, npar, t, spec->mode);
+            stamp_b(c, I, v);
+        } break;
+        case ORA_DEV_ISOURCE: {           /* devices.jl:719-737 */
+            double i = source_value(flags, par, npar, t, spec->mode);
+            stamp_b(c, ix_node(nd[0]), i);
+            stamp_b(c, ix_node(nd[1]), -i);
+        } break;
+        case ORA_DEV_VCVS: {              /* devices.jl:760-775 */
+            mna_index I = alloc_current(c);
+            mna_index op = ix_node(nd[0]), on = ix_node(nd[1]);
+            mna_index ip = ix_node(nd[2]), in = ix_node(nd[3]);
+            stamp_G(c, op, I, 1.0);
+            stamp_G(c, on, I, -1.0);
+            stamp_G(c, I, op, 1.0);
+            stamp_G(c, I, on, -1.0);
+            stamp_G(c, I, ip, -par[0]);
+            stamp_G(c, I, in, par[0]);
+        } break;
+        case ORA_DEV_VCCS: {              /* devices.jl:797-808 */
+            double gm = par[0];
+            mna_index op = ix_node(nd[0]), on = ix_node(nd[1]);
+            mna_index ip = ix_node(nd[2]), in = ix_node(nd[3]);
+            stamp_G(c, op, ip, -gm);
+            stamp_G(c, op, in, gm);
+            stamp_G(c, on, ip, gm);
+            stamp_G(c, on, in, -gm);
+        } break;
+        case ORA_DEV_CCVS: {
+            if (flags == 0) {             /* devices.jl:824-849 */
+                mna_index Iin = alloc_current(c);
+                mna_index Iout = alloc_current(c);
+                mna_index op = ix_node(nd[0]), on = ix_node(nd[1]);
+                mna_index ip = ix_node(nd[2]), in = ix_node(nd[3]);
+                stamp_G(c, ip, Iin, 1.0);
+                stamp_G(c, in, Iin, -1.0);
+                stamp_G(c, Iin, ip, 1.0);
+                stamp_G(c, Iin, in, -1.0);
+                stamp_G(c, op, Iout, 1.0);
+                stamp_G(c, on, Iout, -1.0);
+                stamp_G(c, Iout, op, 1.0);
+                stamp_G(c, Iout, on, -1.0);
+                stamp_G(c, Iout, Iin, -par[0]);
+            } else {                      /* devices.jl:898-913 (existing current) */
+                mna_index Iin = ix_make(IX_CURRENT, nd[2]);
+                mna_index Iout = alloc_current(c);
+                mna_index op = ix_node(nd[0]), on = ix_node(nd[1]);
+                stamp_G(c, op, Iout, 1.0);
+                stamp_G(c, on, Iout, -1.0);
+                stamp_G(c, Iout, op, 1.0);
+                stamp_G(c, Iout, on, -1.0);
+                stamp_G(c, Iout, Iin, -par[0]);
+            }
+        } break;
+        case ORA_DEV_CCCS: {
+            if (flags == 0) {             /* devices.jl:865-881 */
+                mna_index Iin = alloc_current(c);
+                mna_index op = ix_node(nd[0]), on = ix_node(nd[1]);
+                mna_index ip = ix_node(nd[2]), in = ix_node(nd[3]);
+                stamp_G(c, ip, Iin, 1.0);
+                stamp_G(c, in, Iin, -1.0);
+                stamp_G(c, Iin, ip, 1.0);
+                stamp_G(c, Iin, in, -1.0);
+                stamp_G(c, op, Iin, -par[0]);
+                stamp_G(c, on, Iin, par[0]);
+            } else {                      /* devices.jl:924-931 */
+                mna_index Iin = ix_make(IX_CURRENT, nd[2]);
+                stamp_G(c, ix_node(nd[0]), Iin, -par[0]);
+                stamp_G(c, ix_node(nd[1]), Iin, par[0]);
+            }
+        } break;
+        case ORA_DEV_DIODE: {             /* devices.jl:1370-1428 */
+            int64_t p = nd[0], n = nd[1];
+            double V0 = xval(x, nx, p) - xval(x, nx, n);
+            double Is = par[0], Vt = par[1], nf = par[2];
+            double nVt = nf * Vt;
+            if (flags & 1) {
+                double vcrit = par[3];
+                double w = limit_pnjlim(c, p, n, V0, x, nx, nVt, vcrit, vcrit);
+                double I0, Gd;
+                ora_diode_iv(Is, nVt, w, &I0, &Gd);
+                stamp_limited_companion(c, p, n, w, I0, Gd);
+            } else {
+                double expterm = exp(V0 / nVt);
+                double I0 = Is * (expterm - 1.0);
+                double Gd = Is / nVt * expterm;
+                double Ieq = I0 - Gd * V0;
+                stamp_conductance(c, p, n, Gd);
+                stamp_b(c, ix_node(p), -Ieq);
+                stamp_b(c, ix_node(n), Ieq);
+            }
+        } break;
+        case ORA_DEV_DIODECAP: {          /* devices.jl:1558-1602 */
+            int64_t p = nd[0], n = nd[1];
+            double V0 = xval(x, nx, p) - xval(x, nx, n);
+            double Is = par[0], Vt = par[1], nf = par[2];
+            double nVt = nf * Vt;
+            double expterm = exp(V0 / nVt);
+            double I0 = Is * (expterm - 1.0);
+            double G = Is / nVt * expterm;
+            double Ieq = I0 - G * V0;
+            stamp_conductance(c, p, n, G);
+            stamp_b(c, ix_node(p), -Ieq);
+            stamp_b(c, ix_node(n), Ieq);
+            double Cj = diode_junction_cap(V0, par[3], par[4], par[5]);
+            stamp_capacitance(c, p, n, Cj);
+        } break;
+        case ORA_DEV_SIMPLEMOS: {         /* devices.jl:1667-1749 */
+            int64_t dd = nd[0], g = nd[1], s = nd[2];
+            double Vd = xval(x, nx, dd), Vg = xval(x, nx, g), Vs = xval(x, nx, s);
+            double Vgs = Vg - Vs, Vds = Vd - Vs;
+            double Vth = par[0], K = par[1], lambda = par[2];
+            double Ids, gm, gds;
+            if (Vgs <= Vth) { Ids = 0.0; gm = 0.0; gds = 0.0; }
+            else if (Vds <= Vgs - Vth) {
+                Ids = K * ((Vgs - Vth) * Vds - Vds * Vds / 2);
+                gm = K * Vds;
+                gds = K * (Vgs - Vth - Vds);
+            } else {
+                Ids = K / 2 * ((Vgs - Vth) * (Vgs - Vth)) * (1 + lambda * Vds);
+                gm = K * (Vgs - Vth) * (1 + lambda * Vds);
+                gds = K / 2 * ((Vgs - Vth) * (Vgs - Vth)) * lambda;
+            }
+            double Ieq = Ids - gm * Vgs - gds * Vds;
+            mna_index D = ix_node(dd), Gt = ix_node(g), S = ix_node(s);
+            stamp_G(c, D, D, gds);
+            stamp_G(c, D, Gt, gm);
+            stamp_G(c, D, S, -(gds + gm));
+            stamp_G(c, S, D, -gds);
+            stamp_G(c, S, Gt, -gm);
+            stamp_G(c, S, S, gds + gm);
+            stamp_b(c, D, -Ieq);
+            stamp_b(c, S, Ieq);
+            stamp_capacitance(c, g, s, par[4]);   /* Cgs */
+            stamp_capacitance(c, g, dd, par[3]);  /* Cgd */
+        } break;
+        default:
+            fprintf(stderr, "cadnip_oracle: unknown device kind %d\n", nl->kind[d]);
+            abort();
+        }
+    }
+}
+
+/* builder(params, spec, t; x, ctx=nothing) on a fresh MNAContext */
+ora_ctx *ora_build(const ora_netlist *nl, const ora_spec *spec, double t, const double *x,
+                   int64_t nx)
+{
+    ora_ctx *c = ctx_new();
+    ctx_reset_for_restamping(c, nl->n_nodes);
+    run_builder(nl, spec, t, x, nx, c);
+    return c;
+}
+
+/* xorshift64* -- stands in for MersenneTwister(0xDEADBEEF) (solve.jl:999): only
+ * the *outcome* of detection matters; for primitive devices the
+ * structure is independent of x.                                               */
+static double probe_rand(uint64_t *s)
+{
+    *s ^= *s >> 12; *s ^= *s << 25; *s ^= *s >> 27;
+    uint64_t r = *s * 2685821657736338717ULL;
+    return (double)(r >> 11) / 9007199254740992.0;
+}
+
+/* _detect_structure  solve.jl:992-1015 : 5 passes, pass 1 ZERO_VECTOR, then x in [-1,1] */
+ora_ctx *ora_detect_structure(const ora_netlist *nl, const ora_spec *spec)
+{
+    const int N_DETECTION_PASSES = 5;
+    ora_ctx *c = NULL;
+    uint64_t rng = 0xDEADBEEFULL;
+    for (int pass = 1; pass <= N_DETECTION_PASSES; pass++) {
+        if (c == NULL) {
+            c = ora_build(nl, spec, 0.0, NULL, 0);
+        } else {
+            int64_t known = c->n_nodes + c->n_currents + c->n_charges + c->n_limits;
+            double *x = (double *)xrealloc(NULL, sizeof(double) * (known + 1));
+            for (int64_t i = 0; i < known; i++) x[i] = (probe_rand(&rng) - 0.5) * 2.0;
+            ctx_reset_for_restamping(c, nl->n_nodes);
+            run_builder(nl, spec, 0.0, x, known, c);
+            free(x);
+        }
+    }
+    return c;
+}
+
+void ora_ctx_sizes(const ora_ctx *c, int64_t *n_nodes, int64_t *n_currents, int64_t *n_charges,
+                   int64_t *n_limits, int64_t *nG, int64_t *nC, int64_t *nb)
+{
+    if (n_nodes) *n_nodes = c->n_nodes;
+    if (n_currents) *n_currents = c->n_currents;
+    if (n_charges) *n_charges = c->n_charges;
+    if (n_limits) *n_limits = c->n_limits;
+    if (nG) *nG = c->nG;
+    if (nC) *nC = c->nC;
+    if (nb) *nb = c->nb;
+}
+
+void ora_ctx_coo(const ora_ctx *c, int64_t *G_I, int64_t *G_J, double *G_V, int64_t *C_I,
+                 int64_t *C_J, double *C_V, int64_t *b_I, double *b_V, double *limit_init)
+{
+    for (int64_t k = 0; k < c->nG; k++) {
+        if (G_I) G_I[k] = resolve_index(c, c->G_I[k]);
+        if (G_J) G_J[k] = resolve_index(c, c->G_J[k]);
+        if (G_V) G_V[k] = c->G_V[k];
+    }
+    for (int64_t k = 0; k < c->nC; k++) {
+        if (C_I) C_I[k] = resolve_index(c, c->C_I[k]);
+        if (C_J) C_J[k] = resolve_index(c, c->C_J[k]);
+        if (C_V) C_V[k] = c->C_V[k];
+    }
+    for (int64_t k = 0; k < c->nb; k++) {
+        if (b_I) b_I[k] = resolve_index(c, c->b_I[k]);
+        if (b_V) b_V[k] = c->b_V[k];
+    }
+    if (limit_init) for (int64_t k = 0; k < c->n_limits; k++) limit_init[k] = c->limit_init[k];
+}
+
+/* ------------------------------------------------------------------------- */
+/* sparse(I,J,V,n,n): CSC, rows ascending within a column, duplicates summed in
+ * input order, explicit zeros kept (Julia SparseArrays semantics; build.jl:117). */
+/* ------------------------------------------------------------------------- */
+int64_t ora_sparse_coo(int64_t n, int64_t ncoo, const int64_t *I, const int64_t *J,
+                       const double *V, int64_t *colptr, int64_t *rowval, double *nzval,
+                       int64_t *mapping)
+{
+    /* stable counting sort by (column, row) */
+    int64_t *cnt = (int64_t *)calloc((size_t)n + 2, sizeof(int64_t));
+    int64_t *ord = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (ncoo + 1));
+    int64_t *tmp = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (ncoo + 1));
+    /* pass 1: by row */
+    for (int64_t k = 0; k < ncoo; k++) cnt[I[k]]++;
+    { int64_t s = 0; for (int64_t r = 0; r <= n; r++) { int64_t c = cnt[r]; cnt[r] = s; s += c; } }
+    for (int64_t k = 0; k < ncoo; k++) tmp[cnt[I[k]]++] = k;
+    /* pass 2: by column (stable, so rows stay ascending inside a column) */
+    memset(cnt, 0, sizeof(int64_t) * (size_t)(n + 2));
+    for (int64_t k = 0; k < ncoo; k++) cnt[J[k]]++;
+    { int64_t s = 0; for (int64_t c = 0; c <= n; c++) { int64_t q = cnt[c]; cnt[c] = s; s += q; } }
+    for (int64_t q = 0; q < ncoo; q++) { int64_t k = tmp[q]; ord[cnt[J[k]]++] = k; }
+    /* merge duplicates */
+    int64_t nnz = 0;
+    for (int64_t c = 0; c <= n; c++) colptr[c] = 0;
+    int64_t prev_i = -1, prev_j = -1;
+    for (int64_t q = 0; q < ncoo; q++) {
+        int64_t k = ord[q];
+        if (I[k] == prev_i && J[k] == prev_j) {
+            if (nzval) nzval[nnz - 1] += V ? V[k] : 0.0;
+        } else {
+            rowval[nnz] = I[k];
+            if (nzval) nzval[nnz] = V ? V[k] : 0.0;
+            colptr[J[k]]++;            /* count per column (1-based col at slot J) */
+            nnz++;
+            prev_i = I[k]; prev_j = J[k];
+        }
+        if (mapping) mapping[k] = nnz;  /* provisional: 1-based nz index          */
+    }
+    /* colptr[j] currently holds count of column j at index j (1..n); make it Julia colptr */
+    {
+        int64_t s = 1;
+        for (int64_t c = 1; c <= n; c++) { int64_t q = colptr[c]; colptr[c - 1] = s; s += q; }
+        colptr[n] = s;
+    }
+    free(cnt); free(ord); free(tmp);
+    return nnz;
+}
+
+/* ------------------------------------------------------------------------- */
+/* CompiledStructure  precompile.jl:88-160, compile_structure :312-443         */
+/* ------------------------------------------------------------------------- */
+struct ora_structure {
+    ora_netlist nl;          /* shallow: caller keeps arrays alive */
+    int64_t n, n_nodes, n_currents, n_charges, n_limits;
+    int64_t nnz, nG, nC, nb;
+    int64_t *colptr, *rowval;          /* Julia 1-based */
+    double *G_nz0, *C_nz0;             /* values at discovery (padded to pattern) */
+    int64_t *G_coo_to_idx, *C_coo_to_idx, *b_deferred_resolved, *G_diag_idx;
+    double *limit_init;
+};
+
+/* compute_coo_to_nz_mapping  precompile.jl:253-283 : search the column */
+static void coo_to_nz_mapping(int64_t ncoo, const int64_t *I, const int64_t *J,
+                              const int64_t *colptr, const int64_t *rowval, int64_t *mapping)
+{
+    for (int64_t k = 0; k < ncoo; k++) {
+        mapping[k] = 0;
+        int64_t i = I[k], j = J[k];
+        if (i == 0 || j == 0) continue;
+        for (int64_t idx = colptr[j - 1]; idx <= colptr[j] - 1; idx++) {
+            if (rowval[idx - 1] == i) { mapping[k] = idx; break; }
+        }
+        if (mapping[k] == 0) { fprintf(stderr, "cadnip_oracle: COO entry not found\n"); abort(); }
+    }
+}
+
+ora_structure *ora_compile_structure(const ora_netlist *nl, const ora_spec *spec,
+                                     const ora_ctx *ctx0)
+{
+    (void)spec;
+    ora_structure *s = (ora_structure *)calloc(1, sizeof(ora_structure));
+    s->nl = *nl;
+    s->n_nodes = ctx0->n_nodes; s->n_currents = ctx0->n_currents;
+    s->n_charges = ctx0->n_charges; s->n_limits = ctx0->n_limits;
+    s->n = s->n_nodes + s->n_currents + s->n_charges + s->n_limits;
+    s->nG = ctx0->nG; s->nC = ctx0->nC; s->nb = ctx0->nb;
+    int64_t n = s->n, nG = s->nG, nC = s->nC, nb = s->nb;
+
+    int64_t *GI = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (nG + nC + 1));
+    int64_t *GJ = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (nG + nC + 1));
+    double *ones = (double *)xrealloc(NULL, sizeof(double) * (nG + nC + 1));
+    for (int64_t k = 0; k < nG; k++) { GI[k] = resolve_index(ctx0, ctx0->G_I[k]); GJ[k] = resolve_index(ctx0, ctx0->G_J[k]); }
+    /* jac_pattern = sparse(vcat(G_I, C_I), vcat(G_J, C_J), ones)  precompile.jl:410-414 */
+    for (int64_t k = 0; k < nC; k++) { GI[nG + k] = resolve_index(ctx0, ctx0->C_I[k]); GJ[nG + k] = resolve_index(ctx0, ctx0->C_J[k]); }
+    for (int64_t k = 0; k < nG + nC; k++) ones[k] = 1.0;
+
+    s->colptr = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (n + 2));
+    s->rowval = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (nG + nC + 1));
+    double *pat_nz = (double *)xrealloc(NULL, sizeof(double) * (nG + nC + 1));
+    s->nnz = ora_sparse_coo(n, nG + nC, GI, GJ, ones, s->colptr, s->rowval, pat_nz, NULL);
+
+    /* G = _pad_to_pattern(sparse(G_I,G_J,G_V)), same for C  precompile.jl:417-418:
+       equivalent to accumulating the COO values onto the unified pattern.       */
+    s->G_coo_to_idx = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (nG + 1));
+    s->C_coo_to_idx = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (nC + 1));
+    coo_to_nz_mapping(nG, GI, GJ, s->colptr, s->rowval, s->G_coo_to_idx);
+    coo_to_nz_mapping(nC, GI + nG, GJ + nG, s->colptr, s->rowval, s->C_coo_to_idx);
+    s->G_nz0 = (double *)calloc((size_t)s->nnz + 1, sizeof(double));
+    s->C_nz0 = (double *)calloc((size_t)s->nnz + 1, sizeof(double));
+    for (int64_t k = 0; k < nG; k++) s->G_nz0[s->G_coo_to_idx[k] - 1] += ctx0->G_V[k];
+    for (int64_t k = 0; k < nC; k++) s->C_nz0[s->C_coo_to_idx[k] - 1] += ctx0->C_V[k];
+
+    /* b_deferred_resolved  precompile.jl:350-366 */
+    s->b_deferred_resolved = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (nb + 1));
+    for (int64_t k = 0; k < nb; k++) s->b_deferred_resolved[k] = resolve_index(ctx0, ctx0->b_I[k]);
+
+    /* _compute_diag_nz_indices  precompile.jl:451-467 */
+    s->G_diag_idx = (int64_t *)calloc((size_t)s->n_nodes + 1, sizeof(int64_t));
+    for (int64_t col = 1; col <= s->n_nodes; col++) {
+        for (int64_t idx = s->colptr[col - 1]; idx <= s->colptr[col] - 1; idx++) {
+            if (s->rowval[idx - 1] == col) { s->G_diag_idx[col - 1] = idx; break; }
+        }
+    }
+    s->limit_init = (double *)calloc((size_t)s->n_limits + 1, sizeof(double));
+    for (int64_t k = 0; k < s->n_limits; k++) s->limit_init[k] = ctx0->limit_init[k];
+    free(GI); free(GJ); free(ones); free(pat_nz);
+    return s;
+}
+
+void ora_structure_free(ora_structure *s)
+{
+    if (!s) return;
+    free(s->colptr); free(s->rowval); free(s->G_nz0); free(s->C_nz0);
+    free(s->G_coo_to_idx); free(s->C_coo_to_idx); free(s->b_deferred_resolved);
+    free(s->G_diag_idx); free(s->limit_init);
+    free(s);
+}
+
+void ora_structure_sizes(const ora_structure *s, int64_t *n, int64_t *nnz)
+{
+    if (n) *n = s->n;
+    if (nnz) *nnz = s->nnz;
+}
+
+void ora_structure_arrays(const ora_structure *s, int64_t *colptr, int64_t *rowval,
+                          int64_t *G_coo_to_idx, int64_t *C_coo_to_idx, int64_t *b_resolved,
+                          int64_t *G_diag_idx, double *G_nz0, double *C_nz0)
+{
+    if (colptr) memcpy(colptr, s->colptr, sizeof(int64_t) * (s->n + 1));
+    if (rowval) memcpy(rowval, s->rowval, sizeof(int64_t) * s->nnz);
+    if (G_coo_to_idx) memcpy(G_coo_to_idx, s->G_coo_to_idx, sizeof(int64_t) * s->nG);
+    if (C_coo_to_idx) memcpy(C_coo_to_idx, s->C_coo_to_idx, sizeof(int64_t) * s->nC);
+    if (b_resolved) memcpy(b_resolved, s->b_deferred_resolved, sizeof(int64_t) * s->nb);
+    if (G_diag_idx) memcpy(G_diag_idx, s->G_diag_idx, sizeof(int64_t) * s->n_nodes);
+    if (G_nz0) memcpy(G_nz0, s->G_nz0, sizeof(double) * s->nnz);
+    if (C_nz0) memcpy(C_nz0, s->C_nz0, sizeof(double) * s->nnz);
+}
+
+/* ------------------------------------------------------------------------- */
+/* EvalWorkspace  precompile.jl:168-172, create_workspace :193                 */
+/* ------------------------------------------------------------------------- */
+struct ora_workspace {
+    ora_ctx dctx;                 /* DirectStampContext over the arrays below */
+    double *G_nz, *C_nz, *b, *b_V, *limit_w;
+    /* solver scratch */
+    double *F, *delta, *dense, *du, *Jnz;
+    int64_t *piv;
+    int64_t n, nnz;
+};
+
+ora_workspace *ora_create_workspace(const ora_structure *s)
+{
+    ora_workspace *w = (ora_workspace *)calloc(1, sizeof(ora_workspace));
+    w->n = s->n; w->nnz = s->nnz;
+    w->G_nz = (double *)calloc((size_t)s->nnz + 1, sizeof(double));
+    w->C_nz = (double *)calloc((size_t)s->nnz + 1, sizeof(double));
+    w->Jnz = (double *)calloc((size_t)s->nnz + 1, sizeof(double));
+    w->b = (double *)calloc((size_t)s->n + 1, sizeof(double));
+    w->b_V = (double *)calloc((size_t)s->nb + 1, sizeof(double));
+    w->limit_w = (double *)calloc((size_t)s->n_limits + 1, sizeof(double));
+    w->F = (double *)calloc((size_t)s->n + 1, sizeof(double));
+    w->delta = (double *)calloc((size_t)s->n + 1, sizeof(double));
+    w->du = (double *)calloc((size_t)s->n + 1, sizeof(double));
+    w->dense = (double *)calloc((size_t)(s->n * s->n) + 1, sizeof(double));
+    w->piv = (int64_t *)calloc((size_t)s->n + 1, sizeof(int64_t));
+    ora_ctx *d = &w->dctx;
+    d->direct = 1;
+    d->n_nodes = s->n_nodes; d->n_currents = s->n_currents;
+    d->n_charges = s->n_charges; d->n_limits = s->n_limits;
+    d->G_nzval = w->G_nz; d->C_nzval = w->C_nz; d->b = w->b; d->b_V = w->b_V;
+    d->limit_w = w->limit_w;
+    d->G_mapping = s->G_coo_to_idx; d->C_mapping = s->C_coo_to_idx;
+    d->lenG = s->nG; d->lenC = s->nC; d->lenb = s->nb;
+    for (int64_t k = 0; k < s->n_limits; k++) w->limit_w[k] = s->limit_init[k];
+    return w;
+}
+
+void ora_workspace_free(ora_workspace *w)
+{
+    if (!w) return;
+    free(w->G_nz); free(w->C_nz); free(w->Jnz); free(w->b); free(w->b_V); free(w->limit_w);
+    free(w->F); free(w->delta); free(w->du); free(w->dense); free(w->piv);
+    free(w);
+}
+
+/* reset_direct_stamp!  value_only.jl:238-261 */
+static void reset_direct_stamp(ora_workspace *w, const ora_structure *s)
+{
+    ora_ctx *d = &w->dctx;
+    d->G_pos = 1; d->C_pos = 1; d->b_pos = 1; d->current_pos = 1; d->limit_pos = 1;
+    memset(w->G_nz, 0, sizeof(double) * s->nnz);
+    memset(w->C_nz, 0, sizeof(double) * s->nnz);
+    memset(w->b, 0, sizeof(double) * s->n);
+    memset(w->b_V, 0, sizeof(double) * s->nb);
+}
+
+/* fast_rebuild!  precompile.jl:493-537 */
+static void fast_rebuild(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
+                         const double *u, double t)
+{
+    reset_direct_stamp(w, s);
+    run_builder(&s->nl, spec, t, u, s->n, &w->dctx);
+    for (int64_t k = 0; k < s->nb; k++) {            /* deferred b   :509-515 */
+        int64_t idx = s->b_deferred_resolved[k];
+        if (idx > 0) w->b[idx - 1] += w->b_V[k];
+    }
+    if (spec->srcFact < 1.0)                          /* :518-521 */
+        for (int64_t i = 0; i < s->n; i++) w->b[i] *= spec->srcFact;
+    if (spec->gshunt != 0.0)                          /* :524-534 */
+        for (int64_t i = 0; i < s->n_nodes; i++) {
+            int64_t idx = s->G_diag_idx[i];
+            if (idx > 0) w->G_nz[idx - 1] += spec->gshunt;
+        }
+}
+
+void ora_fast_rebuild(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
+                      const double *u, double t, int initjct, double *G_nz, double *C_nz,
+                      double *b, double *limit_w)
+{
+    w->dctx.initjct = initjct;
+    fast_rebuild(w, s, spec, u, t);
+    w->dctx.initjct = 0;
+    if (G_nz) memcpy(G_nz, w->G_nz, sizeof(double) * s->nnz);
+    if (C_nz) memcpy(C_nz, w->C_nz, sizeof(double) * s->nnz);
+    if (b) memcpy(b, w->b, sizeof(double) * s->n);
+    if (limit_w) memcpy(limit_w, w->limit_w, sizeof(double) * s->n_limits);
+}
+
+/* ------------------------------------------------------------------------- */
+/* linear algebra helpers                                                      */
+/* ------------------------------------------------------------------------- */
+
+/* y += A*x for CSC A on the unified pattern (mul!, precompile.jl:552-553) */
+static void csc_mul_add(const ora_structure *s, const double *nz, const double *x, double *y)
+{
+    for (int64_t j = 0; j < s->n; j++) {
+        double xj = x[j];
+        for (int64_t idx = s->colptr[j]; idx < s->colptr[j + 1]; idx++)
+            y[s->rowval[idx - 1] - 1] += nz[idx - 1] * xj;
+    }
+}
+
+static double norm2(const double *v, int64_t n)
+{
+    /* LinearAlgebra.norm: plain sqrt(sum of squares) for moderate magnitudes    */
+    double s = 0.0;
+    for (int64_t i = 0; i < n; i++) s += v[i] * v[i];
+    return sqrt(s);
+}
+
+static int all_finite(const double *v, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) if (!isfinite(v[i])) return 0;
+    return 1;
+}
+
+static int is_zero_vec(const double *v, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) if (v[i] != 0.0) return 0;
+    return 1;
+}
+
+/* Stand-in for KLU (call sites solve.jl:612-613, :667-670): dense LU with partial
+ * pivoting on the scattered CSC matrix.  Returns 0, or 1 if singular.           */
+static int dense_solve(ora_workspace *w, const ora_structure *s, const double *nz,
+                       const double *rhs, double *sol)
+{
+    int64_t n = s->n;
+    double *A = w->dense;
+    memset(A, 0, sizeof(double) * n * n);
+    for (int64_t j = 0; j < n; j++)
+        for (int64_t idx = s->colptr[j]; idx < s->colptr[j + 1]; idx++)
+            A[(s->rowval[idx - 1] - 1) * n + j] = nz[idx - 1];
+    for (int64_t i = 0; i < n; i++) sol[i] = rhs[i];
+    for (int64_t k = 0; k < n; k++) {
+        int64_t p = k; double best = fabs(A[k * n + k]);
+        for (int64_t i = k + 1; i < n; i++) { double a = fabs(A[i * n + k]); if (a > best) { best = a; p = i; } }
+        if (best == 0.0 || !isfinite(best)) return 1;
+        if (p != k) {
+            for (int64_t j = 0; j < n; j++) { double tq = A[k * n + j]; A[k * n + j] = A[p * n + j]; A[p * n + j] = tq; }
+            double tq = sol[k]; sol[k] = sol[p]; sol[p] = tq;
+        }
+        double piv = A[k * n + k];
+        for (int64_t i = k + 1; i < n; i++) {
+            double l = A[i * n + k];
+            if (l == 0.0) continue;
+            l /= piv;
+            A[i * n + k] = l;
+            for (int64_t j = k + 1; j < n; j++) A[i * n + j] -= l * A[k * n + j];
+            sol[i] -= l * sol[k];
+        }
+    }
+    for (int64_t k = n - 1; k >= 0; k--) {
+        double acc = sol[k];
+        for (int64_t j = k + 1; j < n; j++) acc -= A[k * n + j] * sol[j];
+        sol[k] = acc / A[k * n + k];
+    }
+    return 0;
+}
+
+/* F = G*u - b   (solve.jl:557-560, :630-631) */
+static void dc_residual(ora_workspace *w, const ora_structure *s, const double *u, double *F)
+{
+    for (int64_t i = 0; i < s->n; i++) F[i] = 0.0;
+    csc_mul_add(s, w->G_nz, u, F);
+    for (int64_t i = 0; i < s->n; i++) F[i] -= w->b[i];
+}
+
+/* ------------------------------------------------------------------------- */
+/* _dc_pcnr_newton  solve.jl:599-698                                           */
+/* ------------------------------------------------------------------------- */
+int ora_dc_pcnr_newton(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
+                       double *u, double abstol, int maxiters, int *iters)
+{
+    int64_t n = s->n, L = s->n_limits;
+    if (iters) *iters = 0;
+    if (L == 0) return 0;
+    int64_t lim0 = n - L;
+    double *F = w->F, *delta = w->delta;
+    if (is_zero_vec(u, n)) {                         /* :622-627 */
+        for (int64_t k = 0; k < L; k++) u[lim0 + k] = s->limit_init[k];
+        w->dctx.initjct = 1;
+    }
+    int converged = 0, it_out = maxiters;
+    for (int iter = 1; iter <= maxiters; iter++) {
+        fast_rebuild(w, s, spec, u, 0.0);
+        w->dctx.initjct = 0;
+        dc_residual(w, s, u, F);
+        if (!all_finite(F, n)) { it_out = iter - 1; goto done; }
+        if (norm2(F, n) < abstol) {                  /* :640-663 */
+            for (int64_t k = 0; k < L; k++) u[lim0 + k] = w->limit_w[k];
+            fast_rebuild(w, s, spec, u, 0.0);
+            dc_residual(w, s, u, F);
+            if (norm2(F, n) < abstol) { converged = 1; it_out = iter - 1; goto done; }
+        }
+        if (dense_solve(w, s, w->G_nz, F, delta)) { it_out = iter - 1; goto done; }
+        if (!all_finite(delta, n)) { it_out = iter - 1; goto done; }
+        for (int64_t i = 0; i < n; i++) u[i] -= delta[i];
+        for (int64_t k = 0; k < L; k++) u[lim0 + k] = w->limit_w[k];   /* CORRECT :686-689 */
+    }
+done:
+    w->dctx.initjct = 0;                             /* finally :693-697 */
+    if (iters) *iters = it_out;
+    return converged;
+}
+
+/* _dc_newton_compiled  solve.jl:542-578.  The reference hands the problem to
+ * NonlinearSolve's RobustMultiNewton polyalgorithm (third-party, un-vendored,
+ * "parity unpinned"); restated here as plain full-step Newton on
+ * F(u) = G(u)u - b(u), J = G(u), same abstol / maxiters / early-out.            */
+static int dc_newton_compiled(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
+                              double *u, double abstol, int maxiters, int *solves)
+{
+    int64_t n = s->n;
+    double *F = w->F, *delta = w->delta;
+    for (int iter = 0; iter <= maxiters; iter++) {
+        fast_rebuild(w, s, spec, u, 0.0);
+        dc_residual(w, s, u, F);
+        if (!all_finite(F, n)) return 0;
+        if (norm2(F, n) < abstol) return 1;
+        if (iter == maxiters) break;
+        if (dense_solve(w, s, w->G_nz, F, delta)) return 0;
+        if (!all_finite(delta, n)) return 0;
+        for (int64_t i = 0; i < n; i++) u[i] -= delta[i];
+        if (solves) (*solves)++;
+    }
+    return 0;
+}
+
+/* _gshunt_stepping  solve.jl:720-783 */
+static int gshunt_stepping(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
+                           double *u, double abstol, int maxiters, int *solves)
+{
+    int64_t n = s->n;
+    double target = spec->gshunt;
+    double cur = 1e-3, factor = 10.0;
+    const int max_steps = 20;
+    double gmin_thr = target > 1e-12 ? target : 1e-12;
+    double *saved = (double *)xrealloc(NULL, sizeof(double) * (n + 1));
+    double *trial = (double *)xrealloc(NULL, sizeof(double) * (n + 1));
+    memcpy(saved, u, sizeof(double) * n);
+    int converged = 0;
+    for (int step = 1; step <= max_steps; step++) {
+        ora_spec sp = *spec; sp.gshunt = cur;
+        memcpy(trial, u, sizeof(double) * n);
+        int ok = dc_newton_compiled(w, s, &sp, trial, abstol, maxiters, solves);
+        if (ok) {
+            memcpy(u, trial, sizeof(double) * n);
+            memcpy(saved, u, sizeof(double) * n);
+            if (cur <= gmin_thr) {
+                if (cur != target) {
+                    ora_spec sf = *spec; sf.gshunt = target;
+                    memcpy(trial, u, sizeof(double) * n);
+                    if (dc_newton_compiled(w, s, &sf, trial, abstol, maxiters, solves)) {
+                        memcpy(u, trial, sizeof(double) * n);
+                        converged = 1;
+                    }
+                } else converged = 1;
+                break;
+            }
+            cur /= factor;
+            if (cur < gmin_thr) cur = gmin_thr;
+        } else {
+            if (factor <= 1.5) break;
+            factor = sqrt(factor);
+            memcpy(u, saved, sizeof(double) * n);
+        }
+    }
+    free(saved); free(trial);
+    return converged;
+}
+
+/* _source_stepping  solve.jl:805-850 */
+static int source_stepping(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
+                           double *u, double abstol, int maxiters, int *solves)
+{
+    int64_t n = s->n;
+    double srcFact = 0.0, conv = 0.0, raise = 0.1;
+    const int max_steps = 50;
+    double *saved = (double *)xrealloc(NULL, sizeof(double) * (n + 1));
+    double *trial = (double *)xrealloc(NULL, sizeof(double) * (n + 1));
+    memcpy(saved, u, sizeof(double) * n);
+    int result = 0;
+    for (int step = 1; step <= max_steps; step++) {
+        ora_spec sp = *spec; sp.srcFact = srcFact;
+        memcpy(trial, u, sizeof(double) * n);
+        int ok = dc_newton_compiled(w, s, &sp, trial, abstol, maxiters, solves);
+        if (ok) {
+            conv = srcFact;
+            memcpy(u, trial, sizeof(double) * n);
+            memcpy(saved, u, sizeof(double) * n);
+            if (srcFact >= 1.0) { result = 1; break; }
+            srcFact = srcFact + raise < 1.0 ? srcFact + raise : 1.0;
+        } else {
+            if (srcFact - conv < 1e-6) break;
+            raise /= 2.0;
+            srcFact = conv + raise;
+            memcpy(u, saved, sizeof(double) * n);
+        }
+    }
+    free(saved); free(trial);
+    return result;
+}
+
+/* _dc_solve_with_fallbacks  solve.jl:871-929 */
+int ora_dc_solve_with_fallbacks(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
+                                double *u, double abstol, int maxiters, int use_stepping,
+                                int *total_iters)
+{
+    int64_t n = s->n;
+    int solves = 0;
+    if (total_iters) *total_iters = 0;
+    if (n == 0) return 1;
+    double *u0 = (double *)xrealloc(NULL, sizeof(double) * (n + 1));
+    memcpy(u0, u, sizeof(double) * n);
+    int converged = 0;
+    if (s->n_limits > 0) {                           /* tier 0: PCNR :887-899 */
+        int it = 0;
+        converged = ora_dc_pcnr_newton(w, s, spec, u, abstol, maxiters, &it);
+        solves += it;
+        if (converged) goto out;
+        memcpy(u, u0, sizeof(double) * n);           /* next tier restarts from u0 */
+    }
+    converged = dc_newton_compiled(w, s, spec, u, abstol, maxiters, &solves);   /* tier 1 */
+    if (converged || !use_stepping) goto out;
+    memset(u, 0, sizeof(double) * n);                /* tier 2 from zeros :911 */
+    converged = gshunt_stepping(w, s, spec, u, abstol, maxiters, &solves);
+    if (converged) goto out;
+    memset(u, 0, sizeof(double) * n);                /* tier 3 from zeros :920 */
+    converged = source_stepping(w, s, spec, u, abstol, maxiters, &solves);
+out:
+    free(u0);
+    if (total_iters) *total_iters = solves;
+    return converged;
+}
+
+/* solve_dc  solve.jl:2389-2420 (+ _dc_initial_guess :943-950) */
+int ora_solve_dc(const ora_netlist *nl, const ora_spec *spec, const double *u0, int64_t n_u0,
+                 double abstol, int maxiters, double *x, int64_t cap, int64_t *n_out,
+                 int *iters)
+{
+    ora_ctx *ctx = ora_detect_structure(nl, spec);
+    ora_structure *s = ora_compile_structure(nl, spec, ctx);
+    if (n_out) *n_out = s->n;
+    if (s->n > cap) { ora_structure_free(s); ora_ctx_free(ctx); return -1; }
+    ora_workspace *w = ora_create_workspace(s);
+    if (u0 != NULL && n_u0 == s->n) memcpy(x, u0, sizeof(double) * s->n);
+    else memset(x, 0, sizeof(double) * s->n);        /* wrong-length warm start dropped */
+    int conv = ora_dc_solve_with_fallbacks(w, s, spec, x, abstol, maxiters, 1, iters);
+    ora_workspace_free(w); ora_structure_free(s); ora_ctx_free(ctx);
+    return conv;
+}
+
+/* ------------------------------------------------------------------------- */
+/* breakpoints  solve.jl:1847-1918 ; devices.jl:145, :180, :211-214            */
+/* ------------------------------------------------------------------------- */
+static int cmp_double(const void *a, const void *b)
+{
+    double x = *(const double *)a, y = *(const double *)b;
+    return (x > y) - (x < y);
+}
+
+static double eps_of(double x)
+{
+    x = fabs(x);
+    if (x == 0.0) return 4.9406564584124654e-324;
+    return nextafter(x, INFINITY) - x;
+}
+
+int64_t ora_expand_breakpoints(int wave, const double *wp, int nwp, double t0, double t1,
+                               double *out, int64_t cap)
+{
+    const int64_t max_points = 100000;
+    double times[256]; int nt = 0; double period = 0.0;
+    if (wave == ORA_WAVE_PWL) {
+        for (int i = 0; i < nwp / 2 && nt < 256; i++) times[nt++] = wp[2 * i];
+    } else if (wave == ORA_WAVE_SIN) {
+        if (wp[3] > 0) times[nt++] = wp[3];
+    } else if (wave == ORA_WAVE_PULSE) {
+        double td = wp[2], tr = wp[3], tf = wp[4], pw = wp[5], per = wp[6];
+        times[0] = td; times[1] = td + tr; times[2] = td + tr + pw; times[3] = td + tr + pw + tf;
+        nt = 4;
+        period = per > 0 ? per : 0.0;
+    }
+    if (nt == 0) return 0;
+    int64_t m = 0;
+    if (period <= 0) {
+        for (int i = 0; i < nt; i++) if (t0 < times[i] && times[i] < t1 && m < cap) out[m++] = times[i];
+    } else {
+        double tmin = times[0], tmax = times[0];
+        for (int i = 1; i < nt; i++) { if (times[i] < tmin) tmin = times[i]; if (times[i] > tmax) tmax = times[i]; }
+        double ks = floor((t0 - tmax) / period); if (ks < 0.0) ks = 0.0; if (ks > 1e15) ks = 1e15;
+        double ke = ceil((t1 - tmin) / period); if (ke < -1.0) ke = -1.0; if (ke > 1e15) ke = 1e15;
+        int64_t k_start = (int64_t)ks, k_end = (int64_t)ke;
+        if (k_end < k_start) return 0;
+        if (k_end - k_start + 1 > max_points) k_end = k_start + max_points - 1;
+        for (int64_t k = k_start; k <= k_end; k++) {
+            double base = (double)k * period;
+            for (int i = 0; i < nt; i++) {
+                double tt = times[i] + base;
+                if (t0 < tt && tt < t1 && m < cap) out[m++] = tt;
+            }
+        }
+    }
+    if (m == 0) return 0;
+    qsort(out, (size_t)m, sizeof(double), cmp_double);
+    if (m > max_points) m = max_points;
+    int64_t q = 1;
+    for (int64_t i = 1; i < m; i++) {
+        double a = eps_of(out[q - 1]), b = eps_of(out[i]);
+        double tol = 4 * (a > b ? a : b);
+        if (out[i] - out[q - 1] > tol) out[q++] = out[i];
+    }
+    return q;
+}
+
+/* ------------------------------------------------------------------------- */
+/* transient.  The reference delegates time stepping to Sundials IDA /
+ * OrdinaryDiffEq (sweeps.jl:599-601, :650, :664; third-party, "parity
+ * unpinned").  What is in-tree and restated exactly: the residual
+ * F = C*du + G*u - b (fast_residual!, precompile.jl:546-557), the Jacobian
+ * J = G + gamma*C (fast_jacobian!, :568-585) and the CedarTranOp initialisation
+ * (dcop.jl:160-203).  The fixed-step integrators (tran! with
+ * solver=ImplicitEuler()/Trapezoid(), adaptive=false, dt=h) are restated as:
+ *     du = gamma*(u - u_n) + dterm
+ *     BE:    gamma = 1/h,     dterm = 0
+ *     trap:  gamma = 2/h,     dterm = -du_n                    (first step BE)
+ *     Gear2: gamma = 3/(2h),  dterm = -(u_n - u_{n-1})/(2h)    (first step BE)
+ * Newton per step from the predictor u = u_n: rebuild, F, stop when
+ * ||F||_2 < abstol, else solve J delta = F, u -= delta; at most max_nl_iters
+ * solves (IDA max_nonlinear_iters = 10, sweeps.jl:599).  t_k = t0 + k*h.        */
+/* ------------------------------------------------------------------------- */
+static void tran_residual(ora_workspace *w, const ora_structure *s, const double *u,
+                          const double *du, double *F)
+{
+    for (int64_t i = 0; i < s->n; i++) F[i] = 0.0;
+    csc_mul_add(s, w->C_nz, du, F);
+    csc_mul_add(s, w->G_nz, u, F);
+    for (int64_t i = 0; i < s->n; i++) F[i] -= w->b[i];
+}
+
+/* one implicit step; returns status, u updated in place */
+static int implicit_step(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
+                         double *u, const double *un, const double *dterm, double gamma, double t,
+                         double abstol, int max_nl, int64_t *iters)
+{
+    int64_t n = s->n;
+    double *F = w->F, *delta = w->delta, *du = w->du;
+    for (int it = 0; ; it++) {
+        fast_rebuild(w, s, spec, u, t);
+        for (int64_t i = 0; i < n; i++) du[i] = gamma * (u[i] - un[i]) + dterm[i];
+        tran_residual(w, s, u, du, F);
+        if (!all_finite(F, n)) return ORA_LANE_NONFINITE;
+        if (norm2(F, n) < abstol) return ORA_LANE_OK;
+        if (it >= max_nl) return ORA_LANE_MAXITER;
+        for (int64_t k = 0; k < s->nnz; k++) w->Jnz[k] = w->G_nz[k] + gamma * w->C_nz[k];
+        if (dense_solve(w, s, w->Jnz, F, delta)) return ORA_LANE_SINGULAR;
+        if (!all_finite(delta, n)) return ORA_LANE_NONFINITE;
+        for (int64_t i = 0; i < n; i++) u[i] -= delta[i];
+        if (iters) (*iters)++;
+    }
+}
+
+int ora_tran(const ora_netlist *nl, const ora_spec *spec_in, double t0, double t1,
+             const ora_tran_opts *o, const int64_t *save_idx, int n_save, const double *u0,
+             double *out_t, double *out_u, int64_t cap_T, int64_t *T_out,
+             int64_t *newton_iters, int64_t *rejected, double *x_final)
+{
+    /* DAEProblem(circuit, tspan): build_with_detection -> compile_structure ->
+       create_workspace  (solve.jl:2102-2161)                                    */
+    ora_spec spec = *spec_in;
+    ora_ctx *ctx = ora_detect_structure(nl, &spec);
+    ora_structure *s = ora_compile_structure(nl, &spec, ctx);
+    ora_workspace *w = ora_create_workspace(s);
+    int64_t n = s->n;
+    double *u = (double *)calloc((size_t)n + 1, sizeof(double));
+    double *un = (double *)calloc((size_t)n + 1, sizeof(double));
+    double *unm1 = (double *)calloc((size_t)n + 1, sizeof(double));
+    double *dun = (double *)calloc((size_t)n + 1, sizeof(double));
+    double *hist = (double *)calloc((size_t)n + 1, sizeof(double));
+    int status = ORA_LANE_OK;
+    int64_t iters = 0, T = 0, rej = 0;
+
+    /* CedarTranOp  dcop.jl:160-203: mode :tranop, zeros start, fallback chain   */
+    if (o->init == 0) {
+        ora_spec sdc = spec; sdc.mode = ORA_MODE_TRANOP;
+        int dc_iters = 0;
+        int ok = ora_dc_solve_with_fallbacks(w, s, &sdc, u, o->init_abstol, o->init_maxiters, 1,
+                                             &dc_iters);
+        iters += dc_iters;
+        if (!ok) status = ORA_LANE_MAXITER;          /* InitialFailure: continue anyway */
+    } else if (u0) {
+        memcpy(u, u0, sizeof(double) * n);
+    }
+    spec.mode = ORA_MODE_TRAN;
+
+#define SAVE_POINT(tt)                                                          \
+    do {                                                                        \
+        if (T < cap_T) {                                                        \
+            if (out_t) out_t[T] = (tt);                                         \
+            if (out_u) for (int q = 0; q < n_save; q++)                         \
+                out_u[T * n_save + q] = u[save_idx[q] - 1];                     \
+        }                                                                       \
+        T++;                                                                    \
+    } while (0)
+
+    SAVE_POINT(t0);
+    if (!o->adaptive) {
+        double h = o->dt;
+        int64_t nsteps = (int64_t)llround((t1 - t0) / h);
+        int se = o->save_every > 0 ? o->save_every : 1;
+        for (int64_t k = 1; k <= nsteps; k++) {
+            double t = t0 + (double)k * h;
+            int method = (k == 1) ? ORA_METHOD_BE : o->method;   /* bootstrap with BE */
+            double gamma;
+            memcpy(un, u, sizeof(double) * n);
+            if (method == ORA_METHOD_BE) {
+                gamma = 1.0 / h;
+                for (int64_t i = 0; i < n; i++) hist[i] = 0.0;
+            } else if (method == ORA_METHOD_TRAP) {
+                gamma = 2.0 / h;
+                for (int64_t i = 0; i < n; i++) hist[i] = -dun[i];
+            } else {
+                gamma = 3.0 / (2.0 * h);
+                for (int64_t i = 0; i < n; i++) hist[i] = -(un[i] - unm1[i]) / (2.0 * h);
+            }
+            int st = implicit_step(w, s, &spec, u, un, hist, gamma, t, o->abstol, o->max_nl_iters,
+                                   &iters);
+            if (st != ORA_LANE_OK && status == ORA_LANE_OK) status = st;
+            if (st == ORA_LANE_NONFINITE || st == ORA_LANE_SINGULAR) {
+                /* lane is dead: hold the last finite state for the remaining points */
+                memcpy(u, un, sizeof(double) * n);
+            }
+            for (int64_t i = 0; i < n; i++) dun[i] = gamma * (u[i] - un[i]) + hist[i];
+            memcpy(unm1, un, sizeof(double) * n);
+            if (k % se == 0 || k == nsteps) SAVE_POINT(t);
+        }
+    } else {
+        /* adaptive: see tran_adaptive below */
+        extern int ora__tran_adaptive(ora_workspace *, const ora_structure *, const ora_spec *,
+                                      double, double, const ora_tran_opts *, const int64_t *, int,
+                                      double *, double *, double *, int64_t, int64_t *, int64_t *,
+                                      int64_t *);
+        int st = ora__tran_adaptive(w, s, &spec, t0, t1, o, save_idx, n_save, u, out_t, out_u,
+                                    cap_T, &T, &iters, &rej);
+        if (st != ORA_LANE_OK && status == ORA_LANE_OK) status = st;
+    }
+#undef SAVE_POINT
+    if (x_final) memcpy(x_final, u, sizeof(double) * n);
+    if (T_out) *T_out = T;
+    if (newton_iters) *newton_iters = iters;
+    if (rejected) *rejected = rej;
+    free(u); free(un); free(unm1); free(dun); free(hist);
+    ora_workspace_free(w); ora_structure_free(s); ora_ctx_free(ctx);
+    return status;
+}
+
+/* Adaptive trapezoidal integration with LTE step control (stand-in for IDA's
+ * variable-step BDF, "parity unpinned"; algorithm stated in DESIGN.md):
+ *  - tstops = source breakpoints (expand_breakpoints); steps land on them and the
+ *    integrator restarts (BE step, fresh history) after each one;
+ *  - error estimate = scaled difference between the corrector and a polynomial
+ *    predictor through the previous points (order 1 after a restart, else 2);
+ *  - weighted RMS norm with abstol_i + reltol*max(|u_i|,|u_n,i|); accept if <= 1;
+ *  - h_new = h*clamp(0.9*err^(-1/(p+1)), 0.2, 2); Newton failure: h /= 4.        */
+int ora__tran_adaptive(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
+                       double t0, double t1, const ora_tran_opts *o, const int64_t *save_idx,
+                       int n_save, double *u, double *out_t, double *out_u, int64_t cap_T,
+                       int64_t *T_io, int64_t *iters, int64_t *rej)
+{
+    int64_t n = s->n, T = *T_io;
+    const ora_netlist *nl = &s->nl;
+    /* collect tstops from all sources */
+    int64_t cap = 4096, nstop = 0;
+    double *stops = (double *)xrealloc(NULL, sizeof(double) * cap);
+    for (int d = 0; d < nl->n_dev; d++) {
+        if (nl->kind[d] != ORA_DEV_VSOURCE && nl->kind[d] != ORA_DEV_ISOURCE) continue;
+        if (nl->flags[d] == ORA_WAVE_NONE) continue;
+        const double *par = nl->par + nl->par_ptr[d];
+        int npar = nl->par_ptr[d + 1] - nl->par_ptr[d];
+        double tmp[4096];
+        int64_t m = ora_expand_breakpoints(nl->flags[d], par + 1, npar - 1, t0, t1, tmp, 4096);
+        if (nstop + m > cap) { cap = 2 * (nstop + m); stops = (double *)xrealloc(stops, sizeof(double) * cap); }
+        memcpy(stops + nstop, tmp, sizeof(double) * m); nstop += m;
+    }
+    qsort(stops, (size_t)nstop, sizeof(double), cmp_double);
+
+    double *un = (double *)calloc((size_t)n + 1, sizeof(double));
+    double *unm1 = (double *)calloc((size_t)n + 1, sizeof(double));
+    double *unm2 = (double *)calloc((size_t)n + 1, sizeof(double));
+    double *dun = (double *)calloc((size_t)n + 1, sizeof(double));
+    double *hist = (double *)calloc((size_t)n + 1, sizeof(double));
+    double *pred = (double *)calloc((size_t)n + 1, sizeof(double));
+    double span = t1 - t0;
+    double dtmax = o->dtmax > 0 ? o->dtmax : span / 50.0;
+    double dtmin = o->dtmin > 0 ? o->dtmin : span * 1e-12;
+    double h = o->dt > 0 ? o->dt : span * 1e-4;
+    if (h > dtmax) h = dtmax;
+    double t = t0, h1 = 0.0, h2 = 0.0;
+    int nhist = 0;          /* accepted points since last restart (0: only u_n known) */
+    int64_t istop = 0;
+    int status = ORA_LANE_OK;
+    while (t < t1) {
+        while (istop < nstop && stops[istop] <= t * (1 + 4e-16)) istop++;
+        double tnext_stop = istop < nstop ? stops[istop] : t1;
+        if (tnext_stop > t1) tnext_stop = t1;
+        double hh = h;
+        int hit_stop = 0;
+        if (t + hh >= tnext_stop - 1e-3 * hh) { hh = tnext_stop - t; hit_stop = 1; }
+        double tn = hit_stop ? tnext_stop : t + hh;
+        int method = (nhist == 0 || o->method == ORA_METHOD_BE) ? ORA_METHOD_BE : ORA_METHOD_TRAP;
+        double gamma;
+        memcpy(un, u, sizeof(double) * n);
+        if (method == ORA_METHOD_BE) {
+            gamma = 1.0 / hh;
+            for (int64_t i = 0; i < n; i++) hist[i] = 0.0;
+        } else {
+            gamma = 2.0 / hh;
+            for (int64_t i = 0; i < n; i++) hist[i] = -dun[i];
+        }
+        int st = implicit_step(w, s, spec, u, un, hist, gamma, tn, o->abstol, o->max_nl_iters, iters);
+        if (st != ORA_LANE_OK) {
+            memcpy(u, un, sizeof(double) * n);
+            (*rej)++;
+            h = hh / 4.0;
+            if (h < dtmin) { status = (st == ORA_LANE_MAXITER) ? ORA_LANE_DTMIN : st; break; }
+            continue;
+        }
+        /* LTE estimate */
+        double err = 0.0; int p;
+        if (nhist == 0) {
+            err = 0.0; p = 1;             /* no history: accept the restart step */
+        } else if (method == ORA_METHOD_BE || nhist == 1) {
+            p = 1;
+            double r = hh / h1, c = hh / (2.0 * hh + h1);
+            if (method == ORA_METHOD_TRAP) c = hh / (2.0 * hh + h1);   /* conservative: order-1 estimate */
+            double acc = 0.0;
+            for (int64_t i = 0; i < n; i++) {
+                double up = un[i] + r * (un[i] - unm1[i]);
+                double tol = o->lte_abstol + o->reltol * fmax(fabs(u[i]), fabs(un[i]));
+                double e = c * (u[i] - up) / tol;
+                acc += e * e;
+            }
+            err = sqrt(acc / (double)n);
+        } else {
+            p = 2;
+            /* quadratic predictor through (t-h1-h2, unm2), (t-h1, unm1), (t, un) at t+hh */
+            double ta = -(h1 + h2), tb = -h1, tc = 0.0, tx = hh;
+            double la = (tx - tb) * (tx - tc) / ((ta - tb) * (ta - tc));
+            double lb = (tx - ta) * (tx - tc) / ((tb - ta) * (tb - tc));
+            double lc = (tx - ta) * (tx - tb) / ((tc - ta) * (tc - tb));
+            double c = hh * hh / (hh * hh + 2.0 * (hh + h1) * (hh + h1 + h2));
+            double acc = 0.0;
+            for (int64_t i = 0; i < n; i++) {
+                double up = la * unm2[i] + lb * unm1[i] + lc * un[i];
+                double tol = o->lte_abstol + o->reltol * fmax(fabs(u[i]), fabs(un[i]));
+                double e = c * (u[i] - up) / tol;
+                acc += e * e;
+            }
+            err = sqrt(acc / (double)n);
+        }
+        (void)pred;
+        if (err > 1.0) {                  /* reject */
+            memcpy(u, un, sizeof(double) * n);
+            (*rej)++;
+            double f = 0.9 * pow(err, -1.0 / (p + 1));
+            if (f < 0.2) f = 0.2;
+            h = hh * f;
+            if (h < dtmin) { status = ORA_LANE_DTMIN; break; }
+            continue;
+        }
+        /* accept */
+        for (int64_t i = 0; i < n; i++) dun[i] = gamma * (u[i] - un[i]) + hist[i];
+        memcpy(unm2, unm1, sizeof(double) * n);
+        memcpy(unm1, un, sizeof(double) * n);
+        h2 = h1; h1 = hh;
+        t = tn;
+        nhist++;
+        if (T < cap_T) {
+            if (out_t) out_t[T] = t;
+            if (out_u) for (int q = 0; q < n_save; q++) out_u[T * n_save + q] = u[save_idx[q] - 1];
+        }
+        T++;
+        double f = err > 0.0 ? 0.9 * pow(err, -1.0 / (p + 1)) : 2.0;
+        if (f > 2.0) f = 2.0;
+        if (f < 0.2) f = 0.2;
+        h = hh * f;
+        if (h > dtmax) h = dtmax;
+        if (hit_stop && tn < t1) {        /* restart after a breakpoint */
+            nhist = 0;
+            h = fmin(h, dtmax);
+        }
+        if (T >= cap_T && t < t1) { status = ORA_LANE_MAXITER; break; }
+    }
+    *T_io = T;
+    free(stops); free(un); free(unm1); free(unm2); free(dun); free(hist); free(pred);
+    return status;
+}
+
+/* ------------------------------------------------------------------------- */
+/* sweeps  src/sweeps.jl:511-532 (dc!), :692-707 (tran!)                       */
+/* ------------------------------------------------------------------------- */
+int ora_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+int ora_sweep_dc(const ora_netlist *nl, const double *par_lanes, int64_t P, int64_t npar,
+                 const ora_spec *spec, double abstol, int maxiters, int continuation,
+                 double *x_out, int64_t n, int32_t *status, int32_t *iters, int nthreads)
+{
+    if (continuation) {
+        /* the reference's serial loop: warm start from the last *converged* point */
+        double *prev = NULL;
+        for (int64_t p = 0; p < P; p++) {
+            ora_netlist l = *nl; l.par = par_lanes + p * npar;
+            int64_t nn = 0; int it = 0;
+            int ok = ora_solve_dc(&l, spec, prev, prev ? n : 0, abstol, maxiters,
+                                  x_out + p * n, n, &nn, &it);
+            if (status) status[p] = ok == 1 ? ORA_LANE_OK : ORA_LANE_MAXITER;
+            if (iters) iters[p] = it;
+            if (ok == 1) prev = x_out + p * n;
+        }
+        return 0;
+    }
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t p = 0; p < P; p++) {
+        ora_netlist l = *nl; l.par = par_lanes + p * npar;
+        int64_t nn = 0; int it = 0;
+        int ok = ora_solve_dc(&l, spec, NULL, 0, abstol, maxiters, x_out + p * n, n, &nn, &it);
+        if (status) status[p] = ok == 1 ? ORA_LANE_OK : ORA_LANE_MAXITER;
+        if (iters) iters[p] = it;
+    }
+    return 0;
+}
+
+int ora_sweep_tran(const ora_netlist *nl, const double *par_lanes, int64_t P, int64_t npar,
+                   const ora_spec *spec, double t0, double t1, const ora_tran_opts *o,
+                   const int64_t *save_idx, int n_save, double *out_t, double *out_u,
+                   int64_t cap_T, int32_t *T_out, int32_t *status, int64_t *newton_iters,
+                   int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t p = 0; p < P; p++) {
+        ora_netlist l = *nl; l.par = par_lanes + p * npar;
+        int64_t T = 0, it = 0, rej = 0;
+        double *ot = NULL;
+        if (out_t) ot = o->adaptive ? out_t + p * cap_T : (p == 0 ? out_t : NULL);
+        int st = ora_tran(&l, spec, t0, t1, o, save_idx, n_save, NULL, ot,
+                          out_u ? out_u + p * cap_T * n_save : NULL, cap_T, &T, &it, &rej, NULL);
+        if (T_out) T_out[p] = (int32_t)T;
+        if (status) status[p] = st;
+        if (newton_iters) newton_iters[p] = it;
+    }
+    return 0;
+}
