@@ -203,8 +203,15 @@ class CompiledSweep:
     def dc(self, u0=None, abstol=1e-10, maxiters=100, use_stepping=True, mode="dcop"):
         return self.handle.dc(self.spec, u0, abstol, maxiters, use_stepping, mode)
 
+    def specialize(self, dt, method="be"):
+        """Compile and load kernels specialised for this circuit and step size."""
+        self.handle.specialize(self.spec, method, dt)
+
     def tran(self, tspan, dt, method="be", save_idxs=None, save_every=1, abstol=1e-10,
-             max_nl_iters=10, u0=None, init_abstol=1e-9, init_maxiters=500) -> backend.Wave:
+             max_nl_iters=10, u0=None, init_abstol=1e-9, init_maxiters=500,
+             specialize=False) -> backend.Wave:
+        if specialize:
+            self.specialize(dt, method)
         opts = backend.make_tran_opts(method=method, adaptive=False, dt=dt, abstol=abstol,
                                       max_nl_iters=max_nl_iters, save_every=save_every,
                                       init=0 if u0 is None else 1, init_abstol=init_abstol,

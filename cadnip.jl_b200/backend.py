@@ -20,8 +20,10 @@ from .lowering import LoweredCircuit
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_CSRC, "libcadnip_b200.so")
-_SOURCES = ["api.cu", "kernels.cu", "symbolic.cpp"]
-_HEADERS = ["kernels.h", "cb200_internal.h", os.path.join("..", "..", "include", "cadnip_b200.h")]
+_SOURCES = ["api.cu", "kernels.cu", "symbolic.cpp", "specialize.cpp"]
+_HEADERS = ["kernels.h", "cb200_internal.h", "lane_kernels.cuh", "specialize.h",
+            os.path.join("..", "..", "include", "cadnip_b200.h")]
+GEN_DIR = os.path.join(_HERE, "_gen")
 
 OK, EINVAL, ENOMEM, ECUDA, ENODEVICE, ESTATE, ESINGULAR = 0, -1, -2, -3, -4, -5, -6
 LANE_OK, LANE_MAXITER, LANE_SINGULAR, LANE_NONFINITE, LANE_DTMIN = 0, 1, 2, 3, 4
@@ -75,7 +77,8 @@ class TranOpts(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+    _fields_ = [("kernel_ms", C.c_double), ("tran_kernel_ms", C.c_double), ("dc_kernel_ms", C.c_double),
+                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("launches", C.c_int64), ("newton_iters", C.c_int64),
                 ("steps_accepted", C.c_int64), ("steps_rejected", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
@@ -107,7 +110,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libcadnip_b200.so")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH] + _SOURCES
+           "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH] + _SOURCES + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, cwd=_CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -150,6 +153,12 @@ def lib():
     L.cb200_analyze.argtypes = [vp, C.POINTER(Spec), C.c_double]
     L.cb200_get_pivot_order.restype = C.c_int
     L.cb200_get_pivot_order.argtypes = [vp, lp, lp, lp]
+    L.cb200_specialize.restype = C.c_int
+    L.cb200_specialize.argtypes = [vp, C.POINTER(Spec), C.c_int32, C.c_double, C.c_char_p, C.c_char_p, C.c_int32]
+    L.cb200_is_specialized.restype = C.c_int
+    L.cb200_is_specialized.argtypes = [vp]
+    L.cb200_emit_source.restype = C.c_int64
+    L.cb200_emit_source.argtypes = [C.POINTER(Desc), dp, dp, C.c_int32, C.c_int64, C.c_int32, C.c_char_p, C.c_int64]
     L.cb200_eval.restype = C.c_int
     L.cb200_eval.argtypes = [vp, C.POINTER(Spec), C.c_double, C.c_int32, dp, dp, dp, dp, dp]
     L.cb200_dc.restype = C.c_int
@@ -176,6 +185,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "cb200_abi_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_pattern",
     "cb200_get_maps", "cb200_set_lanes", "cb200_analyze", "cb200_get_pivot_order", "cb200_eval",
+    "cb200_specialize", "cb200_is_specialized", "cb200_emit_source",
     "cb200_dc", "cb200_tran", "cb200_wave_info", "cb200_wave_fetch", "cb200_wave_final_state",
     "cb200_wave_free", "cb200_get_stats"]
 
@@ -222,6 +232,22 @@ def make_desc(lc: LoweredCircuit):
              _dp(arr(lc.uniform, np.float64)), _ip(arr(lc.limit_init_ref, np.int32)),
              lc.n_lane_cols, 0)
     return d, keep
+
+
+def emit_source(lc: LoweredCircuit, absJ_dc: np.ndarray, absJ_tr: np.ndarray, P: int = 65536,
+                num_sms: int = 148, method="be") -> str:
+    """Generated CUDA source of the circuit-specialised kernels (host only, no device)."""
+    L = lib()
+    desc, keep = make_desc(lc)
+    a0 = np.ascontiguousarray(absJ_dc, dtype=np.float64)
+    a1 = np.ascontiguousarray(absJ_tr, dtype=np.float64)
+    m = METHODS[method] if isinstance(method, str) else int(method)
+    n = L.cb200_emit_source(C.byref(desc), _dp(a0), _dp(a1), m, P, num_sms, None, 0)
+    if n < 0:
+        raise CB200Error(int(n), (L.cb200_last_error(None) or b"").decode())
+    buf = C.create_string_buffer(n + 1)
+    L.cb200_emit_source(C.byref(desc), _dp(a0), _dp(a1), m, P, num_sms, buf, n + 1)
+    return buf.value.decode()
 
 
 class Wave:
@@ -320,6 +346,17 @@ class Handle:
     def analyze(self, spec: MNASpec, gamma: float, mode: Optional[str] = None):
         s = make_spec(spec, mode)
         self._check(lib().cb200_analyze(self._p, C.byref(s), float(gamma)))
+
+    def specialize(self, spec: MNASpec, method, dt: float, compile_only: bool = False):
+        """Generate + compile (cached in cadnip.jl_b200/_gen) + load kernels specialised
+        for this circuit; later dc/tran calls use them."""
+        s = make_spec(spec, "tran")
+        m = METHODS[method] if isinstance(method, str) else int(method)
+        self._check(lib().cb200_specialize(self._p, C.byref(s), m, float(dt), _CSRC.encode(),
+                                           GEN_DIR.encode(), 1 if compile_only else 0))
+
+    def is_specialized(self) -> bool:
+        return bool(lib().cb200_is_specialized(self._p))
 
     def pivot_order(self):
         r = np.zeros(self.n, np.int64); c = np.zeros(self.n, np.int64); nlu = C.c_int64()

@@ -9,6 +9,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -16,6 +19,7 @@
 
 #include "cb200_internal.h"
 #include "kernels.h"
+#include "specialize.h"
 
 using namespace cb200;
 
@@ -23,15 +27,76 @@ static thread_local std::string g_last_error;
 
 namespace {
 
+// Cache of device allocations shared by a handle and the waves it produced: the
+// waveform buffers of a sweep are large (O(100 MB)) and cudaMalloc / cudaFree of that
+// size cost milliseconds and serialise against every other driver call, so buffers
+// are recycled by exact size instead of being returned to the driver.
+struct BufPool {
+    int device = 0;
+    std::mutex mu;
+    std::multimap<size_t, void *> free_;
+    size_t cached_bytes = 0;
+    static constexpr size_t kMaxCached = (size_t)8 << 30;
+    cudaError_t get(size_t bytes, void **out)
+    {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = free_.find(bytes);
+            if (it != free_.end()) {
+                *out = it->second;
+                cached_bytes -= bytes;
+                free_.erase(it);
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess) {              // out of memory: drop the cache and retry once
+            trim(0);
+            cudaGetLastError();
+            e = cudaMalloc(out, bytes);
+        }
+        return e;
+    }
+    void put(void *p, size_t bytes)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        free_.emplace(bytes, p);
+        cached_bytes += bytes;
+        while (cached_bytes > kMaxCached && !free_.empty()) {
+            auto it = --free_.end();
+            cudaFree(it->second);
+            cached_bytes -= it->first;
+            free_.erase(it);
+        }
+    }
+    void trim(size_t keep)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        while (cached_bytes > keep && !free_.empty()) {
+            auto it = --free_.end();
+            cudaFree(it->second);
+            cached_bytes -= it->first;
+            free_.erase(it);
+        }
+    }
+    ~BufPool()
+    {
+        cudaSetDevice(device);
+        for (auto &kv : free_) cudaFree(kv.second);
+    }
+};
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    std::shared_ptr<BufPool> pool;           // optional
     cudaError_t alloc(size_t count)
     {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
+        if (pool) return pool->get(count * sizeof(T), (void **)&p);
         return cudaMalloc((void **)&p, count * sizeof(T));
     }
     cudaError_t upload(const std::vector<T> &v, cudaStream_t st)
@@ -42,7 +107,10 @@ struct DevBuf {
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pool) pool->put(p, n * sizeof(T));
+            else cudaFree(p);
+        }
         p = nullptr; n = 0;
     }
     ~DevBuf() { release(); }
@@ -68,7 +136,8 @@ struct cb200_handle {
     Structure st;
     // host copies of the description
     std::vector<int> dev_kind, dev_flags, dev_node_ptr, dev_nodes, dev_param_ptr, dev_params;
-    std::vector<int> dev_gbase, dev_cbase, dev_bbase, dyn_list, limit_init_ref;
+    std::vector<int> dev_gbase, dev_cbase, dev_bbase, src_list, nl_list, limit_init_ref;
+    std::vector<unsigned char> src_uniform;
     std::vector<double> uniform;
     int n_lane_cols = 0;
     // lanes
@@ -76,18 +145,25 @@ struct cb200_handle {
     std::vector<double> lanes_host;
     // device copies
     DevBuf<int> d_dev_kind, d_dev_flags, d_dev_node_ptr, d_dev_nodes, d_dev_param_ptr, d_dev_params;
-    DevBuf<int> d_dev_gbase, d_dev_cbase, d_dev_bbase, d_dyn_list, d_limit_init_ref;
+    DevBuf<int> d_dev_gbase, d_dev_cbase, d_dev_bbase, d_src_list, d_nl_list, d_limit_init_ref;
     DevBuf<int> d_gseg_ptr, d_gseg_idx, d_cseg_ptr, d_cseg_idx, d_bseg_ptr, d_bseg_idx;
     DevBuf<int> d_colptr, d_rowval;
-    DevBuf<unsigned char> d_node_diag;
+    DevBuf<unsigned char> d_node_diag, d_src_uniform;
     DevBuf<double> d_uniform, d_lanes;
     DevBuf<double> d_state;        // [n][P]
     DevBuf<double> d_ws_global;    // [n_slots][P] (eval path / shared-memory overflow)
     DevBuf<int> d_status, d_iters;
     DevBuf<unsigned char> d_conv, d_active;
     DevBuf<double> d_gshunt_lane, d_srcfact_lane;
+    DevBuf<int> d_save;
+    std::shared_ptr<BufPool> pool;  // recycled waveform buffers (shared with live waves)
     Program prog{};
     DevLu lu[2];                   // 0: DC (gamma = 0), 1: transient
+    int lu_gen[2] = {0, 0};        // bumped by every (re-)analysis
+    SpecModule spec;               // circuit-specialised kernels (optional)
+    int spec_gen[2] = {-1, -1};    // schedule generations the module was generated from
+    int spec_method = -1;          // integration method baked into the transient kernel
+    int num_sms = 148;
     size_t smem_limit = 0;
     int block_pref = 64;
     cb200_stats stats{};
@@ -152,6 +228,7 @@ static void layout_workspace(cb200_handle *h)
     p.off_SB = o; o += (int)h->st.nb;
     p.off_limw = o; o += h->st.n_limits;
     p.off_lp = o; o += h->n_lane_cols;
+    p.off_srcc = o; o += (int)h->src_list.size();
     p.off_h1 = o; o += n;
     p.off_h2 = o; o += n;
     p.off_LU = o;                       // LU last: its size depends on the schedule
@@ -161,13 +238,12 @@ static void layout_workspace(cb200_handle *h)
     p.n_slots = o;
 }
 
-static bool is_dynamic_kind(int kind)
+// devices whose stamps depend on time only (evaluated once per time step) ...
+static bool is_source_kind(int kind) { return kind == CB200_DEV_VSOURCE || kind == CB200_DEV_ISOURCE; }
+// ... and on the iterate (evaluated every Newton iteration)
+static bool is_nonlinear_kind(int kind)
 {
-    switch (kind) {
-    case CB200_DEV_VSOURCE: case CB200_DEV_ISOURCE: case CB200_DEV_DIODE:
-    case CB200_DEV_DIODECAP: case CB200_DEV_SIMPLEMOS: return true;
-    default: return false;
-    }
+    return kind == CB200_DEV_DIODE || kind == CB200_DEV_DIODECAP || kind == CB200_DEV_SIMPLEMOS;
 }
 
 extern "C" int cb200_abi_version(void) { return CB200_ABI_VERSION; }
@@ -189,6 +265,8 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
                         (ce != cudaSuccess ? cudaGetErrorString(ce) : "device ordinal out of range"));
     cb200_handle *h = new cb200_handle();
     h->device = device;
+    h->pool = std::make_shared<BufPool>();
+    h->pool->device = device;
     ce = cudaSetDevice(device);
     if (ce != cudaSuccess) { delete h; return fail(nullptr, CB200_ECUDA, cudaGetErrorString(ce)); }
     cudaDeviceProp prop;
@@ -200,6 +278,7 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
         return fail(nullptr, CB200_ENODEVICE, m);
     }
     h->smem_limit = prop.sharedMemPerBlockOptin;
+    h->num_sms = prop.multiProcessorCount;
     std::string e = build_structure(*d, h->st);
     if (!e.empty()) { delete h; return fail(nullptr, CB200_EINVAL, e); }
 
@@ -231,8 +310,15 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
             delete h;
             return fail(nullptr, CB200_EINVAL, "cb200_create: device node index out of range");
         }
-    for (int i = 0; i < nd; i++)
-        if (is_dynamic_kind(h->dev_kind[i])) h->dyn_list.push_back(i);
+    for (int i = 0; i < nd; i++) {
+        if (is_source_kind(h->dev_kind[i])) {
+            h->src_list.push_back(i);
+            bool uni = true;
+            for (int q = h->dev_param_ptr[i]; q < h->dev_param_ptr[i + 1]; q++) uni &= h->dev_params[q] >= 0;
+            h->src_uniform.push_back(uni ? 1 : 0);
+        }
+        if (is_nonlinear_kind(h->dev_kind[i])) h->nl_list.push_back(i);
+    }
 
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
@@ -251,7 +337,9 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
               h->d_dev_gbase.upload(h->dev_gbase, s) == cudaSuccess &&
               h->d_dev_cbase.upload(h->dev_cbase, s) == cudaSuccess &&
               h->d_dev_bbase.upload(h->dev_bbase, s) == cudaSuccess &&
-              h->d_dyn_list.upload(h->dyn_list, s) == cudaSuccess &&
+              h->d_src_list.upload(h->src_list, s) == cudaSuccess &&
+              h->d_nl_list.upload(h->nl_list, s) == cudaSuccess &&
+              h->d_src_uniform.upload(h->src_uniform, s) == cudaSuccess &&
               h->d_limit_init_ref.upload(h->limit_init_ref, s) == cudaSuccess &&
               h->d_uniform.upload(h->uniform, s) == cudaSuccess &&
               h->d_gseg_ptr.upload(st.gseg_ptr, s) == cudaSuccess &&
@@ -271,12 +359,14 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
     Program &p = h->prog;
     p.n = st.n; p.n_nodes = st.n_nodes; p.n_limits = st.n_limits; p.nnz = (int)st.nnz;
     p.nG = (int)st.nG; p.nC = (int)st.nC; p.nb = (int)st.nb; p.n_dev = nd;
-    p.n_dyn = (int)h->dyn_list.size(); p.n_lane_cols = h->n_lane_cols; p.P = 0;
+    p.n_src = (int)h->src_list.size(); p.n_nl = (int)h->nl_list.size();
+    p.n_lane_cols = h->n_lane_cols; p.P = 0;
     p.dev_kind = h->d_dev_kind.p; p.dev_flags = h->d_dev_flags.p;
     p.dev_node_ptr = h->d_dev_node_ptr.p; p.dev_nodes = h->d_dev_nodes.p;
     p.dev_param_ptr = h->d_dev_param_ptr.p; p.dev_params = h->d_dev_params.p;
     p.dev_gbase = h->d_dev_gbase.p; p.dev_cbase = h->d_dev_cbase.p; p.dev_bbase = h->d_dev_bbase.p;
-    p.dyn_list = h->d_dyn_list.p; p.uniform = h->d_uniform.p; p.lanes = nullptr;
+    p.src_list = h->d_src_list.p; p.nl_list = h->d_nl_list.p; p.src_uniform = h->d_src_uniform.p;
+    p.uniform = h->d_uniform.p; p.lanes = nullptr;
     p.limit_init_ref = h->d_limit_init_ref.p;
     p.gseg_ptr = h->d_gseg_ptr.p; p.gseg_idx = h->d_gseg_idx.p;
     p.cseg_ptr = h->d_cseg_ptr.p; p.cseg_idx = h->d_cseg_idx.p;
@@ -295,6 +385,7 @@ extern "C" void cb200_destroy(cb200_handle *h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
+    unload_spec(h->spec);
     delete h;
 }
 
@@ -458,6 +549,7 @@ extern "C" int cb200_analyze(cb200_handle *h, const cb200_spec *spec, double gam
     L.host.gamma = gamma;
     rc = upload_lu(h, L);
     if (rc != CB200_OK) return rc;
+    h->lu_gen[which]++;
     layout_workspace(h);
     return CB200_OK;
 }
@@ -518,6 +610,12 @@ extern "C" int cb200_eval(cb200_handle *h, const cb200_spec *spec, double t, int
     return CB200_OK;
 }
 
+// the specialised module is usable only for the LU schedules it was generated from
+static bool spec_usable(const cb200_handle *h)
+{
+    return h->spec.dl != nullptr && h->spec_gen[0] == h->lu_gen[0] && h->spec_gen[1] == h->lu_gen[1];
+}
+
 // ---------------------------------------------------------------------------
 // DC on the device: _dc_solve_with_fallbacks (solve.jl:871-929) over all lanes.
 // State stays in h->d_state; per-lane tier bookkeeping on the host.
@@ -546,8 +644,13 @@ static int dc_launch(DcRun &r, int algorithm, const unsigned char *d_active, con
         a.ws_global = h->d_ws_global.p;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-    CUDA_TRY(h, launch_dc(h->prog, h->lu[0].prog, r.sa, a, h->block_pref, h->smem_limit, h->stream,
-                          &h->stats.launches));
+    if (spec_usable(h)) {
+        h->stats.launches += 1;
+        CUDA_TRY(h, h->spec.dc(&h->prog, &r.sa, &a, h->stream));
+    } else {
+        CUDA_TRY(h, launch_dc(h->prog, h->lu[0].prog, r.sa, a, h->block_pref, h->smem_limit, h->stream,
+                              &h->stats.launches));
+    }
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
@@ -555,9 +658,11 @@ static int dc_launch(DcRun &r, int algorithm, const unsigned char *d_active, con
     return CB200_OK;
 }
 
-// Runs the fallback chain on the device state.  d_state must hold u0 for every lane.
+// Runs the fallback chain on the device state.  d_state must hold u0 for every lane;
+// u0_host is the same start on the host (null = zeros), needed only to restart the
+// lanes tier 0 leaves unconverged.
 static int dc_chain(cb200_handle *h, const cb200_spec *spec, double t, double abstol, int maxiters,
-                    int use_stepping, std::vector<unsigned char> &conv_out,
+                    int use_stepping, const double *u0_host, std::vector<unsigned char> &conv_out,
                     std::vector<int> &status_out)
 {
     const int64_t P = h->P;
@@ -570,7 +675,6 @@ static int dc_chain(cb200_handle *h, const cb200_spec *spec, double t, double ab
     CUDA_TRY(h, cudaMemsetAsync(h->d_conv.p, 0, P, s));
     std::vector<unsigned char> conv(P, 0), active(P, 1);
     std::vector<int> status(P, CB200_LANE_OK);
-    std::vector<double> u0;
 
     auto fetch = [&]() -> int {
         CUDA_TRY(h, cudaMemcpyAsync(conv.data(), h->d_conv.p, P, cudaMemcpyDeviceToHost, s));
@@ -582,10 +686,6 @@ static int dc_chain(cb200_handle *h, const cb200_spec *spec, double t, double ab
 
     const bool has_limits = h->st.n_limits > 0;
     if (has_limits) {
-        // tier 0 needs u0 again if it fails: keep a device-side copy only when needed
-        u0.resize((size_t)n * P);
-        CUDA_TRY(h, cudaMemcpyAsync(u0.data(), h->d_state.p, u0.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(h, cudaStreamSynchronize(s));
         rc = dc_launch(r, 0, nullptr, nullptr, nullptr);                  // tier 0: PCNR
         if (rc != CB200_OK) return rc;
         if ((rc = fetch()) != CB200_OK) return rc;
@@ -598,7 +698,8 @@ static int dc_chain(cb200_handle *h, const cb200_spec *spec, double t, double ab
             CUDA_TRY(h, cudaStreamSynchronize(s));
             for (int64_t l = 0; l < P; l++) {
                 active[l] = conv[l] ? 0 : 1;
-                if (active[l]) for (int i = 0; i < n; i++) cur[(size_t)i * P + l] = u0[(size_t)i * P + l];
+                if (active[l])
+                    for (int i = 0; i < n; i++) cur[(size_t)i * P + l] = u0_host ? u0_host[(size_t)i * P + l] : 0.0;
             }
             CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, cur.data(), cur.size() * sizeof(double), cudaMemcpyHostToDevice, s));
             CUDA_TRY(h, cudaMemcpyAsync(h->d_active.p, active.data(), P, cudaMemcpyHostToDevice, s));
@@ -712,6 +813,7 @@ static int dc_chain(cb200_handle *h, const cb200_spec *spec, double t, double ab
         for (int64_t l = 0; l < P; l++) status[l] = conv[l] ? CB200_LANE_OK : (status[l] == CB200_LANE_OK ? CB200_LANE_MAXITER : status[l]);
     }
     h->stats.kernel_ms += r.kernel_ms;
+    h->stats.dc_kernel_ms += r.kernel_ms;
     conv_out = conv;
     status_out = status;
     for (int64_t l = 0; l < P; l++) if (conv_out[l]) status_out[l] = CB200_LANE_OK;
@@ -737,7 +839,7 @@ extern "C" int cb200_dc(cb200_handle *h, const cb200_spec *spec, const cb200_dc_
     }
     std::vector<unsigned char> conv;
     std::vector<int> st;
-    int rc = dc_chain(h, spec, 0.0, opts->abstol, opts->maxiters, opts->use_stepping, conv, st);
+    int rc = dc_chain(h, spec, 0.0, opts->abstol, opts->maxiters, opts->use_stepping, u0, conv, st);
     if (rc != CB200_OK) return rc;
     if (x_out) {
         CUDA_TRY(h, cudaMemcpyAsync(x_out, h->d_state.p, (size_t)n * P * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -783,7 +885,7 @@ extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, do
         CUDA_TRY(h, cudaMemsetAsync(h->d_state.p, 0, (size_t)n * P * sizeof(double), s));
         cb200_spec sdc = *spec;
         sdc.mode = CB200_MODE_TRANOP;
-        int rc = dc_chain(h, &sdc, t0, o->init_abstol, o->init_maxiters, 1, conv, st0);
+        int rc = dc_chain(h, &sdc, t0, o->init_abstol, o->init_maxiters, 1, nullptr, conv, st0);
         if (rc != CB200_OK) return rc;
     } else {
         if (!u0) return fail(h, CB200_EINVAL, "cb200_tran: init=1 needs u0");
@@ -797,10 +899,15 @@ extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, do
 
     cb200_wave *w = new cb200_wave();
     w->h = h; w->P = P; w->n_save = n_save; w->n = n; w->adaptive = o->adaptive; w->t0 = t0; w->dt = o->dt;
+    w->d_out.pool = w->d_t.pool = w->d_final.pool = h->pool;
+    w->d_count.pool = w->d_status.pool = w->d_iters.pool = h->pool;
     std::vector<int> save0(n_save);
     for (int q = 0; q < n_save; q++) save0[q] = (int)save_idx[q] - 1;
-    DevBuf<int> d_save;
-    if (d_save.upload(save0, s) != cudaSuccess) { delete w; return fail(h, CB200_ECUDA, "cb200_tran: upload failed"); }
+    DevBuf<int> &d_save = h->d_save;
+    if (d_save.n != (size_t)n_save && d_save.alloc(n_save) != cudaSuccess) { delete w; return fail(h, CB200_ECUDA, "cb200_tran: allocation failed"); }
+    if (n_save > 0 && cudaMemcpyAsync(d_save.p, save0.data(), n_save * sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess) {
+        delete w; return fail(h, CB200_ECUDA, "cb200_tran: upload failed");
+    }
     // lanes whose initialisation failed keep that status (InitialFailure, dcop.jl:197-200)
     if (cudaMemcpyAsync(h->d_status.p, st0.data(), P * sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess) {
         delete w; return fail(h, CB200_ECUDA, "cb200_tran: upload failed");
@@ -828,7 +935,12 @@ extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, do
         a.T = T; a.u = h->d_state.p; a.out = w->d_out.p; a.status = h->d_status.p; a.iters = h->d_iters.p;
         a.ws_global = ws_global;
         cudaEventRecord(h->ev0, s);
-        ce = launch_tran_fixed(h->prog, h->lu[1].prog, sa, a, h->block_pref, h->smem_limit, s, &h->stats.launches);
+        if (spec_usable(h) && h->spec_method == o->method) {
+            h->stats.launches += 1;
+            ce = h->spec.tran_fixed(&h->prog, &sa, &a, s);
+        } else {
+            ce = launch_tran_fixed(h->prog, h->lu[1].prog, sa, a, h->block_pref, h->smem_limit, s, &h->stats.launches);
+        }
         cudaEventRecord(h->ev1, s);
     } else {
         // tstops: breakpoints are computed by the host wrapper and passed through dtmax/.. (see
@@ -843,6 +955,7 @@ extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, do
     }
     float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->stats.kernel_ms += ms;
+    h->stats.tran_kernel_ms = ms;
     // keep per-lane results with the wave so the handle can be reused
     w->d_status.alloc(P); w->d_iters.alloc(P); w->d_final.alloc((size_t)n * P);
     cudaMemcpyAsync(w->d_status.p, h->d_status.p, P * sizeof(int), cudaMemcpyDeviceToDevice, s);
@@ -853,6 +966,106 @@ extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, do
     h->stats.steps_accepted = w->nsteps * P;
     *out = w;
     return CB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// circuit specialisation (the emitter)
+// ---------------------------------------------------------------------------
+extern "C" int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t method, double dt,
+                                const char *csrc_dir, const char *cache_dir, int32_t flags)
+{
+    if (method < 0 || method > 2 || !(dt > 0.0)) return fail(h, CB200_EINVAL, "cb200_specialize: bad method / dt");
+    const double gamma = (method == CB200_METHOD_BE ? 1.0 : method == CB200_METHOD_TRAP ? 2.0 : 1.5) / dt;
+    if (!h || !spec || !csrc_dir || !cache_dir) return fail(h, CB200_EINVAL, "cb200_specialize: null argument");
+    if (h->P <= 0) return fail(h, CB200_ESTATE, "cb200_specialize: call cb200_set_lanes first");
+    cudaSetDevice(h->device);
+    cb200_spec sdc = *spec;
+    int rc = ensure_lu(h, &sdc, 0, 0.0);
+    if (rc != CB200_OK) return rc;
+    rc = ensure_lu(h, spec, 1, gamma);
+    if (rc != CB200_OK) return rc;
+    if (spec_usable(h) && h->spec_method == method) return CB200_OK;
+    SpecInput in{};
+    in.st = &h->st; in.prog = &h->prog;
+    in.dev_kind = &h->dev_kind; in.dev_flags = &h->dev_flags; in.dev_node_ptr = &h->dev_node_ptr;
+    in.dev_nodes = &h->dev_nodes; in.dev_param_ptr = &h->dev_param_ptr; in.dev_params = &h->dev_params;
+    in.dev_gbase = &h->dev_gbase; in.dev_cbase = &h->dev_cbase; in.dev_bbase = &h->dev_bbase;
+    in.src_list = &h->src_list; in.nl_list = &h->nl_list; in.limit_init_ref = &h->limit_init_ref;
+    in.src_uniform = &h->src_uniform; in.method = method;
+    in.uniform = &h->uniform; in.lu_dc = &h->lu[0].host; in.lu_tr = &h->lu[1].host;
+    in.n_lane_cols = h->n_lane_cols;
+    // one wave: enough resident blocks per SM for all lanes, as far as registers allow
+    in.block = 64;
+    const int64_t lanes_per_sm = (h->P + h->num_sms - 1) / h->num_sms;
+    int mb = (int)((lanes_per_sm + in.block - 1) / in.block);
+    in.min_blocks = std::max(1, std::min(mb, 1024 / in.block));
+    if (h->prog.n_slots > 4096) return fail(h, CB200_EINVAL, "cb200_specialize: circuit too large for a register-resident kernel");
+    const std::string src = generate_spec_source(in);
+    unload_spec(h->spec);
+    std::string e = build_and_load_spec(src, csrc_dir, cache_dir, (flags & 1) != 0, h->spec);
+    if (!e.empty()) return fail(h, CB200_ECUDA, e);
+    h->spec_gen[0] = h->lu_gen[0];
+    h->spec_gen[1] = h->lu_gen[1];
+    h->spec_method = method;
+    return CB200_OK;
+}
+
+extern "C" int cb200_is_specialized(const cb200_handle *h) { return h && spec_usable(h) ? 1 : 0; }
+
+// Host-only view of the emitter (no device needed): structure + LU analysis from
+// caller-supplied nominal magnitudes |J| (DC and transient) -> generated CUDA source.
+// Used to unit-test the emitter where no GPU is present; returns the source length.
+extern "C" int64_t cb200_emit_source(const cb200_desc *d, const double *absJ_dc, const double *absJ_tr,
+                                     int32_t method, int64_t P, int32_t num_sms, char *out, int64_t cap)
+{
+    if (!d || !absJ_dc || !absJ_tr) { g_last_error = "cb200_emit_source: null argument"; return CB200_EINVAL; }
+    cb200_handle h;
+    std::string e = build_structure(*d, h.st);
+    if (!e.empty()) { g_last_error = e; return CB200_EINVAL; }
+    const int nd = d->n_devices;
+    h.dev_kind = to_int(d->dev_kind, nd); h.dev_flags = to_int(d->dev_flags, nd);
+    h.dev_node_ptr = to_int(d->dev_node_ptr, nd + 1);
+    h.dev_nodes = to_int(d->dev_nodes, nd ? d->dev_node_ptr[nd] : 0);
+    h.dev_param_ptr = to_int(d->dev_param_ptr, nd + 1);
+    h.dev_params = to_int(d->dev_params, nd ? d->dev_param_ptr[nd] : 0);
+    h.dev_gbase = to_int64(d->dev_gbase, nd + 1); h.dev_cbase = to_int64(d->dev_cbase, nd + 1);
+    h.dev_bbase = to_int64(d->dev_bbase, nd + 1);
+    h.uniform.assign(d->uniform, d->uniform + d->n_uniform);
+    h.limit_init_ref = to_int(d->limit_init_ref, d->n_limits);
+    h.n_lane_cols = d->n_lane_cols;
+    for (int i = 0; i < nd; i++) {
+        if (is_source_kind(h.dev_kind[i])) {
+            h.src_list.push_back(i);
+            bool uni = true;
+            for (int q = h.dev_param_ptr[i]; q < h.dev_param_ptr[i + 1]; q++) uni &= h.dev_params[q] >= 0;
+            h.src_uniform.push_back(uni ? 1 : 0);
+        }
+        if (is_nonlinear_kind(h.dev_kind[i])) h.nl_list.push_back(i);
+    }
+    std::vector<double> a0(absJ_dc, absJ_dc + h.st.nnz), a1(absJ_tr, absJ_tr + h.st.nnz);
+    e = analyze_lu(h.st, a0, 1e-3, h.lu[0].host);
+    if (e.empty()) e = analyze_lu(h.st, a1, 1e-3, h.lu[1].host);
+    if (!e.empty()) { g_last_error = e; return CB200_ESINGULAR; }
+    layout_workspace(&h);
+    SpecInput in{};
+    in.st = &h.st; in.prog = &h.prog;
+    in.dev_kind = &h.dev_kind; in.dev_flags = &h.dev_flags; in.dev_node_ptr = &h.dev_node_ptr;
+    in.dev_nodes = &h.dev_nodes; in.dev_param_ptr = &h.dev_param_ptr; in.dev_params = &h.dev_params;
+    in.dev_gbase = &h.dev_gbase; in.dev_cbase = &h.dev_cbase; in.dev_bbase = &h.dev_bbase;
+    in.src_list = &h.src_list; in.nl_list = &h.nl_list; in.limit_init_ref = &h.limit_init_ref;
+    in.src_uniform = &h.src_uniform; in.method = method;
+    in.uniform = &h.uniform; in.lu_dc = &h.lu[0].host; in.lu_tr = &h.lu[1].host;
+    in.n_lane_cols = h.n_lane_cols;
+    in.block = 64;
+    const int64_t lanes_per_sm = (P + num_sms - 1) / num_sms;
+    in.min_blocks = std::max(1, std::min((int)((lanes_per_sm + in.block - 1) / in.block), 1024 / in.block));
+    const std::string src = generate_spec_source(in);
+    if (out && cap > 0) {
+        const int64_t m = std::min<int64_t>(cap - 1, (int64_t)src.size());
+        memcpy(out, src.data(), m);
+        out[m] = 0;
+    }
+    return (int64_t)src.size();
 }
 
 extern "C" int cb200_wave_info(const cb200_wave *w, int64_t *T, int64_t *P, int32_t *n_save,

@@ -10,11 +10,13 @@ namespace cb200 {
 // coordinates, and the layout of a lane's workspace.  All pointers are device
 // pointers to read-only int32 / fp64 arrays that are uniform across lanes.
 struct Program {
-    int n, n_nodes, n_limits, nnz, nG, nC, nb, n_dev, n_dyn, n_lane_cols;
+    int n, n_nodes, n_limits, nnz, nG, nC, nb, n_dev, n_src, n_nl, n_lane_cols;
     int64_t P;                      // lanes on this device
     const int *dev_kind, *dev_flags, *dev_node_ptr, *dev_nodes, *dev_param_ptr, *dev_params;
     const int *dev_gbase, *dev_cbase, *dev_bbase;
-    const int *dyn_list;            // devices whose stamps depend on (x, t)
+    const int *src_list;            // devices whose stamps depend on t only (sources)
+    const int *nl_list;             // devices whose stamps depend on the iterate x
+    const unsigned char *src_uniform;  // [n_src] 1: every parameter of the source is uniform
     const double *uniform;          // uniform parameter pool
     const double *lanes;            // per-lane parameter SoA [col][P]
     const int *limit_init_ref;      // [n_limits]
@@ -24,7 +26,8 @@ struct Program {
     // lane workspace: slot offsets (in doubles); element (slot) of a lane lives at
     // ws[slot * stride + lane_in_block]  (shared) or ws[slot * P + lane] (global).
     int off_u, off_un, off_dterm, off_F, off_wv, off_SG, off_SC, off_SB, off_LU, off_limw, off_lp;
-    int off_h1, off_h2;             // adaptive history (u_{n-1}, u_{n-2}); -1 when absent
+    int off_srcc;                   // [n_src] warp-cooperative source value cache
+    int off_h1, off_h2;             // adaptive history (u_{n-1}, u_{n-2})
     int n_slots;
 };
 

@@ -1,0 +1,870 @@
+// lane_kernels.cuh -- sm_100a device code of the batched MNA Newton / transient hot path.
+//
+// Mapping: one sweep lane per thread.  A lane's whole Newton state --
+// iterate, history, stamp values, the sparse LU factor -- is private to its thread:
+//   * generic kernels: a column of shared memory, ws[slot * blockDim.x + threadIdx.x]
+//     (fp64, conflict-free: a warp touches 32 consecutive 8-byte words), or of a
+//     global [slot][lane] array when the circuit is too large for shared memory
+//     (coalesced: lane is the fastest index);
+//   * specialised kernels (generated per circuit by specialize.cpp): a register
+//     array whose indices are all compile-time constants.
+// Lanes never communicate: no barriers, no atomics.
+//
+// Every kernel is a template over a program type PG and an LU-schedule type LU:
+//   * DynProg / DynLu read the device table, segment lists and elimination schedule
+//     from read-only global arrays at warp-uniform addresses (one compiled kernel
+//     serves every circuit);
+//   * a generated StaticProg / StaticLu exposes the same accessors as constexpr
+//     functions, so after unrolling every index is an immediate and the kernel is
+//     straight-line code for that circuit.
+//
+// The device-evaluation functions restate the stamp! methods of
+// src/mna/devices.jl; they write each stamp VALUE to the slot the reference's
+// DirectStampContext would have visited at that program position
+// (src/mna/value_only.jl:395-478).  Assembly then sums every matrix entry's segment
+// of stamp slots left to right, i.e. in program order: the same floating-point
+// summation order as the reference's `nzval[map[pos]] += v`, without atomics.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+#include "../../include/cadnip_b200.h"
+#include "kernels.h"
+
+namespace cb200 {
+
+// ---------------------------------------------------------------------------
+// dynamic (table-driven) program / LU accessors
+// ---------------------------------------------------------------------------
+struct DynProg {
+    static constexpr bool kStatic = false;
+    static constexpr int kUnroll = 1;
+    static constexpr int kMethod = -1;      // integration method chosen at run time
+    const Program &p;
+    __device__ __forceinline__ explicit DynProg(const Program &pp) : p(pp) {}
+    __device__ __forceinline__ int n() const { return p.n; }
+    __device__ __forceinline__ int n_limits() const { return p.n_limits; }
+    __device__ __forceinline__ int nnz() const { return p.nnz; }
+    __device__ __forceinline__ int n_dev() const { return p.n_dev; }
+    __device__ __forceinline__ int n_src() const { return p.n_src; }
+    __device__ __forceinline__ int n_nl() const { return p.n_nl; }
+    __device__ __forceinline__ int n_lane_cols() const { return p.n_lane_cols; }
+    __device__ __forceinline__ int src_list(int q) const { return __ldg(p.src_list + q); }
+    __device__ __forceinline__ int nl_list(int q) const { return __ldg(p.nl_list + q); }
+    __device__ __forceinline__ bool src_uniform(int q) const { return __ldg(p.src_uniform + q) != 0; }
+    __device__ __forceinline__ int dev_kind(int d) const { return __ldg(p.dev_kind + d); }
+    __device__ __forceinline__ int dev_flags(int d) const { return __ldg(p.dev_flags + d); }
+    __device__ __forceinline__ int dev_node_ptr(int d) const { return __ldg(p.dev_node_ptr + d); }
+    __device__ __forceinline__ int dev_node(int i) const { return __ldg(p.dev_nodes + i); }
+    __device__ __forceinline__ int dev_param_ptr(int d) const { return __ldg(p.dev_param_ptr + d); }
+    __device__ __forceinline__ int dev_param(int i) const { return __ldg(p.dev_params + i); }
+    __device__ __forceinline__ int dev_gbase(int d) const { return __ldg(p.dev_gbase + d); }
+    __device__ __forceinline__ int dev_cbase(int d) const { return __ldg(p.dev_cbase + d); }
+    __device__ __forceinline__ int dev_bbase(int d) const { return __ldg(p.dev_bbase + d); }
+    __device__ __forceinline__ double uniform(int r) const { return __ldg(p.uniform + r); }
+    __device__ __forceinline__ int limit_init_ref(int k) const { return __ldg(p.limit_init_ref + k); }
+    __device__ __forceinline__ int gseg_ptr(int s) const { return __ldg(p.gseg_ptr + s); }
+    __device__ __forceinline__ int gseg_idx(int q) const { return __ldg(p.gseg_idx + q); }
+    __device__ __forceinline__ int cseg_ptr(int s) const { return __ldg(p.cseg_ptr + s); }
+    __device__ __forceinline__ int cseg_idx(int q) const { return __ldg(p.cseg_idx + q); }
+    __device__ __forceinline__ int bseg_ptr(int r) const { return __ldg(p.bseg_ptr + r); }
+    __device__ __forceinline__ int bseg_idx(int q) const { return __ldg(p.bseg_idx + q); }
+    __device__ __forceinline__ int colptr(int j) const { return __ldg(p.colptr + j); }
+    __device__ __forceinline__ int rowval(int s) const { return __ldg(p.rowval + s); }
+    __device__ __forceinline__ bool nz_is_node_diag(int s) const { return __ldg(p.nz_is_node_diag + s) != 0; }
+    __device__ __forceinline__ int off_u() const { return p.off_u; }
+    __device__ __forceinline__ int off_un() const { return p.off_un; }
+    __device__ __forceinline__ int off_dterm() const { return p.off_dterm; }
+    __device__ __forceinline__ int off_F() const { return p.off_F; }
+    __device__ __forceinline__ int off_wv() const { return p.off_wv; }
+    __device__ __forceinline__ int off_SG() const { return p.off_SG; }
+    __device__ __forceinline__ int off_SC() const { return p.off_SC; }
+    __device__ __forceinline__ int off_SB() const { return p.off_SB; }
+    __device__ __forceinline__ int off_LU() const { return p.off_LU; }
+    __device__ __forceinline__ int off_limw() const { return p.off_limw; }
+    __device__ __forceinline__ int off_lp() const { return p.off_lp; }
+    __device__ __forceinline__ int off_srcc() const { return p.off_srcc; }
+    __device__ __forceinline__ int off_h1() const { return p.off_h1; }
+    __device__ __forceinline__ int off_h2() const { return p.off_h2; }
+};
+
+struct DynLu {
+    const LuProgram &l;
+    __device__ __forceinline__ explicit DynLu(const LuProgram &ll) : l(ll) {}
+    __device__ __forceinline__ int n() const { return l.n; }
+    __device__ __forceinline__ int n_fill() const { return l.n_fill; }
+    __device__ __forceinline__ int rowperm(int k) const { return __ldg(l.rowperm + k); }
+    __device__ __forceinline__ int colperm(int k) const { return __ldg(l.colperm + k); }
+    __device__ __forceinline__ int diag_slot(int k) const { return __ldg(l.diag_slot + k); }
+    __device__ __forceinline__ int Lptr(int k) const { return __ldg(l.Lptr + k); }
+    __device__ __forceinline__ int L_slot(int e) const { return __ldg(l.L_slot + e); }
+    __device__ __forceinline__ int L_row(int e) const { return __ldg(l.L_row + e); }
+    __device__ __forceinline__ int Uptr(int k) const { return __ldg(l.Uptr + k); }
+    __device__ __forceinline__ int U_slot(int q) const { return __ldg(l.U_slot + q); }
+    __device__ __forceinline__ int U_col(int q) const { return __ldg(l.U_col + q); }
+    __device__ __forceinline__ int tgt_ptr(int k) const { return __ldg(l.tgt_ptr + k); }
+    __device__ __forceinline__ int tgt(int q) const { return __ldg(l.tgt + q); }
+    __device__ __forceinline__ int jmap(int s) const { return __ldg(l.jmap + s); }
+    __device__ __forceinline__ int fill_slot(int q) const { return __ldg(l.fill_slots + q); }
+};
+
+// ---------------------------------------------------------------------------
+// lane workspace accessors
+// ---------------------------------------------------------------------------
+template <typename IdxT>
+struct LaneWs {
+    double *ws;
+    IdxT stride;
+    __device__ __forceinline__ double &operator()(int slot) const { return ws[(IdxT)slot * stride]; }
+};
+
+template <int N>
+struct RegWs {                      // specialised kernels: constant indices -> registers
+    double r[N > 0 ? N : 1];
+    __device__ __forceinline__ double &operator()(int slot) { return r[slot]; }
+};
+
+#define CB_UNROLL _Pragma("unroll (PG::kUnroll)")
+
+template <typename PG, typename W>
+__device__ __forceinline__ double param(const PG &pg, W &w, int pbase, int i)
+{
+    const int r = pg.dev_param(pbase + i);
+    return r >= 0 ? pg.uniform(r) : w(pg.off_lp() + ~r);
+}
+
+// u[idx] with a run-time index (saved-output gather).  A register workspace must
+// never be indexed dynamically, so the static variant selects over constant slots.
+template <typename PG, typename W>
+__device__ __forceinline__ double read_u(const PG &pg, W &w, int idx)
+{
+    if constexpr (PG::kStatic) {
+        double v = 0.0;
+        CB_UNROLL
+        for (int i = 0; i < pg.n(); i++) {
+            // read first, select after: a guarded read lets the optimiser substitute the
+            // run-time idx for the constant i and demote the register array to local memory
+            const double ui = w(pg.off_u() + i);
+            v = (idx == i) ? ui : v;
+        }
+        return v;
+    } else {
+        return w(pg.off_u() + idx);
+    }
+}
+
+template <typename PG, typename W>
+__device__ __forceinline__ double xval(const PG &pg, W &w, int idx)
+{
+    // V_k = node_k == 0 ? 0.0 : x[node_k]   (devices.jl:1373)
+    return idx == 0 ? 0.0 : w(pg.off_u() + idx - 1);
+}
+
+// ---------------------------------------------------------------------------
+// waveforms (src/mna/devices.jl:30-216)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double d_mod(double x, double y)   // Julia mod, y > 0
+{
+    double r = fmod(x, y);
+    if (r != 0.0 && ((r < 0.0) != (y < 0.0))) r += y;
+    return r;
+}
+
+// Base.sind restated: exact reduction mod 360, octant folding.
+__device__ __forceinline__ double d_sind(double x)
+{
+    const double d2r = 0.017453292519943295;
+    if (isnan(x) || isinf(x)) return NAN;
+    const double rx = copysign(fmod(x, 360.0), x);
+    const double arx = fabs(rx);
+    if (rx == 0.0) return rx;
+    else if (arx < 45.0) return sin(rx * d2r);
+    else if (arx <= 135.0) return copysign(cos((90.0 - arx) * d2r), rx);
+    else if (arx == 180.0) return copysign(0.0, rx);
+    else if (arx < 225.0) return sin(((180.0 - arx) * (rx < 0 ? -1.0 : 1.0)) * d2r);
+    else if (arx <= 315.0) return -copysign(cos((270.0 - arx) * d2r), rx);
+    else return sin((rx - copysign(360.0, rx)) * d2r);
+}
+
+// pulse_at_time  devices.jl:85-103
+__device__ __forceinline__ double d_pulse(double v1, double v2, double td, double tr, double tf,
+                                          double pw, double per, double t)
+{
+    if (t < td) return v1;
+    const double phase = per > 0 ? d_mod(t - td, per) : (t - td);
+    if (phase < tr) return tr > 0 ? v1 + (v2 - v1) * (phase / tr) : v2;
+    else if (phase < tr + pw) return v2;
+    else if (phase < tr + pw + tf) return tf > 0 ? v2 + (v1 - v2) * ((phase - tr - pw) / tf) : v1;
+    else return v1;
+}
+
+// get_source_value (devices.jl:352-360) over PWLWave / PulseWave / SinWave.
+// params: [0] = dc, [1..] = wave parameters.
+template <typename PG, typename W>
+__device__ __forceinline__ double source_value(const PG &pg, W &w, int wave, int pb, int npar,
+                                               double t, int mode)
+{
+    if (wave == CB200_WAVE_NONE) return param(pg, w, pb, 0);
+    if (mode == CB200_MODE_DCOP || mode == CB200_MODE_AC) return param(pg, w, pb, 0);
+    if (wave == CB200_WAVE_SIN) {          // SinWave  devices.jl:168-174
+        const double vo = param(pg, w, pb, 1), va = param(pg, w, pb, 2), fr = param(pg, w, pb, 3);
+        const double td = param(pg, w, pb, 4), th = param(pg, w, pb, 5), ph = param(pg, w, pb, 6);
+        if (t < td) return vo + va * d_sind(ph);
+        return vo + va * exp(-th * (t - td)) * d_sind(360 * fr * (t - td) + ph);
+    }
+    if (wave == CB200_WAVE_PULSE) {
+        return d_pulse(param(pg, w, pb, 1), param(pg, w, pb, 2), param(pg, w, pb, 3),
+                       param(pg, w, pb, 4), param(pg, w, pb, 5), param(pg, w, pb, 6),
+                       param(pg, w, pb, 7), t);
+    }
+    // PWL: pwl_at_time devices.jl:47-71 with find_t_in_ts :30-36.  Written as a
+    // branch-free scan so that it unrolls for a static program.
+    const int np = (npar - 1) / 2;
+    int i = 1;                              // 1-based searchsortedfirst
+    CB_UNROLL
+    for (int k = 1; k <= np; k++)
+        if (param(pg, w, pb, 1 + 2 * (k - 1)) < t) i = k + 1;
+    double result = 0.0;
+    bool found = false;
+    // step past an exact hit
+    bool hit = false;
+    CB_UNROLL
+    for (int k = 1; k <= np; k++)
+        if (k == i && param(pg, w, pb, 1 + 2 * (k - 1)) == t) hit = true;
+    if (hit) i++;
+    if (i <= 1) { result = param(pg, w, pb, 2); found = true; }
+    if (!found && i > np) { result = param(pg, w, pb, 2 + 2 * (np - 1)); found = true; }
+    if (!found) {
+        double t0 = 0, y0 = 0, t1 = 0, y1 = 0;
+        CB_UNROLL
+        for (int k = 2; k <= np; k++)
+            if (k == i) {
+                t0 = param(pg, w, pb, 1 + 2 * (k - 2)); y0 = param(pg, w, pb, 2 + 2 * (k - 2));
+                t1 = param(pg, w, pb, 1 + 2 * (k - 1)); y1 = param(pg, w, pb, 2 + 2 * (k - 1));
+            }
+        if (y0 == y1) result = y1;
+        else if (t1 == t0) result = (y0 + y1) / 2;
+        else {
+            const double slope = (y1 - y0) / (t1 - t0);
+            result = y0 + (t - t0) * slope;
+        }
+    }
+    return result;
+}
+
+// ---------------------------------------------------------------------------
+// limiting primitives (src/mna/devices.jl:1169-1258, :1333-1345)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double d_pnjlim(double vnew, double vold, double vt, double vcrit)
+{
+    if (vnew > vcrit && fabs(vnew - vold) > vt + vt) {
+        if (vold > 0.0) {
+            const double arg = (vnew - vold) / vt;
+            if (arg > 0.0) return vold + vt * (2.0 + log(arg - 2.0));
+            return vold - vt * (2.0 + log(2.0 - arg));
+        }
+        return vt * log(vnew / vt);
+    } else if (vnew < 0.0) {
+        const double arg = vold > 0.0 ? -vold - 1.0 : 2.0 * vold - 1.0;
+        if (vnew < arg) return arg;
+    }
+    return vnew;
+}
+
+__device__ __forceinline__ void d_diode_iv(double Is, double nVt, double v, double &I0, double &Gd)
+{
+    const double xarg = v / nVt;
+    if (xarg > 80.0) {
+        const double e80 = exp(80.0);
+        I0 = Is * (e80 * (1.0 + (xarg - 80.0)) - 1.0);
+        Gd = Is / nVt * e80;
+    } else {
+        const double expterm = exp(xarg);
+        I0 = Is * (expterm - 1.0);
+        Gd = Is / nVt * expterm;
+    }
+}
+
+// diode_junction_cap  devices.jl:1505-1516
+__device__ __forceinline__ double d_junction_cap(double V, double Cj0, double Vj, double m)
+{
+    const double Vmax = 0.9 * Vj;
+    if (V < Vmax) return Cj0 / pow(1 - V / Vj, m);
+    const double C_at_max = Cj0 / pow(1 - Vmax / Vj, m);
+    const double dC_dV = Cj0 * m / Vj / pow(1 - Vmax / Vj, m + 1);
+    return C_at_max + dC_dV * (V - Vmax);
+}
+
+// ---------------------------------------------------------------------------
+// device evaluation: one stamp! call.
+//   PASS 0 writes every stamp (once per kernel);
+//   PASS 1 writes the stamps that depend on the iterate x (every Newton iteration);
+//   PASS 2 writes the stamps that depend on time only (once per time step).
+// Slot positions advance identically in every pass.
+// ---------------------------------------------------------------------------
+#define ST_G(i, j, v) do { if ((i) != 0 && (j) != 0) { if (PASS == 0) w(g) = (v); g++; } } while (0)
+#define DY_G(i, j, v) do { if ((i) != 0 && (j) != 0) { w(g) = (v); g++; } } while (0)
+#define ST_C(i, j, v) do { if ((i) != 0 && (j) != 0) { if (PASS == 0) w(c) = (v); c++; } } while (0)
+#define DY_C(i, j, v) do { if ((i) != 0 && (j) != 0) { w(c) = (v); c++; } } while (0)
+#define DY_B(i, v)    do { if ((i) != 0) { w(b) = (v); b++; } } while (0)
+
+template <int PASS, typename PG, typename W>
+__device__ __forceinline__ void eval_device(const PG &pg, W &w, int d, double t, int mode,
+                                            bool initjct)
+{
+    const int kind = pg.dev_kind(d), flags = pg.dev_flags(d);
+    const int nb = pg.dev_node_ptr(d);
+    const int pb = pg.dev_param_ptr(d);
+    const int npar = pg.dev_param_ptr(d + 1) - pb;
+    int g = pg.off_SG() + pg.dev_gbase(d);
+    int c = pg.off_SC() + pg.dev_cbase(d);
+    int b = pg.off_SB() + pg.dev_bbase(d);
+    (void)npar; (void)c; (void)b; (void)flags; (void)g;
+
+    switch (kind) {
+    case CB200_DEV_RESISTOR: {                       // devices.jl:498-510
+        const int pp = pg.dev_node(nb), nn = pg.dev_node(nb + 1);
+        const double G = 1.0 / param(pg, w, pb, 0);
+        ST_G(pp, pp, G); ST_G(pp, nn, -G); ST_G(nn, pp, -G); ST_G(nn, nn, G);
+    } break;
+    case CB200_DEV_CAPACITOR: {                      // devices.jl:531-534
+        const int pp = pg.dev_node(nb), nn = pg.dev_node(nb + 1);
+        const double C = param(pg, w, pb, 0);
+        ST_C(pp, pp, C); ST_C(pp, nn, -C); ST_C(nn, pp, -C); ST_C(nn, nn, C);
+    } break;
+    case CB200_DEV_INDUCTOR: {                       // devices.jl:569-586
+        const int pp = pg.dev_node(nb), nn = pg.dev_node(nb + 1), I = pg.dev_node(nb + 2);
+        ST_G(pp, I, 1.0); ST_G(nn, I, -1.0); ST_G(I, pp, 1.0); ST_G(I, nn, -1.0);
+        ST_C(I, I, -param(pg, w, pb, 0));
+    } break;
+    case CB200_DEV_VSOURCE: {                        // devices.jl:643-663
+        const int pp = pg.dev_node(nb), nn = pg.dev_node(nb + 1), I = pg.dev_node(nb + 2);
+        ST_G(pp, I, 1.0); ST_G(nn, I, -1.0); ST_G(I, pp, 1.0); ST_G(I, nn, -1.0);
+        if (PASS != 1) DY_B(I, source_value(pg, w, flags, pb, npar, t, mode));
+    } break;
+    case CB200_DEV_ISOURCE: {                        // devices.jl:719-737
+        const int pp = pg.dev_node(nb), nn = pg.dev_node(nb + 1);
+        if (PASS != 1) {
+            const double i = source_value(pg, w, flags, pb, npar, t, mode);
+            DY_B(pp, i); DY_B(nn, -i);
+        }
+    } break;
+    case CB200_DEV_VCVS: {                           // devices.jl:760-775
+        const int op = pg.dev_node(nb), on = pg.dev_node(nb + 1), ip = pg.dev_node(nb + 2);
+        const int in = pg.dev_node(nb + 3), I = pg.dev_node(nb + 4);
+        const double A = param(pg, w, pb, 0);
+        ST_G(op, I, 1.0); ST_G(on, I, -1.0); ST_G(I, op, 1.0); ST_G(I, on, -1.0);
+        ST_G(I, ip, -A); ST_G(I, in, A);
+    } break;
+    case CB200_DEV_VCCS: {                           // devices.jl:797-808
+        const int op = pg.dev_node(nb), on = pg.dev_node(nb + 1), ip = pg.dev_node(nb + 2);
+        const int in = pg.dev_node(nb + 3);
+        const double gm = param(pg, w, pb, 0);
+        ST_G(op, ip, -gm); ST_G(op, in, gm); ST_G(on, ip, gm); ST_G(on, in, -gm);
+    } break;
+    case CB200_DEV_CCVS: {
+        const double rm = param(pg, w, pb, 0);
+        if (flags == 0) {                            // devices.jl:824-849
+            const int op = pg.dev_node(nb), on = pg.dev_node(nb + 1), ip = pg.dev_node(nb + 2);
+            const int in = pg.dev_node(nb + 3), Iin = pg.dev_node(nb + 4), Iout = pg.dev_node(nb + 5);
+            ST_G(ip, Iin, 1.0); ST_G(in, Iin, -1.0); ST_G(Iin, ip, 1.0); ST_G(Iin, in, -1.0);
+            ST_G(op, Iout, 1.0); ST_G(on, Iout, -1.0); ST_G(Iout, op, 1.0); ST_G(Iout, on, -1.0);
+            ST_G(Iout, Iin, -rm);
+        } else {                                     // devices.jl:898-913
+            const int op = pg.dev_node(nb), on = pg.dev_node(nb + 1), Iin = pg.dev_node(nb + 2);
+            const int Iout = pg.dev_node(nb + 3);
+            ST_G(op, Iout, 1.0); ST_G(on, Iout, -1.0); ST_G(Iout, op, 1.0); ST_G(Iout, on, -1.0);
+            ST_G(Iout, Iin, -rm);
+        }
+    } break;
+    case CB200_DEV_CCCS: {
+        const double A = param(pg, w, pb, 0);
+        if (flags == 0) {                            // devices.jl:865-881
+            const int op = pg.dev_node(nb), on = pg.dev_node(nb + 1), ip = pg.dev_node(nb + 2);
+            const int in = pg.dev_node(nb + 3), Iin = pg.dev_node(nb + 4);
+            ST_G(ip, Iin, 1.0); ST_G(in, Iin, -1.0); ST_G(Iin, ip, 1.0); ST_G(Iin, in, -1.0);
+            ST_G(op, Iin, -A); ST_G(on, Iin, A);
+        } else {                                     // devices.jl:924-931
+            const int op = pg.dev_node(nb), on = pg.dev_node(nb + 1), Iin = pg.dev_node(nb + 2);
+            ST_G(op, Iin, -A); ST_G(on, Iin, A);
+        }
+    } break;
+    case CB200_DEV_DIODE: {                          // devices.jl:1370-1428
+        const int pp = pg.dev_node(nb), nn = pg.dev_node(nb + 1);
+        if (flags & 1) {
+            const int lim = pg.dev_node(nb + 2);
+            ST_G(lim, lim, 1.0); ST_G(lim, pp, -1.0); ST_G(lim, nn, 1.0);
+            if (PASS != 2) {
+                const double V0 = xval(pg, w, pp) - xval(pg, w, nn);
+                const double Is = param(pg, w, pb, 0), Vt = param(pg, w, pb, 1), nf = param(pg, w, pb, 2);
+                const double nVt = nf * Vt;
+                // limit!  devices.jl:1209-1234
+                const double vcrit = param(pg, w, pb, 3);
+                const double vold = w(pg.off_u() + lim - 1);
+                const double wv = initjct ? (V0 - V0 + vcrit) : d_pnjlim(V0, vold, nVt, vcrit);
+                w(pg.off_limw() + (lim - 1 - (pg.n() - pg.n_limits()))) = wv;     // record_limit_w!
+                double I0, Gd;
+                d_diode_iv(Is, nVt, wv, I0, Gd);
+                // stamp_limited_companion!  devices.jl:1251-1258
+                DY_G(pp, pp, Gd); DY_G(pp, nn, -Gd); DY_G(nn, pp, -Gd); DY_G(nn, nn, Gd);
+                const double Ieq = I0 - Gd * wv;
+                DY_B(pp, -Ieq); DY_B(nn, Ieq);
+            }
+        } else if (PASS != 2) {
+            const double V0 = xval(pg, w, pp) - xval(pg, w, nn);
+            const double Is = param(pg, w, pb, 0), Vt = param(pg, w, pb, 1), nf = param(pg, w, pb, 2);
+            const double nVt = nf * Vt;
+            const double expterm = exp(V0 / nVt);
+            const double I0 = Is * (expterm - 1.0);
+            const double Gd = Is / nVt * expterm;
+            const double Ieq = I0 - Gd * V0;
+            DY_G(pp, pp, Gd); DY_G(pp, nn, -Gd); DY_G(nn, pp, -Gd); DY_G(nn, nn, Gd);
+            DY_B(pp, -Ieq); DY_B(nn, Ieq);
+        }
+    } break;
+    case CB200_DEV_DIODECAP: {                       // devices.jl:1558-1602
+        if (PASS != 2) {
+            const int pp = pg.dev_node(nb), nn = pg.dev_node(nb + 1);
+            const double V0 = xval(pg, w, pp) - xval(pg, w, nn);
+            const double Is = param(pg, w, pb, 0), Vt = param(pg, w, pb, 1), nf = param(pg, w, pb, 2);
+            const double nVt = nf * Vt;
+            const double expterm = exp(V0 / nVt);
+            const double I0 = Is * (expterm - 1.0);
+            const double G = Is / nVt * expterm;
+            const double Ieq = I0 - G * V0;
+            DY_G(pp, pp, G); DY_G(pp, nn, -G); DY_G(nn, pp, -G); DY_G(nn, nn, G);
+            DY_B(pp, -Ieq); DY_B(nn, Ieq);
+            const double Cj = d_junction_cap(V0, param(pg, w, pb, 3), param(pg, w, pb, 4), param(pg, w, pb, 5));
+            DY_C(pp, pp, Cj); DY_C(pp, nn, -Cj); DY_C(nn, pp, -Cj); DY_C(nn, nn, Cj);
+        }
+    } break;
+    case CB200_DEV_SIMPLEMOS: {                      // devices.jl:1667-1749
+        const int dd = pg.dev_node(nb), gg = pg.dev_node(nb + 1), ss = pg.dev_node(nb + 2);
+        if (PASS != 2) {
+            const double Vd = xval(pg, w, dd), Vg = xval(pg, w, gg), Vs = xval(pg, w, ss);
+            const double Vgs = Vg - Vs, Vds = Vd - Vs;
+            const double Vth = param(pg, w, pb, 0), K = param(pg, w, pb, 1), lambda = param(pg, w, pb, 2);
+            double Ids, gm, gds;
+            if (Vgs <= Vth) { Ids = 0.0; gm = 0.0; gds = 0.0; }
+            else if (Vds <= Vgs - Vth) {
+                Ids = K * ((Vgs - Vth) * Vds - Vds * Vds / 2);
+                gm = K * Vds;
+                gds = K * (Vgs - Vth - Vds);
+            } else {
+                Ids = K / 2 * ((Vgs - Vth) * (Vgs - Vth)) * (1 + lambda * Vds);
+                gm = K * (Vgs - Vth) * (1 + lambda * Vds);
+                gds = K / 2 * ((Vgs - Vth) * (Vgs - Vth)) * lambda;
+            }
+            const double Ieq = Ids - gm * Vgs - gds * Vds;
+            DY_G(dd, dd, gds); DY_G(dd, gg, gm); DY_G(dd, ss, -(gds + gm));
+            DY_G(ss, dd, -gds); DY_G(ss, gg, -gm); DY_G(ss, ss, gds + gm);
+            DY_B(dd, -Ieq); DY_B(ss, Ieq);
+        }
+        if (PASS == 0) {
+            const double Cgd = param(pg, w, pb, 3), Cgs = param(pg, w, pb, 4);
+            ST_C(gg, gg, Cgs); ST_C(gg, ss, -Cgs); ST_C(ss, gg, -Cgs); ST_C(ss, ss, Cgs);
+            ST_C(gg, gg, Cgd); ST_C(gg, dd, -Cgd); ST_C(dd, gg, -Cgd); ST_C(dd, dd, Cgd);
+        }
+    } break;
+    default: break;
+    }
+}
+
+// A static (generated) program supplies eval_all / eval_nonlinear / eval_sources and
+// its LU type supplies assemble / factor_and_solve / apply_update as straight-line
+// code (one statement per stamp, per matrix entry, per elimination update) emitted by
+// specialize.cpp in exactly the order of the loops below.
+template <typename PG, typename W>
+__device__ __forceinline__ void eval_all(const PG &pg, W &w, double t, int mode, bool initjct)
+{
+    if constexpr (PG::kStatic) {
+        PG::eval_all(w, t, mode, initjct);
+    } else {
+        for (int d = 0; d < pg.n_dev(); d++) eval_device<0>(pg, w, d, t, mode, initjct);
+    }
+}
+
+// devices whose stamps depend on the iterate (every Newton iteration)
+template <typename PG, typename W>
+__device__ __forceinline__ void eval_nonlinear(const PG &pg, W &w, double t, int mode, bool initjct)
+{
+    if constexpr (PG::kStatic) {
+        PG::eval_nonlinear(w, t, mode, initjct);
+    } else {
+        for (int q = 0; q < pg.n_nl(); q++) eval_device<1>(pg, w, pg.nl_list(q), t, mode, initjct);
+    }
+}
+
+// value of independent source d at time t, and its b stamps (devices.jl:643-737)
+template <typename PG, typename W>
+__device__ __forceinline__ double device_source_value(const PG &pg, W &w, int d, double t, int mode)
+{
+    const int pb = pg.dev_param_ptr(d);
+    return source_value(pg, w, pg.dev_flags(d), pb, pg.dev_param_ptr(d + 1) - pb, t, mode);
+}
+
+template <typename PG, typename W>
+__device__ __forceinline__ void device_source_stamp(const PG &pg, W &w, int d, double v)
+{
+    const int nb = pg.dev_node_ptr(d);
+    int b = pg.off_SB() + pg.dev_bbase(d);
+    if (pg.dev_kind(d) == CB200_DEV_VSOURCE) {
+        w(b) = v;                                  // stamp_b!(ctx, I_idx, v): I is never ground
+    } else {
+        const int pp = pg.dev_node(nb), nn = pg.dev_node(nb + 1);
+        if (pp != 0) { w(b) = v; b++; }
+        if (nn != 0) { w(b) = -v; b++; }
+    }
+}
+
+// One source, fixed-step mode.  When every parameter of the source is uniform over the
+// sweep, its value at step k is the same in all lanes: each lane of the warp then
+// evaluates ONE of the next 32 time points (t_{k+lane}) and the values are handed out
+// by warp shuffle, one per step -- the waveform (fmod/sin/exp ...) costs 1/32 of an
+// evaluation per step instead of one.  Bit-identical to evaluating in place: the same
+// instructions run on the same inputs, in another lane.
+template <typename PG, typename W>
+__device__ __forceinline__ void source_step_one(const PG &pg, W &w, int q, int d, bool uniform,
+                                                int64_t k, double t0, double h, int mode)
+{
+    double v;
+    if (uniform) {
+        const int j = (int)((k - 1) & 31);
+        if (j == 0)
+            w(pg.off_srcc() + q) = device_source_value(pg, w, d, t0 + (double)(k + (threadIdx.x & 31)) * h, mode);
+        v = __shfl_sync(0xffffffffu, w(pg.off_srcc() + q), j);
+    } else {
+        v = device_source_value(pg, w, d, t0 + (double)k * h, mode);
+    }
+    device_source_stamp(pg, w, d, v);
+}
+
+template <typename PG, typename W>
+__device__ __forceinline__ void eval_sources_step(const PG &pg, W &w, int64_t k, double t0, double h,
+                                                  int mode)
+{
+    if constexpr (PG::kStatic) {
+        PG::eval_sources_step(w, k, t0, h, mode);
+    } else {
+        for (int q = 0; q < pg.n_src(); q++)
+            source_step_one(pg, w, q, pg.src_list(q), pg.src_uniform(q), k, t0, h, mode);
+    }
+}
+
+// sources: stamps depend on time only (once per time step)
+template <typename PG, typename W>
+__device__ __forceinline__ void eval_sources(const PG &pg, W &w, double t, int mode)
+{
+    if constexpr (PG::kStatic) {
+        PG::eval_sources(w, t, mode);
+    } else {
+        for (int q = 0; q < pg.n_src(); q++) eval_device<2>(pg, w, pg.src_list(q), t, mode, false);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// assembly (deterministic segmented reduction) fused with the residual
+//   F = C*du + G*u - b      (fast_residual!, precompile.jl:546-557; DC: F = G*u - b)
+// and the Jacobian scatter  J = G + gamma*C  (fast_jacobian!, :568-585) straight into
+// the LU workspace.  Also applies srcFact / gshunt (fast_rebuild!, :517-534).
+// Returns ||F||_2^2; bad is set when F has a non-finite entry.
+// ---------------------------------------------------------------------------
+template <bool TRAN, typename PG, typename LU, typename W>
+__device__ __forceinline__ double assemble(const PG &pg, const LU &lu, W &w, double gamma,
+                                           double gshunt, double srcFact, bool &bad)
+{
+    if constexpr (PG::kStatic) return LU::template assemble<TRAN>(w, gamma, gshunt, srcFact, bad);
+    for (int r = 0; r < pg.n(); r++) w(pg.off_F() + r) = 0.0;
+    for (int q = 0; q < lu.n_fill(); q++) w(pg.off_LU() + lu.fill_slot(q)) = 0.0;
+    for (int j = 0; j < pg.n(); j++) {
+        const double uj = w(pg.off_u() + j);
+        double duj = 0.0;
+        if (TRAN) duj = gamma * (uj - w(pg.off_un() + j)) + w(pg.off_dterm() + j);
+        const int s1 = pg.colptr(j + 1);
+            for (int s = pg.colptr(j); s < s1; s++) {
+            double gsum = 0.0;
+            const int g1 = pg.gseg_ptr(s + 1);
+                    for (int q = pg.gseg_ptr(s); q < g1; q++) gsum += w(pg.off_SG() + pg.gseg_idx(q));
+            if (gshunt != 0.0 && pg.nz_is_node_diag(s)) gsum += gshunt;
+            double jv = gsum;
+            const int r = pg.rowval(s);
+            double f = w(pg.off_F() + r);
+            if (TRAN) {
+                double csum = 0.0;
+                const int c1 = pg.cseg_ptr(s + 1);
+                            for (int q = pg.cseg_ptr(s); q < c1; q++) csum += w(pg.off_SC() + pg.cseg_idx(q));
+                f += csum * duj;
+                jv += gamma * csum;
+            }
+            f += gsum * uj;
+            w(pg.off_F() + r) = f;
+            w(pg.off_LU() + lu.jmap(s)) = jv;
+        }
+    }
+    double nrm2 = 0.0;
+    bad = false;
+    for (int r = 0; r < pg.n(); r++) {
+        double bsum = 0.0;
+        const int b1 = pg.bseg_ptr(r + 1);
+            for (int q = pg.bseg_ptr(r); q < b1; q++) bsum += w(pg.off_SB() + pg.bseg_idx(q));
+        if (srcFact < 1.0) bsum *= srcFact;
+        const double f = w(pg.off_F() + r) - bsum;
+        w(pg.off_F() + r) = f;
+        bad |= !isfinite(f);
+        nrm2 += f * f;
+    }
+    return nrm2;
+}
+
+// ---------------------------------------------------------------------------
+// numeric refactor on the fixed pattern with the host's static pivot order, then
+// the triangular solves.  delta (in pivot coordinates) ends up in the wv slots.
+// Returns false when a pivot vanished or the solution is non-finite.
+// ---------------------------------------------------------------------------
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ bool factor_and_solve(const PG &pg, const LU &lu, W &w, bool &singular)
+{
+    if constexpr (PG::kStatic) return LU::factor_and_solve(w, singular);
+    singular = false;
+    for (int k = 0; k < lu.n(); k++) {
+        const int ds = pg.off_LU() + lu.diag_slot(k);
+        const double dgl = w(ds);
+        if (!(fabs(dgl) >= DBL_MIN) || !isfinite(dgl)) singular = true;
+        const double inv = 1.0 / dgl;
+        w(ds) = inv;
+        const int l0 = lu.Lptr(k), l1 = lu.Lptr(k + 1);
+        const int u0 = lu.Uptr(k), u1 = lu.Uptr(k + 1);
+        const int t0 = lu.tgt_ptr(k);
+            for (int e = l0; e < l1; e++) {
+            const int ls = pg.off_LU() + lu.L_slot(e);
+            const double l = w(ls) * inv;
+            w(ls) = l;
+                    for (int q = u0; q < u1; q++) {
+                const int ts = pg.off_LU() + lu.tgt(t0 + (e - l0) * (u1 - u0) + (q - u0));
+                w(ts) = w(ts) - l * w(pg.off_LU() + lu.U_slot(q));
+            }
+        }
+    }
+    // forward: z = L^-1 P F
+    for (int k = 0; k < lu.n(); k++) w(pg.off_wv() + k) = w(pg.off_F() + lu.rowperm(k));
+    for (int k = 0; k < lu.n(); k++) {
+        const double zk = w(pg.off_wv() + k);
+        const int l1 = lu.Lptr(k + 1);
+            for (int e = lu.Lptr(k); e < l1; e++) {
+            const int i = pg.off_wv() + lu.L_row(e);
+            w(i) = w(i) - w(pg.off_LU() + lu.L_slot(e)) * zk;
+        }
+    }
+    // backward: y = U^-1 z
+    bool finite = true;
+    for (int kk = 0; kk < lu.n(); kk++) {
+        const int k = lu.n() - 1 - kk;
+        double acc = w(pg.off_wv() + k);
+        const int u1 = lu.Uptr(k + 1);
+            for (int q = lu.Uptr(k); q < u1; q++)
+            acc -= w(pg.off_LU() + lu.U_slot(q)) * w(pg.off_wv() + lu.U_col(q));
+        acc *= w(pg.off_LU() + lu.diag_slot(k));
+        w(pg.off_wv() + k) = acc;
+        finite &= isfinite(acc);
+    }
+    return finite && !singular;
+}
+
+// u[colperm[k]] -= delta[k]
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ void apply_update(const PG &pg, const LU &lu, W &w)
+{
+    if constexpr (PG::kStatic) { LU::apply_update(w); return; }
+    for (int k = 0; k < lu.n(); k++) {
+        const int j = pg.off_u() + lu.colperm(k);
+        w(j) = w(j) - w(pg.off_wv() + k);
+    }
+}
+
+template <typename PG, typename W>
+__device__ __forceinline__ void load_lane_params(const PG &pg, W &w, const double *lanes, int64_t P,
+                                                 int64_t lane)
+{
+    CB_UNROLL
+    for (int c = 0; c < pg.n_lane_cols(); c++) w(pg.off_lp() + c) = lanes[(int64_t)c * P + lane];
+}
+
+// ---------------------------------------------------------------------------
+// DC body: _dc_pcnr_newton (solve.jl:599-698) and the plain-Newton restatement of
+// _dc_newton_compiled (solve.jl:542-578), one lane per thread, masked lanes.
+// ---------------------------------------------------------------------------
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ void dc_body(const PG &pg, const LU &lu, W &w, const Program &p,
+                                        const SpecArgs &sp, const DcArgs &a)
+{
+    const int64_t lane0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = lane0 < p.P;
+    const int64_t lane = in_range ? lane0 : p.P - 1;      // clamp: compute, never commit
+    const bool act = in_range && (a.active == nullptr || a.active[lane]);
+
+    load_lane_params(pg, w, p.lanes, p.P, lane);
+    bool cold = true;
+    CB_UNROLL
+    for (int i = 0; i < pg.n(); i++) {
+        const double v = a.u[(int64_t)i * p.P + lane];
+        w(pg.off_u() + i) = v;
+        cold &= (v == 0.0);
+    }
+    const double gshunt = a.gshunt_lane ? a.gshunt_lane[lane] : sp.gshunt;
+    const double srcFact = a.srcfact_lane ? a.srcfact_lane[lane] : sp.srcFact;
+    const int lim0 = pg.n() - pg.n_limits();
+    const bool pcnr = (a.algorithm == 0);
+    bool initjct = false;
+    if (pcnr && cold) {                                   // solve.jl:622-627
+        CB_UNROLL
+        for (int k = 0; k < pg.n_limits(); k++) {
+            const int r = pg.limit_init_ref(k);
+            w(pg.off_u() + lim0 + k) = r >= 0 ? pg.uniform(r) : w(pg.off_lp() + ~r);
+        }
+        initjct = true;
+    }
+    eval_all(pg, w, a.t, sp.mode, false);                 // static stamps + sources (t fixed)
+
+    bool done = !act;
+    bool settling = false;
+    int status = CB200_LANE_MAXITER, solves = 0, iter = 0;
+    bool conv = false;
+    while (true) {
+        if (__all_sync(0xffffffffu, done)) break;
+        if (!settling) iter++;
+        // loop bound: PCNR `for iter in 1:maxiters`; Newton: maxiters solves then a final test
+        const int bound = pcnr ? a.maxiters : a.maxiters + 1;
+        if (!done && iter > bound) { done = true; status = CB200_LANE_MAXITER; }
+        eval_nonlinear(pg, w, a.t, sp.mode, initjct);
+        initjct = false;
+        bool bad;
+        const double nrm2 = assemble<false>(pg, lu, w, 0.0, gshunt, srcFact, bad);
+        if (done) continue;
+        if (bad) { done = true; status = CB200_LANE_NONFINITE; continue; }
+        if (sqrt(nrm2) < a.abstol) {
+            if (!pcnr || settling) { done = true; conv = true; status = CB200_LANE_OK; continue; }
+            // settle the limit slots and re-verify (solve.jl:640-663)
+            CB_UNROLL
+            for (int k = 0; k < pg.n_limits(); k++) w(pg.off_u() + lim0 + k) = w(pg.off_limw() + k);
+            settling = true;
+            continue;
+        }
+        settling = false;
+        if (!pcnr && iter > a.maxiters) { done = true; status = CB200_LANE_MAXITER; continue; }
+        bool singular;
+        const bool ok = factor_and_solve(pg, lu, w, singular);
+        if (!ok) { done = true; status = singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE; continue; }
+        apply_update(pg, lu, w);
+        solves++;
+        if (pcnr) {                                         // CORRECT  solve.jl:686-689
+            CB_UNROLL
+            for (int k = 0; k < pg.n_limits(); k++) w(pg.off_u() + lim0 + k) = w(pg.off_limw() + k);
+        }
+    }
+    if (act) {
+        CB_UNROLL
+        for (int i = 0; i < pg.n(); i++) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+        a.status[lane] = status;
+        a.iters[lane] += solves;
+        a.converged[lane] = conv ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fixed-step transient body: the whole time loop of a lane on the device.
+//   du = gamma*(u - u_n) + dterm
+//   BE:    gamma = 1/h,      dterm = 0
+//   trap:  gamma = 2/h,      dterm = -du_n                      (first step BE)
+//   Gear2: gamma = 3/(2h),   dterm = -(u_n - u_{n-1})/(2h)      (first step BE)
+// Newton per step from u = u_n: rebuild, F, stop when ||F||_2 < abstol, otherwise
+// solve J delta = F and update; at most max_nl solves.  t_k = t0 + k*h.
+// ---------------------------------------------------------------------------
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w, const Program &p,
+                                                const SpecArgs &sp, const TranArgs &a)
+{
+    const int64_t lane0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = lane0 < p.P;
+    const int64_t lane = act ? lane0 : p.P - 1;
+
+    load_lane_params(pg, w, p.lanes, p.P, lane);
+    CB_UNROLL
+    for (int i = 0; i < pg.n(); i++) {
+        w(pg.off_u() + i) = a.u[(int64_t)i * p.P + lane];
+        w(pg.off_dterm() + i) = 0.0;
+        w(pg.off_un() + i) = 0.0;
+    }
+    eval_all(pg, w, a.t0, CB200_MODE_TRAN, false);
+
+    int status = a.status[lane], solves = 0;       // keeps an InitialFailure from the DC init
+    int64_t tp = 0;
+    if (act)
+        for (int q = 0; q < a.n_save; q++)
+            a.out[((int64_t)q * a.T + tp) * p.P + lane] = read_u(pg, w, __ldg(a.save_idx + q));
+    tp++;
+    const double h = a.h;
+    // a specialised kernel is generated for one integration method: branches on it fold
+    const int amethod = PG::kMethod >= 0 ? PG::kMethod : a.method;
+    for (int64_t k = 1; k <= a.nsteps; k++) {
+        const double t = a.t0 + (double)k * h;
+        const int method = (k == 1) ? CB200_METHOD_BE : amethod;
+        const double gamma = method == CB200_METHOD_BE ? 1.0 / h
+                           : method == CB200_METHOD_TRAP ? 2.0 / h : 3.0 / (2.0 * h);
+        // history terms; un <- u
+        CB_UNROLL
+        for (int i = 0; i < pg.n(); i++) {
+            const double ui = w(pg.off_u() + i);
+            if (method == CB200_METHOD_GEAR2) w(pg.off_dterm() + i) = -(ui - w(pg.off_un() + i)) / (2.0 * h);
+            else if (method == CB200_METHOD_BE) w(pg.off_dterm() + i) = 0.0;
+            /* trap: dterm already holds -du_n */
+            w(pg.off_un() + i) = ui;
+        }
+        eval_sources_step(pg, w, k, a.t0, h, CB200_MODE_TRAN);
+        bool done = false;
+        int st = CB200_LANE_OK;
+        for (int it = 0;; it++) {
+            eval_nonlinear(pg, w, t, CB200_MODE_TRAN, false);
+            bool bad;
+            const double nrm2 = assemble<true>(pg, lu, w, gamma, sp.gshunt, sp.srcFact, bad);
+            if (!done) {
+                if (bad) { done = true; st = CB200_LANE_NONFINITE; }
+                else if (sqrt(nrm2) < a.abstol) { done = true; }
+                else if (it >= a.max_nl) { done = true; st = CB200_LANE_MAXITER; }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+            bool singular;
+            const bool ok = factor_and_solve(pg, lu, w, singular);
+            if (!done) {
+                if (!ok) { done = true; st = singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE; }
+                else { apply_update(pg, lu, w); solves++; }
+            }
+        }
+        if (st != CB200_LANE_OK && status == CB200_LANE_OK) status = st;
+        if (st == CB200_LANE_NONFINITE || st == CB200_LANE_SINGULAR) {  // dead lane: hold last state
+            CB_UNROLL
+            for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
+        }
+        if (amethod == CB200_METHOD_TRAP) {               // dterm <- -du_{n+1}
+            CB_UNROLL
+            for (int i = 0; i < pg.n(); i++)
+                w(pg.off_dterm() + i) = -(gamma * (w(pg.off_u() + i) - w(pg.off_un() + i)) + w(pg.off_dterm() + i));
+        }
+        if (k % a.save_every == 0 || k == a.nsteps) {
+            if (act)
+                for (int q = 0; q < a.n_save; q++)
+                    a.out[((int64_t)q * a.T + tp) * p.P + lane] = read_u(pg, w, __ldg(a.save_idx + q));
+            tp++;
+        }
+    }
+    if (act) {
+        CB_UNROLL
+        for (int i = 0; i < pg.n(); i++) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+        a.status[lane] = status;
+        a.iters[lane] += solves;
+    }
+}
+
+}  // namespace cb200

@@ -1,0 +1,46 @@
+// specialize.h -- circuit-specialised kernel generation (see specialize.cpp).
+#pragma once
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "cb200_internal.h"
+#include "kernels.h"
+
+namespace cb200 {
+
+constexpr int kSpecAbi = 3;
+
+struct SpecInput {
+    const Structure *st;
+    const Program *prog;              // workspace offsets / n_slots
+    const std::vector<int> *dev_kind, *dev_flags, *dev_node_ptr, *dev_nodes, *dev_param_ptr,
+        *dev_params, *dev_gbase, *dev_cbase, *dev_bbase, *src_list, *nl_list, *limit_init_ref;
+    const std::vector<double> *uniform;
+    const std::vector<unsigned char> *src_uniform;
+    int method;                       // CB200_METHOD_* compiled into the transient kernel
+    const LuSchedule *lu_dc, *lu_tr;
+    int n_lane_cols;
+    int block, min_blocks;            // __launch_bounds__ of the generated kernels
+};
+
+typedef cudaError_t (*spec_dc_fn)(const Program *, const SpecArgs *, const DcArgs *, cudaStream_t);
+typedef cudaError_t (*spec_tran_fn)(const Program *, const SpecArgs *, const TranArgs *, cudaStream_t);
+
+struct SpecModule {
+    void *dl = nullptr;
+    spec_dc_fn dc = nullptr;
+    spec_tran_fn tran_fixed = nullptr;
+    int block = 0;
+    std::string path;
+};
+
+std::string generate_spec_source(const SpecInput &in);
+// Returns "" on success.  The shared object is cached under cache_dir, keyed by a hash
+// of the generated source and of the headers it includes.
+std::string build_and_load_spec(const std::string &src, const std::string &csrc_dir,
+                                const std::string &cache_dir, bool compile_only, SpecModule &out);
+void unload_spec(SpecModule &m);
+
+}  // namespace cb200

@@ -42,7 +42,8 @@ def inverter_builder(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
     """CMOS inverter of benchmarks/benchmark_common.jl:82-106 restated with the
     in-tree native ``SimpleMOSFET`` (devices.jl:1637): NMOS pull-down plus a PMOS
     modelled as the complementary square-law device is not expressible with
-    SimpleMOSFET (n-type only), so the pull-up is a resistive load; the `sp_mos1`
+    SimpleMOSFET (n-type only), so the pull-up is a resistive load (lambda = 0: with
+    lambda != 0 the reference's square-law model is discontinuous at Vds = Vgs - Vth); the `sp_mos1`
     Verilog-A tier replaces this builder once the VA emitter lands.
     Nodes vdd, in, out."""
     ctx = MNAContext() if ctx is None else ctx
@@ -54,7 +55,7 @@ def inverter_builder(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
                   [0.0, 0.0, params.Vdd, params.Vdd, 0.0, 0.0, params.Vdd, params.Vdd])
     stamp(VoltageSource(0.0, tran=pwl, name="VIN"), ctx, vin, 0)
     stamp(Resistor(params.Rload, name="RL"), ctx, vdd, out)
-    stamp(SimpleMOSFET(Vth=0.7, K=params.K, lambda_=0.02, Cgd=1e-15, Cgs=2e-15, name="MN"),
+    stamp(SimpleMOSFET(Vth=0.7, K=params.K, lambda_=0.0, Cgd=1e-15, Cgs=2e-15, name="MN"),
           ctx, out, vin, 0)
     stamp(Capacitor(params.CL, name="CL"), ctx, out, 0)
     return ctx

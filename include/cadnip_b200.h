@@ -165,6 +165,8 @@ typedef struct cb200_tran_opts {
  * library's own stream).                                                      */
 typedef struct cb200_stats {
     double  kernel_ms;         /* sum of kernel time of the last dc/tran call   */
+    double  tran_kernel_ms;    /* the time-loop kernel alone (dominant kernel)  */
+    double  dc_kernel_ms;      /* DC / initialisation kernels                    */
     double  h2d_ms, d2h_ms;    /* copies done inside the last call              */
     int64_t launches;          /* kernels launched by the last call             */
     int64_t newton_iters;      /* sum over lanes                                */
@@ -208,6 +210,23 @@ int cb200_analyze(cb200_handle *h, const cb200_spec *spec, double gamma);
 /* perm arrays are int64 1-based: pivot k eliminates row rowperm[k], col colperm[k]. */
 int cb200_get_pivot_order(const cb200_handle *h, int64_t *rowperm, int64_t *colperm,
                           int64_t *nnz_lu);
+
+/* The emitter (north_star: "a new emitter lowers each device model's stamp function
+ * ... to hand-written-style sm_100a CUDA C"): generates, compiles (nvcc, cached under
+ * cache_dir by content hash) and loads kernels specialised for THIS circuit -- device
+ * table, stamp segments, pattern and both LU schedules become compile-time
+ * constants and the lane state lives in registers.  csrc_dir is the directory that
+ * holds lane_kernels.cuh.  (method, dt) select the transient schedule and the integration
+ * method compiled into the time-loop kernel.  flags bit0: compile only.  Without this call the table-driven kernels are used;
+ * both instantiate the same device code.                                         */
+int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t method, double dt,
+                     const char *csrc_dir, const char *cache_dir, int32_t flags);
+int cb200_is_specialized(const cb200_handle *h);
+/* Host-only emitter entry (no device): description + nominal |J| magnitudes for the DC
+ * and transient schedules -> generated CUDA source (returns its length; negative =
+ * error).  Lets the emitter be tested where no GPU is present.                      */
+int64_t cb200_emit_source(const cb200_desc *desc, const double *absJ_dc, const double *absJ_tr,
+                          int32_t method, int64_t P, int32_t num_sms, char *out, int64_t cap);
 
 /* ---- evaluation only: fast_rebuild! (src/mna/precompile.jl:493-537) ------ */
 /* x: [n][P] host (lane fastest) or NULL for ZERO_VECTOR; outputs host arrays

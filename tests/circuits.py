@@ -77,7 +77,7 @@ def controlled_sources(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
     ctx = _ctx(ctx)
     a = get_node(ctx, "a"); b = get_node(ctx, "b"); c = get_node(ctx, "c"); d = get_node(ctx, "d")
     e = get_node(ctx, "e"); f = get_node(ctx, "f"); g = get_node(ctx, "g")
-    Iv = stamp(VoltageSource(2.0, name="V1"), ctx, a, 0)
+    Iv = stamp(VoltageSource(2.0, tran=SinWave(2.0, 1.0, 1e6), name="V1"), ctx, a, 0)
     stamp(Resistor(1e3), ctx, a, b)
     stamp(Resistor(2e3), ctx, b, 0)
     stamp(VCVS(3.0, name="E1"), ctx, c, 0, b, 0)
@@ -90,10 +90,20 @@ def controlled_sources(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
     stamp(Resistor(1e3), ctx, f, 0)
     stamp(CurrentSource(1e-3, name="I1"), ctx, g, 0)
     stamp(Resistor(1e3), ctx, g, 0)
-    stamp(Inductor(1e-3, name="L1"), ctx, g, f)
+    hh = get_node(ctx, "h")
+    stamp(Inductor(1e-3, name="L1"), ctx, g, hh)
+    stamp(Resistor(2e3), ctx, hh, 0)
     stamp(Capacitor(1e-9), ctx, d, 0)
-    stamp(CCVS(50.0, name="H2"), ctx, e, d, g, f)         # 4-terminal form (own sensing branch)
-    stamp(CCCS(0.5, name="F2"), ctx, c, 0, a, b)
+    k = get_node(ctx, "k"); m = get_node(ctx, "m"); q = get_node(ctx, "q")
+    stamp(Resistor(1e3), ctx, a, k)                       # a -[1k]- k -(H2 sense)- m -[1k]- gnd
+    stamp(Resistor(1e3), ctx, m, 0)
+    stamp(CCVS(50.0, name="H2"), ctx, q, 0, k, m)         # 4-terminal form (own sensing branch)
+    stamp(Resistor(1e3), ctx, q, 0)
+    r = get_node(ctx, "r"); s2 = get_node(ctx, "s"); u = get_node(ctx, "u")
+    stamp(Resistor(2e3), ctx, a, r)
+    stamp(Resistor(1e3), ctx, s2, 0)
+    stamp(CCCS(0.5, name="F2"), ctx, u, 0, r, s2)         # 4-terminal form
+    stamp(Resistor(1e3), ctx, u, 0)
     return ctx
 
 
@@ -104,7 +114,7 @@ def mos_amp(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
     stamp(VoltageSource(3.3, name="VDD"), ctx, vdd, 0)
     stamp(VoltageSource(params.vg, tran=PulseWave(0.0, 2.0, 1e-9, 1e-9, 1e-9, 5e-9, 14e-9), name="VG"), ctx, g, 0)
     stamp(Resistor(params.rd), ctx, vdd, d)
-    stamp(SimpleMOSFET(Vth=0.6, K=2e-3, lambda_=0.05, Cgd=2e-15, Cgs=5e-15, name="M1"), ctx, d, g, 0)
+    stamp(SimpleMOSFET(Vth=0.6, K=2e-3, lambda_=0.0, Cgd=2e-15, Cgs=5e-15, name="M1"), ctx, d, g, 0)
     stamp(DiodeWithCap(Is=1e-14, Vt=0.026, n=1.0, Cj0=2e-13, Vj=0.7, m=0.5, name="DC1"), ctx, 0, d)
     stamp(Capacitor(1e-13), ctx, d, 0)
     return ctx

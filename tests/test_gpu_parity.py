@@ -1,0 +1,278 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, same seeded
+inputs.  Bars (BASELINE.json north_star): pattern / stamp maps identical integers;
+fixed-step DC points and waveforms within 1e-9 relative / 1e-12 absolute."""
+import math
+
+import numpy as np
+import pytest
+
+import cadnip_b200 as cb
+import cadnip_oracle as ora
+import circuits
+from cadnip_b200 import backend
+from cadnip_b200.workloads import clipper_sweep, inverter_sweep, CLIPPER_DT, CLIPPER_TSPAN
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-9, 1e-12
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.all(np.abs(a - b) <= atol + rtol * np.maximum(np.abs(a), np.abs(b)))
+
+
+def maxerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b) / (ATOL / RTOL + np.maximum(np.abs(a), np.abs(b)))))
+
+
+def lowered_sweep(cs, mode="tran"):
+    params, P = cs.lane_params()
+    return cb.lower(cs.builder, params, cb.MNASpec(mode=mode), P=P)
+
+
+def small_sweeps():
+    """(name, CircuitSweep) pairs covering every device kind."""
+    rng = np.random.default_rng(20261018)
+    out = []
+    out.append(("divider", cb.CircuitSweep(circuits.divider,
+                                           cb.ProductSweep(R1=np.linspace(100, 2000, 7), R2=np.linspace(100, 2000, 5)))))
+    out.append(("rectifier", cb.CircuitSweep(circuits.rectifier(True), cb.Sweep(dummy=[0.0]), dummy=0.0)))
+    out.append(("chain", cb.CircuitSweep(circuits.chain(True), cb.Sweep(vsrc=np.arange(0.5, 20.01, 0.5)))))
+    out.append(("chain_nolim", cb.CircuitSweep(circuits.chain(False), cb.Sweep(vsrc=np.arange(0.5, 5.01, 0.5)))))
+    out.append(("controlled", cb.CircuitSweep(circuits.controlled_sources, cb.Sweep(dummy=[0.0, 1.0, 2.0]), dummy=0.0)))
+    out.append(("mos_amp", cb.CircuitSweep(circuits.mos_amp,
+                                           cb.ProductSweep(vg=np.linspace(0.0, 2.5, 9), rd=rng.uniform(500, 5e3, 4)))))
+    out.append(("clipper", clipper_sweep(6, 5)))
+    return out
+
+
+SWEEPS = small_sweeps()
+
+
+@pytest.mark.parametrize("name,cs", SWEEPS, ids=[s[0] for s in SWEEPS])
+def test_pattern_and_maps_bit_exact(name, cs):
+    lc = lowered_sweep(cs, "dcop")
+    h = backend.Handle(lc)
+    try:
+        colptr, rowval = h.pattern()
+        maps = h.maps()
+    finally:
+        h.close()
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    S = ora.Structure(nl, ora.make_spec(mode="dcop"))
+    coo = S.coo()
+    a = S.arrays()
+    # the host's COO coordinates and allocation order equal what running the builder
+    # against the oracle's MNAContext produces
+    assert (S.n_nodes, S.n_currents, S.n_charges, S.n_limits) == (lc.n_nodes, lc.n_currents, lc.n_charges, lc.n_limits)
+    assert np.array_equal(coo["G_I"], lc.G_I) and np.array_equal(coo["G_J"], lc.G_J)
+    assert np.array_equal(coo["C_I"], lc.C_I) and np.array_equal(coo["C_J"], lc.C_J)
+    assert np.array_equal(coo["b_I"], lc.b_I)
+    assert np.array_equal(colptr, a["colptr"]) and np.array_equal(rowval, a["rowval"])
+    assert np.array_equal(maps["G_coo_to_idx"], a["G_coo_to_idx"])
+    assert np.array_equal(maps["C_coo_to_idx"], a["C_coo_to_idx"])
+    assert np.array_equal(maps["b_resolved"], a["b_resolved"])
+    assert np.array_equal(maps["G_diag_idx"], a["G_diag_idx"])
+
+
+@pytest.mark.parametrize("name,cs", SWEEPS, ids=[s[0] for s in SWEEPS])
+def test_rebuild_values_match_oracle(name, cs):
+    """K1 device evaluation + K2 segmented assembly == fast_rebuild! at random states."""
+    lc = lowered_sweep(cs, "tran")
+    P, n = lc.P, lc.n
+    rng = np.random.default_rng(7)
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        nl = ora.OracleNetlist(lc.netlist_tables())
+        for trial, (t, initjct) in enumerate([(0.0, False), (3.3e-4, False), (0.0, True)]):
+            x = rng.uniform(-1.0, 1.0, (n, P)) if trial < 2 else np.zeros((n, P))
+            spec = cb.MNASpec(mode="tran", gshunt=1e-9 if trial == 1 else 0.0,
+                              srcFact=0.5 if trial == 1 else 1.0)
+            G, C, b, lw = comp.handle.eval(spec, x, t=t, initjct=initjct)
+            for lane in sorted(set([0, P // 2, P - 1])):
+                S = ora.Structure(nl.for_lane(lane), ora.make_spec(spec))
+                Go, Co, bo, lwo = S.rebuild(x[:, lane], t=t, initjct=initjct)
+                assert close(G[:, lane], Go), (name, trial, lane, maxerr(G[:, lane], Go))
+                assert close(C[:, lane], Co), (name, trial, lane)
+                assert close(b[:, lane], bo), (name, trial, lane, b[:, lane], bo)
+                if lc.n_limits:
+                    assert close(lw[:, lane], lwo)
+    finally:
+        comp.close()
+
+
+@pytest.mark.parametrize("name,cs", SWEEPS, ids=[s[0] for s in SWEEPS])
+def test_dc_matches_oracle(name, cs):
+    lc = lowered_sweep(cs, "dcop")
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="dcop"))
+    try:
+        x, st, it = comp.dc()
+    finally:
+        comp.close()
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
+    assert np.array_equal(st, sto), (name, st, sto)
+    assert close(x.T, xo), (name, maxerr(x.T, xo))
+    if lc.n_limits:       # PCNR iteration counts are part of the reference's contract
+        assert np.array_equal(it, ito), (name, it, ito)
+
+
+def test_dc_api_objects():
+    sol = cb.dc(cb.MNACircuit(circuits.rectifier(True)))
+    assert sol.converged and 0.55 < sol["out"] < 0.75
+    assert sol["D1_vdlim"] == pytest.approx(sol["out"], abs=1e-6)
+    assert sol.iters <= 10
+    r = np.arange(100.0, 2000.1, 100.0)
+    res = cb.dc(cb.CircuitSweep(circuits.divider, cb.ProductSweep(R1=r, R2=r)))
+    assert len(res) == 400
+    for p, s in res:
+        assert s.converged and s["I_V"] == pytest.approx(-1.0 / (p["R1"] + p["R2"]), abs=1e-8)
+
+
+TRAN_CASES = [
+    ("clipper", clipper_sweep(5, 4), (0.0, 4e-4), 1e-6, [1, 2, 3, 4]),
+    ("mos_amp", SWEEPS[5][1], (0.0, 3e-8), 1e-10, None),
+    ("controlled", SWEEPS[4][1], (0.0, 2e-6), 1e-8, None),
+]
+
+
+@pytest.mark.parametrize("method", ["be", "trap", "gear2"])
+@pytest.mark.parametrize("name,cs,tspan,dt,save", TRAN_CASES, ids=[c[0] for c in TRAN_CASES])
+def test_fixed_step_waveforms_match_oracle(name, cs, tspan, dt, save, method):
+    lc = lowered_sweep(cs, "tran")
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    save = save or list(range(1, lc.n + 1))
+    try:
+        wave = comp.tran(tspan, dt, method=method, save_idxs=save, save_every=1)
+        r = wave.fetch()
+        xf = wave.final_state()
+        wave.free()
+    finally:
+        comp.close()
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    o = ora.make_tran_opts(method={"be": 0, "trap": 1, "gear2": 2}[method], dt=dt)
+    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), tspan[0], tspan[1], o, save, nthreads=0)
+    T = r["u"].shape[1]
+    assert (ro["T"] == T).all()
+    assert np.array_equal(r["t"], ro["t"][:T])
+    assert np.array_equal(r["status"], ro["status"]), (r["status"], ro["status"])
+    gpu = np.transpose(r["u"], (2, 1, 0))            # [P][T][save]
+    assert close(gpu, ro["u"][:, :T, :]), (name, method, maxerr(gpu, ro["u"][:, :T, :]))
+    assert np.array_equal(r["newton_iters"], ro["newton_iters"]), (name, method)
+    assert np.all(np.isfinite(xf))
+
+
+def test_save_every_decimation_and_api():
+    cs = clipper_sweep(3, 2)
+    res = cb.tran(cs, (0.0, 2e-4), solver="ImplicitEuler", dt=1e-6, saveat=1e-5, save_idxs=["out", "in"])
+    assert len(res) == 6
+    p, sol = res[4]
+    assert sol.retcode == "Success" and len(sol.t) == 21 and sol.t[-1] == pytest.approx(2e-4)
+    assert sol["in"][5] == pytest.approx(5.0 * math.sin(2 * math.pi * 1e3 * 5e-5), rel=1e-12)
+    full = cb.tran(cs, (0.0, 2e-4), solver="ImplicitEuler", dt=1e-6, save_idxs=["out"])
+    assert np.array_equal(full[4][1]["out"][::10], sol["out"])
+    assert sol(1.5e-5)[0] == pytest.approx(0.5 * (sol["out"][1] + sol["out"][2]))
+    one = cb.tran(cb.MNACircuit(circuits.clipper, R=1e3, C=1e-9), (0.0, 1e-4), solver="Trapezoid", dt=1e-6)
+    assert one.retcode == "Success" and one.u.shape == (101, 4)
+
+
+def test_full_size_properties_clipper():
+    """BASELINE config C2 at full size (65,536 lanes x 2000 BE steps): size-independent
+    properties plus oracle parity on a seeded sample of lanes."""
+    cs = clipper_sweep(256, 256)
+    lc = lowered_sweep(cs, "tran")
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        wave = comp.tran(CLIPPER_TSPAN, CLIPPER_DT, method="be", save_idxs=["in", "out"], save_every=10)
+        r = wave.fetch()
+        wave.free()
+    finally:
+        comp.close()
+    u = r["u"]
+    assert u.shape == (2, 201, 65536) and (r["status"] == 0).all()
+    t = r["t"]
+    # the source node follows SIN(0 5 1k) exactly in every lane
+    vin = 5.0 * np.sin(2 * np.pi * 1e3 * t)
+    assert np.max(np.abs(u[0] - vin[:, None])) < 1e-9
+    # clipping: out never exceeds a diode drop, and never goes below the source's minimum
+    assert u[1].max() < 0.85 and u[1].min() >= -5.0 - 1e-9
+    # lanes with equal R*C product and equal R share... (not in general); instead check
+    # monotonicity in C at fixed R of the negative-peak lag: larger C -> smaller |min|
+    vmin = u[1].min(axis=0).reshape(256, 256)        # [C][R]
+    assert np.all(np.diff(vmin[:, 255], axis=0) >= -1e-9)
+    rng = np.random.default_rng(20261018)
+    lanes = np.sort(rng.choice(65536, 24, replace=False))
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    o = ora.make_tran_opts(method=0, dt=CLIPPER_DT, save_every=10)
+    for lane in lanes:
+        ro = ora.tran(nl.for_lane(int(lane)), ora.make_spec(mode="tran"), 0.0, 2e-3, o,
+                      [lc.index_of("in"), lc.index_of("out")])
+        assert close(u[:, :, lane].T, ro["u"]), (lane, maxerr(u[:, :, lane].T, ro["u"]))
+        assert r["newton_iters"][lane] == ro["newton_iters"]
+
+
+def test_inverter_sweep_tran_sample():
+    cs = inverter_sweep(6, 5, 4)
+    lc = lowered_sweep(cs, "tran")
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        wave = comp.tran((0.0, 4e-7), 1e-10, method="trap", save_idxs=["out"], save_every=20)
+        r = wave.fetch()
+        wave.free()
+    finally:
+        comp.close()
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    o = ora.make_tran_opts(method=1, dt=1e-10, save_every=20)
+    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 4e-7, o, [lc.index_of("out")])
+    gpu = np.transpose(r["u"], (2, 1, 0))
+    assert close(gpu, ro["u"][:, :gpu.shape[1], :]), maxerr(gpu, ro["u"][:, :gpu.shape[1], :])
+    assert (r["status"] == 0).all()
+
+
+def test_fails_loudly_without_lanes():
+    lc = cb.lower_circuit(cb.MNACircuit(circuits.rectifier(True)))
+    h = backend.Handle(lc)
+    try:
+        with pytest.raises(backend.CB200Error):
+            h.dc(cb.MNASpec(mode="dcop"))
+    finally:
+        h.close()
+
+
+# ---- the emitter: circuit-specialised kernels ---------------------------------
+SPEC_CASES = [("clipper", clipper_sweep(5, 4), (0.0, 4e-4), 1e-6, "be"),
+              ("clipper_trap", clipper_sweep(3, 3), (0.0, 2e-4), 1e-6, "trap"),
+              ("mos_amp", SWEEPS[5][1], (0.0, 3e-8), 1e-10, "gear2"),
+              ("controlled", SWEEPS[4][1], (0.0, 2e-6), 1e-8, "trap")]
+
+
+@pytest.mark.parametrize("name,cs,tspan,dt,method", SPEC_CASES, ids=[c[0] for c in SPEC_CASES])
+def test_specialised_kernels_match_oracle_and_generic(name, cs, tspan, dt, method):
+    lc = lowered_sweep(cs, "tran")
+    save = list(range(1, lc.n + 1))
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        wave = comp.tran(tspan, dt, method=method, save_idxs=save)
+        assert not comp.handle.is_specialized()
+        rg = wave.fetch(); wave.free()
+        comp.specialize(dt, method)
+        assert comp.handle.is_specialized()
+        wave = comp.tran(tspan, dt, method=method, save_idxs=save)
+        rs = wave.fetch(); wave.free()
+        xdc_s, st_s, it_s = comp.dc()
+    finally:
+        comp.close()
+    # specialised vs table-driven: same arithmetic, same iteration counts
+    assert np.array_equal(rs["status"], rg["status"])
+    assert np.array_equal(rs["newton_iters"], rg["newton_iters"])
+    assert close(rs["u"], rg["u"]), maxerr(rs["u"], rg["u"])
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    o = ora.make_tran_opts(method={"be": 0, "trap": 1, "gear2": 2}[method], dt=dt)
+    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), tspan[0], tspan[1], o, save)
+    gpu = np.transpose(rs["u"], (2, 1, 0))
+    assert close(gpu, ro["u"][:, :gpu.shape[1], :]), (name, maxerr(gpu, ro["u"][:, :gpu.shape[1], :]))
+    assert np.array_equal(rs["newton_iters"], ro["newton_iters"])
+    xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
+    assert np.array_equal(st_s, sto) and close(xdc_s.T, xo)

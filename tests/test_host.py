@@ -1,0 +1,253 @@
+"""CPU tests of the host logic: sweep iterator algebra (test/sweep.jl:49-180), the
+recording MNAContext (test/mna/core.jl:53-233), lowering, the C-ABI surface, and the
+multi-GPU sharding plumbing under gloo (world_size 2)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cadnip_b200 as cb
+import circuits
+from cadnip_b200 import (MNAContext, ZERO_VECTOR, get_node, stamp_G, stamp_C, stamp_b, stamp,
+                         Resistor, VoltageSource, Sweep, ProductSweep, TandemSweep, SerialSweep,
+                         CircuitSweep, sweepvars, split_axes, sweepify)
+from cadnip_b200 import backend, distributed
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- MNAContext ------------------------------------------------------------
+def test_context_basics_and_stamping_primitives():
+    ctx = MNAContext()
+    assert get_node(ctx, "gnd") == 0 and get_node(ctx, "0") == 0 and get_node(ctx, "gnd!") == 0
+    n1 = get_node(ctx, "n1"); n2 = get_node(ctx, "n2")
+    assert (n1, n2) == (1, 2) and get_node(ctx, "n1") == 1 and get_node(ctx, 7) == 7
+    stamp_G(ctx, n1, n1, 1.0); stamp_G(ctx, n1, n2, -1.0); stamp_G(ctx, n2, n1, -1.0); stamp_G(ctx, n2, n2, 1.0)
+    assert ctx.G_I == [1, 1, 2, 2] and ctx.G_J == [1, 2, 1, 2] and ctx.G_V == [1.0, -1.0, -1.0, 1.0]
+    stamp_C(ctx, n1, n1, 1e-6)
+    assert len(ctx.C_V) == 1
+    stamp_b(ctx, n1, 5.0); stamp_b(ctx, n1, 3.0)
+    assert ctx.b_I == [1, 1] and sum(ctx.b_V) == 8.0
+    stamp_G(ctx, 0, n1, 1.0); stamp_G(ctx, n1, 0, 1.0); stamp_b(ctx, 0, 5.0)   # ground: ignored, not counted
+    assert len(ctx.G_V) == 4 and len(ctx.b_V) == 2
+    i1 = cb.alloc_current(ctx, "I_", "V1")
+    l1 = cb.alloc_limit(ctx, "vdlim", "D1", 1, 2, init=0.66)
+    n3 = cb.alloc_internal_node(ctx, "a_int", "D1")
+    assert n3 == 3 and ctx.node_names[-1] == "D1_a_int" and ctx.internal_node_flags[2]
+    # deferred resolution: indices move when nodes are added later (context.jl:577-581)
+    assert cb.resolve_index(ctx, i1) == 4 and cb.resolve_index(ctx, l1) == 5
+    assert ctx.limit_names == ["D1_vdlim"] and ctx.limit_init == [0.66] and cb.system_size(ctx) == 5
+    assert ctx.get_current_idx("I_V1") == cb.CurrentIndex(1)
+    cb.reset_for_restamping(ctx)
+    assert ctx.n_limits == 0 and ctx.n_nodes == 0 and not ctx.G_I
+
+
+def test_zero_vector_and_sources_reject_closures():
+    assert ZERO_VECTOR[5] == 0.0 and len(ZERO_VECTOR) == 0
+    with pytest.raises(TypeError):
+        VoltageSource(0.0, tran=lambda t: t)
+
+
+# ---- sweeps (test/sweep.jl:49-180) ------------------------------------------
+def test_sweep_iterators():
+    s = Sweep(R1=np.arange(0.1, 1.01, 0.1))
+    assert len(s) == 10 and s.sweepvars() == {"R1"}
+    assert Sweep("R1", [1, 2]) == Sweep(("R1", [1, 2])) == Sweep(R1=[1, 2])
+    with pytest.raises(ValueError):
+        Sweep(a=[1], b=[2])
+    ps = ProductSweep(R1=[1, 2, 3, 4], R2=[10, 20, 30])
+    pts = list(ps)
+    assert len(ps) == 12 and ps.size() == (4, 3)
+    assert pts[0] == (("R1", 1), ("R2", 10)) and pts[1] == (("R1", 2), ("R2", 10)) and pts[4] == (("R1", 1), ("R2", 20))
+    ts = TandemSweep(R1=[1, 2, 3], R2=[4, 5, 6])
+    assert list(ts)[1] == (("R1", 2), ("R2", 5)) and len(ts) == 3
+    with pytest.raises(ValueError):
+        TandemSweep(R1=[1, 2], R2=[1])
+    ss = SerialSweep(R1=[1, 2], R2=[7])
+    assert list(ss) == [(("R1", 1), ("R2", None)), (("R1", 2), ("R2", None)), (("R1", None), ("R2", 7))]
+    nested = ProductSweep(Sweep(A=[1, 2]), TandemSweep(B=[1, 2, 3], C=[4, 5, 6]))
+    assert len(nested) == 6 and list(nested)[3] == (("A", 2), ("B", 2), ("C", 5))
+    assert sweepvars(nested) == {"A", "B", "C"}
+    assert ProductSweep(R1=[1, 2]) == Sweep(R1=[1, 2])
+    outer, inner = split_axes(ProductSweep(A=range(1, 11), B=range(1, 9), C=range(1, 7), D=range(1, 5)), ["A", "C"])
+    assert outer.sweepvars() == {"B", "D"} and len(outer) == 32
+    assert inner.sweepvars() == {"A", "C"} and len(inner) == 60
+    assert len(sweepify([dict(r1=range(1, 11), r2=range(1, 11)), dict(r3=range(1, 11))])) == 110
+    assert cb.find_param_ranges(ps)["R2"] == (10.0, 30.0, 3)
+
+
+def test_columns_match_iteration_order():
+    sweeps = [ProductSweep(R1=[1.0, 2.0, 3.0], R2=[10.0, 20.0], R3=[5.0, 6.0]),
+              ProductSweep(Sweep(A=[1.0, 2.0]), TandemSweep(B=[1.0, 2.0, 3.0], C=[4.0, 5.0, 6.0])),
+              SerialSweep(Sweep(A=[1.0, 2.0]), ProductSweep(A=[3.0], B=[8.0, 9.0]))]
+    for sw in sweeps:
+        vals, isset = sw.columns()
+        for lane, pt in enumerate(sw):
+            for k, v in pt:
+                if v is None:
+                    assert not isset[k][lane]
+                else:
+                    assert isset[k][lane] and vals[k][lane] == v
+
+
+def test_circuit_sweep_and_alter():
+    cs = CircuitSweep(circuits.divider, ProductSweep(R1=[100.0, 200.0], R2=[100.0, 200.0, 300.0]))
+    assert len(cs) == 6 and cs.size() == (2, 3) and cs.sweepvars() == {"R1", "R2"}
+    first = next(iter(cs))
+    assert first.params.R1 == 100.0 and first.params.R2 == 100.0
+    last = list(cs)[-1]
+    assert last.params.R1 == 200.0 and last.params.R2 == 300.0
+    c = cb.MNACircuit(circuits.divider, R1=1.0, R2=2.0)
+    c2 = cb.alter(c, R1=5.0, R2=None, **{"inner.params.R3": 7.0})
+    assert c2.params.R1 == 5.0 and c2.params.R2 == 2.0 and c2.params.inner.params.R3 == 7.0 and c.params.R1 == 1.0
+    # with_mode(circuit, mode) resets the spec to defaults except temp (solve.jl:1976-1979)
+    c3 = cb.with_mode(cb.MNACircuit(circuits.divider, spec=cb.MNASpec(temp=50.0, gmin=1e-9), R1=1.0, R2=1.0), "dcop")
+    assert c3.spec.mode == "dcop" and c3.spec.temp == 50.0 and c3.spec.gmin == 1e-12
+    assert cb.with_mode(cb.MNASpec(gmin=1e-9), "dcop").gmin == 1e-9
+    # serial sweep leaves unset variables at the circuit default
+    cs2 = CircuitSweep(circuits.divider, SerialSweep(R1=[1.0, 2.0], R2=[9.0]), R1=100.0, R2=200.0)
+    p, P = cs2.lane_params()
+    assert list(p.R1) == [1.0, 2.0, 1.0] or list(p.R1) == [1.0, 2.0, 100.0]
+    assert list(p.R2)[2] == 9.0
+
+
+# ---- lowering ---------------------------------------------------------------
+def test_lowering_clipper_c2_shape():
+    """n = 4 (2 nodes + I_V1 + 1 limit), nnz = 8 with the stated entries."""
+    from cadnip_b200.workloads import clipper_sweep
+    cs = clipper_sweep(4, 3)
+    params, P = cs.lane_params()
+    lc = cb.lower(cs.builder, params, cb.MNASpec(), P=P)
+    assert P == 12 and lc.n == 4 and lc.unknown_names() == ["in", "out", "I_V1", "D1_vdlim"]
+    coords = sorted(set(zip(list(lc.G_I) + list(lc.C_I), list(lc.G_J) + list(lc.C_J))))
+    assert coords == sorted([(1, 1), (1, 2), (2, 1), (2, 2), (1, 3), (3, 1), (4, 2), (4, 4)])
+    assert lc.n_lane_cols == 2 and lc.lane_soa.shape == (2, 12)
+    # R is the fastest axis
+    assert lc.lane_soa[0, 0] != lc.lane_soa[0, 1] and lc.lane_soa[1, 0] == lc.lane_soa[1, 1]
+    t = lc.netlist_tables()
+    assert t["par"].shape[0] == 12 and list(t["kind"]) == [4, 1, 10, 2]
+    # the diode's vcrit is uniform here (Is, Vt, n are not swept)
+    assert lc.limit_init_ref[0] >= 0
+
+
+def test_structural_boundary_is_rejected():
+    def bad(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
+        ctx = MNAContext()
+        a = get_node(ctx, "a")
+        stamp(VoltageSource(1.0), ctx, a, 0)
+        if params.rs > 0:                       # branches on a swept value
+            stamp(Resistor(params.rs), ctx, a, 0)
+        return ctx
+    cs = CircuitSweep(bad, Sweep(rs=[0.0, 1.0]))
+    params, P = cs.lane_params()
+    with pytest.raises(cb.StructuralSweepError):
+        cb.lower(cs.builder, params, cb.MNASpec(), P=P)
+
+
+# ---- C ABI ------------------------------------------------------------------
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cadnip_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cb200_[a-z_]+)\s*\(", hdr)))
+    assert declared == sorted(backend.EXPORTED_SYMBOLS)
+    backend.build_library()
+    L = C.CDLL(backend.LIB_PATH)
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert backend.lib().cb200_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product must fail loudly, never fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lc = cb.lower_circuit(cb.MNACircuit(circuits.rectifier(True)))
+    with pytest.raises(backend.CB200Error) as e:
+        backend.Handle(lc)
+    assert e.value.code == backend.ENODEVICE
+    with pytest.raises(backend.CB200Error):
+        cb.dc(cb.MNACircuit(circuits.rectifier(True)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "cadnip.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "cadnip_oracle" not in src and "oracle/" not in src, f
+
+
+# ---- sharding under gloo -----------------------------------------------------
+def test_shard_slices_cover_sweep():
+    for P in (0, 1, 7, 8, 65536, 100000):
+        for world in (1, 2, 3, 8):
+            sl = [distributed.shard_slice(P, r, world) for r in range(world)]
+            got = [i for s in sl for i in range(s.start, s.stop)]
+            assert got == list(range(P))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P = 11
+
+        def run_local(sl):
+            lanes = np.arange(sl.start, sl.stop, dtype=np.float64)
+            return np.stack([lanes, lanes * 10.0])          # [save][lane]
+
+        full = distributed.run_sharded(P, run_local, lane_axis=-1)
+        q.put((rank, None if full is None else full.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[1] is None
+    full = np.array(res[0])
+    assert full.shape == (2, 11)
+    assert np.array_equal(full[0], np.arange(11.0)) and np.array_equal(full[1], np.arange(11.0) * 10)
+
+
+# ---- the emitter (host only) -------------------------------------------------
+def test_emitter_generates_compilable_source(tmp_path):
+    """cb200_emit_source -> nvcc (sm_100a cross-compile, no GPU needed)."""
+    import subprocess
+    import cadnip_oracle as ora
+    from cadnip_b200.workloads import clipper_sweep
+    cs = clipper_sweep(4, 3)
+    params, P = cs.lane_params()
+    lc = cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P)
+    S = ora.Structure(ora.OracleNetlist(lc.netlist_tables()), ora.make_spec(mode="tran"))
+    G, Cm, _, _ = S.rebuild(np.zeros(lc.n), initjct=True)       # nominal magnitudes for the pivot choice
+    src = backend.emit_source(lc, np.abs(G), np.abs(G + 1e6 * Cm), P=65536)
+    assert "cb200_spec_tran_fixed_kernel" in src and "eval_device<1>(pg, w, 2," in src
+    assert "__launch_bounds__(kBlock, kMinBlocks)" in src and "constexpr int kMinBlocks = 7;" in src
+    cu = tmp_path / "spec.cu"
+    cu.write_text(src)
+    nvcc = backend.nvcc_path()
+    if nvcc is None:
+        pytest.skip("nvcc not available")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler",
+                        "-fPIC", "-shared", "-Xptxas", "-v", "-I", os.path.join(ROOT, "cadnip.jl_b200", "csrc"),
+                        "-o", str(tmp_path / "spec.so"), str(cu)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    # the lane state must live in registers: no local-memory frame beyond libm's slow path
+    frames = [int(x) for x in re.findall(r"(\d+) bytes stack frame", r.stderr)]
+    assert max(frames) <= 64, frames
