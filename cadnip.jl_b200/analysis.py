@@ -218,6 +218,26 @@ class CompiledSweep:
                                       init_maxiters=init_maxiters)
         return self.handle.tran(self.spec, tspan[0], tspan[1], opts, self.save_indices(save_idxs), u0)
 
+    def tran_adaptive(self, tspan, dt0=None, method="trap", save_idxs=None, abstol=1e-10,
+                      reltol=1e-6, lte_abstol=1e-9, max_points=4096, dtmin=0.0, dtmax=0.0,
+                      max_nl_iters=10, tstops=None, u0=None, specialize=False) -> backend.Wave:
+        """LTE-controlled stepping, one time axis per lane.  ``tstops`` defaults to the
+        source breakpoints (``auto_tstops``, src/sweeps.jl:620-627)."""
+        if tstops is None:
+            try:
+                tstops = expand_breakpoints(self.lc.breakpoints, tspan)
+            except TypeError as e:
+                raise ValueError("source breakpoints depend on a swept parameter; pass tstops=") from e
+        self.handle.set_tstops(tstops)
+        dt0 = float(dt0) if dt0 else (tspan[1] - tspan[0]) * 1e-4
+        if specialize:
+            self.specialize(dt0, method)
+        opts = backend.make_tran_opts(method=method, adaptive=True, dt=dt0, abstol=abstol,
+                                      reltol=reltol, lte_abstol=lte_abstol, dtmin=dtmin, dtmax=dtmax,
+                                      max_nl_iters=max_nl_iters, max_points=max_points,
+                                      init=0 if u0 is None else 1)
+        return self.handle.tran(self.spec, tspan[0], tspan[1], opts, self.save_indices(save_idxs), u0)
+
     def close(self):
         self.handle.close()
 
@@ -266,21 +286,35 @@ def dc(obj, u0=None, continuation: bool = True, abstol: float = 1e-10, maxiters:
 
 def tran(obj, tspan: Tuple[float, float], solver: Optional[str] = None, abstol: float = 1e-10,
          reltol: float = 1e-8, dt: Optional[float] = None, adaptive: Optional[bool] = None,
-         saveat: Optional[float] = None, save_idxs=None, max_nl_iters: int = 10, device: int = 0):
+         saveat: Optional[float] = None, save_idxs=None, max_nl_iters: int = 10, device: int = 0,
+         max_points: int = 4096):
     """``tran!(circuit, tspan; solver, abstol, reltol, kw...)`` (sweeps.jl:588-601) and
     ``tran!(cs::CircuitSweep, tspan; kw...)`` (sweeps.jl:692-707).
 
     ``solver``: "ImplicitEuler" | "Trapezoid" | "gear2".  Fixed-step mode is the
     reference's ``solver=ImplicitEuler()/Trapezoid(), adaptive=false, dt=h``."""
     method = solver or "Trapezoid"
-    if dt is None:
-        raise ValueError("fixed-step transient needs dt= (adaptive stepping: adaptive=True)")
-    save_every = 1
-    if saveat is not None:
-        save_every = max(1, int(round(saveat / dt)))
     single = isinstance(obj, MNACircuit)
     if not single and not isinstance(obj, CircuitSweep):
         raise TypeError("tran expects an MNACircuit or CircuitSweep")
+    if adaptive or (adaptive is None and dt is None):
+        # the reference's default is a variable-step integrator (IDA, sweeps.jl:599-601)
+        comp = compile_sweep(obj, device=device)
+        try:
+            save = comp.save_indices(save_idxs)
+            wave = comp.tran_adaptive(tspan, dt0=dt, method=method, save_idxs=save, abstol=abstol,
+                                      reltol=reltol, lte_abstol=max(abstol, 1e-12),
+                                      max_nl_iters=max_nl_iters, max_points=max_points)
+            r = wave.fetch()
+            wave.free()
+        finally:
+            comp.close()
+        sols = _LazyTranSolutions(comp.lc, save, r["t"], r["u"], r["count"], r["status"],
+                                  r["newton_iters"], True)
+        return sols[0] if single else SweepResult(obj.iterator.points(), sols)
+    save_every = 1
+    if saveat is not None:
+        save_every = max(1, int(round(saveat / dt)))
     comp = compile_sweep(obj, device=device)
     try:
         save = comp.save_indices(save_idxs)

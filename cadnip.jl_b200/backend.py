@@ -166,6 +166,8 @@ def lib():
     L.cb200_tran.restype = C.c_int
     L.cb200_tran.argtypes = [vp, C.POINTER(Spec), C.c_double, C.c_double, C.POINTER(TranOpts),
                              lp, C.c_int32, dp, C.POINTER(vp)]
+    L.cb200_set_tstops.restype = C.c_int
+    L.cb200_set_tstops.argtypes = [vp, dp, C.c_int32]
     L.cb200_wave_info.restype = C.c_int
     L.cb200_wave_info.argtypes = [vp, lp, lp, ip, ip]
     L.cb200_wave_fetch.restype = C.c_int
@@ -186,7 +188,7 @@ EXPORTED_SYMBOLS = [
     "cb200_abi_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_pattern",
     "cb200_get_maps", "cb200_set_lanes", "cb200_analyze", "cb200_get_pivot_order", "cb200_eval",
     "cb200_specialize", "cb200_is_specialized", "cb200_emit_source",
-    "cb200_dc", "cb200_tran", "cb200_wave_info", "cb200_wave_fetch", "cb200_wave_final_state",
+    "cb200_dc", "cb200_tran", "cb200_set_tstops", "cb200_wave_info", "cb200_wave_fetch", "cb200_wave_final_state",
     "cb200_wave_free", "cb200_get_stats"]
 
 
@@ -398,6 +400,10 @@ class Handle:
         self._check(lib().cb200_tran(self._p, C.byref(s), float(t0), float(t1), C.byref(opts),
                                      _lp(save), len(save), _dp(uu), C.byref(ptr)))
         return Wave(self, ptr)
+
+    def set_tstops(self, tstops: Sequence[float]):
+        t = np.ascontiguousarray(tstops, dtype=np.float64)
+        self._check(lib().cb200_set_tstops(self._p, _dp(t) if t.size else None, int(t.size)))
 
     def stats(self) -> dict:
         s = Stats()

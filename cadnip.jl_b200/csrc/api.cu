@@ -155,7 +155,9 @@ struct cb200_handle {
     DevBuf<int> d_status, d_iters;
     DevBuf<unsigned char> d_conv, d_active;
     DevBuf<double> d_gshunt_lane, d_srcfact_lane;
-    DevBuf<int> d_save;
+    DevBuf<int> d_save, d_rejected;
+    std::vector<double> tstops;    // sorted breakpoints for adaptive stepping
+    DevBuf<double> d_tstops;
     std::shared_ptr<BufPool> pool;  // recycled waveform buffers (shared with live waves)
     Program prog{};
     DevLu lu[2];                   // 0: DC (gamma = 0), 1: transient
@@ -943,10 +945,45 @@ extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, do
         }
         cudaEventRecord(h->ev1, s);
     } else {
-        // tstops: breakpoints are computed by the host wrapper and passed through dtmax/.. (see
-        // cb200_tran_adaptive_stops); plain adaptive call uses none.
-        delete w;
-        return fail(h, CB200_EINVAL, "cb200_tran: adaptive stepping is provided by cb200_tran_adaptive");
+        // LTE-controlled stepping, per-lane time axis; tstops come from cb200_set_tstops
+        const int T = o->max_points > 1 ? o->max_points : 4096;
+        w->T = T;
+        const double span = t1 - t0;
+        AdaptArgs a{};
+        a.method = o->method == CB200_METHOD_BE ? CB200_METHOD_BE : CB200_METHOD_TRAP;
+        a.t0 = t0; a.t1 = t1;
+        a.dtmax = o->dtmax > 0 ? o->dtmax : span / 50.0;
+        a.dtmin = o->dtmin > 0 ? o->dtmin : span * 1e-12;
+        a.h0 = std::min(o->dt, a.dtmax);
+        a.abstol = o->abstol; a.reltol = o->reltol; a.lte_abstol = o->lte_abstol;
+        a.max_nl = o->max_nl_iters; a.n_save = n_save; a.save_idx = d_save.p; a.max_points = T;
+        if (w->d_out.alloc((size_t)std::max(1, n_save) * T * P) != cudaSuccess ||
+            w->d_t.alloc((size_t)T * P) != cudaSuccess || w->d_count.alloc(P) != cudaSuccess ||
+            (h->d_rejected.n != (size_t)P && h->d_rejected.alloc(P) != cudaSuccess)) {
+            delete w; return fail(h, CB200_ENOMEM, "cb200_tran: waveform buffer allocation failed");
+        }
+        a.tstops = h->d_tstops.p; a.n_tstops = (int)h->tstops.size();
+        a.u = h->d_state.p; a.out_t = w->d_t.p; a.out = w->d_out.p; a.count = w->d_count.p;
+        a.status = h->d_status.p; a.iters = h->d_iters.p; a.rejected = h->d_rejected.p;
+        a.ws_global = ws_global;
+        cudaEventRecord(h->ev0, s);
+        if (spec_usable(h) && h->spec_method == a.method) {
+            h->stats.launches += 1;
+            ce = h->spec.tran_adaptive(&h->prog, &sa, &a, s);
+        } else {
+            ce = launch_tran_adaptive(h->prog, h->lu[1].prog, sa, a, h->block_pref, h->smem_limit, s, &h->stats.launches);
+        }
+        cudaEventRecord(h->ev1, s);
+        if (ce == cudaSuccess) {
+            std::vector<int> cnt(P), rj(P);
+            cudaMemcpyAsync(cnt.data(), w->d_count.p, P * sizeof(int), cudaMemcpyDeviceToHost, s);
+            cudaMemcpyAsync(rj.data(), h->d_rejected.p, P * sizeof(int), cudaMemcpyDeviceToHost, s);
+            ce = cudaStreamSynchronize(s);
+            int64_t acc = 0, rejt = 0;
+            for (int64_t l = 0; l < P; l++) { acc += cnt[l] - 1; rejt += rj[l]; }
+            h->stats.steps_accepted = acc;
+            h->stats.steps_rejected = rejt;
+        }
     }
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
     if (ce != cudaSuccess) {
@@ -963,8 +1000,19 @@ extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, do
     cudaMemcpyAsync(w->d_final.p, h->d_state.p, (size_t)n * P * sizeof(double), cudaMemcpyDeviceToDevice, s);
     ce = cudaStreamSynchronize(s);
     if (ce != cudaSuccess) { delete w; return fail(h, CB200_ECUDA, cudaGetErrorString(ce)); }
-    h->stats.steps_accepted = w->nsteps * P;
+    if (!o->adaptive) h->stats.steps_accepted = w->nsteps * P;
     *out = w;
+    return CB200_OK;
+}
+
+extern "C" int cb200_set_tstops(cb200_handle *h, const double *tstops, int32_t n)
+{
+    if (!h || n < 0 || (n > 0 && !tstops)) return fail(h, CB200_EINVAL, "cb200_set_tstops: bad arguments");
+    cudaSetDevice(h->device);
+    h->tstops.assign(tstops, tstops + n);
+    std::sort(h->tstops.begin(), h->tstops.end());
+    CUDA_TRY(h, h->d_tstops.upload(h->tstops, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return CB200_OK;
 }
 

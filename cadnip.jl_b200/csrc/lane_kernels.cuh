@@ -867,4 +867,178 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
     }
 }
 
+// ---------------------------------------------------------------------------
+// adaptive transient body: trapezoidal (or BE) integration with LTE step control, one
+// private time axis per lane, masked lanes.  Stand-in for the reference's third-party
+// variable-step integrators (IDA / OrdinaryDiffEq; sweeps.jl:599-601, :650, :664):
+//  - tstops (source breakpoints, solve.jl:1847-1918) are hit exactly and restart the
+//    integrator (BE step, fresh history);
+//  - error estimate = scaled corrector-minus-predictor difference, linear predictor
+//    while only two points are known (order 1), quadratic afterwards (order 2);
+//  - weighted RMS norm with lte_abstol + reltol*max(|u|, |u_n|); accept when <= 1;
+//  - h_new = h * clamp(0.9 * err^(-1/(p+1)), 0.2, 2); Newton failure: h /= 4;
+//    h < dtmin ends the lane with CB200_LANE_DTMIN.
+// The same statement is the oracle's (oracle/cadnip_oracle.c: ora__tran_adaptive).
+// ---------------------------------------------------------------------------
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W &w, const Program &p,
+                                                   const SpecArgs &sp, const AdaptArgs &a)
+{
+    const int64_t lane0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = lane0 < p.P;
+    const int64_t lane = act ? lane0 : p.P - 1;
+
+    load_lane_params(pg, w, p.lanes, p.P, lane);
+    CB_UNROLL
+    for (int i = 0; i < pg.n(); i++) {
+        w(pg.off_u() + i) = a.u[(int64_t)i * p.P + lane];
+        w(pg.off_dterm() + i) = 0.0;
+        w(pg.off_un() + i) = 0.0;
+        w(pg.off_h1() + i) = 0.0;
+        w(pg.off_h2() + i) = 0.0;
+    }
+    eval_all(pg, w, a.t0, CB200_MODE_TRAN, false);
+
+    int status = a.status[lane], solves = 0, rej = 0, T = 0;
+    if (act) {
+        a.out_t[(int64_t)T * p.P + lane] = a.t0;
+        for (int q = 0; q < a.n_save; q++)
+            a.out[((int64_t)q * a.max_points + T) * p.P + lane] = read_u(pg, w, __ldg(a.save_idx + q));
+    }
+    T++;
+    const int amethod = PG::kMethod >= 0 ? PG::kMethod : a.method;
+    double t = a.t0, h = a.h0, h1 = 0.0, h2 = 0.0;
+    int nhist = 0, istop = 0;
+    bool finished = !(t < a.t1);
+    while (true) {
+        if (__all_sync(0xffffffffu, finished)) break;
+        // ---- choose the step
+        while (istop < a.n_tstops && __ldg(a.tstops + istop) <= t * (1 + 4e-16)) istop++;
+        double tnext = istop < a.n_tstops ? __ldg(a.tstops + istop) : a.t1;
+        if (tnext > a.t1) tnext = a.t1;
+        double hh = h;
+        bool hit = false;
+        if (t + hh >= tnext - 1e-3 * hh) { hh = tnext - t; hit = true; }
+        const double tn = hit ? tnext : t + hh;
+        const bool be = (nhist == 0 || amethod == CB200_METHOD_BE);
+        const double gamma = be ? 1.0 / hh : 2.0 / hh;
+        if (!finished) {
+            CB_UNROLL
+            for (int i = 0; i < pg.n(); i++) {
+                w(pg.off_un() + i) = w(pg.off_u() + i);
+                if (be) w(pg.off_dterm() + i) = 0.0;       // trap: dterm holds -du_n
+            }
+        }
+        eval_sources(pg, w, tn, CB200_MODE_TRAN);
+        // ---- Newton on the implicit step
+        bool done = finished;
+        int st = CB200_LANE_OK;
+        for (int it = 0;; it++) {
+            eval_nonlinear(pg, w, tn, CB200_MODE_TRAN, false);
+            bool bad;
+            const double nrm2 = assemble<true>(pg, lu, w, gamma, sp.gshunt, sp.srcFact, bad);
+            if (!done) {
+                if (bad) { done = true; st = CB200_LANE_NONFINITE; }
+                else if (sqrt(nrm2) < a.abstol) { done = true; }
+                else if (it >= a.max_nl) { done = true; st = CB200_LANE_MAXITER; }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+            bool singular;
+            const bool ok = factor_and_solve(pg, lu, w, singular);
+            if (!done) {
+                if (!ok) { done = true; st = singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE; }
+                else { apply_update(pg, lu, w); solves++; }
+            }
+        }
+        if (finished) continue;
+        if (st != CB200_LANE_OK) {                            // Newton failed: shrink and retry
+            CB_UNROLL
+            for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
+            rej++;
+            h = hh / 4.0;
+            if (h < a.dtmin) {
+                if (status == CB200_LANE_OK) status = (st == CB200_LANE_MAXITER) ? CB200_LANE_DTMIN : st;
+                finished = true;
+            }
+            continue;
+        }
+        // ---- local truncation error estimate
+        double err = 0.0;
+        int pord = 1;
+        if (nhist >= 1) {
+            double acc = 0.0;
+            if (be || nhist == 1) {
+                const double r = hh / h1, c = hh / (2.0 * hh + h1);
+                CB_UNROLL
+                for (int i = 0; i < pg.n(); i++) {
+                    const double ui = w(pg.off_u() + i), uni = w(pg.off_un() + i);
+                    const double up = uni + r * (uni - w(pg.off_h1() + i));
+                    const double tol = a.lte_abstol + a.reltol * fmax(fabs(ui), fabs(uni));
+                    const double e = c * (ui - up) / tol;
+                    acc += e * e;
+                }
+            } else {
+                pord = 2;
+                const double ta = -(h1 + h2), tb = -h1, tc = 0.0, tx = hh;
+                const double la = (tx - tb) * (tx - tc) / ((ta - tb) * (ta - tc));
+                const double lb = (tx - ta) * (tx - tc) / ((tb - ta) * (tb - tc));
+                const double lc = (tx - ta) * (tx - tb) / ((tc - ta) * (tc - tb));
+                const double c = hh * hh / (hh * hh + 2.0 * (hh + h1) * (hh + h1 + h2));
+                CB_UNROLL
+                for (int i = 0; i < pg.n(); i++) {
+                    const double ui = w(pg.off_u() + i), uni = w(pg.off_un() + i);
+                    const double up = la * w(pg.off_h2() + i) + lb * w(pg.off_h1() + i) + lc * uni;
+                    const double tol = a.lte_abstol + a.reltol * fmax(fabs(ui), fabs(uni));
+                    const double e = c * (ui - up) / tol;
+                    acc += e * e;
+                }
+            }
+            err = sqrt(acc / (double)pg.n());
+        }
+        if (err > 1.0) {                                      // reject
+            CB_UNROLL
+            for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
+            rej++;
+            double f = 0.9 * pow(err, -1.0 / (pord + 1));
+            if (f < 0.2) f = 0.2;
+            h = hh * f;
+            if (h < a.dtmin) { if (status == CB200_LANE_OK) status = CB200_LANE_DTMIN; finished = true; }
+            continue;
+        }
+        // ---- accept
+        CB_UNROLL
+        for (int i = 0; i < pg.n(); i++) {
+            const double ui = w(pg.off_u() + i), uni = w(pg.off_un() + i);
+            w(pg.off_dterm() + i) = -(gamma * (ui - uni) + w(pg.off_dterm() + i));   // -du_{n+1}
+            w(pg.off_h2() + i) = w(pg.off_h1() + i);
+            w(pg.off_h1() + i) = uni;
+        }
+        h2 = h1; h1 = hh;
+        t = tn;
+        nhist++;
+        if (act && T < a.max_points) {
+            a.out_t[(int64_t)T * p.P + lane] = t;
+            for (int q = 0; q < a.n_save; q++)
+                a.out[((int64_t)q * a.max_points + T) * p.P + lane] = read_u(pg, w, __ldg(a.save_idx + q));
+        }
+        T++;
+        double f = err > 0.0 ? 0.9 * pow(err, -1.0 / (pord + 1)) : 2.0;
+        if (f > 2.0) f = 2.0;
+        if (f < 0.2) f = 0.2;
+        h = hh * f;
+        if (h > a.dtmax) h = a.dtmax;
+        if (hit && tn < a.t1) nhist = 0;                      // restart after a breakpoint
+        if (!(t < a.t1)) finished = true;
+        else if (T >= a.max_points) { if (status == CB200_LANE_OK) status = CB200_LANE_MAXITER; finished = true; }
+    }
+    if (act) {
+        CB_UNROLL
+        for (int i = 0; i < pg.n(); i++) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+        a.status[lane] = status;
+        a.iters[lane] += solves;
+        a.rejected[lane] = rej;
+        a.count[lane] = T < a.max_points ? T : a.max_points;
+    }
+}
+
 }  // namespace cb200

@@ -10,7 +10,7 @@
 
 namespace cb200 {
 
-constexpr int kSpecAbi = 3;
+constexpr int kSpecAbi = 4;
 
 struct SpecInput {
     const Structure *st;
@@ -27,11 +27,13 @@ struct SpecInput {
 
 typedef cudaError_t (*spec_dc_fn)(const Program *, const SpecArgs *, const DcArgs *, cudaStream_t);
 typedef cudaError_t (*spec_tran_fn)(const Program *, const SpecArgs *, const TranArgs *, cudaStream_t);
+typedef cudaError_t (*spec_adapt_fn)(const Program *, const SpecArgs *, const AdaptArgs *, cudaStream_t);
 
 struct SpecModule {
     void *dl = nullptr;
     spec_dc_fn dc = nullptr;
     spec_tran_fn tran_fixed = nullptr;
+    spec_adapt_fn tran_adaptive = nullptr;
     int block = 0;
     std::string path;
 };

