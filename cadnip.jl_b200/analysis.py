@@ -218,6 +218,16 @@ class CompiledSweep:
                                       init_maxiters=init_maxiters)
         return self.handle.tran(self.spec, tspan[0], tspan[1], opts, self.save_indices(save_idxs), u0)
 
+    def tran_fetch(self, tspan, dt, out_u, method="be", save_idxs=None, save_every=1, abstol=1e-10,
+                   max_nl_iters=10, n_segments=4, init_abstol=1e-9, init_maxiters=500):
+        """Fixed-step transient delivered into the (pinned) host array ``out_u``
+        [save][T][P]; D2H of each time segment overlaps the next segment's compute."""
+        opts = backend.make_tran_opts(method=method, adaptive=False, dt=dt, abstol=abstol,
+                                      max_nl_iters=max_nl_iters, save_every=save_every,
+                                      init_abstol=init_abstol, init_maxiters=init_maxiters)
+        return self.handle.tran_fetch(self.spec, tspan[0], tspan[1], opts,
+                                      self.save_indices(save_idxs), out_u, None, n_segments)
+
     def tran_adaptive(self, tspan, dt0=None, method="trap", save_idxs=None, abstol=1e-10,
                       reltol=1e-6, lte_abstol=1e-9, max_points=4096, dtmin=0.0, dtmax=0.0,
                       max_nl_iters=10, tstops=None, u0=None, specialize=False) -> backend.Wave:

@@ -166,6 +166,9 @@ def lib():
     L.cb200_tran.restype = C.c_int
     L.cb200_tran.argtypes = [vp, C.POINTER(Spec), C.c_double, C.c_double, C.POINTER(TranOpts),
                              lp, C.c_int32, dp, C.POINTER(vp)]
+    L.cb200_tran_fetch.restype = C.c_int
+    L.cb200_tran_fetch.argtypes = [vp, C.POINTER(Spec), C.c_double, C.c_double, C.POINTER(TranOpts),
+                                   lp, C.c_int32, dp, C.c_int32, dp, dp, ip, ip, ip]
     L.cb200_set_tstops.restype = C.c_int
     L.cb200_set_tstops.argtypes = [vp, dp, C.c_int32]
     L.cb200_wave_info.restype = C.c_int
@@ -188,7 +191,7 @@ EXPORTED_SYMBOLS = [
     "cb200_abi_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_pattern",
     "cb200_get_maps", "cb200_set_lanes", "cb200_analyze", "cb200_get_pivot_order", "cb200_eval",
     "cb200_specialize", "cb200_is_specialized", "cb200_emit_source",
-    "cb200_dc", "cb200_tran", "cb200_set_tstops", "cb200_wave_info", "cb200_wave_fetch", "cb200_wave_final_state",
+    "cb200_dc", "cb200_tran", "cb200_tran_fetch", "cb200_set_tstops", "cb200_wave_info", "cb200_wave_fetch", "cb200_wave_final_state",
     "cb200_wave_free", "cb200_get_stats"]
 
 
@@ -400,6 +403,22 @@ class Handle:
         self._check(lib().cb200_tran(self._p, C.byref(s), float(t0), float(t1), C.byref(opts),
                                      _lp(save), len(save), _dp(uu), C.byref(ptr)))
         return Wave(self, ptr)
+
+    def tran_fetch(self, spec: MNASpec, t0: float, t1: float, opts: TranOpts, save_idx: Sequence[int],
+                   out_u: np.ndarray, u0: Optional[np.ndarray] = None, n_segments: int = 4):
+        """Fixed-step tran! with the waveform delivered into ``out_u`` ([save][T][P], ideally
+        pinned), the D2H copy of each time segment overlapping the next segment's compute."""
+        save = np.ascontiguousarray(save_idx, dtype=np.int64)
+        uu = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
+        s = make_spec(spec, "tran")
+        T = out_u.shape[1]
+        t = np.empty(T, dtype=np.float64)
+        count = np.empty(self.P, np.int32); status = np.empty(self.P, np.int32)
+        iters = np.empty(self.P, np.int32)
+        self._check(lib().cb200_tran_fetch(self._p, C.byref(s), float(t0), float(t1), C.byref(opts),
+                                           _lp(save), len(save), _dp(uu), int(n_segments), _dp(t),
+                                           _dp(out_u), _ip(count), _ip(status), _ip(iters)))
+        return dict(t=t, u=out_u, count=count, status=status, newton_iters=iters)
 
     def set_tstops(self, tstops: Sequence[float]):
         t = np.ascontiguousarray(tstops, dtype=np.float64)

@@ -156,6 +156,9 @@ struct cb200_handle {
     DevBuf<unsigned char> d_conv, d_active;
     DevBuf<double> d_gshunt_lane, d_srcfact_lane;
     DevBuf<int> d_save, d_rejected;
+    DevBuf<double> d_hist;         // [2n][P] integrator history between time segments
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t seg_ev[16] = {};
     std::vector<double> tstops;    // sorted breakpoints for adaptive stepping
     DevBuf<double> d_tstops;
     std::shared_ptr<BufPool> pool;  // recycled waveform buffers (shared with live waves)
@@ -327,6 +330,8 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
         delete h;
         return fail(nullptr, CB200_ECUDA, "cb200_create: stream/event creation failed");
     }
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    for (auto &e : h->seg_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaStream_t s = h->stream;
     const Structure &st = h->st;
     std::vector<unsigned char> nd8(st.nz_is_node_diag.begin(), st.nz_is_node_diag.end());
@@ -387,6 +392,8 @@ extern "C" void cb200_destroy(cb200_handle *h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto &e : h->seg_ev) if (e) cudaEventDestroy(e);
     unload_spec(h->spec);
     delete h;
 }
@@ -863,9 +870,11 @@ extern "C" int cb200_dc(cb200_handle *h, const cb200_spec *spec, const cb200_dc_
 // ---------------------------------------------------------------------------
 // transient
 // ---------------------------------------------------------------------------
-extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
-                          const cb200_tran_opts *o, const int64_t *save_idx, int32_t n_save,
-                          const double *u0, cb200_wave **out)
+static const int kMaxSegments = 16;
+
+static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
+                     const cb200_tran_opts *o, const int64_t *save_idx, int32_t n_save,
+                     const double *u0, double *host_u, int n_segments, cb200_wave **out)
 {
     if (!h || !spec || !o || !out) return fail(h, CB200_EINVAL, "cb200_tran: null argument");
     *out = nullptr;
@@ -936,14 +945,45 @@ extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, do
         a.max_nl = o->max_nl_iters; a.save_every = se; a.n_save = n_save; a.save_idx = d_save.p;
         a.T = T; a.u = h->d_state.p; a.out = w->d_out.p; a.status = h->d_status.p; a.iters = h->d_iters.p;
         a.ws_global = ws_global;
+        // Time segments: one launch each.  With a host destination the D2H copy of a finished
+        // segment runs on the copy stream while the next segment computes.
+        int nseg = (host_u != nullptr && n_segments > 1) ? (int)std::min<int64_t>(n_segments, std::max<int64_t>(1, nsteps / 64)) : 1;
+        if (nseg > kMaxSegments) nseg = kMaxSegments;
+        if (nseg > 1) {
+            if (h->d_hist.n != (size_t)2 * n * P && h->d_hist.alloc((size_t)2 * n * P) != cudaSuccess) {
+                delete w; return fail(h, CB200_ENOMEM, "cb200_tran: history buffer allocation failed");
+            }
+            a.hist = h->d_hist.p;
+        }
+        const int64_t seg_len = (nsteps + nseg - 1) / nseg;
         cudaEventRecord(h->ev0, s);
-        if (spec_usable(h) && h->spec_method == o->method) {
-            h->stats.launches += 1;
-            ce = h->spec.tran_fixed(&h->prog, &sa, &a, s);
-        } else {
-            ce = launch_tran_fixed(h->prog, h->lu[1].prog, sa, a, h->block_pref, h->smem_limit, s, &h->stats.launches);
+        for (int g = 0; g < nseg && ce == cudaSuccess; g++) {
+            a.k_begin = (int64_t)g * seg_len + 1;
+            a.k_end = std::min<int64_t>(nsteps, (int64_t)(g + 1) * seg_len);
+            if (a.k_begin > a.k_end) break;
+            a.tp_begin = g == 0 ? 0 : 1 + (a.k_begin - 1) / se;
+            if (spec_usable(h) && h->spec_method == o->method) {
+                h->stats.launches += 1;
+                ce = h->spec.tran_fixed(&h->prog, &sa, &a, s);
+            } else {
+                ce = launch_tran_fixed(h->prog, h->lu[1].prog, sa, a, h->block_pref, h->smem_limit, s, &h->stats.launches);
+            }
+            if (host_u != nullptr && ce == cudaSuccess) {
+                int64_t tp_end = 1 + a.k_end / se;                     // one past the last point written
+                if (a.k_end == nsteps && nsteps % se != 0) tp_end += 1;
+                cudaEventRecord(h->seg_ev[g], s);
+                cudaStreamWaitEvent(h->copy_stream, h->seg_ev[g], 0);
+                for (int q = 0; q < n_save; q++) {
+                    const size_t off = ((size_t)q * T + a.tp_begin) * P;
+                    ce = cudaMemcpyAsync(host_u + off, w->d_out.p + off, (size_t)(tp_end - a.tp_begin) * P * sizeof(double),
+                                         cudaMemcpyDeviceToHost, h->copy_stream);
+                    if (ce != cudaSuccess) break;
+                }
+                h->stats.d2h_bytes += (int64_t)n_save * (tp_end - a.tp_begin) * P * sizeof(double);
+            }
         }
         cudaEventRecord(h->ev1, s);
+        if (host_u != nullptr && ce == cudaSuccess) ce = cudaStreamSynchronize(h->copy_stream);
     } else {
         // LTE-controlled stepping, per-lane time axis; tstops come from cb200_set_tstops
         const int T = o->max_points > 1 ? o->max_points : 4096;
@@ -1003,6 +1043,33 @@ extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, do
     if (!o->adaptive) h->stats.steps_accepted = w->nsteps * P;
     *out = w;
     return CB200_OK;
+}
+
+extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
+                          const cb200_tran_opts *o, const int64_t *save_idx, int32_t n_save,
+                          const double *u0, cb200_wave **out)
+{
+    return tran_impl(h, spec, t0, t1, o, save_idx, n_save, u0, nullptr, 1, out);
+}
+
+// tran! straight into host memory: the time loop is cut into n_segments launches and the
+// waveform of each finished segment is copied out (copy stream) while the next computes.
+extern "C" int cb200_tran_fetch(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
+                                const cb200_tran_opts *o, const int64_t *save_idx, int32_t n_save,
+                                const double *u0, int32_t n_segments, double *t_out, double *u_out,
+                                int32_t *count, int32_t *status, int32_t *newton_iters)
+{
+    if (!o) return fail(h, CB200_EINVAL, "cb200_tran_fetch: null argument");
+    cb200_wave *w = nullptr;
+    const bool pipelined = !o->adaptive && u_out != nullptr;
+    int rc = tran_impl(h, spec, t0, t1, o, save_idx, n_save, u0, pipelined ? u_out : nullptr,
+                       n_segments, &w);
+    if (rc != CB200_OK) return rc;
+    const int64_t d2h = h->stats.d2h_bytes;
+    rc = cb200_wave_fetch(w, t_out, pipelined ? nullptr : u_out, count, status, newton_iters);
+    h->stats.d2h_bytes += d2h;
+    cb200_wave_free(w);
+    return rc;
 }
 
 extern "C" int cb200_set_tstops(cb200_handle *h, const double *tstops, int32_t n)

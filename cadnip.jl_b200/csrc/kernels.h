@@ -76,7 +76,10 @@ cudaError_t launch_dc(const Program &p, const LuProgram &lu, const SpecArgs &s, 
 struct TranArgs {
     int method;             // CB200_METHOD_*
     double t0, h;
-    int64_t nsteps;
+    int64_t nsteps;         // total steps of the run (final point is always saved)
+    int64_t k_begin, k_end; // steps this launch performs (1-based, inclusive)
+    int64_t tp_begin;       // first output point this launch writes
+    double *hist;           // [2n][P] integrator history (u_n, dterm) carried between segments, or null
     double abstol;
     int max_nl;
     int save_every;

@@ -528,13 +528,13 @@ __device__ __forceinline__ void device_source_stamp(const PG &pg, W &w, int d, d
 // instructions run on the same inputs, in another lane.
 template <typename PG, typename W>
 __device__ __forceinline__ void source_step_one(const PG &pg, W &w, int q, int d, bool uniform,
-                                                int64_t k, double t0, double h, int mode)
+                                                int64_t k, bool first, double t0, double h, int mode)
 {
     double v;
     if (uniform) {
         const int j = (int)((k - 1) & 31);
-        if (j == 0)
-            w(pg.off_srcc() + q) = device_source_value(pg, w, d, t0 + (double)(k + (threadIdx.x & 31)) * h, mode);
+        if (j == 0 || first)      // lane L holds the value of step (k - j) + L
+            w(pg.off_srcc() + q) = device_source_value(pg, w, d, t0 + (double)((k - j) + (threadIdx.x & 31)) * h, mode);
         v = __shfl_sync(0xffffffffu, w(pg.off_srcc() + q), j);
     } else {
         v = device_source_value(pg, w, d, t0 + (double)k * h, mode);
@@ -543,14 +543,14 @@ __device__ __forceinline__ void source_step_one(const PG &pg, W &w, int q, int d
 }
 
 template <typename PG, typename W>
-__device__ __forceinline__ void eval_sources_step(const PG &pg, W &w, int64_t k, double t0, double h,
-                                                  int mode)
+__device__ __forceinline__ void eval_sources_step(const PG &pg, W &w, int64_t k, bool first, double t0,
+                                                  double h, int mode)
 {
     if constexpr (PG::kStatic) {
-        PG::eval_sources_step(w, k, t0, h, mode);
+        PG::eval_sources_step(w, k, first, t0, h, mode);
     } else {
         for (int q = 0; q < pg.n_src(); q++)
-            source_step_one(pg, w, q, pg.src_list(q), pg.src_uniform(q), k, t0, h, mode);
+            source_step_one(pg, w, q, pg.src_list(q), pg.src_uniform(q), k, first, t0, h, mode);
     }
 }
 
@@ -790,25 +790,31 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
     const bool act = lane0 < p.P;
     const int64_t lane = act ? lane0 : p.P - 1;
 
+    // The time loop may be cut into segments [k_begin, k_end] (one launch each) so that the
+    // copy of a finished segment's waveform to the host overlaps the next segment's compute;
+    // a resumed segment reloads the integrator history (u_n, dterm) the previous one stored.
+    const bool resume = a.k_begin > 1;
     load_lane_params(pg, w, p.lanes, p.P, lane);
     CB_UNROLL
     for (int i = 0; i < pg.n(); i++) {
         w(pg.off_u() + i) = a.u[(int64_t)i * p.P + lane];
-        w(pg.off_dterm() + i) = 0.0;
-        w(pg.off_un() + i) = 0.0;
+        w(pg.off_dterm() + i) = resume ? a.hist[(int64_t)(pg.n() + i) * p.P + lane] : 0.0;
+        w(pg.off_un() + i) = resume ? a.hist[(int64_t)i * p.P + lane] : 0.0;
     }
     eval_all(pg, w, a.t0, CB200_MODE_TRAN, false);
 
     int status = a.status[lane], solves = 0;       // keeps an InitialFailure from the DC init
-    int64_t tp = 0;
-    if (act)
-        for (int q = 0; q < a.n_save; q++)
-            a.out[((int64_t)q * a.T + tp) * p.P + lane] = read_u(pg, w, __ldg(a.save_idx + q));
-    tp++;
+    int64_t tp = a.tp_begin;
+    if (!resume) {
+        if (act)
+            for (int q = 0; q < a.n_save; q++)
+                a.out[((int64_t)q * a.T + tp) * p.P + lane] = read_u(pg, w, __ldg(a.save_idx + q));
+        tp++;
+    }
     const double h = a.h;
     // a specialised kernel is generated for one integration method: branches on it fold
     const int amethod = PG::kMethod >= 0 ? PG::kMethod : a.method;
-    for (int64_t k = 1; k <= a.nsteps; k++) {
+    for (int64_t k = a.k_begin; k <= a.k_end; k++) {
         const double t = a.t0 + (double)k * h;
         const int method = (k == 1) ? CB200_METHOD_BE : amethod;
         const double gamma = method == CB200_METHOD_BE ? 1.0 / h
@@ -822,7 +828,7 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
             /* trap: dterm already holds -du_n */
             w(pg.off_un() + i) = ui;
         }
-        eval_sources_step(pg, w, k, a.t0, h, CB200_MODE_TRAN);
+        eval_sources_step(pg, w, k, k == a.k_begin, a.t0, h, CB200_MODE_TRAN);
         bool done = false;
         int st = CB200_LANE_OK;
         for (int it = 0;; it++) {
@@ -861,7 +867,13 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
     }
     if (act) {
         CB_UNROLL
-        for (int i = 0; i < pg.n(); i++) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+        for (int i = 0; i < pg.n(); i++) {
+            a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+            if (a.hist != nullptr) {                     // history for a resumed segment
+                a.hist[(int64_t)i * p.P + lane] = w(pg.off_un() + i);
+                a.hist[(int64_t)(pg.n() + i) * p.P + lane] = w(pg.off_dterm() + i);
+            }
+        }
         a.status[lane] = status;
         a.iters[lane] += solves;
     }

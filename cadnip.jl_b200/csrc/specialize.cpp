@@ -236,10 +236,10 @@ std::string generate_spec_source(const SpecInput &in)
     o << "    template <typename W>\n    __device__ static __forceinline__ void eval_sources(W &w, double t, int mode)\n    {\n        SProg pg;\n";
     for (int d : *in.src_list) o << "        eval_device<2>(pg, w, " << d << ", t, mode, false);\n";
     o << "    }\n";
-    o << "    template <typename W>\n    __device__ static __forceinline__ void eval_sources_step(W &w, int64_t k, double t0, double h, int mode)\n    {\n        SProg pg;\n";
+    o << "    template <typename W>\n    __device__ static __forceinline__ void eval_sources_step(W &w, int64_t k, bool first, double t0, double h, int mode)\n    {\n        SProg pg;\n";
     for (size_t q = 0; q < in.src_list->size(); q++)
         o << "        source_step_one(pg, w, " << q << ", " << (*in.src_list)[q] << ", "
-          << ((*in.src_uniform)[q] ? "true" : "false") << ", k, t0, h, mode);\n";
+          << ((*in.src_uniform)[q] ? "true" : "false") << ", k, first, t0, h, mode);\n";
     o << "    }\n";
     o << "};\n";
     emit_lu(o, "SLuDc", st, p, *in.lu_dc);

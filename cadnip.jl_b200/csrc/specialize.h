@@ -10,7 +10,7 @@
 
 namespace cb200 {
 
-constexpr int kSpecAbi = 4;
+constexpr int kSpecAbi = 5;
 
 struct SpecInput {
     const Structure *st;

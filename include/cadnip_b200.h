@@ -248,6 +248,16 @@ int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
                const cb200_tran_opts *opts, const int64_t *save_idx, int32_t n_save,
                const double *u0, cb200_wave **out);
 
+/* tran! with the result delivered straight into host memory (what a caller of
+ * tran!(::CircuitSweep) ultimately reads).  Fixed-step runs are cut into n_segments
+ * launches; the waveform of a finished segment is copied to u_out on a second stream
+ * while the next segment computes, so only the last segment's copy is exposed.  u_out
+ * should be page-locked for the copies to overlap.  Layouts as cb200_wave_fetch.       */
+int cb200_tran_fetch(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
+                     const cb200_tran_opts *opts, const int64_t *save_idx, int32_t n_save,
+                     const double *u0, int32_t n_segments, double *t_out, double *u_out,
+                     int32_t *count, int32_t *status, int32_t *newton_iters);
+
 /* Adaptive stepping only: time points the integrator must hit exactly -- the source
  * breakpoints the host derives with expand_breakpoints (src/mna/solve.jl:1847-1918;
  * tran!'s auto_tstops, src/sweeps.jl:620-627).  Copied; persists until replaced.   */
