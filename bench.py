@@ -230,8 +230,7 @@ def run_b200(args):
     step_e2e()
 
     # ---- timed: inputs resident in HBM --------------------------------------
-    time.sleep(0.5)
-    sampler.lines.clear()
+    time.sleep(0.3)                      # samples cover warm-up and both timed regions (same load)
     barrier()
     t0 = time.perf_counter()
     kern_ms = tran_ms = 0.0

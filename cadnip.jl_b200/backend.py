@@ -181,6 +181,8 @@ def lib():
     L.cb200_wave_free.argtypes = [vp]
     L.cb200_get_stats.restype = C.c_int
     L.cb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.cb200_debug_exp.restype = C.c_int
+    L.cb200_debug_exp.argtypes = [dp, dp, C.c_int32]
     if L.cb200_abi_version() != 1:
         raise CB200Error(EINVAL, "libcadnip_b200.so ABI version mismatch")
     _lib = L
@@ -192,7 +194,7 @@ EXPORTED_SYMBOLS = [
     "cb200_get_maps", "cb200_set_lanes", "cb200_analyze", "cb200_get_pivot_order", "cb200_eval",
     "cb200_specialize", "cb200_is_specialized", "cb200_emit_source",
     "cb200_dc", "cb200_tran", "cb200_tran_fetch", "cb200_set_tstops", "cb200_wave_info", "cb200_wave_fetch", "cb200_wave_final_state",
-    "cb200_wave_free", "cb200_get_stats"]
+    "cb200_wave_free", "cb200_get_stats", "cb200_debug_exp"]
 
 
 def _dp(a):
@@ -428,6 +430,16 @@ class Handle:
         s = Stats()
         self._check(lib().cb200_get_stats(self._p, C.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+def debug_exp(x: np.ndarray) -> np.ndarray:
+    """The device kernels' junction exp evaluated on the GPU (accuracy tests)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    rc = lib().cb200_debug_exp(_dp(x), _dp(y), int(x.size))
+    if rc != OK:
+        raise CB200Error(rc, (lib().cb200_last_error(None) or b"").decode())
+    return y
 
 
 def make_tran_opts(method="be", adaptive=False, dt=0.0, abstol=1e-10, reltol=1e-8, lte_abstol=1e-10,

@@ -1252,6 +1252,20 @@ extern "C" void cb200_wave_free(cb200_wave *w)
     delete w;
 }
 
+// Test hook: evaluates the device-side junction exp (lane_kernels.cuh: d_exp) on host data.
+extern "C" int cb200_debug_exp(const double *x, double *y, int32_t n)
+{
+    if (!x || !y || n <= 0) return CB200_EINVAL;
+    double *dx = nullptr, *dy = nullptr;
+    if (cudaMalloc((void **)&dx, n * sizeof(double)) != cudaSuccess) return fail(nullptr, CB200_ENODEVICE, "cb200_debug_exp: no device");
+    cudaMalloc((void **)&dy, n * sizeof(double));
+    cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice);
+    cudaError_t e = launch_debug_exp(dx, dy, n, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dy);
+    return e == cudaSuccess ? CB200_OK : fail(nullptr, CB200_ECUDA, cudaGetErrorString(e));
+}
+
 extern "C" int cb200_get_stats(const cb200_handle *h, cb200_stats *out)
 {
     if (!h || !out) return CB200_EINVAL;

@@ -118,6 +118,8 @@ cudaError_t launch_tran_adaptive(const Program &p, const LuProgram &lu, const Sp
                                  const AdaptArgs &a, int block, size_t smem_limit,
                                  cudaStream_t st, int64_t *launches);
 
+cudaError_t launch_debug_exp(const double *x, double *y, int n, cudaStream_t st);
+
 // pick lanes-per-block so the lane workspace fits in shared memory (0 = use global)
 int choose_block(int n_slots, size_t smem_limit, int preferred);
 

@@ -256,6 +256,33 @@ __device__ __forceinline__ double source_value(const PG &pg, W &w, int wave, int
 }
 
 // ---------------------------------------------------------------------------
+// exp for the junction models.  Same algorithm as any libm exp (k = rint(x/ln2),
+// Cody-Waite reduction, polynomial, scale by 2^k; <= 1 ulp), but the coefficients sit
+// in constant memory so that every FMA takes its coefficient as a constant-bank
+// operand: libdevice's exp spends more issue slots materialising its fp64 immediates
+// (UMOV + IMAD.MOV pairs) than on arithmetic, and this kernel is issue-bound.
+// ---------------------------------------------------------------------------
+__constant__ double cb200_exp_coef[14] = {
+    1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03,
+    1.3888888888888889e-03, 1.9841269841269841e-04, 2.4801587301587302e-05, 2.7557319223985893e-06,
+    2.7557319223985888e-07, 2.5052108385441720e-08, 2.0876756987868100e-09, 1.6059043836821613e-10};
+
+__device__ __forceinline__ double d_exp(double x)
+{
+    if (!(fabs(x) < 700.0)) return exp(x);                 // overflow / underflow / NaN: library path
+    const double magic = 6755399441055744.0;               // 1.5 * 2^52: rounds to nearest integer
+    const double t = fma(x, 1.4426950408889634, magic);
+    const double k = t - magic;
+    double r = fma(k, -6.93147180369123816490e-01, x);     // ln2 high part (exact product for |k| < 2^11)
+    r = fma(k, -1.90821492927058770002e-10, r);            // ln2 low part
+    double p = cb200_exp_coef[13];
+#pragma unroll
+    for (int i = 12; i >= 0; i--) p = fma(p, r, cb200_exp_coef[i]);
+    const int ki = __double2loint(t);                      // low word of the magic sum = k
+    return __hiloint2double(__double2hiint(p) + (ki << 20), __double2loint(p));
+}
+
+// ---------------------------------------------------------------------------
 // limiting primitives (src/mna/devices.jl:1169-1258, :1333-1345)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double d_pnjlim(double vnew, double vold, double vt, double vcrit)
@@ -282,7 +309,7 @@ __device__ __forceinline__ void d_diode_iv(double Is, double nVt, double v, doub
         I0 = Is * (e80 * (1.0 + (xarg - 80.0)) - 1.0);
         Gd = Is / nVt * e80;
     } else {
-        const double expterm = exp(xarg);
+        const double expterm = d_exp(xarg);
         I0 = Is * (expterm - 1.0);
         Gd = Is / nVt * expterm;
     }
@@ -417,7 +444,7 @@ __device__ __forceinline__ void eval_device(const PG &pg, W &w, int d, double t,
             const double V0 = xval(pg, w, pp) - xval(pg, w, nn);
             const double Is = param(pg, w, pb, 0), Vt = param(pg, w, pb, 1), nf = param(pg, w, pb, 2);
             const double nVt = nf * Vt;
-            const double expterm = exp(V0 / nVt);
+            const double expterm = d_exp(V0 / nVt);
             const double I0 = Is * (expterm - 1.0);
             const double Gd = Is / nVt * expterm;
             const double Ieq = I0 - Gd * V0;
@@ -431,7 +458,7 @@ __device__ __forceinline__ void eval_device(const PG &pg, W &w, int d, double t,
             const double V0 = xval(pg, w, pp) - xval(pg, w, nn);
             const double Is = param(pg, w, pb, 0), Vt = param(pg, w, pb, 1), nf = param(pg, w, pb, 2);
             const double nVt = nf * Vt;
-            const double expterm = exp(V0 / nVt);
+            const double expterm = d_exp(V0 / nVt);
             const double I0 = Is * (expterm - 1.0);
             const double G = Is / nVt * expterm;
             const double Ieq = I0 - G * V0;
@@ -613,9 +640,9 @@ __device__ __forceinline__ double assemble(const PG &pg, const LU &lu, W &w, dou
         if (srcFact < 1.0) bsum *= srcFact;
         const double f = w(pg.off_F() + r) - bsum;
         w(pg.off_F() + r) = f;
-        bad |= !isfinite(f);
         nrm2 += f * f;
     }
+    bad = !isfinite(nrm2);     // a NaN / Inf entry of F poisons the sum (all(isfinite, F), solve.jl:632)
     return nrm2;
 }
 
@@ -717,6 +744,7 @@ __device__ __forceinline__ void dc_body(const PG &pg, const LU &lu, W &w, const 
     const double srcFact = a.srcfact_lane ? a.srcfact_lane[lane] : sp.srcFact;
     const int lim0 = pg.n() - pg.n_limits();
     const bool pcnr = (a.algorithm == 0);
+    const double abstol2 = a.abstol * a.abstol;     // ||F||_2 < abstol  <=>  ||F||_2^2 < abstol^2
     bool initjct = false;
     if (pcnr && cold) {                                   // solve.jl:622-627
         CB_UNROLL
@@ -744,7 +772,7 @@ __device__ __forceinline__ void dc_body(const PG &pg, const LU &lu, W &w, const 
         const double nrm2 = assemble<false>(pg, lu, w, 0.0, gshunt, srcFact, bad);
         if (done) continue;
         if (bad) { done = true; status = CB200_LANE_NONFINITE; continue; }
-        if (sqrt(nrm2) < a.abstol) {
+        if (nrm2 < abstol2) {
             if (!pcnr || settling) { done = true; conv = true; status = CB200_LANE_OK; continue; }
             // settle the limit slots and re-verify (solve.jl:640-663)
             CB_UNROLL
@@ -812,6 +840,7 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
         tp++;
     }
     const double h = a.h;
+    const double abstol2 = a.abstol * a.abstol;
     // a specialised kernel is generated for one integration method: branches on it fold
     const int amethod = PG::kMethod >= 0 ? PG::kMethod : a.method;
     for (int64_t k = a.k_begin; k <= a.k_end; k++) {
@@ -837,7 +866,7 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
             const double nrm2 = assemble<true>(pg, lu, w, gamma, sp.gshunt, sp.srcFact, bad);
             if (!done) {
                 if (bad) { done = true; st = CB200_LANE_NONFINITE; }
-                else if (sqrt(nrm2) < a.abstol) { done = true; }
+                else if (nrm2 < abstol2) { done = true; }
                 else if (it >= a.max_nl) { done = true; st = CB200_LANE_MAXITER; }
             }
             if (__all_sync(0xffffffffu, done)) break;
@@ -919,6 +948,7 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
     }
     T++;
     const int amethod = PG::kMethod >= 0 ? PG::kMethod : a.method;
+    const double abstol2 = a.abstol * a.abstol;
     double t = a.t0, h = a.h0, h1 = 0.0, h2 = 0.0;
     int nhist = 0, istop = 0;
     bool finished = !(t < a.t1);
@@ -951,7 +981,7 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
             const double nrm2 = assemble<true>(pg, lu, w, gamma, sp.gshunt, sp.srcFact, bad);
             if (!done) {
                 if (bad) { done = true; st = CB200_LANE_NONFINITE; }
-                else if (sqrt(nrm2) < a.abstol) { done = true; }
+                else if (nrm2 < abstol2) { done = true; }
                 else if (it >= a.max_nl) { done = true; st = CB200_LANE_MAXITER; }
             }
             if (__all_sync(0xffffffffu, done)) break;

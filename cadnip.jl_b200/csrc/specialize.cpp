@@ -80,16 +80,16 @@ static void emit_assemble(std::ostringstream &o, const Structure &st, const Prog
         }
         o << "        }\n";
     }
-    o << "        double nrm2 = 0.0;\n        bad = false;\n";
+    o << "        double nrm2 = 0.0;\n";
     for (int r = 0; r < st.n; r++) {
         o << "        {\n            double bsum = 0.0;\n";
         for (int q = st.bseg_ptr[r]; q < st.bseg_ptr[r + 1]; q++)
             o << "            bsum += w(" << p.off_SB + st.bseg_idx[q] << ");\n";
         if (st.bseg_ptr[r] < st.bseg_ptr[r + 1]) o << "            if (srcFact < 1.0) bsum *= srcFact;\n";
         o << "            const double f = F" << r << " - bsum;\n";
-        o << "            w(" << p.off_F + r << ") = f;\n            bad |= !isfinite(f);\n            nrm2 += f * f;\n        }\n";
+        o << "            w(" << p.off_F + r << ") = f;\n            nrm2 += f * f;\n        }\n";
     }
-    o << "        return nrm2;\n    }\n";
+    o << "        bad = !isfinite(nrm2);\n        return nrm2;\n    }\n";
 }
 
 static void emit_factor_solve(std::ostringstream &o, const Program &p, const LuSchedule &S)

@@ -276,6 +276,9 @@ void cb200_wave_free(cb200_wave *w);
 
 int cb200_get_stats(const cb200_handle *h, cb200_stats *out);
 
+/* Test hook: y[i] = the device kernels' junction exp(x[i]) (accuracy tests).          */
+int cb200_debug_exp(const double *x, double *y, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif
