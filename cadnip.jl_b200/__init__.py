@@ -22,6 +22,7 @@ from .sweeps import (Sweep, ProductSweep, TandemSweep, SerialSweep, CircuitSweep
 from .lowering import lower, lower_circuit, LoweredCircuit, StructuralSweepError
 from .analysis import (dc, tran, DCSolution, TranSolution, CompiledSweep, compile_sweep,
                        expand_breakpoints, breakpoints)
+from .verilog_a import va, VAModel, VAError
 from . import backend
 
 __all__ = [n for n in dir() if not n.startswith("_")]

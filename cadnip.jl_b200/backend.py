@@ -157,6 +157,8 @@ def lib():
     L.cb200_specialize.argtypes = [vp, C.POINTER(Spec), C.c_int32, C.c_double, C.c_char_p, C.c_char_p, C.c_int32]
     L.cb200_is_specialized.restype = C.c_int
     L.cb200_is_specialized.argtypes = [vp]
+    L.cb200_load_va_models.restype = C.c_int
+    L.cb200_load_va_models.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
     L.cb200_emit_source.restype = C.c_int64
     L.cb200_emit_source.argtypes = [C.POINTER(Desc), dp, dp, C.c_int32, C.c_int64, C.c_int32, C.c_char_p, C.c_int64]
     L.cb200_eval.restype = C.c_int
@@ -192,9 +194,18 @@ def lib():
 EXPORTED_SYMBOLS = [
     "cb200_abi_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_pattern",
     "cb200_get_maps", "cb200_set_lanes", "cb200_analyze", "cb200_get_pivot_order", "cb200_eval",
-    "cb200_specialize", "cb200_is_specialized", "cb200_emit_source",
+    "cb200_specialize", "cb200_is_specialized", "cb200_emit_source", "cb200_load_va_models",
     "cb200_dc", "cb200_tran", "cb200_tran_fetch", "cb200_set_tstops", "cb200_wave_info", "cb200_wave_fetch", "cb200_wave_final_state",
     "cb200_wave_free", "cb200_get_stats", "cb200_debug_exp"]
+
+
+def prebuild_va_models(models) -> None:
+    """Build the kernel set for a circuit's Verilog-A models into the in-tree cache
+    (no GPU needed; what Handle.load_va_models would otherwise build on first use)."""
+    from . import verilog_a as _va
+    rc = lib().cb200_load_va_models(None, _va.cuda_header(list(models)).encode(), _CSRC.encode(), GEN_DIR.encode())
+    if rc != OK:
+        raise CB200Error(rc, (lib().cb200_last_error(None) or b"").decode())
 
 
 def _dp(a):
@@ -310,6 +321,13 @@ class Handle:
             raise CB200Error(rc, (L.cb200_last_error(None) or b"").decode())
         self._p = ptr
         self.P = 0
+        if getattr(lc, "va_models", None):
+            from . import verilog_a as _va
+            self.load_va_models(_va.cuda_header(lc.va_models))
+
+    def load_va_models(self, cuda_header: str):
+        """Rebuild (cached) and load the kernel set with the circuit's Verilog-A models."""
+        self._check(lib().cb200_load_va_models(self._p, cuda_header.encode(), _CSRC.encode(), GEN_DIR.encode()))
 
     def _check(self, rc: int):
         if rc != OK:

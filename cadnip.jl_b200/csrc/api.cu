@@ -165,6 +165,8 @@ struct cb200_handle {
     Program prog{};
     DevLu lu[2];                   // 0: DC (gamma = 0), 1: transient
     int lu_gen[2] = {0, 0};        // bumped by every (re-)analysis
+    KernelSet k;                   // table-driven kernels: built-in, or rebuilt with VA models
+    bool has_va = false;
     SpecModule spec;               // circuit-specialised kernels (optional)
     int spec_gen[2] = {-1, -1};    // schedule generations the module was generated from
     int spec_method = -1;          // integration method baked into the transient kernel
@@ -248,7 +250,8 @@ static bool is_source_kind(int kind) { return kind == CB200_DEV_VSOURCE || kind 
 // ... and on the iterate (evaluated every Newton iteration)
 static bool is_nonlinear_kind(int kind)
 {
-    return kind == CB200_DEV_DIODE || kind == CB200_DEV_DIODECAP || kind == CB200_DEV_SIMPLEMOS;
+    return kind == CB200_DEV_DIODE || kind == CB200_DEV_DIODECAP || kind == CB200_DEV_SIMPLEMOS ||
+           kind == CB200_DEV_VA;
 }
 
 extern "C" int cb200_abi_version(void) { return CB200_ABI_VERSION; }
@@ -270,6 +273,8 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
                         (ce != cudaSuccess ? cudaGetErrorString(ce) : "device ordinal out of range"));
     cb200_handle *h = new cb200_handle();
     h->device = device;
+    h->k.eval = cb200_k_eval; h->k.dc = cb200_k_dc;
+    h->k.tran_fixed = cb200_k_tran_fixed; h->k.tran_adaptive = cb200_k_tran_adaptive;
     h->pool = std::make_shared<BufPool>();
     h->pool->device = device;
     ce = cudaSetDevice(device);
@@ -294,6 +299,7 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
             return fail(nullptr, CB200_EINVAL, "cb200_create: unknown device kind");
         }
     h->dev_kind = to_int(d->dev_kind, nd);
+    for (int kd : h->dev_kind) h->has_va |= (kd == CB200_DEV_VA);
     h->dev_flags = to_int(d->dev_flags, nd);
     h->dev_node_ptr = to_int(d->dev_node_ptr, nd + 1);
     h->dev_nodes = to_int(d->dev_nodes, nd ? d->dev_node_ptr[nd] : 0);
@@ -395,6 +401,7 @@ extern "C" void cb200_destroy(cb200_handle *h)
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto &e : h->seg_ev) if (e) cudaEventDestroy(e);
     unload_spec(h->spec);
+    if (h->k.dl) unload_kernel_set(h->k);
     delete h;
 }
 
@@ -489,6 +496,13 @@ static int upload_lu(cb200_handle *h, DevLu &L)
     return CB200_OK;
 }
 
+static int require_models(cb200_handle *h)
+{
+    if (h->has_va && h->k.va_header_path.empty())
+        return fail(h, CB200_ESTATE, "the circuit contains Verilog-A devices: call cb200_load_va_models first");
+    return CB200_OK;
+}
+
 // Evaluate G, C at state x for a compact set of sample lanes; returns |G + gamma*C|
 // maxima per pattern entry.  Runs the K1/K2 evaluation kernels on a temporary
 // program whose lane SoA holds only the samples.
@@ -530,7 +544,7 @@ static int probe_magnitudes(cb200_handle *h, const cb200_spec *spec, double gamm
         EvalArgs a{};
         a.t = 0.0; a.initjct = (probe == 0); a.ws = d_ws.p; a.G_nz = d_G.p; a.C_nz = d_C.p;
         SpecArgs sa = spec_args(spec);
-        CUDA_TRY(h, launch_eval(p, sa, a, h->stream, &h->stats.launches));
+        CUDA_TRY(h, h->k.eval(&p, &sa, &a, h->stream, &h->stats.launches));
         CUDA_TRY(h, cudaMemcpyAsync(hG.data(), d_G.p, hG.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaMemcpyAsync(hC.data(), d_C.p, hC.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -547,6 +561,7 @@ extern "C" int cb200_analyze(cb200_handle *h, const cb200_spec *spec, double gam
 {
     if (!h || !spec) return fail(h, CB200_EINVAL, "cb200_analyze: null argument");
     if (h->P <= 0) return fail(h, CB200_ESTATE, "cb200_analyze: call cb200_set_lanes first");
+    if (require_models(h) != CB200_OK) return CB200_ESTATE;
     cudaSetDevice(h->device);
     const int which = gamma == 0.0 ? 0 : 1;
     std::vector<double> absJ;
@@ -588,6 +603,7 @@ extern "C" int cb200_eval(cb200_handle *h, const cb200_spec *spec, double t, int
 {
     if (!h || !spec) return fail(h, CB200_EINVAL, "cb200_eval: null argument");
     if (h->P <= 0) return fail(h, CB200_ESTATE, "cb200_eval: call cb200_set_lanes first");
+    if (require_models(h) != CB200_OK) return CB200_ESTATE;
     cudaSetDevice(h->device);
     const int64_t P = h->P;
     const int n = h->st.n;
@@ -606,7 +622,10 @@ extern "C" int cb200_eval(cb200_handle *h, const cb200_spec *spec, double t, int
     a.t = t; a.initjct = initjct; a.ws = h->d_ws_global.p;
     a.G_nz = dG.p; a.C_nz = dC.p; a.b = db.p; a.limw = dl.p;
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));
-    CUDA_TRY(h, launch_eval(h->prog, spec_args(spec), a, s, &h->stats.launches));
+    {
+        SpecArgs sa = spec_args(spec);
+        CUDA_TRY(h, h->k.eval(&h->prog, &sa, &a, s, &h->stats.launches));
+    }
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     if (G_nz) CUDA_TRY(h, cudaMemcpyAsync(G_nz, dG.p, (size_t)nnz * P * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (C_nz) CUDA_TRY(h, cudaMemcpyAsync(C_nz, dC.p, (size_t)nnz * P * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -657,8 +676,8 @@ static int dc_launch(DcRun &r, int algorithm, const unsigned char *d_active, con
         h->stats.launches += 1;
         CUDA_TRY(h, h->spec.dc(&h->prog, &r.sa, &a, h->stream));
     } else {
-        CUDA_TRY(h, launch_dc(h->prog, h->lu[0].prog, r.sa, a, h->block_pref, h->smem_limit, h->stream,
-                              &h->stats.launches));
+        CUDA_TRY(h, h->k.dc(&h->prog, &h->lu[0].prog, &r.sa, &a, h->block_pref, h->smem_limit, h->stream,
+                            &h->stats.launches));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -966,7 +985,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
                 h->stats.launches += 1;
                 ce = h->spec.tran_fixed(&h->prog, &sa, &a, s);
             } else {
-                ce = launch_tran_fixed(h->prog, h->lu[1].prog, sa, a, h->block_pref, h->smem_limit, s, &h->stats.launches);
+                ce = h->k.tran_fixed(&h->prog, &h->lu[1].prog, &sa, &a, h->block_pref, h->smem_limit, s, &h->stats.launches);
             }
             if (host_u != nullptr && ce == cudaSuccess) {
                 int64_t tp_end = 1 + a.k_end / se;                     // one past the last point written
@@ -1011,7 +1030,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
             h->stats.launches += 1;
             ce = h->spec.tran_adaptive(&h->prog, &sa, &a, s);
         } else {
-            ce = launch_tran_adaptive(h->prog, h->lu[1].prog, sa, a, h->block_pref, h->smem_limit, s, &h->stats.launches);
+            ce = h->k.tran_adaptive(&h->prog, &h->lu[1].prog, &sa, &a, h->block_pref, h->smem_limit, s, &h->stats.launches);
         }
         cudaEventRecord(h->ev1, s);
         if (ce == cudaSuccess) {
@@ -1072,6 +1091,22 @@ extern "C" int cb200_tran_fetch(cb200_handle *h, const cb200_spec *spec, double 
     return rc;
 }
 
+extern "C" int cb200_load_va_models(cb200_handle *h, const char *cuda_header, const char *csrc_dir,
+                                    const char *cache_dir)
+{
+    if (!cuda_header || !csrc_dir || !cache_dir) return fail(h, CB200_EINVAL, "cb200_load_va_models: null argument");
+    KernelSet ks;
+    std::string e = build_va_kernel_set(cuda_header, csrc_dir, cache_dir, ks);
+    if (!e.empty()) return fail(h, CB200_ECUDA, e);
+    if (!h) { unload_kernel_set(ks); return CB200_OK; }      // cache warm-up only
+    cudaSetDevice(h->device);
+    if (h->k.dl) unload_kernel_set(h->k);
+    h->k = ks;
+    unload_spec(h->spec);                 // specialised kernels were generated without these models
+    h->spec_gen[0] = h->spec_gen[1] = -1;
+    return CB200_OK;
+}
+
 extern "C" int cb200_set_tstops(cb200_handle *h, const double *tstops, int32_t n)
 {
     if (!h || n < 0 || (n > 0 && !tstops)) return fail(h, CB200_EINVAL, "cb200_set_tstops: bad arguments");
@@ -1107,6 +1142,7 @@ extern "C" int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t
     in.dev_gbase = &h->dev_gbase; in.dev_cbase = &h->dev_cbase; in.dev_bbase = &h->dev_bbase;
     in.src_list = &h->src_list; in.nl_list = &h->nl_list; in.limit_init_ref = &h->limit_init_ref;
     in.src_uniform = &h->src_uniform; in.method = method;
+    in.va_header_path = h->k.va_header_path;
     in.uniform = &h->uniform; in.lu_dc = &h->lu[0].host; in.lu_tr = &h->lu[1].host;
     in.n_lane_cols = h->n_lane_cols;
     // one wave: enough resident blocks per SM for all lanes, as far as registers allow

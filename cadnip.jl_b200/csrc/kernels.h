@@ -124,3 +124,17 @@ cudaError_t launch_debug_exp(const double *x, double *y, int n, cudaStream_t st)
 int choose_block(int n_slots, size_t smem_limit, int preferred);
 
 }  // namespace cb200
+
+// C entry points of a kernel set (kernels.cu; see KernelSet in specialize.h)
+extern "C" {
+int cb200_k_abi(void);
+cudaError_t cb200_k_eval(const cb200::Program *, const cb200::SpecArgs *, const cb200::EvalArgs *,
+                         cudaStream_t, int64_t *);
+cudaError_t cb200_k_dc(const cb200::Program *, const cb200::LuProgram *, const cb200::SpecArgs *,
+                       const cb200::DcArgs *, int, size_t, cudaStream_t, int64_t *);
+cudaError_t cb200_k_tran_fixed(const cb200::Program *, const cb200::LuProgram *, const cb200::SpecArgs *,
+                               const cb200::TranArgs *, int, size_t, cudaStream_t, int64_t *);
+cudaError_t cb200_k_tran_adaptive(const cb200::Program *, const cb200::LuProgram *,
+                                  const cb200::SpecArgs *, const cb200::AdaptArgs *, int, size_t,
+                                  cudaStream_t, int64_t *);
+}

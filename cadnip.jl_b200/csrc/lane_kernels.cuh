@@ -326,6 +326,18 @@ __device__ __forceinline__ double d_junction_cap(double V, double Cj0, double Vj
 }
 
 // ---------------------------------------------------------------------------
+// Verilog-A modules: the emitter (cadnip_b200/verilog_a.py) writes one va_stamp_<module>
+// function per module plus va_dispatch; kernels that serve circuits with VA devices
+// are compiled with -DCB200_VA_HEADER="...".
+// ---------------------------------------------------------------------------
+#ifdef CB200_VA_HEADER
+#include CB200_VA_HEADER
+#else
+template <int PASS, typename PG, typename W>
+__device__ __forceinline__ void va_dispatch(const PG &, W &, int, int, double) {}
+#endif
+
+// ---------------------------------------------------------------------------
 // device evaluation: one stamp! call.
 //   PASS 0 writes every stamp (once per kernel);
 //   PASS 1 writes the stamps that depend on the iterate x (every Newton iteration);
@@ -496,6 +508,9 @@ __device__ __forceinline__ void eval_device(const PG &pg, W &w, int d, double t,
             ST_C(gg, gg, Cgd); ST_C(gg, dd, -Cgd); ST_C(dd, gg, -Cgd); ST_C(dd, dd, Cgd);
         }
     } break;
+    case CB200_DEV_VA:                               // emitted Verilog-A module, flags = model index
+        va_dispatch<PASS>(pg, w, d, flags, t);
+        break;
     default: break;
     }
 }

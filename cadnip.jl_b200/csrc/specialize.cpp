@@ -174,6 +174,7 @@ std::string generate_spec_source(const SpecInput &in)
     const Program &p = *in.prog;
     std::ostringstream o;
     o << "// generated by cadnip-b200 (specialize.cpp) -- circuit-specialised kernels; do not edit\n";
+    if (!in.va_header_path.empty()) o << "#define CB200_VA_HEADER \"" << in.va_header_path << "\"\n";
     o << "#include \"lane_kernels.cuh\"\n";
     o << "namespace {\nusing namespace cb200;\n";
     o << "struct SProg {\n";
@@ -296,6 +297,63 @@ static std::string find_nvcc()
     if (env && exists(env)) return env;
     if (exists("/usr/local/cuda/bin/nvcc")) return "/usr/local/cuda/bin/nvcc";
     return "nvcc";
+}
+
+void unload_kernel_set(KernelSet &k)
+{
+    if (k.dl) dlclose(k.dl);
+    k = KernelSet();
+}
+
+std::string build_va_kernel_set(const std::string &va_header_text, const std::string &csrc_dir,
+                                const std::string &cache_dir, KernelSet &out)
+{
+    uint64_t h = 1469598103934665603ULL;
+    h = fnv1a(h, va_header_text);
+    char hex[32];
+    snprintf(hex, sizeof hex, "%016llx", (unsigned long long)h);
+    mkdir(cache_dir.c_str(), 0755);
+    const std::string hdr = cache_dir + "/va_" + hex + ".cuh";
+    if (!exists(hdr)) {
+        const std::string tmp = hdr + ".tmp" + std::to_string((long)getpid());
+        { std::ofstream f(tmp); f << va_header_text; if (!f) return "va models: cannot write " + tmp; }
+        if (rename(tmp.c_str(), hdr.c_str()) != 0) return "va models: cannot move " + tmp;
+    }
+    // the kernel set also depends on the sources it is rebuilt from
+    uint64_t hk = h;
+    for (const char *f : {"/kernels.cu", "/lane_kernels.cuh", "/kernels.h", "/../../include/cadnip_b200.h"}) {
+        std::string body = slurp(csrc_dir + f);
+        if (body.empty()) return "va models: cannot read " + csrc_dir + f;
+        hk = fnv1a(hk, body);
+    }
+    snprintf(hex, sizeof hex, "%016llx", (unsigned long long)hk);
+    const std::string so = cache_dir + "/kern_" + hex + ".so", log = cache_dir + "/kern_" + hex + ".log";
+    if (!exists(so)) {
+        const std::string tmp = cache_dir + "/kern_" + hex + ".tmp" + std::to_string((long)getpid()) + ".so";
+        std::string cmd = find_nvcc() + " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 "
+                          "-Xcompiler -fPIC -shared -DCB200_VA_HEADER='\"" + hdr + "\"' -I\"" + csrc_dir +
+                          "\" -o \"" + tmp + "\" \"" + csrc_dir + "/kernels.cu\" > \"" + log + "\" 2>&1";
+        if (system(cmd.c_str()) != 0) {
+            std::string l = slurp(log);
+            if (l.size() > 3000) l = l.substr(l.size() - 3000);
+            return "va models: nvcc failed (" + cmd + "):\n" + l;
+        }
+        if (rename(tmp.c_str(), so.c_str()) != 0) return "va models: cannot move " + tmp;
+    }
+    void *dl = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!dl) return std::string("va models: dlopen failed: ") + dlerror();
+    out.eval = (k_eval_fn)dlsym(dl, "cb200_k_eval");
+    out.dc = (k_dc_fn)dlsym(dl, "cb200_k_dc");
+    out.tran_fixed = (k_tran_fn)dlsym(dl, "cb200_k_tran_fixed");
+    out.tran_adaptive = (k_adapt_fn)dlsym(dl, "cb200_k_tran_adaptive");
+    if (!out.eval || !out.dc || !out.tran_fixed || !out.tran_adaptive) {
+        dlclose(dl);
+        out = KernelSet();
+        return "va models: " + so + " does not export the kernel entry points";
+    }
+    out.dl = dl;
+    out.va_header_path = hdr;
+    return "";
 }
 
 void unload_spec(SpecModule &m)

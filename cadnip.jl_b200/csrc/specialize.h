@@ -20,6 +20,7 @@ struct SpecInput {
     const std::vector<double> *uniform;
     const std::vector<unsigned char> *src_uniform;
     int method;                       // CB200_METHOD_* compiled into the transient kernel
+    std::string va_header_path;       // emitted Verilog-A models ("" = none)
     const LuSchedule *lu_dc, *lu_tr;
     int n_lane_cols;
     int block, min_blocks;            // __launch_bounds__ of the generated kernels
@@ -37,6 +38,29 @@ struct SpecModule {
     int block = 0;
     std::string path;
 };
+
+// A kernel set: the table-driven kernels of kernels.cu, either the library's built-in
+// copy or a variant rebuilt with Verilog-A device models (-DCB200_VA_HEADER=...).
+typedef cudaError_t (*k_eval_fn)(const Program *, const SpecArgs *, const EvalArgs *, cudaStream_t, int64_t *);
+typedef cudaError_t (*k_dc_fn)(const Program *, const LuProgram *, const SpecArgs *, const DcArgs *, int,
+                               size_t, cudaStream_t, int64_t *);
+typedef cudaError_t (*k_tran_fn)(const Program *, const LuProgram *, const SpecArgs *, const TranArgs *, int,
+                                 size_t, cudaStream_t, int64_t *);
+typedef cudaError_t (*k_adapt_fn)(const Program *, const LuProgram *, const SpecArgs *, const AdaptArgs *, int,
+                                  size_t, cudaStream_t, int64_t *);
+struct KernelSet {
+    void *dl = nullptr;
+    k_eval_fn eval = nullptr;
+    k_dc_fn dc = nullptr;
+    k_tran_fn tran_fixed = nullptr;
+    k_adapt_fn tran_adaptive = nullptr;
+    std::string va_header_path;       // "" for the built-in set
+};
+// Writes the emitted Verilog-A header into cache_dir, rebuilds kernels.cu against it
+// (nvcc, cached by content hash) and loads the result.  Returns "" on success.
+std::string build_va_kernel_set(const std::string &va_header_text, const std::string &csrc_dir,
+                                const std::string &cache_dir, KernelSet &out);
+void unload_kernel_set(KernelSet &k);
 
 std::string generate_spec_source(const SpecInput &in);
 // Returns "" on success.  The shared object is cached under cache_dir, keyed by a hash

@@ -56,6 +56,8 @@ class LoweredCircuit:
     dev_names: List[str]
     dev_user_nodes: List[List[int]]
     breakpoints: List[Any]
+    va_models: List[Any] = field(default_factory=list)   # VAModel per DEV_VA flags value
+    n_user_nodes: int = -1          # nodes allocated by get_node! (the rest are internal nodes)
 
     @property
     def n(self) -> int:
@@ -103,7 +105,8 @@ class LoweredCircuit:
                     node_ptr=np.asarray(node_ptr, dtype=np.int32),
                     nodes=np.asarray(nodes, dtype=np.int32),
                     par_ptr=self.dev_param_ptr.astype(np.int32),
-                    par=np.ascontiguousarray(par), n_nodes=self.n_nodes)
+                    par=np.ascontiguousarray(par),
+                    n_nodes=self.n_user_nodes if self.n_user_nodes >= 0 else self.n_nodes)
 
 
 class _ParamPool:
@@ -168,8 +171,16 @@ def lower(builder, params: Params, spec: MNASpec, P: int = 1) -> LoweredCircuit:
 
     kind, flags, node_ptr, nodes, par_ptr, pars = [], [], [0], [], [0], []
     gbase, cbase, bbase, names, user_nodes = [], [], [], [], []
+    va_models: List[Any] = []
     for d in ctx.devices:
-        kind.append(d.kind); flags.append(d.flags); names.append(d.name)
+        f = d.flags
+        if d.model is not None:                        # DEV_VA: flags = index of the model
+            uids = [m.uid for m in va_models]
+            if d.model.uid not in uids:
+                va_models.append(d.model)
+                uids.append(d.model.uid)
+            f = uids.index(d.model.uid)
+        kind.append(d.kind); flags.append(f); names.append(d.name)
         nodes += [res(i) for i in d.nodes]
         node_ptr.append(len(nodes))
         pars += [pool.ref(v) for v in d.params]
@@ -194,7 +205,20 @@ def lower(builder, params: Params, spec: MNASpec, P: int = 1) -> LoweredCircuit:
         uniform=np.asarray(pool.uniform, dtype=np.float64),
         limit_init_ref=np.asarray(limit_init_ref, dtype=np.int32),
         lane_soa=np.ascontiguousarray(soa, dtype=np.float64), P=P,
-        dev_names=names, dev_user_nodes=user_nodes, breakpoints=list(ctx.breakpoints))
+        dev_names=names, dev_user_nodes=user_nodes, breakpoints=list(ctx.breakpoints),
+        va_models=va_models, n_user_nodes=_user_node_count(ctx))
+
+
+def _user_node_count(ctx: MNAContext) -> int:
+    """Nodes the builder allocated itself; internal nodes (alloc_internal_node!) must all
+    come after them -- the reference's builders allocate every external node before the
+    first stamp! call (offset-stability discipline, test/mna/pcnr.jl:33-36)."""
+    flags = ctx.internal_node_flags
+    n_user = sum(1 for f in flags if not f)
+    if any(flags[:n_user]):
+        raise ValueError("allocate all circuit nodes with get_node before stamping devices that "
+                         "create internal nodes")
+    return n_user
 
 
 def lower_circuit(circuit: MNACircuit, spec: Optional[MNASpec] = None) -> LoweredCircuit:

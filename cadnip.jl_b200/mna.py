@@ -26,6 +26,7 @@ import numpy as np
 # device kind / wave ids: must match include/cadnip_b200.h
 DEV_RESISTOR, DEV_CAPACITOR, DEV_INDUCTOR, DEV_VSOURCE, DEV_ISOURCE = 1, 2, 3, 4, 5
 DEV_VCVS, DEV_VCCS, DEV_CCVS, DEV_CCCS, DEV_DIODE, DEV_DIODECAP, DEV_SIMPLEMOS = 6, 7, 8, 9, 10, 11, 12
+DEV_VA = 13
 WAVE_NONE, WAVE_PWL, WAVE_PULSE, WAVE_SIN = 0, 1, 2, 3
 
 
@@ -83,6 +84,7 @@ class DeviceRow:
     gbase: int
     cbase: int
     bbase: int
+    model: Any = None              # VAModel for DEV_VA rows
 
 
 class MNAContext:
@@ -569,6 +571,28 @@ def stamp(dev, ctx: MNAContext, *ports, t=0.0, mode="tran", x=ZERO_VECTOR):
         ctx.stamp_capacitance(g, d, dev.Cgd)
         ctx._record(DEV_SIMPLEMOS, 0, dev.name, [d, g, s], [d, g, s],
                     [dev.Vth, dev.K, dev.lambda_, dev.Cgd, dev.Cgs], base)
+        return None
+    from .verilog_a import VAInstance
+    if isinstance(dev, VAInstance):                    # generated VA stamp!, src/vasim.jl:2993-3985
+        m = dev.model
+        if len(pr) != len(m.ports):
+            raise TypeError(f"{m.name} has {len(m.ports)} ports, got {len(pr)}")
+        loc: List[Index] = list(pr)
+        for node in m.internal:                        # alloc_internal_node! in declaration order
+            loc.append(ctx.alloc_internal_node(f"{m.name}_{node}", dev.name))
+        S = STATE_DEPENDENT
+        for item in m.stamp_plan():
+            if item[0] == "Q":                         # alloc_charge!(ctx, name, instance, p, n)
+                _, pi, ni, qname = item
+                loc.append(ctx.alloc_charge(f"{dev.name}_{m.name}_{qname}", loc[pi], 0 if ni is None else loc[ni]))
+            elif item[0] == "G":
+                ctx.stamp_G(loc[item[1]], loc[item[2]], S)
+            elif item[0] == "C":
+                ctx.stamp_C(loc[item[1]], loc[item[2]], S)
+            else:
+                ctx.stamp_b(loc[item[1]], S)
+        ctx._record(DEV_VA, 0, dev.name, list(pr), loc, dev.params, base)
+        ctx.devices[-1].model = m
         return None
     raise TypeError(f"no stamp method for device of type {type(dev).__name__}")
 

@@ -71,7 +71,11 @@ extern "C" {
                                    flags bit0 = limit (PCNR)                            */
 #define CB200_DEV_DIODECAP  11  /* nodes p,n  params Is,Vt,n,Cj0,Vj,m   devices.jl:1558 */
 #define CB200_DEV_SIMPLEMOS 12  /* nodes d,g,s params Vth,K,lambda,Cgd,Cgs devices.jl:1667 */
-#define CB200_DEV_KIND_MAX  12
+#define CB200_DEV_VA        13  /* emitted Verilog-A module (cadnip_b200.verilog_a / src/vasim.jl:2993-3985):
+                                   flags = model index in the header given to
+                                   cb200_load_va_models; nodes ports, internal nodes,
+                                   charge unknowns; params in declaration order          */
+#define CB200_DEV_KIND_MAX  13
 
 /* source waveform selector, stored in dev_flags of V/I sources
  * (PWLWave / PulseWave / SinWave, src/mna/devices.jl:130-216)                */
@@ -210,6 +214,14 @@ int cb200_analyze(cb200_handle *h, const cb200_spec *spec, double gamma);
 /* perm arrays are int64 1-based: pivot k eliminates row rowperm[k], col colperm[k]. */
 int cb200_get_pivot_order(const cb200_handle *h, int64_t *rowperm, int64_t *colperm,
                           int64_t *nnz_lu);
+
+/* Verilog-A device models.  cuda_header is the text emitted for the circuit's modules
+ * (va_stamp_<module> functions + va_dispatch): the kernels are rebuilt with it (nvcc,
+ * cached under cache_dir by content hash) and the handle switches to them.  Required
+ * before any evaluation when the description contains CB200_DEV_VA rows.  With
+ * h == NULL the kernel set is only built into the cache (no device needed).           */
+int cb200_load_va_models(cb200_handle *h, const char *cuda_header, const char *csrc_dir,
+                         const char *cache_dir);
 
 /* The emitter (north_star: "a new emitter lowers each device model's stamp function
  * ... to hand-written-style sm_100a CUDA C"): generates, compiles (nvcc, cached under

@@ -55,7 +55,8 @@ struct ora_ctx {
     double *G_nzval, *C_nzval, *b;            /* storage owned by the workspace */
     const int64_t *G_mapping, *C_mapping;     /* 1-based nz index, 0 = skip     */
     int64_t lenG, lenC, lenb;
-    int64_t G_pos, C_pos, b_pos, current_pos, limit_pos;
+    int64_t G_pos, C_pos, b_pos, current_pos, limit_pos, charge_pos, internal_pos;
+    int64_t n_user_nodes;             /* nodes the builder allocated with get_node! */
 };
 
 static void *xrealloc(void *p, size_t sz)
@@ -86,6 +87,7 @@ void ora_ctx_free(ora_ctx *c)
 static void ctx_reset_for_restamping(ora_ctx *c, int64_t n_nodes_prealloc)
 {
     c->n_nodes = n_nodes_prealloc;   /* the builder's get_node! calls re-create them */
+    c->n_user_nodes = n_nodes_prealloc;
     c->n_currents = 0; c->n_charges = 0; c->n_limits = 0;
     c->nG = c->nC = c->nb = 0;
 }
@@ -393,6 +395,64 @@ static double diode_junction_cap(double V, double Cj0, double Vj, double m)
 }
 
 /* ------------------------------------------------------------------------- */
+/* Verilog-A modules.  The stamp! method of a VA module is generated code
+ * (src/vasim.jl:2993-3985).  Here it is C emitted by the product's emitter
+ * (cadnip.jl_b200/verilog_a.py) from the same IR as the CUDA version, compiled into a small
+ * shared object by the test harness and registered with ora_set_va_table; it talks to
+ * the context only through this callback table.  Handles: > 0 node index, 0 ground,
+ * < 0 charge unknown -k (ChargeIndex(k)).                                           */
+/* ------------------------------------------------------------------------- */
+typedef struct ora_va_api {
+    long (*alloc_internal_node)(void *ctx);
+    long (*alloc_charge)(void *ctx, long p, long n);
+    double (*xval)(void *ctx, long node, const double *x, long nx);
+    void (*stamp_G)(void *ctx, long i, long j, double v);
+    void (*stamp_C)(void *ctx, long i, long j, double v);
+    void (*stamp_b)(void *ctx, long i, double v);
+} ora_va_api;
+typedef void (*ora_va_fn)(const ora_va_api *, void *, const int *, const double *, const double *, long, double);
+static ora_va_fn (*g_va_table)(int) = NULL;
+
+void ora_set_va_table(void *table_fn) { g_va_table = (ora_va_fn (*)(int))table_fn; }
+
+static mna_index va_index(long h)
+{
+    if (h > 0) return ix_make(IX_NODE, h);
+    if (h < 0) return ix_make(IX_CHARGE, -h);
+    return ix_make(IX_GROUND, 0);
+}
+/* alloc_internal_node!  context.jl:654-679 ; value_only.jl (counter based) */
+static long va_alloc_internal_node(void *vc)
+{
+    ora_ctx *c = (ora_ctx *)vc;
+    if (c->direct) { int64_t pos = c->internal_pos++; return (long)(c->n_user_nodes + pos + 1); }
+    c->n_nodes += 1;
+    return (long)c->n_nodes;
+}
+/* alloc_charge!  context.jl:741-746 */
+static long va_alloc_charge(void *vc, long p, long n)
+{
+    ora_ctx *c = (ora_ctx *)vc;
+    (void)p; (void)n;
+    if (c->direct) { int64_t pos = c->charge_pos++; return -(long)pos; }
+    c->n_charges += 1;
+    return -(long)c->n_charges;
+}
+/* V_k = node_k == 0 ? 0.0 : x[node_k], tolerant of an x shorter than the system
+ * (vasim.jl:3123-3133)                                                             */
+static double va_xval(void *vc, long node, const double *x, long nx)
+{
+    (void)vc;
+    if (node <= 0 || x == NULL || nx == 0 || node > nx) return 0.0;
+    return x[node - 1];
+}
+static void va_stamp_G(void *vc, long i, long j, double v) { stamp_G((ora_ctx *)vc, va_index(i), va_index(j), v); }
+static void va_stamp_C(void *vc, long i, long j, double v) { stamp_C((ora_ctx *)vc, va_index(i), va_index(j), v); }
+static void va_stamp_b(void *vc, long i, double v) { stamp_b((ora_ctx *)vc, va_index(i), v); }
+static const ora_va_api g_va_api = {va_alloc_internal_node, va_alloc_charge, va_xval,
+                                    va_stamp_G, va_stamp_C, va_stamp_b};
+
+/* ------------------------------------------------------------------------- */
 /* the builder: one stamp! call per netlist row, in order                      */
 /* ------------------------------------------------------------------------- */
 static void run_builder(const ora_netlist *nl, const ora_spec *spec, double t,
@@ -562,6 +622,11 @@ static void run_builder(const ora_netlist *nl, const ora_spec *spec, double t,
             stamp_b(c, S, Ieq);
             stamp_capacitance(c, g, s, par[4]);   /* Cgs */
             stamp_capacitance(c, g, dd, par[3]);  /* Cgd */
+        } break;
+        case ORA_DEV_VA: {                /* generated VA stamp!, vasim.jl:2993-3985 */
+            ora_va_fn fn = g_va_table ? g_va_table(flags) : NULL;
+            if (!fn) { fprintf(stderr, "cadnip_oracle: VA model %d not registered\n", flags); abort(); }
+            fn(&g_va_api, c, nd, par, x, (long)nx, t);
         } break;
         default:
             fprintf(stderr, "cadnip_oracle: unknown device kind %d\n", nl->kind[d]);
@@ -830,6 +895,7 @@ ora_workspace *ora_create_workspace(const ora_structure *s)
     w->piv = (int64_t *)calloc((size_t)s->n + 1, sizeof(int64_t));
     ora_ctx *d = &w->dctx;
     d->direct = 1;
+    d->n_user_nodes = s->nl.n_nodes;
     d->n_nodes = s->n_nodes; d->n_currents = s->n_currents;
     d->n_charges = s->n_charges; d->n_limits = s->n_limits;
     d->G_nzval = w->G_nz; d->C_nzval = w->C_nz; d->b = w->b; d->b_V = w->b_V;
@@ -853,6 +919,7 @@ static void reset_direct_stamp(ora_workspace *w, const ora_structure *s)
 {
     ora_ctx *d = &w->dctx;
     d->G_pos = 1; d->C_pos = 1; d->b_pos = 1; d->current_pos = 1; d->limit_pos = 1;
+    d->charge_pos = 1; d->internal_pos = 0;
     memset(w->G_nz, 0, sizeof(double) * s->nnz);
     memset(w->C_nz, 0, sizeof(double) * s->nnz);
     memset(w->b, 0, sizeof(double) * s->n);

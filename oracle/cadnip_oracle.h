@@ -31,7 +31,7 @@ enum {
     ORA_DEV_RESISTOR = 1, ORA_DEV_CAPACITOR = 2, ORA_DEV_INDUCTOR = 3,
     ORA_DEV_VSOURCE = 4, ORA_DEV_ISOURCE = 5, ORA_DEV_VCVS = 6, ORA_DEV_VCCS = 7,
     ORA_DEV_CCVS = 8, ORA_DEV_CCCS = 9, ORA_DEV_DIODE = 10, ORA_DEV_DIODECAP = 11,
-    ORA_DEV_SIMPLEMOS = 12
+    ORA_DEV_SIMPLEMOS = 12, ORA_DEV_VA = 13
 };
 enum { ORA_WAVE_NONE = 0, ORA_WAVE_PWL = 1, ORA_WAVE_PULSE = 2, ORA_WAVE_SIN = 3 };
 enum { ORA_MODE_DCOP = 0, ORA_MODE_TRAN = 1, ORA_MODE_TRANOP = 2, ORA_MODE_AC = 3 };
@@ -64,6 +64,10 @@ typedef struct ora_netlist {
 typedef struct ora_ctx ora_ctx;           /* MNAContext           context.jl:248  */
 typedef struct ora_structure ora_structure; /* CompiledStructure  precompile.jl:88 */
 typedef struct ora_workspace ora_workspace; /* EvalWorkspace      precompile.jl:168 */
+
+/* Verilog-A modules: registers the lookup `fn(model_index) -> stamp function` of a
+ * shared object holding the C the product's emitter generated (see cadnip_oracle.c).  */
+void ora_set_va_table(void *table_fn);
 
 /* ---- pure functions (known-answer tests) -------------------------------- */
 double ora_pwl_at_time(const double *ts, const double *ys, int n, double t);    /* devices.jl:47  */

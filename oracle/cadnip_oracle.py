@@ -117,6 +117,8 @@ def lib():
                                      C.c_double, C.c_double, C.POINTER(TranOpts), lp, C.c_int,
                                      dp, dp, C.c_int64, ip, ip, lp, C.c_int]
         L.ora_num_threads.restype = C.c_int
+        L.ora_set_va_table.restype = None
+        L.ora_set_va_table.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -329,6 +331,35 @@ def sweep_tran(nl: OracleNetlist, spec: Spec, t0, t1, opts: TranOpts, save_idx, 
                      _lp(save), len(save), _dp(ot), _dp(ou), cap_T, _ip(Tn), _ip(st), _lp(it),
                      nthreads)
     return dict(t=ot, u=ou, T=Tn, status=st, newton_iters=it)
+
+
+_va_libs = []
+
+
+def load_va_models(models) -> None:
+    """Compile the C the product's emitter generated for these Verilog-A modules
+    (gcc, cached under oracle/_gen) and register it with the oracle.  The model index
+    is the position in ``models`` (== dev_flags of the lowered circuit)."""
+    import hashlib
+    import sys
+    sys.path.insert(0, os.path.dirname(_HERE))
+    import cadnip_b200.verilog_a as va
+    src = va.c_source(models)
+    gen = os.path.join(_HERE, "_gen")
+    os.makedirs(gen, exist_ok=True)
+    h = hashlib.sha256(src.encode()).hexdigest()[:16]
+    so = os.path.join(gen, f"va_{h}.so")
+    if not os.path.exists(so):
+        cfile = os.path.join(gen, f"va_{h}.c")
+        with open(cfile, "w") as f:
+            f.write(src)
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.run([cc, "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", so + ".tmp", cfile, "-lm"],
+                       check=True)
+        os.replace(so + ".tmp", so)
+    L = C.CDLL(so)
+    _va_libs.append(L)
+    lib().ora_set_va_table(C.cast(L.ora_va_table, C.c_void_p))
 
 
 def num_threads() -> int:

@@ -1,0 +1,377 @@
+"""Verilog-A emitter (tier 0): the reference's inline VA test models, checked through the
+oracle against the reference's known answers (CPU) and GPU-vs-oracle parity (-m gpu).
+Model sources are the reference's test fixtures (test/mna/vadistiller.jl, va_mosfet.jl)."""
+import math
+
+import numpy as np
+import pytest
+
+import cadnip_b200 as cb
+import cadnip_oracle as ora
+from cadnip_b200 import MNAContext, ZERO_VECTOR, get_node, stamp, VoltageSource, Resistor
+
+VADDiode = cb.va("""
+module VADDiode(a, c);
+    parameter real Is = 1e-14;
+    parameter real N = 1.0;
+    inout a, c;
+    electrical a, c;
+    analog begin
+        I(a,c) <+ Is*(exp(V(a,c)/(N*0.02585)) - 1.0);
+    end
+endmodule""")                                   # test/mna/vadistiller.jl:141-151
+
+VADDiodeRs = cb.va("""
+module VADDiodeRs(a, c);
+    parameter real Is = 1e-14;
+    parameter real N = 1.0;
+    parameter real Rs = 10.0;
+    inout a, c;
+    electrical a, c, a_int;
+    analog begin
+        I(a, a_int) <+ V(a, a_int) / Rs;
+        I(a_int, c) <+ Is*(exp(V(a_int,c)/(N*0.02585)) - 1.0);
+    end
+endmodule""")                                   # test/mna/vadistiller.jl:184-196
+
+ChainDiodeRs = cb.va("""
+module ChainDiodeRs(a, c);
+    parameter real Is = 76.9e-12;
+    parameter real N = 1.45;
+    parameter real Rs = 0.042;
+    inout a, c;
+    electrical a, c, a_int;
+    analog begin
+        I(a, a_int) <+ V(a, a_int) / Rs;
+        I(a_int, c) <+ Is*(limexp(V(a_int,c)/(N*0.02585)) - 1.0);
+    end
+endmodule""")                                   # test/mna/vadistiller.jl:245-257
+
+_MOS_BODY = """
+    real Vgs, Vds, Vov, Ids;
+    analog begin
+        Vgs = V(g, s);
+        Vds = V(d, s);
+        Vov = Vgs - Vth;
+        if (Vov <= 0) begin
+            Ids = 0;
+        end else if (Vds < Vov) begin
+            Ids = K * (Vov * Vds - Vds * Vds / 2);
+        end else begin
+            Ids = K / 2 * Vov * Vov;
+        end
+        I(d, s) <+ Ids;
+"""
+SimpleMOS = cb.va("module SimpleMOS(d, g, s);\n parameter real K = 1e-3;\n parameter real Vth = 0.5;\n"
+                  " inout d, g, s;\n electrical d, g, s;\n" + _MOS_BODY + " end\nendmodule")   # va_mosfet.jl:71-95
+CapMOS = cb.va("module CapMOS(d, g, s);\n parameter real K = 1e-3;\n parameter real Vth = 0.5;\n"
+               " parameter real Cgs = 10e-15;\n parameter real Cgd = 5e-15;\n inout d, g, s;\n electrical d, g, s;\n"
+               + _MOS_BODY + "  I(g, s) <+ Cgs * ddt(V(g, s));\n  I(g, d) <+ Cgd * ddt(V(g, d));\n end\nendmodule")
+PMOS = cb.va("""
+module PMOS(d, g, s);
+    parameter real K = 1e-3;
+    parameter real Vth = 0.5;
+    inout d, g, s;
+    electrical d, g, s;
+    real Vsg, Vsd, Vov, Ids;
+    analog begin
+        Vsg = V(s, g);
+        Vsd = V(s, d);
+        Vov = Vsg - Vth;
+        if (Vov <= 0) begin
+            Ids = 0;
+        end else if (Vsd < Vov) begin
+            Ids = K * (Vov * Vsd - Vsd * Vsd / 2);
+        end else begin
+            Ids = K / 2 * Vov * Vov;
+        end
+        I(s, d) <+ Ids;
+    end
+endmodule""")                                   # va_mosfet.jl:357-381
+JunctionCap = cb.va("""
+module JunctionCap(p, n);
+    parameter real Cj0 = 1e-12;
+    parameter real phi = 0.8;
+    parameter real m = 0.5;
+    inout p, n;
+    electrical p, n;
+    real V, C;
+    analog begin
+        V = V(p, n);
+        if (V < 0.5 * phi) begin
+            C = Cj0 / $pow(1 - V/phi, m);
+        end else begin
+            C = Cj0 / $pow(0.5, m);
+        end
+        I(p, n) <+ C * ddt(V(p, n));
+    end
+endmodule""")                                   # va_mosfet.jl:465-484
+
+
+# model lists (in lowering order) of the GPU tests below: __graft_entry__.build() pre-builds
+# their kernel sets so the GPU box finds them in the in-tree cache
+GPU_MODEL_SETS = [[PMOS, SimpleMOS], [CapMOS, JunctionCap], [ChainDiodeRs]]
+
+
+def B(f):
+    def build(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
+        ctx = MNAContext() if ctx is None else ctx
+        f(ctx, params)
+        return ctx
+    return build
+
+
+def mos_bias(model, vg, vd, **kw):
+    def f(ctx, params):
+        d = get_node(ctx, "d"); g = get_node(ctx, "g")
+        stamp(VoltageSource(vg, name="Vg"), ctx, g, 0)
+        stamp(VoltageSource(vd, name="Vd"), ctx, d, 0)
+        stamp(model(K=1e-3, Vth=0.5, **kw), ctx, d, g, 0)
+    return B(f)
+
+
+def inverter(vin):
+    def f(ctx, params):
+        vdd = get_node(ctx, "vdd"); out = get_node(ctx, "out"); inp = get_node(ctx, "inp")
+        stamp(VoltageSource(3.0, name="Vdd"), ctx, vdd, 0)
+        stamp(VoltageSource(params.vin if "vin" in params else vin, name="Vin"), ctx, inp, 0)
+        stamp(PMOS(K=1e-3, Vth=0.5, name="MP"), ctx, out, inp, vdd)
+        stamp(SimpleMOS(K=params.kn if "kn" in params else 1e-3, Vth=0.5, name="MN"), ctx, out, inp, 0)
+        stamp(Resistor(1e6, name="Rload"), ctx, out, 0)
+    return B(f)
+
+
+def chain(ctx, params):
+    n1, na, nb, nc = [get_node(ctx, s) for s in ("n1", "na", "nb", "nc")]
+    stamp(VoltageSource(50.0, name="V1"), ctx, n1, 0)
+    stamp(ChainDiodeRs(name="d1"), ctx, n1, na)
+    stamp(ChainDiodeRs(name="d2"), ctx, na, nb)
+    stamp(ChainDiodeRs(name="d3"), ctx, nb, nc)
+
+
+def oracle_dc(builder, mode="dcop", **params):
+    lc = cb.lower_circuit(cb.MNACircuit(builder, **params))
+    ora.load_va_models(lc.va_models)
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    x, ok, it = ora.solve_dc(nl, ora.make_spec(mode=mode))
+    return lc, nl, x, ok
+
+
+# ---- emitter structure ---------------------------------------------------------
+def test_parser_and_structure():
+    assert SimpleMOS.ports == ["d", "g", "s"] and SimpleMOS.internal == [] and SimpleMOS.branches == [("d", "s")]
+    assert ChainDiodeRs.internal == ["a_int"] and ChainDiodeRs.branches == [("a", "a_int"), ("a_int", "c")]
+    assert CapMOS.reactive == [False, True, True] and CapMOS.vdep == [False, False, False]
+    assert JunctionCap.reactive == [True] and JunctionCap.vdep == [True] and JunctionCap.n_charges == 1
+    # per branch: 2 G stamps per module node, then 2 b stamps (vasim.jl:3382-3392, :3490-3518)
+    plan = SimpleMOS.stamp_plan()
+    assert [p[0] for p in plan] == ["G"] * 6 + ["b"] * 2
+    assert SimpleMOS(K=2e-3).params == [2e-3, 0.5] and SimpleMOS(k=2e-3, vth=0.7).params == [2e-3, 0.7]
+    with pytest.raises(cb.VAError):
+        SimpleMOS(W=1.0)
+    for bad in ("module m(a); electrical a; analog V(a) <+ 1.0; endmodule",
+                "module m(a,b); electrical a,b; analog I(a,b) <+ $limit(V(a,b), 1, 2); endmodule"):
+        with pytest.raises(cb.VAError):
+            cb.va(bad)
+    src = SimpleMOS.emit_cuda()
+    assert "va_stamp_SimpleMOS_" in src and "VA_G(0, 0, I0_d0);" in src and "VA_B(2, Ieq);" in src
+
+
+# ---- known answers through the oracle -------------------------------------------
+def test_vaddiode_current_known_answer():
+    def f(ctx, params):
+        a = get_node(ctx, "anode")
+        stamp(VoltageSource(0.6, name="V1"), ctx, a, 0)
+        stamp(VADDiode(Is=1e-14, N=1.0), ctx, a, 0)
+    lc, nl, x, ok = oracle_dc(B(f))
+    expected = 1e-14 * (math.exp(0.6 / 0.02585) - 1)
+    assert ok and -x[lc.index_of("I_V1") - 1] == pytest.approx(expected, rel=0.01)   # vadistiller.jl:172-176
+
+    def g(ctx, params):
+        a = get_node(ctx, "anode")
+        stamp(VoltageSource(0.7, name="V1"), ctx, a, 0)
+        stamp(VADDiodeRs(Is=1e-14, N=1.0, Rs=10.0), ctx, a, 0)
+    lc, nl, x, ok = oracle_dc(B(g))
+    i = -x[lc.index_of("I_V1") - 1]
+    assert ok and 0 < i < 0.1                                                          # vadistiller.jl:217-219
+    assert lc.node_names == ["anode", "VADDiodeRs_VADDiodeRs_a_int"] and lc.n == 3
+
+
+def test_chain_internal_nodes_carry_no_anchor_current():
+    lc = cb.lower_circuit(cb.MNACircuit(B(chain)))
+    ora.load_va_models(lc.va_models)
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    S = ora.Structure(nl, ora.make_spec(mode="dcop"))
+    assert lc.node_names[4:] == ["d1_ChainDiodeRs_a_int", "d2_ChainDiodeRs_a_int", "d3_ChainDiodeRs_a_int"]
+    coo = S.coo()
+    assert np.array_equal(coo["G_I"], lc.G_I) and np.array_equal(coo["G_J"], lc.G_J) and np.array_equal(coo["b_I"], lc.b_I)
+    u = np.zeros(S.n); u[:S.n_nodes] = 50.0
+    G, C, b, _ = S.rebuild(u)
+    F = S.dense(G) @ u - b
+    for i, name in enumerate(lc.node_names):
+        if name != "n1":
+            # no gmin anchor to ground: only rounding of the 1190 A-scale cancellation remains
+            # (the old anchor injected 5e-11 A; vadistiller.jl:286-296)
+            assert abs(F[i]) < 1e-12
+    x, ok, it = ora.solve_dc(nl, ora.make_spec(mode="dcop"))
+    for name in ("na", "nb", "nc"):
+        assert x[lc.index_of(name) - 1] == pytest.approx(50.0, abs=2e-2)               # vadistiller.jl:302-306
+
+
+@pytest.mark.parametrize("vg,vd,expect,atol", [(1.5, 2.0, -0.0005, 1e-5), (1.5, 0.3, -0.000255, 1e-6),
+                                               (0.3, 2.0, 0.0, 1e-8)])
+def test_simple_mos_regions(vg, vd, expect, atol):
+    lc, nl, x, ok = oracle_dc(mos_bias(SimpleMOS, vg, vd))
+    assert ok and x[lc.index_of("I_Vd") - 1] == pytest.approx(expect, abs=atol)        # va_mosfet.jl:113-160
+
+
+def test_cmos_inverter_dc():
+    lc, nl, x, ok = oracle_dc(inverter(0.0))
+    assert ok and x[lc.index_of("out") - 1] == pytest.approx(3.0, abs=0.01)            # va_mosfet.jl:411-417
+    lc, nl, x, ok = oracle_dc(inverter(3.0))
+    assert ok and x[lc.index_of("out") - 1] == pytest.approx(0.0, abs=0.01)            # va_mosfet.jl:452-458
+
+
+def test_capmos_dc_and_gate_charging():
+    lc, nl, x, ok = oracle_dc(mos_bias(CapMOS, 1.5, 2.0, Cgs=10e-15, Cgd=5e-15))
+    assert ok and x[lc.index_of("I_Vd") - 1] == pytest.approx(-0.0005, abs=1e-5)       # va_mosfet.jl:211-214
+    S = ora.Structure(nl, ora.make_spec(mode="tran"))
+    G, C, b, _ = S.rebuild(x)
+    assert np.any(C != 0.0) and S.n_charges == 0                                       # linear caps: plain C stamps
+
+    Rg, Cgs, Cgd = 1e3, 10e-12, 5e-12
+    def f(ctx, params):
+        d = get_node(ctx, "d"); g = get_node(ctx, "g"); vin = get_node(ctx, "vin")
+        stamp(VoltageSource(2.0, name="Vin"), ctx, vin, 0)
+        stamp(Resistor(Rg, name="Rg"), ctx, vin, g)
+        stamp(VoltageSource(3.0, name="Vd"), ctx, d, 0)
+        stamp(CapMOS(K=1e-3, Vth=0.5, Cgs=Cgs, Cgd=Cgd), ctx, d, g, 0)
+    lc = cb.lower_circuit(cb.MNACircuit(B(f)))
+    ora.load_va_models(lc.va_models)
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    tau = Rg * (Cgs + Cgd)
+    u0 = np.zeros(lc.n); u0[lc.index_of("vin") - 1] = 2.0; u0[lc.index_of("d") - 1] = 3.0   # gate starts at 0 V
+    o = ora.make_tran_opts(method=1, dt=tau / 200, init=1)
+    r = ora.tran(nl, ora.make_spec(mode="tran"), 0.0, 5 * tau, o, [lc.index_of("g")], u0=u0)
+    assert r["status"] == 0
+    assert r["u"][-1, 0] == pytest.approx(2.0 * (1 - math.exp(-5)), rel=0.05)          # va_mosfet.jl:258-262
+
+
+def test_voltage_dependent_charge_uses_charge_state_formulation():
+    """charge_formulation.jl:151-220: C[p,q] = 1/CHARGE_SCALE, G[q,q] = 1,
+    G[q,p] = -CHARGE_SCALE*dQ/dVp, C[q,q] = 0 (the charge row is algebraic)."""
+    def f(ctx, params):
+        p = get_node(ctx, "p")
+        stamp(VoltageSource(0.4, name="V1"), ctx, p, 0)
+        stamp(JunctionCap(Cj0=1e-12, phi=0.8, m=0.5, name="J1"), ctx, p, 0)
+    lc = cb.lower_circuit(cb.MNACircuit(B(f)))
+    assert lc.n_charges == 1 and lc.charge_names == ["J1_JunctionCap_Q_p_n"] and lc.n == 3
+    ora.load_va_models(lc.va_models)
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    S = ora.Structure(nl, ora.make_spec(mode="tran"))
+    assert S.n_charges == 1
+    p, q = 0, 2                       # unknowns [p | I_V1 | q]
+    CS = 1e12
+    # V = 0.4 is not < 0.5*phi: the guard branch holds C constant, so dQ/dV = C = Cj0/sqrt(0.5)
+    # (the reference's own check, va_mosfet.jl:500-504)
+    G, C, b, _ = S.rebuild(np.array([0.4, 0.0, 0.0]))
+    Gd, Cd = S.dense(G), S.dense(C)
+    assert Cd[p, q] == 1.0 / CS and Cd[q, q] == 0.0 and Gd[q, q] == 1.0
+    assert Gd[q, p] == pytest.approx(-CS * 1e-12 / math.sqrt(0.5), rel=1e-12)
+    assert abs(b[q]) < 1e-12
+    # below the guard the s-dual charge of C(V)*ddt(V) is Q = C(V)*V  =>  dQ/dV = C + V*dC/dV
+    v = 0.2
+    G, C, b, _ = S.rebuild(np.array([v, 0.0, 0.0]))
+    Gd = S.dense(G)
+    Cj = 1e-12 / math.sqrt(1 - v / 0.8)
+    dC = 1e-12 * 0.5 / 0.8 * (1 - v / 0.8) ** -1.5
+    assert Gd[q, p] == pytest.approx(-CS * (Cj + v * dC), rel=1e-12)
+    assert b[q] == pytest.approx(CS * (Cj * v - (Cj + v * dC) * v), rel=1e-9)
+
+
+# ---- GPU parity -----------------------------------------------------------------
+def _sweep_vs_oracle(cs, tran=None):
+    params, P = cs.lane_params()
+    lc = cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P)
+    ora.load_va_models(lc.va_models)
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    out = {}
+    try:
+        x, st, it = comp.dc()
+        xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
+        out["dc"] = (x.T, xo, st, sto)
+        if tran:
+            tspan, dt, method, spec = tran
+            save = list(range(1, lc.n + 1))
+            wave = comp.tran(tspan, dt, method=method, save_idxs=save, specialize=spec)
+            r = wave.fetch(); wave.free()
+            o = ora.make_tran_opts(method={"be": 0, "trap": 1, "gear2": 2}[method], dt=dt)
+            ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), tspan[0], tspan[1], o, save)
+            out["tran"] = (np.transpose(r["u"], (2, 1, 0)), ro["u"], r, ro, comp.handle.is_specialized())
+    finally:
+        comp.close()
+    return lc, out
+
+
+def _close(a, b, rtol=1e-9, atol=1e-12):
+    return np.all(np.abs(a - b) <= atol + rtol * np.maximum(np.abs(a), np.abs(b)))
+
+
+@pytest.mark.gpu
+def test_gpu_va_inverter_sweep_dc_and_transient():
+    cs = cb.CircuitSweep(inverter(0.0), cb.ProductSweep(vin=np.linspace(0.0, 3.0, 13), kn=[0.5e-3, 1e-3, 2e-3]))
+    lc, out = _sweep_vs_oracle(cs)
+    x, xo, st, sto = out["dc"]
+    assert np.array_equal(st, sto) and (st == 0).all()
+    assert _close(x, xo)
+    vout = x[:, lc.index_of("out") - 1].reshape(3, 13)
+    assert np.all(np.diff(vout, axis=1) <= 1e-9)          # transfer curve is monotone
+    assert vout[1, 0] == pytest.approx(3.0, abs=0.01) and vout[1, -1] == pytest.approx(0.0, abs=0.01)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec", [False, True], ids=["table", "specialised"])
+def test_gpu_va_capmos_transient(spec):
+    def f(ctx, params):
+        d = get_node(ctx, "d"); g = get_node(ctx, "g"); vin = get_node(ctx, "vin"); vdd = get_node(ctx, "vdd")
+        stamp(VoltageSource(0.0, tran=cb.PulseWave(0.0, 2.0, 1e-9, 1e-9, 1e-9, 20e-9, 60e-9), name="Vin"), ctx, vin, 0)
+        stamp(VoltageSource(3.0, name="Vdd"), ctx, vdd, 0)
+        stamp(Resistor(params.rg, name="Rg"), ctx, vin, g)
+        stamp(Resistor(2e3, name="Rd"), ctx, vdd, d)
+        stamp(CapMOS(K=params.k, Vth=0.5, Cgs=1e-12, Cgd=0.5e-12), ctx, d, g, 0)
+        stamp(JunctionCap(Cj0=2e-13, phi=0.8, m=0.5, name="Jdb"), ctx, 0, d)     # reverse-biased drain junction
+    cs = cb.CircuitSweep(B(f), cb.ProductSweep(rg=[500.0, 1e3, 2e3], k=[0.5e-3, 1e-3]))
+    lc, out = _sweep_vs_oracle(cs, tran=((0.0, 4e-8), 2e-10, "trap", spec))
+    assert lc.n_charges == 1
+    gpu, ref, r, ro, is_spec = out["tran"]
+    assert is_spec == spec
+    assert np.array_equal(r["status"], ro["status"]) and (r["status"] == 0).all()
+    assert _close(gpu, ref[:, :gpu.shape[1], :]), float(np.max(np.abs(gpu - ref[:, :gpu.shape[1], :])))
+    assert np.array_equal(r["newton_iters"], ro["newton_iters"])
+    d = gpu[:, :, lc.index_of("d") - 1]
+    assert d.min() < 2.0 and d.max() > 2.9                 # the stage actually switches
+
+
+@pytest.mark.gpu
+def test_gpu_va_chain_dc():
+    cs = cb.CircuitSweep(B(chain), cb.Sweep(dummy=[0.0, 1.0]), dummy=0.0)
+    lc, out = _sweep_vs_oracle(cs)
+    x, xo, st, sto = out["dc"]
+    assert np.array_equal(st, sto) and _close(x, xo)
+
+
+@pytest.mark.gpu
+def test_gpu_va_requires_models():
+    from cadnip_b200 import backend
+    lc = cb.lower_circuit(cb.MNACircuit(mos_bias(SimpleMOS, 1.5, 2.0)))
+    models = lc.va_models
+    lc.va_models = []                    # handle created without loading the emitted models
+    h = backend.Handle(lc)
+    try:
+        h.set_lanes(lc.lane_soa, 1)
+        with pytest.raises(backend.CB200Error):
+            h.dc(cb.MNASpec(mode="dcop"))
+    finally:
+        h.close()
+        lc.va_models = models
