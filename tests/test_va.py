@@ -358,7 +358,13 @@ def test_gpu_va_chain_dc():
     cs = cb.CircuitSweep(B(chain), cb.Sweep(dummy=[0.0, 1.0]), dummy=0.0)
     lc, out = _sweep_vs_oracle(cs)
     x, xo, st, sto = out["dc"]
-    assert np.array_equal(st, sto) and _close(x, xo)
+    # a floating chain end behind pA junctions: the operating point is determined only to
+    # ~abstol/Is-slope, so pivot order shows at 1e-6 relative; the reference itself checks
+    # this circuit to 2e-2 V (vadistiller.jl:302-306)
+    assert np.array_equal(st, sto) and (st == 0).all()
+    assert np.allclose(x, xo, rtol=0.0, atol=1e-3)
+    for name in ("na", "nb", "nc"):
+        assert np.allclose(x[:, lc.index_of(name) - 1], 50.0, atol=2e-2)
 
 
 @pytest.mark.gpu
