@@ -201,9 +201,11 @@ EXPORTED_SYMBOLS = [
 
 def prebuild_va_models(models) -> None:
     """Build the kernel set for a circuit's Verilog-A models into the in-tree cache
-    (no GPU needed; what Handle.load_va_models would otherwise build on first use)."""
+    (no GPU needed; what Handle.load_va_models would otherwise build on first use).
+    models: the emitted header text (LoweredCircuit.va_cuda_header) or a list of models."""
     from . import verilog_a as _va
-    rc = lib().cb200_load_va_models(None, _va.cuda_header(list(models)).encode(), _CSRC.encode(), GEN_DIR.encode())
+    text = models if isinstance(models, str) else _va.cuda_header(list(models))
+    rc = lib().cb200_load_va_models(None, text.encode(), _CSRC.encode(), GEN_DIR.encode())
     if rc != OK:
         raise CB200Error(rc, (lib().cb200_last_error(None) or b"").decode())
 
@@ -321,9 +323,8 @@ class Handle:
             raise CB200Error(rc, (L.cb200_last_error(None) or b"").decode())
         self._p = ptr
         self.P = 0
-        if getattr(lc, "va_models", None):
-            from . import verilog_a as _va
-            self.load_va_models(_va.cuda_header(lc.va_models))
+        if getattr(lc, "va_cuda_header", ""):
+            self.load_va_models(lc.va_cuda_header)
 
     def load_va_models(self, cuda_header: str):
         """Rebuild (cached) and load the kernel set with the circuit's Verilog-A models."""

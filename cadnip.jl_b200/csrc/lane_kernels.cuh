@@ -334,7 +334,7 @@ __device__ __forceinline__ double d_junction_cap(double V, double Cj0, double Vj
 #include CB200_VA_HEADER
 #else
 template <int PASS, typename PG, typename W>
-__device__ __forceinline__ void va_dispatch(const PG &, W &, int, int, double) {}
+__device__ __forceinline__ void va_dispatch(const PG &, W &, int, int, double, int, bool) {}
 #endif
 
 // ---------------------------------------------------------------------------
@@ -509,7 +509,7 @@ __device__ __forceinline__ void eval_device(const PG &pg, W &w, int d, double t,
         }
     } break;
     case CB200_DEV_VA:                               // emitted Verilog-A module, flags = model index
-        va_dispatch<PASS>(pg, w, d, flags, t);
+        va_dispatch<PASS>(pg, w, d, flags, t, mode, initjct);
         break;
     default: break;
     }

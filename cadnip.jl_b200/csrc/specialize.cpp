@@ -174,7 +174,8 @@ std::string generate_spec_source(const SpecInput &in)
     const Program &p = *in.prog;
     std::ostringstream o;
     o << "// generated by cadnip-b200 (specialize.cpp) -- circuit-specialised kernels; do not edit\n";
-    if (!in.va_header_path.empty()) o << "#define CB200_VA_HEADER \"" << in.va_header_path << "\"\n";
+    if (!in.va_header_path.empty())
+        o << "#define CB200_VA_FN __forceinline__\n#define CB200_VA_HEADER \"" << in.va_header_path << "\"\n";
     o << "#include \"lane_kernels.cuh\"\n";
     o << "namespace {\nusing namespace cb200;\n";
     o << "struct SProg {\n";

@@ -18,6 +18,7 @@ import numpy as np
 
 from .circuit import MNACircuit, MNASpec, Params
 from .mna import (MNAContext, ZERO_VECTOR, CurrentIndex, DeviceRow)
+from . import verilog_a as _va
 
 
 class StructuralSweepError(ValueError):
@@ -58,6 +59,8 @@ class LoweredCircuit:
     breakpoints: List[Any]
     va_models: List[Any] = field(default_factory=list)   # VAModel per DEV_VA flags value
     n_user_nodes: int = -1          # nodes allocated by get_node! (the rest are internal nodes)
+    va_cuda_header: str = ""        # emitted CUDA for the circuit's Verilog-A modules (cb200_load_va_models)
+    va_c_source: str = ""           # the same modules as plain C: input of the CPU oracle, never run by the product
 
     @property
     def n(self) -> int:
@@ -141,13 +144,29 @@ class _ParamPool:
         return ~i
 
 
-def run_builder(builder, params: Params, spec: MNASpec) -> MNAContext:
-    """One discovery pass: ``builder(params, spec, 0.0; x=ZERO_VECTOR)``
-    (solve.jl:1793-1822 pass 1).  The reference's passes 2-5 only refine
-    voltage-dependent-charge detection for Verilog-A devices (contrib.jl:214-257);
-    the primitive devices' structure is independent of x."""
+_N_DETECTION_PASSES = 5
+
+
+def _probe_stream():
+    """The detection probes x in [-1, 1]: the reference draws them from
+    ``MersenneTwister(0xDEADBEEF)`` (solve.jl:999, :1799), a stream that is not reproducible
+    outside Julia; this xorshift64* restates the oracle's so both sides probe the same points."""
+    s = 0xDEADBEEF
+    mask = (1 << 64) - 1
+    while True:
+        s ^= s >> 12
+        s ^= (s << 25) & mask
+        s ^= s >> 27
+        r = (s * 2685821657736338717) & mask
+        yield ((r >> 11) / 9007199254740992.0 - 0.5) * 2.0
+
+
+def _call_builder(builder, params, spec, x, ctx):
+    from . import mna as _mna
+    _mna._SPEC_STACK.append(spec)
+    _mna._X_STACK.append(x)
     try:
-        ctx = builder(params, spec, 0.0, x=ZERO_VECTOR, ctx=None)
+        out = builder(params, spec, 0.0, x=x, ctx=ctx)
     except StructuralSweepError:
         raise
     except ValueError as e:
@@ -156,8 +175,34 @@ def run_builder(builder, params: Params, spec: MNASpec) -> MNAContext:
                 "builder branches on a swept parameter: a CircuitSweep must not cross a "
                 "structural boundary (run such points as separate sweeps)") from e
         raise
-    if not isinstance(ctx, MNAContext):
+    finally:
+        _mna._SPEC_STACK.pop()
+        _mna._X_STACK.pop()
+    if not isinstance(out, MNAContext):
         raise TypeError("builder must return the MNAContext it stamped into")
+    return out
+
+
+def run_builder(builder, params: Params, spec: MNASpec) -> MNAContext:
+    """``build_with_detection`` (solve.jl:1793-1822): pass 1 runs the builder at
+    ``x = ZERO_VECTOR``; passes 2-5 re-stamp the SAME context at random operating points so
+    that Verilog-A devices can compare their branch charges across passes
+    (``detect_or_cached!``, contrib.jl:214-257) and settle ``charge_is_vdep``.  The system may
+    grow between passes (charge states appear), so each probe is sized to the previous pass.
+    Circuits without reactive Verilog-A branches need only pass 1: the primitive devices'
+    structure is independent of x."""
+    ctx = _call_builder(builder, params, spec, ZERO_VECTOR, None)
+    if not ctx.charge_Q_values:
+        return ctx
+    probes = _probe_stream()
+    for _ in range(2, _N_DETECTION_PASSES + 1):
+        known = ctx.system_size()
+        x = np.fromiter((next(probes) for _ in range(known)), dtype=np.float64, count=known)
+        ctx.reset_for_restamping()
+        out = _call_builder(builder, params, spec, x, ctx)
+        if out is not ctx:
+            raise TypeError("builder must stamp into the context it is given (ctx=...) when re-run "
+                            "for charge detection")
     return ctx
 
 
@@ -206,7 +251,9 @@ def lower(builder, params: Params, spec: MNASpec, P: int = 1) -> LoweredCircuit:
         limit_init_ref=np.asarray(limit_init_ref, dtype=np.int32),
         lane_soa=np.ascontiguousarray(soa, dtype=np.float64), P=P,
         dev_names=names, dev_user_nodes=user_nodes, breakpoints=list(ctx.breakpoints),
-        va_models=va_models, n_user_nodes=_user_node_count(ctx))
+        va_models=va_models, n_user_nodes=_user_node_count(ctx),
+        va_cuda_header=_va.cuda_header(va_models) if va_models else "",
+        va_c_source=_va.c_source(va_models) if va_models else "")
 
 
 def _user_node_count(ctx: MNAContext) -> int:

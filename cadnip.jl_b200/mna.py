@@ -114,6 +114,31 @@ class MNAContext:
         self.b_V: List[Any] = []
         self.devices: List[DeviceRow] = []
         self.breakpoints: List[Any] = []
+        # voltage-dependent-charge detection cache (context.jl:338-341): survives restamping
+        if not hasattr(self, "charge_is_vdep"):
+            self.charge_is_vdep: List[bool] = []
+            self.charge_Q_values: List[float] = []
+            self.charge_V_values: List[float] = []
+        self.charge_detection_pos = 0
+
+    def detect_or_cached(self, V: float, Q: float) -> bool:
+        """``detect_or_cached!`` (src/mna/contrib.jl:214-257): positional, sticky."""
+        pos = self.charge_detection_pos
+        self.charge_detection_pos = pos + 1
+        if pos >= len(self.charge_Q_values):              # first run: assume linear
+            self.charge_is_vdep.append(False)
+            self.charge_Q_values.append(float(Q))
+            self.charge_V_values.append(float(V))
+            return False
+        Vs, Qs = self.charge_V_values[pos], self.charge_Q_values[pos]
+        if abs(V) > 1e-6 and abs(Vs) > 1e-6:
+            Cc, Cs = Q / V, Qs / Vs
+            diff, maxC = abs(Cc - Cs), max(abs(Cc), abs(Cs))
+            if diff > 1e-15 and (maxC < 1e-30 or diff / maxC > 1e-6):
+                self.charge_is_vdep[pos] = True
+        self.charge_Q_values[pos] = float(Q)
+        self.charge_V_values[pos] = float(V)
+        return self.charge_is_vdep[pos]
 
     # -- sizes ------------------------------------------------------------- #
     def system_size(self) -> int:
@@ -577,13 +602,25 @@ def stamp(dev, ctx: MNAContext, *ports, t=0.0, mode="tran", x=ZERO_VECTOR):
         m = dev.model
         if len(pr) != len(m.ports):
             raise TypeError(f"{m.name} has {len(m.ports)} ports, got {len(pr)}")
+        spec, xvec = current_spec(), current_x()
+        collapsed = dev.collapsed(spec)                # V(int, ext) <+ 0 aliasing, vasim.jl:3532-3564
         loc: List[Index] = list(pr)
         for node in m.internal:                        # alloc_internal_node! in declaration order
-            loc.append(ctx.alloc_internal_node(f"{m.name}_{node}", dev.name))
+            if node in collapsed:
+                loc.append(pr[m.ports.index(collapsed[node])])
+            else:
+                loc.append(ctx.alloc_internal_node(f"{m.name}_{node}", dev.name))
+        var = m.variant(dev.given, dev.detect_vdep(spec, ctx, xvec, [int(x) for x in loc]))
         S = STATE_DEPENDENT
-        for item in m.stamp_plan():
-            if item[0] == "Q":                         # alloc_charge!(ctx, name, instance, p, n)
-                _, pi, ni, qname = item
+        for item in var.stamp_plan():
+            if item[0] == "L":                         # alloc_limit!(ctx, name, instance, p, n; init=0.0)
+                _, slot, pi, ni, lname = item
+                assert slot == len(loc)
+                loc.append(ctx.alloc_limit(f"{m.name}_{lname}", dev.name, loc[pi],
+                                           0 if ni is None else loc[ni], init=0.0))
+            elif item[0] == "Q":                       # alloc_charge!(ctx, name, instance, p, n)
+                _, slot, pi, ni, qname = item
+                assert slot == len(loc)
                 loc.append(ctx.alloc_charge(f"{dev.name}_{m.name}_{qname}", loc[pi], 0 if ni is None else loc[ni]))
             elif item[0] == "G":
                 ctx.stamp_G(loc[item[1]], loc[item[2]], S)
@@ -591,10 +628,29 @@ def stamp(dev, ctx: MNAContext, *ports, t=0.0, mode="tran", x=ZERO_VECTOR):
                 ctx.stamp_C(loc[item[1]], loc[item[2]], S)
             else:
                 ctx.stamp_b(loc[item[1]], S)
-        ctx._record(DEV_VA, 0, dev.name, list(pr), loc, dev.params, base)
-        ctx.devices[-1].model = m
+        params = list(dev.params) + [dev.mfactor] + dev.extra_values(var, spec)
+        ctx._record(DEV_VA, 0, dev.name, list(pr), loc, params, base)
+        ctx.devices[-1].model = var
         return None
     raise TypeError(f"no stamp method for device of type {type(dev).__name__}")
+
+
+_SPEC_STACK: List[Any] = []
+_X_STACK: List[Any] = []
+
+
+def current_x():
+    """The operating point ``x`` of the builder call in progress (``_mna_x_``)."""
+    return _X_STACK[-1] if _X_STACK else ZERO_VECTOR
+
+
+def current_spec():
+    """The MNASpec of the builder call in progress (the reference passes it to every
+    generated stamp! as ``_mna_spec_``); defaults when stamping outside a builder."""
+    if _SPEC_STACK:
+        return _SPEC_STACK[-1]
+    from .circuit import MNASpec
+    return MNASpec()
 
 
 def _recip(r):

@@ -1,32 +1,38 @@
-"""Verilog-A device-model emitter (tier 0).
+"""Verilog-A device-model emitter.
 
 north_star: "a new emitter lowers each device model's stamp function ... to
-hand-written-style sm_100a CUDA C".  This module reads a Verilog-A module (the subset
-the reference's inline test models use: parameters, internal nodes, real locals,
-assignments, if/else, ``I(a,b) <+ expr`` contributions with ``ddt``), and emits the
-module's ``stamp!`` method as straight-line C with ANALYTIC partial derivatives
-(forward-mode differentiation at emit time; no dual numbers at run time) -- once as a
-CUDA device function for ``lane_kernels.cuh`` and once as plain C for the CPU oracle,
-from the same IR so both share one arithmetic order.
+hand-written-style sm_100a CUDA C".  This module reads a Verilog-A module -- the inline
+test models of the reference AND the VADistiller SPICE models under
+``models/VADistillerModels.jl/va`` (sp_diode, sp_mos1, ...) -- and emits the module's
+``stamp!`` method as straight-line C with ANALYTIC partial derivatives (forward-mode
+differentiation at emit time, structurally-zero partials never materialised; no dual
+numbers at run time): once as a CUDA device function for ``lane_kernels.cuh`` and once
+as plain C for the CPU oracle, from the same IR so both share one arithmetic order.
 
 The stamping protocol restates ``generate_mna_stamp_method_nterm``
 (src/vasim.jl:2993-3985):
-  * internal nodes are allocated in declaration order (``alloc_internal_node!``);
+  * internal nodes are allocated in declaration order, or aliased to a port when the
+    model's ``if (cond) V(int, ext) <+ 0;`` condition holds (vasim.jl:2723-2825, :3532-3564);
+  * ``$limit`` (PCNR): one limit unknown per unique probe branch with the tracking row
+    ``G[l,l]=1, G[l,p]=-1, G[l,n]=+1`` (vasim.jl:3109-3146); each call site evaluates the
+    model's limiter, records ``w`` and returns a pass-through dual anchored at ``w``
+    with a private partial slot (vasim.jl:1257-1334);
   * per current branch, in order of first contribution: ``G[p,k] += dI/dV_k``,
-    ``G[n,k] -= dI/dV_k`` for EVERY node k of the module (ports then internals),
-    each guarded by node != 0 (vasim.jl:3382-3392);
-  * a branch with a ``ddt`` term is reactive BY TYPE (vasim.jl:3307-3308): constant
-    capacitance -> plain C stamps (vasim.jl:3474-3485); voltage-dependent charge ->
-    charge-state formulation with ``CHARGE_SCALE = 1e12`` (vasim.jl:3433-3472,
-    src/mna/contrib.jl:39): the reference decides by probing Q/V numerically
-    (contrib.jl:214-257), here the same outcome is derived statically from whether the
-    charge's partials depend on a node voltage;
-  * ``Ieq = I0 - sum_k dI/dV_k V_k``; ``b[p] -= Ieq``, ``b[n] += Ieq`` (vasim.jl:3490-3518).
-``ddt`` follows the s-dual algebra of src/mna/contrib.jl:356-375: ``c * ddt(q)`` has
-charge ``c*q`` with the full product rule on the partials.
+    ``G[n,k] -= dI/dV_k`` for EVERY node k of the module (vasim.jl:3382-3392);
+  * a branch with a ``ddt`` term is reactive BY TYPE (vasim.jl:3307-3308): plain C stamps
+    when its charge is proportional to the branch voltage, else the charge-state
+    formulation with ``CHARGE_SCALE = 1e12`` (vasim.jl:3433-3485, contrib.jl:39).  The
+    reference decides per instance by probing Q/V numerically over the detection passes
+    (contrib.jl:214-257); here the same probe is run on the host by a small interpreter
+    of the module (``_Interp``) and the outcome selects the emitted variant;
+  * ``Ieq = I0 - sum_k dI/dV_k V_k + sum_j dI/dw_j (V_probe,j - w_j)``; ``b[p] -= Ieq``,
+    ``b[n] += Ieq`` (vasim.jl:3490-3518).
+``ddt`` follows the s-dual algebra of src/mna/contrib.jl:356-375 and is carried through
+variables.  ``$param_given`` is folded at emit time: one emitted variant per set of given
+parameters.  ``$temperature`` / ``$simparam`` are bound per instance from the MNASpec.
 
-Not supported in this tier (rejected loudly): ``$limit``, voltage contributions,
-node collapse, analog functions, ``$vt`` / ``$temperature``, noise, strings.
+Not supported (rejected loudly): named branches and general voltage contributions
+(``V(br) <+``, inductor.va), ``idt``/``laplace``, ``ddx``, strings parameters.
 """
 from __future__ import annotations
 
@@ -35,6 +41,8 @@ import math
 import re
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
 
 CHARGE_SCALE = 1e12          # src/mna/contrib.jl:39
 
@@ -47,15 +55,44 @@ class VAError(ValueError):
 # lexer
 # --------------------------------------------------------------------------- #
 _TOKEN = re.compile(r"""
-    (?P<ws>\s+|//[^\n]*|/\*.*?\*/) |
-    (?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?[TGMKkmunpfa]?) |
+    (?P<ws>\s+|//[^\n]*|/\*.*?\*/|\(\*.*?\*\)|`include[^\n]*) |
+    (?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?[TGMKkmunpfa]?(?![A-Za-z_0-9])) |
     (?P<id>[$A-Za-z_`][A-Za-z0-9_$]*) |
-    (?P<str>"[^"]*") |
-    (?P<op><\+|\*\*|<=|>=|==|!=|&&|\|\||[-+*/%<>=!?:;,()\[\]{}@^~&|#.])
+    (?P<str>"(?:[^"\\]|\\.)*") |
+    (?P<op><\+|\*\*|<=|>=|==|!=|&&|\|\||<<|>>|[-+*/%<>=!?:;,()\[\]{}@^~&|#.'])
 """, re.X | re.S)
 
 _SCALE = {"T": 1e12, "G": 1e9, "M": 1e6, "K": 1e3, "k": 1e3, "m": 1e-3, "u": 1e-6, "n": 1e-9,
           "p": 1e-12, "f": 1e-15, "a": 1e-18}
+
+
+def _preprocess(src: str) -> str:
+    """`ifdef/`ifndef/`else/`endif with nothing defined (the reference defines no macros
+    for these models); object-like `define NAME value."""
+    out, stack, defs = [], [], {}
+    for line in src.split("\n"):
+        s = line.strip()
+        if s.startswith("`ifdef"):
+            stack.append(s.split()[1] in defs); continue
+        if s.startswith("`ifndef"):
+            stack.append(s.split()[1] not in defs); continue
+        if s.startswith("`else"):
+            stack[-1] = not stack[-1]; continue
+        if s.startswith("`endif"):
+            stack.pop(); continue
+        if not all(stack):
+            continue
+        if s.startswith("`define"):
+            parts = s.split(None, 2)
+            if "(" in parts[1]:
+                raise VAError("Verilog-A: function-like `define macros are not supported")
+            defs[parts[1]] = parts[2] if len(parts) > 2 else ""
+            continue
+        out.append(line)
+    text = "\n".join(out)
+    for k, v in defs.items():
+        text = re.sub(r"`" + re.escape(k) + r"\b", v, text)
+    return text
 
 
 def _lex(src: str) -> List[Tuple[str, str]]:
@@ -83,7 +120,7 @@ def _number(tok: str) -> float:
 # --------------------------------------------------------------------------- #
 class _Parser:
     def __init__(self, src: str):
-        self.t = _lex(src)
+        self.t = _lex(_preprocess(src))
         self.i = 0
 
     def peek(self):
@@ -95,7 +132,7 @@ class _Parser:
         return tok
 
     def accept(self, val):
-        if self.t[self.i][1] == val:
+        if self.t[self.i][1] == val and self.t[self.i][0] != "str":
             self.i += 1
             return True
         return False
@@ -110,8 +147,18 @@ class _Parser:
             raise VAError(f"Verilog-A: expected identifier, got {v!r}")
         return v
 
+    def _skip_to_semicolon(self):
+        while not self.accept(";"):
+            if self.peek()[0] == "eof":
+                raise VAError("Verilog-A: unexpected end of file")
+            self.next()
+
     # module ------------------------------------------------------------- #
     def module(self):
+        while self.peek()[1] != "module":
+            if self.peek()[0] == "eof":
+                raise VAError("Verilog-A: no module found")
+            self.next()
         self.expect("module")
         name = self.ident()
         ports = []
@@ -120,56 +167,101 @@ class _Parser:
                 ports.append(self.ident())
                 self.accept(",")
         self.expect(";")
-        params, electrical, reals, body = [], [], [], None
+        m = dict(name=name, ports=ports, params=[], ptypes={}, aliases={}, electrical=[], vars=[],
+                 vtypes={}, vinit={}, functions={}, body=None)
         while not self.accept("endmodule"):
             k, v = self.peek()
-            if v == "parameter":
+            if v in ("parameter", "localparam"):
                 self.next()
-                if self.peek()[1] in ("real", "integer"):
-                    self.next()
+                typ = "real"
+                if self.peek()[1] in ("real", "integer", "string"):
+                    typ = self.next()[1]
+                if typ == "string":
+                    raise VAError("Verilog-A: string parameters are not supported")
                 pname = self.ident()
                 self.expect("=")
                 default = self.expr()
-                while not self.accept(";"):          # skip `from [..]` / `exclude` ranges
-                    self.next()
-                params.append((pname, default))
+                self._skip_to_semicolon()                 # `from [..]` / `exclude` ranges
+                m["params"].append((pname, default))
+                m["ptypes"][pname] = typ
+            elif v == "aliasparam":
+                self.next()
+                alias = self.ident()
+                self.expect("=")
+                m["aliases"][alias] = self.ident()
+                self.expect(";")
             elif v in ("inout", "input", "output"):
                 self.next()
-                while not self.accept(";"):
-                    self.next()
+                self._skip_to_semicolon()
             elif v == "electrical":
                 self.next()
                 while True:
-                    electrical.append(self.ident())
+                    m["electrical"].append(self.ident())
                     if self.accept(";"):
                         break
                     self.expect(",")
             elif v in ("real", "integer"):
-                self.next()
-                while True:
-                    reals.append(self.ident())
-                    if self.accept("="):
-                        raise VAError("Verilog-A: variable initialisers are not supported")
-                    if self.accept(";"):
-                        break
-                    self.expect(",")
+                self._var_decl(m["vars"], m["vtypes"], m["vinit"])
             elif v == "analog":
                 self.next()
                 if self.peek()[1] == "function":
-                    raise VAError("Verilog-A: analog functions are not supported in this tier")
-                body = self.stmt()
-            elif v in ("branch", "ground", "string", "genvar", "aliasparam", "localparam"):
-                raise VAError(f"Verilog-A: `{v}` is not supported in this tier")
+                    f = self.function()
+                    m["functions"][f["name"]] = f
+                else:
+                    if m["body"] is not None:
+                        raise VAError("Verilog-A: more than one analog block")
+                    m["body"] = self.stmt(m)
+            elif v in ("branch", "ground", "string", "genvar"):
+                raise VAError(f"Verilog-A: `{v}` declarations are not supported")
             elif k == "eof":
                 raise VAError("Verilog-A: missing endmodule")
             else:
                 raise VAError(f"Verilog-A: unexpected {v!r} in module body")
-        if body is None:
+        if m["body"] is None:
             raise VAError("Verilog-A: module has no analog block")
-        return dict(name=name, ports=ports, params=params, electrical=electrical, reals=reals, body=body)
+        return m
+
+    def _var_decl(self, names, types, inits):
+        typ = self.next()[1]
+        while True:
+            name = self.ident()
+            names.append(name)
+            types[name] = typ
+            if self.accept("="):
+                inits[name] = self.expr()
+            if self.accept(";"):
+                break
+            self.expect(",")
+
+    def function(self):
+        self.expect("function")
+        rtype = "real"
+        if self.peek()[1] in ("real", "integer"):
+            rtype = self.next()[1]
+        name = self.ident()
+        self.expect(";")
+        f = dict(name=name, rtype=rtype, args=[], dirs={}, vars=[], vtypes={}, vinit={}, body=None)
+        while True:
+            v = self.peek()[1]
+            if v in ("input", "output", "inout"):
+                self.next()
+                while True:
+                    a = self.ident()
+                    f["args"].append(a)
+                    f["dirs"][a] = v
+                    if self.accept(";"):
+                        break
+                    self.expect(",")
+            elif v in ("real", "integer"):
+                self._var_decl(f["vars"], f["vtypes"], f["vinit"])
+            else:
+                break
+        f["body"] = self.stmt(f)
+        self.expect("endfunction")
+        return f
 
     # statements ----------------------------------------------------------- #
-    def stmt(self):
+    def stmt(self, scope):
         k, v = self.peek()
         if v == "begin":
             self.next()
@@ -177,20 +269,58 @@ class _Parser:
                 self.ident()
             stmts = []
             while not self.accept("end"):
-                stmts.append(self.stmt())
+                if self.peek()[1] in ("real", "integer"):        # block-local declarations
+                    self._var_decl(scope["vars"], scope["vtypes"], scope["vinit"])
+                    continue
+                stmts.append(self.stmt(scope))
             return ("block", stmts)
         if v == "if":
             self.next()
             self.expect("(")
             cond = self.expr()
             self.expect(")")
-            then = self.stmt()
-            other = self.stmt() if self.accept("else") else ("block", [])
+            then = self.stmt(scope)
+            other = self.stmt(scope) if self.accept("else") else ("block", [])
             return ("if", cond, then, other)
+        if v == "for":
+            self.next()
+            self.expect("(")
+            init = self._assign_nosemi()
+            self.expect(";")
+            cond = self.expr()
+            self.expect(";")
+            step = self._assign_nosemi()
+            self.expect(")")
+            return ("for", init, cond, step, self.stmt(scope))
+        if v == "while":
+            self.next()
+            self.expect("(")
+            cond = self.expr()
+            self.expect(")")
+            return ("for", ("block", []), cond, ("block", []), self.stmt(scope))
+        if v == "case":
+            self.next()
+            self.expect("(")
+            sel = self.expr()
+            self.expect(")")
+            arms, default = [], ("block", [])
+            while not self.accept("endcase"):
+                if self.accept("default"):
+                    self.accept(":")
+                    default = self.stmt(scope)
+                    continue
+                vals = [self.expr()]
+                while self.accept(","):
+                    vals.append(self.expr())
+                self.expect(":")
+                arms.append((vals, self.stmt(scope)))
+            return ("case", sel, arms, default)
         if v == ";":
             self.next()
             return ("block", [])
-        if v in ("I", "V") and self.t[self.i + 1][1] == "(":
+        if v == "@":
+            raise VAError("Verilog-A: event control @(...) is not supported")
+        if v in ("I", "V") and self.t[self.i + 1][1] == "(" and self._is_contribution():
             kind = self.next()[1]
             self.expect("(")
             a = self.ident()
@@ -199,24 +329,40 @@ class _Parser:
             self.expect("<+")
             e = self.expr()
             self.expect(";")
-            if kind == "V":
-                raise VAError("Verilog-A: voltage contributions V(..) <+ are not supported in this tier")
-            return ("contrib", a, b, e)
+            return ("vcontrib" if kind == "V" else "contrib", a, b, e)
         if k == "id" and v.startswith("$"):
             # system tasks ($strobe, $warning, ...) are no-ops on this path (vasim.jl:1181-1256)
             self.next()
             if self.accept("("):
                 depth = 1
                 while depth:
-                    t = self.next()[1]
-                    depth += (t == "(") - (t == ")")
+                    kk, t = self.next()
+                    if kk != "str":
+                        depth += (t == "(") - (t == ")")
             self.expect(";")
             return ("block", [])
+        if k == "id" and self.t[self.i + 1][1] == "(":          # function call used as a statement
+            e = self.primary()
+            self.expect(";")
+            return ("callstmt", e)
+        s = self._assign_nosemi()
+        self.expect(";")
+        return s
+
+    def _is_contribution(self):
+        j, depth = self.i + 1, 0
+        while True:
+            t = self.t[j][1]
+            depth += (t == "(") - (t == ")")
+            j += 1
+            if depth == 0:
+                break
+        return self.t[j][1] == "<+"
+
+    def _assign_nosemi(self):
         name = self.ident()
         self.expect("=")
-        e = self.expr()
-        self.expect(";")
-        return ("assign", name, e)
+        return ("assign", name, self.expr())
 
     # expressions ---------------------------------------------------------- #
     def expr(self):
@@ -230,7 +376,7 @@ class _Parser:
 
     def _binary(self, sub, ops):
         left = sub()
-        while self.peek()[1] in ops:
+        while self.peek()[1] in ops and self.peek()[0] == "op":
             op = self.next()[1]
             left = ("bin", op, left, sub())
         return left
@@ -239,10 +385,13 @@ class _Parser:
         return self._binary(self.land, ("||",))
 
     def land(self):
-        return self._binary(self.cmp, ("&&",))
+        return self._binary(self.eq, ("&&",))
+
+    def eq(self):
+        return self._binary(self.cmp, ("==", "!="))
 
     def cmp(self):
-        return self._binary(self.add, ("==", "!=", "<", "<=", ">", ">="))
+        return self._binary(self.add, ("<", "<=", ">", ">="))
 
     def add(self):
         return self._binary(self.mul, ("+", "-"))
@@ -269,26 +418,25 @@ class _Parser:
         k, v = self.next()
         if k == "num":
             return ("num", _number(v))
+        if k == "str":
+            return ("str", v[1:-1])
         if v == "(":
             e = self.expr()
             self.expect(")")
             return e
         if k == "id":
-            if self.peek()[1] == "(":
+            if self.peek()[1] == "(" and self.peek()[0] == "op":
                 self.next()
                 if v in ("V", "I"):
                     a = self.ident()
                     b = self.ident() if self.accept(",") else None
                     self.expect(")")
                     if v == "I":
-                        raise VAError("Verilog-A: current probes I(..) are not supported in this tier")
+                        raise VAError("Verilog-A: current probes I(..) are not supported")
                     return ("V", a, b)
                 args = []
                 while not self.accept(")"):
-                    if self.peek()[0] == "str":
-                        args.append(("str", self.next()[1].strip('"')))
-                    else:
-                        args.append(self.expr())
+                    args.append(self.expr())
                     self.accept(",")
                 return ("call", v, args)
             return ("var", v)
@@ -296,15 +444,413 @@ class _Parser:
 
 
 # --------------------------------------------------------------------------- #
+# shared: built-in function table
+# --------------------------------------------------------------------------- #
+_SYS_MATH = ("pow", "exp", "ln", "log", "sqrt", "abs", "sin", "cos", "tan", "tanh", "sinh", "cosh",
+             "atan", "atan2", "asin", "acos", "min", "max", "hypot", "floor", "ceil", "limexp")
+
+# MNASpec fields $simparam can read (vasim.jl:1189-1207); anything else -> the default
+_SPEC_FIELDS = ("temp", "gmin", "gshunt", "srcFact", "tnom", "abstol", "reltol", "vntol", "iabstol")
+
+
+def _va_round(x: float) -> float:
+    """real -> integer conversion rounds half away from zero (va_env.jl:110-120)."""
+    return float(math.floor(x + 0.5)) if x >= 0 else float(math.ceil(x - 0.5))
+
+
+# --------------------------------------------------------------------------- #
+# host interpreter: evaluates the module with plain floats.  Used at stamp time for the
+# node-collapse conditions and for the reference's numeric voltage-dependent-charge
+# detection (contrib.jl:214-257); never on the device path.
+# --------------------------------------------------------------------------- #
+class _Interp:
+    def __init__(self, mod, params: Dict[str, float], given: frozenset, sim: Dict[str, float],
+                 mode: str = "dcop", mfactor: float = 1.0):
+        self.mod, self.params, self.given, self.sim = mod, params, given, sim
+        self.mode, self.mfactor = mode, mfactor
+        self.V: Dict[str, float] = {}
+        self.vold: Dict[Tuple[str, Optional[str]], float] = {}
+        self.scopes: List[Dict[str, float]] = [{}]
+        self.types: List[Dict[str, str]] = [mod["vtypes"]]
+        self.I: Dict[Tuple[str, Optional[str]], float] = {}
+        self.Q: Dict[Tuple[str, Optional[str]], float] = {}
+        self.reactive: Dict[Tuple[str, Optional[str]], bool] = {}
+        self.depth = 0
+
+    def init_vars(self):
+        env = self.scopes[0]
+        for name in self.mod["vars"]:
+            env[name] = (0.0, 0.0)
+        for name in self.mod["vars"]:
+            if name in self.mod["vinit"]:
+                self._assign(name, self.ev(self.mod["vinit"][name]))
+
+    def run(self, V: Dict[str, float], vold=None):
+        self.V, self.vold = V, vold or {}
+        self.I, self.Q, self.reactive = {}, {}, {}
+        self.scopes = [{}]
+        self.init_vars()
+        self.stmt(self.mod["body"])
+        return self
+
+    # r, q pairs ----------------------------------------------------------- #
+    def _lookup(self, name):
+        for env in reversed(self.scopes):
+            if name in env:
+                return env[name]
+        return None
+
+    def _assign(self, name, val):
+        for env, types in zip(reversed(self.scopes), reversed(self.types)):
+            if name in env:
+                if types.get(name) == "integer":
+                    val = (_va_round(val[0]), 0.0)
+                env[name] = val
+                return
+        raise VAError(f"Verilog-A: assignment to undeclared variable {name!r}")
+
+    def ev(self, e) -> Tuple[float, float]:
+        k = e[0]
+        if k == "num":
+            return (e[1], 0.0)
+        if k == "str":
+            return (0.0, 0.0)
+        if k == "var":
+            name = e[1]
+            v = self._lookup(name)
+            if v is not None:
+                return v
+            if len(self.scopes) == 1 or True:
+                if name in self.params:
+                    return (float(self.params[name]), 0.0)
+            if name == "$mfactor":
+                return (self.mfactor, 0.0)
+            if name == "$temperature":
+                return (self.sim["temp"] + 273.15, 0.0)
+            if name == "$vt":
+                return ((self.sim["temp"] + 273.15) * 8.617333262e-5, 0.0)
+            if name == "$abstime":
+                return (0.0, 0.0)
+            raise VAError(f"Verilog-A: unknown identifier {name!r}")
+        if k == "V":
+            a = self.V[e[1]]
+            b = self.V[e[2]] if e[2] is not None else 0.0
+            return (a - b, 0.0)
+        if k == "neg":
+            r, q = self.ev(e[1])
+            return (-r, -q)
+        if k == "not":
+            return (1.0 if self.ev(e[1])[0] == 0.0 else 0.0, 0.0)
+        if k == "?":
+            return self.ev(e[2]) if self.ev(e[1])[0] != 0.0 else self.ev(e[3])
+        if k == "bin":
+            op = e[1]
+            if op == "&&":
+                return (1.0 if (self.ev(e[2])[0] != 0.0 and self.ev(e[3])[0] != 0.0) else 0.0, 0.0)
+            if op == "||":
+                return (1.0 if (self.ev(e[2])[0] != 0.0 or self.ev(e[3])[0] != 0.0) else 0.0, 0.0)
+            (a, aq), (b, bq) = self.ev(e[2]), self.ev(e[3])
+            with np.errstate(all="ignore"):
+                if op == "+":
+                    return (a + b, aq + bq)
+                if op == "-":
+                    return (a - b, aq - bq)
+                if op == "*":
+                    return (a * b, aq * b + a * bq)
+                if op == "/":
+                    return (float(np.float64(a) / np.float64(b)), float(np.float64(aq) / np.float64(b)))
+                if op == "%":
+                    return (math.fmod(a, b), 0.0)
+            return (1.0 if {"==": a == b, "!=": a != b, "<": a < b, "<=": a <= b,
+                            ">": a > b, ">=": a >= b}[op] else 0.0, 0.0)
+        if k == "call":
+            return self.call(e[1], e[2])
+        raise VAError(f"Verilog-A: cannot evaluate {k!r}")
+
+    def call(self, fn, args):
+        if fn == "ddt":
+            return (0.0, self.ev(args[0])[0])
+        if fn in ("white_noise", "flicker_noise"):
+            return (0.0, 0.0)
+        if fn == "$param_given":
+            return (1.0 if args[0][1] in self.given else 0.0, 0.0)
+        if fn == "$simparam":
+            name = args[0][1]
+            if name == "iniLim":
+                return (0.0, 0.0)
+            if name in self.sim:
+                return (float(self.sim[name]), 0.0)
+            if len(args) > 1:
+                return self.ev(args[1])
+            raise VAError(f"Verilog-A: unknown simparam {name!r}")
+        if fn == "analysis":
+            what = args[0][1]
+            return (1.0 if ((what in ("dc", "static") and self.mode == "dcop") or
+                            (what in ("tran", "transient") and self.mode == "tran") or
+                            (what == "ac" and self.mode == "ac")) else 0.0, 0.0)
+        if fn in ("$temperature", "$vt", "$mfactor", "$abstime"):
+            return self.ev(("var", fn))
+        if fn == "$limit":
+            probe = args[0]
+            key = (probe[1], probe[2])
+            vnew = self.ev(probe)[0]
+            vold = self.vold.get(key, 0.0)
+            f = self.mod["functions"][args[1][1]]
+            return (self.user_call(f, [(vnew, 0.0), (vold, 0.0)] + [self.ev(a) for a in args[2:]],
+                                   [None, None] + list(args[2:])), 0.0)
+        if fn in self.mod["functions"]:
+            f = self.mod["functions"][fn]
+            return (self.user_call(f, [self.ev(a) for a in args], list(args)), 0.0)
+        if fn.startswith("$") and fn[1:] in _SYS_MATH:
+            fn = fn[1:]
+        a = [self.ev(x)[0] for x in args]
+        with np.errstate(all="ignore"):
+            f64 = np.float64
+            if fn == "exp":
+                return (float(np.exp(f64(a[0]))), 0.0)
+            if fn == "limexp":
+                return (float(np.exp(f64(min(max(a[0], -80.0), 80.0)))), 0.0)
+            if fn == "ln":
+                return (float(np.log(f64(a[0]))), 0.0)
+            if fn == "log":
+                return (float(np.log10(f64(a[0]))), 0.0)
+            if fn == "sqrt":
+                return (float(np.sqrt(f64(a[0]))), 0.0)
+            if fn == "pow":
+                return (float(np.power(f64(a[0]), f64(a[1]))), 0.0)
+            if fn == "abs":
+                return (abs(a[0]), 0.0)
+            if fn in ("min", "max"):
+                return ((min if fn == "min" else max)(a[0], a[1]), 0.0)
+            if fn in ("sin", "cos", "tan", "tanh", "sinh", "cosh", "floor", "ceil"):
+                return (float(getattr(np, fn)(f64(a[0]))), 0.0)
+            if fn in ("atan", "asin", "acos"):
+                return (float(getattr(np, "arc" + fn[1:])(f64(a[0]))), 0.0)
+            if fn == "atan2":
+                return (float(np.arctan2(f64(a[0]), f64(a[1]))), 0.0)
+            if fn == "hypot":
+                return (float(np.hypot(f64(a[0]), f64(a[1]))), 0.0)
+        raise VAError(f"Verilog-A: function {fn!r} is not supported")
+
+    def user_call(self, f, vals, arg_exprs) -> float:
+        if self.depth > 16:
+            raise VAError("Verilog-A: recursive analog functions are not supported")
+        env = {f["name"]: (0.0, 0.0)}
+        for a in f["args"] + f["vars"]:
+            env[a] = (0.0, 0.0)
+        types = dict(f["vtypes"])
+        types[f["name"]] = f["rtype"]
+        self.scopes.append(env)
+        self.types.append(types)
+        self.depth += 1
+        for a, v in zip(f["args"], vals):
+            if f["dirs"][a] in ("input", "inout"):
+                self._assign(a, (v[0], 0.0))
+        for name in f["vars"]:
+            if name in f["vinit"]:
+                self._assign(name, self.ev(f["vinit"][name]))
+        self.stmt(f["body"])
+        ret = env[f["name"]][0]
+        outs = [(ae, env[a]) for a, ae in zip(f["args"], arg_exprs)
+                if f["dirs"][a] in ("output", "inout") and ae is not None]
+        self.scopes.pop()
+        self.types.pop()
+        self.depth -= 1
+        for ae, v in outs:
+            if ae[0] != "var":
+                raise VAError("Verilog-A: output argument must be a variable")
+            self._assign(ae[1], v)
+        return ret
+
+    def stmt(self, s):
+        k = s[0]
+        if k == "block":
+            for x in s[1]:
+                self.stmt(x)
+        elif k == "assign":
+            self._assign(s[1], self.ev(s[2]))
+        elif k == "if":
+            self.stmt(s[2] if self.ev(s[1])[0] != 0.0 else s[3])
+        elif k == "for":
+            self.stmt(s[1])
+            n = 0
+            while self.ev(s[2])[0] != 0.0:
+                self.stmt(s[4])
+                self.stmt(s[3])
+                n += 1
+                if n > 100000:
+                    raise VAError("Verilog-A: loop does not terminate")
+        elif k == "case":
+            sel = self.ev(s[1])[0]
+            for vals, body in s[2]:
+                if any(self.ev(v)[0] == sel for v in vals):
+                    self.stmt(body)
+                    return
+            self.stmt(s[3])
+        elif k == "contrib":
+            key = (s[1], s[2])
+            r, q = self.ev(s[3])
+            self.I[key] = self.I.get(key, 0.0) + r
+            self.Q[key] = self.Q.get(key, 0.0) + q
+            if _has_ddt(s[3], self.mod):
+                self.reactive[key] = True
+        elif k == "vcontrib":
+            pass
+        elif k == "callstmt":
+            self.ev(s[1])
+        else:
+            raise VAError(f"Verilog-A: statement {k!r} not supported")
+
+
+def _has_ddt(e, mod, _memo=None) -> bool:
+    """Reactive BY TYPE: does a ddt() reach this expression (directly or through variables)?
+    Conservative: any variable that was ever assigned a ddt-carrying value counts."""
+    if _memo is None:
+        _memo = _ddt_vars(mod)
+    k = e[0]
+    if k == "call":
+        if e[1] == "ddt":
+            return True
+        if e[1] in ("white_noise", "flicker_noise"):
+            return False                              # plain 0.0 on the value path
+        return any(_has_ddt(a, mod, _memo) for a in e[2] if isinstance(a, tuple))
+    if k == "var":
+        return e[1] in _memo
+    if k in ("neg", "not"):
+        return _has_ddt(e[1], mod, _memo)
+    if k == "bin":
+        return _has_ddt(e[2], mod, _memo) or _has_ddt(e[3], mod, _memo)
+    if k == "?":
+        return _has_ddt(e[2], mod, _memo) or _has_ddt(e[3], mod, _memo)
+    return False
+
+
+def _ddt_vars(mod) -> set:
+    cached = mod.get("_ddt_vars")
+    if cached is not None:
+        return cached
+    out: set = set()
+    changed = True
+
+    def walk(s):
+        nonlocal changed
+        k = s[0]
+        if k == "block":
+            for x in s[1]:
+                walk(x)
+        elif k == "assign":
+            if s[1] not in out and _has_ddt(s[2], mod, out):
+                out.add(s[1])
+                changed = True
+        elif k == "if":
+            walk(s[2]); walk(s[3])
+        elif k == "for":
+            walk(s[1]); walk(s[4]); walk(s[3])
+        elif k == "case":
+            for _, b in s[2]:
+                walk(b)
+            walk(s[3])
+    while changed:
+        changed = False
+        walk(mod["body"])
+    mod["_ddt_vars"] = out
+    return out
+
+
+def _expr_vars(e, out: set, mod):
+    """Variables an expression's VALUE PATH reads (noise-source arguments contribute 0)."""
+    k = e[0]
+    if k == "var":
+        out.add(e[1])
+    elif k in ("neg", "not"):
+        _expr_vars(e[1], out, mod)
+    elif k == "bin":
+        _expr_vars(e[2], out, mod); _expr_vars(e[3], out, mod)
+    elif k == "?":
+        _expr_vars(e[1], out, mod); _expr_vars(e[2], out, mod); _expr_vars(e[3], out, mod)
+    elif k == "call":
+        if e[1] in ("white_noise", "flicker_noise", "$param_given"):
+            return
+        for a in e[2]:
+            if isinstance(a, tuple):
+                _expr_vars(a, out, mod)
+
+
+def _live_vars(mod) -> set:
+    """Module variables that can influence a contribution, a ``$limit`` site or control
+    flow (flow-insensitive).  Assignments to the others -- operating-point outputs and
+    noise-only intermediates -- are not emitted."""
+    cached = mod.get("_live")
+    if cached is not None:
+        return cached
+    live: set = set()
+    assigns: List[Tuple[str, Any]] = []
+    calls: List[Any] = []
+
+    def walk(s):
+        k = s[0]
+        if k == "block":
+            for x in s[1]:
+                walk(x)
+        elif k == "assign":
+            assigns.append((s[1], s[2]))
+        elif k == "if":
+            _expr_vars(s[1], live, mod); walk(s[2]); walk(s[3])
+        elif k == "for":
+            walk(s[1]); _expr_vars(s[2], live, mod); walk(s[3]); walk(s[4])
+        elif k == "case":
+            _expr_vars(s[1], live, mod)
+            for vals, b in s[2]:
+                for v in vals:
+                    _expr_vars(v, live, mod)
+                walk(b)
+            walk(s[3])
+        elif k in ("contrib", "vcontrib"):
+            _expr_vars(s[3], live, mod)
+        elif k == "callstmt":
+            calls.append(s[1])
+    walk(mod["body"])
+    # $limit sites are side effects wherever they appear
+    def has_limit(e) -> bool:
+        if not isinstance(e, tuple):
+            return False
+        if e[0] == "call" and e[1] == "$limit":
+            return True
+        return any(has_limit(x) if isinstance(x, tuple) else any(has_limit(y) for y in x if isinstance(y, tuple))
+                   for x in e[1:] if isinstance(x, (tuple, list)))
+    for name, rhs in assigns:
+        if has_limit(rhs):
+            live.add(name)
+    changed = True
+    while changed:
+        changed = False
+        for name, rhs in assigns:
+            if name in live:
+                before = len(live)
+                _expr_vars(rhs, live, mod)
+                changed |= len(live) != before
+        for c in calls:                       # f(a, b, out): live if an output variable is
+            outs = [a[1] for a in c[2] if isinstance(a, tuple) and a[0] == "var"]
+            if any(o in live for o in outs):
+                before = len(live)
+                _expr_vars(c, live, mod)
+                changed |= len(live) != before
+    mod["_live"] = live
+    return live
+
+
+# --------------------------------------------------------------------------- #
 # forward-mode differentiation at emit time
 # --------------------------------------------------------------------------- #
-@dataclass
 class _D:
-    """value + partials w.r.t. the module's node voltages; strings are C expressions,
-    ``None`` partial = structurally zero; ``const`` = Python float when known."""
-    v: str
-    d: List[Optional[str]]
-    const: Optional[float] = None
+    """value + SPARSE partials w.r.t. the module's node voltages (slots 0..N-1) and the
+    ``$limit`` site slots (N..N+S-1).  ``v`` and the partials are C expressions (names of
+    emitted temporaries); a missing slot is a structural zero; ``const`` is the Python
+    float when the value is known at emit time."""
+    __slots__ = ("v", "d", "const")
+
+    def __init__(self, v: str, d: Optional[Dict[int, str]] = None, const: Optional[float] = None):
+        self.v, self.d, self.const = v, (d or {}), const
 
     def is_const(self):
         return self.const is not None
@@ -316,24 +862,42 @@ def _lit(x: float) -> str:
     if x in (float("inf"), float("-inf")):
         return "(1.0/0.0)" if x > 0 else "(-1.0/0.0)"
     r = repr(float(x))
-    if "e" not in r and "." not in r:
+    if "e" not in r and "." not in r and "inf" not in r:
         r += ".0"
     return "(" + r + ")" if x < 0 else r
 
 
+_Pair = Tuple[_D, Optional[_D]]          # (resistive, reactive-or-None)
+
+
 class _Emitter:
-    def __init__(self, mod: dict, params: List[str], nodes: List[str]):
-        self.mod, self.params, self.nodes = mod, params, nodes
-        self.N = len(nodes)
+    """One pass over the analog block producing C lines.  Passes are repeated until the
+    per-variable activity sets (which partial / reactive components can be non-zero)
+    stop growing; the last pass is the emitted code."""
+
+    def __init__(self, mod: dict, given: frozenset, act: dict, bact: dict):
+        self.mod, self.given = mod, given
+        self.params = [p[0] for p in mod["params"]]
+        ports = list(mod["ports"])
+        self.nodes = ports + [n for n in mod["electrical"] if n not in ports]
+        self.N = len(self.nodes)
         self.lines: List[str] = []
         self.tmp = 0
         self.indent = 1
-        self.vars = set(mod["reals"])
-        self.assigned: set = set()
-        # branch accumulators, in order of first contribution
+        self.act, self.bact = act, bact
+        self.changed = False
+        self.live = _live_vars(mod)
+        self.qz: set = set()         # variables whose reactive part is known to be zero HERE
+        self.scopes: List[Dict[str, str]] = [{name: name for name in mod["vars"]}]
+        self.vtypes: Dict[str, str] = dict(mod["vtypes"])       # by C name
+        self.decl_order: List[str] = list(mod["vars"])
+        self.callno = 0
+        self.cond_depth = 0
         self.branches: List[Tuple[str, Optional[str]]] = []
-        self.reactive: Dict[int, bool] = {}
-        self.vdep: Dict[int, bool] = {}
+        self.lim_branches: List[Tuple[str, Optional[str]]] = []
+        self.sites: List[int] = []                                # site j -> limit branch index
+        self.extras: List[Tuple] = []                             # hidden per-instance parameters
+        self.collapse: Dict[str, Tuple[str, Any]] = {}            # internal node -> (port, condition AST)
 
     # -- helpers ------------------------------------------------------------ #
     def emit(self, s: str):
@@ -346,22 +910,15 @@ class _Emitter:
         return name
 
     def const(self, x: float) -> _D:
-        return _D(_lit(x), [None] * self.N, float(x))
+        return _D(_lit(x), {}, float(x))
 
     def zero(self):
         return self.const(0.0)
 
-    def _padd(self, a, b, sign="+"):
-        if a is None and b is None:
-            return None
-        if b is None:
-            return a
-        if a is None:
-            return b if sign == "+" else self.temp(f"-{b}")
-        return self.temp(f"{a} {sign} {b}")
-
-    def _pscale(self, p, s: str):
-        return None if p is None else self.temp(f"{p} * {s}")
+    def extra(self, key: Tuple) -> _D:
+        if key not in self.extras:
+            self.extras.append(key)
+        return _D(f"x_{self.extras.index(key)}")
 
     # -- arithmetic on duals -------------------------------------------------- #
     def add(self, a: _D, b: _D, sign="+") -> _D:
@@ -372,12 +929,21 @@ class _Emitter:
         if a.is_const() and a.const == 0.0 and sign == "+":
             return b
         v = self.temp(f"{a.v} {sign} {b.v}")
-        return _D(v, [self._padd(x, y, sign) for x, y in zip(a.d, b.d)])
+        d = {}
+        for k in sorted(set(a.d) | set(b.d)):
+            x, y = a.d.get(k), b.d.get(k)
+            if y is None:
+                d[k] = x
+            elif x is None:
+                d[k] = y if sign == "+" else self.temp(f"-{y}")
+            else:
+                d[k] = self.temp(f"{x} {sign} {y}")
+        return _D(v, d)
 
     def neg(self, a: _D) -> _D:
         if a.is_const():
             return self.const(-a.const)
-        return _D(self.temp(f"-{a.v}"), [None if p is None else self.temp(f"-{p}") for p in a.d])
+        return _D(self.temp(f"-{a.v}"), {k: self.temp(f"-{p}") for k, p in a.d.items()})
 
     def mul(self, a: _D, b: _D) -> _D:
         if a.is_const() and b.is_const():
@@ -388,97 +954,135 @@ class _Emitter:
             if x.is_const() and x.const == 0.0:
                 return self.zero()
         v = self.temp(f"{a.v} * {b.v}")
-        d = []
-        for pa, pb in zip(a.d, b.d):
-            t1 = None if pa is None else f"{pa} * {b.v}"
-            t2 = None if pb is None else f"{a.v} * {pb}"
-            if t1 is None and t2 is None:
-                d.append(None)
-            elif t2 is None:
-                d.append(self.temp(t1))
-            elif t1 is None:
-                d.append(self.temp(t2))
+        d = {}
+        for k in sorted(set(a.d) | set(b.d)):
+            pa, pb = a.d.get(k), b.d.get(k)
+            if pb is None:
+                d[k] = self.temp(f"{pa} * {b.v}")
+            elif pa is None:
+                d[k] = self.temp(f"{a.v} * {pb}")
             else:
-                d.append(self.temp(f"{t1} + {t2}"))
+                d[k] = self.temp(f"{pa} * {b.v} + {a.v} * {pb}")
         return _D(v, d)
 
     def div(self, a: _D, b: _D) -> _D:
         if a.is_const() and b.is_const() and b.const != 0.0:
             return self.const(a.const / b.const)
         v = self.temp(f"{a.v} / {b.v}")
-        if all(p is None for p in b.d):
-            return _D(v, [None if p is None else self.temp(f"{p} / {b.v}") for p in a.d])
-        d = []
-        for pa, pb in zip(a.d, b.d):        # (a/b)' = (a' - (a/b) b') / b
-            if pa is None and pb is None:
-                d.append(None)
-            elif pb is None:
-                d.append(self.temp(f"{pa} / {b.v}"))
+        d = {}
+        for k in sorted(set(a.d) | set(b.d)):        # (a/b)' = (a' - (a/b) b') / b
+            pa, pb = a.d.get(k), b.d.get(k)
+            if pb is None:
+                d[k] = self.temp(f"{pa} / {b.v}")
             elif pa is None:
-                d.append(self.temp(f"-({v} * {pb}) / {b.v}"))
+                d[k] = self.temp(f"-({v} * {pb}) / {b.v}")
             else:
-                d.append(self.temp(f"({pa} - {v} * {pb}) / {b.v}"))
+                d[k] = self.temp(f"({pa} - {v} * {pb}) / {b.v}")
         return _D(v, d)
 
     def unary_fn(self, a: _D, val_expr: str, dfac_expr) -> _D:
         """f(a): value val_expr, derivative factor dfac_expr(valname) (a C expression)."""
         v = self.temp(val_expr)
-        if all(p is None for p in a.d):
-            return _D(v, [None] * self.N)
+        if not a.d:
+            return _D(v)
         fac = self.temp(dfac_expr(v))
-        return _D(v, [self._pscale(p, fac) for p in a.d])
+        return _D(v, {k: self.temp(f"{p} * {fac}") for k, p in a.d.items()})
 
     def select(self, c: str, a: _D, b: _D) -> _D:
         v = self.temp(f"({c}) ? {a.v} : {b.v}")
-        d = []
-        for pa, pb in zip(a.d, b.d):
-            if pa is None and pb is None:
-                d.append(None)
-            else:
-                d.append(self.temp(f"({c}) ? {pa or '0.0'} : {pb or '0.0'}"))
+        d = {}
+        for k in sorted(set(a.d) | set(b.d)):
+            d[k] = self.temp(f"({c}) ? {a.d.get(k, '0.0')} : {b.d.get(k, '0.0')}")
         return _D(v, d)
 
-    # -- expressions: returns (resistive, reactive-or-None) ------------------- #
-    def ev(self, e) -> Tuple[_D, Optional[_D]]:
+    def flag(self, cexpr: str) -> _D:
+        return _D(self.temp(f"({cexpr}) ? 1.0 : 0.0"))
+
+    # -- variables ------------------------------------------------------------ #
+    def _cname(self, name: str) -> Optional[str]:
+        for sc in reversed(self.scopes):
+            if name in sc:
+                return sc[name]
+        return None
+
+    def _act(self, cname: str) -> dict:
+        a = self.act.get(cname)
+        if a is None:
+            a = self.act[cname] = {"d": set(), "q": False, "qd": set()}
+        return a
+
+    def read_var(self, cname: str) -> _Pair:
+        a = self._act(cname)
+        r = _D(f"v_{cname}", {k: f"v_{cname}_d{k}" for k in sorted(a["d"])})
+        q = None
+        if a["q"] and cname not in self.qz:
+            q = _D(f"vq_{cname}", {k: f"vq_{cname}_d{k}" for k in sorted(a["qd"])})
+        return r, q
+
+    def assign_var(self, cname: str, val: _Pair):
+        r, q = val
+        a = self._act(cname)
+        if self.vtypes.get(cname) == "integer":
+            if r.is_const():
+                r = self.const(_va_round(r.const))
+            else:
+                r = _D(self.temp(f"VA_ROUND({r.v})"))
+            q = None
+        new_d = set(r.d) - a["d"]
+        if new_d:
+            a["d"] |= new_d
+            self.changed = True
+        if q is not None:
+            if not a["q"]:
+                a["q"] = True
+                self.changed = True
+            new_q = set(q.d) - a["qd"]
+            if new_q:
+                a["qd"] |= new_q
+                self.changed = True
+        if q is None:
+            self.qz.add(cname)
+        else:
+            self.qz.discard(cname)
+        self.emit(f"v_{cname} = {r.v};")
+        for k in sorted(a["d"]):
+            self.emit(f"v_{cname}_d{k} = {r.d.get(k, '0.0')};")
+        if a["q"]:
+            self.emit(f"vq_{cname} = {q.v if q is not None else '0.0'};")
+            for k in sorted(a["qd"]):
+                self.emit(f"vq_{cname}_d{k} = {q.d.get(k, '0.0') if q is not None else '0.0'};")
+
+    # -- expressions ---------------------------------------------------------- #
+    def ev(self, e) -> _Pair:
         kind = e[0]
         if kind == "num":
             return self.const(e[1]), None
+        if kind == "str":
+            raise VAError("Verilog-A: string in an arithmetic expression")
         if kind == "var":
             name = e[1]
+            cname = self._cname(name)
+            if cname is not None:
+                return self.read_var(cname)
             if name in self.params:
-                return _D(f"p_{name}", [None] * self.N), None
-            if name in self.vars:
-                if name not in self.assigned:
-                    return self.zero(), None           # VA reals start at 0
-                return _D(f"v_{name}", [f"v_{name}_d{k}" for k in range(self.N)]), None
-            if name in ("$mfactor",):
-                return self.const(1.0), None
-            if name == "$abstime":
-                return _D("t", [None] * self.N), None
+                return _D(f"p_{name}"), None
+            if name in ("$mfactor", "$temperature", "$vt", "$abstime"):
+                return self.call(name, [])
             raise VAError(f"Verilog-A: unknown identifier {name!r}")
         if kind == "V":
-            a, b = e[1], e[2]
-            d: List[Optional[str]] = [None] * self.N
-            ia = self._node(a)
-            if b is None:
-                d[ia] = "1.0"
-                return _D(f"V{ia}", d), None
-            ib = self._node(b)
-            if ia == ib:
-                return self.zero(), None
-            d[ia] = "1.0"
-            d[ib] = "(-1.0)"
-            return _D(self.temp(f"V{ia} - V{ib}"), d), None
+            return self.probe(e[1], e[2]), None
         if kind == "neg":
             r, q = self.ev(e[1])
             return self.neg(r), (None if q is None else self.neg(q))
         if kind == "not":
             r, q = self.ev(e[1])
-            self._no_react(q, "!")
-            return _D(self.temp(f"({r.v} == 0.0) ? 1.0 : 0.0"), [None] * self.N), None
+            if r.is_const():
+                return self.const(1.0 if r.const == 0.0 else 0.0), None
+            return self.flag(f"{r.v} == 0.0"), None
         if kind == "?":
             c, cq = self.ev(e[1])
-            self._no_react(cq, "?:")
+            if c.is_const():
+                return self.ev(e[2] if c.const != 0.0 else e[3])
             ar, aq = self.ev(e[2])
             br, bq = self.ev(e[3])
             cond = f"{c.v} != 0.0"
@@ -487,42 +1091,69 @@ class _Emitter:
                 q = self.select(cond, aq or self.zero(), bq or self.zero())
             return self.select(cond, ar, br), q
         if kind == "bin":
-            op = e[1]
-            ar, aq = self.ev(e[2])
-            br, bq = self.ev(e[3])
-            if op in ("+", "-"):
-                q = None
-                if aq is not None or bq is not None:
-                    q = self.add(aq or self.zero(), bq or self.zero(), op)
-                return self.add(ar, br, op), q
-            if op == "*":
-                if aq is not None and bq is not None:
-                    raise VAError("Verilog-A: product of two ddt() terms")
-                q = None
-                if aq is not None:
-                    q = self.mul(aq, br)
-                elif bq is not None:
-                    q = self.mul(ar, bq)
-                return self.mul(ar, br), q
-            if op == "/":
-                self._no_react(bq, "/")
-                q = None if aq is None else self.div(aq, br)
-                return self.div(ar, br), q
-            self._no_react(aq, op)
-            self._no_react(bq, op)
-            if op == "%":
-                return _D(self.temp(f"fmod({ar.v}, {br.v})"), list(ar.d)), None
-            cop = {"==": "==", "!=": "!=", "<": "<", "<=": "<=", ">": ">", ">=": ">="}.get(op)
-            if cop:
-                return _D(self.temp(f"({ar.v} {cop} {br.v}) ? 1.0 : 0.0"), [None] * self.N), None
-            if op == "&&":
-                return _D(self.temp(f"({ar.v} != 0.0 && {br.v} != 0.0) ? 1.0 : 0.0"), [None] * self.N), None
-            if op == "||":
-                return _D(self.temp(f"({ar.v} != 0.0 || {br.v} != 0.0) ? 1.0 : 0.0"), [None] * self.N), None
-            raise VAError(f"Verilog-A: operator {op!r} not supported")
+            return self.binary(e)
         if kind == "call":
             return self.call(e[1], e[2])
         raise VAError(f"Verilog-A: cannot lower {kind!r}")
+
+    def probe(self, a: str, b: Optional[str]) -> _D:
+        ia = self._node(a)
+        if b is None:
+            return _D(f"V{ia}", {ia: "1.0"})
+        ib = self._node(b)
+        if ia == ib:
+            return self.zero()
+        return _D(self.temp(f"V{ia} - V{ib}"), {ia: "1.0", ib: "(-1.0)"})
+
+    def binary(self, e) -> _Pair:
+        op = e[1]
+        ar, aq = self.ev(e[2])
+        if op in ("&&", "||") and ar.is_const():
+            self._no_react(aq, op)
+            short = (op == "&&" and ar.const == 0.0) or (op == "||" and ar.const != 0.0)
+            if short:
+                return self.const(0.0 if op == "&&" else 1.0), None
+            br, bq = self.ev(e[3])
+            self._no_react(bq, op)
+            if br.is_const():
+                return self.const(1.0 if br.const != 0.0 else 0.0), None
+            return self.flag(f"{br.v} != 0.0"), None
+        br, bq = self.ev(e[3])
+        if op in ("+", "-"):
+            q = None
+            if aq is not None or bq is not None:
+                q = self.add(aq or self.zero(), bq or self.zero(), op)
+            return self.add(ar, br, op), q
+        if op == "*":
+            if aq is not None and bq is not None:
+                raise VAError("Verilog-A: product of two ddt() terms")
+            q = None
+            if aq is not None:
+                q = self.mul(aq, br)
+            elif bq is not None:
+                q = self.mul(ar, bq)
+            return self.mul(ar, br), q
+        if op == "/":
+            self._no_react(bq, "/")
+            q = None if aq is None else self.div(aq, br)
+            return self.div(ar, br), q
+        # comparisons and logic look at the value only (ForwardDiff semantics)
+        if op == "%":
+            return _D(self.temp(f"fmod({ar.v}, {br.v})"), dict(ar.d)), None
+        if op in ("==", "!=", "<", "<=", ">", ">="):
+            if ar.is_const() and br.is_const():
+                a, b = ar.const, br.const
+                return self.const(1.0 if {"==": a == b, "!=": a != b, "<": a < b, "<=": a <= b,
+                                          ">": a > b, ">=": a >= b}[op] else 0.0), None
+            return self.flag(f"{ar.v} {op} {br.v}"), None
+        if op in ("&&", "||"):
+            if br.is_const():
+                bc = br.const != 0.0
+                if (op == "&&" and not bc) or (op == "||" and bc):
+                    return self.const(1.0 if op == "||" else 0.0), None
+                return self.flag(f"{ar.v} != 0.0"), None
+            return self.flag(f"{ar.v} != 0.0 {op} {br.v} != 0.0"), None
+        raise VAError(f"Verilog-A: operator {op!r} not supported")
 
     def _no_react(self, q, what):
         if q is not None:
@@ -534,86 +1165,198 @@ class _Emitter:
         except ValueError:
             raise VAError(f"Verilog-A: {name!r} is not a node of the module") from None
 
-    def call(self, fn: str, args) -> Tuple[_D, Optional[_D]]:
+    def call(self, fn: str, args) -> _Pair:
         if fn == "ddt":
             r, q = self.ev(args[0])
             self._no_react(q, "ddt")                 # second derivatives are out of scope
             return self.zero(), r                      # va_ddt: s-dual (contrib.jl:356-375)
         if fn in ("white_noise", "flicker_noise"):
-            return self.zero(), None                   # 0 on the value path (vasim.jl)
+            return self.zero(), None                   # 0 on the value path (vasim.jl:1336-1345)
+        if fn == "$param_given":
+            if len(args) != 1 or args[0][0] != "var":
+                raise VAError("Verilog-A: $param_given takes a parameter name")
+            return self.const(1.0 if args[0][1] in self.given else 0.0), None
+        if fn == "$mfactor":
+            return _D("va_mfactor"), None
+        if fn == "$temperature":                       # _mna_spec_.temp + 273.15 (vasim.jl:1181)
+            return self.extra(("temperature",)), None
+        if fn == "$vt":                                # (temp + 273.15) * 8.617333262e-5 (vasim.jl:1183)
+            return self.extra(("vt",)), None
+        if fn == "$abstime":
+            return _D("t"), None
         if fn == "$simparam":
+            if not args or args[0][0] != "str":
+                raise VAError("Verilog-A: $simparam needs a string name")
+            name = args[0][1]
+            if name == "iniLim":                       # Int(ctx.initjct) (vasim.jl:1197-1199)
+                return _D("va_initjct"), None
+            if name in _SPEC_FIELDS:
+                return self.extra(("simparam", name)), None
             if len(args) > 1:
-                r, _ = self.ev(args[1])
+                r, q = self.ev(args[1])
+                self._no_react(q, "$simparam")
                 return r, None
-            raise VAError("Verilog-A: $simparam without default is not supported")
-        if fn in ("$limit", "$vt", "$temperature", "$param_given", "analysis"):
-            raise VAError(f"Verilog-A: {fn} is not supported in this tier")
-        if fn.startswith("$") and fn[1:] in ("pow", "exp", "ln", "log", "sqrt", "abs", "sin", "cos", "tan",
-                                             "tanh", "sinh", "cosh", "atan", "min", "max", "hypot",
-                                             "floor", "ceil", "limexp"):
+            raise VAError(f"Verilog-A: unknown simparam {name!r}")
+        if fn == "analysis":                           # vasim.jl:1208-1240
+            what = args[0][1] if args and args[0][0] == "str" else None
+            code = {"dc": 0, "static": 0, "tran": 1, "transient": 1, "ac": 3}.get(what)
+            if code is None:
+                return self.const(0.0), None
+            return self.flag(f"va_mode == {code}"), None
+        if fn == "$limit":
+            return self.limit(args), None
+        if fn in self.mod["functions"]:
+            return self.user_call(self.mod["functions"][fn], [self.ev(a) for a in args], list(args)), None
+        if fn in ("idt", "ddx", "absdelay", "transition", "laplace_nd", "laplace_zp", "$port_connected"):
+            raise VAError(f"Verilog-A: {fn} is not supported")
+        if fn.startswith("$") and fn[1:] in _SYS_MATH:
             fn = fn[1:]                              # $pow(...) etc.: system-function spelling
         ev = [self.ev(a) for a in args]
+        if fn == "abs" and ev[0][1] is not None:          # |r + s q| = |r| + s sign(r) q
+            r, q = ev[0]
+            return self.math(fn, [r]), self.select(f"{r.v} < 0.0", self.neg(q), q)
         for _, q in ev:
             self._no_react(q, fn)
-        a = ev[0][0]
-        b = ev[1][0] if len(ev) > 1 else None
-        one = lambda f: (f, None)
+        return self.math(fn, [x[0] for x in ev]), None
+
+    def math(self, fn: str, av: List[_D]) -> _D:
+        a = av[0] if av else None
+        b = av[1] if len(av) > 1 else None
+        if all(x.is_const() for x in av) and fn in _SYS_MATH:
+            it = _Interp.__new__(_Interp)
+            it.mod = {"functions": {}}
+            it.ev = lambda e: (e, 0.0)                 # constants pass straight through
+            try:
+                return self.const(_Interp.call(it, fn, [x.const for x in av])[0])
+            except (ValueError, OverflowError, ZeroDivisionError):
+                pass
         if fn == "exp":
-            return one(self.unary_fn(a, f"CB_EXP({a.v})", lambda v: v))
+            return self.unary_fn(a, f"CB_EXP({a.v})", lambda v: v)
         if fn == "limexp":          # exp(clamp(x,-80,80)), zero slope outside (va_env.jl)
             c = self.temp(f"fmin(fmax({a.v}, -80.0), 80.0)")
-            return one(self.unary_fn(a, f"CB_EXP({c})",
-                                     lambda v: f"({a.v} >= -80.0 && {a.v} <= 80.0) ? {v} : 0.0"))
+            return self.unary_fn(a, f"CB_EXP({c})",
+                                 lambda v: f"({a.v} >= -80.0 && {a.v} <= 80.0) ? {v} : 0.0")
         if fn == "ln":
-            return one(self.unary_fn(a, f"log({a.v})", lambda v: f"1.0 / {a.v}"))
+            return self.unary_fn(a, f"log({a.v})", lambda v: f"1.0 / {a.v}")
         if fn == "log":
-            return one(self.unary_fn(a, f"log10({a.v})", lambda v: f"1.0 / ({a.v} * 2.302585092994046)"))
+            return self.unary_fn(a, f"log10({a.v})", lambda v: f"1.0 / ({a.v} * 2.302585092994046)")
         if fn == "sqrt":
-            return one(self.unary_fn(a, f"sqrt({a.v})", lambda v: f"0.5 / {v}"))
+            return self.unary_fn(a, f"sqrt({a.v})", lambda v: f"0.5 / {v}")
         if fn == "abs":
-            return one(self.unary_fn(a, f"fabs({a.v})", lambda v: f"({a.v} < 0.0) ? -1.0 : 1.0"))
+            return self.unary_fn(a, f"fabs({a.v})", lambda v: f"({a.v} < 0.0) ? -1.0 : 1.0")
         if fn == "sin":
-            return one(self.unary_fn(a, f"sin({a.v})", lambda v: f"cos({a.v})"))
+            return self.unary_fn(a, f"sin({a.v})", lambda v: f"cos({a.v})")
         if fn == "cos":
-            return one(self.unary_fn(a, f"cos({a.v})", lambda v: f"-sin({a.v})"))
+            return self.unary_fn(a, f"cos({a.v})", lambda v: f"-sin({a.v})")
         if fn == "tan":
-            return one(self.unary_fn(a, f"tan({a.v})", lambda v: f"1.0 + {v} * {v}"))
+            return self.unary_fn(a, f"tan({a.v})", lambda v: f"1.0 + {v} * {v}")
         if fn == "tanh":
-            return one(self.unary_fn(a, f"tanh({a.v})", lambda v: f"1.0 - {v} * {v}"))
+            return self.unary_fn(a, f"tanh({a.v})", lambda v: f"1.0 - {v} * {v}")
         if fn == "sinh":
-            return one(self.unary_fn(a, f"sinh({a.v})", lambda v: f"cosh({a.v})"))
+            return self.unary_fn(a, f"sinh({a.v})", lambda v: f"cosh({a.v})")
         if fn == "cosh":
-            return one(self.unary_fn(a, f"cosh({a.v})", lambda v: f"sinh({a.v})"))
+            return self.unary_fn(a, f"cosh({a.v})", lambda v: f"sinh({a.v})")
         if fn == "atan":
-            return one(self.unary_fn(a, f"atan({a.v})", lambda v: f"1.0 / (1.0 + {a.v} * {a.v})"))
+            return self.unary_fn(a, f"atan({a.v})", lambda v: f"1.0 / (1.0 + {a.v} * {a.v})")
+        if fn == "asin":
+            return self.unary_fn(a, f"asin({a.v})", lambda v: f"1.0 / sqrt(1.0 - {a.v} * {a.v})")
+        if fn == "acos":
+            return self.unary_fn(a, f"acos({a.v})", lambda v: f"-1.0 / sqrt(1.0 - {a.v} * {a.v})")
         if fn in ("floor", "ceil"):
-            return one(_D(self.temp(f"{fn}({a.v})"), [None] * self.N))
+            return _D(self.temp(f"{fn}({a.v})"))
         if fn == "pow":
             v = self.temp(f"pow({a.v}, {b.v})")
-            d = []
+            d = {}
             fa = fb = None
-            for pa, pb in zip(a.d, b.d):
+            for k in sorted(set(a.d) | set(b.d)):
                 terms = []
-                if pa is not None:
+                if k in a.d:
                     fa = fa or self.temp(f"{b.v} * pow({a.v}, {b.v} - 1.0)")
-                    terms.append(f"{fa} * {pa}")
-                if pb is not None:
+                    terms.append(f"{fa} * {a.d[k]}")
+                if k in b.d:
                     fb = fb or self.temp(f"{v} * log({a.v})")
-                    terms.append(f"{fb} * {pb}")
-                d.append(self.temp(" + ".join(terms)) if terms else None)
-            return one(_D(v, d))
+                    terms.append(f"{fb} * {b.d[k]}")
+                d[k] = self.temp(" + ".join(terms))
+            return _D(v, d)
         if fn in ("min", "max"):
             cmp = "<" if fn == "min" else ">"
-            return one(self.select(f"{a.v} {cmp} {b.v}", a, b))
+            return self.select(f"{a.v} {cmp} {b.v}", a, b)
         if fn == "hypot":
             h = self.temp(f"sqrt({a.v} * {a.v} + {b.v} * {b.v})")
-            d = []
-            for pa, pb in zip(a.d, b.d):
-                terms = [f"{a.v} * {pa}" if pa else None, f"{b.v} * {pb}" if pb else None]
-                terms = [x for x in terms if x]
-                d.append(self.temp("(" + " + ".join(terms) + f") / {h}") if terms else None)
-            return one(_D(h, d))
-        raise VAError(f"Verilog-A: function {fn!r} is not supported in this tier")
+            d = {}
+            for k in sorted(set(a.d) | set(b.d)):
+                terms = [f"{a.v} * {a.d[k]}" if k in a.d else None, f"{b.v} * {b.d[k]}" if k in b.d else None]
+                d[k] = self.temp("(" + " + ".join(x for x in terms if x) + f") / {h}")
+            return _D(h, d)
+        if fn == "atan2":
+            v = self.temp(f"atan2({a.v}, {b.v})")
+            den = self.temp(f"{a.v} * {a.v} + {b.v} * {b.v}")
+            d = {}
+            for k in sorted(set(a.d) | set(b.d)):
+                d[k] = self.temp(f"({b.v} * {a.d.get(k, '0.0')} - {a.v} * {b.d.get(k, '0.0')}) / {den}")
+            return _D(v, d)
+        raise VAError(f"Verilog-A: function {fn!r} is not supported")
+
+    # -- analog functions: inlined per call site ---------------------------------- #
+    def user_call(self, f, vals: List[_Pair], arg_exprs) -> _D:
+        if len(self.scopes) > 12:
+            raise VAError("Verilog-A: recursive analog functions are not supported")
+        self.callno += 1
+        pre = f"f{self.callno}_"
+        scope = {}
+        for name in [f["name"]] + f["args"] + f["vars"]:
+            cn = pre + name
+            scope[name] = cn
+            self.vtypes[cn] = f["rtype"] if name == f["name"] else f["vtypes"].get(name, "real")
+            if cn not in self.decl_order:
+                self.decl_order.append(cn)
+        self.emit(f"/* {f['name']}() */")
+        # locals start at zero on every call
+        for name in [f["name"]] + f["args"] + f["vars"]:
+            cn = scope[name]
+            a = self._act(cn)
+            self.emit(f"v_{cn} = 0.0;" + "".join(f" v_{cn}_d{k} = 0.0;" for k in sorted(a["d"])))
+        self.scopes.append(scope)
+        for a, v in zip(f["args"], vals):
+            if f["dirs"][a] in ("input", "inout"):
+                self._no_react(v[1], "function argument")
+                self.assign_var(scope[a], (v[0], None))
+        for name in f["vars"]:
+            if name in f["vinit"]:
+                self.assign_var(scope[name], self.ev(f["vinit"][name]))
+        self.stmt(f["body"])
+        self.scopes.pop()
+        for a, ae in zip(f["args"], arg_exprs):
+            if f["dirs"][a] in ("output", "inout") and ae is not None:
+                if ae[0] != "var" or self._cname(ae[1]) is None:
+                    raise VAError("Verilog-A: output argument must be a variable")
+                self.assign_var(self._cname(ae[1]), self.read_var(scope[a]))
+        r, _ = self.read_var(scope[f["name"]])
+        # snapshot: the function variable may be overwritten by a later call of the same site
+        return _D(self.temp(r.v), {k: self.temp(p) for k, p in r.d.items()})
+
+    # -- $limit (vasim.jl:1257-1334) ------------------------------------------------ #
+    def limit(self, args) -> _D:
+        if len(args) < 2 or args[0][0] != "V":
+            raise VAError("$limit: first argument must be a potential probe V(p[,n])")
+        if self.cond_depth:
+            raise VAError("$limit under a runtime conditional is unsupported (would desync stamping counters)")
+        if args[1][0] != "var" or args[1][1] not in self.mod["functions"]:
+            raise VAError("$limit: the limiter must be an analog function of the module")
+        key = (args[0][1], args[0][2])
+        if key not in self.lim_branches:
+            self.lim_branches.append(key)
+        b = self.lim_branches.index(key)
+        self.sites.append(b)
+        j = len(self.sites) - 1
+        vnew = self.probe(*key)
+        vals = [(vnew, None), (_D(f"vold{b}"), None)] + [self.ev(a) for a in args[2:]]
+        r = self.user_call(self.mod["functions"][args[1][1]], vals, [None, None] + list(args[2:]))
+        self.emit(f"const double limw{j} = {r.v};")
+        self.emit(f"VA_LIMW({b}, limw{j});")                      # record_limit_w!
+        d = dict(vnew.d)                                           # pass-through: +1 / -1 on the probe nodes
+        d[self.N + j] = "1.0"                                      # and the site's own slot
+        return _D(f"limw{j}", d)
 
     # -- statements ------------------------------------------------------------ #
     def stmt(self, s):
@@ -622,133 +1365,276 @@ class _Emitter:
             for x in s[1]:
                 self.stmt(x)
         elif kind == "assign":
-            name = s[1]
-            if name not in self.vars:
-                raise VAError(f"Verilog-A: assignment to undeclared variable {name!r}")
-            r, q = self.ev(s[2])
-            self._no_react(q, "assignment")
-            self.emit(f"v_{name} = {r.v};")
-            for k in range(self.N):
-                self.emit(f"v_{name}_d{k} = {r.d[k] or '0.0'};")
-            self.assigned.add(name)
+            cname = self._cname(s[1])
+            if cname is None:
+                raise VAError(f"Verilog-A: assignment to undeclared variable {s[1]!r}")
+            if len(self.scopes) == 1 and s[1] not in self.live:
+                return                                   # dead on the value path (op-vars, noise)
+            self.assign_var(cname, self.ev(s[2]))
         elif kind == "if":
             c, cq = self.ev(s[1])
-            self._no_react(cq, "if")
-            # a variable first assigned inside a branch must read as declared afterwards
-            before = set(self.assigned)
+            if c.is_const():
+                self.stmt(s[2] if c.const != 0.0 else s[3])
+                return
+            self.cond_depth += 1
+            qz0 = set(self.qz)
             self.emit(f"if ({c.v} != 0.0) {{")
             self.indent += 1
             self.stmt(s[2])
             self.indent -= 1
-            a1 = set(self.assigned)
-            self.assigned = set(before)
-            self.emit("} else {")
+            qz1, self.qz = self.qz, set(qz0)
+            if s[3] != ("block", []):
+                self.emit("} else {")
+                self.indent += 1
+                self.stmt(s[3])
+                self.indent -= 1
+            self.emit("}")
+            self.qz &= qz1
+            self.cond_depth -= 1
+        elif kind == "case":
+            sel, sq = self.ev(s[1])
+            chain = s[3]
+            for vals, body in reversed(s[2]):
+                cond = None
+                for v in vals:
+                    c = ("bin", "==", ("cval", sel), v)
+                    cond = c if cond is None else ("bin", "||", cond, c)
+                chain = ("if", cond, body, chain)
+            self.stmt(chain)
+        elif kind == "for":
+            self.stmt(s[1])
+            self.cond_depth += 1
+            self.qz = set()                              # loop-carried values: assume nothing
+            self.emit("for (;;) {")
             self.indent += 1
+            c, cq = self.ev(s[2])
+            self.emit(f"if (!({c.v} != 0.0)) break;")
+            self.stmt(s[4])
             self.stmt(s[3])
             self.indent -= 1
             self.emit("}")
-            self.assigned = a1 | self.assigned
+            self.qz = set()
+            self.cond_depth -= 1
         elif kind == "contrib":
-            key = (s[1], s[2])
-            if key not in self.branches:
-                self.branches.append(key)
-            bi = self.branches.index(key)
-            r, q = self.ev(s[3])
-            self.emit(f"I{bi} += {r.v};")
-            for k in range(self.N):
-                if r.d[k] is not None:
-                    self.emit(f"I{bi}_d{k} += {r.d[k]};")
-            if q is not None:
-                self.reactive[bi] = True
-                self.emit(f"Q{bi} += {q.v};")
-                for k in range(self.N):
-                    if q.d[k] is not None:
-                        self.emit(f"Q{bi}_d{k} += {q.d[k]};")
-                # voltage-dependent iff a partial of the charge is not a parameter-only constant
-                if any(p is not None and not self._param_only(p) for p in q.d):
-                    self.vdep[bi] = True
+            self.contrib(s)
+        elif kind == "callstmt":
+            outs = [a[1] for a in s[1][2] if isinstance(a, tuple) and a[0] == "var"]
+            if len(self.scopes) == 1 and not any(o in self.live for o in outs):
+                return
+            self.ev(s[1])
+        elif kind == "vcontrib":
+            # only the node-collapse idiom `if (cond) V(int, ext) <+ 0;` (vasim.jl:2723-2825):
+            # aliased when cond holds, never executed otherwise -> no code either way
+            pass
         else:
             raise VAError(f"Verilog-A: statement {kind!r} not supported")
 
-    def _param_only(self, expr: str, _seen=None) -> bool:
-        """True when the C expression depends on parameters / literals only."""
-        _seen = _seen or set()
-        for name in re.findall(r"[A-Za-z_][A-Za-z0-9_]*", expr):
-            if name in ("fmin", "fmax", "pow", "log", "exp", "sqrt", "CB_EXP", "fabs", "e", "E"):
-                continue
-            if name.startswith("p_"):
-                continue
-            if re.fullmatch(r"t\d+", name):
-                if name in _seen:
-                    continue
-                _seen.add(name)
-                rhs = self._temp_rhs(name)
-                if rhs is None or not self._param_only(rhs, _seen):
-                    return False
-                continue
-            return False             # V*, v_* (state-dependent) or anything unknown
-        return True
+    def contrib(self, s):
+        key = (s[1], s[2])
+        if key not in self.branches:
+            self.branches.append(key)
+        bi = self.branches.index(key)
+        ba = self.bact.setdefault(bi, {"d": set(), "q": False, "qd": set()})
+        r, q = self.ev(s[3])
+        if _has_ddt(s[3], self.mod) and not ba["q"]:
+            ba["q"] = True
+            self.changed = True
+        if not (r.is_const() and r.const == 0.0):
+            self.emit(f"I{bi} += {r.v};")
+        for k in sorted(r.d):
+            if k not in ba["d"]:
+                ba["d"].add(k); self.changed = True
+            self.emit(f"I{bi}_d{k} += {r.d[k]};")
+        if q is not None:
+            self.emit(f"Q{bi} += {q.v};")
+            for k in sorted(q.d):
+                if k not in ba["qd"]:
+                    ba["qd"].add(k); self.changed = True
+                self.emit(f"Q{bi}_d{k} += {q.d[k]};")
 
-    def _temp_rhs(self, name: str) -> Optional[str]:
-        pat = f"const double {name} = "
-        for ln in self.lines:
-            s = ln.strip()
-            if s.startswith(pat):
-                return s[len(pat):-1]
-        return None
+
+# `case` selectors are evaluated once: a ("cval", _D) node passes the value through
+_orig_ev = _Emitter.ev
+
+
+def _ev_with_cval(self, e):
+    if e[0] == "cval":
+        return e[1], None
+    return _orig_ev(self, e)
+
+
+_Emitter.ev = _ev_with_cval
+
+
+def _find_collapses(mod) -> Dict[str, Tuple[str, Any]]:
+    """``if (cond) V(int, ext) <+ 0;`` directly inside a conditional of the analog block
+    (detect_short_circuits, vasim.jl:2723-2825): internal node -> (port, cond)."""
+    ports = set(mod["ports"])
+    internal = set(mod["electrical"]) - ports
+    out: Dict[str, Tuple[str, Any]] = {}
+
+    def scan(stmts, cond):
+        for s in stmts:
+            if s[0] == "block":
+                scan(s[1], cond)
+            elif s[0] == "vcontrib":
+                if s[3] != ("num", 0.0):
+                    raise VAError("Verilog-A: voltage contributions other than the node-collapse idiom "
+                                  "`V(internal, port) <+ 0` are not supported")
+                p, n = s[1], s[2]
+                if p in internal and n in ports:
+                    out[p] = (n, cond)
+                elif n in internal and p in ports:
+                    out[n] = (p, cond)
+                else:
+                    raise VAError("Verilog-A: V(a,b) <+ 0 must join an internal node and a port")
+
+    def walk(s):
+        if s[0] == "block":
+            for x in s[1]:
+                walk(x)
+        elif s[0] == "if":
+            scan([s[2]], s[1])
+            if s[3][0] == "if":
+                walk(s[3])
+
+    def count(s) -> int:
+        if s[0] == "vcontrib":
+            return 1
+        if s[0] == "block":
+            return sum(count(x) for x in s[1])
+        if s[0] == "if":
+            return count(s[2]) + count(s[3])
+        if s[0] == "for":
+            return count(s[4])
+        if s[0] == "case":
+            return sum(count(b) for _, b in s[2]) + count(s[3])
+        return 0
+    walk(mod["body"])
+    if count(mod["body"]) != len(out):
+        raise VAError("Verilog-A: voltage contributions other than `if (cond) V(internal, port) <+ 0;` "
+                      "are not supported")
+    return out
 
 
 # --------------------------------------------------------------------------- #
-# model object
+# model objects
 # --------------------------------------------------------------------------- #
-class VAModel:
-    """A parsed Verilog-A module: knows its structure (ports, internal nodes, branches)
-    and emits its stamp function for the CUDA kernels and for the C oracle."""
+class VAVariant:
+    """The emitted stamp function of a module for one set of given parameters and one
+    outcome of the voltage-dependent-charge detection."""
 
-    def __init__(self, source: str):
-        self.source = source
-        self.mod = _Parser(source).module()
-        m = self.mod
-        self.name = m["name"]
-        self.ports = list(m["ports"])
-        self.internal = [n for n in m["electrical"] if n not in self.ports]
-        self.nodes = self.ports + self.internal           # "all nodes": ports, then internals
-        self.param_names = [p[0] for p in m["params"]]
-        self.param_defaults = [p[1] for p in m["params"]]
-        em = _Emitter(m, self.param_names, self.nodes)
-        em.stmt(m["body"])
+    def __init__(self, model: "VAModel", given: frozenset, vdep: Optional[Tuple[bool, ...]]):
+        self.model, self.given = model, given
+        mod = model.mod
+        act: dict = {}
+        bact: dict = {}
+        for _ in range(40):
+            em = _Emitter(mod, given, act, bact)
+            # module-level initialisers, in declaration order (vasim.jl:3149-3212)
+            for name in mod["vars"]:
+                if name in mod["vinit"]:
+                    em.assign_var(name, em.ev(mod["vinit"][name]))
+            em.stmt(mod["body"])
+            if not em.changed:
+                break
+        else:
+            raise VAError(f"{model.name}: derivative activity analysis did not converge")
         self._em = em
+        self.nodes = em.nodes
+        self.N = em.N
         self.branches = list(em.branches)
-        self.reactive = [bool(em.reactive.get(i)) for i in range(len(self.branches))]
-        self.vdep = [bool(em.vdep.get(i)) for i in range(len(self.branches))]
-        self.n_charges = sum(1 for i in range(len(self.branches)) if self.reactive[i] and self.vdep[i])
-        self.uid = hashlib.sha256(source.encode()).hexdigest()[:12]
-        self.cname = re.sub(r"\W", "_", self.name) + "_" + self.uid
+        self.lim_branches = list(em.lim_branches)
+        self.sites = list(em.sites)
+        self.extras = list(em.extras)
+        self.bact = {bi: bact.get(bi, {"d": set(), "q": False, "qd": set()}) for bi in range(len(self.branches))}
+        self.reactive = [bool(self.bact[bi]["q"]) for bi in range(len(self.branches))]
+        self.static_vdep = [self.reactive[bi] and not self._proportional(bi) for bi in range(len(self.branches))]
+        self.vdep = list(self.static_vdep) if vdep is None else [bool(x) for x in vdep]
+        self.n_charges = sum(1 for bi in range(len(self.branches)) if self.reactive[bi] and self.vdep[bi])
+        key = f"{model.uid}|{sorted(given)}|{self.vdep}"
+        self.uid = hashlib.sha256(key.encode()).hexdigest()[:12]
+        self.cname = re.sub(r"\W", "_", model.name) + "_" + self.uid
+        # local slot layout: nodes, then limit unknowns, then charge unknowns (in stamping order)
+        self.lim_slot = [self.N + b for b in range(len(self.lim_branches))]
+        self.q_slot: Dict[int, int] = {}
+        nxt = self.N + len(self.lim_branches)
+        for bi in range(len(self.branches)):
+            if self.reactive[bi] and self.vdep[bi]:
+                self.q_slot[bi] = nxt
+                nxt += 1
+        self.n_slots = nxt
 
-    # ---- instances ----------------------------------------------------------- #
-    def __call__(self, **kwargs):
-        return VAInstance(self, kwargs)
+    # convenience mirrors used by tests / lowering
+    @property
+    def name(self):
+        return self.model.name
 
-    def default_params(self, given: Dict[str, Any]) -> List[Any]:
-        lower = {k.lower(): v for k, v in given.items() if k != "name"}
-        unknown = set(lower) - {p.lower() for p in self.param_names}
-        if unknown:
-            raise VAError(f"{self.name}: unknown parameter(s) {sorted(unknown)}")
-        vals: Dict[str, Any] = {}
-        for name, default in zip(self.param_names, self.param_defaults):
-            if name.lower() in lower:
-                vals[name] = lower[name.lower()]
-            else:
-                vals[name] = _const_eval(default, vals)
-        return [vals[n] for n in self.param_names]
+    @property
+    def ports(self):
+        return self.model.ports
+
+    @property
+    def internal(self):
+        return self.model.internal
+
+    def _proportional(self, bi: int) -> bool:
+        """Static stand-in for the Q/V probe when no instance is at hand: the branch charge is
+        c*(V_p - V_n) with c independent of the node voltages."""
+        ba = self.bact[bi]
+        a, b = self.branches[bi]
+        p = self.nodes.index(a)
+        n = self.nodes.index(b) if b is not None else None
+        if set(ba["qd"]) - {p, n}:
+            return False
+        return not self._bias_dependent_partials(bi)
+
+    def _bias_dependent_partials(self, bi: int) -> bool:
+        em = self._em
+        rhs = {}
+        for ln in em.lines:
+            s = ln.strip()
+            m = re.match(r"const double (t\d+) = (.*);$", s)
+            if m:
+                rhs[m.group(1)] = m.group(2)
+        seen: set = set()
+
+        def dep(expr: str) -> bool:
+            for name in re.findall(r"[A-Za-z_][A-Za-z0-9_]*", expr):
+                if name in ("fmin", "fmax", "pow", "log", "log10", "exp", "sqrt", "CB_EXP", "fabs", "e", "E",
+                            "va_mfactor", "VA_ROUND") or name.startswith("p_") or name.startswith("x_"):
+                    continue
+                if re.fullmatch(r"t\d+", name):
+                    if name in seen:
+                        continue
+                    seen.add(name)
+                    if name not in rhs or dep(rhs[name]):
+                        return True
+                    continue
+                return True
+            return False
+        for ln in em.lines:
+            m = re.match(rf"\s*Q{bi}_d\d+ \+= (.*);$", ln)
+            if m and dep(m.group(1)):
+                return True
+        return False
 
     # ---- structure (the COO order the emitted code produces) ------------------ #
     def stamp_plan(self):
-        """[(kind, args)] in emission order; kinds: G(i,j) C(i,j) b(i) where i, j are
-        local node slots (0..N-1 = module nodes, N.. = charge unknowns) ."""
-        N = len(self.nodes)
-        plan = []
-        q = 0
+        """[(kind, ...)] in emission order.  ``("L", slot, p, n, name)`` alloc_limit!,
+        ``("Q", slot, p, n, name)`` alloc_charge!, ``("G", i, j)``, ``("C", i, j)``, ``("b", i)``
+        with i, j local slots (0..N-1 module nodes, then limit and charge unknowns)."""
+        N = self.N
+        plan: List[Tuple] = []
+        for b, (a, c) in enumerate(self.lim_branches):
+            p = self.nodes.index(a)
+            n = self.nodes.index(c) if c is not None else None
+            ls = self.lim_slot[b]
+            plan.append(("L", ls, p, n, f"lim_{a}_{c if c is not None else '0'}"))
+            plan.append(("G", ls, ls))
+            plan.append(("G", ls, p))
+            if n is not None:
+                plan.append(("G", ls, n))
         for bi, (a, b) in enumerate(self.branches):
             p = self.nodes.index(a)
             n = self.nodes.index(b) if b is not None else None
@@ -758,9 +1644,8 @@ class VAModel:
                     plan.append(("G", n, k))
             if self.reactive[bi]:
                 if self.vdep[bi]:
-                    qi = N + q
-                    q += 1
-                    plan.append(("Q", p, n, f"Q_{a}_{b if b is not None else '0'}"))   # alloc_charge!
+                    qi = self.q_slot[bi]
+                    plan.append(("Q", qi, p, n, f"Q_{a}_{b if b is not None else '0'}"))   # alloc_charge!
                     plan.append(("C", p, qi))
                     if n is not None:
                         plan.append(("C", n, qi))
@@ -779,108 +1664,279 @@ class VAModel:
         return plan
 
     # ---- code emission --------------------------------------------------------- #
-    def _body(self, target: str) -> str:
-        """target: 'cuda' or 'c'.  The two differ only in the prologue / stamping macros."""
-        em, N = self._em, len(self.nodes)
+    def _decls(self) -> List[str]:
+        em, L = self._em, []
+        for cn in em.decl_order:
+            a = em.act.get(cn, {"d": set(), "q": False, "qd": set()})
+            names = [f"v_{cn}"] + [f"v_{cn}_d{k}" for k in sorted(a["d"])]
+            if a["q"]:
+                names += [f"vq_{cn}"] + [f"vq_{cn}_d{k}" for k in sorted(a["qd"])]
+            L.append("    double " + ", ".join(f"{x} = 0.0" for x in names) + "; " +
+                     " ".join(f"(void){x};" for x in names))
+        return L
+
+    def _body(self, charge_alloc: bool = False) -> str:
+        """Shared by the CUDA and the C back end: they differ only in the prologue and in
+        the stamping macros.  charge_alloc: emit the oracle's run-time detection protocol."""
+        em, N = self._em, self.N
+        S = len(self.sites)
         L: List[str] = []
         for k in range(N):
-            L.append(f"    const double V{k} = VA_V({k});")
-        for i, name in enumerate(self.param_names):
+            L.append(f"    const double V{k} = VA_V({k}); (void)V{k};")
+        for i, name in enumerate(self.model.param_names):
             L.append(f"    const double p_{name} = VA_PARAM({i}); (void)p_{name};")
-        for name in self.mod["reals"]:
-            L.append(f"    double v_{name} = 0.0; (void)v_{name};")
-            L.append("    double " + ", ".join(f"v_{name}_d{k} = 0.0" for k in range(N)) + ";")
-            L.append("    " + " ".join(f"(void)v_{name}_d{k};" for k in range(N)))
+        np_ = len(self.model.param_names)
+        L.append(f"    const double va_mfactor = VA_PARAM({np_}); (void)va_mfactor;")
+        for i in range(len(self.extras)):
+            L.append(f"    const double x_{i} = VA_PARAM({np_ + 1 + i}); (void)x_{i};")
+        for b, (a, c) in enumerate(self.lim_branches):              # $limit preamble, vasim.jl:3109-3146
+            p = self.nodes.index(a)
+            ls = self.lim_slot[b]
+            L.append(f"    const double vold{b} = VA_V({ls}); (void)vold{b};")
+            L.append(f"    VA_G({ls}, {ls}, 1.0);")
+            L.append(f"    VA_G({ls}, {p}, -1.0);")
+            if c is not None:
+                L.append(f"    VA_G({ls}, {self.nodes.index(c)}, 1.0);")
+        L += self._decls()
         for bi in range(len(self.branches)):
-            L.append(f"    double I{bi} = 0.0, " + ", ".join(f"I{bi}_d{k} = 0.0" for k in range(N)) + ";")
-            if self.reactive[bi]:
-                L.append(f"    double Q{bi} = 0.0, " + ", ".join(f"Q{bi}_d{k} = 0.0" for k in range(N)) + ";")
+            ba = self.bact[bi]
+            names = [f"I{bi}"] + [f"I{bi}_d{k}" for k in sorted(ba["d"])]
+            if ba["q"]:
+                names += [f"Q{bi}"] + [f"Q{bi}_d{k}" for k in sorted(ba["qd"])]
+            L.append("    double " + ", ".join(f"{x} = 0.0" for x in names) + ";")
         L += em.lines
-        q = 0
+
+        def part(prefix, bi, k, act):
+            return f"va_mfactor * {prefix}{bi}_d{k}" if k in act else "0.0"
+
         for bi, (a, b) in enumerate(self.branches):
+            ba = self.bact[bi]
             p = self.nodes.index(a)
             n = self.nodes.index(b) if b is not None else None
             L.append(f"    /* branch {bi}: I({a}{',' + b if b else ''}) */")
+            L.append("    {")
             for k in range(N):
-                L.append(f"    VA_G({p}, {k}, I{bi}_d{k});")
+                if k in ba["d"]:
+                    L.append(f"    const double dI{k} = va_mfactor * I{bi}_d{k};")
+            for k in range(N):
+                g = f"dI{k}" if k in ba["d"] else "0.0"
+                L.append(f"    VA_G({p}, {k}, {g});")
                 if n is not None:
-                    L.append(f"    VA_G({n}, {k}, -I{bi}_d{k});")
+                    L.append(f"    VA_G({n}, {k}, -{g});")
             if self.reactive[bi]:
-                if self.vdep[bi]:
-                    qi = N + q
-                    q += 1
-                    L.append(f"    VA_C({p}, {qi}, 1.0 / {CHARGE_SCALE!r});")
+                for k in range(N):
+                    if k in ba["qd"]:
+                        L.append(f"    const double dQ{k} = va_mfactor * Q{bi}_d{k};")
+                qterms = [f"      bq -= dQ{k} * V{k};" for k in range(N) if k in ba["qd"]]
+                for j in range(S):                                  # lim_rhs anchoring of the charge companion
+                    if N + j in ba["qd"]:
+                        qterms.append(f"      bq += va_mfactor * Q{bi}_d{N + j} * ({self._probe_expr(j)} - limw{j});")
+                charge_rows = []
+                qi = self.q_slot.get(bi)
+                if qi is not None or charge_alloc:
+                    qs = "QX" if charge_alloc else qi
+                    charge_rows.append(f"    VA_C({p}, {qs}, 1.0 / {CHARGE_SCALE!r});")
                     if n is not None:
-                        L.append(f"    VA_C({n}, {qi}, -1.0 / {CHARGE_SCALE!r});")
-                    L.append(f"    VA_G({qi}, {qi}, 1.0);")
+                        charge_rows.append(f"    VA_C({n}, {qs}, -1.0 / {CHARGE_SCALE!r});")
+                    charge_rows.append(f"    VA_G({qs}, {qs}, 1.0);")
                     for k in range(N):
-                        L.append(f"    VA_G({qi}, {k}, -{CHARGE_SCALE!r} * Q{bi}_d{k});")
-                    L.append(f"    {{ double bq = Q{bi};")
-                    for k in range(N):
-                        L.append(f"      bq -= Q{bi}_d{k} * V{k};")
-                    L.append(f"      VA_B({qi}, {CHARGE_SCALE!r} * bq); }}")
+                        dq = f"dQ{k}" if k in ba["qd"] else "0.0"
+                        charge_rows.append(f"    VA_G({qs}, {k}, -{CHARGE_SCALE!r} * {dq});")
+                    charge_rows.append(f"    {{ double bq = va_mfactor * Q{bi};")
+                    charge_rows += qterms
+                    charge_rows.append(f"      VA_B({qs}, {CHARGE_SCALE!r} * bq); }}")
+                plain_rows = []
+                for k in range(N):
+                    dq = f"dQ{k}" if k in ba["qd"] else "0.0"
+                    plain_rows.append(f"    VA_C({p}, {k}, {dq});")
+                    if n is not None:
+                        plain_rows.append(f"    VA_C({n}, {k}, -{dq});")
+                if charge_alloc:
+                    # oracle: detect_or_cached! decides at run time (contrib.jl:214-296)
+                    vb = f"V{p}" + (f" - V{n}" if n is not None else "")
+                    L.append(f"    if (VA_DETECT({vb}, va_mfactor * Q{bi})) {{")
+                    L.append(f"    VA_ALLOC_Q(QX, {p}, {n if n is not None else -1});")
+                    L += charge_rows
+                    L.append("    } else {")
+                    L += plain_rows
+                    L.append("    }")
+                elif self.vdep[bi]:
+                    L += charge_rows
                 else:
-                    for k in range(N):
-                        L.append(f"    VA_C({p}, {k}, Q{bi}_d{k});")
-                        if n is not None:
-                            L.append(f"    VA_C({n}, {k}, -Q{bi}_d{k});")
-            L.append(f"    {{ double Ieq = I{bi};")
+                    L += plain_rows
+            L.append(f"    double Ieq = va_mfactor * I{bi};")
             for k in range(N):
-                L.append(f"      Ieq += -I{bi}_d{k} * V{k};")
-            L.append(f"      VA_B({p}, -Ieq);")
+                if k in ba["d"]:
+                    L.append(f"    Ieq += -dI{k} * V{k};")
+            for j in range(S):                                      # lim_rhs anchoring, vasim.jl:3493-3501
+                if N + j in ba["d"]:
+                    L.append(f"    Ieq += va_mfactor * I{bi}_d{N + j} * ({self._probe_expr(j)} - limw{j});")
+            L.append(f"    VA_B({p}, -Ieq);")
             if n is not None:
-                L.append(f"      VA_B({n}, Ieq);")
+                L.append(f"    VA_B({n}, Ieq);")
             L.append("    }")
         return "\n".join(L)
 
+    def _probe_expr(self, j: int) -> str:
+        a, c = self.lim_branches[self.sites[j]]
+        p = self.nodes.index(a)
+        return f"V{p}" + (f" - V{self.nodes.index(c)}" if c is not None else " - 0.0")
+
     def emit_cuda(self) -> str:
         """``template <int PASS, typename PG, typename W> va_stamp_<cname>(...)`` for
-        lane_kernels.cuh: node slot i of the module = ``pg.dev_node(nb + i)``."""
-        nloc = len(self.nodes) + self.n_charges
-        head = [f"// Verilog-A module {self.name} (emitted by cadnip_b200.verilog_a)",
+        lane_kernels.cuh: local slot i of the module = ``pg.dev_node(nb + i)``."""
+        head = [f"// Verilog-A module {self.name} (emitted by cadnip_b200.verilog_a); given: "
+                f"{', '.join(sorted(self.given)) or '-'}",
                 "template <int PASS, typename PG, typename W>",
-                f"__device__ __forceinline__ void va_stamp_{self.cname}(const PG &pg, W &w, int d, double t)",
+                f"__device__ CB200_VA_FN void va_stamp_{self.cname}(const PG &pg, W &w, int d, double t,"
+                " int va_mode, bool va_initjct_b)",
                 "{",
-                "    (void)t;",
+                "    (void)t; (void)va_mode;",
                 "    if (PASS == 2) return;                      // nothing depends on time alone",
+                "    const double va_initjct = va_initjct_b ? 1.0 : 0.0; (void)va_initjct;",
                 "    const int nb = pg.dev_node_ptr(d), pb = pg.dev_param_ptr(d);",
                 "    int g = pg.off_SG() + pg.dev_gbase(d), c = pg.off_SC() + pg.dev_cbase(d);",
                 "    int b = pg.off_SB() + pg.dev_bbase(d);",
                 "    (void)c;"]
-        for i in range(nloc):
+        for i in range(self.n_slots):
             head.append(f"    const int n{i} = pg.dev_node(nb + {i});")
-        return "\n".join(head) + "\n" + self._body("cuda") + "\n}\n"
+        return "\n".join(head) + "\n" + self._body() + "\n}\n"
 
     def emit_c(self) -> str:
-        """Plain C for the oracle: ``void ora_va_<cname>(const ora_va_api *A, void *ctx, ...)``."""
-        nloc = len(self.nodes) + self.n_charges
-        N = len(self.nodes)
+        """Plain C for the oracle: it allocates its own internal nodes / limit and charge
+        unknowns (it is the builder) and decides node collapse and charge formulation at
+        run time, as the reference's generated stamp! does."""
+        N = self.N
+        nlim = len(self.lim_branches)
         L = [f"/* Verilog-A module {self.name} (emitted by cadnip_b200.verilog_a) */",
              f"void ora_va_{self.cname}(const ora_va_api *A, void *ctx, const int *ports, const double *par,",
-             "                          const double *x, long nx, double t)",
+             "                          const double *x, long nx, double t, int va_mode)",
              "{",
-             "    (void)t;",
-             f"    long n[{nloc}];"]
+             "    (void)t; (void)va_mode;",
+             "    const double va_initjct = A->initjct(ctx) ? 1.0 : 0.0; (void)va_initjct;",
+             f"    long n[{N + nlim + 1}]; long QX = {N + nlim}; (void)QX;"]
         for i in range(len(self.ports)):
             L.append(f"    n[{i}] = ports[{i}];")
+        if self.model.collapses:
+            L.append("    /* node-collapse conditions, evaluated with the parameters and the variables'")
+            L.append("       initial values (vasim.jl:3532-3564) */")
+            L.append(self.model.collapse_c(self.given))
         for j, name in enumerate(self.internal):
-            L.append(f"    n[{len(self.ports) + j}] = A->alloc_internal_node(ctx);   /* {name} */")
-        L.append(f"    double Vn[{N}];")
-        L.append(f"    for (int k = 0; k < {N}; k++) Vn[k] = A->xval(ctx, n[k], x, nx);")
-        # charge unknowns are allocated where the reference allocates them: inside the branch loop
-        body = self._body("c")
-        q = 0
-        for bi in range(len(self.branches)):
-            if self.reactive[bi] and self.vdep[bi]:
-                a, b = self.branches[bi]
-                p = self.nodes.index(a)
-                nn = self.nodes.index(b) if b is not None else -1
-                marker = f"    VA_C({p}, {N + q}, 1.0 / {CHARGE_SCALE!r});"
-                alloc = (f"    n[{N + q}] = A->alloc_charge(ctx, n[{p}], "
-                         f"{'n[%d]' % nn if nn >= 0 else '0'});\n")
-                body = body.replace(marker, alloc + marker, 1)
-                q += 1
-        return "\n".join(L) + "\n" + body + "\n}\n"
+            slot = len(self.ports) + j
+            if name in self.model.collapses:
+                ext = self.ports.index(self.model.collapses[name][0])
+                L.append(f"    n[{slot}] = va_collapse_{name} ? n[{ext}] : A->alloc_internal_node(ctx);   /* {name} */")
+            else:
+                L.append(f"    n[{slot}] = A->alloc_internal_node(ctx);   /* {name} */")
+        for b, (a, c) in enumerate(self.lim_branches):
+            p = self.nodes.index(a)
+            nn = f"n[{self.nodes.index(c)}]" if c is not None else "0"
+            L.append(f"    n[{self.lim_slot[b]}] = A->alloc_limit(ctx, n[{p}], {nn});")
+        L.append(f"    double Vn[{N + nlim}];")
+        L.append(f"    for (int k = 0; k < {N + nlim}; k++) Vn[k] = A->xval(ctx, n[k], x, nx);")
+        return "\n".join(L) + "\n" + self._body(charge_alloc=True) + "\n}\n"
+
+
+class VAModel:
+    """A parsed Verilog-A module.  ``model(**params)`` makes an instance; the emitted code
+    lives in per-(given-set, detection outcome) variants."""
+
+    def __init__(self, source: str):
+        self.source = source
+        self.mod = _Parser(source).module()
+        m = self.mod
+        self.name = m["name"]
+        self.ports = list(m["ports"])
+        self.internal = [n for n in m["electrical"] if n not in self.ports]
+        self.nodes = self.ports + self.internal           # "all nodes": ports, then internals
+        self.param_names = [p[0] for p in m["params"]]
+        self.param_defaults = [p[1] for p in m["params"]]
+        self.uid = hashlib.sha256(source.encode()).hexdigest()[:12]
+        self.collapses = _find_collapses(m)
+        self._variants: Dict[Tuple, VAVariant] = {}
+        self._default: Optional[VAVariant] = None
+        self.default                                      # emit once now: unsupported constructs fail here
+
+    def variant(self, given=frozenset(), vdep=None) -> VAVariant:
+        key = (frozenset(given), None if vdep is None else tuple(bool(x) for x in vdep))
+        v = self._variants.get(key)
+        if v is None:
+            v = self._variants[key] = VAVariant(self, key[0], key[1])
+        return v
+
+    # model-level view (no parameters given, static charge classification)
+    @property
+    def default(self) -> VAVariant:
+        if self._default is None:
+            self._default = self.variant()
+        return self._default
+
+    branches = property(lambda self: self.default.branches)
+    reactive = property(lambda self: self.default.reactive)
+    vdep = property(lambda self: self.default.vdep)
+    n_charges = property(lambda self: self.default.n_charges)
+    cname = property(lambda self: self.default.cname)
+
+    def stamp_plan(self):
+        return self.default.stamp_plan()
+
+    def emit_cuda(self) -> str:
+        return self.default.emit_cuda()
+
+    def emit_c(self) -> str:
+        return self.default.emit_c()
+
+    # ---- instances ----------------------------------------------------------- #
+    def __call__(self, **kwargs):
+        return VAInstance(self, kwargs)
+
+    def resolve_params(self, given: Dict[str, Any]) -> Tuple[Dict[str, Any], frozenset]:
+        """``spicecall``: case-insensitive names, aliasparam (src/spectre.jl:474-513)."""
+        canon = {p.lower(): p for p in self.param_names}
+        alias = {a.lower(): t for a, t in self.mod["aliases"].items()}
+        vals: Dict[str, Any] = {}
+        for k, v in given.items():
+            lk = k.lower()
+            name = canon.get(lk) or alias.get(lk)
+            if name is None:
+                raise VAError(f"{self.name}: unknown parameter {k!r}")
+            vals[name] = v
+        g = frozenset(vals)
+        full: Dict[str, Any] = {}
+        for name, default in zip(self.param_names, self.param_defaults):
+            full[name] = vals[name] if name in vals else _const_eval(default, full)
+        return full, g
+
+    def collapse_c(self, given: frozenset) -> str:
+        """C statements defining ``va_collapse_<node>`` for the oracle's allocation step."""
+        act: dict = {}
+        em = _Emitter(self.mod, given, act, {})
+        em.indent = 1
+        for _ in range(3):
+            em = _Emitter(self.mod, given, act, {})
+            for name in self.mod["vars"]:
+                if name in self.mod["vinit"]:
+                    em.assign_var(name, em.ev(self.mod["vinit"][name]))
+            conds = {}
+            for node, (ext, cond) in self.collapses.items():
+                c, _ = em.ev(cond)
+                conds[node] = c.v
+            if not em.changed:
+                break
+        L = ["    {"]
+        for i, name in enumerate(self.param_names):
+            L.append(f"    const double p_{name} = par[{i}]; (void)p_{name};")
+        npar = len(self.param_names)
+        L.append(f"    const double va_mfactor = par[{npar}]; (void)va_mfactor;")
+        for i in range(len(em.extras)):
+            L.append(f"    const double x_{i} = par[{npar + 1 + i}]; (void)x_{i};")
+        for cn in em.decl_order:
+            L.append(f"    double v_{cn} = 0.0; (void)v_{cn};")
+        L += em.lines
+        for node, cexpr in conds.items():
+            L.append(f"    va_collapse_{node} = ({cexpr}) != 0.0;")
+        L.append("    }")
+        return "\n".join([f"    int va_collapse_{node} = 0;" for node in self.collapses] + L)
 
 
 def _const_eval(e, env: Dict[str, Any]):
@@ -898,20 +1954,113 @@ def _const_eval(e, env: Dict[str, Any]):
         a, b = _const_eval(e[2], env), _const_eval(e[3], env)
         return {"+": lambda: a + b, "-": lambda: a - b, "*": lambda: a * b, "/": lambda: a / b}[e[1]]()
     if k == "call" and e[1] in ("exp", "ln", "sqrt", "pow"):
-        import numpy as np
         args = [_const_eval(a, env) for a in e[2]]
         return {"exp": np.exp, "ln": np.log, "sqrt": np.sqrt, "pow": np.power}[e[1]](*args)
     raise VAError("Verilog-A: unsupported expression in a parameter default")
 
 
+def _lane0(v) -> float:
+    a = np.asarray(v, dtype=np.float64)
+    return float(a.reshape(-1)[0])
+
+
 class VAInstance:
-    """``NMOS(K=1e-3, Vth=0.5)``: a module with its parameter values bound
-    (``spicecall`` with case-insensitive names, src/spectre.jl:474-513)."""
+    """``sp_mos1(vto=0.7, kp=100e-6, w=1e-6, l=1e-6)``: a module with its parameter values
+    bound; ``m=`` is the multiplicity (``_mna_mfactor_``, codegen.jl:2210-2219)."""
 
     def __init__(self, model: VAModel, kwargs: Dict[str, Any]):
+        kwargs = dict(kwargs)
         self.model = model
         self.name = kwargs.pop("name", model.name)
-        self.params = model.default_params(kwargs)
+        self.mfactor = kwargs.pop("mfactor", 1.0)
+        if "m" in kwargs and "m" not in {p.lower() for p in model.param_names}:
+            self.mfactor = kwargs.pop("m")
+        self.values, self.given = model.resolve_params(kwargs)
+        self.params = [self.values[n] for n in model.param_names]       # declared parameters only
+
+    # -- host-side structure decisions ---------------------------------------- #
+    def _interp(self, spec) -> _Interp:
+        sim = {f: getattr(spec, f) for f in _SPEC_FIELDS if hasattr(spec, f)}
+        sim.setdefault("temp", 27.0)
+        vals = {k: _lane0(v) for k, v in self.values.items()}
+        return _Interp(self.model.mod, vals, self.given, sim, mode=getattr(spec, "mode", "dcop"),
+                       mfactor=_lane0(self.mfactor))
+
+    def collapsed(self, spec) -> Dict[str, str]:
+        """internal node -> port it aliases (conditions evaluated at allocation time)."""
+        out = {}
+        if self.model.collapses:
+            it = self._interp(spec)
+            it.init_vars()
+            for node, (ext, cond) in self.model.collapses.items():
+                vals = self.values
+                for name in _names_in(cond):
+                    v = vals.get(name)
+                    if isinstance(v, np.ndarray) and v.ndim and not np.all(v == v.reshape(-1)[0]):
+                        from .lowering import StructuralSweepError
+                        raise StructuralSweepError(
+                            f"{self.model.name}: node-collapse condition depends on swept parameter {name!r}")
+                if it.ev(cond)[0] != 0.0:
+                    out[node] = ext
+        return out
+
+    def detect_vdep(self, spec, ctx, x, node_of_slot: List[int]) -> Tuple[bool, ...]:
+        """One detection pass of this instance (the reference's generated stamp! calls
+        ``detect_or_cached!`` per reactive branch, vasim.jl:3427-3437): evaluate the branch
+        charges at the builder's operating point ``x`` and consult / update the context's
+        positional cache.  node_of_slot maps module nodes to circuit nodes."""
+        var = self.model.variant(self.given, None)
+        if not any(var.reactive):
+            return tuple(False for _ in var.branches)
+        xs = np.asarray(x, dtype=np.float64).reshape(-1) if isinstance(x, np.ndarray) else np.zeros(0)
+
+        def xval(i):
+            return float(xs[i - 1]) if 0 < i <= len(xs) else 0.0
+        volt = {name: xval(cn) for name, cn in zip(var.nodes, node_of_slot)}
+        # limit unknowns of THIS instance are allocated next, in order (vasim.jl:3121-3133):
+        # vold = li <= length(x) ? x[li] : 0.0 with li resolved against the context so far
+        vold = {}
+        for b, key in enumerate(var.lim_branches):
+            li = ctx.n_nodes + ctx.n_currents + ctx.n_charges + ctx.n_limits + b + 1
+            vold[key] = xval(li)
+        it = self._interp(spec)
+        it.run(volt, vold)
+        flags = []
+        for bi, key in enumerate(var.branches):
+            if not var.reactive[bi]:
+                flags.append(False)
+                continue
+            q = it.mfactor * it.Q.get(key, 0.0)
+            v = volt[key[0]] - (volt[key[1]] if key[1] is not None else 0.0)
+            flags.append(ctx.detect_or_cached(v, q))
+        return tuple(flags)
+
+    def extra_values(self, variant: VAVariant, spec) -> List[float]:
+        out = []
+        temp = float(getattr(spec, "temp", 27.0))
+        for key in variant.extras:
+            if key[0] == "temperature":
+                out.append(temp + 273.15)
+            elif key[0] == "vt":
+                out.append((temp + 273.15) * 8.617333262e-5)
+            else:
+                out.append(float(getattr(spec, key[1])))
+        return out
+
+
+def _names_in(e) -> List[str]:
+    if not isinstance(e, tuple):
+        return []
+    if e[0] == "var":
+        return [e[1]]
+    out: List[str] = []
+    for x in e[1:]:
+        if isinstance(x, tuple):
+            out += _names_in(x)
+        elif isinstance(x, list):
+            for y in x:
+                out += _names_in(y)
+    return out
 
 
 def va(source: str) -> VAModel:
@@ -919,26 +2068,39 @@ def va(source: str) -> VAModel:
     return VAModel(source)
 
 
+def load_va(path: str) -> VAModel:
+    """A module from a ``.va`` file (e.g. the VADistiller models)."""
+    with open(path) as f:
+        return VAModel(f.read())
+
+
 # --------------------------------------------------------------------------- #
 # per-circuit headers
 # --------------------------------------------------------------------------- #
 _CUDA_PRELUDE = """// generated by cadnip_b200.verilog_a -- Verilog-A device models for lane_kernels.cuh
+#ifndef CB200_VA_FN            /* specialised kernels inline the model; the table-driven set calls it */
+#define CB200_VA_FN __noinline__
+#endif
 #define CB_EXP(x) d_exp(x)
+#define VA_ROUND(x) (((x) >= 0.0) ? floor((x) + 0.5) : ceil((x) - 0.5))
 #define VA_V(k) xval(pg, w, n##k)
 #define VA_PARAM(i) param(pg, w, pb, i)
 #define VA_G(i, j, v) do { if (n##i != 0 && n##j != 0) { w(g) = (v); g++; } } while (0)
 #define VA_C(i, j, v) do { if (n##i != 0 && n##j != 0) { w(c) = (v); c++; } } while (0)
 #define VA_B(i, v) do { if (n##i != 0) { w(b) = (v); b++; } } while (0)
+#define VA_LIMW(bi, v) w(pg.off_limw() + (VA_LIMSLOT(bi) - 1 - (pg.n() - pg.n_limits()))) = (v)
 /* included from lane_kernels.cuh, inside namespace cb200 */
 """
 
 _CUDA_EPILOGUE = """
 #undef CB_EXP
+#undef VA_ROUND
 #undef VA_V
 #undef VA_PARAM
 #undef VA_G
 #undef VA_C
 #undef VA_B
+#undef VA_LIMW
 """
 
 _C_PRELUDE = """/* generated by cadnip_b200.verilog_a -- Verilog-A device models for the CPU oracle */
@@ -946,43 +2108,66 @@ _C_PRELUDE = """/* generated by cadnip_b200.verilog_a -- Verilog-A device models
 typedef struct ora_va_api {
     long (*alloc_internal_node)(void *ctx);
     long (*alloc_charge)(void *ctx, long p, long n);
+    long (*alloc_limit)(void *ctx, long p, long n);
     double (*xval)(void *ctx, long node, const double *x, long nx);
     void (*stamp_G)(void *ctx, long i, long j, double v);
     void (*stamp_C)(void *ctx, long i, long j, double v);
     void (*stamp_b)(void *ctx, long i, double v);
+    void (*record_limit_w)(void *ctx, long l, double w);
+    int (*detect_or_cached)(void *ctx, double v_branch, double q);
+    int (*initjct)(void *ctx);
 } ora_va_api;
 #define CB_EXP(x) exp(x)
+#define VA_ROUND(x) (((x) >= 0.0) ? floor((x) + 0.5) : ceil((x) - 0.5))
 #define VA_V(k) Vn[k]
 #define VA_PARAM(i) par[i]
 #define VA_G(i, j, v) A->stamp_G(ctx, n[i], n[j], (v))
 #define VA_C(i, j, v) A->stamp_C(ctx, n[i], n[j], (v))
 #define VA_B(i, v) A->stamp_b(ctx, n[i], (v))
+#define VA_DETECT(vb, q) A->detect_or_cached(ctx, (vb), (q))
+#define VA_ALLOC_Q(slot, p, nn) n[slot] = A->alloc_charge(ctx, n[p], (nn) < 0 ? 0 : n[(nn) < 0 ? 0 : (nn)])
 """
 
 
-def cuda_header(models: Sequence[VAModel]) -> str:
-    """All models of a circuit + the dispatcher ``va_dispatch<PASS>(pg, w, d, model, t)``."""
+def _limw_define(v: VAVariant, target: str) -> str:
+    if target == "cuda":
+        sel = " : ".join(f"(bi) == {b} ? n{v.lim_slot[b]}" for b in range(len(v.lim_branches)))
+        return f"#define VA_LIMSLOT(bi) ({sel + ' : 0' if sel else '0'})\n"
+    sel = " : ".join(f"(bi) == {b} ? n[{v.lim_slot[b]}]" for b in range(len(v.lim_branches)))
+    return (f"#define VA_LIMW(bi, v) A->record_limit_w(ctx, ({sel + ' : 0' if sel else '0'}), (v))\n")
+
+
+def cuda_header(models: Sequence[VAVariant]) -> str:
+    """All model variants of a circuit + ``va_dispatch<PASS>(pg, w, d, model, t, mode, initjct)``."""
     out = [_CUDA_PRELUDE]
     for m in models:
-        out.append(m.emit_cuda())
+        m = m.default if isinstance(m, VAModel) else m
+        out.append(_limw_define(m, "cuda") + m.emit_cuda() + "#undef VA_LIMSLOT\n")
     out.append("template <int PASS, typename PG, typename W>\n"
-               "__device__ __forceinline__ void va_dispatch(const PG &pg, W &w, int d, int model, double t)\n{\n"
+               "__device__ __forceinline__ void va_dispatch(const PG &pg, W &w, int d, int model, double t,\n"
+               "                                            int mode, bool initjct)\n{\n"
                "    switch (model) {")
     for i, m in enumerate(models):
-        out.append(f"    case {i}: va_stamp_{m.cname}<PASS>(pg, w, d, t); break;")
+        m = m.default if isinstance(m, VAModel) else m
+        out.append(f"    case {i}: va_stamp_{m.cname}<PASS>(pg, w, d, t, mode, initjct); break;")
     out.append("    default: break;\n    }\n}")
     out.append(_CUDA_EPILOGUE)
     return "\n".join(out)
 
 
-def c_source(models: Sequence[VAModel]) -> str:
+def c_source(models: Sequence[VAVariant]) -> str:
+    """The oracle's C: one function per MODULE + given-set (the oracle makes its own collapse
+    and charge-formulation decisions, so detection outcomes do not select code here)."""
     out = [_C_PRELUDE]
+    names = []
     for m in models:
-        out.append(m.emit_c())
-    out.append("typedef void (*ora_va_fn)(const ora_va_api *, void *, const int *, const double *, const double *, long, double);")
-    out.append(f"int ora_va_count(void) {{ return {len(models)}; }}")
+        m = m.default if isinstance(m, VAModel) else m
+        out.append(_limw_define(m, "c") + m.emit_c() + "#undef VA_LIMW\n")
+        names.append(m.cname)
+    out.append("typedef void (*ora_va_fn)(const ora_va_api *, void *, const int *, const double *, const double *, long, double, int);")
+    out.append(f"int ora_va_count(void) {{ return {len(names)}; }}")
     out.append("ora_va_fn ora_va_table(int i)\n{\n    switch (i) {")
-    for i, m in enumerate(models):
-        out.append(f"    case {i}: return ora_va_{m.cname};")
+    for i, n in enumerate(names):
+        out.append(f"    case {i}: return ora_va_{n};")
     out.append("    default: return 0;\n    }\n}")
     return "\n".join(out)

@@ -57,6 +57,10 @@ struct ora_ctx {
     int64_t lenG, lenC, lenb;
     int64_t G_pos, C_pos, b_pos, current_pos, limit_pos, charge_pos, internal_pos;
     int64_t n_user_nodes;             /* nodes the builder allocated with get_node! */
+    /* voltage-dependent-charge detection cache (context.jl:338-341, value_only.jl:77-78) */
+    int *charge_is_vdep; double *charge_Q_values, *charge_V_values;
+    int64_t n_det, cap_det, charge_detection_pos;
+    int mode;                         /* spec.mode of the builder call in progress */
 };
 
 static void *xrealloc(void *p, size_t sz)
@@ -80,6 +84,7 @@ void ora_ctx_free(ora_ctx *c)
     free(c->C_I); free(c->C_J); free(c->C_V);
     free(c->b_I); free(c->b_V);
     free(c->limit_init); free(c->limit_w);
+    free(c->charge_is_vdep); free(c->charge_Q_values); free(c->charge_V_values);
     free(c);
 }
 
@@ -90,6 +95,7 @@ static void ctx_reset_for_restamping(ora_ctx *c, int64_t n_nodes_prealloc)
     c->n_user_nodes = n_nodes_prealloc;
     c->n_currents = 0; c->n_charges = 0; c->n_limits = 0;
     c->nG = c->nC = c->nb = 0;
+    c->charge_detection_pos = 1;     /* the detection cache itself persists (context.jl:1582) */
 }
 
 /* resolve_index  context.jl:577-581 / value_only.jl:214-231 */
@@ -405,19 +411,26 @@ static double diode_junction_cap(double V, double Cj0, double Vj, double m)
 typedef struct ora_va_api {
     long (*alloc_internal_node)(void *ctx);
     long (*alloc_charge)(void *ctx, long p, long n);
+    long (*alloc_limit)(void *ctx, long p, long n);
     double (*xval)(void *ctx, long node, const double *x, long nx);
     void (*stamp_G)(void *ctx, long i, long j, double v);
     void (*stamp_C)(void *ctx, long i, long j, double v);
     void (*stamp_b)(void *ctx, long i, double v);
+    void (*record_limit_w)(void *ctx, long l, double w);
+    int (*detect_or_cached)(void *ctx, double v_branch, double q);
+    int (*initjct)(void *ctx);
 } ora_va_api;
-typedef void (*ora_va_fn)(const ora_va_api *, void *, const int *, const double *, const double *, long, double);
+typedef void (*ora_va_fn)(const ora_va_api *, void *, const int *, const double *, const double *, long,
+                          double, int);
 static ora_va_fn (*g_va_table)(int) = NULL;
 
 void ora_set_va_table(void *table_fn) { g_va_table = (ora_va_fn (*)(int))table_fn; }
 
+#define VA_LIM_BASE (1L << 30)        /* handles <= -VA_LIM_BASE: limit unknown -(h) - VA_LIM_BASE */
 static mna_index va_index(long h)
 {
     if (h > 0) return ix_make(IX_NODE, h);
+    if (h <= -VA_LIM_BASE) return ix_make(IX_LIMIT, -h - VA_LIM_BASE);
     if (h < 0) return ix_make(IX_CHARGE, -h);
     return ix_make(IX_GROUND, 0);
 }
@@ -438,19 +451,64 @@ static long va_alloc_charge(void *vc, long p, long n)
     c->n_charges += 1;
     return -(long)c->n_charges;
 }
-/* V_k = node_k == 0 ? 0.0 : x[node_k], tolerant of an x shorter than the system
- * (vasim.jl:3123-3133)                                                             */
+/* alloc_limit!(ctx, name, instance, p, n; init=0.0)  vasim.jl:3121 */
+static long va_alloc_limit(void *vc, long p, long n)
+{
+    (void)p; (void)n;
+    mna_index l = alloc_limit((ora_ctx *)vc, 0.0);
+    return -(VA_LIM_BASE + (long)l.k);
+}
+/* V_k = node_k == 0 ? 0.0 : x[node_k]; limit unknowns: vold = li <= length(x) ? x[li] : 0.0,
+ * both tolerant of an x shorter than the system (vasim.jl:3123-3133)                  */
 static double va_xval(void *vc, long node, const double *x, long nx)
 {
-    (void)vc;
+    if (node <= -VA_LIM_BASE) {
+        int64_t li = resolve_index((ora_ctx *)vc, va_index(node));
+        if (x == NULL || nx == 0 || li > nx) return 0.0;
+        return x[li - 1];
+    }
     if (node <= 0 || x == NULL || nx == 0 || node > nx) return 0.0;
     return x[node - 1];
 }
 static void va_stamp_G(void *vc, long i, long j, double v) { stamp_G((ora_ctx *)vc, va_index(i), va_index(j), v); }
 static void va_stamp_C(void *vc, long i, long j, double v) { stamp_C((ora_ctx *)vc, va_index(i), va_index(j), v); }
 static void va_stamp_b(void *vc, long i, double v) { stamp_b((ora_ctx *)vc, va_index(i), v); }
-static const ora_va_api g_va_api = {va_alloc_internal_node, va_alloc_charge, va_xval,
-                                    va_stamp_G, va_stamp_C, va_stamp_b};
+static void va_record_limit_w(void *vc, long l, double w) { record_limit_w((ora_ctx *)vc, va_index(l), w); }
+/* detect_or_cached!  contrib.jl:214-296 */
+static int va_detect_or_cached(void *vc, double V, double Q)
+{
+    ora_ctx *c = (ora_ctx *)vc;
+    int64_t pos = c->charge_detection_pos++;
+    if (c->direct) return c->charge_is_vdep[pos - 1];
+    if (pos > c->n_det) {                                   /* first run: assume linear */
+        if (c->n_det + 1 > c->cap_det) {
+            c->cap_det = c->cap_det ? 2 * c->cap_det : 8;
+            c->charge_is_vdep = (int *)xrealloc(c->charge_is_vdep, sizeof(int) * c->cap_det);
+            c->charge_Q_values = (double *)xrealloc(c->charge_Q_values, sizeof(double) * c->cap_det);
+            c->charge_V_values = (double *)xrealloc(c->charge_V_values, sizeof(double) * c->cap_det);
+        }
+        c->charge_is_vdep[c->n_det] = 0;
+        c->charge_Q_values[c->n_det] = Q;
+        c->charge_V_values[c->n_det] = V;
+        c->n_det += 1;
+        return 0;
+    }
+    double Vs = c->charge_V_values[pos - 1], Qs = c->charge_Q_values[pos - 1];
+    const double V_min = 1e-6;
+    if (fabs(V) > V_min && fabs(Vs) > V_min) {
+        double Cc = Q / V, Cs = Qs / Vs;
+        double diff = fabs(Cc - Cs), maxC = fmax(fabs(Cc), fabs(Cs));
+        int different = diff > 1e-15 && (maxC < 1e-30 || diff / maxC > 1e-6);
+        if (different) c->charge_is_vdep[pos - 1] = 1;      /* sticky */
+    }
+    c->charge_Q_values[pos - 1] = Q;
+    c->charge_V_values[pos - 1] = V;
+    return c->charge_is_vdep[pos - 1];
+}
+static int va_initjct(void *vc) { return ((ora_ctx *)vc)->initjct; }
+static const ora_va_api g_va_api = {va_alloc_internal_node, va_alloc_charge, va_alloc_limit, va_xval,
+                                    va_stamp_G, va_stamp_C, va_stamp_b, va_record_limit_w,
+                                    va_detect_or_cached, va_initjct};
 
 /* ------------------------------------------------------------------------- */
 /* the builder: one stamp! call per netlist row, in order                      */
@@ -626,7 +684,7 @@ static void run_builder(const ora_netlist *nl, const ora_spec *spec, double t,
         case ORA_DEV_VA: {                /* generated VA stamp!, vasim.jl:2993-3985 */
             ora_va_fn fn = g_va_table ? g_va_table(flags) : NULL;
             if (!fn) { fprintf(stderr, "cadnip_oracle: VA model %d not registered\n", flags); abort(); }
-            fn(&g_va_api, c, nd, par, x, (long)nx, t);
+            fn(&g_va_api, c, nd, par, x, (long)nx, t, spec->mode);
         } break;
         default:
             fprintf(stderr, "cadnip_oracle: unknown device kind %d\n", nl->kind[d]);
@@ -767,6 +825,7 @@ struct ora_structure {
     double *G_nz0, *C_nz0;             /* values at discovery (padded to pattern) */
     int64_t *G_coo_to_idx, *C_coo_to_idx, *b_deferred_resolved, *G_diag_idx;
     double *limit_init;
+    int *charge_is_vdep; int64_t n_det;     /* detection outcome, replayed positionally */
 };
 
 /* compute_coo_to_nz_mapping  precompile.jl:253-283 : search the column */
@@ -833,6 +892,9 @@ ora_structure *ora_compile_structure(const ora_netlist *nl, const ora_spec *spec
     }
     s->limit_init = (double *)calloc((size_t)s->n_limits + 1, sizeof(double));
     for (int64_t k = 0; k < s->n_limits; k++) s->limit_init[k] = ctx0->limit_init[k];
+    s->n_det = ctx0->n_det;
+    s->charge_is_vdep = (int *)calloc((size_t)s->n_det + 1, sizeof(int));
+    for (int64_t k = 0; k < s->n_det; k++) s->charge_is_vdep[k] = ctx0->charge_is_vdep[k];
     free(GI); free(GJ); free(ones); free(pat_nz);
     return s;
 }
@@ -842,7 +904,7 @@ void ora_structure_free(ora_structure *s)
     if (!s) return;
     free(s->colptr); free(s->rowval); free(s->G_nz0); free(s->C_nz0);
     free(s->G_coo_to_idx); free(s->C_coo_to_idx); free(s->b_deferred_resolved);
-    free(s->G_diag_idx); free(s->limit_init);
+    free(s->G_diag_idx); free(s->limit_init); free(s->charge_is_vdep);
     free(s);
 }
 
@@ -903,6 +965,7 @@ ora_workspace *ora_create_workspace(const ora_structure *s)
     d->G_mapping = s->G_coo_to_idx; d->C_mapping = s->C_coo_to_idx;
     d->lenG = s->nG; d->lenC = s->nC; d->lenb = s->nb;
     for (int64_t k = 0; k < s->n_limits; k++) w->limit_w[k] = s->limit_init[k];
+    d->charge_is_vdep = s->charge_is_vdep; d->n_det = s->n_det;   /* value_only.jl:133 */
     return w;
 }
 
@@ -919,7 +982,7 @@ static void reset_direct_stamp(ora_workspace *w, const ora_structure *s)
 {
     ora_ctx *d = &w->dctx;
     d->G_pos = 1; d->C_pos = 1; d->b_pos = 1; d->current_pos = 1; d->limit_pos = 1;
-    d->charge_pos = 1; d->internal_pos = 0;
+    d->charge_pos = 1; d->internal_pos = 0; d->charge_detection_pos = 1;
     memset(w->G_nz, 0, sizeof(double) * s->nnz);
     memset(w->C_nz, 0, sizeof(double) * s->nnz);
     memset(w->b, 0, sizeof(double) * s->n);

@@ -342,9 +342,12 @@ def load_va_models(models) -> None:
     is the position in ``models`` (== dev_flags of the lowered circuit)."""
     import hashlib
     import sys
-    sys.path.insert(0, os.path.dirname(_HERE))
-    import cadnip_b200.verilog_a as va
-    src = va.c_source(models)
+    if isinstance(models, str):                  # LoweredCircuit.va_c_source
+        src = models
+    else:
+        sys.path.insert(0, os.path.dirname(_HERE))
+        import cadnip_b200.verilog_a as va
+        src = va.c_source(models)
     gen = os.path.join(_HERE, "_gen")
     os.makedirs(gen, exist_ok=True)
     h = hashlib.sha256(src.encode()).hexdigest()[:16]

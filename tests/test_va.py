@@ -108,11 +108,6 @@ module JunctionCap(p, n);
 endmodule""")                                   # va_mosfet.jl:465-484
 
 
-# model lists (in lowering order) of the GPU tests below: __graft_entry__.build() pre-builds
-# their kernel sets so the GPU box finds them in the in-tree cache
-GPU_MODEL_SETS = [[PMOS, SimpleMOS], [CapMOS, JunctionCap], [ChainDiodeRs]]
-
-
 def B(f):
     def build(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
         ctx = MNAContext() if ctx is None else ctx
@@ -151,7 +146,7 @@ def chain(ctx, params):
 
 def oracle_dc(builder, mode="dcop", **params):
     lc = cb.lower_circuit(cb.MNACircuit(builder, **params))
-    ora.load_va_models(lc.va_models)
+    ora.load_va_models(lc.va_c_source)
     nl = ora.OracleNetlist(lc.netlist_tables())
     x, ok, it = ora.solve_dc(nl, ora.make_spec(mode=mode))
     return lc, nl, x, ok
@@ -174,7 +169,7 @@ def test_parser_and_structure():
         with pytest.raises(cb.VAError):
             cb.va(bad)
     src = SimpleMOS.emit_cuda()
-    assert "va_stamp_SimpleMOS_" in src and "VA_G(0, 0, I0_d0);" in src and "VA_B(2, Ieq);" in src
+    assert "va_stamp_SimpleMOS_" in src and "VA_G(0, 0, dI0);" in src and "VA_B(2, Ieq);" in src
 
 
 # ---- known answers through the oracle -------------------------------------------
@@ -199,7 +194,7 @@ def test_vaddiode_current_known_answer():
 
 def test_chain_internal_nodes_carry_no_anchor_current():
     lc = cb.lower_circuit(cb.MNACircuit(B(chain)))
-    ora.load_va_models(lc.va_models)
+    ora.load_va_models(lc.va_c_source)
     nl = ora.OracleNetlist(lc.netlist_tables())
     S = ora.Structure(nl, ora.make_spec(mode="dcop"))
     assert lc.node_names[4:] == ["d1_ChainDiodeRs_a_int", "d2_ChainDiodeRs_a_int", "d3_ChainDiodeRs_a_int"]
@@ -247,7 +242,7 @@ def test_capmos_dc_and_gate_charging():
         stamp(VoltageSource(3.0, name="Vd"), ctx, d, 0)
         stamp(CapMOS(K=1e-3, Vth=0.5, Cgs=Cgs, Cgd=Cgd), ctx, d, g, 0)
     lc = cb.lower_circuit(cb.MNACircuit(B(f)))
-    ora.load_va_models(lc.va_models)
+    ora.load_va_models(lc.va_c_source)
     nl = ora.OracleNetlist(lc.netlist_tables())
     tau = Rg * (Cgs + Cgd)
     u0 = np.zeros(lc.n); u0[lc.index_of("vin") - 1] = 2.0; u0[lc.index_of("d") - 1] = 3.0   # gate starts at 0 V
@@ -266,7 +261,7 @@ def test_voltage_dependent_charge_uses_charge_state_formulation():
         stamp(JunctionCap(Cj0=1e-12, phi=0.8, m=0.5, name="J1"), ctx, p, 0)
     lc = cb.lower_circuit(cb.MNACircuit(B(f)))
     assert lc.n_charges == 1 and lc.charge_names == ["J1_JunctionCap_Q_p_n"] and lc.n == 3
-    ora.load_va_models(lc.va_models)
+    ora.load_va_models(lc.va_c_source)
     nl = ora.OracleNetlist(lc.netlist_tables())
     S = ora.Structure(nl, ora.make_spec(mode="tran"))
     assert S.n_charges == 1
@@ -293,7 +288,7 @@ def test_voltage_dependent_charge_uses_charge_state_formulation():
 def _sweep_vs_oracle(cs, tran=None):
     params, P = cs.lane_params()
     lc = cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P)
-    ora.load_va_models(lc.va_models)
+    ora.load_va_models(lc.va_c_source)
     nl = ora.OracleNetlist(lc.netlist_tables())
     comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
     out = {}
@@ -318,9 +313,38 @@ def _close(a, b, rtol=1e-9, atol=1e-12):
     return np.all(np.abs(a - b) <= atol + rtol * np.maximum(np.abs(a), np.abs(b)))
 
 
+def _capmos_stage(ctx, params):
+    d = get_node(ctx, "d"); g = get_node(ctx, "g"); vin = get_node(ctx, "vin"); vdd = get_node(ctx, "vdd")
+    stamp(VoltageSource(0.0, tran=cb.PulseWave(0.0, 2.0, 1e-9, 1e-9, 1e-9, 20e-9, 60e-9), name="Vin"), ctx, vin, 0)
+    stamp(VoltageSource(3.0, name="Vdd"), ctx, vdd, 0)
+    stamp(Resistor(params.rg, name="Rg"), ctx, vin, g)
+    stamp(Resistor(2e3, name="Rd"), ctx, vdd, d)
+    stamp(CapMOS(K=params.k, Vth=0.5, Cgs=1e-12, Cgd=0.5e-12), ctx, d, g, 0)
+    stamp(JunctionCap(Cj0=2e-13, phi=0.8, m=0.5, name="Jdb"), ctx, 0, d)     # reverse-biased drain junction
+
+
+GPU_SWEEPS = {
+    "inverter": lambda: cb.CircuitSweep(inverter(0.0), cb.ProductSweep(vin=np.linspace(0.0, 3.0, 13),
+                                                                        kn=[0.5e-3, 1e-3, 2e-3])),
+    "capmos": lambda: cb.CircuitSweep(B(_capmos_stage), cb.ProductSweep(rg=[500.0, 1e3, 2e3], k=[0.5e-3, 1e-3])),
+    "chain": lambda: cb.CircuitSweep(B(chain), cb.Sweep(dummy=[0.0, 1.0]), dummy=0.0),
+}
+
+
+def gpu_va_headers():
+    """Emitted CUDA headers of the GPU tests' circuits: __graft_entry__.build() pre-builds their
+    kernel sets so the GPU box finds them in the in-tree cache."""
+    out = []
+    for make in GPU_SWEEPS.values():
+        cs = make()
+        params, P = cs.lane_params()
+        out.append(cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P).va_cuda_header)
+    return out
+
+
 @pytest.mark.gpu
 def test_gpu_va_inverter_sweep_dc_and_transient():
-    cs = cb.CircuitSweep(inverter(0.0), cb.ProductSweep(vin=np.linspace(0.0, 3.0, 13), kn=[0.5e-3, 1e-3, 2e-3]))
+    cs = GPU_SWEEPS["inverter"]()
     lc, out = _sweep_vs_oracle(cs)
     x, xo, st, sto = out["dc"]
     assert np.array_equal(st, sto) and (st == 0).all()
@@ -333,15 +357,7 @@ def test_gpu_va_inverter_sweep_dc_and_transient():
 @pytest.mark.gpu
 @pytest.mark.parametrize("spec", [False, True], ids=["table", "specialised"])
 def test_gpu_va_capmos_transient(spec):
-    def f(ctx, params):
-        d = get_node(ctx, "d"); g = get_node(ctx, "g"); vin = get_node(ctx, "vin"); vdd = get_node(ctx, "vdd")
-        stamp(VoltageSource(0.0, tran=cb.PulseWave(0.0, 2.0, 1e-9, 1e-9, 1e-9, 20e-9, 60e-9), name="Vin"), ctx, vin, 0)
-        stamp(VoltageSource(3.0, name="Vdd"), ctx, vdd, 0)
-        stamp(Resistor(params.rg, name="Rg"), ctx, vin, g)
-        stamp(Resistor(2e3, name="Rd"), ctx, vdd, d)
-        stamp(CapMOS(K=params.k, Vth=0.5, Cgs=1e-12, Cgd=0.5e-12), ctx, d, g, 0)
-        stamp(JunctionCap(Cj0=2e-13, phi=0.8, m=0.5, name="Jdb"), ctx, 0, d)     # reverse-biased drain junction
-    cs = cb.CircuitSweep(B(f), cb.ProductSweep(rg=[500.0, 1e3, 2e3], k=[0.5e-3, 1e-3]))
+    cs = GPU_SWEEPS["capmos"]()
     lc, out = _sweep_vs_oracle(cs, tran=((0.0, 4e-8), 2e-10, "trap", spec))
     assert lc.n_charges == 1
     gpu, ref, r, ro, is_spec = out["tran"]
@@ -355,7 +371,7 @@ def test_gpu_va_capmos_transient(spec):
 
 @pytest.mark.gpu
 def test_gpu_va_chain_dc():
-    cs = cb.CircuitSweep(B(chain), cb.Sweep(dummy=[0.0, 1.0]), dummy=0.0)
+    cs = GPU_SWEEPS["chain"]()
     lc, out = _sweep_vs_oracle(cs)
     x, xo, st, sto = out["dc"]
     # a floating chain end behind pA junctions: the operating point is determined only to
@@ -371,8 +387,8 @@ def test_gpu_va_chain_dc():
 def test_gpu_va_requires_models():
     from cadnip_b200 import backend
     lc = cb.lower_circuit(cb.MNACircuit(mos_bias(SimpleMOS, 1.5, 2.0)))
-    models = lc.va_models
-    lc.va_models = []                    # handle created without loading the emitted models
+    models = lc.va_cuda_header
+    lc.va_cuda_header = ""               # handle created without loading the emitted models
     h = backend.Handle(lc)
     try:
         h.set_lanes(lc.lane_soa, 1)
@@ -380,4 +396,4 @@ def test_gpu_va_requires_models():
             h.dc(cb.MNASpec(mode="dcop"))
     finally:
         h.close()
-        lc.va_models = models
+        lc.va_cuda_header = models

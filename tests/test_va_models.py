@@ -1,0 +1,295 @@
+"""The reference's VADistiller models (sp_mos1, sp_diode: $limit / PCNR, node collapse,
+$param_given, analog functions, charge detection) through the emitter.  Circuits come from
+the committed fixtures (tests/golden/va_*.pkl.gz, made by tests/golden/make_va_fixtures.py from
+the reference's .va files); known answers are the reference's own (test/params.jl,
+test/sweep.jl, test/mna/oscillator_test.jl)."""
+import gzip
+import math
+import os
+import pickle
+import subprocess
+
+import numpy as np
+import pytest
+
+import cadnip_b200 as cb
+import cadnip_oracle as ora
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HAVE_REF = os.path.isdir("/root/reference/models/VADistillerModels.jl/va")
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
+
+FIXTURE_NAMES = ["mos1_corner", "diode_chain", "diode_rs_cap", "mos1_inverter", "mos1_ring", "mos1_ring_caps"]
+
+
+GPU_FIXTURES = ["mos1_corner", "diode_chain", "mos1_inverter", "diode_rs_cap", "mos1_ring"]   # used by -m gpu tests
+
+
+def fixture(name):
+    with gzip.open(os.path.join(HERE, "golden", f"va_{name}.pkl.gz"), "rb") as f:
+        return pickle.load(f)
+
+
+def oracle_of(lc):
+    ora.load_va_models(lc.va_c_source)
+    return ora.OracleNetlist(lc.netlist_tables())
+
+
+# ---- emitter over the reference's model files ---------------------------------------
+@needs_ref
+@pytest.mark.parametrize("name", ["resistor", "capacitor", "diode", "mos1", "mos2", "mos3", "mos6", "mos9",
+                                  "jfet1", "mes1"])
+def test_vadistiller_model_emits_compilable_c(name, tmp_path):
+    from cadnip_b200 import verilog_a
+    import va_circuits
+    m = verilog_a.load_va(va_circuits.VA_DIR + name + ".va")
+    v = m.default
+    assert v.nodes[:len(m.ports)] == m.ports
+    src = verilog_a.c_source([v])
+    c = tmp_path / "m.c"
+    c.write_text(src)
+    subprocess.run(["gcc", "-O0", "-fsyntax-only", "-Wall", "-Werror=implicit-function-declaration", str(c)],
+                   check=True)
+    assert f"va_stamp_{v.cname}" in verilog_a.cuda_header([v])
+
+
+@needs_ref
+def test_sp_mos1_structure():
+    from cadnip_b200 import verilog_a
+    import va_circuits
+    m = verilog_a.load_va(va_circuits.VA_DIR + "mos1.va")
+    v = m.default
+    assert v.nodes == ["d", "g", "s", "b", "d_int", "s_int"]
+    # one limit unknown per unique $limit probe branch, 8 call sites (mos1.va:919-922, :976-979)
+    assert v.lim_branches == [("g", "s_int"), ("d_int", "s_int"), ("b", "s_int"), ("b", "d_int")]
+    assert len(v.sites) == 8
+    # node-to-ground contributions first, then the three noise branches (mos1.va:1164-1221)
+    assert v.branches[:6] == [(n, None) for n in ("d", "g", "s", "b", "d_int", "s_int")]
+    assert v.branches[6:] == [("d_int", "d"), ("s_int", "s"), ("d_int", "s_int")]
+    assert v.reactive == [False, True, False, True, True, True, False, False, False]
+    assert set(m.collapses) == {"d_int", "s_int"}           # V(d_int,d) <+ 0 / V(s_int,s) <+ 0
+    inst = m(type=1, vto=0.7, kp=1e-4, w=1e-6, l=1e-6)
+    assert inst.collapsed(cb.MNASpec()) == {"d_int": "d", "s_int": "s"}
+    assert m(type=1, rd=10.0).collapsed(cb.MNASpec()) == {"s_int": "s"}
+    assert m(VTO=0.7).given == frozenset({"vto"}) and m(vt0=0.7).given == frozenset({"vto"})   # aliasparam
+
+
+@needs_ref
+@pytest.mark.parametrize("name", FIXTURE_NAMES)
+def test_fixtures_are_current(name):
+    import va_circuits
+    lc = va_circuits.lower_fixture(name)
+    fx = fixture(name)
+    assert lc.va_cuda_header == fx.va_cuda_header and lc.va_c_source == fx.va_c_source
+    assert np.array_equal(lc.G_I, fx.G_I) and np.array_equal(lc.dev_nodes, fx.dev_nodes)
+    assert np.array_equal(lc.lane_soa, fx.lane_soa) and np.array_equal(lc.uniform, fx.uniform)
+
+
+# ---- host structure == oracle structure -----------------------------------------------
+@pytest.mark.parametrize("name", FIXTURE_NAMES)
+def test_host_coo_matches_oracle_builder(name):
+    """The oracle runs the emitted C as the builder (it allocates its own internal nodes,
+    limit and charge unknowns, evaluates the collapse conditions and detects
+    voltage-dependent charges over 5 passes); the host derives the same from the stamp plan."""
+    lc = fixture(name)
+    nl = oracle_of(lc)
+    S = ora.Structure(nl, ora.make_spec(mode="tran"))
+    assert (S.n, S.n_nodes, S.n_charges, S.n_limits) == (lc.n, lc.n_nodes, lc.n_charges, lc.n_limits)
+    coo = S.coo()
+    for k in ("G_I", "G_J", "C_I", "C_J", "b_I"):
+        assert np.array_equal(coo[k], getattr(lc, k)), k
+
+
+def test_sp_mos1_unknown_count():
+    lc = fixture("mos1_inverter")
+    # 4 nodes + 3 source currents + 2 x 4 limit unknowns; zero device caps -> no charge states
+    assert (lc.n_nodes, lc.n_currents, lc.n_charges, lc.n_limits) == (4, 3, 0, 8)
+    assert lc.limit_names[:4] == ["MP_sp_mos1_lim_g_s_int", "MP_sp_mos1_lim_d_int_s_int",
+                                  "MP_sp_mos1_lim_b_s_int", "MP_sp_mos1_lim_b_d_int"]
+    assert fixture("mos1_ring_caps").n_charges > 0
+
+
+# ---- known answers ------------------------------------------------------------------------
+def test_mos1_square_law_known_answer():
+    """test/params.jl:686-712: V(drain) = 5 - 10e3 * 1/2 kp 20 (1.2 - vto)^2, atol 1e-6."""
+    lc = fixture("mos1_corner")
+    nl = oracle_of(lc)
+    x, st, it = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
+    assert (st == 0).all() and it.max() <= 10
+    vd = x[:, lc.index_of("drain") - 1].reshape(2, 3)
+    for j, kp in enumerate((100e-6, 50e-6)):
+        for i, vto in enumerate((0.6, 0.7, 0.9)):
+            assert vd[j, i] == pytest.approx(5 - 10e3 * 0.5 * kp * 20 * (1.2 - vto) ** 2, abs=1e-6)
+
+
+def test_sp_diode_chain_sweep_known_answer():
+    """test/sweep.jl:334-353: 40 points converge, n1 monotone in the supply, clamped near 3 x 0.7 V."""
+    lc = fixture("diode_chain")
+    nl = oracle_of(lc)
+    x, st, it = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
+    assert (st == 0).all()
+    n1 = x[:, lc.index_of("n1") - 1]
+    assert np.all(np.diff(n1) > 0) and 1.5 < n1[-1] < 2.5
+    # Shockley law at the solved point: I = Is (exp(V/(n kT/q)) - 1) + gmin V per junction
+    i = -x[:, lc.index_of("I_v1") - 1]
+    vt = 1.38064852e-23 / 1.6021766208e-19 * 300.15
+    v3 = x[:, lc.index_of("n3") - 1]
+    assert np.allclose(i, 1e-14 * np.expm1(v3 / vt) + 1e-12 * v3, rtol=1e-6, atol=1e-15)
+    # limit unknowns settle on their probe voltages (PCNR fixed point)
+    assert np.allclose(x[:, lc.index_of("d3_sp_diode_lim_a_int_c") - 1], v3, atol=1e-9)
+
+
+def _ring_u0(lc):
+    u0 = np.zeros(lc.n)
+    u0[lc.index_of("vdd") - 1] = 3.3
+    u0[lc.index_of("out1") - 1] = 3.3                     # asymmetric start (UIC)
+    return u0
+
+
+@pytest.mark.parametrize("name", ["mos1_ring", "mos1_ring_caps"])
+def test_ring_oscillator_known_answer(name):
+    """test/mna/oscillator_test.jl:73-160: swing > 2 V on 3.3 V, rails reached, period 0.5-50 ns."""
+    lc = fixture(name)
+    nl = oracle_of(lc)
+    save = [lc.index_of(n) for n in ("out1", "out2", "in1")]
+    o = ora.make_tran_opts(method=1, dt=5e-12, init=1)
+    r = ora.tran(nl, ora.make_spec(mode="tran"), 0.0, 20e-9, o, save, u0=_ring_u0(lc))
+    assert r["status"] == 0
+    t, u = r["t"], r["u"]
+    late = t > 10e-9
+    for k in range(3):
+        v = u[late, k]
+        assert v.max() - v.min() > 2.0 and v.max() > 2.5 and v.min() < 0.8
+    v = u[late, 0]
+    mid = 0.5 * (v.max() + v.min())
+    crossings = np.count_nonzero(np.diff((v > mid).astype(int)))
+    period = 2 * (t[late][-1] - t[late][0]) / crossings
+    assert 0.05e-9 < period < 50e-9
+
+
+# ---- emitted derivatives against finite differences ------------------------------------------
+@pytest.mark.parametrize("name", ["mos1_inverter", "diode_rs_cap", "mos1_ring_caps"])
+def test_emitted_jacobian_matches_finite_differences(name):
+    """F(u) = G(u) u - b(u) is the sum of branch currents; with the limit unknowns on their
+    probe voltages (no limiting active) dF/du must equal the stamped G."""
+    lc = fixture(name)
+    nl = oracle_of(lc)
+    S = ora.Structure(nl, ora.make_spec(mode="tran"))
+    rng = np.random.default_rng(7)
+    n = S.n
+    for trial in range(3):
+        u = np.zeros(n)
+        u[:lc.n_nodes] = rng.uniform(0.2, 2.5, lc.n_nodes)
+
+        def settle(u):
+            # put every limit unknown on its probe voltage: x_lim = V_p - V_n
+            for k, (p, q) in enumerate(lc_limit_branches(lc)):
+                u[n - lc.n_limits + k] = (u[p - 1] if p else 0.0) - (u[q - 1] if q else 0.0)
+            return u
+
+        def F(u):
+            G, C, b, _ = S.rebuild(settle(u.copy()))
+            return S.dense(G) @ settle(u.copy()) - b
+        u = settle(u)
+        G, C, b, _ = S.rebuild(u)
+        Gd = S.dense(G)
+        for j in range(lc.n_nodes):
+            h = 1e-6
+            up, um = u.copy(), u.copy()
+            up[j] += h; um[j] -= h
+            dF = (F(up) - F(um)) / (2 * h)
+            # total derivative along "limit unknowns follow their probes": G[:, j] + G[:, lim] dlim/du_j
+            col = Gd[:, j].copy()
+            for k, (p, q) in enumerate(lc_limit_branches(lc)):
+                s = (1.0 if p == j + 1 else 0.0) - (1.0 if q == j + 1 else 0.0)
+                col += Gd[:, n - lc.n_limits + k] * s
+            rows = [i for i in range(lc.n_nodes)]
+            # central differences on currents of size |G|max * |u|: absolute floor ~1e-8 of that
+            scale = np.abs(Gd[:lc.n_nodes, :lc.n_nodes]).max() + 1e-12
+            assert np.allclose(dF[rows], col[rows], rtol=1e-5, atol=1e-8 * scale), (name, trial, j)
+
+
+def lc_limit_branches(lc):
+    """(p, n) circuit nodes of each limit unknown, from its tracking row G[l,l]=1, G[l,p]=-1, G[l,n]=+1."""
+    lim0 = lc.n - lc.n_limits
+    out = [[0, 0] for _ in range(lc.n_limits)]
+    seen = [0] * lc.n_limits
+    for i, j in zip(lc.G_I, lc.G_J):
+        if i > lim0 and j <= lc.n_nodes and seen[i - lim0 - 1] < 2:
+            k = i - lim0 - 1
+            out[k][seen[k]] = int(j)
+            seen[k] += 1
+    return [tuple(x) for x in out]
+
+
+# ---- GPU parity ------------------------------------------------------------------------------
+def _close(a, b, rtol=1e-9, atol=1e-12):
+    return bool(np.all(np.abs(a - b) <= atol + rtol * np.maximum(np.abs(a), np.abs(b))))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mos1_corner", "diode_chain", "mos1_inverter"])
+def test_gpu_va_models_dc(name):
+    lc = fixture(name)
+    nl = oracle_of(lc)
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        x, st, it = comp.dc()
+    finally:
+        comp.close()
+    xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
+    assert np.array_equal(st, sto) and (st == 0).all()
+    assert _close(x.T, xo, rtol=1e-8, atol=1e-10), float(np.max(np.abs(x.T - xo)))
+    assert np.array_equal(it, ito)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,tspan,dt,method,spec", [
+    ("mos1_inverter", (0.0, 10e-9), 1e-11, "trap", False),
+    ("mos1_inverter", (0.0, 10e-9), 1e-11, "be", True),
+    ("diode_rs_cap", (0.0, 10e-9), 1e-11, "trap", True),
+])
+def test_gpu_va_models_transient(name, tspan, dt, method, spec):
+    lc = fixture(name)
+    nl = oracle_of(lc)
+    save = list(range(1, lc.n + 1))
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        wave = comp.tran(tspan, dt, method=method, save_idxs=save, specialize=spec)
+        r = wave.fetch(); wave.free()
+        assert comp.handle.is_specialized() == spec
+    finally:
+        comp.close()
+    o = ora.make_tran_opts(method={"be": 0, "trap": 1, "gear2": 2}[method], dt=dt)
+    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), tspan[0], tspan[1], o, save)
+    gpu = np.transpose(r["u"], (2, 1, 0))
+    ref = ro["u"][:, :gpu.shape[1], :]
+    assert np.array_equal(r["status"], ro["status"]) and (r["status"] == 0).all()
+    assert _close(gpu, ref, rtol=1e-7, atol=1e-9), float(np.max(np.abs(gpu - ref)))
+    assert np.array_equal(r["newton_iters"], ro["newton_iters"])
+    if name == "mos1_inverter":
+        q = gpu[:, :, lc.index_of("q") - 1]
+        vdd = gpu[:, 0, lc.index_of("vdd") - 1]
+        assert np.all(q.max(axis=1) > 0.95 * vdd) and np.all(q.min(axis=1) < 0.05 * vdd)   # it inverts
+
+
+@pytest.mark.gpu
+def test_gpu_va_ring_oscillator():
+    lc = fixture("mos1_ring")
+    nl = oracle_of(lc)
+    save = [lc.index_of(n) for n in ("out1", "out2", "in1")]
+    u0 = np.repeat(_ring_u0(lc)[:, None], lc.P, axis=1)
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        wave = comp.tran((0.0, 5e-9), 5e-12, method="trap", save_idxs=save, u0=u0)
+        r = wave.fetch(); wave.free()
+    finally:
+        comp.close()
+    o = ora.make_tran_opts(method=1, dt=5e-12, init=1)
+    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 5e-9, o, save, u0=u0.T.copy())
+    gpu = np.transpose(r["u"], (2, 1, 0))
+    ref = ro["u"][:, :gpu.shape[1], :]
+    assert (r["status"] == 0).all()
+    # an oscillator amplifies rounding differences: compare loosely, and the swing exactly
+    assert np.max(np.abs(gpu - ref)) < 1e-3
+    assert gpu[:, :, 0].max() - gpu[:, :, 0].min() > 2.0

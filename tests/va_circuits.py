@@ -1,0 +1,114 @@
+"""Circuits built from the reference's VADistiller models (sp_mos1, sp_diode), shared by the
+fixture generator (tests/golden/make_va_fixtures.py) and the CPU tests.  The builders take
+the parsed models as arguments: the GPU box has no /root/reference, so the GPU tests load the
+lowered circuits from the committed fixtures instead of parsing the .va files."""
+import numpy as np
+
+import cadnip_b200 as cb
+from cadnip_b200 import (MNAContext, ZERO_VECTOR, get_node, stamp, VoltageSource, Resistor, Capacitor,
+                         VCVS, PWLWave)
+
+VA_DIR = "/root/reference/models/VADistillerModels.jl/va/"
+
+
+def _B(f):
+    def build(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
+        ctx = MNAContext() if ctx is None else ctx
+        f(ctx, params)
+        return ctx
+    return build
+
+
+def mos1_corner(sp_mos1):
+    """test/params.jl:377-385 corner_ckt: square-law MOS1 in saturation, W/L = 20, RD = 10k,
+    VGS = 1.2; swept over the model card (vto, kp)."""
+    def f(ctx, p):
+        vdd = get_node(ctx, "vdd"); g = get_node(ctx, "g"); drain = get_node(ctx, "drain")
+        stamp(VoltageSource(5.0, name="Vdd"), ctx, vdd, 0)
+        stamp(VoltageSource(1.2, name="Vg"), ctx, g, 0)
+        stamp(sp_mos1(type=1, vto=p.vt0, kp=p.kpn, w=20e-6, l=1e-6, name="M1"), ctx, drain, g, 0, 0)
+        stamp(Resistor(10e3, name="Rd"), ctx, vdd, drain)
+    return cb.CircuitSweep(_B(f), cb.ProductSweep(vt0=[0.6, 0.7, 0.9], kpn=[100e-6, 50e-6]))
+
+
+def diode_chain(sp_diode):
+    """test/sweep.jl:322-332 diode_chain: three series junctions behind 1k, vsrc 0.5:0.5:20."""
+    def f(ctx, p):
+        vin = get_node(ctx, "in"); n1 = get_node(ctx, "n1"); n2 = get_node(ctx, "n2"); n3 = get_node(ctx, "n3")
+        stamp(VoltageSource(p.vsrc, name="v1"), ctx, vin, 0)
+        stamp(Resistor(1e3, name="r1"), ctx, vin, n1)
+        stamp(sp_diode(**{"is": 1e-14, "n": 1.0, "name": "d1"}), ctx, n1, n2)
+        stamp(sp_diode(**{"is": 1e-14, "n": 1.0, "name": "d2"}), ctx, n2, n3)
+        stamp(sp_diode(**{"is": 1e-14, "n": 1.0, "name": "d3"}), ctx, n3, 0)
+    return cb.CircuitSweep(_B(f), cb.Sweep(vsrc=np.arange(0.5, 20.01, 0.5)))
+
+
+def diode_rs_cap(sp_diode):
+    """One sp_diode with series resistance (internal node kept), junction capacitance and
+    transit time behind a resistor, driven by a pulse: exercises the charge-state rows."""
+    def f(ctx, p):
+        vin = get_node(ctx, "in"); a = get_node(ctx, "a")
+        stamp(VoltageSource(0.0, tran=PWLWave([0.0, 1e-9, 2e-9, 6e-9, 7e-9], [-2.0, -2.0, 1.0, 1.0, -2.0]),
+                            name="v1"), ctx, vin, 0)
+        stamp(Resistor(p.r, name="r1"), ctx, vin, a)
+        stamp(sp_diode(**{"is": 1e-14, "rs": 5.0, "cjo": 2e-12, "tt": 1e-10, "vj": 0.8, "m": 0.4,
+                          "name": "d1"}), ctx, a, 0)
+    return cb.CircuitSweep(_B(f), cb.Sweep(r=[200.0, 1e3]))
+
+
+_NMOS = dict(type=1, vto=0.7, kp=100e-6)       # test/mna/oscillator_test.jl:43-44
+_PMOS = dict(type=-1, vto=-0.7, kp=50e-6)
+
+
+def mos1_inverter(sp_mos1):
+    """CMOS inverter of benchmarks/benchmark_common.jl:82-106 with sp_mos1 cards:
+    W_n x Vdd x C_L sweep, W_p = 1.375 W_n; the input ramp is scaled to Vdd by a VCVS."""
+    def f(ctx, p):
+        vdd = get_node(ctx, "vdd"); d = get_node(ctx, "d"); q = get_node(ctx, "q"); ramp = get_node(ctx, "ramp")
+        stamp(VoltageSource(p.vdd, name="VDD"), ctx, vdd, 0)
+        stamp(VoltageSource(0.0, tran=PWLWave([0.0, 1e-9, 2e-9, 6e-9, 7e-9, 10e-9], [0.0, 0.0, 1.0, 1.0, 0.0, 0.0]),
+                            name="VR"), ctx, ramp, 0)
+        stamp(VCVS(p.vdd, name="EIN"), ctx, d, 0, ramp, 0)
+        stamp(sp_mos1(w=1.375 * p.wn, l=1e-6, name="MP", **_PMOS), ctx, q, d, vdd, vdd)
+        stamp(sp_mos1(w=p.wn, l=1e-6, name="MN", **_NMOS), ctx, q, d, 0, 0)
+        stamp(Capacitor(p.cl, name="CL"), ctx, q, 0)
+    return cb.CircuitSweep(_B(f), cb.ProductSweep(wn=[0.36e-6, 3.6e-6], vdd=[1.8, 5.0], cl=[1e-15, 100e-15]))
+
+
+def mos1_ring(sp_mos1, caps=False):
+    """3-stage ring oscillator of test/mna/oscillator_test.jl:38-68; caps=True adds the
+    device's own overlap / junction / Meyer capacitances (voltage-dependent charges)."""
+    extra = dict(cgso=3e-10, cgdo=3e-10, cbd=2e-15, cbs=2e-15, tox=2e-8) if caps else {}
+
+    def f(ctx, p):
+        vdd = get_node(ctx, "vdd"); in1 = get_node(ctx, "in1"); out1 = get_node(ctx, "out1"); out2 = get_node(ctx, "out2")
+        stamp(VoltageSource(3.3, name="Vdd"), ctx, vdd, 0)
+        for k, (i, o) in enumerate(((in1, out1), (out1, out2), (out2, in1)), 1):
+            stamp(sp_mos1(w=2e-6, l=1e-6, name=f"MP{k}", **_PMOS, **extra), ctx, o, i, vdd, vdd)
+            stamp(sp_mos1(w=1e-6, l=1e-6, name=f"MN{k}", **_NMOS, **extra), ctx, o, i, 0, 0)
+        stamp(Capacitor(p.c, name="C1"), ctx, out1, 0)
+        stamp(Capacitor(p.c, name="C2"), ctx, out2, 0)
+        stamp(Capacitor(p.c, name="C3"), ctx, in1, 0)
+    return cb.CircuitSweep(_B(f), cb.Sweep(c=[10e-15, 20e-15] if not caps else [10e-15]))
+
+
+FIXTURES = {
+    "mos1_corner": ("mos1", mos1_corner),
+    "diode_chain": ("diode", diode_chain),
+    "diode_rs_cap": ("diode", diode_rs_cap),
+    "mos1_inverter": ("mos1", mos1_inverter),
+    "mos1_ring": ("mos1", mos1_ring),
+    "mos1_ring_caps": ("mos1", lambda m: mos1_ring(m, caps=True)),
+}
+
+
+def lower_fixture(name, models=None):
+    """Lower one of the circuits above from the reference's .va sources."""
+    from cadnip_b200 import verilog_a
+    model_file, make = FIXTURES[name]
+    models = {} if models is None else models
+    if model_file not in models:
+        models[model_file] = verilog_a.load_va(VA_DIR + model_file + ".va")
+    cs = make(models[model_file])
+    params, P = cs.lane_params()
+    return cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P)
