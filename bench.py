@@ -26,14 +26,30 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 import numpy as np
 
 N_R, N_C = 256, 256
-TSPAN = (0.0, 2e-3)
-DT = 1e-6
-SAVE_EVERY = 10
 N_SEGMENTS = int(os.environ.get("CB200_SEGMENTS", "8"))
 METRIC = "transient_sweep_points_per_sec"
 UNIT = "points/s"
-WORKLOAD = ("C2 RC/diode clipper CircuitSweep: 65536 points (256 R x 256 C, log grids), DC op "
-            "(CedarTranOp/PCNR) + fixed-step BE 2000 x 1us; V(out) saved every 10th step")
+# c2 = BASELINE.json configs[1] (the default, the configuration the metric is quoted on);
+# c3 = configs[2], the 100k-point CMOS inverter sweep with the sp_mos1 Verilog-A model
+#      (circuit from tests/golden/va_mos1_c3.pkl.gz, lanes regenerated here).
+WORKLOADS = {
+    "c2": dict(tspan=(0.0, 2e-3), dt=1e-6, save_every=10, save="out", steps=2000, limit=False,
+               text="C2 RC/diode clipper CircuitSweep: 65536 points (256 R x 256 C, log grids), DC op "
+                    "(CedarTranOp/PCNR) + fixed-step BE 2000 x 1us; V(out) saved every 10th step"),
+    "c3": dict(tspan=(0.0, 4e-7), dt=1e-10, save_every=10, save="q", steps=4000, limit=True,
+               text="C3 CMOS inverter CircuitSweep (sp_mos1 Verilog-A model through the emitter): 100000 points "
+                    "(50 W_n x 50 Vdd x 40 C_L), DC op (CedarTranOp/PCNR) + fixed-step BE 4000 x 0.1ns "
+                    "(CB200_TRAN_LIMIT: steps that miss 10 Newton solves are redone with $limit damping); "
+                    "V(q) saved every 10th step"),
+}
+W = WORKLOADS["c2"]
+TSPAN, DT, SAVE_EVERY, WORKLOAD = W["tspan"], W["dt"], W["save_every"], W["text"]
+
+
+def select_workload(name):
+    global W, TSPAN, DT, SAVE_EVERY, WORKLOAD
+    W = WORKLOADS[name]
+    TSPAN, DT, SAVE_EVERY, WORKLOAD = W["tspan"], W["dt"], W["save_every"], W["text"]
 
 
 def parse():
@@ -44,6 +60,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lanes", type=int, default=0, help="debug: override lane count (square grid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     return ap.parse_args()
 
 
@@ -91,9 +108,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def c3_lanes(lc, n_lanes):
+    """The C3 grid: W_n lin [0.36, 3.6] um x Vdd lin [1.8, 5.0] V x C_L log [1, 100] fF,
+    first axis fastest; W_p = 1.375 W_n."""
+    if n_lanes:
+        side = max(2, int(round(n_lanes ** (1.0 / 3.0))))
+        shape = (side, side, side)
+    else:
+        shape = (50, 50, 40)
+    wn = np.linspace(0.36e-6, 3.6e-6, shape[0])
+    vdd = np.linspace(1.8, 5.0, shape[1])
+    cl = np.logspace(-15, -13, shape[2])
+    k, j, i = np.meshgrid(np.arange(shape[2]), np.arange(shape[1]), np.arange(shape[0]), indexing="ij")
+    col = {"wn": wn[i.ravel()], "1.375*wn": 1.375 * wn[i.ravel()], "vdd": vdd[j.ravel()], "cl": cl[k.ravel()]}
+    return np.ascontiguousarray(np.stack([col[e] for e in lc.lane_exprs])), int(i.size)
+
+
 def build_sweep(args):
     import cadnip_b200 as cb
     from cadnip_b200.workloads import clipper_sweep
+    if args.workload == "c3":
+        import gzip
+        import pickle
+        with gzip.open(os.path.join(ROOT, "tests", "golden", "va_mos1_c3.pkl.gz"), "rb") as f:
+            lc = pickle.load(f)
+        lc.lane_soa, lc.P = c3_lanes(lc, args.lanes)
+        return cb, None, lc, lc.P
     if args.lanes:
         side = max(1, int(round(args.lanes ** 0.5)))
         cs = clipper_sweep(side, side)
@@ -117,13 +157,15 @@ def cpu_oracle_rate(lc, sample_lanes, nthreads=0):
     """Times the CPU oracle (kind 'port') on a strided sample of the same sweep."""
     import cadnip_oracle as ora
     nthreads = nthreads or host_threads()
+    if lc.va_c_source:
+        ora.load_va_models(lc.va_c_source)
     nl = ora.OracleNetlist(lc.netlist_tables())
     par = np.ascontiguousarray(nl.par_lanes[sample_lanes])
     sub = dict(lc.netlist_tables()); sub["par"] = par
     nls = ora.OracleNetlist(sub)
-    o = ora.make_tran_opts(method=0, dt=DT, save_every=SAVE_EVERY)
+    o = ora.make_tran_opts(method=0, dt=DT, save_every=SAVE_EVERY, limit=W["limit"])
     t0 = time.perf_counter()
-    r = ora.sweep_tran(nls, ora.make_spec(mode="tran"), TSPAN[0], TSPAN[1], o, [lc.index_of("out")],
+    r = ora.sweep_tran(nls, ora.make_spec(mode="tran"), TSPAN[0], TSPAN[1], o, [lc.index_of(W["save"])],
                        nthreads=nthreads)
     dt = time.perf_counter() - t0
     return len(sample_lanes) / dt, int(r["newton_iters"].sum()), dt
@@ -160,7 +202,7 @@ def run_reference(args):
             "config": {"workload": WORKLOAD, "lanes_per_step": n_sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{n_sample} of {P} lanes (strided over the sweep), full "
-                                       "2000-step transient each, OpenMP over lanes"},
+                                       f"{W['steps']}-step transient each, OpenMP over lanes"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -186,7 +228,7 @@ def run_b200(args):
     cb, cs, lc, P = build_sweep(args)
     # weak scaling: every rank solves the full C2 sweep (per-GPU work fixed as N grows)
     comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"), device=local_rank)
-    save = [lc.index_of("out")]
+    save = [lc.index_of(W["save"])]
     T = 1 + int(round((TSPAN[1] - TSPAN[0]) / DT)) // SAVE_EVERY
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     pinned_out = torch.empty((len(save), T, P), dtype=torch.float64, pin_memory=True)
@@ -199,7 +241,7 @@ def run_b200(args):
         comp.specialize(DT, "be")        # emitter: circuit-specialised kernels (nvcc, cached in-tree)
 
     def step_resident():
-        wave = comp.tran(TSPAN, DT, method="be", save_idxs=save, save_every=SAVE_EVERY)
+        wave = comp.tran(TSPAN, DT, method="be", save_idxs=save, save_every=SAVE_EVERY, limit=W["limit"])
         st = comp.handle.stats()
         return wave, st
 
@@ -208,7 +250,7 @@ def run_b200(args):
         h2d = comp.handle.stats()["h2d_bytes"]
         # tran! into pinned host memory: D2H of each time segment overlaps the next one's compute
         r = comp.tran_fetch(TSPAN, DT, out_np, method="be", save_idxs=save, save_every=SAVE_EVERY,
-                            n_segments=N_SEGMENTS)
+                            n_segments=N_SEGMENTS, limit=W["limit"])
         st = comp.handle.stats()
         d2h = st["d2h_bytes"]
         return st, r, h2d, d2h
@@ -277,7 +319,8 @@ def run_b200(args):
     achieved = alg_bytes / tran_s / 1e9 if tran_s > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("tran_fixed_kernel")
+        if args.workload == "c2":          # the capture under profiles/ is of the C2 kernel
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("tran_fixed_kernel")
     except Exception:
         pass
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -287,7 +330,7 @@ def run_b200(args):
             "newton_iters_per_sec": world * iters_per_step * args.steps / wall,
             "newton_iters_per_step": iters_per_step,
             "config": {"workload": WORKLOAD, "lanes_per_gpu": P, "parallelism": f"lanes sharded x{world}"
-                       if world > 1 else "1 GPU", "method": "BE fixed dt=1e-6, 2000 steps",
+                       if world > 1 else "1 GPU", "method": f"BE fixed dt={DT:g}, {W['steps']} steps",
                        "l2": "256 MiB device memset between steps (inside the timed region)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * wall_e2e / args.steps,
@@ -316,7 +359,7 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "newton_iters_per_sec": it / secs,
                                     "sample": f"{n_sample} of {P} lanes (strided over the sweep), full "
-                                              f"2000-step transient each, OpenMP over lanes, {secs:.1f} s"}
+                                              f"{W['steps']}-step transient each, OpenMP over lanes, {secs:.1f} s"}
         print(json.dumps(line), flush=True)
     comp.close()
     if world > 1:
@@ -325,6 +368,7 @@ def run_b200(args):
 
 def main():
     args = parse()
+    select_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -209,22 +209,24 @@ class CompiledSweep:
 
     def tran(self, tspan, dt, method="be", save_idxs=None, save_every=1, abstol=1e-10,
              max_nl_iters=10, u0=None, init_abstol=1e-9, init_maxiters=500,
-             specialize=False) -> backend.Wave:
+             specialize=False, limit=False) -> backend.Wave:
+        """limit=True applies the PCNR corrector inside the transient Newton loop too
+        (CB200_TRAN_LIMIT): the models' $limit functions then damp the iteration."""
         if specialize:
             self.specialize(dt, method)
         opts = backend.make_tran_opts(method=method, adaptive=False, dt=dt, abstol=abstol,
                                       max_nl_iters=max_nl_iters, save_every=save_every,
                                       init=0 if u0 is None else 1, init_abstol=init_abstol,
-                                      init_maxiters=init_maxiters)
+                                      init_maxiters=init_maxiters, limit=limit)
         return self.handle.tran(self.spec, tspan[0], tspan[1], opts, self.save_indices(save_idxs), u0)
 
     def tran_fetch(self, tspan, dt, out_u, method="be", save_idxs=None, save_every=1, abstol=1e-10,
-                   max_nl_iters=10, n_segments=4, init_abstol=1e-9, init_maxiters=500):
+                   max_nl_iters=10, n_segments=4, init_abstol=1e-9, init_maxiters=500, limit=False):
         """Fixed-step transient delivered into the (pinned) host array ``out_u``
         [save][T][P]; D2H of each time segment overlaps the next segment's compute."""
         opts = backend.make_tran_opts(method=method, adaptive=False, dt=dt, abstol=abstol,
                                       max_nl_iters=max_nl_iters, save_every=save_every,
-                                      init_abstol=init_abstol, init_maxiters=init_maxiters)
+                                      init_abstol=init_abstol, init_maxiters=init_maxiters, limit=limit)
         return self.handle.tran_fetch(self.spec, tspan[0], tspan[1], opts,
                                       self.save_indices(save_idxs), out_u, None, n_segments)
 

@@ -73,7 +73,7 @@ class TranOpts(C.Structure):
                 ("lte_abstol", C.c_double), ("dtmin", C.c_double), ("dtmax", C.c_double),
                 ("max_nl_iters", C.c_int32), ("save_every", C.c_int32),
                 ("max_points", C.c_int32), ("init", C.c_int32),
-                ("init_abstol", C.c_double), ("init_maxiters", C.c_int32), ("_pad", C.c_int32)]
+                ("init_abstol", C.c_double), ("init_maxiters", C.c_int32), ("flags", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -463,7 +463,8 @@ def debug_exp(x: np.ndarray) -> np.ndarray:
 
 def make_tran_opts(method="be", adaptive=False, dt=0.0, abstol=1e-10, reltol=1e-8, lte_abstol=1e-10,
                    dtmin=0.0, dtmax=0.0, max_nl_iters=10, save_every=1, max_points=0, init=0,
-                   init_abstol=1e-9, init_maxiters=500) -> TranOpts:
+                   init_abstol=1e-9, init_maxiters=500, limit=False) -> TranOpts:
+    """limit: CB200_TRAN_LIMIT -- PCNR corrector inside the transient Newton loop."""
     m = METHODS[method] if isinstance(method, str) else int(method)
     return TranOpts(m, int(adaptive), dt, abstol, reltol, lte_abstol, dtmin, dtmax, max_nl_iters,
-                    save_every, max_points, init, init_abstol, init_maxiters, 0)
+                    save_every, max_points, init, init_abstol, init_maxiters, 1 if limit else 0)

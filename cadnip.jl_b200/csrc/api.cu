@@ -961,7 +961,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         }
         TranArgs a{};
         a.method = o->method; a.t0 = t0; a.h = o->dt; a.nsteps = nsteps; a.abstol = o->abstol;
-        a.max_nl = o->max_nl_iters; a.save_every = se; a.n_save = n_save; a.save_idx = d_save.p;
+        a.max_nl = o->max_nl_iters; a.limit = o->flags & CB200_TRAN_LIMIT; a.save_every = se; a.n_save = n_save; a.save_idx = d_save.p;
         a.T = T; a.u = h->d_state.p; a.out = w->d_out.p; a.status = h->d_status.p; a.iters = h->d_iters.p;
         a.ws_global = ws_global;
         // Time segments: one launch each.  With a host destination the D2H copy of a finished
@@ -1015,7 +1015,8 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         a.dtmin = o->dtmin > 0 ? o->dtmin : span * 1e-12;
         a.h0 = std::min(o->dt, a.dtmax);
         a.abstol = o->abstol; a.reltol = o->reltol; a.lte_abstol = o->lte_abstol;
-        a.max_nl = o->max_nl_iters; a.n_save = n_save; a.save_idx = d_save.p; a.max_points = T;
+        a.max_nl = o->max_nl_iters; a.limit = o->flags & CB200_TRAN_LIMIT;
+        a.n_save = n_save; a.save_idx = d_save.p; a.max_points = T;
         if (w->d_out.alloc((size_t)std::max(1, n_save) * T * P) != cudaSuccess ||
             w->d_t.alloc((size_t)T * P) != cudaSuccess || w->d_count.alloc(P) != cudaSuccess ||
             (h->d_rejected.n != (size_t)P && h->d_rejected.alloc(P) != cudaSuccess)) {

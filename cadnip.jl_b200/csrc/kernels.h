@@ -82,6 +82,7 @@ struct TranArgs {
     double *hist;           // [2n][P] integrator history (u_n, dterm) carried between segments, or null
     double abstol;
     int max_nl;
+    int limit;              // CB200_TRAN_LIMIT: PCNR corrector after every transient Newton solve
     int save_every;
     int n_save;
     const int *save_idx;    // device, 0-based unknown indices
@@ -102,6 +103,7 @@ struct AdaptArgs {
     double t0, t1, h0, dtmin, dtmax;
     double abstol, reltol, lte_abstol;
     int max_nl;
+    int limit;
     int n_save;
     const int *save_idx;
     int max_points;

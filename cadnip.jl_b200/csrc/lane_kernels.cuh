@@ -875,21 +875,40 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
         eval_sources_step(pg, w, k, k == a.k_begin, a.t0, h, CB200_MODE_TRAN);
         bool done = false;
         int st = CB200_LANE_OK;
+        // a.limit (CB200_TRAN_LIMIT): a step the plain iteration does not finish in max_nl solves
+        // is redone from u_n with the PCNR corrector after every solve (4*max_nl solves allowed)
+        bool lim_on = false;
+        int it0 = 0;
         for (int it = 0;; it++) {
             eval_nonlinear(pg, w, t, CB200_MODE_TRAN, false);
             bool bad;
             const double nrm2 = assemble<true>(pg, lu, w, gamma, sp.gshunt, sp.srcFact, bad);
+            bool restart = false;
             if (!done) {
                 if (bad) { done = true; st = CB200_LANE_NONFINITE; }
                 else if (nrm2 < abstol2) { done = true; }
-                else if (it >= a.max_nl) { done = true; st = CB200_LANE_MAXITER; }
+                else if (it - it0 >= (lim_on ? 4 * a.max_nl : a.max_nl)) {
+                    if (a.limit && !lim_on) { lim_on = true; it0 = it + 1; restart = true; }
+                    else { done = true; st = CB200_LANE_MAXITER; }
+                }
             }
             if (__all_sync(0xffffffffu, done)) break;
             bool singular;
             const bool ok = factor_and_solve(pg, lu, w, singular);
             if (!done) {
-                if (!ok) { done = true; st = singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE; }
-                else { apply_update(pg, lu, w); solves++; }
+                if (restart) {                             // redo the step from u_n, limiting on
+                    CB_UNROLL
+                    for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
+                } else if (!ok) { done = true; st = singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE; }
+                else {
+                    apply_update(pg, lu, w);
+                    solves++;
+                    if (lim_on) {                          // PCNR corrector, solve.jl:686-689
+                        const int lim0 = pg.n() - pg.n_limits();
+                        CB_UNROLL
+                        for (int q = 0; q < pg.n_limits(); q++) w(pg.off_u() + lim0 + q) = w(pg.off_limw() + q);
+                    }
+                }
             }
         }
         if (st != CB200_LANE_OK && status == CB200_LANE_OK) status = st;
@@ -990,21 +1009,40 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
         // ---- Newton on the implicit step
         bool done = finished;
         int st = CB200_LANE_OK;
+        // a.limit (CB200_TRAN_LIMIT): a step the plain iteration does not finish in max_nl solves
+        // is redone from u_n with the PCNR corrector after every solve (4*max_nl solves allowed)
+        bool lim_on = false;
+        int it0 = 0;
         for (int it = 0;; it++) {
             eval_nonlinear(pg, w, tn, CB200_MODE_TRAN, false);
             bool bad;
             const double nrm2 = assemble<true>(pg, lu, w, gamma, sp.gshunt, sp.srcFact, bad);
+            bool restart = false;
             if (!done) {
                 if (bad) { done = true; st = CB200_LANE_NONFINITE; }
                 else if (nrm2 < abstol2) { done = true; }
-                else if (it >= a.max_nl) { done = true; st = CB200_LANE_MAXITER; }
+                else if (it - it0 >= (lim_on ? 4 * a.max_nl : a.max_nl)) {
+                    if (a.limit && !lim_on) { lim_on = true; it0 = it + 1; restart = true; }
+                    else { done = true; st = CB200_LANE_MAXITER; }
+                }
             }
             if (__all_sync(0xffffffffu, done)) break;
             bool singular;
             const bool ok = factor_and_solve(pg, lu, w, singular);
             if (!done) {
-                if (!ok) { done = true; st = singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE; }
-                else { apply_update(pg, lu, w); solves++; }
+                if (restart) {                             // redo the step from u_n, limiting on
+                    CB_UNROLL
+                    for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
+                } else if (!ok) { done = true; st = singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE; }
+                else {
+                    apply_update(pg, lu, w);
+                    solves++;
+                    if (lim_on) {                          // PCNR corrector, solve.jl:686-689
+                        const int lim0 = pg.n() - pg.n_limits();
+                        CB_UNROLL
+                        for (int q = 0; q < pg.n_limits(); q++) w(pg.off_u() + lim0 + q) = w(pg.off_limw() + q);
+                    }
+                }
             }
         }
         if (finished) continue;

@@ -162,8 +162,14 @@ typedef struct cb200_tran_opts {
     int32_t init;          /* 0: CedarTranOp (dcop.jl:160); 1: u0 given (UIC)  */
     double  init_abstol;   /* 1e-9  */
     int32_t init_maxiters; /* 500   */
-    int32_t _pad;
+    int32_t flags;         /* CB200_TRAN_* bits                                */
 } cb200_tran_opts;
+/* Apply the PCNR corrector inside the transient Newton loop as well: after every solve the
+ * limit unknowns are set to the recorded limited voltages w (solve.jl:686-689), so the
+ * models' $limit functions (pnjlim / fetlim / limvds) damp the iteration as they do in
+ * ngspice's transient.  Off = the reference's formulation (limit rows are ordinary
+ * algebraic unknowns in transient).  The converged step is the same either way.        */
+#define CB200_TRAN_LIMIT 1
 
 /* Counters of the most recent call (all device times from CUDA events on the
  * library's own stream).                                                      */

@@ -1377,21 +1377,32 @@ static void tran_residual(ora_workspace *w, const ora_structure *s, const double
 /* one implicit step; returns status, u updated in place */
 static int implicit_step(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
                          double *u, const double *un, const double *dterm, double gamma, double t,
-                         double abstol, int max_nl, int64_t *iters)
+                         double abstol, int max_nl, int64_t *iters, int limit)
 {
     int64_t n = s->n;
     double *F = w->F, *delta = w->delta, *du = w->du;
+    /* limit (CB200_TRAN_LIMIT): when the plain iteration has not converged after max_nl
+     * solves, the step is redone from u_n with the PCNR corrector (solve.jl:686-689) after
+     * every solve, so the models' $limit functions damp it; 4*max_nl solves allowed.     */
+    int lim_on = 0, it0 = 0;
     for (int it = 0; ; it++) {
         fast_rebuild(w, s, spec, u, t);
         for (int64_t i = 0; i < n; i++) du[i] = gamma * (u[i] - un[i]) + dterm[i];
         tran_residual(w, s, u, du, F);
         if (!all_finite(F, n)) return ORA_LANE_NONFINITE;
         if (norm2(F, n) < abstol) return ORA_LANE_OK;
-        if (it >= max_nl) return ORA_LANE_MAXITER;
+        if (it - it0 >= (lim_on ? 4 * max_nl : max_nl)) {
+            if (!limit || lim_on) return ORA_LANE_MAXITER;
+            lim_on = 1; it0 = it + 1;
+            for (int64_t i = 0; i < n; i++) u[i] = un[i];
+            continue;
+        }
         for (int64_t k = 0; k < s->nnz; k++) w->Jnz[k] = w->G_nz[k] + gamma * w->C_nz[k];
         if (dense_solve(w, s, w->Jnz, F, delta)) return ORA_LANE_SINGULAR;
         if (!all_finite(delta, n)) return ORA_LANE_NONFINITE;
         for (int64_t i = 0; i < n; i++) u[i] -= delta[i];
+        if (lim_on)
+            for (int64_t k = 0; k < s->n_limits; k++) u[n - s->n_limits + k] = w->limit_w[k];
         if (iters) (*iters)++;
     }
 }
@@ -1460,7 +1471,7 @@ int ora_tran(const ora_netlist *nl, const ora_spec *spec_in, double t0, double t
                 for (int64_t i = 0; i < n; i++) hist[i] = -(un[i] - unm1[i]) / (2.0 * h);
             }
             int st = implicit_step(w, s, &spec, u, un, hist, gamma, t, o->abstol, o->max_nl_iters,
-                                   &iters);
+                                   &iters, o->flags & 1);
             if (st != ORA_LANE_OK && status == ORA_LANE_OK) status = st;
             if (st == ORA_LANE_NONFINITE || st == ORA_LANE_SINGULAR) {
                 /* lane is dead: hold the last finite state for the remaining points */
@@ -1553,7 +1564,7 @@ int ora__tran_adaptive(ora_workspace *w, const ora_structure *s, const ora_spec 
             gamma = 2.0 / hh;
             for (int64_t i = 0; i < n; i++) hist[i] = -dun[i];
         }
-        int st = implicit_step(w, s, spec, u, un, hist, gamma, tn, o->abstol, o->max_nl_iters, iters);
+        int st = implicit_step(w, s, spec, u, un, hist, gamma, tn, o->abstol, o->max_nl_iters, iters, o->flags & 1);
         if (st != ORA_LANE_OK) {
             memcpy(u, un, sizeof(double) * n);
             (*rej)++;

@@ -141,7 +141,7 @@ typedef struct ora_tran_opts {
     int32_t method, adaptive;
     double dt, abstol, reltol, lte_abstol, dtmin, dtmax;
     int32_t max_nl_iters, save_every, max_points, init;
-    double init_abstol; int32_t init_maxiters; int32_t _pad;
+    double init_abstol; int32_t init_maxiters; int32_t flags;   /* bit 0: PCNR corrector in transient */
 } ora_tran_opts;
 
 /* One circuit.  Fixed step: nsteps = round((t1-t0)/dt); saved points are k = 0,

@@ -48,7 +48,7 @@ class TranOpts(C.Structure):
                 ("lte_abstol", C.c_double), ("dtmin", C.c_double), ("dtmax", C.c_double),
                 ("max_nl_iters", C.c_int32), ("save_every", C.c_int32),
                 ("max_points", C.c_int32), ("init", C.c_int32),
-                ("init_abstol", C.c_double), ("init_maxiters", C.c_int32), ("_pad", C.c_int32)]
+                ("init_abstol", C.c_double), ("init_maxiters", C.c_int32), ("flags", C.c_int32)]
 
 
 _MODES = {"dcop": 0, "tran": 1, "tranop": 2, "ac": 3}
@@ -150,9 +150,9 @@ def make_spec(spec=None, **over) -> Spec:
 
 def make_tran_opts(method=0, adaptive=0, dt=0.0, abstol=1e-10, reltol=1e-8, lte_abstol=1e-10,
                    dtmin=0.0, dtmax=0.0, max_nl_iters=10, save_every=1, max_points=0, init=0,
-                   init_abstol=1e-9, init_maxiters=500) -> TranOpts:
+                   init_abstol=1e-9, init_maxiters=500, limit=False) -> TranOpts:
     return TranOpts(method, adaptive, dt, abstol, reltol, lte_abstol, dtmin, dtmax, max_nl_iters,
-                    save_every, max_points, init, init_abstol, init_maxiters, 0)
+                    save_every, max_points, init, init_abstol, init_maxiters, 1 if limit else 0)
 
 
 class OracleNetlist:

@@ -19,10 +19,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 HAVE_REF = os.path.isdir("/root/reference/models/VADistillerModels.jl/va")
 needs_ref = pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
 
-FIXTURE_NAMES = ["mos1_corner", "diode_chain", "diode_rs_cap", "mos1_inverter", "mos1_ring", "mos1_ring_caps"]
+FIXTURE_NAMES = ["mos1_corner", "diode_chain", "diode_rs_cap", "mos1_inverter", "mos1_c3", "mos1_ring",
+                 "mos1_ring_caps"]
 
 
-GPU_FIXTURES = ["mos1_corner", "diode_chain", "mos1_inverter", "diode_rs_cap", "mos1_ring"]   # used by -m gpu tests
+GPU_FIXTURES = ["mos1_corner", "diode_chain", "mos1_inverter", "diode_rs_cap", "mos1_ring", "mos1_c3"]   # used by -m gpu tests
 
 
 def fixture(name):
@@ -167,6 +168,25 @@ def test_ring_oscillator_known_answer(name):
     assert 0.05e-9 < period < 50e-9
 
 
+def test_transient_limiting_rescues_fast_edges():
+    """C3 corner lanes: with a 1 fF load the output flips inside one 0.1 ns step and
+    the first Newton iterate forward-biases a bulk junction; the plain iteration (limit rows as
+    ordinary unknowns, the reference's transient formulation) crawls down the exponential and
+    misses 10 solves, CB200_TRAN_LIMIT redoes those steps with the models' $limit damping."""
+    lc = fixture("mos1_c3")
+    nl = oracle_of(lc)
+    save = [lc.index_of("q")]
+    plain = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 1.3e-7,
+                           ora.make_tran_opts(method=0, dt=1e-10, save_every=10), save)
+    lim = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 1.3e-7,
+                         ora.make_tran_opts(method=0, dt=1e-10, save_every=10, limit=True), save)
+    assert (plain["status"] == 1).any() and (lim["status"] == 0).all()
+    ok = plain["status"] == 0
+    assert np.allclose(plain["u"][ok], lim["u"][ok], rtol=0, atol=1e-6)      # same converged steps
+    vdd = lc.param_value(int(lc.dev_params[lc.dev_param_ptr[lc.dev_names.index("VVDD")]]))
+    assert np.all(lim["u"][:, -1, 0] < 0.05 * vdd)                              # input high -> output low
+
+
 # ---- emitted derivatives against finite differences ------------------------------------------
 @pytest.mark.parametrize("name", ["mos1_inverter", "diode_rs_cap", "mos1_ring_caps"])
 def test_emitted_jacobian_matches_finite_differences(name):
@@ -270,7 +290,27 @@ def test_gpu_va_models_transient(name, tspan, dt, method, spec):
     if name == "mos1_inverter":
         q = gpu[:, :, lc.index_of("q") - 1]
         vdd = gpu[:, 0, lc.index_of("vdd") - 1]
-        assert np.all(q.max(axis=1) > 0.95 * vdd) and np.all(q.min(axis=1) < 0.05 * vdd)   # it inverts
+        assert np.all(q.max(axis=1) > 0.95 * vdd)                          # it inverts ...
+        assert np.all(q[:4].min(axis=1) < 0.05 * vdd[:4])                  # ... fully, with the 1 fF load
+
+
+@pytest.mark.gpu
+def test_gpu_va_c3_corner_lanes_with_transient_limiting():
+    lc = fixture("mos1_c3")
+    nl = oracle_of(lc)
+    save = [lc.index_of("q"), lc.index_of("d")]
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        wave = comp.tran((0.0, 1.3e-7), 1e-10, method="be", save_idxs=save, save_every=10, limit=True)
+        r = wave.fetch(); wave.free()
+    finally:
+        comp.close()
+    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 1.3e-7,
+                        ora.make_tran_opts(method=0, dt=1e-10, save_every=10, limit=True), save)
+    gpu = np.transpose(r["u"], (2, 1, 0))
+    assert np.array_equal(r["status"], ro["status"]) and (r["status"] == 0).all()
+    assert _close(gpu, ro["u"][:, :gpu.shape[1], :], rtol=1e-6, atol=1e-8), float(np.max(np.abs(gpu - ro["u"][:, :gpu.shape[1], :])))
+    assert np.array_equal(r["newton_iters"], ro["newton_iters"])
 
 
 @pytest.mark.gpu
@@ -286,9 +326,9 @@ def test_gpu_va_ring_oscillator():
     finally:
         comp.close()
     o = ora.make_tran_opts(method=1, dt=5e-12, init=1)
-    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 5e-9, o, save, u0=u0.T.copy())
     gpu = np.transpose(r["u"], (2, 1, 0))
-    ref = ro["u"][:, :gpu.shape[1], :]
+    ref = np.stack([ora.tran(nl.for_lane(p), ora.make_spec(mode="tran"), 0.0, 5e-9, o, save,
+                             u0=u0[:, p].copy())["u"][:gpu.shape[1]] for p in range(lc.P)])
     assert (r["status"] == 0).all()
     # an oscillator amplifies rounding differences: compare loosely, and the swing exactly
     assert np.max(np.abs(gpu - ref)) < 1e-3

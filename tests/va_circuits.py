@@ -75,6 +75,44 @@ def mos1_inverter(sp_mos1):
     return cb.CircuitSweep(_B(f), cb.ProductSweep(wn=[0.36e-6, 3.6e-6], vdd=[1.8, 5.0], cl=[1e-15, 100e-15]))
 
 
+C3_PWL_T = [0.0, 100e-9, 110e-9, 200e-9, 210e-9, 300e-9, 310e-9, 400e-9]
+C3_PWL_Y = [0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 1.0, 1.0]
+
+
+def mos1_c3(sp_mos1):
+    """SURVEY 8d config C3 (BASELINE configs[2]): the inverter deck of
+    benchmarks/benchmark_common.jl:82-106 (Xneg W=3.6e-7 L=6e-7, Xpos W=4.95e-7 L=5e-7 = 1.375 W_n,
+    VSS source, CQ D 0 1e-15, PWL 0/100n/110n/200n/210n/300n/310n/400n) with the PDK FETs
+    replaced by sp_mos1 cards (vto=+-0.7, kp=100u/50u), a load C_L on Q, and the input ramp scaled
+    to Vdd by a VCVS; swept over W_n x Vdd x C_L.  The fixture holds a 2x2x2 corner grid; bench.py
+    regenerates the 50x50x40 = 100 000-lane columns from `lane_exprs`."""
+    def f(ctx, p):
+        vdd = get_node(ctx, "vdd"); vss = get_node(ctx, "vss"); d = get_node(ctx, "d"); q = get_node(ctx, "q")
+        ramp = get_node(ctx, "ramp")
+        stamp(sp_mos1(w=p.wn, l=6e-7, name="Xneg", **_NMOS), ctx, q, d, vss, vss)
+        stamp(sp_mos1(w=1.375 * p.wn, l=5e-7, name="Xpos", **_PMOS), ctx, q, d, vdd, vdd)
+        stamp(VoltageSource(p.vdd, name="VVDD"), ctx, vdd, 0)
+        stamp(VoltageSource(0.0, name="VVSS"), ctx, vss, 0)
+        stamp(Capacitor(1e-15, name="CQ"), ctx, d, 0)
+        stamp(VoltageSource(0.0, tran=PWLWave(C3_PWL_T, C3_PWL_Y), name="VR"), ctx, ramp, 0)
+        stamp(VCVS(p.vdd, name="VD"), ctx, d, 0, ramp, 0)
+        stamp(Capacitor(p.cl, name="CL"), ctx, q, 0)
+    return cb.CircuitSweep(_B(f), cb.ProductSweep(wn=[0.36e-6, 3.6e-6], vdd=[1.8, 5.0], cl=[1e-15, 100e-15]))
+
+
+def c3_lane_exprs(lc, cs):
+    """Which swept quantity each lane column of the lowered C3 circuit holds."""
+    params, P = cs.lane_params()
+    cand = {"wn": params.wn, "1.375*wn": 1.375 * params.wn, "vdd": params.vdd, "cl": params.cl}
+    out = []
+    for col in lc.lane_soa:
+        hit = [k for k, v in cand.items() if np.array_equal(col, np.asarray(v, dtype=np.float64))]
+        if len(hit) != 1:
+            raise ValueError("unrecognised lane column in the C3 circuit")
+        out.append(hit[0])
+    return out
+
+
 def mos1_ring(sp_mos1, caps=False):
     """3-stage ring oscillator of test/mna/oscillator_test.jl:38-68; caps=True adds the
     device's own overlap / junction / Meyer capacitances (voltage-dependent charges)."""
@@ -97,6 +135,7 @@ FIXTURES = {
     "diode_chain": ("diode", diode_chain),
     "diode_rs_cap": ("diode", diode_rs_cap),
     "mos1_inverter": ("mos1", mos1_inverter),
+    "mos1_c3": ("mos1", mos1_c3),
     "mos1_ring": ("mos1", mos1_ring),
     "mos1_ring_caps": ("mos1", lambda m: mos1_ring(m, caps=True)),
 }
@@ -111,4 +150,7 @@ def lower_fixture(name, models=None):
         models[model_file] = verilog_a.load_va(VA_DIR + model_file + ".va")
     cs = make(models[model_file])
     params, P = cs.lane_params()
-    return cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P)
+    lc = cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P)
+    if name == "mos1_c3":
+        lc.lane_exprs = c3_lane_exprs(lc, cs)
+    return lc
