@@ -60,7 +60,8 @@ class Desc(C.Structure):
                 ("dev_bbase", C.POINTER(C.c_int64)),
                 ("uniform", C.POINTER(C.c_double)),
                 ("limit_init_ref", C.POINTER(C.c_int32)),
-                ("n_lane_cols", C.c_int32), ("_pad", C.c_int32)]
+                ("n_lane_cols", C.c_int32), ("_pad", C.c_int32),
+                ("dev_state_ptr", C.POINTER(C.c_int32))]
 
 
 class DcOpts(C.Structure):
@@ -250,7 +251,9 @@ def make_desc(lc: LoweredCircuit):
              _lp(arr(lc.dev_gbase, np.int64)), _lp(arr(lc.dev_cbase, np.int64)),
              _lp(arr(lc.dev_bbase, np.int64)),
              _dp(arr(lc.uniform, np.float64)), _ip(arr(lc.limit_init_ref, np.int32)),
-             lc.n_lane_cols, 0)
+             lc.n_lane_cols, 0,
+             _ip(arr(getattr(lc, "dev_state_ptr", None) if getattr(lc, "dev_state_ptr", None) is not None
+                     else np.zeros(len(lc.dev_kind) + 1), np.int32)))
     return d, keep
 
 

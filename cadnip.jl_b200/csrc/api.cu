@@ -136,7 +136,7 @@ struct cb200_handle {
     Structure st;
     // host copies of the description
     std::vector<int> dev_kind, dev_flags, dev_node_ptr, dev_nodes, dev_param_ptr, dev_params;
-    std::vector<int> dev_gbase, dev_cbase, dev_bbase, src_list, nl_list, limit_init_ref;
+    std::vector<int> dev_gbase, dev_cbase, dev_bbase, dev_sbase, src_list, nl_list, limit_init_ref;
     std::vector<unsigned char> src_uniform;
     std::vector<double> uniform;
     int n_lane_cols = 0;
@@ -145,7 +145,7 @@ struct cb200_handle {
     std::vector<double> lanes_host;
     // device copies
     DevBuf<int> d_dev_kind, d_dev_flags, d_dev_node_ptr, d_dev_nodes, d_dev_param_ptr, d_dev_params;
-    DevBuf<int> d_dev_gbase, d_dev_cbase, d_dev_bbase, d_src_list, d_nl_list, d_limit_init_ref;
+    DevBuf<int> d_dev_gbase, d_dev_cbase, d_dev_bbase, d_dev_sbase, d_src_list, d_nl_list, d_limit_init_ref;
     DevBuf<int> d_gseg_ptr, d_gseg_idx, d_cseg_ptr, d_cseg_idx, d_bseg_ptr, d_bseg_idx;
     DevBuf<int> d_colptr, d_rowval;
     DevBuf<unsigned char> d_node_diag, d_src_uniform;
@@ -235,6 +235,7 @@ static void layout_workspace(cb200_handle *h)
     p.off_SB = o; o += (int)h->st.nb;
     p.off_limw = o; o += h->st.n_limits;
     p.off_lp = o; o += h->n_lane_cols;
+    p.off_DS = o; o += h->dev_sbase.empty() ? 0 : h->dev_sbase.back();
     p.off_srcc = o; o += (int)h->src_list.size();
     p.off_h1 = o; o += n;
     p.off_h2 = o; o += n;
@@ -308,6 +309,7 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
     h->dev_gbase = to_int64(d->dev_gbase, nd + 1);
     h->dev_cbase = to_int64(d->dev_cbase, nd + 1);
     h->dev_bbase = to_int64(d->dev_bbase, nd + 1);
+    h->dev_sbase = d->dev_state_ptr ? to_int(d->dev_state_ptr, nd + 1) : std::vector<int>(nd + 1, 0);
     h->uniform.assign(d->uniform, d->uniform + d->n_uniform);
     h->limit_init_ref = to_int(d->limit_init_ref, d->n_limits);
     h->n_lane_cols = d->n_lane_cols;
@@ -350,6 +352,7 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
               h->d_dev_gbase.upload(h->dev_gbase, s) == cudaSuccess &&
               h->d_dev_cbase.upload(h->dev_cbase, s) == cudaSuccess &&
               h->d_dev_bbase.upload(h->dev_bbase, s) == cudaSuccess &&
+              h->d_dev_sbase.upload(h->dev_sbase, s) == cudaSuccess &&
               h->d_src_list.upload(h->src_list, s) == cudaSuccess &&
               h->d_nl_list.upload(h->nl_list, s) == cudaSuccess &&
               h->d_src_uniform.upload(h->src_uniform, s) == cudaSuccess &&
@@ -378,6 +381,7 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
     p.dev_node_ptr = h->d_dev_node_ptr.p; p.dev_nodes = h->d_dev_nodes.p;
     p.dev_param_ptr = h->d_dev_param_ptr.p; p.dev_params = h->d_dev_params.p;
     p.dev_gbase = h->d_dev_gbase.p; p.dev_cbase = h->d_dev_cbase.p; p.dev_bbase = h->d_dev_bbase.p;
+    p.dev_sbase = h->d_dev_sbase.p;
     p.src_list = h->d_src_list.p; p.nl_list = h->d_nl_list.p; p.src_uniform = h->d_src_uniform.p;
     p.uniform = h->d_uniform.p; p.lanes = nullptr;
     p.limit_init_ref = h->d_limit_init_ref.p;
@@ -445,7 +449,7 @@ static int ensure_lane_buffers(cb200_handle *h)
 
 static int ensure_global_ws(cb200_handle *h)
 {
-    const size_t need = (size_t)h->prog.n_slots * h->P;
+    const size_t need = (size_t)h->prog.n_slots * ((h->P + 63) / 64 * 64);   // lane kernels pad to the block (64)
     if (h->d_ws_global.n < need) CUDA_TRY(h, h->d_ws_global.alloc(need));
     return CB200_OK;
 }
@@ -1140,7 +1144,7 @@ extern "C" int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t
     in.st = &h->st; in.prog = &h->prog;
     in.dev_kind = &h->dev_kind; in.dev_flags = &h->dev_flags; in.dev_node_ptr = &h->dev_node_ptr;
     in.dev_nodes = &h->dev_nodes; in.dev_param_ptr = &h->dev_param_ptr; in.dev_params = &h->dev_params;
-    in.dev_gbase = &h->dev_gbase; in.dev_cbase = &h->dev_cbase; in.dev_bbase = &h->dev_bbase;
+    in.dev_gbase = &h->dev_gbase; in.dev_cbase = &h->dev_cbase; in.dev_bbase = &h->dev_bbase; in.dev_sbase = &h->dev_sbase;
     in.src_list = &h->src_list; in.nl_list = &h->nl_list; in.limit_init_ref = &h->limit_init_ref;
     in.src_uniform = &h->src_uniform; in.method = method;
     in.va_header_path = h->k.va_header_path;
@@ -1186,6 +1190,7 @@ extern "C" int64_t cb200_emit_source(const cb200_desc *d, const double *absJ_dc,
     h.dev_params = to_int(d->dev_params, nd ? d->dev_param_ptr[nd] : 0);
     h.dev_gbase = to_int64(d->dev_gbase, nd + 1); h.dev_cbase = to_int64(d->dev_cbase, nd + 1);
     h.dev_bbase = to_int64(d->dev_bbase, nd + 1);
+    h.dev_sbase = d->dev_state_ptr ? to_int(d->dev_state_ptr, nd + 1) : std::vector<int>(nd + 1, 0);
     h.uniform.assign(d->uniform, d->uniform + d->n_uniform);
     h.limit_init_ref = to_int(d->limit_init_ref, d->n_limits);
     h.n_lane_cols = d->n_lane_cols;
@@ -1207,7 +1212,7 @@ extern "C" int64_t cb200_emit_source(const cb200_desc *d, const double *absJ_dc,
     in.st = &h.st; in.prog = &h.prog;
     in.dev_kind = &h.dev_kind; in.dev_flags = &h.dev_flags; in.dev_node_ptr = &h.dev_node_ptr;
     in.dev_nodes = &h.dev_nodes; in.dev_param_ptr = &h.dev_param_ptr; in.dev_params = &h.dev_params;
-    in.dev_gbase = &h.dev_gbase; in.dev_cbase = &h.dev_cbase; in.dev_bbase = &h.dev_bbase;
+    in.dev_gbase = &h.dev_gbase; in.dev_cbase = &h.dev_cbase; in.dev_bbase = &h.dev_bbase; in.dev_sbase = &h.dev_sbase;
     in.src_list = &h.src_list; in.nl_list = &h.nl_list; in.limit_init_ref = &h.limit_init_ref;
     in.src_uniform = &h.src_uniform; in.method = method;
     in.uniform = &h.uniform; in.lu_dc = &h.lu[0].host; in.lu_tr = &h.lu[1].host;

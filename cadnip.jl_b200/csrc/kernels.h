@@ -14,6 +14,7 @@ struct Program {
     int64_t P;                      // lanes on this device
     const int *dev_kind, *dev_flags, *dev_node_ptr, *dev_nodes, *dev_param_ptr, *dev_params;
     const int *dev_gbase, *dev_cbase, *dev_bbase;
+    const int *dev_sbase;           // first private state slot of each device (relative to off_DS)
     const int *src_list;            // devices whose stamps depend on t only (sources)
     const int *nl_list;             // devices whose stamps depend on the iterate x
     const unsigned char *src_uniform;  // [n_src] 1: every parameter of the source is uniform
@@ -26,6 +27,7 @@ struct Program {
     // lane workspace: slot offsets (in doubles); element (slot) of a lane lives at
     // ws[slot * stride + lane_in_block]  (shared) or ws[slot * P + lane] (global).
     int off_u, off_un, off_dterm, off_F, off_wv, off_SG, off_SC, off_SB, off_LU, off_limw, off_lp;
+    int off_DS;                     // private device state (Verilog-A set-up values)
     int off_srcc;                   // [n_src] warp-cooperative source value cache
     int off_h1, off_h2;             // adaptive history (u_{n-1}, u_{n-2})
     int n_slots;

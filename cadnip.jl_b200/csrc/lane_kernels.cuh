@@ -64,6 +64,7 @@ struct DynProg {
     __device__ __forceinline__ int dev_gbase(int d) const { return __ldg(p.dev_gbase + d); }
     __device__ __forceinline__ int dev_cbase(int d) const { return __ldg(p.dev_cbase + d); }
     __device__ __forceinline__ int dev_bbase(int d) const { return __ldg(p.dev_bbase + d); }
+    __device__ __forceinline__ int dev_sbase(int d) const { return __ldg(p.dev_sbase + d); }
     __device__ __forceinline__ double uniform(int r) const { return __ldg(p.uniform + r); }
     __device__ __forceinline__ int limit_init_ref(int k) const { return __ldg(p.limit_init_ref + k); }
     __device__ __forceinline__ int gseg_ptr(int s) const { return __ldg(p.gseg_ptr + s); }
@@ -86,6 +87,7 @@ struct DynProg {
     __device__ __forceinline__ int off_LU() const { return p.off_LU; }
     __device__ __forceinline__ int off_limw() const { return p.off_limw; }
     __device__ __forceinline__ int off_lp() const { return p.off_lp; }
+    __device__ __forceinline__ int off_DS() const { return p.off_DS; }
     __device__ __forceinline__ int off_srcc() const { return p.off_srcc; }
     __device__ __forceinline__ int off_h1() const { return p.off_h1; }
     __device__ __forceinline__ int off_h2() const { return p.off_h2; }

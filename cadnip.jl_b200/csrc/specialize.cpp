@@ -175,7 +175,8 @@ std::string generate_spec_source(const SpecInput &in)
     std::ostringstream o;
     o << "// generated by cadnip-b200 (specialize.cpp) -- circuit-specialised kernels; do not edit\n";
     if (!in.va_header_path.empty())
-        o << "#define CB200_VA_FN __forceinline__\n#define CB200_VA_HEADER \"" << in.va_header_path << "\"\n";
+        o << "#define CB200_VA_FN " << (getenv("CB200_SPEC_VA_NOINLINE") ? "__noinline__" : "__forceinline__")
+          << "\n#define CB200_VA_HEADER \"" << in.va_header_path << "\"\n";
     o << "#include \"lane_kernels.cuh\"\n";
     o << "namespace {\nusing namespace cb200;\n";
     o << "struct SProg {\n";
@@ -199,6 +200,7 @@ std::string generate_spec_source(const SpecInput &in)
     emit_int_table(o, "dev_gbase", *in.dev_gbase);
     emit_int_table(o, "dev_cbase", *in.dev_cbase);
     emit_int_table(o, "dev_bbase", *in.dev_bbase);
+    emit_int_table(o, "dev_sbase", *in.dev_sbase);
     o << "    __device__ static constexpr double uniform(int i) { constexpr double t[] = {";
     if (in.uniform->empty()) o << "0.0";
     for (size_t i = 0; i < in.uniform->size(); i++) o << (i ? "," : "") << hexdouble((*in.uniform)[i]);
@@ -225,6 +227,7 @@ std::string generate_spec_source(const SpecInput &in)
     emit_const(o, "off_SC", p.off_SC); emit_const(o, "off_SB", p.off_SB);
     emit_const(o, "off_LU", p.off_LU); emit_const(o, "off_limw", p.off_limw);
     emit_const(o, "off_lp", p.off_lp); emit_const(o, "off_srcc", p.off_srcc);
+    emit_const(o, "off_DS", p.off_DS);
     emit_const(o, "off_h1", p.off_h1);
     emit_const(o, "off_h2", p.off_h2);
     // straight-line device evaluation lists (eval_all / eval_nonlinear / eval_sources)

@@ -16,7 +16,7 @@ struct SpecInput {
     const Structure *st;
     const Program *prog;              // workspace offsets / n_slots
     const std::vector<int> *dev_kind, *dev_flags, *dev_node_ptr, *dev_nodes, *dev_param_ptr,
-        *dev_params, *dev_gbase, *dev_cbase, *dev_bbase, *src_list, *nl_list, *limit_init_ref;
+        *dev_params, *dev_gbase, *dev_cbase, *dev_bbase, *dev_sbase, *src_list, *nl_list, *limit_init_ref;
     const std::vector<double> *uniform;
     const std::vector<unsigned char> *src_uniform;
     int method;                       // CB200_METHOD_* compiled into the transient kernel

@@ -59,6 +59,7 @@ class LoweredCircuit:
     breakpoints: List[Any]
     va_models: List[Any] = field(default_factory=list)   # VAModel per DEV_VA flags value
     n_user_nodes: int = -1          # nodes allocated by get_node! (the rest are internal nodes)
+    dev_state_ptr: Optional[np.ndarray] = None   # [n_dev+1] private state slots per device (VA set-up values)
     va_cuda_header: str = ""        # emitted CUDA for the circuit's Verilog-A modules (cb200_load_va_models)
     va_c_source: str = ""           # the same modules as plain C: input of the CPU oracle, never run by the product
 
@@ -216,6 +217,7 @@ def lower(builder, params: Params, spec: MNASpec, P: int = 1) -> LoweredCircuit:
 
     kind, flags, node_ptr, nodes, par_ptr, pars = [], [], [0], [], [0], []
     gbase, cbase, bbase, names, user_nodes = [], [], [], [], []
+    state_ptr = [0]
     va_models: List[Any] = []
     for d in ctx.devices:
         f = d.flags
@@ -231,6 +233,7 @@ def lower(builder, params: Params, spec: MNASpec, P: int = 1) -> LoweredCircuit:
         pars += [pool.ref(v) for v in d.params]
         par_ptr.append(len(pars))
         gbase.append(d.gbase); cbase.append(d.cbase); bbase.append(d.bbase)
+        state_ptr.append(state_ptr[-1] + (d.model.n_state if d.model is not None else 0))
         user_nodes.append(list(d.user_nodes))
     gbase.append(len(ctx.G_I)); cbase.append(len(ctx.C_I)); bbase.append(len(ctx.b_I))
     limit_init_ref = [pool.ref(v) for v in ctx.limit_init]
@@ -252,6 +255,7 @@ def lower(builder, params: Params, spec: MNASpec, P: int = 1) -> LoweredCircuit:
         lane_soa=np.ascontiguousarray(soa, dtype=np.float64), P=P,
         dev_names=names, dev_user_nodes=user_nodes, breakpoints=list(ctx.breakpoints),
         va_models=va_models, n_user_nodes=_user_node_count(ctx),
+        dev_state_ptr=np.asarray(state_ptr, dtype=np.int32),
         va_cuda_header=_va.cuda_header(va_models) if va_models else "",
         va_c_source=_va.c_source(va_models) if va_models else "")
 

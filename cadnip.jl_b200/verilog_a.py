@@ -46,6 +46,15 @@ import numpy as np
 
 CHARGE_SCALE = 1e12          # src/mna/contrib.jl:39
 
+# Emit the bias-independent part of a module (parameter / temperature preprocessing) as a separate
+# set-up section that runs once per kernel and hands its results to the per-iteration code through
+# private state slots.  Measured on B200 (C3, two sp_mos1 instances, circuit-specialised kernel): the
+# compiler already hoists that code out of the time loop, and the ~100 extra state doubles per
+# instance cost more local-memory traffic than the hoisting saves (485 ms vs 364 ms), so it is OFF
+# by default; it pays only where the model body is not inlined.
+import os as _os
+SPLIT_SETUP = _os.environ.get("CB200_VA_SPLIT", "0") == "1"
+
 
 class VAError(ValueError):
     pass
@@ -882,6 +891,13 @@ class _Emitter:
         self.nodes = ports + [n for n in mod["electrical"] if n not in ports]
         self.N = len(self.nodes)
         self.lines: List[str] = []
+        self.tags: List[str] = []    # per line: 'S' bias-independent set-up, 'D' per-evaluation, 'B' both
+        self.dyn: set = {"t", "va_initjct"}   # C identifiers whose value depends on the operating point
+        self.dyn_depth = 0           # > 0 inside control flow that depends on the operating point
+        self.ver: Dict[str, int] = {}
+        self.snap: Dict[str, Tuple[int, str, Tuple[int, ...]]] = {}
+        self.blocks: List[int] = []  # open C blocks (ids), for the scope of cached snapshots
+        self.block_id = 0
         self.tmp = 0
         self.indent = 1
         self.act, self.bact = act, bact
@@ -900,14 +916,39 @@ class _Emitter:
         self.collapse: Dict[str, Tuple[str, Any]] = {}            # internal node -> (port, condition AST)
 
     # -- helpers ------------------------------------------------------------ #
-    def emit(self, s: str):
+    _IDENT = re.compile(r"[A-Za-z_][A-Za-z0-9_]*")
+
+    def is_dyn(self, expr: str) -> bool:
+        """Does a C expression read anything that depends on the operating point?"""
+        for name in self._IDENT.findall(expr):
+            if name in self.dyn:
+                return True
+            c = name[0]
+            if c == "V" and name[1:].isdigit():
+                return True
+            if name.startswith("vold") or name.startswith("limw"):
+                return True
+        return False
+
+    def emit(self, s: str, tag: str = "D"):
         self.lines.append("    " * self.indent + s)
+        self.tags.append("D" if self.dyn_depth else tag)
 
     def temp(self, expr: str) -> str:
         self.tmp += 1
         name = f"t{self.tmp}"
-        self.emit(f"const double {name} = {expr};")
+        dyn = self.dyn_depth > 0 or self.is_dyn(expr)
+        if dyn:
+            self.dyn.add(name)
+        self.emit(f"const double {name} = {expr};", "D" if dyn else "S")
         return name
+
+    def open_block(self):
+        self.block_id += 1
+        self.blocks.append(self.block_id)
+
+    def close_block(self):
+        self.blocks.pop()
 
     def const(self, x: float) -> _D:
         return _D(_lit(x), {}, float(x))
@@ -970,14 +1011,12 @@ class _Emitter:
             return self.const(a.const / b.const)
         v = self.temp(f"{a.v} / {b.v}")
         d = {}
-        for k in sorted(set(a.d) | set(b.d)):        # (a/b)' = (a' - (a/b) b') / b
+        keys = sorted(set(a.d) | set(b.d))
+        inv = self.temp(f"1.0 / {b.v}") if len(keys) > 1 else None     # one reciprocal for all partials
+        for k in keys:                               # (a/b)' = (a' - (a/b) b') / b
             pa, pb = a.d.get(k), b.d.get(k)
-            if pb is None:
-                d[k] = self.temp(f"{pa} / {b.v}")
-            elif pa is None:
-                d[k] = self.temp(f"-({v} * {pb}) / {b.v}")
-            else:
-                d[k] = self.temp(f"({pa} - {v} * {pb}) / {b.v}")
+            num = pa if pb is None else (f"-({v} * {pb})" if pa is None else f"({pa} - {v} * {pb})")
+            d[k] = self.temp(f"{num} * {inv}" if inv else f"{num} / {b.v}")
         return _D(v, d)
 
     def unary_fn(self, a: _D, val_expr: str, dfac_expr) -> _D:
@@ -1013,10 +1052,26 @@ class _Emitter:
 
     def read_var(self, cname: str) -> _Pair:
         a = self._act(cname)
+        if not a.get("dyn"):
+            # bias-independent variable: hand out an immutable snapshot of its current value, so
+            # per-evaluation code never depends on WHEN the set-up code assigned it
+            ver = self.ver.get(cname, 0)
+            hit = self.snap.get(cname)
+            if hit is not None and hit[0] == ver and tuple(self.blocks[:len(hit[2])]) == hit[2]:
+                return _D(hit[1]), None
+            self.tmp += 1
+            name = f"t{self.tmp}"
+            self.lines.append("    " * self.indent + f"const double {name} = v_{cname};")
+            self.tags.append("S")
+            self.snap[cname] = (ver, name, tuple(self.blocks))
+            return _D(name), None
+        names = [f"v_{cname}"] + [f"v_{cname}_d{k}" for k in a["d"]]
         r = _D(f"v_{cname}", {k: f"v_{cname}_d{k}" for k in sorted(a["d"])})
         q = None
         if a["q"] and cname not in self.qz:
             q = _D(f"vq_{cname}", {k: f"vq_{cname}_d{k}" for k in sorted(a["qd"])})
+            names += [f"vq_{cname}"] + [f"vq_{cname}_d{k}" for k in a["qd"]]
+        self.dyn.update(names)
         return r, q
 
     def assign_var(self, cname: str, val: _Pair):
@@ -1044,13 +1099,20 @@ class _Emitter:
             self.qz.add(cname)
         else:
             self.qz.discard(cname)
-        self.emit(f"v_{cname} = {r.v};")
+        # a variable is per-evaluation (flow-insensitively) once ANY assignment to it depends on
+        # the operating point or sits under control flow that does
+        if not a.get("dyn") and (self.dyn_depth or r.d or q is not None or self.is_dyn(r.v)):
+            a["dyn"] = True
+            self.changed = True
+        tag = "D" if a.get("dyn") else "S"
+        self.ver[cname] = self.ver.get(cname, 0) + 1
+        self.emit(f"v_{cname} = {r.v};", tag)
         for k in sorted(a["d"]):
-            self.emit(f"v_{cname}_d{k} = {r.d.get(k, '0.0')};")
+            self.emit(f"v_{cname}_d{k} = {r.d.get(k, '0.0')};", tag)
         if a["q"]:
-            self.emit(f"vq_{cname} = {q.v if q is not None else '0.0'};")
+            self.emit(f"vq_{cname} = {q.v if q is not None else '0.0'};", tag)
             for k in sorted(a["qd"]):
-                self.emit(f"vq_{cname}_d{k} = {q.d.get(k, '0.0') if q is not None else '0.0'};")
+                self.emit(f"vq_{cname}_d{k} = {q.d.get(k, '0.0') if q is not None else '0.0'};", tag)
 
     # -- expressions ---------------------------------------------------------- #
     def ev(self, e) -> _Pair:
@@ -1310,12 +1372,14 @@ class _Emitter:
             self.vtypes[cn] = f["rtype"] if name == f["name"] else f["vtypes"].get(name, "real")
             if cn not in self.decl_order:
                 self.decl_order.append(cn)
-        self.emit(f"/* {f['name']}() */")
+        self.emit(f"/* {f['name']}() */", "B")
         # locals start at zero on every call
         for name in [f["name"]] + f["args"] + f["vars"]:
             cn = scope[name]
             a = self._act(cn)
-            self.emit(f"v_{cn} = 0.0;" + "".join(f" v_{cn}_d{k} = 0.0;" for k in sorted(a["d"])))
+            self.ver[cn] = self.ver.get(cn, 0) + 1
+            self.emit(f"v_{cn} = 0.0;" + "".join(f" v_{cn}_d{k} = 0.0;" for k in sorted(a["d"])),
+                      "D" if a.get("dyn") else "S")
         self.scopes.append(scope)
         for a, v in zip(f["args"], vals):
             if f["dirs"][a] in ("input", "inout"):
@@ -1352,8 +1416,8 @@ class _Emitter:
         vnew = self.probe(*key)
         vals = [(vnew, None), (_D(f"vold{b}"), None)] + [self.ev(a) for a in args[2:]]
         r = self.user_call(self.mod["functions"][args[1][1]], vals, [None, None] + list(args[2:]))
-        self.emit(f"const double limw{j} = {r.v};")
-        self.emit(f"VA_LIMW({b}, limw{j});")                      # record_limit_w!
+        self.emit(f"const double limw{j} = {r.v};", "D")
+        self.emit(f"VA_LIMW({b}, limw{j});", "D")                 # record_limit_w!
         d = dict(vnew.d)                                           # pass-through: +1 / -1 on the probe nodes
         d[self.N + j] = "1.0"                                      # and the site's own slot
         return _D(f"limw{j}", d)
@@ -1377,19 +1441,26 @@ class _Emitter:
                 self.stmt(s[2] if c.const != 0.0 else s[3])
                 return
             self.cond_depth += 1
+            cdyn = self.is_dyn(c.v)
+            self.dyn_depth += cdyn
             qz0 = set(self.qz)
-            self.emit(f"if ({c.v} != 0.0) {{")
+            self.emit(f"if ({c.v} != 0.0) {{", "B")
             self.indent += 1
+            self.open_block()
             self.stmt(s[2])
+            self.close_block()
             self.indent -= 1
             qz1, self.qz = self.qz, set(qz0)
             if s[3] != ("block", []):
-                self.emit("} else {")
+                self.emit("} else {", "B")
                 self.indent += 1
+                self.open_block()
                 self.stmt(s[3])
+                self.close_block()
                 self.indent -= 1
-            self.emit("}")
+            self.emit("}", "B")
             self.qz &= qz1
+            self.dyn_depth -= cdyn
             self.cond_depth -= 1
         elif kind == "case":
             sel, sq = self.ev(s[1])
@@ -1405,14 +1476,18 @@ class _Emitter:
             self.stmt(s[1])
             self.cond_depth += 1
             self.qz = set()                              # loop-carried values: assume nothing
+            self.dyn_depth += 1                          # loops are evaluated per evaluation, whole
             self.emit("for (;;) {")
             self.indent += 1
+            self.open_block()
             c, cq = self.ev(s[2])
             self.emit(f"if (!({c.v} != 0.0)) break;")
             self.stmt(s[4])
             self.stmt(s[3])
+            self.close_block()
             self.indent -= 1
             self.emit("}")
+            self.dyn_depth -= 1
             self.qz = set()
             self.cond_depth -= 1
         elif kind == "contrib":
@@ -1675,6 +1750,69 @@ class VAVariant:
                      " ".join(f"(void){x};" for x in names))
         return L
 
+    @staticmethod
+    def _prune(lines: List[str]) -> List[str]:
+        """Drop control-flow skeletons left empty after the set-up / evaluation split."""
+        changed = True
+        while changed:
+            changed = False
+            out: List[str] = []
+            i = 0
+            while i < len(lines):
+                a = lines[i].strip()
+                b = lines[i + 1].strip() if i + 1 < len(lines) else ""
+                if a.startswith("/*") and a.endswith("*/") and (b.startswith("/*") or b in ("}", "} else {", "")):
+                    i += 1; changed = True; continue
+                if a.startswith("if (") and a.endswith("{") and b == "}":
+                    i += 2; changed = True; continue
+                if a == "} else {" and b == "}":
+                    out.append(lines[i + 1]); i += 2; changed = True; continue
+                out.append(lines[i]); i += 1
+            lines = out
+        return lines
+
+    def _sections(self, split: Optional[bool] = None) -> Tuple[List[str], List[str], int]:
+        """(set-up lines, per-evaluation lines, number of exported values).  Set-up = the
+        bias-independent part of the analog block (parameter and temperature preprocessing),
+        executed once per kernel; the values the per-evaluation code reads from it are stored
+        to the instance's private state slots (VA_ST) and loaded back (VA_LD).  Without the
+        split everything is per-evaluation code, in program order."""
+        split = SPLIT_SETUP if split is None else split
+        cache = self.__dict__.setdefault("_sec", {})
+        if split in cache:
+            return cache[split]
+        em = self._em
+        if not split:
+            cache[split] = ([], list(em.lines), 0)
+            return cache[split]
+        S = self._prune([ln for ln, t in zip(em.lines, em.tags) if t in ("S", "B")])
+        D = self._prune([ln for ln, t in zip(em.lines, em.tags) if t in ("D", "B")])
+        defs = {}
+        for ln in S:
+            m = re.match(r"\s*const double (t\d+) = ", ln)
+            if m:
+                defs[m.group(1)] = True
+        used: List[str] = []
+        seen = set()
+        for ln in D:
+            for name in re.findall(r"\bt\d+\b", ln):
+                if name in defs and name not in seen and not re.match(rf"\s*const double {name} = ", ln):
+                    seen.add(name); used.append(name)
+        slot = {name: k for k, name in enumerate(used)}
+        S2: List[str] = []
+        for ln in S:
+            S2.append(ln)
+            m = re.match(r"(\s*)const double (t\d+) = ", ln)
+            if m and m.group(2) in slot:
+                S2.append(f"{m.group(1)}VA_ST({slot[m.group(2)]}, {m.group(2)});")
+        loads = [f"    const double {name} = VA_LD({k}); (void){name};" for name, k in slot.items()]
+        cache[split] = (S2, loads + D, len(used))
+        return cache[split]
+
+    @property
+    def n_state(self) -> int:
+        return self._sections()[2]
+
     def _body(self, charge_alloc: bool = False) -> str:
         """Shared by the CUDA and the C back end: they differ only in the prologue and in
         the stamping macros.  charge_alloc: emit the oracle's run-time detection protocol."""
@@ -1704,7 +1842,12 @@ class VAVariant:
             if ba["q"]:
                 names += [f"Q{bi}"] + [f"Q{bi}_d{k}" for k in sorted(ba["qd"])]
             L.append("    double " + ", ".join(f"{x} = 0.0" for x in names) + ";")
-        L += em.lines
+        setup, evaln, _ = self._sections()
+        if setup:
+            L.append("    if (VA_SETUP) {   /* bias-independent part: once per kernel (PASS 0) */")
+            L += setup
+            L.append("    }")
+        L += evaln
 
         def part(prefix, bi, k, act):
             return f"va_mfactor * {prefix}{bi}_d{k}" if k in act else "0.0"
@@ -1797,6 +1940,7 @@ class VAVariant:
                 "    const int nb = pg.dev_node_ptr(d), pb = pg.dev_param_ptr(d);",
                 "    int g = pg.off_SG() + pg.dev_gbase(d), c = pg.off_SC() + pg.dev_cbase(d);",
                 "    int b = pg.off_SB() + pg.dev_bbase(d);",
+                "    const int sb = pg.off_DS() + pg.dev_sbase(d); (void)sb;   // this instance's private state",
                 "    (void)c;"]
         for i in range(self.n_slots):
             head.append(f"    const int n{i} = pg.dev_node(nb + {i});")
@@ -1814,7 +1958,8 @@ class VAVariant:
              "{",
              "    (void)t; (void)va_mode;",
              "    const double va_initjct = A->initjct(ctx) ? 1.0 : 0.0; (void)va_initjct;",
-             f"    long n[{N + nlim + 1}]; long QX = {N + nlim}; (void)QX;"]
+             f"    long n[{N + nlim + 1}]; long QX = {N + nlim}; (void)QX;",
+             f"    double va_state[{self.n_state + 1}];"]
         for i in range(len(self.ports)):
             L.append(f"    n[{i}] = ports[{i}];")
         if self.model.collapses:
@@ -2089,6 +2234,9 @@ _CUDA_PRELUDE = """// generated by cadnip_b200.verilog_a -- Verilog-A device mod
 #define VA_C(i, j, v) do { if (n##i != 0 && n##j != 0) { w(c) = (v); c++; } } while (0)
 #define VA_B(i, v) do { if (n##i != 0) { w(b) = (v); b++; } } while (0)
 #define VA_LIMW(bi, v) w(pg.off_limw() + (VA_LIMSLOT(bi) - 1 - (pg.n() - pg.n_limits()))) = (v)
+#define VA_SETUP (PASS == 0)
+#define VA_ST(k, v) w(sb + (k)) = (v)
+#define VA_LD(k) w(sb + (k))
 /* included from lane_kernels.cuh, inside namespace cb200 */
 """
 
@@ -2101,6 +2249,9 @@ _CUDA_EPILOGUE = """
 #undef VA_C
 #undef VA_B
 #undef VA_LIMW
+#undef VA_SETUP
+#undef VA_ST
+#undef VA_LD
 """
 
 _C_PRELUDE = """/* generated by cadnip_b200.verilog_a -- Verilog-A device models for the CPU oracle */
@@ -2124,6 +2275,9 @@ typedef struct ora_va_api {
 #define VA_G(i, j, v) A->stamp_G(ctx, n[i], n[j], (v))
 #define VA_C(i, j, v) A->stamp_C(ctx, n[i], n[j], (v))
 #define VA_B(i, v) A->stamp_b(ctx, n[i], (v))
+#define VA_SETUP 1
+#define VA_ST(k, v) va_state[k] = (v)
+#define VA_LD(k) va_state[k]
 #define VA_DETECT(vb, q) A->detect_or_cached(ctx, (vb), (q))
 #define VA_ALLOC_Q(slot, p, nn) n[slot] = A->alloc_charge(ctx, n[p], (nn) < 0 ? 0 : n[(nn) < 0 ? 0 : (nn)])
 """

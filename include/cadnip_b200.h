@@ -128,6 +128,9 @@ typedef struct cb200_desc {
     const int32_t *limit_init_ref;      /* [n_limits] parameter refs (context.jl:826) */
     int32_t n_lane_cols;                /* columns cb200_set_lanes must supply */
     int32_t _pad;
+    const int32_t *dev_state_ptr;       /* [n_devices+1] or NULL: private per-lane state slots of each
+                                           device (bias-independent set-up values of Verilog-A
+                                           instances, computed once per kernel)            */
 } cb200_desc;
 
 typedef struct cb200_handle cb200_handle;

@@ -73,6 +73,14 @@ def test_sp_mos1_structure():
     assert inst.collapsed(cb.MNASpec()) == {"d_int": "d", "s_int": "s"}
     assert m(type=1, rd=10.0).collapsed(cb.MNASpec()) == {"s_int": "s"}
     assert m(VTO=0.7).given == frozenset({"vto"}) and m(vt0=0.7).given == frozenset({"vto"})   # aliasparam
+    # set-up / evaluation split: parameter and temperature preprocessing (mos1.va:560-900) runs once
+    # per kernel and hands its results to the per-iteration code through private state slots
+    var = m.variant(inst.given, None)
+    setup, evaln, n_state = var._sections(split=True)     # optional (verilog_a.SPLIT_SETUP), off by default
+    assert 40 < n_state < 200
+    assert sum(ln.count("VA_ST(") for ln in setup) == n_state == sum(ln.count("VA_LD(") for ln in evaln)
+    assert not any("V0" in ln or "vold" in ln or "limw" in ln for ln in setup)      # nothing bias-dependent
+    assert sum(ln.count("log(") for ln in setup) >= 5 and sum(ln.count("CB_EXP(") for ln in setup) >= 3
 
 
 @needs_ref
@@ -103,6 +111,7 @@ def test_host_coo_matches_oracle_builder(name):
 
 def test_sp_mos1_unknown_count():
     lc = fixture("mos1_inverter")
+    assert lc.dev_state_ptr[0] == 0 and np.all(np.diff(lc.dev_state_ptr) >= 0)
     # 4 nodes + 3 source currents + 2 x 4 limit unknowns; zero device caps -> no charge states
     assert (lc.n_nodes, lc.n_currents, lc.n_charges, lc.n_limits) == (4, 3, 0, 8)
     assert lc.limit_names[:4] == ["MP_sp_mos1_lim_g_s_int", "MP_sp_mos1_lim_d_int_s_int",
@@ -292,6 +301,29 @@ def test_gpu_va_models_transient(name, tspan, dt, method, spec):
         vdd = gpu[:, 0, lc.index_of("vdd") - 1]
         assert np.all(q.max(axis=1) > 0.95 * vdd)                          # it inverts ...
         assert np.all(q[:4].min(axis=1) < 0.05 * vdd[:4])                  # ... fully, with the 1 fF load
+
+
+@pytest.mark.gpu
+def test_gpu_global_workspace_path_with_ragged_lane_count(monkeypatch):
+    """Lane state in HBM ([slot][lane], the layout for circuits too large for shared memory) with a
+    lane count that is not a multiple of the block: every thread must own its workspace column."""
+    monkeypatch.setenv("CB200_FORCE_GLOBAL_WS", "1")
+    lc = fixture("mos1_inverter")                      # 8 lanes, blocks of 64
+    nl = oracle_of(lc)
+    save = list(range(1, lc.n + 1))
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        x, st, it = comp.dc()
+        wave = comp.tran((0.0, 4e-9), 1e-11, method="trap", save_idxs=save)
+        r = wave.fetch(); wave.free()
+    finally:
+        comp.close()
+    xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
+    assert np.array_equal(st, sto) and _close(x.T, xo, rtol=1e-8, atol=1e-10) and np.array_equal(it, ito)
+    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 4e-9, ora.make_tran_opts(method=1, dt=1e-11), save)
+    gpu = np.transpose(r["u"], (2, 1, 0))
+    assert (r["status"] == 0).all() and np.array_equal(r["newton_iters"], ro["newton_iters"])
+    assert _close(gpu, ro["u"][:, :gpu.shape[1], :], rtol=1e-7, atol=1e-9)
 
 
 @pytest.mark.gpu
