@@ -1220,6 +1220,7 @@ extern "C" int64_t cb200_emit_source(const cb200_desc *d, const double *absJ_dc,
     in.block = 64;
     const int64_t lanes_per_sm = (P + num_sms - 1) / num_sms;
     in.min_blocks = std::max(1, std::min((int)((lanes_per_sm + in.block - 1) / in.block), 1024 / in.block));
+    if (h.prog.n_slots > 120) in.min_blocks = std::min(in.min_blocks, 4);
     const std::string src = generate_spec_source(in);
     if (out && cap > 0) {
         const int64_t m = std::min<int64_t>(cap - 1, (int64_t)src.size());

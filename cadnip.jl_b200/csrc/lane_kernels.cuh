@@ -224,29 +224,40 @@ __device__ __forceinline__ double source_value(const PG &pg, W &w, int wave, int
     }
     // PWL: pwl_at_time devices.jl:47-71 with find_t_in_ts :30-36.  Written as a
     // branch-free scan so that it unrolls for a static program.
+    // Every parameter is READ FIRST and selected after: a read guarded by `k == i` lets the
+    // optimiser substitute the run-time i for the constant k, i.e. index the parameter tables --
+    // and through them the register workspace -- dynamically, which demotes the whole lane state
+    // of a specialised kernel to local memory.
     const int np = (npar - 1) / 2;
     int i = 1;                              // 1-based searchsortedfirst
     CB_UNROLL
-    for (int k = 1; k <= np; k++)
-        if (param(pg, w, pb, 1 + 2 * (k - 1)) < t) i = k + 1;
+    for (int k = 1; k <= np; k++) {
+        const double tk = param(pg, w, pb, 1 + 2 * (k - 1));
+        i = (tk < t) ? k + 1 : i;
+    }
     double result = 0.0;
     bool found = false;
     // step past an exact hit
     bool hit = false;
     CB_UNROLL
-    for (int k = 1; k <= np; k++)
-        if (k == i && param(pg, w, pb, 1 + 2 * (k - 1)) == t) hit = true;
+    for (int k = 1; k <= np; k++) {
+        const double tk = param(pg, w, pb, 1 + 2 * (k - 1));
+        hit = (k == i && tk == t) ? true : hit;
+    }
     if (hit) i++;
-    if (i <= 1) { result = param(pg, w, pb, 2); found = true; }
-    if (!found && i > np) { result = param(pg, w, pb, 2 + 2 * (np - 1)); found = true; }
+    const double y_first = param(pg, w, pb, 2), y_last = param(pg, w, pb, 2 + 2 * (np - 1));
+    if (i <= 1) { result = y_first; found = true; }
+    if (!found && i > np) { result = y_last; found = true; }
     if (!found) {
         double t0 = 0, y0 = 0, t1 = 0, y1 = 0;
         CB_UNROLL
-        for (int k = 2; k <= np; k++)
-            if (k == i) {
-                t0 = param(pg, w, pb, 1 + 2 * (k - 2)); y0 = param(pg, w, pb, 2 + 2 * (k - 2));
-                t1 = param(pg, w, pb, 1 + 2 * (k - 1)); y1 = param(pg, w, pb, 2 + 2 * (k - 1));
-            }
+        for (int k = 2; k <= np; k++) {
+            const double a0 = param(pg, w, pb, 1 + 2 * (k - 2)), b0 = param(pg, w, pb, 2 + 2 * (k - 2));
+            const double a1 = param(pg, w, pb, 1 + 2 * (k - 1)), b1 = param(pg, w, pb, 2 + 2 * (k - 1));
+            const bool sel = (k == i);
+            t0 = sel ? a0 : t0; y0 = sel ? b0 : y0;
+            t1 = sel ? a1 : t1; y1 = sel ? b1 : y1;
+        }
         if (y0 == y1) result = y1;
         else if (t1 == t0) result = (y0 + y1) / 2;
         else {

@@ -18,12 +18,22 @@
 
 namespace cb200 {
 
+// Tables live at namespace scope (`__device__ constexpr`): an access with a constant index
+// folds to the literal, one with a run-time index is a read-only global load.  A function-local
+// `constexpr T t[]` would be copied to the STACK for any run-time index -- and the stores that
+// rebuild it stay in the kernel even when every such access is later optimised away.
+static std::ostringstream *g_data = nullptr;     // namespace-scope table definitions of the file being generated
+static std::string g_prefix;                     // struct the accessors belong to (table names must be unique)
+
 static void emit_int_table(std::ostringstream &o, const char *name, const std::vector<int> &v)
 {
-    o << "    __device__ static constexpr int " << name << "(int i) { constexpr int t[] = {";
-    if (v.empty()) o << "0";
-    for (size_t i = 0; i < v.size(); i++) o << (i ? "," : "") << v[i];
-    o << "}; return t[i]; }\n";
+    std::ostringstream &d = *g_data;
+    d << "__device__ constexpr int k_" << g_prefix << "_" << name << "[] = {";
+    if (v.empty()) d << "0";
+    for (size_t i = 0; i < v.size(); i++) d << (i ? "," : "") << v[i];
+    d << "};\n";
+    o << "    __device__ static constexpr int " << name << "(int i) { return k_" << g_prefix << "_" << name
+      << "[i]; }\n";
 }
 
 static void emit_const(std::ostringstream &o, const char *name, long long v)
@@ -147,6 +157,7 @@ static void emit_factor_solve(std::ostringstream &o, const Program &p, const LuS
 static void emit_lu(std::ostringstream &o, const char *sname, const Structure &st, const Program &p,
                     const LuSchedule &S)
 {
+    g_prefix = sname;
     o << "struct " << sname << " {\n";
     emit_assemble(o, st, p, S);
     emit_factor_solve(o, p, S);
@@ -172,13 +183,15 @@ std::string generate_spec_source(const SpecInput &in)
 {
     const Structure &st = *in.st;
     const Program &p = *in.prog;
-    std::ostringstream o;
-    o << "// generated by cadnip-b200 (specialize.cpp) -- circuit-specialised kernels; do not edit\n";
+    std::ostringstream head, data, o;
+    g_data = &data;
+    g_prefix = "SProg";
+    head << "// generated by cadnip-b200 (specialize.cpp) -- circuit-specialised kernels; do not edit\n";
     if (!in.va_header_path.empty())
-        o << "#define CB200_VA_FN " << (getenv("CB200_SPEC_VA_NOINLINE") ? "__noinline__" : "__forceinline__")
-          << "\n#define CB200_VA_HEADER \"" << in.va_header_path << "\"\n";
-    o << "#include \"lane_kernels.cuh\"\n";
-    o << "namespace {\nusing namespace cb200;\n";
+        head << "#define CB200_VA_FN " << (getenv("CB200_SPEC_VA_NOINLINE") ? "__noinline__" : "__forceinline__")
+             << "\n#define CB200_VA_HEADER \"" << in.va_header_path << "\"\n";
+    head << "#include \"lane_kernels.cuh\"\n";
+    head << "namespace {\nusing namespace cb200;\n";
     o << "struct SProg {\n";
     o << "    static constexpr bool kStatic = true;\n    static constexpr int kUnroll = 4096;\n";
     o << "    static constexpr int kMethod = " << in.method << ";\n";
@@ -201,10 +214,11 @@ std::string generate_spec_source(const SpecInput &in)
     emit_int_table(o, "dev_cbase", *in.dev_cbase);
     emit_int_table(o, "dev_bbase", *in.dev_bbase);
     emit_int_table(o, "dev_sbase", *in.dev_sbase);
-    o << "    __device__ static constexpr double uniform(int i) { constexpr double t[] = {";
-    if (in.uniform->empty()) o << "0.0";
-    for (size_t i = 0; i < in.uniform->size(); i++) o << (i ? "," : "") << hexdouble((*in.uniform)[i]);
-    o << "}; return t[i]; }\n";
+    data << "__device__ constexpr double k_SProg_uniform[] = {";
+    if (in.uniform->empty()) data << "0.0";
+    for (size_t i = 0; i < in.uniform->size(); i++) data << (i ? "," : "") << hexdouble((*in.uniform)[i]);
+    data << "};\n";
+    o << "    __device__ static constexpr double uniform(int i) { return k_SProg_uniform[i]; }\n";
     emit_int_table(o, "limit_init_ref", *in.limit_init_ref);
     emit_int_table(o, "gseg_ptr", st.gseg_ptr);
     emit_int_table(o, "gseg_idx", st.gseg_idx);
@@ -216,10 +230,11 @@ std::string generate_spec_source(const SpecInput &in)
     emit_int_table(o, "rowval", st.rowval);
     {
         std::vector<int> nd(st.nz_is_node_diag.begin(), st.nz_is_node_diag.end());
-        o << "    __device__ static constexpr bool nz_is_node_diag(int i) { constexpr int t[] = {";
-        if (nd.empty()) o << "0";
-        for (size_t i = 0; i < nd.size(); i++) o << (i ? "," : "") << nd[i];
-        o << "}; return t[i] != 0; }\n";
+        data << "__device__ constexpr int k_SProg_nz_is_node_diag[] = {";
+        if (nd.empty()) data << "0";
+        for (size_t i = 0; i < nd.size(); i++) data << (i ? "," : "") << nd[i];
+        data << "};\n";
+        o << "    __device__ static constexpr bool nz_is_node_diag(int i) { return k_SProg_nz_is_node_diag[i] != 0; }\n";
     }
     emit_const(o, "off_u", p.off_u); emit_const(o, "off_un", p.off_un);
     emit_const(o, "off_dterm", p.off_dterm); emit_const(o, "off_F", p.off_F);
@@ -272,7 +287,8 @@ std::string generate_spec_source(const SpecInput &in)
          "                                                const cb200::AdaptArgs *a, cudaStream_t st)\n{\n"
          "    const unsigned grid = (unsigned)((p->P + kBlock - 1) / kBlock);\n"
          "    cb200_spec_tran_adaptive_kernel<<<grid, kBlock, 0, st>>>(*p, *s, *a);\n    return cudaGetLastError();\n}\n";
-    return o.str();
+    g_data = nullptr;
+    return head.str() + data.str() + o.str();
 }
 
 static uint64_t fnv1a(uint64_t h, const std::string &s)

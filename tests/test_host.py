@@ -230,14 +230,25 @@ def test_emitter_generates_compilable_source(tmp_path):
     """cb200_emit_source -> nvcc (sm_100a cross-compile, no GPU needed)."""
     import subprocess
     import cadnip_oracle as ora
-    from cadnip_b200.workloads import clipper_sweep
-    cs = clipper_sweep(4, 3)
+    from cadnip_b200.workloads import clipper_builder
+
+    def builder(params, spec, t=0.0, x=cb.ZERO_VECTOR, ctx=None):
+        # the C2 clipper plus a PWL-driven branch: the PWL table walk must not index the
+        # parameter tables (and through them the register workspace) dynamically
+        ctx = clipper_builder(params, spec, t, x=x, ctx=ctx)
+        aux = cb.get_node(ctx, "aux")
+        cb.stamp(cb.VoltageSource(0.0, tran=cb.PWLWave([0.0, 1e-4, 2e-4, 5e-4], [0.0, 1.0, 1.0, 0.0]), name="V2"),
+                 ctx, aux, 0)
+        cb.stamp(cb.Resistor(params.R, name="R2"), ctx, aux, cb.get_node(ctx, "out"))
+        return ctx
+    cs = cb.CircuitSweep(builder, cb.ProductSweep(R=[1e2, 1e3, 1e4, 1e5], C=[1e-10, 1e-9, 1e-8]))
     params, P = cs.lane_params()
     lc = cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P)
     S = ora.Structure(ora.OracleNetlist(lc.netlist_tables()), ora.make_spec(mode="tran"))
     G, Cm, _, _ = S.rebuild(np.zeros(lc.n), initjct=True)       # nominal magnitudes for the pivot choice
     src = backend.emit_source(lc, np.abs(G), np.abs(G + 1e6 * Cm), P=65536)
     assert "cb200_spec_tran_fixed_kernel" in src and "eval_device<1>(pg, w, 2," in src
+    assert "__device__ constexpr int k_SProg_dev_node[]" in src      # tables at namespace scope, not on the stack
     assert "__launch_bounds__(kBlock, kMinBlocks)" in src and "constexpr int kMinBlocks = 7;" in src
     cu = tmp_path / "spec.cu"
     cu.write_text(src)
