@@ -238,7 +238,7 @@ def run_b200(args):
 
     use_spec = os.environ.get("CB200_NO_SPECIALIZE", "0") != "1"
     if use_spec:
-        comp.specialize(DT, "be")        # emitter: circuit-specialised kernels (nvcc, cached in-tree)
+        comp.specialize(DT, "be", limit=W["limit"], fixed_only=True)        # emitter: circuit-specialised kernels (nvcc, cached in-tree)
 
     def step_resident():
         wave = comp.tran(TSPAN, DT, method="be", save_idxs=save, save_every=SAVE_EVERY, limit=W["limit"])
@@ -263,6 +263,7 @@ def run_b200(args):
         wave, st = step_resident()
         if iters_per_step is None:
             r = wave.fetch()
+            first_u = r["u"][0].copy()                    # [T][P] saved waveform of the first pass
             iters_per_step = int(r["newton_iters"].astype(np.int64).sum())
             bad = int((r["status"] != 0).sum())
             if bad:
@@ -356,6 +357,16 @@ def run_b200(args):
             n_sample = int(min(P, max(len(probe), rate * 12.0)))
             lanes = np.linspace(0, P - 1, n_sample, dtype=np.int64)
             rate, it, secs = cpu_oracle_rate(lc, lanes)
+            # spot check of the measured pass against the oracle (8 lanes spread over the sweep)
+            chk = np.linspace(0, P - 1, 8, dtype=np.int64)
+            sub = dict(lc.netlist_tables()); sub["par"] = np.ascontiguousarray(sub["par"][chk])
+            ro = ora.sweep_tran(ora.OracleNetlist(sub), ora.make_spec(mode="tran"), TSPAN[0], TSPAN[1],
+                                ora.make_tran_opts(method=0, dt=DT, save_every=SAVE_EVERY, limit=W["limit"]),
+                                [lc.index_of(W["save"])])
+            diff = float(np.max(np.abs(ro["u"][:, :first_u.shape[0], 0] - first_u[:, chk].T)))
+            line["parity"] = {"lanes_checked": 8, "max_abs_diff_vs_oracle": diff}
+            if not diff < 1e-6:
+                raise SystemExit(f"bench.py: GPU waveform differs from the oracle by {diff}")
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "newton_iters_per_sec": it / secs,
                                     "sample": f"{n_sample} of {P} lanes (strided over the sweep), full "

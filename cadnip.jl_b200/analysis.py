@@ -203,9 +203,9 @@ class CompiledSweep:
     def dc(self, u0=None, abstol=1e-10, maxiters=100, use_stepping=True, mode="dcop"):
         return self.handle.dc(self.spec, u0, abstol, maxiters, use_stepping, mode)
 
-    def specialize(self, dt, method="be"):
+    def specialize(self, dt, method="be", limit=False, fixed_only=False):
         """Compile and load kernels specialised for this circuit and step size."""
-        self.handle.specialize(self.spec, method, dt)
+        self.handle.specialize(self.spec, method, dt, limit=limit, fixed_only=fixed_only)
 
     def tran(self, tspan, dt, method="be", save_idxs=None, save_every=1, abstol=1e-10,
              max_nl_iters=10, u0=None, init_abstol=1e-9, init_maxiters=500,
@@ -213,7 +213,7 @@ class CompiledSweep:
         """limit=True applies the PCNR corrector inside the transient Newton loop too
         (CB200_TRAN_LIMIT): the models' $limit functions then damp the iteration."""
         if specialize:
-            self.specialize(dt, method)
+            self.specialize(dt, method, limit=limit, fixed_only=True)
         opts = backend.make_tran_opts(method=method, adaptive=False, dt=dt, abstol=abstol,
                                       max_nl_iters=max_nl_iters, save_every=save_every,
                                       init=0 if u0 is None else 1, init_abstol=init_abstol,

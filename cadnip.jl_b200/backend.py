@@ -376,13 +376,15 @@ class Handle:
         s = make_spec(spec, mode)
         self._check(lib().cb200_analyze(self._p, C.byref(s), float(gamma)))
 
-    def specialize(self, spec: MNASpec, method, dt: float, compile_only: bool = False):
+    def specialize(self, spec: MNASpec, method, dt: float, compile_only: bool = False, limit: bool = False,
+                   fixed_only: bool = False):
         """Generate + compile (cached in cadnip.jl_b200/_gen) + load kernels specialised
-        for this circuit; later dc/tran calls use them."""
+        for this circuit; later dc/tran calls use them.  limit: include the CB200_TRAN_LIMIT
+        path (otherwise transients that ask for it run on the table-driven kernels)."""
         s = make_spec(spec, "tran")
         m = METHODS[method] if isinstance(method, str) else int(method)
         self._check(lib().cb200_specialize(self._p, C.byref(s), m, float(dt), _CSRC.encode(),
-                                           GEN_DIR.encode(), 1 if compile_only else 0))
+                                           GEN_DIR.encode(), (1 if compile_only else 0) | (2 if limit else 0) | (4 if fixed_only else 0)))
 
     def is_specialized(self) -> bool:
         return bool(lib().cb200_is_specialized(self._p))

@@ -170,6 +170,7 @@ struct cb200_handle {
     SpecModule spec;               // circuit-specialised kernels (optional)
     int spec_gen[2] = {-1, -1};    // schedule generations the module was generated from
     int spec_method = -1;          // integration method baked into the transient kernel
+    bool spec_limit = false;       // transient kernels were generated with the CB200_TRAN_LIMIT path
     int num_sms = 148;
     size_t smem_limit = 0;
     int block_pref = 64;
@@ -985,7 +986,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
             a.k_end = std::min<int64_t>(nsteps, (int64_t)(g + 1) * seg_len);
             if (a.k_begin > a.k_end) break;
             a.tp_begin = g == 0 ? 0 : 1 + (a.k_begin - 1) / se;
-            if (spec_usable(h) && h->spec_method == o->method) {
+            if (spec_usable(h) && h->spec_method == o->method && (!a.limit || h->spec_limit)) {
                 h->stats.launches += 1;
                 ce = h->spec.tran_fixed(&h->prog, &sa, &a, s);
             } else {
@@ -1031,7 +1032,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         a.status = h->d_status.p; a.iters = h->d_iters.p; a.rejected = h->d_rejected.p;
         a.ws_global = ws_global;
         cudaEventRecord(h->ev0, s);
-        if (spec_usable(h) && h->spec_method == a.method) {
+        if (spec_usable(h) && h->spec.tran_adaptive && h->spec_method == a.method && (!a.limit || h->spec_limit)) {
             h->stats.launches += 1;
             ce = h->spec.tran_adaptive(&h->prog, &sa, &a, s);
         } else {
@@ -1139,8 +1140,13 @@ extern "C" int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t
     if (rc != CB200_OK) return rc;
     rc = ensure_lu(h, spec, 1, gamma);
     if (rc != CB200_OK) return rc;
-    if (spec_usable(h) && h->spec_method == method) return CB200_OK;
+    const bool want_limit = (flags & CB200_SPEC_TRAN_LIMIT) != 0;
+    const bool want_adaptive = (flags & CB200_SPEC_FIXED_ONLY) == 0;
+    if (spec_usable(h) && h->spec_method == method && h->spec_limit == want_limit &&
+        (!want_adaptive || h->spec.tran_adaptive)) return CB200_OK;
     SpecInput in{};
+    in.tran_limit = want_limit;
+    in.with_adaptive = want_adaptive;
     in.st = &h->st; in.prog = &h->prog;
     in.dev_kind = &h->dev_kind; in.dev_flags = &h->dev_flags; in.dev_node_ptr = &h->dev_node_ptr;
     in.dev_nodes = &h->dev_nodes; in.dev_param_ptr = &h->dev_param_ptr; in.dev_params = &h->dev_params;
@@ -1167,6 +1173,7 @@ extern "C" int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t
     h->spec_gen[0] = h->lu_gen[0];
     h->spec_gen[1] = h->lu_gen[1];
     h->spec_method = method;
+    h->spec_limit = want_limit;
     return CB200_OK;
 }
 

@@ -43,6 +43,7 @@ struct DynProg {
     static constexpr bool kStatic = false;
     static constexpr int kUnroll = 1;
     static constexpr int kMethod = -1;      // integration method chosen at run time
+    static constexpr bool kTranLimit = true; // CB200_TRAN_LIMIT supported (specialised kernels: opt-in)
     const Program &p;
     __device__ __forceinline__ explicit DynProg(const Program &pp) : p(pp) {}
     __device__ __forceinline__ int n() const { return p.n; }
@@ -901,7 +902,7 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
                 if (bad) { done = true; st = CB200_LANE_NONFINITE; }
                 else if (nrm2 < abstol2) { done = true; }
                 else if (it - it0 >= (lim_on ? 4 * a.max_nl : a.max_nl)) {
-                    if (a.limit && !lim_on) { lim_on = true; it0 = it + 1; restart = true; }
+                    if (PG::kTranLimit && a.limit && !lim_on) { lim_on = true; it0 = it + 1; restart = true; }
                     else { done = true; st = CB200_LANE_MAXITER; }
                 }
             }
@@ -1035,7 +1036,7 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
                 if (bad) { done = true; st = CB200_LANE_NONFINITE; }
                 else if (nrm2 < abstol2) { done = true; }
                 else if (it - it0 >= (lim_on ? 4 * a.max_nl : a.max_nl)) {
-                    if (a.limit && !lim_on) { lim_on = true; it0 = it + 1; restart = true; }
+                    if (PG::kTranLimit && a.limit && !lim_on) { lim_on = true; it0 = it + 1; restart = true; }
                     else { done = true; st = CB200_LANE_MAXITER; }
                 }
             }

@@ -195,6 +195,7 @@ std::string generate_spec_source(const SpecInput &in)
     o << "struct SProg {\n";
     o << "    static constexpr bool kStatic = true;\n    static constexpr int kUnroll = 4096;\n";
     o << "    static constexpr int kMethod = " << in.method << ";\n";
+    o << "    static constexpr bool kTranLimit = " << (in.tran_limit ? "true" : "false") << ";\n";
     emit_const(o, "n", st.n);
     emit_const(o, "n_limits", st.n_limits);
     emit_const(o, "nnz", st.nnz);
@@ -270,8 +271,9 @@ std::string generate_spec_source(const SpecInput &in)
          "{\n    SProg pg; SLuDc lu; RegWs<kSlots> w;\n    dc_body(pg, lu, w, p, sp, a);\n}\n";
     o << "__global__ void __launch_bounds__(kBlock, kMinBlocks) cb200_spec_tran_fixed_kernel(Program p, SpecArgs sp, TranArgs a)\n"
          "{\n    SProg pg; SLuTr lu; RegWs<kSlots> w;\n    tran_fixed_body(pg, lu, w, p, sp, a);\n}\n";
-    o << "__global__ void __launch_bounds__(kBlock, kMinBlocks) cb200_spec_tran_adaptive_kernel(Program p, SpecArgs sp, AdaptArgs a)\n"
-         "{\n    SProg pg; SLuTr lu; RegWs<kSlots> w;\n    tran_adaptive_body(pg, lu, w, p, sp, a);\n}\n";
+    if (in.with_adaptive)
+        o << "__global__ void __launch_bounds__(kBlock, kMinBlocks) cb200_spec_tran_adaptive_kernel(Program p, SpecArgs sp, AdaptArgs a)\n"
+             "{\n    SProg pg; SLuTr lu; RegWs<kSlots> w;\n    tran_adaptive_body(pg, lu, w, p, sp, a);\n}\n";
     o << "}  // namespace\n";
     o << "extern \"C\" int cb200_spec_abi(void) { return " << kSpecAbi << "; }\n";
     o << "extern \"C\" int cb200_spec_block(void) { return kBlock; }\n";
@@ -283,6 +285,7 @@ std::string generate_spec_source(const SpecInput &in)
          "                                             const cb200::TranArgs *a, cudaStream_t st)\n{\n"
          "    const unsigned grid = (unsigned)((p->P + kBlock - 1) / kBlock);\n"
          "    cb200_spec_tran_fixed_kernel<<<grid, kBlock, 0, st>>>(*p, *s, *a);\n    return cudaGetLastError();\n}\n";
+    if (in.with_adaptive)
     o << "extern \"C\" cudaError_t cb200_spec_tran_adaptive(const cb200::Program *p, const cb200::SpecArgs *s,\n"
          "                                                const cb200::AdaptArgs *a, cudaStream_t st)\n{\n"
          "    const unsigned grid = (unsigned)((p->P + kBlock - 1) / kBlock);\n"
@@ -425,7 +428,7 @@ std::string build_and_load_spec(const std::string &src, const std::string &csrc_
     out.dc = (spec_dc_fn)dlsym(dl, "cb200_spec_dc");
     out.tran_fixed = (spec_tran_fn)dlsym(dl, "cb200_spec_tran_fixed");
     out.tran_adaptive = (spec_adapt_fn)dlsym(dl, "cb200_spec_tran_adaptive");
-    if (!abi || !blk || !out.dc || !out.tran_fixed || !out.tran_adaptive || abi() != kSpecAbi) {
+    if (!abi || !blk || !out.dc || !out.tran_fixed || abi() != kSpecAbi) {       // tran_adaptive is optional
         dlclose(dl);
         out = SpecModule();
         return "specialize: " + so + " does not export the expected entry points";

@@ -21,6 +21,8 @@ struct SpecInput {
     const std::vector<unsigned char> *src_uniform;
     int method;                       // CB200_METHOD_* compiled into the transient kernel
     std::string va_header_path;       // emitted Verilog-A models ("" = none)
+    bool with_adaptive = true;        // also generate the adaptive transient kernel (a third of the compile time)
+    bool tran_limit = false;          // compile the CB200_TRAN_LIMIT restart path into the transient kernels
     const LuSchedule *lu_dc, *lu_tr;
     int n_lane_cols;
     int block, min_blocks;            // __launch_bounds__ of the generated kernels

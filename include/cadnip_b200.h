@@ -173,6 +173,12 @@ typedef struct cb200_tran_opts {
  * ngspice's transient.  Off = the reference's formulation (limit rows are ordinary
  * algebraic unknowns in transient).  The converged step is the same either way.        */
 #define CB200_TRAN_LIMIT 1
+/* cb200_specialize flags */
+#define CB200_SPEC_COMPILE_ONLY 1   /* generate + compile into the cache, do not load          */
+#define CB200_SPEC_FIXED_ONLY   4   /* skip the adaptive transient kernel (a third of the compile time) */
+#define CB200_SPEC_TRAN_LIMIT   2   /* include the CB200_TRAN_LIMIT path in the transient kernels
+                                       (without it, a transient with that flag runs on the
+                                       table-driven kernels)                                     */
 
 /* Counters of the most recent call (all device times from CUDA events on the
  * library's own stream).                                                      */
