@@ -41,6 +41,12 @@ WORKLOADS = {
                     "(50 W_n x 50 Vdd x 40 C_L), DC op (CedarTranOp/PCNR) + fixed-step BE 4000 x 0.1ns "
                     "(CB200_TRAN_LIMIT: steps that miss 10 Newton solves are redone with $limit damping); "
                     "V(q) saved every 10th step"),
+    "c4": dict(tspan=(0.0, 6e-7), dt=1e-12, save_every=1, save="Q", steps=0, limit=True, adaptive=True,
+               reltol=1e-3, lte_abstol=1e-5, max_points=2048, probe_per_core=2,
+               text="C4 gf180 D flip-flop corner/Monte-Carlo CircuitSweep (30 FETs; PDK cards absent -> FALLBACK tier: "
+                    "sp_mos1 Verilog-A model, synthetic 5 V card, 5 fF parasitic per net): 16384 points (4 corners x "
+                    "4096 draws), DC op (PCNR + fallbacks) + adaptive trapezoidal/LTE transient (0, 6e-7), reltol 1e-3; "
+                    "table-driven kernels, lane state in HBM"),
 }
 W = WORKLOADS["c2"]
 TSPAN, DT, SAVE_EVERY, WORKLOAD = W["tspan"], W["dt"], W["save_every"], W["text"]
@@ -124,9 +130,31 @@ def c3_lanes(lc, n_lanes):
     return np.ascontiguousarray(np.stack([col[e] for e in lc.lane_exprs])), int(i.size)
 
 
+def c4_lanes(lc, n_lanes):
+    """4 process corners (vto, kp +-10 %) x Monte-Carlo draws (dvto ~ N(0, 15 mV), dkp/kp ~ N(0, 2 %)),
+    numpy.random.default_rng(20261018) -- the same construction as tests/va_circuits.mos1_dff."""
+    n_lanes = n_lanes or 16384
+    rng = np.random.default_rng(20261018)
+    per = max(1, n_lanes // 4)
+    col = {"vton": [], "vtop": [], "kpn": [], "kpp": []}
+    for cv, ck in ((+1, +1), (+1, -1), (-1, +1), (-1, -1)):
+        dv = rng.normal(0.0, 15e-3, (per, 2))
+        dk = rng.normal(0.0, 0.02, (per, 2))
+        col["vton"] += list(0.7 * (1 + 0.1 * cv) + dv[:, 0]); col["vtop"] += list(-0.7 * (1 + 0.1 * cv) - dv[:, 1])
+        col["kpn"] += list(100e-6 * (1 + 0.1 * ck) * (1 + dk[:, 0])); col["kpp"] += list(50e-6 * (1 + 0.1 * ck) * (1 + dk[:, 1]))
+    return np.ascontiguousarray(np.stack([np.asarray(col[e]) for e in lc.lane_exprs])), 4 * per
+
+
 def build_sweep(args):
     import cadnip_b200 as cb
     from cadnip_b200.workloads import clipper_sweep
+    if args.workload == "c4":
+        import gzip
+        import pickle
+        with gzip.open(os.path.join(ROOT, "tests", "golden", "va_mos1_dff.pkl.gz"), "rb") as f:
+            lc = pickle.load(f)
+        lc.lane_soa, lc.P = c4_lanes(lc, args.lanes)
+        return cb, None, lc, lc.P
     if args.workload == "c3":
         import gzip
         import pickle
@@ -163,7 +191,11 @@ def cpu_oracle_rate(lc, sample_lanes, nthreads=0):
     par = np.ascontiguousarray(nl.par_lanes[sample_lanes])
     sub = dict(lc.netlist_tables()); sub["par"] = par
     nls = ora.OracleNetlist(sub)
-    o = ora.make_tran_opts(method=0, dt=DT, save_every=SAVE_EVERY, limit=W["limit"])
+    if W.get("adaptive"):
+        o = ora.make_tran_opts(method=1, adaptive=1, dt=DT, reltol=W["reltol"], lte_abstol=W["lte_abstol"],
+                               max_points=W["max_points"], limit=W["limit"])
+    else:
+        o = ora.make_tran_opts(method=0, dt=DT, save_every=SAVE_EVERY, limit=W["limit"])
     t0 = time.perf_counter()
     r = ora.sweep_tran(nls, ora.make_spec(mode="tran"), TSPAN[0], TSPAN[1], o, [lc.index_of(W["save"])],
                        nthreads=nthreads)
@@ -181,7 +213,7 @@ def run_reference(args):
     cb, cs, lc, P = build_sweep(args)
     cores = host_threads()
     # calibrate a bounded sample: ~4 s of wall per step
-    probe = np.linspace(0, P - 1, min(P, 64 * cores), dtype=np.int64)
+    probe = np.linspace(0, P - 1, min(P, W.get("probe_per_core", 64) * cores), dtype=np.int64)
     rate, _, _ = cpu_oracle_rate(lc, probe)
     n_sample = int(min(P, max(len(probe), rate * 4.0)))
     lanes = np.linspace(0, P - 1, n_sample, dtype=np.int64)
@@ -229,25 +261,37 @@ def run_b200(args):
     # weak scaling: every rank solves the full C2 sweep (per-GPU work fixed as N grows)
     comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"), device=local_rank)
     save = [lc.index_of(W["save"])]
-    T = 1 + int(round((TSPAN[1] - TSPAN[0]) / DT)) // SAVE_EVERY
+    adaptive = bool(W.get("adaptive"))
+    T = W["max_points"] if adaptive else 1 + int(round((TSPAN[1] - TSPAN[0]) / DT)) // SAVE_EVERY
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     pinned_out = torch.empty((len(save), T, P), dtype=torch.float64, pin_memory=True)
     out_np = pinned_out.numpy()
     pinned_in = torch.from_numpy(np.ascontiguousarray(lc.lane_soa)).pin_memory()
     comp._soa = pinned_in.numpy()
 
-    use_spec = os.environ.get("CB200_NO_SPECIALIZE", "0") != "1"
+    # 30 inlined model instances are beyond a straight-line kernel: C4 runs table-driven
+    use_spec = os.environ.get("CB200_NO_SPECIALIZE", "0") != "1" and not adaptive
     if use_spec:
         comp.specialize(DT, "be", limit=W["limit"], fixed_only=True)        # emitter: circuit-specialised kernels (nvcc, cached in-tree)
 
     def step_resident():
-        wave = comp.tran(TSPAN, DT, method="be", save_idxs=save, save_every=SAVE_EVERY, limit=W["limit"])
+        if adaptive:
+            wave = comp.tran_adaptive(TSPAN, dt0=DT, method="trap", save_idxs=save, reltol=W["reltol"],
+                                      lte_abstol=W["lte_abstol"], max_points=W["max_points"], limit=W["limit"])
+        else:
+            wave = comp.tran(TSPAN, DT, method="be", save_idxs=save, save_every=SAVE_EVERY, limit=W["limit"])
         st = comp.handle.stats()
         return wave, st
 
     def step_e2e():
         comp.upload_lanes()                                   # H2D from pinned memory
         h2d = comp.handle.stats()["h2d_bytes"]
+        if adaptive:                                          # ragged waveforms: one D2H after the run
+            wave = comp.tran_adaptive(TSPAN, dt0=DT, method="trap", save_idxs=save, reltol=W["reltol"],
+                                      lte_abstol=W["lte_abstol"], max_points=W["max_points"], limit=W["limit"])
+            st = comp.handle.stats()
+            r = wave.fetch(out_np); wave.free()
+            return st, r, h2d, int(out_np.nbytes + 8 * T * P + 12 * P)
         # tran! into pinned host memory: D2H of each time segment overlaps the next one's compute
         r = comp.tran_fetch(TSPAN, DT, out_np, method="be", save_idxs=save, save_every=SAVE_EVERY,
                             n_segments=N_SEGMENTS, limit=W["limit"])
@@ -264,6 +308,7 @@ def run_b200(args):
         if iters_per_step is None:
             r = wave.fetch()
             first_u = r["u"][0].copy()                    # [T][P] saved waveform of the first pass
+            first_t, first_count = (r["t"].copy(), r["count"].copy()) if adaptive else (None, None)
             iters_per_step = int(r["newton_iters"].astype(np.int64).sum())
             bad = int((r["status"] != 0).sum())
             if bad:
@@ -331,7 +376,9 @@ def run_b200(args):
             "newton_iters_per_sec": world * iters_per_step * args.steps / wall,
             "newton_iters_per_step": iters_per_step,
             "config": {"workload": WORKLOAD, "lanes_per_gpu": P, "parallelism": f"lanes sharded x{world}"
-                       if world > 1 else "1 GPU", "method": f"BE fixed dt={DT:g}, {W['steps']} steps",
+                       if world > 1 else "1 GPU",
+                       "method": (f"adaptive trapezoidal + LTE, reltol {W['reltol']:g}, <= {W['max_points']} points/lane"
+                                  if adaptive else f"BE fixed dt={DT:g}, {W['steps']} steps"),
                        "l2": "256 MiB device memset between steps (inside the timed region)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * wall_e2e / args.steps,
@@ -342,7 +389,8 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": "cb200_spec_tran_fixed_kernel (circuit-specialised, registers)" if comp.handle.is_specialized()
-                         else "tran_fixed_kernel<smem> (table-driven)", "algorithmic_bytes_per_launch": alg_bytes,
+                         else ("tran_adaptive_kernel<global> (table-driven, lane state in HBM)" if adaptive
+                               else "tran_fixed_kernel<smem> (table-driven)"), "algorithmic_bytes_per_launch": alg_bytes,
                          "bytes_per_newton_iter_per_lane": b_iter,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "note": "state is on-chip (fused lane-per-thread kernel): the algorithmic-byte "
@@ -352,7 +400,7 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             import cadnip_oracle as ora
             cores = host_threads()
-            probe = np.linspace(0, P - 1, min(P, 64 * cores), dtype=np.int64)
+            probe = np.linspace(0, P - 1, min(P, W.get("probe_per_core", 64) * cores), dtype=np.int64)
             rate, _, _ = cpu_oracle_rate(lc, probe)
             n_sample = int(min(P, max(len(probe), rate * 12.0)))
             lanes = np.linspace(0, P - 1, n_sample, dtype=np.int64)
@@ -360,13 +408,30 @@ def run_b200(args):
             # spot check of the measured pass against the oracle (8 lanes spread over the sweep)
             chk = np.linspace(0, P - 1, 8, dtype=np.int64)
             sub = dict(lc.netlist_tables()); sub["par"] = np.ascontiguousarray(sub["par"][chk])
-            ro = ora.sweep_tran(ora.OracleNetlist(sub), ora.make_spec(mode="tran"), TSPAN[0], TSPAN[1],
-                                ora.make_tran_opts(method=0, dt=DT, save_every=SAVE_EVERY, limit=W["limit"]),
+            oo = (ora.make_tran_opts(method=1, adaptive=1, dt=DT, reltol=W["reltol"], lte_abstol=W["lte_abstol"],
+                                     max_points=W["max_points"], limit=W["limit"]) if adaptive else
+                  ora.make_tran_opts(method=0, dt=DT, save_every=SAVE_EVERY, limit=W["limit"]))
+            ro = ora.sweep_tran(ora.OracleNetlist(sub), ora.make_spec(mode="tran"), TSPAN[0], TSPAN[1], oo,
                                 [lc.index_of(W["save"])])
-            diff = float(np.max(np.abs(ro["u"][:, :first_u.shape[0], 0] - first_u[:, chk].T)))
-            line["parity"] = {"lanes_checked": 8, "max_abs_diff_vs_oracle": diff}
-            if not diff < 1e-6:
-                raise SystemExit(f"bench.py: GPU waveform differs from the oracle by {diff}")
+            if adaptive:                                  # ragged time axes: compare on a common grid
+                tg = np.linspace(TSPAN[0], TSPAN[1], 400)
+                diff = 0.0
+                for q, lane in enumerate(chk):
+                    ng, no = int(first_count[lane]), int(ro["count"][q])
+                    a = np.interp(tg, first_t[:ng, lane], first_u[:ng, lane])
+                    b = np.interp(tg, ro["t"][q, :no], ro["u"][q, :no, 0])
+                    diff = max(diff, float(np.max(np.abs(a - b))))
+                line["parity"] = {"lanes_checked": 8, "max_abs_diff_vs_oracle": diff,
+                                  "timepoints_gpu": [int(first_count[l]) for l in chk],
+                                  "timepoints_oracle": [int(c) for c in ro["count"]]}
+                if not diff < 0.25:                       # edges shift by a fraction of an adaptive step
+                    raise SystemExit(f"bench.py: GPU waveform differs from the oracle by {diff}")
+            else:
+                diff = float(np.max(np.abs(ro["u"][:, :first_u.shape[0], 0] - first_u[:, chk].T)))
+            if not adaptive:
+                line["parity"] = {"lanes_checked": 8, "max_abs_diff_vs_oracle": diff}
+                if not diff < 1e-6:
+                    raise SystemExit(f"bench.py: GPU waveform differs from the oracle by {diff}")
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "newton_iters_per_sec": it / secs,
                                     "sample": f"{n_sample} of {P} lanes (strided over the sweep), full "

@@ -232,7 +232,7 @@ class CompiledSweep:
 
     def tran_adaptive(self, tspan, dt0=None, method="trap", save_idxs=None, abstol=1e-10,
                       reltol=1e-6, lte_abstol=1e-9, max_points=4096, dtmin=0.0, dtmax=0.0,
-                      max_nl_iters=10, tstops=None, u0=None, specialize=False) -> backend.Wave:
+                      max_nl_iters=10, tstops=None, u0=None, specialize=False, limit=False) -> backend.Wave:
         """LTE-controlled stepping, one time axis per lane.  ``tstops`` defaults to the
         source breakpoints (``auto_tstops``, src/sweeps.jl:620-627)."""
         if tstops is None:
@@ -243,11 +243,11 @@ class CompiledSweep:
         self.handle.set_tstops(tstops)
         dt0 = float(dt0) if dt0 else (tspan[1] - tspan[0]) * 1e-4
         if specialize:
-            self.specialize(dt0, method)
+            self.specialize(dt0, method, limit=limit)
         opts = backend.make_tran_opts(method=method, adaptive=True, dt=dt0, abstol=abstol,
                                       reltol=reltol, lte_abstol=lte_abstol, dtmin=dtmin, dtmax=dtmax,
                                       max_nl_iters=max_nl_iters, max_points=max_points,
-                                      init=0 if u0 is None else 1)
+                                      init=0 if u0 is None else 1, limit=limit)
         return self.handle.tran(self.spec, tspan[0], tspan[1], opts, self.save_indices(save_idxs), u0)
 
     def close(self):

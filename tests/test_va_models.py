@@ -19,11 +19,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 HAVE_REF = os.path.isdir("/root/reference/models/VADistillerModels.jl/va")
 needs_ref = pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
 
-FIXTURE_NAMES = ["mos1_corner", "diode_chain", "diode_rs_cap", "mos1_inverter", "mos1_c3", "mos1_ring",
+FIXTURE_NAMES = ["mos1_corner", "diode_chain", "diode_rs_cap", "mos1_inverter", "mos1_c3", "mos1_dff", "mos1_ring",
                  "mos1_ring_caps"]
 
 
-GPU_FIXTURES = ["mos1_corner", "diode_chain", "mos1_inverter", "diode_rs_cap", "mos1_ring", "mos1_c3"]   # used by -m gpu tests
+GPU_FIXTURES = ["mos1_corner", "diode_chain", "mos1_inverter", "diode_rs_cap", "mos1_ring", "mos1_c3", "mos1_dff"]   # used by -m gpu tests
 
 
 def fixture(name):
@@ -196,6 +196,24 @@ def test_transient_limiting_rescues_fast_edges():
     assert np.all(lim["u"][:, -1, 0] < 0.05 * vdd)                              # input high -> output low
 
 
+def test_dff_known_behaviour():
+    """SURVEY 8d C4 (gf180 D flip-flop, 30 FETs; sp_mos1 fallback card): n = 18 nodes + 7 source
+    currents + 30 x 4 limit unknowns; the DC operating point latches Q high with D low and CLKN high,
+    and the first falling clock edge (t = 51 ns) transfers D = 0 to Q."""
+    lc = fixture("mos1_dff")
+    assert (lc.n_nodes, lc.n_currents, lc.n_charges, lc.n_limits) == (18, 7, 0, 120)
+    nl = oracle_of(lc)
+    x, st, it = ora.sweep_dc(nl, ora.make_spec(mode="tranop"), lc.n)
+    assert (st == 0).all()
+    for name, level in (("Q_neg", 0.0), ("cki", 5.0), ("ncki", 0.0)):
+        assert np.allclose(x[:, lc.index_of(name) - 1], level, atol=1e-3)
+    o = ora.make_tran_opts(method=1, adaptive=1, dt=1e-12, reltol=1e-3, lte_abstol=1e-5, max_points=4000, limit=True)
+    r = ora.tran(nl, ora.make_spec(mode="tran"), 0.0, 1.2e-7, o, [lc.index_of("Q"), lc.index_of("CLKN")])
+    assert r["status"] == 0 and 100 < len(r["t"]) < 4000
+    q = np.interp([40e-9, 110e-9], r["t"], r["u"][:, 0])
+    assert q[0] > 4.9 and q[1] < 0.1
+
+
 # ---- emitted derivatives against finite differences ------------------------------------------
 @pytest.mark.parametrize("name", ["mos1_inverter", "diode_rs_cap", "mos1_ring_caps"])
 def test_emitted_jacobian_matches_finite_differences(name):
@@ -343,6 +361,36 @@ def test_gpu_va_c3_corner_lanes_with_transient_limiting():
     assert np.array_equal(r["status"], ro["status"]) and (r["status"] == 0).all()
     assert _close(gpu, ro["u"][:, :gpu.shape[1], :], rtol=1e-6, atol=1e-8), float(np.max(np.abs(gpu - ro["u"][:, :gpu.shape[1], :])))
     assert np.array_equal(r["newton_iters"], ro["newton_iters"])
+
+
+@pytest.mark.gpu
+def test_gpu_va_dff_adaptive():
+    """C4 on the table-driven kernels (lane state in HBM: n = 145, ~5000 workspace doubles per lane)."""
+    lc = fixture("mos1_dff")
+    nl = oracle_of(lc)
+    save = [lc.index_of("Q"), lc.index_of("Q_neg"), lc.index_of("net0")]
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        x, st, it = comp.dc()
+        wave = comp.tran_adaptive((0.0, 1.2e-7), dt0=1e-12, method="trap", save_idxs=save, reltol=1e-3,
+                                  lte_abstol=1e-5, max_points=4000, limit=True)
+        r = wave.fetch(); wave.free()
+    finally:
+        comp.close()
+    xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
+    assert np.array_equal(st, sto) and (st == 0).all() and _close(x.T, xo, rtol=1e-7, atol=1e-9)
+    o = ora.make_tran_opts(method=1, adaptive=1, dt=1e-12, reltol=1e-3, lte_abstol=1e-5, max_points=4000, limit=True)
+    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 1.2e-7, o, save)
+    assert (r["status"] == 0).all() and np.array_equal(r["status"], ro["status"])
+    tg = np.linspace(0.0, 1.2e-7, 600)
+    for p in range(lc.P):
+        ng, no = int(r["count"][p]), int(ro["count"][p])
+        assert abs(ng - no) <= max(3, no // 50), (ng, no)                # time-point counts reported and close
+        for k in range(len(save)):
+            a = np.interp(tg, r["t"][:ng, p], r["u"][k, :ng, p])
+            b = np.interp(tg, ro["t"][p, :no], ro["u"][p, :no, k])
+            # adaptive mode: agreement within the LTE tolerance class (north_star: reltol-level)
+            assert np.max(np.abs(a - b)) < 5e-2, (p, k, float(np.max(np.abs(a - b))))
 
 
 @pytest.mark.gpu

@@ -113,6 +113,89 @@ def c3_lane_exprs(lc, cs):
     return out
 
 
+DFF_DIR = "/root/reference/test/DFF/"
+
+
+def _spice_lines(path):
+    """Logical lines of a SPICE deck: comments dropped, `+` continuations joined."""
+    out = []
+    for raw in open(path).read().split("\n"):
+        ln = raw.strip()
+        if not ln or ln.startswith("*"):
+            continue
+        if ln.startswith("+"):
+            out[-1] += " " + ln[1:].strip()
+        else:
+            out.append(ln)
+    return out
+
+
+def mos1_dff(sp_mos1, n_lanes=4):
+    """the gf180 D flip-flop of test/DFF/DFF_cap_all.cir +
+    gf180mcu_fd_sc_mcu7t5v0__dffnq_4.ngspice (30 FETs, CQ = 1.7205e-13, CLKN / D PWL stimuli, the
+    0 V probe sources VQ / VNW / VPW).  The PDK cards are not in the reference tree, so the FETs are
+    sp_mos1 with a synthetic 5 V card (vto = +-0.7, kp = 100u / 50u: the FALLBACK tier SURVEY names) and
+    every internal net carries a synthetic 5 fF parasitic to ground.  Lanes: process corners x
+    Monte-Carlo draws on (vto_n, vto_p, kp_n, kp_p)."""
+    fets, caps, srcs = [], [], []
+    for ln in _spice_lines(DFF_DIR + "gf180mcu_fd_sc_mcu7t5v0__dffnq_4.ngspice"):
+        f = ln.split()
+        if f[0][0] in "xX":
+            kw = dict(x.split("=") for x in f[6:])
+            fets.append((f[0], f[1], f[2], f[3], f[4], f[5], float(kw["W"]), float(kw["L"])))
+    for ln in _spice_lines(DFF_DIR + "DFF_cap_all.cir"):
+        f = ln.replace("(", " ").replace(")", " ").split()
+        if f[0][0] in "cC":
+            caps.append((f[0], f[1], f[2], float(f[3])))
+        elif f[0][0] in "vV":
+            if len(f) > 3 and f[3].upper() == "PWL":
+                vals = [float(x) for x in f[4:]]
+                srcs.append((f[0], f[1], f[2], 0.0, (vals[0::2], vals[1::2])))
+            else:
+                srcs.append((f[0], f[1], f[2], float(f[3]), None))
+    assert len(fets) == 30 and len(srcs) == 7
+    nets = []
+    for _, d, g, s_, b, *_ in fets:
+        for n in (d, g, s_, b):
+            if n not in nets:
+                nets.append(n)
+    for _, p, n, *_ in srcs + caps:
+        for x in (p, n):
+            if x != "0" and x not in nets:
+                nets.append(x)
+    driven = {p for _, p, n, *_ in srcs}
+
+    def f(ctx, p):
+        node = {"0": 0}
+        for n in nets:
+            node[n] = get_node(ctx, n)
+        for name, a, b, dc, pwl in srcs:
+            stamp(VoltageSource(dc if pwl is None else pwl[1][0], tran=None if pwl is None else PWLWave(*pwl),
+                                name=name), ctx, node[a], node[b])
+        for name, a, b, c in caps:
+            stamp(Capacitor(c, name=name), ctx, node[a], node[b])
+        for n in nets:
+            if n not in driven and n not in ("VDD", "VSS"):
+                stamp(Capacitor(5e-15, name="Cpar_" + n), ctx, node[n], 0)
+        for name, d, g, s_, b, model, w, l in fets:
+            if model.startswith("nfet"):
+                card = dict(type=1, vto=p.vton, kp=p.kpn)
+            else:
+                card = dict(type=-1, vto=p.vtop, kp=p.kpp)
+            stamp(sp_mos1(w=w, l=l, name=name, **card), ctx, node[d], node[g], node[s_], node[b])
+
+    rng = np.random.default_rng(20261018)
+    per = max(1, n_lanes // 4)
+    corner = [(+1, +1), (+1, -1), (-1, +1), (-1, -1)]                   # (vto, kp) +-10 %
+    vton, vtop, kpn, kpp = [], [], [], []
+    for cv, ck in corner:
+        dv = rng.normal(0.0, 15e-3, (per, 2))
+        dk = rng.normal(0.0, 0.02, (per, 2))
+        vton += list(0.7 * (1 + 0.1 * cv) + dv[:, 0]); vtop += list(-0.7 * (1 + 0.1 * cv) - dv[:, 1])
+        kpn += list(100e-6 * (1 + 0.1 * ck) * (1 + dk[:, 0])); kpp += list(50e-6 * (1 + 0.1 * ck) * (1 + dk[:, 1]))
+    return cb.CircuitSweep(_B(f), cb.TandemSweep(vton=vton, vtop=vtop, kpn=kpn, kpp=kpp))
+
+
 def mos1_ring(sp_mos1, caps=False):
     """3-stage ring oscillator of test/mna/oscillator_test.jl:38-68; caps=True adds the
     device's own overlap / junction / Meyer capacitances (voltage-dependent charges)."""
@@ -136,6 +219,7 @@ FIXTURES = {
     "diode_rs_cap": ("diode", diode_rs_cap),
     "mos1_inverter": ("mos1", mos1_inverter),
     "mos1_c3": ("mos1", mos1_c3),
+    "mos1_dff": ("mos1", mos1_dff),
     "mos1_ring": ("mos1", mos1_ring),
     "mos1_ring_caps": ("mos1", lambda m: mos1_ring(m, caps=True)),
 }
@@ -153,4 +237,7 @@ def lower_fixture(name, models=None):
     lc = cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P)
     if name == "mos1_c3":
         lc.lane_exprs = c3_lane_exprs(lc, cs)
+    if name == "mos1_dff":
+        cand = {k: np.asarray(getattr(params, k), dtype=np.float64) for k in ("vton", "vtop", "kpn", "kpp")}
+        lc.lane_exprs = [next(k for k, v in cand.items() if np.array_equal(col, v)) for col in lc.lane_soa]
     return lc
