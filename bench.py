@@ -234,7 +234,8 @@ def run_reference(args):
             "config": {"workload": WORKLOAD, "lanes_per_step": n_sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{n_sample} of {P} lanes (strided over the sweep), full "
-                                       f"{W['steps']}-step transient each, OpenMP over lanes"},
+                                       f"{'adaptive' if W.get('adaptive') else str(W['steps']) + '-step'} transient each, "
+                                       "OpenMP over lanes"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -393,8 +394,11 @@ def run_b200(args):
                                else "tran_fixed_kernel<smem> (table-driven)"), "algorithmic_bytes_per_launch": alg_bytes,
                          "bytes_per_newton_iter_per_lane": b_iter,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                         "note": "state is on-chip (fused lane-per-thread kernel): the algorithmic-byte "
-                                 "figure counts traffic a non-fused pipeline would move through HBM"},
+                         "note": ("lane state in HBM ([slot][thread] workspace): every stamp, factor entry and vector "
+                                  "element of an iteration is an HBM access, several times the algorithmic bytes"
+                                  if adaptive else
+                                  "state is on-chip (fused lane-per-thread kernel): the algorithmic-byte "
+                                  "figure counts traffic a non-fused pipeline would move through HBM")},
             "clocks": clocks}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -417,13 +421,13 @@ def run_b200(args):
                 tg = np.linspace(TSPAN[0], TSPAN[1], 400)
                 diff = 0.0
                 for q, lane in enumerate(chk):
-                    ng, no = int(first_count[lane]), int(ro["count"][q])
+                    ng, no = int(first_count[lane]), int(ro["T"][q])
                     a = np.interp(tg, first_t[:ng, lane], first_u[:ng, lane])
                     b = np.interp(tg, ro["t"][q, :no], ro["u"][q, :no, 0])
                     diff = max(diff, float(np.max(np.abs(a - b))))
                 line["parity"] = {"lanes_checked": 8, "max_abs_diff_vs_oracle": diff,
                                   "timepoints_gpu": [int(first_count[l]) for l in chk],
-                                  "timepoints_oracle": [int(c) for c in ro["count"]]}
+                                  "timepoints_oracle": [int(c) for c in ro["T"]]}
                 if not diff < 0.25:                       # edges shift by a fraction of an adaptive step
                     raise SystemExit(f"bench.py: GPU waveform differs from the oracle by {diff}")
             else:
@@ -435,7 +439,8 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "newton_iters_per_sec": it / secs,
                                     "sample": f"{n_sample} of {P} lanes (strided over the sweep), full "
-                                              f"{W['steps']}-step transient each, OpenMP over lanes, {secs:.1f} s"}
+                                              f"{'adaptive' if adaptive else str(W['steps']) + '-step'} transient each, "
+                                              f"OpenMP over lanes, {secs:.1f} s"}
         print(json.dumps(line), flush=True)
     comp.close()
     if world > 1:

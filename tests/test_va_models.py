@@ -384,7 +384,7 @@ def test_gpu_va_dff_adaptive():
     assert (r["status"] == 0).all() and np.array_equal(r["status"], ro["status"])
     tg = np.linspace(0.0, 1.2e-7, 600)
     for p in range(lc.P):
-        ng, no = int(r["count"][p]), int(ro["count"][p])
+        ng, no = int(r["count"][p]), int(ro["T"][p])
         assert abs(ng - no) <= max(3, no // 50), (ng, no)                # time-point counts reported and close
         for k in range(len(save)):
             a = np.interp(tg, r["t"][:ng, p], r["u"][k, :ng, p])
