@@ -250,6 +250,8 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
