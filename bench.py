@@ -249,9 +249,12 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: whatever libraries print there while the run is in
+    # progress (NCCL's version banner at the first collective) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -443,6 +446,8 @@ def run_b200(args):
                                     "sample": f"{n_sample} of {P} lanes (strided over the sweep), full "
                                               f"{'adaptive' if adaptive else str(W['steps']) + '-step'} transient each, "
                                               f"OpenMP over lanes, {secs:.1f} s"}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
     comp.close()
     if world > 1:
