@@ -46,7 +46,7 @@ WORKLOADS = {
                text="C4 gf180 D flip-flop corner/Monte-Carlo CircuitSweep (30 FETs; PDK cards absent -> FALLBACK tier: "
                     "sp_mos1 Verilog-A model, synthetic 5 V card, 5 fF parasitic per net): 16384 points (4 corners x "
                     "4096 draws), DC op (PCNR + fallbacks) + adaptive trapezoidal/LTE transient (0, 6e-7), reltol 1e-3; "
-                    "table-driven kernels, lane state in HBM"),
+                    "table-driven kernels, one lane per warp"),
 }
 W = WORKLOADS["c2"]
 TSPAN, DT, SAVE_EVERY, WORKLOAD = W["tspan"], W["dt"], W["save_every"], W["text"]
@@ -395,13 +395,20 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": "cb200_spec_tran_fixed_kernel (circuit-specialised, registers)" if comp.handle.is_specialized()
-                         else ("tran_adaptive_kernel<global> (table-driven, lane state in HBM)" if adaptive
-                               else "tran_fixed_kernel<smem> (table-driven)"), "algorithmic_bytes_per_launch": alg_bytes,
+                         else (("tran_adaptive" if adaptive else "tran_fixed") +
+                               {"warp": "_warp_kernel (table-driven, one lane per warp, workspace row in HBM/L2)",
+                                "thread/hbm": "_kernel<global> (table-driven, one lane per thread, lane state in HBM)",
+                                "thread/smem": "_kernel<smem> (table-driven, one lane per thread)"}[comp.handle.lane_mapping()]),
+                         "algorithmic_bytes_per_launch": alg_bytes,
                          "bytes_per_newton_iter_per_lane": b_iter,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                         "note": ("lane state in HBM ([slot][thread] workspace): every stamp, factor entry and vector "
+                         "note": ("lane state is a [lane][slot] row in global memory shared by the 32 threads of the "
+                                  "lane's warp; the resident rows fit the L2, so DRAM traffic (ncu) is below the "
+                                  "algorithmic bytes and the limiter is latency per pivot / per device evaluation"
+                                  if comp.handle.lane_mapping() == "warp" else
+                                  "lane state in HBM ([slot][thread] workspace): every stamp, factor entry and vector "
                                   "element of an iteration is an HBM access, several times the algorithmic bytes"
-                                  if adaptive else
+                                  if comp.handle.lane_mapping() == "thread/hbm" else
                                   "state is on-chip (fused lane-per-thread kernel): the algorithmic-byte "
                                   "figure counts traffic a non-fused pipeline would move through HBM")},
             "clocks": clocks}

@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_CSRC, "libcadnip_b200.so")
 _SOURCES = ["api.cu", "kernels.cu", "symbolic.cpp", "specialize.cpp"]
-_HEADERS = ["kernels.h", "cb200_internal.h", "lane_kernels.cuh", "specialize.h",
+_HEADERS = ["kernels.h", "cb200_internal.h", "lane_kernels.cuh", "warp_kernels.cuh", "specialize.h",
             os.path.join("..", "..", "include", "cadnip_b200.h")]
 GEN_DIR = os.path.join(_HERE, "_gen")
 
@@ -158,6 +158,8 @@ def lib():
     L.cb200_specialize.argtypes = [vp, C.POINTER(Spec), C.c_int32, C.c_double, C.c_char_p, C.c_char_p, C.c_int32]
     L.cb200_is_specialized.restype = C.c_int
     L.cb200_is_specialized.argtypes = [vp]
+    L.cb200_lane_mapping.restype = C.c_int
+    L.cb200_lane_mapping.argtypes = [vp]
     L.cb200_load_va_models.restype = C.c_int
     L.cb200_load_va_models.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
     L.cb200_emit_source.restype = C.c_int64
@@ -195,7 +197,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "cb200_abi_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_pattern",
     "cb200_get_maps", "cb200_set_lanes", "cb200_analyze", "cb200_get_pivot_order", "cb200_eval",
-    "cb200_specialize", "cb200_is_specialized", "cb200_emit_source", "cb200_load_va_models",
+    "cb200_specialize", "cb200_is_specialized", "cb200_lane_mapping", "cb200_emit_source", "cb200_load_va_models",
     "cb200_dc", "cb200_tran", "cb200_tran_fetch", "cb200_set_tstops", "cb200_wave_info", "cb200_wave_fetch", "cb200_wave_final_state",
     "cb200_wave_free", "cb200_get_stats", "cb200_debug_exp"]
 
@@ -388,6 +390,10 @@ class Handle:
 
     def is_specialized(self) -> bool:
         return bool(lib().cb200_is_specialized(self._p))
+
+    def lane_mapping(self) -> str:
+        """Mapping of the table-driven kernels for this circuit (cb200_lane_mapping)."""
+        return {0: "thread/smem", 1: "thread/hbm", 2: "warp"}[lib().cb200_lane_mapping(self._p)]
 
     def pivot_order(self):
         r = np.zeros(self.n, np.int64); c = np.zeros(self.n, np.int64); nlu = C.c_int64()

@@ -123,6 +123,8 @@ struct DevLu {
     LuSchedule host;
     DevBuf<int> rowperm, colperm, diag_slot, Lptr, L_slot, L_row, Uptr, U_slot, U_col, tgt_ptr, tgt,
         jmap, fill_slots;
+    LevelSchedule lvl;
+    DevBuf<int> piv_ptr, sc_ptr, tg_ptr, piv, sc, tg, upd, flev_ptr, frow, fent, blev_ptr, brow, bent;
     LuProgram prog{};
 };
 
@@ -147,7 +149,7 @@ struct cb200_handle {
     DevBuf<int> d_dev_kind, d_dev_flags, d_dev_node_ptr, d_dev_nodes, d_dev_param_ptr, d_dev_params;
     DevBuf<int> d_dev_gbase, d_dev_cbase, d_dev_bbase, d_dev_sbase, d_src_list, d_nl_list, d_limit_init_ref;
     DevBuf<int> d_gseg_ptr, d_gseg_idx, d_cseg_ptr, d_cseg_idx, d_bseg_ptr, d_bseg_idx;
-    DevBuf<int> d_colptr, d_rowval;
+    DevBuf<int> d_colptr, d_rowval, d_rowptr, d_row_nz, d_nz_col;
     DevBuf<unsigned char> d_node_diag, d_src_uniform;
     DevBuf<double> d_uniform, d_lanes;
     DevBuf<double> d_state;        // [n][P]
@@ -245,6 +247,19 @@ static void layout_workspace(cb200_handle *h)
     if (nlu == 0) nlu = h->st.nnz;
     o += (int)nlu;
     p.n_slots = o;
+    // lane-per-warp kernels: per-entry sums and reciprocal pivots behind the common layout;
+    // a lane's row is padded to a whole number of 128-byte lines
+    p.off_GS = o; o += (int)h->st.nnz;
+    p.off_CS = o; o += (int)h->st.nnz;
+    p.off_DI = o; o += n;
+    p.n_slots_w = (o + 15) / 16 * 16;
+}
+
+// the lane workspace lives in global memory (lane-per-warp kernels, or shared-memory overflow)
+static bool needs_global_ws(const cb200_handle *h)
+{
+    return use_warp_kernels(h->prog.n_slots, h->smem_limit, h->block_pref) ||
+           choose_block(h->prog.n_slots, h->smem_limit, h->block_pref) == 0;
 }
 
 // devices whose stamps depend on time only (evaluated once per time step) ...
@@ -344,6 +359,19 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
     cudaStream_t s = h->stream;
     const Structure &st = h->st;
     std::vector<unsigned char> nd8(st.nz_is_node_diag.begin(), st.nz_is_node_diag.end());
+    // CSR view of the CSC pattern for the row-parallel residual of the lane-per-warp kernels:
+    // a counting sort over columns in ascending order leaves every row's entries column-sorted
+    std::vector<int> rowptr(st.n + 1, 0), row_nz(st.nnz), nz_col(st.nnz);
+    for (int64_t q = 0; q < st.nnz; q++) rowptr[st.rowval[q] + 1]++;
+    for (int r = 0; r < st.n; r++) rowptr[r + 1] += rowptr[r];
+    {
+        std::vector<int> fillp(rowptr.begin(), rowptr.end() - 1);
+        for (int j = 0; j < st.n; j++)
+            for (int q = st.colptr[j]; q < st.colptr[j + 1]; q++) {
+                nz_col[q] = j;
+                row_nz[fillp[st.rowval[q]]++] = q;
+            }
+    }
     bool ok = h->d_dev_kind.upload(h->dev_kind, s) == cudaSuccess &&
               h->d_dev_flags.upload(h->dev_flags, s) == cudaSuccess &&
               h->d_dev_node_ptr.upload(h->dev_node_ptr, s) == cudaSuccess &&
@@ -367,6 +395,9 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
               h->d_bseg_idx.upload(st.bseg_idx, s) == cudaSuccess &&
               h->d_colptr.upload(st.colptr, s) == cudaSuccess &&
               h->d_rowval.upload(st.rowval, s) == cudaSuccess &&
+              h->d_rowptr.upload(rowptr, s) == cudaSuccess &&
+              h->d_row_nz.upload(row_nz, s) == cudaSuccess &&
+              h->d_nz_col.upload(nz_col, s) == cudaSuccess &&
               h->d_node_diag.upload(nd8, s) == cudaSuccess;
     if (!ok || cudaStreamSynchronize(s) != cudaSuccess) {
         std::string m = std::string("cb200_create: upload failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -390,6 +421,7 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
     p.cseg_ptr = h->d_cseg_ptr.p; p.cseg_idx = h->d_cseg_idx.p;
     p.bseg_ptr = h->d_bseg_ptr.p; p.bseg_idx = h->d_bseg_idx.p;
     p.colptr = h->d_colptr.p; p.rowval = h->d_rowval.p; p.nz_is_node_diag = h->d_node_diag.p;
+    p.rowptr = h->d_rowptr.p; p.row_nz = h->d_row_nz.p; p.nz_col = h->d_nz_col.p;
     layout_workspace(h);
     *out = h;
     return CB200_OK;
@@ -450,7 +482,8 @@ static int ensure_lane_buffers(cb200_handle *h)
 
 static int ensure_global_ws(cb200_handle *h)
 {
-    const size_t need = (size_t)h->prog.n_slots * ((h->P + 63) / 64 * 64);   // lane kernels pad to the block (64)
+    // lane-per-thread kernels: [n_slots][P padded to the block (64)]; lane-per-warp: [P][n_slots_w]
+    const size_t need = (size_t)std::max(h->prog.n_slots, h->prog.n_slots_w) * ((h->P + 63) / 64 * 64);
     if (h->d_ws_global.n < need) CUDA_TRY(h, h->d_ws_global.alloc(need));
     return CB200_OK;
 }
@@ -491,6 +524,14 @@ static int upload_lu(cb200_handle *h, DevLu &L)
     CUDA_TRY(h, L.U_col.upload(S.U_col, s));
     CUDA_TRY(h, L.tgt_ptr.upload(S.tgt_ptr, s)); CUDA_TRY(h, L.tgt.upload(S.tgt, s));
     CUDA_TRY(h, L.jmap.upload(S.jmap, s)); CUDA_TRY(h, L.fill_slots.upload(S.fill_slots, s));
+    build_level_schedule(S, L.lvl);
+    const LevelSchedule &V = L.lvl;
+    CUDA_TRY(h, L.piv_ptr.upload(V.piv_ptr, s)); CUDA_TRY(h, L.sc_ptr.upload(V.sc_ptr, s));
+    CUDA_TRY(h, L.tg_ptr.upload(V.tg_ptr, s)); CUDA_TRY(h, L.piv.upload(V.piv, s));
+    CUDA_TRY(h, L.sc.upload(V.sc, s)); CUDA_TRY(h, L.tg.upload(V.tg, s)); CUDA_TRY(h, L.upd.upload(V.upd, s));
+    CUDA_TRY(h, L.flev_ptr.upload(V.flev_ptr, s)); CUDA_TRY(h, L.frow.upload(V.frow, s));
+    CUDA_TRY(h, L.fent.upload(V.fent, s)); CUDA_TRY(h, L.blev_ptr.upload(V.blev_ptr, s));
+    CUDA_TRY(h, L.brow.upload(V.brow, s)); CUDA_TRY(h, L.bent.upload(V.bent, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     LuProgram &q = L.prog;
     q.n = S.n; q.nlu = (int)S.nlu; q.n_fill = (int)S.fill_slots.size();
@@ -498,6 +539,12 @@ static int upload_lu(cb200_handle *h, DevLu &L)
     q.Lptr = L.Lptr.p; q.L_slot = L.L_slot.p; q.L_row = L.L_row.p;
     q.Uptr = L.Uptr.p; q.U_slot = L.U_slot.p; q.U_col = L.U_col.p;
     q.tgt_ptr = L.tgt_ptr.p; q.tgt = L.tgt.p; q.jmap = L.jmap.p; q.fill_slots = L.fill_slots.p;
+    q.n_lev = V.n_lev; q.n_fwd = V.n_fwd; q.n_bwd = V.n_bwd;
+    q.piv_ptr = L.piv_ptr.p; q.sc_ptr = L.sc_ptr.p; q.tg_ptr = L.tg_ptr.p;
+    q.piv = (const int2 *)L.piv.p; q.sc = (const int2 *)L.sc.p;
+    q.tg = (const int4 *)L.tg.p; q.upd = (const int4 *)L.upd.p;
+    q.flev_ptr = L.flev_ptr.p; q.frow = (const int4 *)L.frow.p; q.fent = (const int2 *)L.fent.p;
+    q.blev_ptr = L.blev_ptr.p; q.brow = (const int4 *)L.brow.p; q.bent = (const int2 *)L.bent.p;
     return CB200_OK;
 }
 
@@ -671,7 +718,7 @@ static int dc_launch(DcRun &r, int algorithm, const unsigned char *d_active, con
     a.u = h->d_state.p; a.active = d_active; a.gshunt_lane = d_gshunt; a.srcfact_lane = d_srcfact;
     a.status = h->d_status.p; a.iters = h->d_iters.p; a.converged = h->d_conv.p;
     a.ws_global = nullptr;
-    if (choose_block(h->prog.n_slots, h->smem_limit, h->block_pref) == 0) {
+    if (needs_global_ws(h)) {
         int rc = ensure_global_ws(h);
         if (rc != CB200_OK) return rc;
         a.ws_global = h->d_ws_global.p;
@@ -950,7 +997,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
     SpecArgs sa = spec_args(spec);
     sa.mode = CB200_MODE_TRAN;
     double *ws_global = nullptr;
-    if (choose_block(h->prog.n_slots, h->smem_limit, h->block_pref) == 0) {
+    if (needs_global_ws(h)) {
         rc = ensure_global_ws(h);
         if (rc != CB200_OK) { delete w; return rc; }
         ws_global = h->d_ws_global.p;
@@ -1178,6 +1225,13 @@ extern "C" int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t
 }
 
 extern "C" int cb200_is_specialized(const cb200_handle *h) { return h && spec_usable(h) ? 1 : 0; }
+
+extern "C" int cb200_lane_mapping(const cb200_handle *h)
+{
+    if (!h) return CB200_EINVAL;
+    if (use_warp_kernels(h->prog.n_slots, h->smem_limit, h->block_pref)) return 2;
+    return choose_block(h->prog.n_slots, h->smem_limit, h->block_pref) == 0 ? 1 : 0;
+}
 
 // Host-only view of the emitter (no device needed): structure + LU analysis from
 // caller-supplied nominal magnitudes |J| (DC and transient) -> generated CUDA source.

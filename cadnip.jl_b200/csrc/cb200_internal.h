@@ -50,4 +50,26 @@ struct LuSchedule {
 std::string analyze_lu(const Structure &s, const std::vector<double> &absJ, double threshold,
                        LuSchedule &out);
 
+// Level schedule of the same factorisation for the lane-per-warp kernels (warp_kernels.cuh):
+// the elimination DAG cut into levels whose operations are independent, so that the 32 threads
+// of a lane's warp work in parallel between two __syncwarp()s.  Every target entry still receives
+// its updates in ascending pivot order and every row of the triangular solves its terms in
+// ascending (L) / stored (U) order: the floating-point results equal the serial schedule's bit
+// for bit.  Arrays of int2 / int4 records are stored flattened.
+struct LevelSchedule {
+    int n_lev = 0, n_fwd = 0, n_bwd = 0;
+    std::vector<int> piv_ptr, sc_ptr, tg_ptr;   // [n_lev + 1] ranges of the three per-level lists
+    std::vector<int> piv;                       // int2 {pivot k, diag slot}
+    std::vector<int> sc;                        // int2 {L slot, pivot k}: L[slot] *= 1/pivot
+    std::vector<int> tg;                        // int4 {target slot, upd begin, upd end, 0}
+    std::vector<int> upd;                       // int4 {L slot, U slot, pivot k, 0}
+    std::vector<int> flev_ptr;                  // [n_fwd + 1]
+    std::vector<int> frow;                      // int4 {row i, rowperm[i], ent begin, ent end}
+    std::vector<int> fent;                      // int2 {L slot, column k}
+    std::vector<int> blev_ptr;                  // [n_bwd + 1]
+    std::vector<int> brow;                      // int4 {row k, ent begin, ent end, 0}
+    std::vector<int> bent;                      // int2 {U slot, column}
+};
+void build_level_schedule(const LuSchedule &S, LevelSchedule &out);
+
 }  // namespace cb200

@@ -31,6 +31,13 @@ struct Program {
     int off_srcc;                   // [n_src] warp-cooperative source value cache
     int off_h1, off_h2;             // adaptive history (u_{n-1}, u_{n-2})
     int n_slots;
+    // lane-per-warp kernels (warp_kernels.cuh): CSR view of the pattern (row -> nz indices in
+    // column order, nz -> column) and three more workspace arrays behind the n_slots above:
+    // per-entry G and C sums [nnz] each, reciprocal pivots [n].  A lane's workspace is the
+    // contiguous row ws[lane * n_slots_w + slot].
+    const int *rowptr, *row_nz, *nz_col;
+    int off_GS, off_CS, off_DI;
+    int n_slots_w;
 };
 
 // Static-pivot LU schedule (see LuSchedule in cb200_internal.h).
@@ -38,6 +45,18 @@ struct LuProgram {
     int n, nlu, n_fill;
     const int *rowperm, *colperm, *diag_slot;
     const int *Lptr, *L_slot, *L_row, *Uptr, *U_slot, *U_col, *tgt_ptr, *tgt, *jmap, *fill_slots;
+    // level schedule of the same factorisation (lane-per-warp kernels; LevelSchedule in
+    // cb200_internal.h): per level the pivots, the L entries to scale and the update targets
+    int n_lev, n_fwd, n_bwd;
+    const int *piv_ptr, *sc_ptr, *tg_ptr;
+    const int2 *piv, *sc;
+    const int4 *tg, *upd;
+    const int *flev_ptr;
+    const int4 *frow;
+    const int2 *fent;
+    const int *blev_ptr;
+    const int4 *brow;
+    const int2 *bent;
 };
 
 struct SpecArgs {
@@ -70,6 +89,7 @@ struct DcArgs {
     int *iters;             // [P] (+= linear solves)
     unsigned char *converged;  // [P]
     double *ws_global;      // used when the lane workspace does not fit in shared memory
+    int hot_smem;           // set by the launcher (lane-per-warp kernels: shared-memory configuration)
 };
 cudaError_t launch_dc(const Program &p, const LuProgram &lu, const SpecArgs &s, const DcArgs &a,
                       int block, size_t smem_limit, cudaStream_t st, int64_t *launches);
@@ -94,6 +114,7 @@ struct TranArgs {
     int *status;            // [P]
     int *iters;             // [P]
     double *ws_global;
+    int hot_smem;
 };
 cudaError_t launch_tran_fixed(const Program &p, const LuProgram &lu, const SpecArgs &s,
                               const TranArgs &a, int block, size_t smem_limit, cudaStream_t st,
@@ -117,6 +138,7 @@ struct AdaptArgs {
     int *count;             // [P]
     int *status, *iters, *rejected;
     double *ws_global;
+    int hot_smem;
 };
 cudaError_t launch_tran_adaptive(const Program &p, const LuProgram &lu, const SpecArgs &s,
                                  const AdaptArgs &a, int block, size_t smem_limit,
@@ -126,6 +148,8 @@ cudaError_t launch_debug_exp(const double *x, double *y, int n, cudaStream_t st)
 
 // pick lanes-per-block so the lane workspace fits in shared memory (0 = use global)
 int choose_block(int n_slots, size_t smem_limit, int preferred);
+// true: the circuit runs on the lane-per-warp kernels (workspace [lane][n_slots_w] in HBM / L2)
+bool use_warp_kernels(int n_slots, size_t smem_limit, int preferred);
 
 }  // namespace cb200
 

@@ -92,6 +92,13 @@ struct DynProg {
     __device__ __forceinline__ int off_srcc() const { return p.off_srcc; }
     __device__ __forceinline__ int off_h1() const { return p.off_h1; }
     __device__ __forceinline__ int off_h2() const { return p.off_h2; }
+    // lane-per-warp kernels only (warp_kernels.cuh)
+    __device__ __forceinline__ int rowptr(int r) const { return __ldg(p.rowptr + r); }
+    __device__ __forceinline__ int row_nz(int q) const { return __ldg(p.row_nz + q); }
+    __device__ __forceinline__ int nz_col(int s) const { return __ldg(p.nz_col + s); }
+    __device__ __forceinline__ int off_GS() const { return p.off_GS; }
+    __device__ __forceinline__ int off_CS() const { return p.off_CS; }
+    __device__ __forceinline__ int off_DI() const { return p.off_DI; }
 };
 
 struct DynLu {

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <numeric>
 
 #include "cb200_internal.h"
@@ -231,6 +232,113 @@ std::string analyze_lu(const Structure &s, const std::vector<double> &absJ, doub
     for (int64_t t = 0; t < nlu; t++) if (!has_src[t]) out.fill_slots.push_back((int)t);
     out.valid = true;
     return "";
+}
+
+// ---------------------------------------------------------------------------
+// Level schedule for the lane-per-warp kernels (see LevelSchedule).
+// ---------------------------------------------------------------------------
+void build_level_schedule(const LuSchedule &S, LevelSchedule &out)
+{
+    out = LevelSchedule();
+    const int n = S.n;
+    // ---- factorisation levels.  Pivot k may run once every update into its row, column and
+    // diagonal has been applied (lev[min(i, j)] > lev[k] for each target (i, j) of k); and the
+    // updates of one target must keep ascending pivot order, so a pivot never runs at a level
+    // below the last pivot that touched one of its targets.
+    std::vector<int> lev(n, 0), last_lev((size_t)S.nlu, -1);
+    for (int k = 0; k < n; k++) {
+        const int l0 = S.Lptr[k], nL = S.Lptr[k + 1] - l0, u0 = S.Uptr[k], nU = S.Uptr[k + 1] - u0;
+        const int t0 = S.tgt_ptr[k];
+        for (int x = 0; x < nL * nU; x++) lev[k] = std::max(lev[k], last_lev[S.tgt[t0 + x]]);
+        for (int e = 0; e < nL; e++)
+            for (int q = 0; q < nU; q++) {
+                last_lev[S.tgt[t0 + e * nU + q]] = lev[k];
+                const int m = std::min(S.L_row[l0 + e], S.U_col[u0 + q]);
+                lev[m] = std::max(lev[m], lev[k] + 1);
+            }
+    }
+    int nlev = 0;
+    for (int k = 0; k < n; k++) nlev = std::max(nlev, lev[k] + 1);
+    out.n_lev = nlev;
+    std::vector<std::vector<int>> by_lev(nlev);
+    for (int k = 0; k < n; k++) by_lev[lev[k]].push_back(k);
+    out.piv_ptr.push_back(0); out.sc_ptr.push_back(0); out.tg_ptr.push_back(0);
+    std::vector<int> tg_of((size_t)S.nlu, -1);          // target slot -> index in this level's list
+    for (int v = 0; v < nlev; v++) {
+        std::vector<int> tslots;
+        std::vector<std::vector<int>> ups;               // per target: {ls, us, k} triples, ascending k
+        for (int k : by_lev[v]) {
+            out.piv.push_back(k); out.piv.push_back(S.diag_slot[k]);
+            const int l0 = S.Lptr[k], nL = S.Lptr[k + 1] - l0, u0 = S.Uptr[k], nU = S.Uptr[k + 1] - u0;
+            for (int e = 0; e < nL; e++) { out.sc.push_back(S.L_slot[l0 + e]); out.sc.push_back(k); }
+            for (int e = 0; e < nL; e++)
+                for (int q = 0; q < nU; q++) {
+                    const int t = S.tgt[S.tgt_ptr[k] + e * nU + q];
+                    if (tg_of[t] < 0) { tg_of[t] = (int)tslots.size(); tslots.push_back(t); ups.emplace_back(); }
+                    std::vector<int> &u = ups[tg_of[t]];
+                    u.push_back(S.L_slot[l0 + e]); u.push_back(S.U_slot[u0 + q]); u.push_back(k);
+                }
+        }
+        for (size_t i = 0; i < tslots.size(); i++) {
+            const int ub = (int)(out.upd.size() / 4);
+            for (size_t x = 0; x < ups[i].size(); x += 3) {
+                out.upd.push_back(ups[i][x]); out.upd.push_back(ups[i][x + 1]);
+                out.upd.push_back(ups[i][x + 2]); out.upd.push_back(0);
+            }
+            out.tg.push_back(tslots[i]); out.tg.push_back(ub);
+            out.tg.push_back((int)(out.upd.size() / 4)); out.tg.push_back(0);
+            tg_of[tslots[i]] = -1;
+        }
+        out.piv_ptr.push_back((int)(out.piv.size() / 2));
+        out.sc_ptr.push_back((int)(out.sc.size() / 2));
+        out.tg_ptr.push_back((int)(out.tg.size() / 4));
+    }
+    // ---- forward solve z = L^-1 P F by rows: z[i] = F[rowperm[i]] - sum_k L[i][k] z[k], k ascending
+    std::vector<int> zl(n, 0);
+    std::vector<std::vector<int>> lrow(n);
+    for (int k = 0; k < n; k++)
+        for (int e = S.Lptr[k]; e < S.Lptr[k + 1]; e++) {
+            const int i = S.L_row[e];
+            zl[i] = std::max(zl[i], zl[k] + 1);
+            lrow[i].push_back(S.L_slot[e]); lrow[i].push_back(k);
+        }
+    int nf = 0;
+    for (int i = 0; i < n; i++) nf = std::max(nf, zl[i] + 1);
+    out.n_fwd = nf;
+    out.flev_ptr.push_back(0);
+    for (int v = 0; v < nf; v++) {
+        for (int i = 0; i < n; i++) {
+            if (zl[i] != v) continue;
+            const int b = (int)(out.fent.size() / 2);
+            out.fent.insert(out.fent.end(), lrow[i].begin(), lrow[i].end());
+            out.frow.push_back(i); out.frow.push_back(S.rowperm[i]);
+            out.frow.push_back(b); out.frow.push_back((int)(out.fent.size() / 2));
+        }
+        out.flev_ptr.push_back((int)(out.frow.size() / 4));
+    }
+    // ---- backward solve y = U^-1 z by rows, last pivot first
+    std::vector<int> xl(n, 0);
+    int nb = 0;
+    for (int k = n - 1; k >= 0; k--) {
+        for (int q = S.Uptr[k]; q < S.Uptr[k + 1]; q++) xl[k] = std::max(xl[k], xl[S.U_col[q]] + 1);
+        nb = std::max(nb, xl[k] + 1);
+    }
+    out.n_bwd = nb;
+    out.blev_ptr.push_back(0);
+    for (int v = 0; v < nb; v++) {
+        for (int k = n - 1; k >= 0; k--) {
+            if (xl[k] != v) continue;
+            const int b = (int)(out.bent.size() / 2);
+            for (int q = S.Uptr[k]; q < S.Uptr[k + 1]; q++) { out.bent.push_back(S.U_slot[q]); out.bent.push_back(S.U_col[q]); }
+            out.brow.push_back(k); out.brow.push_back(b);
+            out.brow.push_back((int)(out.bent.size() / 2)); out.brow.push_back(0);
+        }
+        out.blev_ptr.push_back((int)(out.brow.size() / 4));
+    }
+    if (getenv("CB200_DEBUG_LU"))
+        fprintf(stderr, "[cb200] level schedule: n=%d nlu=%lld factor levels=%d (targets=%zu updates=%zu) "
+                        "forward levels=%d backward levels=%d\n", n, (long long)S.nlu, nlev,
+                out.tg.size() / 4, out.upd.size() / 4, nf, nb);
 }
 
 }  // namespace cb200

@@ -1,0 +1,581 @@
+// warp_kernels.cuh -- the batched MNA Newton / transient hot path for MEDIUM circuits:
+// one sweep lane per WARP.
+//
+// lane_kernels.cuh gives every lane one thread.  That is the right mapping while the lane state
+// fits in registers / shared memory and the sweep has >> 148 * 2048 lanes; a circuit such as
+// the gf180 D flip-flop (30 Verilog-A FETs, n = 145, ~5000 workspace doubles, 16 384 lanes) then
+// runs 110 threads per SM, each walking its own 40 KB column of HBM -- pure latency.  Here the 32
+// threads of a warp share ONE lane:
+//   * device evaluation: thread i evaluates device instance i, i + 32, ... (30 FETs = one round);
+//   * assembly: thread per matrix entry sums its stamp segment in program order, then thread per
+//     row forms F = C*du + G*u - b over the row's entries in column order;
+//   * LU refactor on the host's static pivot order, cut into LEVELS of independent pivots: per
+//     level one thread per pivot (reciprocal), one per L entry (scaling), one per target entry
+//     (its updates in ascending pivot order), two __syncwarp per level;
+//   * triangular solves by rows, one thread per row of a level, one __syncwarp per level;
+//   * norms are summed by every thread over ALL rows in index order.
+// Every floating-point operation is performed with the same operands in the same order as in
+// lane_kernels.cuh (only WHICH thread performs it changes), so the two mappings agree bit for bit;
+// tests/test_gpu_parity.py asserts identical waveforms and Newton iteration counts.
+// The lane's workspace is a contiguous row ws[lane][slot] of a global array: consecutive slots
+// are consecutive addresses, a warp's accesses coalesce, and the resident working set
+// (16 warps/SM * 148 SMs * 40 KB = 95 MB) lives in the 126 MB L2.  The arrays on the
+// DEPENDENT chains of the refactor and the triangular solves -- the LU factor, the residual /
+// solution vector, the work vector and the reciprocal pivots (3n + nnz_LU doubles, 9 KB for the
+// flip-flop) -- are staged in SHARED memory (struct Hot): a pivot step is two dependent memory
+// round trips, and at L2 latency those 145 * 2 * 3 round trips were the whole iteration
+// (measured: 3.75 s per C4 sweep with the factor in L2; see profiles/README.md).
+#pragma once
+#include "lane_kernels.cuh"
+
+namespace cb200 {
+
+#define CB_FULL 0xffffffffu
+
+// latency-critical arrays of a lane: shared memory when they fit (generic pointers: the same
+// code runs with them left in the lane's global row)
+struct Hot {
+    double *F, *wv, *DI, *LU;
+    double *buf;      // shared-memory gather buffer of the segmented assembly, ch doubles
+    int ch;
+};
+
+__device__ __forceinline__ int wtid() { return threadIdx.x & 31; }
+
+template <typename PG, typename W>
+__device__ __forceinline__ void w_eval_all(const PG &pg, W &w, double t, int mode, bool initjct)
+{
+    for (int d = wtid(); d < pg.n_dev(); d += 32) eval_device<0>(pg, w, d, t, mode, initjct);
+    __syncwarp();
+}
+
+template <typename PG, typename W>
+__device__ __forceinline__ void w_eval_nonlinear(const PG &pg, W &w, double t, int mode, bool initjct)
+{
+    for (int q = wtid(); q < pg.n_nl(); q += 32) eval_device<1>(pg, w, pg.nl_list(q), t, mode, initjct);
+    __syncwarp();
+}
+
+template <typename PG, typename W>
+__device__ __forceinline__ void w_eval_sources(const PG &pg, W &w, double t, int mode)
+{
+    for (int q = wtid(); q < pg.n_src(); q += 32) eval_device<2>(pg, w, pg.src_list(q), t, mode, false);
+    __syncwarp();
+}
+
+// Segmented sums of the assembly.  A segment (all stamps of one matrix entry, in program order)
+// must be added up left to right to reproduce the reference's `nzval[idx] += v`, and segment
+// lengths are wildly skewed (the flip-flop's (VDD, VDD) entry collects ~900 stamps, the median
+// entry 4), so one thread walking `w(off + idx[q])` serialises ~900 dependent global-memory
+// round trips -- measured: 54 % of the kernel at 3.8 active threads.  Instead the warp gathers
+// the stamps of `ch` consecutive segment positions into shared memory with all 32 threads
+// (independent loads, one latency for the lot), and each thread then adds up the part of ITS
+// segments that lies in the chunk from shared memory, carrying the running sum of a segment that
+// spans chunks in a register.  Same addition order, two orders of magnitude less latency.
+template <typename W, typename PtrF, typename IdxF, typename Fin>
+__device__ __forceinline__ void w_segsum(W &w, const Hot &hot, int off, int nseg, int total, PtrF ptr,
+                                         IdxF idx, Fin finish)
+{
+    const int tl = wtid();
+    int s = tl, p = 0, pend = 0;
+    double acc = 0.0;
+    if (s < nseg) { p = ptr(s); pend = ptr(s + 1); }
+    for (int c0 = 0; c0 < total; c0 += hot.ch) {
+        const int cend = min(c0 + hot.ch, total);
+        for (int j = c0 + tl; j < cend; j += 32) hot.buf[j - c0] = w(off + idx(j));
+        __syncwarp();
+        while (s < nseg) {
+            const int hi = pend < cend ? pend : cend;
+            for (; p < hi; p++) acc += hot.buf[p - c0];
+            if (pend > cend) break;                         // the segment continues in the next chunk
+            finish(s, acc);
+            s += 32; acc = 0.0;
+            if (s < nseg) { p = ptr(s); pend = ptr(s + 1); }
+        }
+        __syncwarp();
+    }
+    for (; s < nseg; s += 32) finish(s, 0.0);               // total == 0: every segment is empty
+}
+
+// assemble() of lane_kernels.cuh: segmented sums (above), Jacobian scatter entry-parallel,
+// residual row-parallel.
+template <bool TRAN, typename PG, typename LU, typename W>
+__device__ __forceinline__ double w_assemble(const PG &pg, const LU &lu, W &w, const Hot &hot,
+                                             double gamma, double gshunt, double srcFact, bool &bad)
+{
+    const int tl = wtid();
+    const int oGS = pg.off_GS(), oCS = pg.off_CS();
+    for (int q = tl; q < lu.n_fill(); q += 32) hot.LU[lu.fill_slot(q)] = 0.0;
+    w_segsum(w, hot, pg.off_SG(), pg.nnz(), pg.p.nG,
+             [&](int s) { return pg.gseg_ptr(s); }, [&](int q) { return pg.gseg_idx(q); },
+             [&](int s, double v) {
+                 if (gshunt != 0.0 && pg.nz_is_node_diag(s)) v += gshunt;
+                 w(oGS + s) = v;
+             });
+    if (TRAN)
+        w_segsum(w, hot, pg.off_SC(), pg.nnz(), pg.p.nC,
+                 [&](int s) { return pg.cseg_ptr(s); }, [&](int q) { return pg.cseg_idx(q); },
+                 [&](int s, double v) { w(oCS + s) = v; });
+    w_segsum(w, hot, pg.off_SB(), pg.n(), pg.p.nb,
+             [&](int r) { return pg.bseg_ptr(r); }, [&](int q) { return pg.bseg_idx(q); },
+             [&](int r, double v) { hot.wv[r] = v; });      // wv is free until the solve
+    for (int s = tl; s < pg.nnz(); s += 32) {               // thread s % 32 reads back its own sums
+        double jv = w(oGS + s);
+        if (TRAN) jv += gamma * w(oCS + s);
+        hot.LU[lu.jmap(s)] = jv;
+    }
+    __syncwarp();
+    for (int r = tl; r < pg.n(); r += 32) {
+        double f = 0.0;
+        const int q1 = pg.rowptr(r + 1);
+        for (int q = pg.rowptr(r); q < q1; q++) {           // the row's entries, columns ascending
+            const int s = pg.row_nz(q), j = pg.nz_col(s);
+            const double uj = w(pg.off_u() + j);
+            if (TRAN) {
+                const double duj = gamma * (uj - w(pg.off_un() + j)) + w(pg.off_dterm() + j);
+                f += w(oCS + s) * duj;
+            }
+            f += w(oGS + s) * uj;
+        }
+        double bsum = hot.wv[r];
+        if (srcFact < 1.0) bsum *= srcFact;
+        hot.F[r] = f - bsum;
+    }
+    __syncwarp();
+    double nrm2 = 0.0;
+    for (int r = 0; r < pg.n(); r++) {                      // every thread, index order (broadcast loads)
+        const double f = hot.F[r];
+        nrm2 += f * f;
+    }
+    bad = !isfinite(nrm2);
+    return nrm2;
+}
+
+// factor_and_solve() of lane_kernels.cuh on the LEVEL schedule (LevelSchedule, cb200_internal.h):
+// the pivots of a level are independent, so a level is two warp-wide phases --
+//   A: 1/pivot for the level's pivots (to its own array DI, so that no thread can see it in place
+//      of the pivot) and, one level late, the scaling of the previous level's L columns;
+//   B: one thread per target entry applies that entry's updates a -= (L_raw * 1/pivot) * U in
+//      ascending pivot order;
+// then the triangular solves by rows, one thread per row of a level.  The solution ends up in
+// the F slots (pivot coordinates).  Same operands, same order per entry as the serial schedule.
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ bool w_factor_and_solve(const PG &pg, const LU &lu, W &w, const Hot &hot,
+                                                   bool &singular)
+{
+    const int tl = wtid();
+    const LuProgram &l = lu.l;
+    double *const sLU = hot.LU, *const sDI = hot.DI, *const sWV = hot.wv, *const sF = hot.F;
+    bool sing = false;
+    const int nlev = l.n_lev;
+    for (int v = 0; v <= nlev; v++) {
+        if (v < nlev) {
+            const int p1 = __ldg(l.piv_ptr + v + 1);
+            for (int q = __ldg(l.piv_ptr + v) + tl; q < p1; q += 32) {
+                const int2 pk = __ldg(l.piv + q);
+                const double dgl = sLU[pk.y];
+                if (!(fabs(dgl) >= DBL_MIN) || !isfinite(dgl)) sing = true;
+                sDI[pk.x] = 1.0 / dgl;
+            }
+        }
+        if (v > 0) {
+            const int s1 = __ldg(l.sc_ptr + v);
+            for (int q = __ldg(l.sc_ptr + v - 1) + tl; q < s1; q += 32) {
+                const int2 e = __ldg(l.sc + q);
+                sLU[e.x] = sLU[e.x] * sDI[e.y];
+            }
+        }
+        __syncwarp();
+        if (v < nlev) {
+            const int t1 = __ldg(l.tg_ptr + v + 1);
+            for (int q = __ldg(l.tg_ptr + v) + tl; q < t1; q += 32) {
+                const int4 t = __ldg(l.tg + q);
+                double a = sLU[t.x];
+                for (int u = t.y; u < t.z; u++) {
+                    const int4 up = __ldg(l.upd + u);
+                    const double lv = sLU[up.x] * sDI[up.z];
+                    a = a - lv * sLU[up.y];
+                }
+                sLU[t.x] = a;
+            }
+            __syncwarp();
+        }
+    }
+    // forward: z[i] = F[rowperm[i]] - sum_k L[i][k] z[k]
+    for (int v = 0; v < l.n_fwd; v++) {
+        const int r1 = __ldg(l.flev_ptr + v + 1);
+        for (int q = __ldg(l.flev_ptr + v) + tl; q < r1; q += 32) {
+            const int4 r = __ldg(l.frow + q);
+            double acc = sF[r.y];
+            for (int e = r.z; e < r.w; e++) {
+                const int2 en = __ldg(l.fent + e);
+                acc = acc - sLU[en.x] * sWV[en.y];
+            }
+            sWV[r.x] = acc;
+        }
+        __syncwarp();
+    }
+    // backward: y[k] = (z[k] - sum_j U[k][j] y[j]) / pivot; y in the F slots
+    bool finite = true;
+    for (int v = 0; v < l.n_bwd; v++) {
+        const int r1 = __ldg(l.blev_ptr + v + 1);
+        for (int q = __ldg(l.blev_ptr + v) + tl; q < r1; q += 32) {
+            const int4 r = __ldg(l.brow + q);
+            double acc = sWV[r.x];
+            for (int e = r.y; e < r.z; e++) {
+                const int2 en = __ldg(l.bent + e);
+                acc -= sLU[en.x] * sF[en.y];
+            }
+            acc *= sDI[r.x];
+            sF[r.x] = acc;
+            finite &= isfinite(acc);
+        }
+        __syncwarp();
+    }
+    singular = __any_sync(CB_FULL, sing);
+    return __all_sync(CB_FULL, finite) && !singular;
+}
+
+// u[colperm[k]] -= delta[k]   (delta in the F slots)
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ void w_apply_update(const PG &pg, const LU &lu, W &w, const Hot &hot)
+{
+    for (int k = wtid(); k < lu.n(); k += 32) {
+        const int j = pg.off_u() + lu.colperm(k);
+        w(j) = w(j) - hot.F[k];
+    }
+    __syncwarp();
+}
+
+template <typename PG, typename W>
+__device__ __forceinline__ void w_copy(const PG &pg, W &w, int dst, int src, int count)
+{
+    for (int i = wtid(); i < count; i += 32) w(dst + i) = w(src + i);
+    __syncwarp();
+}
+
+template <typename PG, typename W>
+__device__ __forceinline__ void w_load_lane_params(const PG &pg, W &w, const double *lanes, int64_t P,
+                                                   int64_t lane)
+{
+    for (int c = wtid(); c < pg.n_lane_cols(); c += 32) w(pg.off_lp() + c) = lanes[(int64_t)c * P + lane];
+}
+
+// ---------------------------------------------------------------------------
+// dc_body of lane_kernels.cuh (PCNR, solve.jl:599-698 / plain Newton, :542-578), one lane per warp
+// ---------------------------------------------------------------------------
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ void w_dc_body(const PG &pg, const LU &lu, W &w, const Program &p,
+                                          const SpecArgs &sp, const DcArgs &a, int64_t lane, const Hot &hot)
+{
+    const int tl = wtid();
+    if (a.active != nullptr && !a.active[lane]) return;      // masked lane: nothing to commit
+    const int n = pg.n();
+    w_load_lane_params(pg, w, p.lanes, p.P, lane);
+    bool cold = true;
+    for (int i = tl; i < n; i += 32) {
+        const double v = a.u[(int64_t)i * p.P + lane];
+        w(pg.off_u() + i) = v;
+        cold &= (v == 0.0);
+    }
+    cold = __all_sync(CB_FULL, cold);
+    const double gshunt = a.gshunt_lane ? a.gshunt_lane[lane] : sp.gshunt;
+    const double srcFact = a.srcfact_lane ? a.srcfact_lane[lane] : sp.srcFact;
+    const int lim0 = n - pg.n_limits();
+    const bool pcnr = (a.algorithm == 0);
+    const double abstol2 = a.abstol * a.abstol;
+    bool initjct = false;
+    if (pcnr && cold) {                                       // solve.jl:622-627
+        for (int k = tl; k < pg.n_limits(); k += 32) {
+            const int r = pg.limit_init_ref(k);
+            w(pg.off_u() + lim0 + k) = r >= 0 ? pg.uniform(r) : w(pg.off_lp() + ~r);
+        }
+        initjct = true;
+    }
+    __syncwarp();
+    w_eval_all(pg, w, a.t, sp.mode, false);
+
+    bool settling = false, conv = false;
+    int status = CB200_LANE_MAXITER, solves = 0, iter = 0;
+    while (true) {
+        if (!settling) iter++;
+        const int bound = pcnr ? a.maxiters : a.maxiters + 1;
+        if (iter > bound) { status = CB200_LANE_MAXITER; break; }
+        w_eval_nonlinear(pg, w, a.t, sp.mode, initjct);
+        initjct = false;
+        bool bad;
+        const double nrm2 = w_assemble<false>(pg, lu, w, hot, 0.0, gshunt, srcFact, bad);
+        if (bad) { status = CB200_LANE_NONFINITE; break; }
+        if (nrm2 < abstol2) {
+            if (!pcnr || settling) { conv = true; status = CB200_LANE_OK; break; }
+            w_copy(pg, w, pg.off_u() + lim0, pg.off_limw(), pg.n_limits());   // settle, re-verify
+            settling = true;
+            continue;
+        }
+        settling = false;
+        if (!pcnr && iter > a.maxiters) { status = CB200_LANE_MAXITER; break; }
+        bool singular;
+        const bool ok = w_factor_and_solve(pg, lu, w, hot, singular);
+        if (!ok) { status = singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE; break; }
+        w_apply_update(pg, lu, w, hot);
+        solves++;
+        if (pcnr) w_copy(pg, w, pg.off_u() + lim0, pg.off_limw(), pg.n_limits());   // CORRECT
+    }
+    __syncwarp();
+    for (int i = tl; i < n; i += 32) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+    if (tl == 0) {
+        a.status[lane] = status;
+        a.iters[lane] += solves;
+        a.converged[lane] = conv ? 1 : 0;
+    }
+}
+
+// One implicit step's Newton loop (shared by the fixed-step and adaptive bodies); returns the
+// lane status of the step and counts the linear solves.
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ int w_newton_step(const PG &pg, const LU &lu, W &w, const Hot &hot,
+                                             const SpecArgs &sp,
+                                             double t, double gamma, double abstol2, int max_nl,
+                                             int limit, int &solves)
+{
+    bool lim_on = false;
+    int it0 = 0;
+    for (int it = 0;; it++) {
+        w_eval_nonlinear(pg, w, t, CB200_MODE_TRAN, false);
+        bool bad;
+        const double nrm2 = w_assemble<true>(pg, lu, w, hot, gamma, sp.gshunt, sp.srcFact, bad);
+        bool restart = false;
+        if (bad) return CB200_LANE_NONFINITE;
+        if (nrm2 < abstol2) return CB200_LANE_OK;
+        if (it - it0 >= (lim_on ? 4 * max_nl : max_nl)) {
+            if (limit && !lim_on) { lim_on = true; it0 = it + 1; restart = true; }
+            else return CB200_LANE_MAXITER;
+        }
+        if (restart) {                                     // redo the step from u_n, limiting on
+            w_copy(pg, w, pg.off_u(), pg.off_un(), pg.n());
+            continue;
+        }
+        bool singular;
+        const bool ok = w_factor_and_solve(pg, lu, w, hot, singular);
+        if (!ok) return singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE;
+        w_apply_update(pg, lu, w, hot);
+        solves++;
+        if (lim_on) {                                      // PCNR corrector, solve.jl:686-689
+            const int lim0 = pg.n() - pg.n_limits();
+            w_copy(pg, w, pg.off_u() + lim0, pg.off_limw(), pg.n_limits());
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// tran_fixed_body of lane_kernels.cuh, one lane per warp
+// ---------------------------------------------------------------------------
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ void w_tran_fixed_body(const PG &pg, const LU &lu, W &w, const Program &p,
+                                                  const SpecArgs &sp, const TranArgs &a, int64_t lane,
+                                                  const Hot &hot)
+{
+    const int tl = wtid();
+    const int n = pg.n();
+    const bool resume = a.k_begin > 1;
+    w_load_lane_params(pg, w, p.lanes, p.P, lane);
+    for (int i = tl; i < n; i += 32) {
+        w(pg.off_u() + i) = a.u[(int64_t)i * p.P + lane];
+        w(pg.off_dterm() + i) = resume ? a.hist[(int64_t)(n + i) * p.P + lane] : 0.0;
+        w(pg.off_un() + i) = resume ? a.hist[(int64_t)i * p.P + lane] : 0.0;
+    }
+    __syncwarp();
+    w_eval_all(pg, w, a.t0, CB200_MODE_TRAN, false);
+
+    int status = a.status[lane], solves = 0;
+    int64_t tp = a.tp_begin;
+    if (!resume) {
+        for (int q = tl; q < a.n_save; q += 32)
+            a.out[((int64_t)q * a.T + tp) * p.P + lane] = w(pg.off_u() + __ldg(a.save_idx + q));
+        tp++;
+    }
+    const double h = a.h;
+    const double abstol2 = a.abstol * a.abstol;
+    const int amethod = a.method;
+    for (int64_t k = a.k_begin; k <= a.k_end; k++) {
+        const double t = a.t0 + (double)k * h;
+        const int method = (k == 1) ? CB200_METHOD_BE : amethod;
+        const double gamma = method == CB200_METHOD_BE ? 1.0 / h
+                           : method == CB200_METHOD_TRAP ? 2.0 / h : 3.0 / (2.0 * h);
+        for (int i = tl; i < n; i += 32) {
+            const double ui = w(pg.off_u() + i);
+            if (method == CB200_METHOD_GEAR2) w(pg.off_dterm() + i) = -(ui - w(pg.off_un() + i)) / (2.0 * h);
+            else if (method == CB200_METHOD_BE) w(pg.off_dterm() + i) = 0.0;
+            w(pg.off_un() + i) = ui;
+        }
+        __syncwarp();
+        w_eval_sources(pg, w, t, CB200_MODE_TRAN);
+        const int st = w_newton_step(pg, lu, w, hot, sp, t, gamma, abstol2, a.max_nl, a.limit, solves);
+        if (st != CB200_LANE_OK && status == CB200_LANE_OK) status = st;
+        if (st == CB200_LANE_NONFINITE || st == CB200_LANE_SINGULAR)     // dead lane: hold last state
+            w_copy(pg, w, pg.off_u(), pg.off_un(), n);
+        if (amethod == CB200_METHOD_TRAP) {
+            for (int i = tl; i < n; i += 32)
+                w(pg.off_dterm() + i) = -(gamma * (w(pg.off_u() + i) - w(pg.off_un() + i)) + w(pg.off_dterm() + i));
+            __syncwarp();
+        }
+        if (k % a.save_every == 0 || k == a.nsteps) {
+            for (int q = tl; q < a.n_save; q += 32)
+                a.out[((int64_t)q * a.T + tp) * p.P + lane] = w(pg.off_u() + __ldg(a.save_idx + q));
+            tp++;
+        }
+    }
+    for (int i = tl; i < n; i += 32) {
+        a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+        if (a.hist != nullptr) {
+            a.hist[(int64_t)i * p.P + lane] = w(pg.off_un() + i);
+            a.hist[(int64_t)(n + i) * p.P + lane] = w(pg.off_dterm() + i);
+        }
+    }
+    if (tl == 0) {
+        a.status[lane] = status;
+        a.iters[lane] += solves;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// tran_adaptive_body of lane_kernels.cuh, one lane per warp.  The LTE norm is summed by every
+// thread over all unknowns in index order (the scaled errors are staged in the wv slots).
+// ---------------------------------------------------------------------------
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ void w_tran_adaptive_body(const PG &pg, const LU &lu, W &w, const Program &p,
+                                                     const SpecArgs &sp, const AdaptArgs &a, int64_t lane,
+                                                     const Hot &hot)
+{
+    const int tl = wtid();
+    const int n = pg.n();
+    w_load_lane_params(pg, w, p.lanes, p.P, lane);
+    for (int i = tl; i < n; i += 32) {
+        w(pg.off_u() + i) = a.u[(int64_t)i * p.P + lane];
+        w(pg.off_dterm() + i) = 0.0;
+        w(pg.off_un() + i) = 0.0;
+        w(pg.off_h1() + i) = 0.0;
+        w(pg.off_h2() + i) = 0.0;
+    }
+    __syncwarp();
+    w_eval_all(pg, w, a.t0, CB200_MODE_TRAN, false);
+
+    int status = a.status[lane], solves = 0, rej = 0, T = 0;
+    if (tl == 0) a.out_t[(int64_t)T * p.P + lane] = a.t0;
+    for (int q = tl; q < a.n_save; q += 32)
+        a.out[((int64_t)q * a.max_points + T) * p.P + lane] = w(pg.off_u() + __ldg(a.save_idx + q));
+    T++;
+    const int amethod = a.method;
+    const double abstol2 = a.abstol * a.abstol;
+    double t = a.t0, h = a.h0, h1 = 0.0, h2 = 0.0;
+    int nhist = 0, istop = 0;
+    bool finished = !(t < a.t1);
+    while (!finished) {
+        // ---- choose the step
+        while (istop < a.n_tstops && __ldg(a.tstops + istop) <= t * (1 + 4e-16)) istop++;
+        double tnext = istop < a.n_tstops ? __ldg(a.tstops + istop) : a.t1;
+        if (tnext > a.t1) tnext = a.t1;
+        double hh = h;
+        bool hit = false;
+        if (t + hh >= tnext - 1e-3 * hh) { hh = tnext - t; hit = true; }
+        const double tn = hit ? tnext : t + hh;
+        const bool be = (nhist == 0 || amethod == CB200_METHOD_BE);
+        const double gamma = be ? 1.0 / hh : 2.0 / hh;
+        for (int i = tl; i < n; i += 32) {
+            w(pg.off_un() + i) = w(pg.off_u() + i);
+            if (be) w(pg.off_dterm() + i) = 0.0;           // trap: dterm holds -du_n
+        }
+        __syncwarp();
+        w_eval_sources(pg, w, tn, CB200_MODE_TRAN);
+        const int st = w_newton_step(pg, lu, w, hot, sp, tn, gamma, abstol2, a.max_nl, a.limit, solves);
+        if (st != CB200_LANE_OK) {                            // Newton failed: shrink and retry
+            w_copy(pg, w, pg.off_u(), pg.off_un(), n);
+            rej++;
+            h = hh / 4.0;
+            if (h < a.dtmin) {
+                if (status == CB200_LANE_OK) status = (st == CB200_LANE_MAXITER) ? CB200_LANE_DTMIN : st;
+                finished = true;
+            }
+            continue;
+        }
+        // ---- local truncation error estimate
+        double err = 0.0;
+        int pord = 1;
+        if (nhist >= 1) {
+            if (be || nhist == 1) {
+                const double r = hh / h1, c = hh / (2.0 * hh + h1);
+                for (int i = tl; i < n; i += 32) {
+                    const double ui = w(pg.off_u() + i), uni = w(pg.off_un() + i);
+                    const double up = uni + r * (uni - w(pg.off_h1() + i));
+                    const double tol = a.lte_abstol + a.reltol * fmax(fabs(ui), fabs(uni));
+                    hot.wv[i] = c * (ui - up) / tol;
+                }
+            } else {
+                pord = 2;
+                const double ta = -(h1 + h2), tb = -h1, tc = 0.0, tx = hh;
+                const double la = (tx - tb) * (tx - tc) / ((ta - tb) * (ta - tc));
+                const double lb = (tx - ta) * (tx - tc) / ((tb - ta) * (tb - tc));
+                const double lc = (tx - ta) * (tx - tb) / ((tc - ta) * (tc - tb));
+                const double c = hh * hh / (hh * hh + 2.0 * (hh + h1) * (hh + h1 + h2));
+                for (int i = tl; i < n; i += 32) {
+                    const double ui = w(pg.off_u() + i), uni = w(pg.off_un() + i);
+                    const double up = la * w(pg.off_h2() + i) + lb * w(pg.off_h1() + i) + lc * uni;
+                    const double tol = a.lte_abstol + a.reltol * fmax(fabs(ui), fabs(uni));
+                    hot.wv[i] = c * (ui - up) / tol;
+                }
+            }
+            __syncwarp();
+            double acc = 0.0;
+            for (int i = 0; i < n; i++) {
+                const double e = hot.wv[i];
+                acc += e * e;
+            }
+            err = sqrt(acc / (double)n);
+            __syncwarp();
+        }
+        if (err > 1.0) {                                      // reject
+            w_copy(pg, w, pg.off_u(), pg.off_un(), n);
+            rej++;
+            double f = 0.9 * pow(err, -1.0 / (pord + 1));
+            if (f < 0.2) f = 0.2;
+            h = hh * f;
+            if (h < a.dtmin) { if (status == CB200_LANE_OK) status = CB200_LANE_DTMIN; finished = true; }
+            continue;
+        }
+        // ---- accept
+        for (int i = tl; i < n; i += 32) {
+            const double ui = w(pg.off_u() + i), uni = w(pg.off_un() + i);
+            w(pg.off_dterm() + i) = -(gamma * (ui - uni) + w(pg.off_dterm() + i));   // -du_{n+1}
+            w(pg.off_h2() + i) = w(pg.off_h1() + i);
+            w(pg.off_h1() + i) = uni;
+        }
+        __syncwarp();
+        h2 = h1; h1 = hh;
+        t = tn;
+        nhist++;
+        if (T < a.max_points) {
+            if (tl == 0) a.out_t[(int64_t)T * p.P + lane] = t;
+            for (int q = tl; q < a.n_save; q += 32)
+                a.out[((int64_t)q * a.max_points + T) * p.P + lane] = w(pg.off_u() + __ldg(a.save_idx + q));
+        }
+        T++;
+        double f = err > 0.0 ? 0.9 * pow(err, -1.0 / (pord + 1)) : 2.0;
+        if (f > 2.0) f = 2.0;
+        if (f < 0.2) f = 0.2;
+        h = hh * f;
+        if (h > a.dtmax) h = a.dtmax;
+        if (hit && tn < a.t1) nhist = 0;                      // restart after a breakpoint
+        if (!(t < a.t1)) finished = true;
+        else if (T >= a.max_points) { if (status == CB200_LANE_OK) status = CB200_LANE_MAXITER; finished = true; }
+    }
+    __syncwarp();
+    for (int i = tl; i < n; i += 32) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+    if (tl == 0) {
+        a.status[lane] = status;
+        a.iters[lane] += solves;
+        a.rejected[lane] = rej;
+        a.count[lane] = T < a.max_points ? T : a.max_points;
+    }
+}
+
+}  // namespace cb200

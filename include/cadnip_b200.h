@@ -249,6 +249,13 @@ int cb200_load_va_models(cb200_handle *h, const char *cuda_header, const char *c
 int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t method, double dt,
                      const char *csrc_dir, const char *cache_dir, int32_t flags);
 int cb200_is_specialized(const cb200_handle *h);
+/* Which mapping the table-driven kernels use for this circuit (the specialised kernels, when
+ * loaded, are always lane-per-thread / registers): 0 = one lane per thread, workspace in
+ * shared memory; 1 = one lane per thread, workspace column in HBM; 2 = one lane per WARP,
+ * workspace row in HBM / L2 (medium circuits: the lane state leaves < 64 lanes per block in
+ * shared memory).  No reference counterpart: the reference solves one point at a time
+ * (src/sweeps.jl:511-532).                                                          */
+int cb200_lane_mapping(const cb200_handle *h);
 /* Host-only emitter entry (no device): description + nominal |J| magnitudes for the DC
  * and transient schedules -> generated CUDA source (returns its length; negative =
  * error).  Lets the emitter be tested where no GPU is present.                      */

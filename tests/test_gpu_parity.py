@@ -394,3 +394,56 @@ def test_device_exp_is_within_one_ulp():
     assert ulp.max() <= 1.0, ulp.max()
     assert np.array_equal(np.isinf(y), np.isinf(ref))
     assert y[np.where(x == 0.0)[0][0]] == 1.0
+
+
+# ---- lane-per-warp kernels (warp_kernels.cuh) -------------------------------------
+def _run_all_analyses(lc, tspan, dt, dt0):
+    """DC, the three fixed-step methods (single launch and 3 segments) and the adaptive
+    integrator on one lowered sweep; everything a mapping must reproduce."""
+    out = {}
+    save = list(range(1, lc.n + 1))
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        out["dc"] = comp.dc()
+        for method in ("be", "trap", "gear2"):
+            wave = comp.tran(tspan, dt, method=method, save_idxs=save)
+            r = wave.fetch(); wave.free()
+            out["fixed_" + method] = (r["u"], r["status"], r["newton_iters"])
+            host = np.full_like(r["u"], np.nan)
+            r2 = comp.tran_fetch(tspan, dt, host, method=method, save_idxs=save, n_segments=3)
+            out["segments_" + method] = (r2["u"], r2["status"], r2["newton_iters"])
+        wave = comp.tran_adaptive(tspan, dt0=dt0, method="trap", save_idxs=save, reltol=1e-5,
+                                  lte_abstol=1e-8, max_points=20000)
+        r = wave.fetch(); wave.free()
+        T = int(r["count"].max())
+        valid = np.arange(T)[:, None] < r["count"][None, :]            # [T][P]: points the lane wrote
+        out["adaptive"] = (r["count"], r["status"], r["newton_iters"], np.where(valid, r["t"][:T], 0.0),
+                           np.where(valid[None], r["u"][:, :T], 0.0))
+    finally:
+        comp.close()
+    return out
+
+
+WARP_CASES = [("clipper", clipper_sweep(7, 5), (0.0, 3e-4), 1e-6, 2e-7),       # 35 lanes: ragged last block
+              ("mos_amp", SWEEPS[5][1], (0.0, 3e-8), 1e-10, 1e-11),
+              ("controlled", SWEEPS[4][1], (0.0, 2e-6), 1e-8, 1e-9),
+              ("chain", SWEEPS[2][1], (0.0, 1e-6), 1e-8, 1e-9)]
+
+
+@pytest.mark.parametrize("name,cs,tspan,dt,dt0", WARP_CASES, ids=[c[0] for c in WARP_CASES])
+def test_lane_per_warp_kernels_equal_lane_per_thread_bitwise(name, cs, tspan, dt, dt0, monkeypatch):
+    """The medium-circuit mapping (one lane per warp, workspace row in HBM/L2) performs the same
+    floating-point operations in the same order as the lane-per-thread kernels: results must be
+    IDENTICAL -- states, waveforms, time grids, statuses and Newton iteration counts."""
+    lc = lowered_sweep(cs, "tran")
+    monkeypatch.setenv("CB200_LANE_PER_THREAD", "1")
+    ref = _run_all_analyses(lc, tspan, dt, dt0)
+    monkeypatch.delenv("CB200_LANE_PER_THREAD")
+    monkeypatch.setenv("CB200_LANE_PER_WARP", "1")
+    got = _run_all_analyses(lc, tspan, dt, dt0)
+    for key in ref:
+        for a, b in zip(ref[key], got[key]):
+            assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), (name, key)
+    # and the segmented run equals the single launch under the warp mapping too
+    for method in ("be", "trap", "gear2"):
+        assert np.array_equal(got["fixed_" + method][0], got["segments_" + method][0])

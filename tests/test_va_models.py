@@ -394,6 +394,40 @@ def test_gpu_va_dff_adaptive():
 
 
 @pytest.mark.gpu
+def test_gpu_va_dff_lane_per_warp_equals_lane_per_thread(monkeypatch):
+    """The flip-flop (n = 145, 30 FETs) runs on the lane-per-warp kernels with the level-scheduled
+    refactor / solves; they must reproduce the serial lane-per-thread schedule bit for bit
+    (DC state, PCNR iteration counts, adaptive time grid, waveforms)."""
+    lc = fixture("mos1_dff")
+    save = [lc.index_of("Q"), lc.index_of("Q_neg"), lc.index_of("net0")]
+
+    def run():
+        comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+        try:
+            mapping = comp.handle.lane_mapping()
+            x, st, it = comp.dc()
+            wave = comp.tran_adaptive((0.0, 4e-8), dt0=1e-12, method="trap", save_idxs=save, reltol=1e-3,
+                                      lte_abstol=1e-5, max_points=4000, limit=True)
+            r = wave.fetch(); wave.free()
+            wave = comp.tran((0.0, 2e-9), 1e-11, method="trap", save_idxs=save, limit=True)
+            rf = wave.fetch(); wave.free()
+        finally:
+            comp.close()
+        T = int(r["count"].max())
+        valid = np.arange(T)[:, None] < r["count"][None, :]
+        return mapping, [x, st, it, r["count"], r["status"], r["newton_iters"], np.where(valid, r["t"][:T], 0.0),
+                         np.where(valid[None], r["u"][:, :T], 0.0), rf["u"], rf["newton_iters"], rf["status"]]
+
+    m_warp, got = run()
+    assert m_warp == "warp"
+    monkeypatch.setenv("CB200_LANE_PER_THREAD", "1")
+    m_thr, ref = run()
+    assert m_thr == "thread/hbm"
+    for a, b in zip(ref, got):
+        assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+@pytest.mark.gpu
 def test_gpu_va_ring_oscillator():
     lc = fixture("mos1_ring")
     nl = oracle_of(lc)
