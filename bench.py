@@ -151,7 +151,9 @@ def build_sweep(args):
     if args.workload == "c4":
         import gzip
         import pickle
-        with gzip.open(os.path.join(ROOT, "tests", "golden", "va_mos1_dff.pkl.gz"), "rb") as f:
+        # CB200_C4_FIXTURE: experiment hook (e.g. a fixture emitted with the set-up / evaluation split)
+        with gzip.open(os.environ.get("CB200_C4_FIXTURE") or
+                       os.path.join(ROOT, "tests", "golden", "va_mos1_dff.pkl.gz"), "rb") as f:
             lc = pickle.load(f)
         lc.lane_soa, lc.P = c4_lanes(lc, args.lanes)
         return cb, None, lc, lc.P

@@ -160,6 +160,8 @@ def lib():
     L.cb200_is_specialized.argtypes = [vp]
     L.cb200_lane_mapping.restype = C.c_int
     L.cb200_lane_mapping.argtypes = [vp]
+    L.cb200_host_lu_check.restype = C.c_int
+    L.cb200_host_lu_check.argtypes = [C.POINTER(Desc), dp, dp, dp, dp, lp, lp, ip]
     L.cb200_load_va_models.restype = C.c_int
     L.cb200_load_va_models.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
     L.cb200_emit_source.restype = C.c_int64
@@ -197,7 +199,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "cb200_abi_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_pattern",
     "cb200_get_maps", "cb200_set_lanes", "cb200_analyze", "cb200_get_pivot_order", "cb200_eval",
-    "cb200_specialize", "cb200_is_specialized", "cb200_lane_mapping", "cb200_emit_source", "cb200_load_va_models",
+    "cb200_specialize", "cb200_is_specialized", "cb200_lane_mapping", "cb200_host_lu_check", "cb200_emit_source", "cb200_load_va_models",
     "cb200_dc", "cb200_tran", "cb200_tran_fetch", "cb200_set_tstops", "cb200_wave_info", "cb200_wave_fetch", "cb200_wave_final_state",
     "cb200_wave_free", "cb200_get_stats", "cb200_debug_exp"]
 
@@ -273,6 +275,32 @@ def emit_source(lc: LoweredCircuit, absJ_dc: np.ndarray, absJ_tr: np.ndarray, P:
     buf = C.create_string_buffer(n + 1)
     L.cb200_emit_source(C.byref(desc), _dp(a0), _dp(a1), m, P, num_sms, buf, n + 1)
     return buf.value.decode()
+
+
+def host_lu_check(lc: LoweredCircuit, J_nz: Optional[np.ndarray] = None, rhs: Optional[np.ndarray] = None):
+    """cb200_host_lu_check (host only, no device).  Without J_nz: (colptr, rowval) of the pattern,
+    1-based.  With J_nz / rhs: (x_serial, x_level, info) -- the serial static-pivot schedule and the
+    level schedule of the lane-per-warp kernels executed on the host for that matrix."""
+    L = lib()
+    desc, keep = make_desc(lc)
+    info = np.zeros(6, dtype=np.int32)
+    rc = L.cb200_host_lu_check(C.byref(desc), None, None, None, None, None, None, _ip(info))
+    if rc != OK:
+        raise CB200Error(rc, (L.cb200_last_error(None) or b"").decode())
+    n, nnz = int(info[0]), int(info[1])
+    colptr, rowval = np.zeros(n + 1, dtype=np.int64), np.zeros(nnz, dtype=np.int64)
+    if J_nz is None:
+        L.cb200_host_lu_check(C.byref(desc), None, None, None, None, _lp(colptr), _lp(rowval), _ip(info))
+        return colptr, rowval
+    J = np.ascontiguousarray(J_nz, dtype=np.float64)
+    r = np.ascontiguousarray(rhs, dtype=np.float64)
+    assert J.shape == (nnz,) and r.shape == (n,)
+    xs, xl = np.zeros(n), np.zeros(n)
+    rc = L.cb200_host_lu_check(C.byref(desc), _dp(J), _dp(r), _dp(xs), _dp(xl), None, None, _ip(info))
+    if rc != OK:
+        raise CB200Error(rc, (L.cb200_last_error(None) or b"").decode())
+    return xs, xl, dict(n=n, nnz=nnz, nlu=int(info[2]), factor_levels=int(info[3]),
+                        forward_levels=int(info[4]), backward_levels=int(info[5]))
 
 
 class Wave:

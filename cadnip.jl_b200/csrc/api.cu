@@ -1226,6 +1226,36 @@ extern "C" int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t
 
 extern "C" int cb200_is_specialized(const cb200_handle *h) { return h && spec_usable(h) ? 1 : 0; }
 
+// Host-only test hook (no device): pattern + static-pivot schedule + level schedule of a
+// description, and both schedules executed on the host for one matrix.  info = {n, nnz, nlu,
+// factor levels, forward levels, backward levels}.
+extern "C" int cb200_host_lu_check(const cb200_desc *d, const double *J_nz, const double *rhs,
+                                   double *x_serial, double *x_level, int64_t *colptr, int64_t *rowval,
+                                   int32_t *info)
+{
+    if (!d || !info) { g_last_error = "cb200_host_lu_check: null argument"; return CB200_EINVAL; }
+    Structure st;
+    std::string e = build_structure(*d, st);
+    if (!e.empty()) { g_last_error = e; return CB200_EINVAL; }
+    info[0] = st.n; info[1] = (int32_t)st.nnz; info[2] = info[3] = info[4] = info[5] = 0;
+    if (colptr) for (int j = 0; j <= st.n; j++) colptr[j] = st.colptr[j] + 1;
+    if (rowval) for (int64_t q = 0; q < st.nnz; q++) rowval[q] = st.rowval[q] + 1;
+    if (!J_nz) return CB200_OK;
+    if (!rhs || !x_serial || !x_level) { g_last_error = "cb200_host_lu_check: null argument"; return CB200_EINVAL; }
+    std::vector<double> J(J_nz, J_nz + st.nnz), a(st.nnz), r(rhs, rhs + st.n), xs, xl;
+    for (int64_t q = 0; q < st.nnz; q++) a[q] = std::fabs(J[q]);
+    LuSchedule S;
+    e = analyze_lu(st, a, 1e-3, S);
+    if (!e.empty()) { g_last_error = e; return CB200_ESINGULAR; }
+    LevelSchedule V;
+    build_level_schedule(S, V);
+    info[2] = (int32_t)S.nlu; info[3] = V.n_lev; info[4] = V.n_fwd; info[5] = V.n_bwd;
+    host_lu_solve(S, V, J, r, xs, xl);
+    std::copy(xs.begin(), xs.end(), x_serial);
+    std::copy(xl.begin(), xl.end(), x_level);
+    return CB200_OK;
+}
+
 extern "C" int cb200_lane_mapping(const cb200_handle *h)
 {
     if (!h) return CB200_EINVAL;

@@ -71,5 +71,8 @@ struct LevelSchedule {
     std::vector<int> bent;                      // int2 {U slot, column}
 };
 void build_level_schedule(const LuSchedule &S, LevelSchedule &out);
+// test hook: run the serial and the level schedule on the host (J in pattern order)
+void host_lu_solve(const LuSchedule &S, const LevelSchedule &V, const std::vector<double> &J,
+                   const std::vector<double> &rhs, std::vector<double> &x_serial, std::vector<double> &x_level);
 
 }  // namespace cb200

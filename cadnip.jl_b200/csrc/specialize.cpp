@@ -349,12 +349,17 @@ std::string build_va_kernel_set(const std::string &va_header_text, const std::st
         if (body.empty()) return "va models: cannot read " + csrc_dir + f;
         hk = fnv1a(hk, body);
     }
+    // CB200_NVCC_FLAGS: extra compiler flags for the kernel set (tuning experiments, e.g.
+    // -DCB200_WARP_MIN_BLOCKS=8); part of the cache key
+    const char *extra_env = getenv("CB200_NVCC_FLAGS");
+    const std::string extra = extra_env ? extra_env : "";
+    hk = fnv1a(hk, extra);
     snprintf(hex, sizeof hex, "%016llx", (unsigned long long)hk);
     const std::string so = cache_dir + "/kern_" + hex + ".so", log = cache_dir + "/kern_" + hex + ".log";
     if (!exists(so)) {
         const std::string tmp = cache_dir + "/kern_" + hex + ".tmp" + std::to_string((long)getpid()) + ".so";
         std::string cmd = find_nvcc() + " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 "
-                          "-Xcompiler -fPIC -shared -DCB200_VA_HEADER='\"" + hdr + "\"' -I\"" + csrc_dir +
+                          "-Xcompiler -fPIC -shared " + extra + " -DCB200_VA_HEADER='\"" + hdr + "\"' -I\"" + csrc_dir +
                           "\" -o \"" + tmp + "\" \"" + csrc_dir + "/kernels.cu\" > \"" + log + "\" 2>&1";
         if (system(cmd.c_str()) != 0) {
             std::string l = slurp(log);

@@ -341,4 +341,81 @@ void build_level_schedule(const LuSchedule &S, LevelSchedule &out)
                 out.tg.size() / 4, out.upd.size() / 4, nf, nb);
 }
 
+// ---------------------------------------------------------------------------
+// Host execution of both schedules on one matrix (test hook, cb200_host_lu_check): the serial
+// loop nest is factor_and_solve of lane_kernels.cuh, the level loop nest w_factor_and_solve of
+// warp_kernels.cuh, statement for statement.  x solves J x = rhs (original coordinates).
+// ---------------------------------------------------------------------------
+void host_lu_solve(const LuSchedule &S, const LevelSchedule &V, const std::vector<double> &J,
+                   const std::vector<double> &rhs, std::vector<double> &x_serial, std::vector<double> &x_level)
+{
+    const int n = S.n;
+    {
+        std::vector<double> LU((size_t)S.nlu, 0.0), wv(n);
+        for (size_t q = 0; q < J.size(); q++) LU[S.jmap[q]] = J[q];
+        for (int k = 0; k < n; k++) {
+            const double inv = 1.0 / LU[S.diag_slot[k]];
+            LU[S.diag_slot[k]] = inv;
+            const int l0 = S.Lptr[k], l1 = S.Lptr[k + 1], u0 = S.Uptr[k], u1 = S.Uptr[k + 1], t0 = S.tgt_ptr[k];
+            for (int e = l0; e < l1; e++) {
+                const double l = LU[S.L_slot[e]] * inv;
+                LU[S.L_slot[e]] = l;
+                for (int q = u0; q < u1; q++) {
+                    const int ts = S.tgt[t0 + (e - l0) * (u1 - u0) + (q - u0)];
+                    LU[ts] = LU[ts] - l * LU[S.U_slot[q]];
+                }
+            }
+        }
+        for (int k = 0; k < n; k++) wv[k] = rhs[S.rowperm[k]];
+        for (int k = 0; k < n; k++) {
+            const double zk = wv[k];
+            for (int e = S.Lptr[k]; e < S.Lptr[k + 1]; e++) wv[S.L_row[e]] = wv[S.L_row[e]] - LU[S.L_slot[e]] * zk;
+        }
+        for (int k = n - 1; k >= 0; k--) {
+            double acc = wv[k];
+            for (int q = S.Uptr[k]; q < S.Uptr[k + 1]; q++) acc -= LU[S.U_slot[q]] * wv[S.U_col[q]];
+            acc *= LU[S.diag_slot[k]];
+            wv[k] = acc;
+        }
+        x_serial.assign(n, 0.0);
+        for (int k = 0; k < n; k++) x_serial[S.colperm[k]] = wv[k];
+    }
+    {
+        std::vector<double> LU((size_t)S.nlu, 0.0), DI(n), wv(n), F(rhs);
+        for (size_t q = 0; q < J.size(); q++) LU[S.jmap[q]] = J[q];
+        for (int v = 0; v <= V.n_lev; v++) {
+            if (v < V.n_lev)
+                for (int q = V.piv_ptr[v]; q < V.piv_ptr[v + 1]; q++) DI[V.piv[2 * q]] = 1.0 / LU[V.piv[2 * q + 1]];
+            if (v > 0)
+                for (int q = V.sc_ptr[v - 1]; q < V.sc_ptr[v]; q++) LU[V.sc[2 * q]] = LU[V.sc[2 * q]] * DI[V.sc[2 * q + 1]];
+            if (v < V.n_lev)
+                for (int q = V.tg_ptr[v]; q < V.tg_ptr[v + 1]; q++) {
+                    double a = LU[V.tg[4 * q]];
+                    for (int u = V.tg[4 * q + 1]; u < V.tg[4 * q + 2]; u++) {
+                        const double lv = LU[V.upd[4 * u]] * DI[V.upd[4 * u + 2]];
+                        a = a - lv * LU[V.upd[4 * u + 1]];
+                    }
+                    LU[V.tg[4 * q]] = a;
+                }
+        }
+        for (int v = 0; v < V.n_fwd; v++)
+            for (int q = V.flev_ptr[v]; q < V.flev_ptr[v + 1]; q++) {
+                double acc = F[V.frow[4 * q + 1]];
+                for (int e = V.frow[4 * q + 2]; e < V.frow[4 * q + 3]; e++) acc = acc - LU[V.fent[2 * e]] * wv[V.fent[2 * e + 1]];
+                wv[V.frow[4 * q]] = acc;
+            }
+        std::vector<double> y(n);
+        for (int v = 0; v < V.n_bwd; v++)
+            for (int q = V.blev_ptr[v]; q < V.blev_ptr[v + 1]; q++) {
+                const int k = V.brow[4 * q];
+                double acc = wv[k];
+                for (int e = V.brow[4 * q + 1]; e < V.brow[4 * q + 2]; e++) acc -= LU[V.bent[2 * e]] * y[V.bent[2 * e + 1]];
+                acc *= DI[k];
+                y[k] = acc;
+            }
+        x_level.assign(n, 0.0);
+        for (int k = 0; k < n; k++) x_level[S.colperm[k]] = y[k];
+    }
+}
+
 }  // namespace cb200

@@ -82,11 +82,26 @@ __device__ __forceinline__ void w_segsum(W &w, const Hot &hot, int off, int nseg
     if (s < nseg) { p = ptr(s); pend = ptr(s + 1); }
     for (int c0 = 0; c0 < total; c0 += hot.ch) {
         const int cend = min(c0 + hot.ch, total);
-        for (int j = c0 + tl; j < cend; j += 32) hot.buf[j - c0] = w(off + idx(j));
+        for (int j0 = c0 + tl; j0 < cend; j0 += 32 * 8) {     // 8 independent loads in flight per thread
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int j = j0 + 32 * u; v[u] = j < cend ? w(off + idx(j)) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int j = j0 + 32 * u; if (j < cend) hot.buf[j - c0] = v[u]; }
+        }
         __syncwarp();
         while (s < nseg) {
             const int hi = pend < cend ? pend : cend;
-            for (; p < hi; p++) acc += hot.buf[p - c0];
+            // loads first, dependent adds after: the chain then runs at DADD latency per element
+            const double *bp = hot.buf + (p - c0);
+            int cnt = hi - p;
+            for (; cnt >= 8; cnt -= 8, bp += 8) {
+                const double v0 = bp[0], v1 = bp[1], v2 = bp[2], v3 = bp[3];
+                const double v4 = bp[4], v5 = bp[5], v6 = bp[6], v7 = bp[7];
+                acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
+            }
+            for (; cnt > 0; cnt--, bp++) acc += *bp;
+            if (hi > p) p = hi;
             if (pend > cend) break;                         // the segment continues in the next chunk
             finish(s, acc);
             s += 32; acc = 0.0;
@@ -125,10 +140,12 @@ __device__ __forceinline__ double w_assemble(const PG &pg, const LU &lu, W &w, c
         hot.LU[lu.jmap(s)] = jv;
     }
     __syncwarp();
+    // Residual by rows: one thread per row, the row's entries in column order (a cooperative
+    // shared-memory staging of the operands, as for the segment sums, measured 6 % SLOWER on C4).
     for (int r = tl; r < pg.n(); r += 32) {
         double f = 0.0;
         const int q1 = pg.rowptr(r + 1);
-        for (int q = pg.rowptr(r); q < q1; q++) {           // the row's entries, columns ascending
+        for (int q = pg.rowptr(r); q < q1; q++) {
             const int s = pg.row_nz(q), j = pg.nz_col(s);
             const double uj = w(pg.off_u() + j);
             if (TRAN) {

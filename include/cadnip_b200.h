@@ -256,6 +256,14 @@ int cb200_is_specialized(const cb200_handle *h);
  * shared memory).  No reference counterpart: the reference solves one point at a time
  * (src/sweeps.jl:511-532).                                                          */
 int cb200_lane_mapping(const cb200_handle *h);
+/* Host-only test hook (no device): builds the pattern, the static-pivot schedule (pivoting on
+ * |J_nz|) and the level schedule of the lane-per-warp kernels for a description, and executes
+ * BOTH schedules on the host for the matrix J_nz (pattern order) and right-hand side rhs; the
+ * two solutions must be identical.  J_nz == NULL: only the pattern (1-based) and info[0..1] =
+ * {n, nnz} are returned.  info[2..5] = {nnz(LU), factor levels, forward levels, backward levels}. */
+int cb200_host_lu_check(const cb200_desc *desc, const double *J_nz, const double *rhs,
+                        double *x_serial, double *x_level, int64_t *colptr, int64_t *rowval,
+                        int32_t *info);
 /* Host-only emitter entry (no device): description + nominal |J| magnitudes for the DC
  * and transient schedules -> generated CUDA source (returns its length; negative =
  * error).  Lets the emitter be tested where no GPU is present.                      */

@@ -262,3 +262,49 @@ def test_emitter_generates_compilable_source(tmp_path):
     # the lane state must live in registers: no local-memory frame beyond libm's slow path
     frames = [int(x) for x in re.findall(r"(\d+) bytes stack frame", r.stderr)]
     assert max(frames) <= 64, frames
+
+
+def _random_matrix_on_pattern(colptr, rowval, rng):
+    """Random values on a CSC pattern (1-based), made safely non-singular: strong diagonal where the
+    pattern has one, O(1) couplings elsewhere (MNA source rows have a structurally zero diagonal)."""
+    n = len(colptr) - 1
+    A = np.zeros((n, n))
+    J = rng.uniform(-1.0, 1.0, len(rowval))
+    for j in range(n):
+        for q in range(colptr[j] - 1, colptr[j + 1] - 1):
+            i = rowval[q] - 1
+            if i == j:
+                J[q] = rng.uniform(4.0, 8.0) * n ** 0.5
+            A[i, j] = J[q]
+    return J, A
+
+
+def test_level_schedule_equals_serial_schedule_on_host():
+    """The level-scheduled refactor / solves of the lane-per-warp kernels (symbolic.cpp:
+    build_level_schedule) run on the host next to the serial static-pivot schedule: identical bits,
+    and both solve the system.  Covers the gf180 flip-flop (n = 145) and small circuits."""
+    import gzip
+    import pickle
+    import test_gpu_parity as tg
+    rng = np.random.default_rng(20261018)
+    cases = []
+    with gzip.open(os.path.join(os.path.dirname(__file__), "golden", "va_mos1_dff.pkl.gz"), "rb") as f:
+        cases.append(("dff", pickle.load(f)))
+    for name, cs in tg.SWEEPS:
+        params, P = cs.lane_params()
+        cases.append((name, cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P)))
+    for name, lc in cases:
+        colptr, rowval = backend.host_lu_check(lc)
+        assert colptr[0] == 1 and colptr[-1] == len(rowval) + 1
+        for trial in range(3):
+            J, A = _random_matrix_on_pattern(colptr, rowval, rng)
+            if abs(np.linalg.det(A / np.abs(A).max())) < 1e-200 or np.linalg.cond(A) > 1e10:
+                continue
+            rhs = rng.uniform(-1.0, 1.0, len(colptr) - 1)
+            xs, xl, info = backend.host_lu_check(lc, J, rhs)
+            assert np.array_equal(xs, xl), (name, trial)
+            ref = np.linalg.solve(A, rhs)
+            assert np.allclose(xs, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max()), (name, trial)
+            assert 1 <= info["factor_levels"] <= info["n"] and info["nlu"] >= info["nnz"]
+            if name == "dff":
+                assert info["n"] == 145 and info["factor_levels"] < 40      # 145 pivots, a few levels
