@@ -365,7 +365,8 @@ def test_gpu_va_c3_corner_lanes_with_transient_limiting():
 
 @pytest.mark.gpu
 def test_gpu_va_dff_adaptive():
-    """C4 on the table-driven kernels (lane state in HBM: n = 145, ~5000 workspace doubles per lane)."""
+    """C4 on the table-driven kernels (n = 145, ~5000 workspace doubles per lane: the lane-per-warp
+    mapping, workspace row in HBM / L2) against the oracle."""
     lc = fixture("mos1_dff")
     nl = oracle_of(lc)
     save = [lc.index_of("Q"), lc.index_of("Q_neg"), lc.index_of("net0")]
