@@ -540,6 +540,8 @@ static int upload_lu(cb200_handle *h, DevLu &L)
     q.Uptr = L.Uptr.p; q.U_slot = L.U_slot.p; q.U_col = L.U_col.p;
     q.tgt_ptr = L.tgt_ptr.p; q.tgt = L.tgt.p; q.jmap = L.jmap.p; q.fill_slots = L.fill_slots.p;
     q.n_lev = V.n_lev; q.n_fwd = V.n_fwd; q.n_bwd = V.n_bwd;
+    q.n_sc = (int)(V.sc.size() / 2); q.n_bent = (int)(V.bent.size() / 2);
+    q.n_tg = (int)(V.tg.size() / 4); q.n_upd = (int)(V.upd.size() / 4);
     q.piv_ptr = L.piv_ptr.p; q.sc_ptr = L.sc_ptr.p; q.tg_ptr = L.tg_ptr.p;
     q.piv = (const int2 *)L.piv.p; q.sc = (const int2 *)L.sc.p;
     q.tg = (const int4 *)L.tg.p; q.upd = (const int4 *)L.upd.p;

@@ -48,6 +48,7 @@ struct LuProgram {
     // level schedule of the same factorisation (lane-per-warp kernels; LevelSchedule in
     // cb200_internal.h): per level the pivots, the L entries to scale and the update targets
     int n_lev, n_fwd, n_bwd;
+    int n_sc, n_bent, n_tg, n_upd;      // record counts of sc / fent, bent, tg, upd
     const int *piv_ptr, *sc_ptr, *tg_ptr;
     const int2 *piv, *sc;
     const int4 *tg, *upd;

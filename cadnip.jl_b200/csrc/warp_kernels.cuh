@@ -34,10 +34,27 @@ namespace cb200 {
 
 // latency-critical arrays of a lane: shared memory when they fit (generic pointers: the same
 // code runs with them left in the lane's global row)
+// The read-only tables the warp kernels walk on every Newton iteration (segment lists, CSR view,
+// level schedule: 43 KB for the flip-flop).  Every data access of the assembly and of the
+// refactor is index -> data, so an index that misses the L1 (the lane rows and the model body's
+// spills compete for it) puts an L2 round trip on the dependent chain.  A block CAN stage the
+// tables in shared memory once (stage_tables, kernels.cu; CB200_WARP_STAGE_TABLES=1) -- measured
+// on C4 that loses (2.00 s vs 1.34 s): the shared memory it takes from the L1 costs more than the
+// guaranteed index hits save -- so by default WTab points at the global arrays.  The struct
+// itself lives in shared memory.
+struct WTab {
+    const int *gseg_ptr, *gseg_idx, *cseg_ptr, *cseg_idx, *bseg_ptr, *bseg_idx, *rowptr, *row_nz, *nz_col;
+    const int *jmap, *fill_slots, *colperm;
+    const int *piv_ptr, *sc_ptr, *tg_ptr, *flev_ptr, *blev_ptr;
+    const int2 *piv, *sc, *fent, *bent;
+    const int4 *tg, *upd, *frow, *brow;
+};
+
 struct Hot {
     double *F, *wv, *DI, *LU;
     double *buf;      // shared-memory gather buffer of the segmented assembly, ch doubles
     int ch;
+    const WTab *tb;   // in shared memory
 };
 
 __device__ __forceinline__ int wtid() { return threadIdx.x & 31; }
@@ -120,33 +137,44 @@ __device__ __forceinline__ double w_assemble(const PG &pg, const LU &lu, W &w, c
 {
     const int tl = wtid();
     const int oGS = pg.off_GS(), oCS = pg.off_CS();
-    for (int q = tl; q < lu.n_fill(); q += 32) hot.LU[lu.fill_slot(q)] = 0.0;
-    w_segsum(w, hot, pg.off_SG(), pg.nnz(), pg.p.nG,
-             [&](int s) { return pg.gseg_ptr(s); }, [&](int q) { return pg.gseg_idx(q); },
-             [&](int s, double v) {
-                 if (gshunt != 0.0 && pg.nz_is_node_diag(s)) v += gshunt;
-                 w(oGS + s) = v;
-             });
-    if (TRAN)
+    const WTab &tb = *hot.tb;
+    for (int q = tl; q < lu.n_fill(); q += 32) hot.LU[tb.fill_slots[q]] = 0.0;
+    {   // table pointers are copied out of the shared WTab once per phase (no reload per access)
+        const int *sp = tb.gseg_ptr, *si = tb.gseg_idx;
+        w_segsum(w, hot, pg.off_SG(), pg.nnz(), pg.p.nG,
+                 [&](int s) { return sp[s]; }, [&](int q) { return si[q]; },
+                 [&](int s, double v) {
+                     if (gshunt != 0.0 && pg.nz_is_node_diag(s)) v += gshunt;
+                     w(oGS + s) = v;
+                 });
+    }
+    if (TRAN) {
+        const int *sp = tb.cseg_ptr, *si = tb.cseg_idx;
         w_segsum(w, hot, pg.off_SC(), pg.nnz(), pg.p.nC,
-                 [&](int s) { return pg.cseg_ptr(s); }, [&](int q) { return pg.cseg_idx(q); },
+                 [&](int s) { return sp[s]; }, [&](int q) { return si[q]; },
                  [&](int s, double v) { w(oCS + s) = v; });
-    w_segsum(w, hot, pg.off_SB(), pg.n(), pg.p.nb,
-             [&](int r) { return pg.bseg_ptr(r); }, [&](int q) { return pg.bseg_idx(q); },
-             [&](int r, double v) { hot.wv[r] = v; });      // wv is free until the solve
+    }
+    {
+        const int *sp = tb.bseg_ptr, *si = tb.bseg_idx;
+        w_segsum(w, hot, pg.off_SB(), pg.n(), pg.p.nb,
+                 [&](int r) { return sp[r]; }, [&](int q) { return si[q]; },
+                 [&](int r, double v) { hot.wv[r] = v; });      // wv is free until the solve
+    }
+    const int *const jmap = tb.jmap;
     for (int s = tl; s < pg.nnz(); s += 32) {               // thread s % 32 reads back its own sums
         double jv = w(oGS + s);
         if (TRAN) jv += gamma * w(oCS + s);
-        hot.LU[lu.jmap(s)] = jv;
+        hot.LU[jmap[s]] = jv;
     }
     __syncwarp();
     // Residual by rows: one thread per row, the row's entries in column order (a cooperative
     // shared-memory staging of the operands, as for the segment sums, measured 6 % SLOWER on C4).
+    const int *const rowptr = tb.rowptr, *const row_nz = tb.row_nz, *const nz_col = tb.nz_col;
     for (int r = tl; r < pg.n(); r += 32) {
         double f = 0.0;
-        const int q1 = pg.rowptr(r + 1);
-        for (int q = pg.rowptr(r); q < q1; q++) {
-            const int s = pg.row_nz(q), j = pg.nz_col(s);
+        const int q1 = rowptr[r + 1];
+        for (int q = rowptr[r]; q < q1; q++) {
+            const int s = row_nz[q], j = nz_col[s];
             const double uj = w(pg.off_u() + j);
             if (TRAN) {
                 const double duj = gamma * (uj - w(pg.off_un() + j)) + w(pg.off_dterm() + j);
@@ -182,34 +210,35 @@ __device__ __forceinline__ bool w_factor_and_solve(const PG &pg, const LU &lu, W
 {
     const int tl = wtid();
     const LuProgram &l = lu.l;
+    const WTab &tb = *hot.tb;
     double *const sLU = hot.LU, *const sDI = hot.DI, *const sWV = hot.wv, *const sF = hot.F;
     bool sing = false;
     const int nlev = l.n_lev;
     for (int v = 0; v <= nlev; v++) {
         if (v < nlev) {
-            const int p1 = __ldg(l.piv_ptr + v + 1);
-            for (int q = __ldg(l.piv_ptr + v) + tl; q < p1; q += 32) {
-                const int2 pk = __ldg(l.piv + q);
+            const int p1 = tb.piv_ptr[v + 1];
+            for (int q = tb.piv_ptr[v] + tl; q < p1; q += 32) {
+                const int2 pk = tb.piv[q];
                 const double dgl = sLU[pk.y];
                 if (!(fabs(dgl) >= DBL_MIN) || !isfinite(dgl)) sing = true;
                 sDI[pk.x] = 1.0 / dgl;
             }
         }
         if (v > 0) {
-            const int s1 = __ldg(l.sc_ptr + v);
-            for (int q = __ldg(l.sc_ptr + v - 1) + tl; q < s1; q += 32) {
-                const int2 e = __ldg(l.sc + q);
+            const int s1 = tb.sc_ptr[v];
+            for (int q = tb.sc_ptr[v - 1] + tl; q < s1; q += 32) {
+                const int2 e = tb.sc[q];
                 sLU[e.x] = sLU[e.x] * sDI[e.y];
             }
         }
         __syncwarp();
         if (v < nlev) {
-            const int t1 = __ldg(l.tg_ptr + v + 1);
-            for (int q = __ldg(l.tg_ptr + v) + tl; q < t1; q += 32) {
-                const int4 t = __ldg(l.tg + q);
+            const int t1 = tb.tg_ptr[v + 1];
+            for (int q = tb.tg_ptr[v] + tl; q < t1; q += 32) {
+                const int4 t = tb.tg[q];
                 double a = sLU[t.x];
                 for (int u = t.y; u < t.z; u++) {
-                    const int4 up = __ldg(l.upd + u);
+                    const int4 up = tb.upd[u];
                     const double lv = sLU[up.x] * sDI[up.z];
                     a = a - lv * sLU[up.y];
                 }
@@ -220,12 +249,12 @@ __device__ __forceinline__ bool w_factor_and_solve(const PG &pg, const LU &lu, W
     }
     // forward: z[i] = F[rowperm[i]] - sum_k L[i][k] z[k]
     for (int v = 0; v < l.n_fwd; v++) {
-        const int r1 = __ldg(l.flev_ptr + v + 1);
-        for (int q = __ldg(l.flev_ptr + v) + tl; q < r1; q += 32) {
-            const int4 r = __ldg(l.frow + q);
+        const int r1 = tb.flev_ptr[v + 1];
+        for (int q = tb.flev_ptr[v] + tl; q < r1; q += 32) {
+            const int4 r = tb.frow[q];
             double acc = sF[r.y];
             for (int e = r.z; e < r.w; e++) {
-                const int2 en = __ldg(l.fent + e);
+                const int2 en = tb.fent[e];
                 acc = acc - sLU[en.x] * sWV[en.y];
             }
             sWV[r.x] = acc;
@@ -235,12 +264,12 @@ __device__ __forceinline__ bool w_factor_and_solve(const PG &pg, const LU &lu, W
     // backward: y[k] = (z[k] - sum_j U[k][j] y[j]) / pivot; y in the F slots
     bool finite = true;
     for (int v = 0; v < l.n_bwd; v++) {
-        const int r1 = __ldg(l.blev_ptr + v + 1);
-        for (int q = __ldg(l.blev_ptr + v) + tl; q < r1; q += 32) {
-            const int4 r = __ldg(l.brow + q);
+        const int r1 = tb.blev_ptr[v + 1];
+        for (int q = tb.blev_ptr[v] + tl; q < r1; q += 32) {
+            const int4 r = tb.brow[q];
             double acc = sWV[r.x];
             for (int e = r.y; e < r.z; e++) {
-                const int2 en = __ldg(l.bent + e);
+                const int2 en = tb.bent[e];
                 acc -= sLU[en.x] * sF[en.y];
             }
             acc *= sDI[r.x];
@@ -258,7 +287,7 @@ template <typename PG, typename LU, typename W>
 __device__ __forceinline__ void w_apply_update(const PG &pg, const LU &lu, W &w, const Hot &hot)
 {
     for (int k = wtid(); k < lu.n(); k += 32) {
-        const int j = pg.off_u() + lu.colperm(k);
+        const int j = pg.off_u() + hot.tb->colperm[k];
         w(j) = w(j) - hot.F[k];
     }
     __syncwarp();
