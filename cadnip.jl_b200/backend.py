@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 import shutil
 import subprocess
 from dataclasses import dataclass
@@ -82,7 +83,8 @@ class Stats(C.Structure):
                 ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("launches", C.c_int64), ("newton_iters", C.c_int64),
                 ("steps_accepted", C.c_int64), ("steps_rejected", C.c_int64),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("device_evals", C.c_int64),
+                ("dc_stepping_lanes", C.c_int64)]
 
 
 def nvcc_path() -> Optional[str]:
@@ -176,6 +178,15 @@ def lib():
     L.cb200_tran_fetch.restype = C.c_int
     L.cb200_tran_fetch.argtypes = [vp, C.POINTER(Spec), C.c_double, C.c_double, C.POINTER(TranOpts),
                                    lp, C.c_int32, dp, C.c_int32, dp, dp, ip, ip, ip]
+    L.cb200_tran_fetch_ld.restype = C.c_int
+    L.cb200_tran_fetch_ld.argtypes = [vp, C.POINTER(Spec), C.c_double, C.c_double, C.POINTER(TranOpts),
+                                      lp, C.c_int32, dp, C.c_int32, dp, dp, C.c_int64, ip, ip, ip]
+    L.cb200_wave_fetch_ld.restype = C.c_int
+    L.cb200_wave_fetch_ld.argtypes = [vp, dp, dp, C.c_int64, C.c_int64, ip, ip, ip]
+    L.cb200_measure_fp64_peak.restype = C.c_int
+    L.cb200_measure_fp64_peak.argtypes = [C.c_int32, dp, dp]
+    L.cb200_flop_model.restype = C.c_int
+    L.cb200_flop_model.argtypes = [vp, lp]
     L.cb200_set_tstops.restype = C.c_int
     L.cb200_set_tstops.argtypes = [vp, dp, C.c_int32]
     L.cb200_wave_info.restype = C.c_int
@@ -190,7 +201,7 @@ def lib():
     L.cb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.cb200_debug_exp.restype = C.c_int
     L.cb200_debug_exp.argtypes = [dp, dp, C.c_int32]
-    if L.cb200_abi_version() != 1:
+    if L.cb200_abi_version() != 2:
         raise CB200Error(EINVAL, "libcadnip_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -200,8 +211,9 @@ EXPORTED_SYMBOLS = [
     "cb200_abi_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_pattern",
     "cb200_get_maps", "cb200_set_lanes", "cb200_analyze", "cb200_get_pivot_order", "cb200_eval",
     "cb200_specialize", "cb200_is_specialized", "cb200_lane_mapping", "cb200_host_lu_check", "cb200_emit_source", "cb200_load_va_models",
-    "cb200_dc", "cb200_tran", "cb200_tran_fetch", "cb200_set_tstops", "cb200_wave_info", "cb200_wave_fetch", "cb200_wave_final_state",
-    "cb200_wave_free", "cb200_get_stats", "cb200_debug_exp"]
+    "cb200_dc", "cb200_tran", "cb200_tran_fetch", "cb200_tran_fetch_ld", "cb200_set_tstops", "cb200_wave_info",
+    "cb200_wave_fetch", "cb200_wave_fetch_ld", "cb200_wave_final_state",
+    "cb200_wave_free", "cb200_get_stats", "cb200_debug_exp", "cb200_measure_fp64_peak", "cb200_flop_model"]
 
 
 def prebuild_va_models(models) -> None:
@@ -225,6 +237,59 @@ def _lp(a):
 
 def _ip(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _check_f64(a: np.ndarray, shape, what: str) -> np.ndarray:
+    """A caller-supplied float64 buffer the C side reads or writes ``prod(shape)`` doubles of:
+    wrong dtype, shape or layout is an error here, never a heap overrun there."""
+    if not isinstance(a, np.ndarray) or a.dtype != np.float64:
+        raise ValueError(f"{what}: expected a float64 numpy array, got {getattr(a, 'dtype', type(a))}")
+    if tuple(a.shape) != tuple(shape):
+        raise ValueError(f"{what}: shape {tuple(a.shape)}, expected {tuple(shape)}")
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"{what}: must be C-contiguous")
+    return a
+
+
+def _lane_block(a: np.ndarray, lead_shape, P: int, what: str, writable: bool = True) -> int:
+    """``a`` is [*lead_shape][P] float64 whose last axis is contiguous and whose leading axes are
+    packed over rows of ``ld >= P`` doubles (a column block of a wider array).  Returns ld."""
+    if not isinstance(a, np.ndarray) or a.dtype != np.float64:
+        raise ValueError(f"{what}: expected a float64 numpy array, got {getattr(a, 'dtype', type(a))}")
+    if tuple(a.shape) != tuple(lead_shape) + (P,):
+        raise ValueError(f"{what}: shape {tuple(a.shape)}, expected {tuple(lead_shape) + (P,)}")
+    if writable and not a.flags["WRITEABLE"]:
+        raise ValueError(f"{what}: must be writable")
+    if a.size == 0:
+        return P
+    st = a.strides
+    if P > 1 and st[-1] != 8:
+        raise ValueError(f"{what}: the lane axis must be contiguous")
+    rows = int(np.prod(lead_shape)) if lead_shape else 1
+    if rows <= 1:
+        return P
+    ld = None
+    for ax in range(len(lead_shape) - 1, -1, -1):        # innermost leading axis with extent > 1 sets ld
+        if lead_shape[ax] > 1:
+            ld = st[ax] // 8
+            break
+    if ld is None or ld < P or ld * 8 != st[ax]:
+        raise ValueError(f"{what}: rows must be at least P doubles apart")
+    expect = ld * 8
+    for ax in range(len(lead_shape) - 1, -1, -1):        # every leading axis packed over rows of ld
+        if lead_shape[ax] > 1 and st[ax] != expect:
+            raise ValueError(f"{what}: leading axes must be packed (strides {st})")
+        expect *= lead_shape[ax]
+    return int(ld)
+
+
+def measure_fp64_peak(device: int = 0):
+    """(TFLOP/s, kernel ms) of the register-only FP64 FMA microbenchmark on ``device``."""
+    tf, ms = C.c_double(), C.c_double()
+    rc = lib().cb200_measure_fp64_peak(int(device), C.byref(tf), C.byref(ms))
+    if rc != OK:
+        raise CB200Error(rc, (lib().cb200_last_error(None) or b"").decode())
+    return tf.value, ms.value
 
 
 def make_spec(spec: MNASpec, mode: Optional[str] = None) -> Spec:
@@ -311,29 +376,45 @@ class Wave:
         T, P, ns, ad = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
         handle._check(lib().cb200_wave_info(ptr, C.byref(T), C.byref(P), C.byref(ns), C.byref(ad)))
         self.T, self.P, self.n_save, self.adaptive = T.value, P.value, ns.value, bool(ad.value)
+        handle._waves.add(self)
 
-    def fetch(self, out_u: Optional[np.ndarray] = None):
-        """D2H copy.  Returns dict(t, u[save][T][P], count, status, newton_iters)."""
+    def _live(self):
+        if not self._p:
+            raise CB200Error(ESTATE, "the wave was freed, or its handle was closed")
+        return self._p
+
+    def fetch(self, out_u: Optional[np.ndarray] = None, out_t: Optional[np.ndarray] = None):
+        """D2H copy.  Returns dict(t, u[save][T][P], count, status, newton_iters).  ``out_u``
+        ([save][T][P]) and, for adaptive waves, ``out_t`` ([T][P]) may be column blocks of wider
+        arrays (multi-GPU gather); dtype, shape and layout are checked."""
         L = lib()
+        p = self._live()
         if out_u is None:
             out_u = np.empty((self.n_save, self.T, self.P), dtype=np.float64)
-        t = np.empty((self.T, self.P) if self.adaptive else (self.T,), dtype=np.float64)
+        u_ld = _lane_block(out_u, (self.n_save, self.T), self.P, "Wave.fetch(out_u)")
+        if self.adaptive:
+            t = np.empty((self.T, self.P), dtype=np.float64) if out_t is None else out_t
+            t_ld = _lane_block(t, (self.T,), self.P, "Wave.fetch(out_t)")
+        else:
+            t, t_ld = np.empty((self.T,), dtype=np.float64), self.P
         count = np.empty(self.P, np.int32)
         status = np.empty(self.P, np.int32)
         iters = np.empty(self.P, np.int32)
-        self._h._check(L.cb200_wave_fetch(self._p, _dp(t), _dp(out_u), _ip(count), _ip(status),
-                                          _ip(iters)))
+        self._h._check(L.cb200_wave_fetch_ld(p, _dp(t), _dp(out_u) if out_u.size else None, u_ld, t_ld,
+                                             _ip(count), _ip(status), _ip(iters)))
         return dict(t=t, u=out_u, count=count, status=status, newton_iters=iters)
 
     def final_state(self) -> np.ndarray:
         x = np.empty((self._h.n, self.P), dtype=np.float64)
-        self._h._check(lib().cb200_wave_final_state(self._p, _dp(x)))
+        self._h._check(lib().cb200_wave_final_state(self._live(), _dp(x)))
         return x
 
     def free(self):
         if self._p:
             lib().cb200_wave_free(self._p)
             self._p = None
+        if self._h is not None:
+            self._h._waves.discard(self)
 
     def __del__(self):
         try:
@@ -356,6 +437,7 @@ class Handle:
             raise CB200Error(rc, (L.cb200_last_error(None) or b"").decode())
         self._p = ptr
         self.P = 0
+        self._waves = weakref.WeakSet()      # waves must not outlive the handle (their stream is its)
         if getattr(lc, "va_cuda_header", ""):
             self.load_va_models(lc.va_cuda_header)
 
@@ -369,6 +451,8 @@ class Handle:
 
     def close(self):
         if getattr(self, "_p", None):
+            for w in list(self._waves):      # outstanding waves become unusable, not dangling
+                w.free()
             lib().cb200_destroy(self._p)
             self._p = None
 
@@ -448,7 +532,7 @@ class Handle:
            maxiters: int = 100, use_stepping: bool = True, mode: Optional[str] = "dcop"):
         n, P = self.n, self.P
         x = np.empty((n, P)); st = np.empty(P, np.int32); it = np.empty(P, np.int32)
-        uu = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
+        uu = None if u0 is None else _check_f64(np.ascontiguousarray(u0, dtype=np.float64), (n, P), "dc(u0)")
         s = make_spec(spec, mode)
         o = DcOpts(abstol, maxiters, int(use_stepping))
         self._check(lib().cb200_dc(self._p, C.byref(s), C.byref(o), _dp(uu), _dp(x), _ip(st), _ip(it)))
@@ -457,7 +541,7 @@ class Handle:
     def tran(self, spec: MNASpec, t0: float, t1: float, opts: TranOpts, save_idx: Sequence[int],
              u0: Optional[np.ndarray] = None) -> Wave:
         save = np.ascontiguousarray(save_idx, dtype=np.int64)
-        uu = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
+        uu = None if u0 is None else _check_f64(np.ascontiguousarray(u0, dtype=np.float64), (self.n, self.P), "tran(u0)")
         s = make_spec(spec, "tran")
         ptr = C.c_void_p()
         self._check(lib().cb200_tran(self._p, C.byref(s), float(t0), float(t1), C.byref(opts),
@@ -469,16 +553,27 @@ class Handle:
         """Fixed-step tran! with the waveform delivered into ``out_u`` ([save][T][P], ideally
         pinned), the D2H copy of each time segment overlapping the next segment's compute."""
         save = np.ascontiguousarray(save_idx, dtype=np.int64)
-        uu = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
+        uu = None if u0 is None else _check_f64(np.ascontiguousarray(u0, dtype=np.float64), (self.n, self.P), "tran_fetch(u0)")
         s = make_spec(spec, "tran")
-        T = out_u.shape[1]
+        if opts.adaptive:
+            raise ValueError("tran_fetch is the fixed-step path; use tran(...).fetch(out_u) for adaptive runs")
+        T = fixed_step_points(t0, t1, opts.dt, opts.save_every)     # what the C side will write
+        u_ld = _lane_block(out_u, (len(save), T), self.P, "tran_fetch(out_u)")
         t = np.empty(T, dtype=np.float64)
         count = np.empty(self.P, np.int32); status = np.empty(self.P, np.int32)
         iters = np.empty(self.P, np.int32)
-        self._check(lib().cb200_tran_fetch(self._p, C.byref(s), float(t0), float(t1), C.byref(opts),
-                                           _lp(save), len(save), _dp(uu), int(n_segments), _dp(t),
-                                           _dp(out_u), _ip(count), _ip(status), _ip(iters)))
+        self._check(lib().cb200_tran_fetch_ld(self._p, C.byref(s), float(t0), float(t1), C.byref(opts),
+                                              _lp(save), len(save), _dp(uu), int(n_segments), _dp(t),
+                                              _dp(out_u) if out_u.size else None, u_ld, _ip(count), _ip(status),
+                                              _ip(iters)))
         return dict(t=t, u=out_u, count=count, status=status, newton_iters=iters)
+
+    def flop_model(self) -> dict:
+        """Static flop counts of one Newton iteration's linear algebra (cb200_flop_model)."""
+        o = np.zeros(8, np.int64)
+        self._check(lib().cb200_flop_model(self._p, _lp(o)))
+        return dict(assemble_dc=int(o[0]), assemble_tran=int(o[1]), factor_dc=int(o[2]), factor_tran=int(o[3]),
+                    solve_dc=int(o[4]), solve_tran=int(o[5]), update=int(o[6]), nonlinear_devices=int(o[7]))
 
     def set_tstops(self, tstops: Sequence[float]):
         t = np.ascontiguousarray(tstops, dtype=np.float64)
@@ -488,6 +583,13 @@ class Handle:
         s = Stats()
         self._check(lib().cb200_get_stats(self._p, C.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+def fixed_step_points(t0: float, t1: float, dt: float, save_every: int = 1) -> int:
+    """Saved points per lane of a fixed-step run: the same arithmetic as tran_impl (api.cu)."""
+    nsteps = int(np.floor((float(t1) - float(t0)) / float(dt) + 0.5))        # llround for positives
+    se = save_every if save_every > 0 else 1
+    return 1 + nsteps // se + (1 if nsteps % se else 0)
 
 
 def debug_exp(x: np.ndarray) -> np.ndarray:

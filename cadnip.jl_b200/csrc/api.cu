@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -36,7 +37,13 @@ struct BufPool {
     std::mutex mu;
     std::multimap<size_t, void *> free_;
     size_t cached_bytes = 0;
-    static constexpr size_t kMaxCached = (size_t)8 << 30;
+    // cap of the cache: 1 GiB unless CB200_POOL_MAX_MB says otherwise (a second handle on the same
+    // GPU must not be starved by buffers this one only keeps for reuse)
+    size_t kMaxCached = (size_t)1 << 30;
+    BufPool()
+    {
+        if (const char *e = getenv("CB200_POOL_MAX_MB")) kMaxCached = (size_t)std::max(0, atoi(e)) << 20;
+    }
     cudaError_t get(size_t bytes, void **out)
     {
         {
@@ -50,13 +57,14 @@ struct BufPool {
             }
         }
         cudaError_t e = cudaMalloc(out, bytes);
-        if (e != cudaSuccess) {              // out of memory: drop the cache and retry once
-            trim(0);
+        if (e != cudaSuccess) {              // out of memory: drop EVERY pool's cache and retry once
+            trim_all_pools();
             cudaGetLastError();
             e = cudaMalloc(out, bytes);
         }
         return e;
     }
+    static void trim_all_pools();
     void put(void *p, size_t bytes)
     {
         std::lock_guard<std::mutex> g(mu);
@@ -85,6 +93,26 @@ struct BufPool {
         for (auto &kv : free_) cudaFree(kv.second);
     }
 };
+
+// live pools of the process (weak: a pool dies with its handle and its last wave)
+static std::mutex g_pools_mu;
+static std::vector<std::weak_ptr<BufPool>> g_pools;
+
+void BufPool::trim_all_pools()
+{
+    std::vector<std::shared_ptr<BufPool>> live;
+    {
+        std::lock_guard<std::mutex> g(g_pools_mu);
+        for (auto it = g_pools.begin(); it != g_pools.end();) {
+            if (auto sp = it->lock()) { live.push_back(sp); ++it; }
+            else it = g_pools.erase(it);
+        }
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &p : live) { cudaSetDevice(p->device); p->trim(0); }
+    cudaSetDevice(cur);
+}
 
 template <typename T>
 struct DevBuf {
@@ -157,7 +185,7 @@ struct cb200_handle {
     DevBuf<int> d_status, d_iters;
     DevBuf<unsigned char> d_conv, d_active;
     DevBuf<double> d_gshunt_lane, d_srcfact_lane;
-    DevBuf<int> d_save, d_rejected;
+    DevBuf<int> d_save, d_rejected, d_evals;
     DevBuf<double> d_hist;         // [2n][P] integrator history between time segments
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t seg_ev[16] = {};
@@ -177,10 +205,11 @@ struct cb200_handle {
     size_t smem_limit = 0;
     int block_pref = 64;
     cb200_stats stats{};
+    std::vector<cb200_wave *> waves;   // live waves: orphaned (buffers released) by cb200_destroy
 };
 
 struct cb200_wave {
-    cb200_handle *h = nullptr;
+    cb200_handle *h = nullptr;     // null once the handle was destroyed: every accessor then fails with CB200_ESTATE
     int64_t T = 0, P = 0;
     int n_save = 0, adaptive = 0, n = 0;
     double t0 = 0, dt = 0;
@@ -294,6 +323,10 @@ extern "C" int cb200_create(const cb200_desc *d, int32_t device, cb200_handle **
     h->k.tran_fixed = cb200_k_tran_fixed; h->k.tran_adaptive = cb200_k_tran_adaptive;
     h->pool = std::make_shared<BufPool>();
     h->pool->device = device;
+    {
+        std::lock_guard<std::mutex> g(g_pools_mu);
+        g_pools.push_back(h->pool);
+    }
     ce = cudaSetDevice(device);
     if (ce != cudaSuccess) { delete h; return fail(nullptr, CB200_ECUDA, cudaGetErrorString(ce)); }
     cudaDeviceProp prop;
@@ -437,6 +470,12 @@ extern "C" void cb200_destroy(cb200_handle *h)
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto &e : h->seg_ev) if (e) cudaEventDestroy(e);
+    for (cb200_wave *w : h->waves) {     // waves the caller still holds: free their device memory now
+        w->d_out.release(); w->d_t.release(); w->d_final.release();
+        w->d_count.release(); w->d_status.release(); w->d_iters.release();
+        w->h = nullptr;
+    }
+    h->waves.clear();
     unload_spec(h->spec);
     if (h->k.dl) unload_kernel_set(h->k);
     delete h;
@@ -494,9 +533,18 @@ extern "C" int cb200_set_lanes(cb200_handle *h, int64_t P, int32_t n_cols, const
     if (n_cols != h->n_lane_cols) return fail(h, CB200_EINVAL, "cb200_set_lanes: column count differs from the description");
     if (n_cols > 0 && !soa) return fail(h, CB200_EINVAL, "cb200_set_lanes: null SoA");
     cudaSetDevice(h->device);
+    // New parameter values: the static pivot order was chosen from magnitudes probed on the OLD
+    // lanes, so both schedules are re-analysed on next use (re-sending identical values, e.g. a
+    // per-step H2D refresh, keeps them -- and the kernels specialised for them).
+    const size_t cnt = (size_t)n_cols * P;
+    if (P != h->P || h->lanes_host.size() != cnt ||
+        (cnt > 0 && memcmp(h->lanes_host.data(), soa, cnt * sizeof(double)) != 0)) {
+        h->lu[0].host.valid = false;
+        h->lu[1].host.valid = false;
+    }
     h->P = P;
     h->prog.P = P;
-    h->lanes_host.assign(soa, soa + (size_t)n_cols * P);
+    h->lanes_host.assign(soa, soa + cnt);
     if (n_cols > 0) {
         if (h->d_lanes.n != (size_t)n_cols * P) CUDA_TRY(h, h->d_lanes.alloc((size_t)n_cols * P));
         CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
@@ -791,108 +839,38 @@ static int dc_chain(cb200_handle *h, const cb200_spec *spec, double t, double ab
         if ((rc = fetch()) != CB200_OK) return rc;
     }
     if (use_stepping && !all_conv()) {
-        // tiers 2 and 3, per lane, host-driven: _gshunt_stepping (solve.jl:720-783)
-        // then _source_stepping (:805-850), each restarted from zeros.
-        std::vector<double> state((size_t)n * P), saved((size_t)n * P, 0.0);
-        CUDA_TRY(h, cudaMemcpyAsync(state.data(), h->d_state.p, state.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(h, cudaStreamSynchronize(s));
-        std::vector<unsigned char> todo(P), final_conv = conv;
+        // tiers 2 and 3 on the device: _gshunt_stepping (solve.jl:720-783), then _source_stepping
+        // (:805-850), each from zeros, one launch for all lanes that are still unconverged -- the
+        // per-lane continuation state never leaves the GPU (lane_kernels.cuh: dc_stepping_body).
+        // Always the table-driven kernels: a rare path is not worth a third specialised kernel.
+        std::vector<unsigned char> todo(P);
+        std::vector<int> status01 = status;
         for (int64_t l = 0; l < P; l++) todo[l] = conv[l] ? 0 : 1;
-        auto put_state = [&]() -> int {
-            CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, state.data(), state.size() * sizeof(double), cudaMemcpyHostToDevice, s));
-            return CB200_OK;
-        };
-        auto get_state = [&](std::vector<double> &dst) -> int {
-            CUDA_TRY(h, cudaMemcpyAsync(dst.data(), h->d_state.p, dst.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(h, cudaStreamSynchronize(s));
-            return CB200_OK;
-        };
-        auto copy_lane = [&](std::vector<double> &dst, const std::vector<double> &src, int64_t l) {
-            for (int i = 0; i < n; i++) dst[(size_t)i * P + l] = src[(size_t)i * P + l];
-        };
-        // ---- gshunt stepping
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_active.p, todo.data(), P, cudaMemcpyHostToDevice, s));
         {
-            const double target = spec->gshunt, gmin_thr = std::max(target, 1e-12);
-            std::vector<double> cur(P, 1e-3), factor(P, 10.0), gl(P, 0.0);
-            std::vector<unsigned char> act(P), fin(P, 0);
-            for (int64_t l = 0; l < P; l++) { act[l] = todo[l]; if (act[l]) for (int i = 0; i < n; i++) state[(size_t)i * P + l] = 0.0; }
-            saved = state;
-            std::vector<double> trial((size_t)n * P);
-            for (int step = 1; step <= 21; step++) {
-                bool any = false;
-                for (int64_t l = 0; l < P; l++) { any |= act[l] != 0; gl[l] = fin[l] ? target : cur[l]; }
-                if (!any) break;
-                if ((rc = put_state()) != CB200_OK) return rc;
-                CUDA_TRY(h, cudaMemcpyAsync(h->d_active.p, act.data(), P, cudaMemcpyHostToDevice, s));
-                CUDA_TRY(h, cudaMemcpyAsync(h->d_gshunt_lane.p, gl.data(), P * sizeof(double), cudaMemcpyHostToDevice, s));
-                rc = dc_launch(r, 1, h->d_active.p, h->d_gshunt_lane.p, nullptr);
-                if (rc != CB200_OK) return rc;
-                if ((rc = fetch()) != CB200_OK) return rc;
-                if ((rc = get_state(trial)) != CB200_OK) return rc;
-                for (int64_t l = 0; l < P; l++) {
-                    if (!act[l]) continue;
-                    if (fin[l]) {                       // final solve at the exact target
-                        if (conv[l]) { copy_lane(state, trial, l); final_conv[l] = 1; todo[l] = 0; }
-                        act[l] = 0;
-                        continue;
-                    }
-                    if (conv[l]) {
-                        copy_lane(state, trial, l); copy_lane(saved, trial, l);
-                        if (cur[l] <= gmin_thr) {
-                            if (cur[l] != target) fin[l] = 1;
-                            else { final_conv[l] = 1; todo[l] = 0; act[l] = 0; }
-                            continue;
-                        }
-                        cur[l] /= factor[l];
-                        if (cur[l] < gmin_thr) cur[l] = gmin_thr;
-                    } else {
-                        if (factor[l] <= 1.5) { act[l] = 0; continue; }
-                        factor[l] = std::sqrt(factor[l]);
-                        copy_lane(state, saved, l);
-                    }
-                    if (step >= 20 && !fin[l]) act[l] = 0;   // max_steps = 20
-                }
+            DcArgs a{};
+            a.algorithm = 2; a.abstol = r.abstol; a.maxiters = r.maxiters; a.t = r.t;
+            a.u = h->d_state.p; a.active = h->d_active.p;
+            a.status = h->d_status.p; a.iters = h->d_iters.p; a.converged = h->d_conv.p;
+            if (needs_global_ws(h)) {
+                if ((rc = ensure_global_ws(h)) != CB200_OK) return rc;
+                a.ws_global = h->d_ws_global.p;
             }
+            CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+            CUDA_TRY(h, h->k.dc(&h->prog, &h->lu[0].prog, &r.sa, &a, h->block_pref, h->smem_limit, s, &h->stats.launches));
+            CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+            CUDA_TRY(h, cudaStreamSynchronize(s));
+            float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+            r.kernel_ms += ms;
         }
-        // ---- source stepping
-        bool any_todo = std::any_of(todo.begin(), todo.end(), [](unsigned char c) { return c != 0; });
-        if (any_todo) {
-            std::vector<double> sf(P, 0.0), convsf(P, 0.0), raise(P, 0.1), sl(P, 1.0);
-            std::vector<unsigned char> act(P);
-            for (int64_t l = 0; l < P; l++) { act[l] = todo[l]; if (act[l]) for (int i = 0; i < n; i++) state[(size_t)i * P + l] = 0.0; }
-            saved = state;
-            std::vector<double> trial((size_t)n * P);
-            for (int step = 1; step <= 50; step++) {
-                bool any = false;
-                for (int64_t l = 0; l < P; l++) { any |= act[l] != 0; sl[l] = sf[l]; }
-                if (!any) break;
-                if ((rc = put_state()) != CB200_OK) return rc;
-                CUDA_TRY(h, cudaMemcpyAsync(h->d_active.p, act.data(), P, cudaMemcpyHostToDevice, s));
-                CUDA_TRY(h, cudaMemcpyAsync(h->d_srcfact_lane.p, sl.data(), P * sizeof(double), cudaMemcpyHostToDevice, s));
-                rc = dc_launch(r, 1, h->d_active.p, nullptr, h->d_srcfact_lane.p);
-                if (rc != CB200_OK) return rc;
-                if ((rc = fetch()) != CB200_OK) return rc;
-                if ((rc = get_state(trial)) != CB200_OK) return rc;
-                for (int64_t l = 0; l < P; l++) {
-                    if (!act[l]) continue;
-                    if (conv[l]) {
-                        convsf[l] = sf[l];
-                        copy_lane(state, trial, l); copy_lane(saved, trial, l);
-                        if (sf[l] >= 1.0) { final_conv[l] = 1; todo[l] = 0; act[l] = 0; continue; }
-                        sf[l] = std::min(sf[l] + raise[l], 1.0);
-                    } else {
-                        if (sf[l] - convsf[l] < 1e-6) { act[l] = 0; continue; }
-                        raise[l] /= 2.0;
-                        sf[l] = convsf[l] + raise[l];
-                        copy_lane(state, saved, l);
-                    }
-                }
-            }
+        if ((rc = fetch()) != CB200_OK) return rc;
+        h->stats.dc_stepping_lanes = 0;
+        for (int64_t l = 0; l < P; l++) {
+            if (!todo[l]) continue;
+            h->stats.dc_stepping_lanes++;
+            // a lane the continuation could not rescue keeps the status of its direct attempt
+            if (!conv[l] && status01[l] != CB200_LANE_OK) status[l] = status01[l];
         }
-        if ((rc = put_state()) != CB200_OK) return rc;
-        CUDA_TRY(h, cudaStreamSynchronize(s));
-        conv = final_conv;
-        for (int64_t l = 0; l < P; l++) status[l] = conv[l] ? CB200_LANE_OK : (status[l] == CB200_LANE_OK ? CB200_LANE_MAXITER : status[l]);
     }
     h->stats.kernel_ms += r.kernel_ms;
     h->stats.dc_kernel_ms += r.kernel_ms;
@@ -947,7 +925,7 @@ static const int kMaxSegments = 16;
 
 static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
                      const cb200_tran_opts *o, const int64_t *save_idx, int32_t n_save,
-                     const double *u0, double *host_u, int n_segments, cb200_wave **out)
+                     const double *u0, double *host_u, int64_t host_ld, int n_segments, cb200_wave **out)
 {
     if (!h || !spec || !o || !out) return fail(h, CB200_EINVAL, "cb200_tran: null argument");
     *out = nullptr;
@@ -998,6 +976,10 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
     }
     SpecArgs sa = spec_args(spec);
     sa.mode = CB200_MODE_TRAN;
+    if ((h->d_evals.n != (size_t)P && h->d_evals.alloc(P) != cudaSuccess) ||
+        cudaMemsetAsync(h->d_evals.p, 0, P * sizeof(int), s) != cudaSuccess) {
+        delete w; return fail(h, CB200_ECUDA, "cb200_tran: allocation failed");
+    }
     double *ws_global = nullptr;
     if (needs_global_ws(h)) {
         rc = ensure_global_ws(h);
@@ -1017,6 +999,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         a.method = o->method; a.t0 = t0; a.h = o->dt; a.nsteps = nsteps; a.abstol = o->abstol;
         a.max_nl = o->max_nl_iters; a.limit = o->flags & CB200_TRAN_LIMIT; a.save_every = se; a.n_save = n_save; a.save_idx = d_save.p;
         a.T = T; a.u = h->d_state.p; a.out = w->d_out.p; a.status = h->d_status.p; a.iters = h->d_iters.p;
+        a.evals = h->d_evals.p;
         a.ws_global = ws_global;
         // Time segments: one launch each.  With a host destination the D2H copy of a finished
         // segment runs on the copy stream while the next segment computes.
@@ -1047,9 +1030,13 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
                 cudaEventRecord(h->seg_ev[g], s);
                 cudaStreamWaitEvent(h->copy_stream, h->seg_ev[g], 0);
                 for (int q = 0; q < n_save; q++) {
+                    // host rows may be wider than the device rows (host_ld >= P): this handle's lanes
+                    // are then one column block of a waveform array that several GPUs fill
                     const size_t off = ((size_t)q * T + a.tp_begin) * P;
-                    ce = cudaMemcpyAsync(host_u + off, w->d_out.p + off, (size_t)(tp_end - a.tp_begin) * P * sizeof(double),
-                                         cudaMemcpyDeviceToHost, h->copy_stream);
+                    const size_t hoff = ((size_t)q * T + a.tp_begin) * (size_t)host_ld;
+                    ce = cudaMemcpy2DAsync(host_u + hoff, (size_t)host_ld * sizeof(double), w->d_out.p + off,
+                                           (size_t)P * sizeof(double), (size_t)P * sizeof(double),
+                                           (size_t)(tp_end - a.tp_begin), cudaMemcpyDeviceToHost, h->copy_stream);
                     if (ce != cudaSuccess) break;
                 }
                 h->stats.d2h_bytes += (int64_t)n_save * (tp_end - a.tp_begin) * P * sizeof(double);
@@ -1079,6 +1066,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         a.tstops = h->d_tstops.p; a.n_tstops = (int)h->tstops.size();
         a.u = h->d_state.p; a.out_t = w->d_t.p; a.out = w->d_out.p; a.count = w->d_count.p;
         a.status = h->d_status.p; a.iters = h->d_iters.p; a.rejected = h->d_rejected.p;
+        a.evals = h->d_evals.p;
         a.ws_global = ws_global;
         cudaEventRecord(h->ev0, s);
         if (spec_usable(h) && h->spec.tran_adaptive && h->spec_method == a.method && (!a.limit || h->spec_limit)) {
@@ -1115,6 +1103,15 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
     ce = cudaStreamSynchronize(s);
     if (ce != cudaSuccess) { delete w; return fail(h, CB200_ECUDA, cudaGetErrorString(ce)); }
     if (!o->adaptive) h->stats.steps_accepted = w->nsteps * P;
+    {   // device-model evaluation passes executed (sum over lanes): the work the FP64 roofline counts
+        std::vector<int> ev(P);
+        cudaMemcpyAsync(ev.data(), h->d_evals.p, P * sizeof(int), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        int64_t tot = 0;
+        for (int64_t l = 0; l < P; l++) tot += ev[l];
+        h->stats.device_evals = tot;
+    }
+    h->waves.push_back(w);
     *out = w;
     return CB200_OK;
 }
@@ -1123,27 +1120,41 @@ extern "C" int cb200_tran(cb200_handle *h, const cb200_spec *spec, double t0, do
                           const cb200_tran_opts *o, const int64_t *save_idx, int32_t n_save,
                           const double *u0, cb200_wave **out)
 {
-    return tran_impl(h, spec, t0, t1, o, save_idx, n_save, u0, nullptr, 1, out);
+    return tran_impl(h, spec, t0, t1, o, save_idx, n_save, u0, nullptr, 0, 1, out);
 }
 
 // tran! straight into host memory: the time loop is cut into n_segments launches and the
 // waveform of each finished segment is copied out (copy stream) while the next computes.
+static int wave_fetch_impl(cb200_wave *w, double *t, double *u, int64_t u_ld, int64_t t_ld, int32_t *count,
+                           int32_t *status, int32_t *newton_iters);
+
+extern "C" int cb200_tran_fetch_ld(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
+                                   const cb200_tran_opts *o, const int64_t *save_idx, int32_t n_save,
+                                   const double *u0, int32_t n_segments, double *t_out, double *u_out,
+                                   int64_t u_ld, int32_t *count, int32_t *status, int32_t *newton_iters)
+{
+    if (!o || !h) return fail(h, CB200_EINVAL, "cb200_tran_fetch: null argument");
+    if (u_ld == 0) u_ld = h->P;
+    if (u_ld < h->P) return fail(h, CB200_EINVAL, "cb200_tran_fetch: u_ld is smaller than the lane count");
+    cb200_wave *w = nullptr;
+    const bool pipelined = !o->adaptive && u_out != nullptr;
+    int rc = tran_impl(h, spec, t0, t1, o, save_idx, n_save, u0, pipelined ? u_out : nullptr, u_ld,
+                       n_segments, &w);
+    if (rc != CB200_OK) return rc;
+    const int64_t d2h = h->stats.d2h_bytes;
+    rc = wave_fetch_impl(w, t_out, pipelined ? nullptr : u_out, u_ld, u_ld, count, status, newton_iters);
+    h->stats.d2h_bytes += d2h;
+    cb200_wave_free(w);
+    return rc;
+}
+
 extern "C" int cb200_tran_fetch(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
                                 const cb200_tran_opts *o, const int64_t *save_idx, int32_t n_save,
                                 const double *u0, int32_t n_segments, double *t_out, double *u_out,
                                 int32_t *count, int32_t *status, int32_t *newton_iters)
 {
-    if (!o) return fail(h, CB200_EINVAL, "cb200_tran_fetch: null argument");
-    cb200_wave *w = nullptr;
-    const bool pipelined = !o->adaptive && u_out != nullptr;
-    int rc = tran_impl(h, spec, t0, t1, o, save_idx, n_save, u0, pipelined ? u_out : nullptr,
-                       n_segments, &w);
-    if (rc != CB200_OK) return rc;
-    const int64_t d2h = h->stats.d2h_bytes;
-    rc = cb200_wave_fetch(w, t_out, pipelined ? nullptr : u_out, count, status, newton_iters);
-    h->stats.d2h_bytes += d2h;
-    cb200_wave_free(w);
-    return rc;
+    return cb200_tran_fetch_ld(h, spec, t0, t1, o, save_idx, n_save, u0, n_segments, t_out, u_out, 0,
+                               count, status, newton_iters);
 }
 
 extern "C" int cb200_load_va_models(cb200_handle *h, const char *cuda_header, const char *csrc_dir,
@@ -1327,6 +1338,7 @@ extern "C" int cb200_wave_info(const cb200_wave *w, int64_t *T, int64_t *P, int3
                                int32_t *adaptive)
 {
     if (!w) return CB200_EINVAL;
+    if (!w->h) return fail(nullptr, CB200_ESTATE, "cb200_wave_info: the wave's handle was destroyed");
     if (T) *T = w->T;
     if (P) *P = w->P;
     if (n_save) *n_save = w->n_save;
@@ -1337,20 +1349,41 @@ extern "C" int cb200_wave_info(const cb200_wave *w, int64_t *T, int64_t *P, int3
 extern "C" int cb200_wave_fetch(cb200_wave *w, double *t, double *u, int32_t *count, int32_t *status,
                                 int32_t *newton_iters)
 {
+    return wave_fetch_impl(w, t, u, 0, 0, count, status, newton_iters);
+}
+
+extern "C" int cb200_wave_fetch_ld(cb200_wave *w, double *t, double *u, int64_t u_ld, int64_t t_ld,
+                                   int32_t *count, int32_t *status, int32_t *newton_iters)
+{
+    return wave_fetch_impl(w, t, u, u_ld, t_ld, count, status, newton_iters);
+}
+
+static int wave_fetch_impl(cb200_wave *w, double *t, double *u, int64_t u_ld, int64_t t_ld, int32_t *count,
+                           int32_t *status, int32_t *newton_iters)
+{
     if (!w) return CB200_EINVAL;
     cb200_handle *h = w->h;
+    if (!h) return fail(nullptr, CB200_ESTATE, "cb200_wave_fetch: the wave's handle was destroyed");
+    if (u_ld == 0) u_ld = w->P;
+    if (t_ld == 0) t_ld = w->P;
+    if (u_ld < w->P || t_ld < w->P) return fail(h, CB200_EINVAL, "cb200_wave_fetch: leading dimension smaller than the lane count");
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));
     int64_t bytes = 0;
     if (u && w->n_save > 0) {
-        CUDA_TRY(h, cudaMemcpyAsync(u, w->d_out.p, (size_t)w->n_save * w->T * w->P * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaMemcpy2DAsync(u, (size_t)u_ld * sizeof(double), w->d_out.p, (size_t)w->P * sizeof(double),
+                                      (size_t)w->P * sizeof(double), (size_t)w->n_save * w->T, cudaMemcpyDeviceToHost, s));
         bytes += (int64_t)w->n_save * w->T * w->P * sizeof(double);
     }
     if (status) { CUDA_TRY(h, cudaMemcpyAsync(status, w->d_status.p, w->P * sizeof(int), cudaMemcpyDeviceToHost, s)); bytes += w->P * 4; }
     if (newton_iters) { CUDA_TRY(h, cudaMemcpyAsync(newton_iters, w->d_iters.p, w->P * sizeof(int), cudaMemcpyDeviceToHost, s)); bytes += w->P * 4; }
     if (w->adaptive) {
-        if (t) CUDA_TRY(h, cudaMemcpyAsync(t, w->d_t.p, (size_t)w->T * w->P * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (t) {
+            CUDA_TRY(h, cudaMemcpy2DAsync(t, (size_t)t_ld * sizeof(double), w->d_t.p, (size_t)w->P * sizeof(double),
+                                          (size_t)w->P * sizeof(double), (size_t)w->T, cudaMemcpyDeviceToHost, s));
+            bytes += (int64_t)w->T * w->P * sizeof(double);
+        }
         if (count) CUDA_TRY(h, cudaMemcpyAsync(count, w->d_count.p, w->P * sizeof(int), cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
@@ -1379,6 +1412,7 @@ extern "C" int cb200_wave_final_state(cb200_wave *w, double *x_out)
 {
     if (!w || !x_out) return CB200_EINVAL;
     cb200_handle *h = w->h;
+    if (!h) return fail(nullptr, CB200_ESTATE, "cb200_wave_final_state: the wave's handle was destroyed");
     cudaSetDevice(h->device);
     CUDA_TRY(h, cudaMemcpyAsync(x_out, w->d_final.p, (size_t)w->n * w->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1388,7 +1422,11 @@ extern "C" int cb200_wave_final_state(cb200_wave *w, double *x_out)
 extern "C" void cb200_wave_free(cb200_wave *w)
 {
     if (!w) return;
-    cudaSetDevice(w->h->device);
+    if (w->h) {
+        cudaSetDevice(w->h->device);
+        auto &v = w->h->waves;
+        v.erase(std::remove(v.begin(), v.end(), w), v.end());
+    }
     delete w;
 }
 
@@ -1404,6 +1442,95 @@ extern "C" int cb200_debug_exp(const double *x, double *y, int32_t n)
     if (e == cudaSuccess) e = cudaMemcpy(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(dx); cudaFree(dy);
     return e == cudaSuccess ? CB200_OK : fail(nullptr, CB200_ECUDA, cudaGetErrorString(e));
+}
+
+// ---------------------------------------------------------------------------
+// FP64 roofline support: a measured FMA peak and the static flop model of the
+// per-iteration linear algebra ("measure once with an FMA microbenchmark").
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cb200_fp64_fma_kernel(double *out, int iters, double a, double b)
+{
+    // 8 independent dependent-FMA chains per thread, 64 resident warps per SM: the FP64 pipe is
+    // the only limiter (no memory traffic, no other pipe in the loop)
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0;
+    double x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" int cb200_measure_fp64_peak(int32_t device, double *tflops, double *ms_out)
+{
+    if (!tflops) return fail(nullptr, CB200_EINVAL, "cb200_measure_fp64_peak: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(nullptr, CB200_ENODEVICE, "cb200_measure_fp64_peak: no usable CUDA device");
+    cudaSetDevice(device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double *d = nullptr;
+    if (cudaMalloc((void **)&d, (size_t)blocks * threads * sizeof(double)) != cudaSuccess)
+        return fail(nullptr, CB200_ENOMEM, "cb200_measure_fp64_peak: allocation failed");
+    cudaStream_t s;
+    cudaEvent_t e0, e1;
+    cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {               // first launches warm the clocks up
+        cudaEventRecord(e0, s);
+        cb200_fp64_fma_kernel<<<blocks, threads, 0, s>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1, s);
+        cudaError_t ce = cudaStreamSynchronize(s);
+        if (ce != cudaSuccess) {
+            cudaFree(d);
+            return fail(nullptr, CB200_ECUDA, std::string("cb200_measure_fp64_peak: ") + cudaGetErrorString(ce));
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep >= 2 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s); cudaFree(d);
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = flops / ((double)best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return CB200_OK;
+}
+
+// Static flop counts of ONE Newton iteration's linear algebra for this circuit (adds, multiplies
+// and FMAs as 1 / 1 / 2; each reciprocal counted as ONE flop): out[0..1] assembly + residual
+// (DC, transient), out[2..3] numeric refactor, out[4..5] both triangular solves, out[6] update,
+// out[7] number of device rows evaluated per iteration (nonlinear devices).
+extern "C" int cb200_flop_model(const cb200_handle *h, int64_t *out)
+{
+    if (!h || !out) return CB200_EINVAL;
+    const Structure &st = h->st;
+    int64_t asm_dc = 0, asm_tr = 3LL * st.n;          // du_j = gamma (u_j - un_j) + dterm_j
+    for (int64_t s = 0; s < st.nnz; s++) {
+        const int64_t ng = st.gseg_ptr[s + 1] - st.gseg_ptr[s], nc = st.cseg_ptr[s + 1] - st.cseg_ptr[s];
+        asm_dc += ng + 2; asm_tr += ng + 2;           // segment sum, F += gsum * u_j
+        if (nc > 0) asm_tr += nc + 4;                 // segment sum, F += csum * du_j, J += gamma * csum
+    }
+    for (int r = 0; r < st.n; r++) {
+        const int64_t nb = st.bseg_ptr[r + 1] - st.bseg_ptr[r];
+        asm_dc += nb + 3; asm_tr += nb + 3;           // segment sum, F -= b, ||F||^2 += F^2
+    }
+    out[0] = asm_dc; out[1] = asm_tr;
+    for (int w = 0; w < 2; w++) {
+        const LuSchedule &S = h->lu[w].host;
+        int64_t fac = 0, sol = 0;
+        if (S.valid) {
+            fac = S.n + (int64_t)S.L_slot.size() + 2LL * (int64_t)S.tgt.size();
+            sol = 2LL * (int64_t)S.L_slot.size() + 2LL * (int64_t)S.U_slot.size() + S.n;
+        }
+        out[2 + w] = fac; out[4 + w] = sol;
+    }
+    out[6] = st.n;
+    out[7] = (int64_t)h->nl_list.size();
+    return CB200_OK;
 }
 
 extern "C" int cb200_get_stats(const cb200_handle *h, cb200_stats *out)

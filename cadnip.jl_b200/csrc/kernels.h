@@ -114,6 +114,7 @@ struct TranArgs {
     double *out;            // [n_save][T][P]
     int *status;            // [P]
     int *iters;             // [P]
+    int *evals;             // [P] or null: += device-model evaluation passes executed for the lane
     double *ws_global;
     int hot_smem;
 };
@@ -138,6 +139,7 @@ struct AdaptArgs {
     double *out;            // [n_save][max_points][P]
     int *count;             // [P]
     int *status, *iters, *rejected;
+    int *evals;             // [P] or null (see TranArgs)
     double *ws_global;
     int hot_smem;
 };

@@ -353,7 +353,15 @@ __device__ __forceinline__ double d_junction_cap(double V, double Cj0, double Vj
 // ---------------------------------------------------------------------------
 #ifdef CB200_VA_HEADER
 #include CB200_VA_HEADER
+#endif
+// A nonlinear device whose stamps depend on the time ($abstime in a Verilog-A module) as well as on
+// the iterate: the time loops then re-evaluate at the start of every step (see `fresh` below).
+#ifdef CB200_VA_TIME_DEP
+constexpr bool kNlTimeDep = true;
 #else
+constexpr bool kNlTimeDep = false;
+#endif
+#ifndef CB200_VA_HEADER
 template <int PASS, typename PG, typename W>
 __device__ __forceinline__ void va_dispatch(const PG &, W &, int, int, double, int, bool) {}
 #endif
@@ -545,6 +553,7 @@ __device__ __forceinline__ void eval_all(const PG &pg, W &w, double t, int mode,
 {
     if constexpr (PG::kStatic) {
         PG::eval_all(w, t, mode, initjct);
+        PG::accumulate(w);          // G(u), C(u) entry sums: what the static assemble() reads
     } else {
         for (int d = 0; d < pg.n_dev(); d++) eval_device<0>(pg, w, d, t, mode, initjct);
     }
@@ -556,6 +565,7 @@ __device__ __forceinline__ void eval_nonlinear(const PG &pg, W &w, double t, int
 {
     if constexpr (PG::kStatic) {
         PG::eval_nonlinear(w, t, mode, initjct);
+        PG::accumulate(w);
     } else {
         for (int q = 0; q < pg.n_nl(); q++) eval_device<1>(pg, w, pg.nl_list(q), t, mode, initjct);
     }
@@ -838,6 +848,118 @@ __device__ __forceinline__ void dc_body(const PG &pg, const LU &lu, W &w, const 
 }
 
 // ---------------------------------------------------------------------------
+// DC continuation on the device: _gshunt_stepping (solve.jl:720-783) then _source_stepping
+// (:805-850) for the lanes tiers 0-1 left unconverged (DcArgs.algorithm == 2).  The per-lane
+// controller below is the reference's loop turned inside out: the kernel runs ONE flat loop of
+// Newton iterations (_dc_newton_compiled: at most maxiters solves, then a final test) and the
+// controller is told the outcome of every inner solve; it answers with the next (gshunt,
+// srcFact) and whether the lane restarts from its saved state.  No state leaves the device
+// between continuation steps.
+// ---------------------------------------------------------------------------
+struct StepCtl {
+    int phase;                 // 0 gshunt ramp, 1 final solve at the exact target, 2 source ramp, 3 finished
+    double cur, factor, target, thr;
+    double sf, sf_conv, raise;
+    int steps;                 // inner solves of the current ramp (max 20 / 50)
+    bool conv;
+    __device__ __forceinline__ void begin(double target_gshunt)
+    {
+        phase = 0; cur = 1e-3; factor = 10.0; target = target_gshunt;
+        thr = target > 1e-12 ? target : 1e-12;
+        sf = 0.0; sf_conv = 0.0; raise = 0.1; steps = 0; conv = false;
+    }
+    __device__ __forceinline__ double gshunt() const { return phase == 0 ? cur : target; }
+    __device__ __forceinline__ double srcfact(double spec_srcfact) const { return phase == 2 ? sf : spec_srcfact; }
+    // outcome of one inner solve; returns what the lane state must become: 0 keep u (and save it),
+    // 1 restore the saved state, 2 restart from zeros (source stepping begins), 3 keep (finished)
+    __device__ __forceinline__ int result(bool ok)
+    {
+        if (phase == 0) {
+            steps++;
+            if (ok) {
+                if (cur <= thr) {
+                    if (cur != target) { phase = 1; return 0; }
+                    conv = true; phase = 3; return 3;
+                }
+                cur /= factor;
+                if (cur < thr) cur = thr;
+                if (steps >= 20) { start_source(); return 2; }
+                return 0;
+            }
+            if (factor <= 1.5 || steps >= 20) { start_source(); return 2; }
+            factor = sqrt(factor);
+            return 1;
+        }
+        if (phase == 1) {
+            if (ok) { conv = true; phase = 3; return 3; }
+            start_source();
+            return 2;
+        }
+        steps++;
+        if (ok) {
+            sf_conv = sf;
+            if (sf >= 1.0) { conv = true; phase = 3; return 3; }
+            sf = sf + raise < 1.0 ? sf + raise : 1.0;
+            if (steps >= 50) { phase = 3; return 3; }
+            return 0;
+        }
+        if (sf - sf_conv < 1e-6 || steps >= 50) { phase = 3; return 1; }
+        raise /= 2.0;
+        sf = sf_conv + raise;
+        return 1;
+    }
+    __device__ __forceinline__ void start_source() { phase = 2; sf = 0.0; sf_conv = 0.0; raise = 0.1; steps = 0; }
+};
+
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ void dc_stepping_body(const PG &pg, const LU &lu, W &w, const Program &p,
+                                                 const SpecArgs &sp, const DcArgs &a)
+{
+    const int64_t lane0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = lane0 < p.P;
+    const int64_t lane = in_range ? lane0 : p.P - 1;
+    const bool act = in_range && (a.active == nullptr || a.active[lane]);
+
+    load_lane_params(pg, w, p.lanes, p.P, lane);
+    for (int i = 0; i < pg.n(); i++) { w(pg.off_u() + i) = 0.0; w(pg.off_h1() + i) = 0.0; }   // both tiers start from zeros
+    eval_all(pg, w, a.t, sp.mode, false);
+    StepCtl ctl;
+    ctl.begin(sp.gshunt);
+    const double abstol2 = a.abstol * a.abstol;
+    int iter = 0, solves = 0;
+    bool fin = !act;
+    while (true) {
+        if (__all_sync(0xffffffffu, fin)) break;
+        eval_nonlinear(pg, w, a.t, sp.mode, false);
+        bool bad;
+        const double nrm2 = assemble<false>(pg, lu, w, 0.0, ctl.gshunt(), ctl.srcfact(sp.srcFact), bad);
+        if (fin) continue;
+        int res = -1;                                       // -1: the inner solve goes on
+        if (bad) res = 0;
+        else if (nrm2 < abstol2) res = 1;
+        else if (iter == a.maxiters) res = 0;
+        else {
+            bool singular;
+            if (!factor_and_solve(pg, lu, w, singular)) res = 0;
+            else { apply_update(pg, lu, w); solves++; iter++; }
+        }
+        if (res < 0) continue;
+        iter = 0;
+        const int act_on = ctl.result(res == 1);
+        if (act_on == 0) { for (int i = 0; i < pg.n(); i++) w(pg.off_h1() + i) = w(pg.off_u() + i); }
+        else if (act_on == 1) { for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_h1() + i); }
+        else if (act_on == 2) { for (int i = 0; i < pg.n(); i++) { w(pg.off_u() + i) = 0.0; w(pg.off_h1() + i) = 0.0; } }
+        if (ctl.phase == 3) fin = true;
+    }
+    if (act) {
+        for (int i = 0; i < pg.n(); i++) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+        a.status[lane] = ctl.conv ? CB200_LANE_OK : CB200_LANE_MAXITER;
+        a.iters[lane] += solves;
+        a.converged[lane] = ctl.conv ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // fixed-step transient body: the whole time loop of a lane on the device.
 //   du = gamma*(u - u_n) + dterm
 //   BE:    gamma = 1/h,      dterm = 0
@@ -868,6 +990,7 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
     eval_all(pg, w, a.t0, CB200_MODE_TRAN, false);
 
     int status = a.status[lane], solves = 0;       // keeps an InitialFailure from the DC init
+    int evals = 0;                                 // device-model evaluation passes this thread executed
     int64_t tp = a.tp_begin;
     if (!resume) {
         if (act)
@@ -879,6 +1002,12 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
     const double abstol2 = a.abstol * a.abstol;
     // a specialised kernel is generated for one integration method: branches on it fold
     const int amethod = PG::kMethod >= 0 ? PG::kMethod : a.method;
+    // `fresh`: the stamp slots of the nonlinear devices hold their values AT the current iterate.
+    // A step that converged ends with an evaluation at its final u, and the next step starts its
+    // Newton iteration from that same u: G(u), C(u) and the companion currents are functions of
+    // u alone, so the first residual of a step re-assembles them with the new source values and
+    // history terms instead of evaluating every device model again for identical values.
+    bool fresh = false;
     for (int64_t k = a.k_begin; k <= a.k_end; k++) {
         const double t = a.t0 + (double)k * h;
         const int method = (k == 1) ? CB200_METHOD_BE : amethod;
@@ -901,7 +1030,9 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
         bool lim_on = false;
         int it0 = 0;
         for (int it = 0;; it++) {
-            eval_nonlinear(pg, w, t, CB200_MODE_TRAN, false);
+            // lanes that are fresh recompute identical values when another lane of the warp is not
+            if (__any_sync(0xffffffffu, kNlTimeDep || !fresh)) { eval_nonlinear(pg, w, t, CB200_MODE_TRAN, false); evals++; }
+            fresh = true;
             bool bad;
             const double nrm2 = assemble<true>(pg, lu, w, gamma, sp.gshunt, sp.srcFact, bad);
             bool restart = false;
@@ -920,9 +1051,11 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
                 if (restart) {                             // redo the step from u_n, limiting on
                     CB_UNROLL
                     for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
+                    fresh = false;
                 } else if (!ok) { done = true; st = singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE; }
                 else {
                     apply_update(pg, lu, w);
+                    fresh = false;
                     solves++;
                     if (lim_on) {                          // PCNR corrector, solve.jl:686-689
                         const int lim0 = pg.n() - pg.n_limits();
@@ -933,6 +1066,7 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
             }
         }
         if (st != CB200_LANE_OK && status == CB200_LANE_OK) status = st;
+        if (st != CB200_LANE_OK) fresh = false;           // the last evaluation was not at the state kept
         if (st == CB200_LANE_NONFINITE || st == CB200_LANE_SINGULAR) {  // dead lane: hold last state
             CB_UNROLL
             for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
@@ -960,6 +1094,7 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
         }
         a.status[lane] = status;
         a.iters[lane] += solves;
+        if (a.evals != nullptr) a.evals[lane] += evals;
     }
 }
 
@@ -995,7 +1130,8 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
     }
     eval_all(pg, w, a.t0, CB200_MODE_TRAN, false);
 
-    int status = a.status[lane], solves = 0, rej = 0, T = 0;
+    int status = a.status[lane], solves = 0, rej = 0, T = 0, evals = 0;
+    bool fresh = false;                                    // see tran_fixed_body
     if (act) {
         a.out_t[(int64_t)T * p.P + lane] = a.t0;
         for (int q = 0; q < a.n_save; q++)
@@ -1010,7 +1146,7 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
     while (true) {
         if (__all_sync(0xffffffffu, finished)) break;
         // ---- choose the step
-        while (istop < a.n_tstops && __ldg(a.tstops + istop) <= t * (1 + 4e-16)) istop++;
+        while (istop < a.n_tstops && __ldg(a.tstops + istop) <= fma(4.440892098500626e-16, fabs(t), t)) istop++;   // 4 eps(t), either sign of t
         double tnext = istop < a.n_tstops ? __ldg(a.tstops + istop) : a.t1;
         if (tnext > a.t1) tnext = a.t1;
         double hh = h;
@@ -1035,7 +1171,8 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
         bool lim_on = false;
         int it0 = 0;
         for (int it = 0;; it++) {
-            eval_nonlinear(pg, w, tn, CB200_MODE_TRAN, false);
+            if (__any_sync(0xffffffffu, kNlTimeDep || !fresh)) { eval_nonlinear(pg, w, tn, CB200_MODE_TRAN, false); evals++; }
+            fresh = true;
             bool bad;
             const double nrm2 = assemble<true>(pg, lu, w, gamma, sp.gshunt, sp.srcFact, bad);
             bool restart = false;
@@ -1054,9 +1191,11 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
                 if (restart) {                             // redo the step from u_n, limiting on
                     CB_UNROLL
                     for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
+                    fresh = false;
                 } else if (!ok) { done = true; st = singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE; }
                 else {
                     apply_update(pg, lu, w);
+                    fresh = false;
                     solves++;
                     if (lim_on) {                          // PCNR corrector, solve.jl:686-689
                         const int lim0 = pg.n() - pg.n_limits();
@@ -1070,6 +1209,7 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
         if (st != CB200_LANE_OK) {                            // Newton failed: shrink and retry
             CB_UNROLL
             for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
+            fresh = false;
             rej++;
             h = hh / 4.0;
             if (h < a.dtmin) {
@@ -1114,6 +1254,7 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
         if (err > 1.0) {                                      // reject
             CB_UNROLL
             for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
+            fresh = false;
             rej++;
             double f = 0.9 * pow(err, -1.0 / (pord + 1));
             if (f < 0.2) f = 0.2;
@@ -1154,6 +1295,7 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
         a.iters[lane] += solves;
         a.rejected[lane] = rej;
         a.count[lane] = T < a.max_points ? T : a.max_points;
+        if (a.evals != nullptr) a.evals[lane] += evals;
     }
 }
 

@@ -54,6 +54,30 @@ static std::string hexdouble(double v)
 // ---- straight-line code: one statement per stamp / matrix entry / elimination update,
 // in exactly the order of the loops of lane_kernels.cuh (assemble, factor_and_solve,
 // apply_update), so both variants perform the same floating-point operations.
+// Per-entry sums of the stamp segments, G and C separately: G(u) and C(u) as CSC values.  They
+// depend on the iterate only (sources and linear devices stamp constants into G / C), so the time
+// loop keeps them from the converged check of one step to the first residual of the next
+// (tran_fixed_body: `fresh`).  Emitted into SProg; called after every device evaluation.
+static void emit_accumulate(std::ostringstream &o, const Structure &st, const Program &p)
+{
+    o << "    template <typename W>\n    __device__ static __forceinline__ void accumulate(W &w)\n    {\n";
+    for (int s = 0; s < (int)st.nnz; s++) {
+        if (st.gseg_ptr[s] < st.gseg_ptr[s + 1]) {
+            o << "        {\n            double gsum = 0.0;\n";
+            for (int q = st.gseg_ptr[s]; q < st.gseg_ptr[s + 1]; q++)
+                o << "            gsum += w(" << p.off_SG + st.gseg_idx[q] << ");\n";
+            o << "            w(" << p.off_GS + s << ") = gsum;\n        }\n";
+        }
+        if (st.cseg_ptr[s] < st.cseg_ptr[s + 1]) {
+            o << "        {\n            double csum = 0.0;\n";
+            for (int q = st.cseg_ptr[s]; q < st.cseg_ptr[s + 1]; q++)
+                o << "            csum += w(" << p.off_SC + st.cseg_idx[q] << ");\n";
+            o << "            w(" << p.off_CS + s << ") = csum;\n        }\n";
+        }
+    }
+    o << "    }\n";
+}
+
 static void emit_assemble(std::ostringstream &o, const Structure &st, const Program &p,
                           const LuSchedule &S)
 {
@@ -74,15 +98,12 @@ static void emit_assemble(std::ostringstream &o, const Structure &st, const Prog
             const bool has_g = st.gseg_ptr[s] < st.gseg_ptr[s + 1];
             const bool has_c = st.cseg_ptr[s] < st.cseg_ptr[s + 1];
             o << "            {   // (" << r << "," << j << ")\n";
-            o << "                double gsum = 0.0;\n";
-            for (int q = st.gseg_ptr[s]; q < st.gseg_ptr[s + 1]; q++)
-                o << "                gsum += w(" << p.off_SG + st.gseg_idx[q] << ");\n";
+            if (has_g) o << "                double gsum = w(" << p.off_GS + s << ");\n";
+            else o << "                double gsum = 0.0;\n";
             if (st.nz_is_node_diag[s]) o << "                if (gshunt != 0.0) gsum += gshunt;\n";
             o << "                double jv = gsum;\n";
             if (has_c) {
-                o << "                if (TRAN) {\n                    double csum = 0.0;\n";
-                for (int q = st.cseg_ptr[s]; q < st.cseg_ptr[s + 1]; q++)
-                    o << "                    csum += w(" << p.off_SC + st.cseg_idx[q] << ");\n";
+                o << "                if (TRAN) {\n                    const double csum = w(" << p.off_CS + s << ");\n";
                 o << "                    F" << r << " += csum * duj;\n                    jv += gamma * csum;\n                }\n";
             }
             if (has_g || st.nz_is_node_diag[s]) o << "                F" << r << " += gsum * uj;\n";
@@ -246,6 +267,9 @@ std::string generate_spec_source(const SpecInput &in)
     emit_const(o, "off_DS", p.off_DS);
     emit_const(o, "off_h1", p.off_h1);
     emit_const(o, "off_h2", p.off_h2);
+    emit_const(o, "off_GS", p.off_GS);
+    emit_const(o, "off_CS", p.off_CS);
+    emit_accumulate(o, st, p);
     // straight-line device evaluation lists (eval_all / eval_nonlinear / eval_sources)
     o << "    template <typename W>\n    __device__ static __forceinline__ void eval_all(W &w, double t, int mode, bool initjct)\n    {\n        SProg pg;\n";
     for (size_t d = 0; d < in.dev_kind->size(); d++)
@@ -265,7 +289,7 @@ std::string generate_spec_source(const SpecInput &in)
     o << "};\n";
     emit_lu(o, "SLuDc", st, p, *in.lu_dc);
     emit_lu(o, "SLuTr", st, p, *in.lu_tr);
-    o << "constexpr int kSlots = " << p.n_slots << ";\n";
+    o << "constexpr int kSlots = " << p.n_slots_w << ";\n";
     o << "constexpr int kBlock = " << in.block << ";\nconstexpr int kMinBlocks = " << in.min_blocks << ";\n";
     o << "__global__ void __launch_bounds__(kBlock, kMinBlocks) cb200_spec_dc_kernel(Program p, SpecArgs sp, DcArgs a)\n"
          "{\n    SProg pg; SLuDc lu; RegWs<kSlots> w;\n    dc_body(pg, lu, w, p, sp, a);\n}\n";
@@ -322,9 +346,17 @@ static std::string find_nvcc()
     return "nvcc";
 }
 
+// Generated modules stay mapped until the process exits: a handle that is done with one merely
+// forgets it.  (dlopen of a path that is already loaded returns the same mapping, so reloading is
+// free; and a driver that lists the shared objects of the process after the run sees every kernel
+// module that executed, not only libcadnip_b200.so.)
+static void *open_module(const std::string &path)
+{
+    return dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL | RTLD_NODELETE);
+}
+
 void unload_kernel_set(KernelSet &k)
 {
-    if (k.dl) dlclose(k.dl);
     k = KernelSet();
 }
 
@@ -368,14 +400,13 @@ std::string build_va_kernel_set(const std::string &va_header_text, const std::st
         }
         if (rename(tmp.c_str(), so.c_str()) != 0) return "va models: cannot move " + tmp;
     }
-    void *dl = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+    void *dl = open_module(so);
     if (!dl) return std::string("va models: dlopen failed: ") + dlerror();
     out.eval = (k_eval_fn)dlsym(dl, "cb200_k_eval");
     out.dc = (k_dc_fn)dlsym(dl, "cb200_k_dc");
     out.tran_fixed = (k_tran_fn)dlsym(dl, "cb200_k_tran_fixed");
     out.tran_adaptive = (k_adapt_fn)dlsym(dl, "cb200_k_tran_adaptive");
     if (!out.eval || !out.dc || !out.tran_fixed || !out.tran_adaptive) {
-        dlclose(dl);
         out = KernelSet();
         return "va models: " + so + " does not export the kernel entry points";
     }
@@ -386,7 +417,6 @@ std::string build_va_kernel_set(const std::string &va_header_text, const std::st
 
 void unload_spec(SpecModule &m)
 {
-    if (m.dl) dlclose(m.dl);
     m = SpecModule();
 }
 
@@ -425,7 +455,7 @@ std::string build_and_load_spec(const std::string &src, const std::string &csrc_
     }
     out.path = so;
     if (compile_only) return "";
-    void *dl = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+    void *dl = open_module(so);
     if (!dl) return std::string("specialize: dlopen failed: ") + dlerror();
     typedef int (*int_fn)(void);
     int_fn abi = (int_fn)dlsym(dl, "cb200_spec_abi");
@@ -434,7 +464,6 @@ std::string build_and_load_spec(const std::string &src, const std::string &csrc_
     out.tran_fixed = (spec_tran_fn)dlsym(dl, "cb200_spec_tran_fixed");
     out.tran_adaptive = (spec_adapt_fn)dlsym(dl, "cb200_spec_tran_adaptive");
     if (!abi || !blk || !out.dc || !out.tran_fixed || abi() != kSpecAbi) {       // tran_adaptive is optional
-        dlclose(dl);
         out = SpecModule();
         return "specialize: " + so + " does not export the expected entry points";
     }

@@ -10,7 +10,7 @@
 
 namespace cb200 {
 
-constexpr int kSpecAbi = 5;
+constexpr int kSpecAbi = 6;
 
 struct SpecInput {
     const Structure *st;

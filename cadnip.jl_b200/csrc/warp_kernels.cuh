@@ -133,13 +133,16 @@ __device__ __forceinline__ void w_segsum(W &w, const Hot &hot, int off, int nseg
 // residual row-parallel.
 template <bool TRAN, typename PG, typename LU, typename W>
 __device__ __forceinline__ double w_assemble(const PG &pg, const LU &lu, W &w, const Hot &hot,
-                                             double gamma, double gshunt, double srcFact, bool &bad)
+                                             double gamma, double gshunt, double srcFact, bool &bad,
+                                             bool have_gc = false)
 {
     const int tl = wtid();
     const int oGS = pg.off_GS(), oCS = pg.off_CS();
     const WTab &tb = *hot.tb;
     for (int q = tl; q < lu.n_fill(); q += 32) hot.LU[tb.fill_slots[q]] = 0.0;
-    {   // table pointers are copied out of the shared WTab once per phase (no reload per access)
+    // have_gc: the per-entry sums in the lane row are those of the current iterate already (the
+    // first residual of a time step, see `fresh` in lane_kernels.cuh: tran_fixed_body)
+    if (!have_gc) {   // table pointers are copied out of the shared WTab once per phase (no reload per access)
         const int *sp = tb.gseg_ptr, *si = tb.gseg_idx;
         w_segsum(w, hot, pg.off_SG(), pg.nnz(), pg.p.nG,
                  [&](int s) { return sp[s]; }, [&](int q) { return si[q]; },
@@ -148,7 +151,7 @@ __device__ __forceinline__ double w_assemble(const PG &pg, const LU &lu, W &w, c
                      w(oGS + s) = v;
                  });
     }
-    if (TRAN) {
+    if (TRAN && !have_gc) {
         const int *sp = tb.cseg_ptr, *si = tb.cseg_idx;
         w_segsum(w, hot, pg.off_SC(), pg.nnz(), pg.p.nC,
                  [&](int s) { return sp[s]; }, [&](int q) { return si[q]; },
@@ -376,20 +379,72 @@ __device__ __forceinline__ void w_dc_body(const PG &pg, const LU &lu, W &w, cons
     }
 }
 
+// dc_stepping_body of lane_kernels.cuh (gshunt stepping, then source stepping, on the device), one
+// lane per warp: the controller is warp-uniform.
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ void w_dc_stepping_body(const PG &pg, const LU &lu, W &w, const Program &p,
+                                                   const SpecArgs &sp, const DcArgs &a, int64_t lane,
+                                                   const Hot &hot)
+{
+    const int tl = wtid();
+    if (a.active != nullptr && !a.active[lane]) return;
+    const int n = pg.n();
+    w_load_lane_params(pg, w, p.lanes, p.P, lane);
+    for (int i = tl; i < n; i += 32) { w(pg.off_u() + i) = 0.0; w(pg.off_h1() + i) = 0.0; }
+    __syncwarp();
+    w_eval_all(pg, w, a.t, sp.mode, false);
+    StepCtl ctl;
+    ctl.begin(sp.gshunt);
+    const double abstol2 = a.abstol * a.abstol;
+    int iter = 0, solves = 0;
+    while (ctl.phase != 3) {
+        w_eval_nonlinear(pg, w, a.t, sp.mode, false);
+        bool bad;
+        const double nrm2 = w_assemble<false>(pg, lu, w, hot, 0.0, ctl.gshunt(), ctl.srcfact(sp.srcFact), bad);
+        int res = -1;
+        if (bad) res = 0;
+        else if (nrm2 < abstol2) res = 1;
+        else if (iter == a.maxiters) res = 0;
+        else {
+            bool singular;
+            if (!w_factor_and_solve(pg, lu, w, hot, singular)) res = 0;
+            else { w_apply_update(pg, lu, w, hot); solves++; iter++; }
+        }
+        if (res < 0) continue;
+        iter = 0;
+        const int act_on = ctl.result(res == 1);
+        if (act_on == 0) w_copy(pg, w, pg.off_h1(), pg.off_u(), n);
+        else if (act_on == 1) w_copy(pg, w, pg.off_u(), pg.off_h1(), n);
+        else if (act_on == 2) {
+            for (int i = tl; i < n; i += 32) { w(pg.off_u() + i) = 0.0; w(pg.off_h1() + i) = 0.0; }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    for (int i = tl; i < n; i += 32) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+    if (tl == 0) {
+        a.status[lane] = ctl.conv ? CB200_LANE_OK : CB200_LANE_MAXITER;
+        a.iters[lane] += solves;
+        a.converged[lane] = ctl.conv ? 1 : 0;
+    }
+}
+
 // One implicit step's Newton loop (shared by the fixed-step and adaptive bodies); returns the
 // lane status of the step and counts the linear solves.
 template <typename PG, typename LU, typename W>
 __device__ __forceinline__ int w_newton_step(const PG &pg, const LU &lu, W &w, const Hot &hot,
                                              const SpecArgs &sp,
                                              double t, double gamma, double abstol2, int max_nl,
-                                             int limit, int &solves)
+                                             int limit, int &solves, bool &fresh, int &evals)
 {
     bool lim_on = false;
     int it0 = 0;
     for (int it = 0;; it++) {
-        w_eval_nonlinear(pg, w, t, CB200_MODE_TRAN, false);
+        const bool have = fresh && !kNlTimeDep;            // stamps and entry sums are those of this u
+        if (!have) { w_eval_nonlinear(pg, w, t, CB200_MODE_TRAN, false); evals++; }
+        fresh = true;
         bool bad;
-        const double nrm2 = w_assemble<true>(pg, lu, w, hot, gamma, sp.gshunt, sp.srcFact, bad);
+        const double nrm2 = w_assemble<true>(pg, lu, w, hot, gamma, sp.gshunt, sp.srcFact, bad, have);
         bool restart = false;
         if (bad) return CB200_LANE_NONFINITE;
         if (nrm2 < abstol2) return CB200_LANE_OK;
@@ -399,12 +454,14 @@ __device__ __forceinline__ int w_newton_step(const PG &pg, const LU &lu, W &w, c
         }
         if (restart) {                                     // redo the step from u_n, limiting on
             w_copy(pg, w, pg.off_u(), pg.off_un(), pg.n());
+            fresh = false;
             continue;
         }
         bool singular;
         const bool ok = w_factor_and_solve(pg, lu, w, hot, singular);
         if (!ok) return singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE;
         w_apply_update(pg, lu, w, hot);
+        fresh = false;
         solves++;
         if (lim_on) {                                      // PCNR corrector, solve.jl:686-689
             const int lim0 = pg.n() - pg.n_limits();
@@ -433,7 +490,8 @@ __device__ __forceinline__ void w_tran_fixed_body(const PG &pg, const LU &lu, W 
     __syncwarp();
     w_eval_all(pg, w, a.t0, CB200_MODE_TRAN, false);
 
-    int status = a.status[lane], solves = 0;
+    int status = a.status[lane], solves = 0, evals = 0;
+    bool fresh = false;
     int64_t tp = a.tp_begin;
     if (!resume) {
         for (int q = tl; q < a.n_save; q += 32)
@@ -456,8 +514,9 @@ __device__ __forceinline__ void w_tran_fixed_body(const PG &pg, const LU &lu, W 
         }
         __syncwarp();
         w_eval_sources(pg, w, t, CB200_MODE_TRAN);
-        const int st = w_newton_step(pg, lu, w, hot, sp, t, gamma, abstol2, a.max_nl, a.limit, solves);
+        const int st = w_newton_step(pg, lu, w, hot, sp, t, gamma, abstol2, a.max_nl, a.limit, solves, fresh, evals);
         if (st != CB200_LANE_OK && status == CB200_LANE_OK) status = st;
+        if (st != CB200_LANE_OK) fresh = false;
         if (st == CB200_LANE_NONFINITE || st == CB200_LANE_SINGULAR)     // dead lane: hold last state
             w_copy(pg, w, pg.off_u(), pg.off_un(), n);
         if (amethod == CB200_METHOD_TRAP) {
@@ -481,6 +540,7 @@ __device__ __forceinline__ void w_tran_fixed_body(const PG &pg, const LU &lu, W 
     if (tl == 0) {
         a.status[lane] = status;
         a.iters[lane] += solves;
+        if (a.evals != nullptr) a.evals[lane] += evals;
     }
 }
 
@@ -506,7 +566,8 @@ __device__ __forceinline__ void w_tran_adaptive_body(const PG &pg, const LU &lu,
     __syncwarp();
     w_eval_all(pg, w, a.t0, CB200_MODE_TRAN, false);
 
-    int status = a.status[lane], solves = 0, rej = 0, T = 0;
+    int status = a.status[lane], solves = 0, rej = 0, T = 0, evals = 0;
+    bool fresh = false;
     if (tl == 0) a.out_t[(int64_t)T * p.P + lane] = a.t0;
     for (int q = tl; q < a.n_save; q += 32)
         a.out[((int64_t)q * a.max_points + T) * p.P + lane] = w(pg.off_u() + __ldg(a.save_idx + q));
@@ -518,7 +579,7 @@ __device__ __forceinline__ void w_tran_adaptive_body(const PG &pg, const LU &lu,
     bool finished = !(t < a.t1);
     while (!finished) {
         // ---- choose the step
-        while (istop < a.n_tstops && __ldg(a.tstops + istop) <= t * (1 + 4e-16)) istop++;
+        while (istop < a.n_tstops && __ldg(a.tstops + istop) <= fma(4.440892098500626e-16, fabs(t), t)) istop++;   // 4 eps(t), either sign of t
         double tnext = istop < a.n_tstops ? __ldg(a.tstops + istop) : a.t1;
         if (tnext > a.t1) tnext = a.t1;
         double hh = h;
@@ -533,9 +594,10 @@ __device__ __forceinline__ void w_tran_adaptive_body(const PG &pg, const LU &lu,
         }
         __syncwarp();
         w_eval_sources(pg, w, tn, CB200_MODE_TRAN);
-        const int st = w_newton_step(pg, lu, w, hot, sp, tn, gamma, abstol2, a.max_nl, a.limit, solves);
+        const int st = w_newton_step(pg, lu, w, hot, sp, tn, gamma, abstol2, a.max_nl, a.limit, solves, fresh, evals);
         if (st != CB200_LANE_OK) {                            // Newton failed: shrink and retry
             w_copy(pg, w, pg.off_u(), pg.off_un(), n);
+            fresh = false;
             rej++;
             h = hh / 4.0;
             if (h < a.dtmin) {
@@ -581,6 +643,7 @@ __device__ __forceinline__ void w_tran_adaptive_body(const PG &pg, const LU &lu,
         }
         if (err > 1.0) {                                      // reject
             w_copy(pg, w, pg.off_u(), pg.off_un(), n);
+            fresh = false;
             rej++;
             double f = 0.9 * pow(err, -1.0 / (pord + 1));
             if (f < 0.2) f = 0.2;
@@ -621,6 +684,7 @@ __device__ __forceinline__ void w_tran_adaptive_body(const PG &pg, const LU &lu,
         a.iters[lane] += solves;
         a.rejected[lane] = rej;
         a.count[lane] = T < a.max_points ? T : a.max_points;
+        if (a.evals != nullptr) a.evals[lane] += evals;
     }
 }
 

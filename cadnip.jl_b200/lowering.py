@@ -84,6 +84,69 @@ class LoweredCircuit:
         except ValueError:
             raise KeyError(f"no unknown named {name!r}; have {names}") from None
 
+    # ------------------------------------------------------------------ #
+    # Reviewable on-disk form (gzip'd JSON: integer / float tables as lists, the emitted CUDA
+    # and C text as strings).  Replaces pickled fixtures: loading executes nothing.
+    _ARRAYS = {"G_I": np.int64, "G_J": np.int64, "C_I": np.int64, "C_J": np.int64, "b_I": np.int64,
+               "dev_kind": np.int32, "dev_flags": np.int32, "dev_node_ptr": np.int32, "dev_nodes": np.int32,
+               "dev_param_ptr": np.int32, "dev_params": np.int32, "dev_gbase": np.int64, "dev_cbase": np.int64,
+               "dev_bbase": np.int64, "uniform": np.float64, "limit_init_ref": np.int32,
+               "dev_state_ptr": np.int32}
+    _PLAIN = ("n_nodes", "n_currents", "n_charges", "n_limits", "node_names", "current_names", "charge_names",
+              "limit_names", "P", "dev_names", "dev_user_nodes", "n_user_nodes", "va_cuda_header", "va_c_source")
+
+    def to_dict(self) -> dict:
+        from .analysis import breakpoints as _bp
+        d = {k: getattr(self, k) for k in self._PLAIN}
+        for k in self._ARRAYS:
+            v = getattr(self, k)
+            d[k] = None if v is None else [float(x).hex() for x in v] if self._ARRAYS[k] is np.float64 else [int(x) for x in v]
+        d["lane_soa"] = [[float(x).hex() for x in col] for col in self.lane_soa]
+        bps = []
+        for w in self.breakpoints:              # waveform objects -> (times, period, count)
+            t = w if (w is None or isinstance(w, (tuple, list))) else _bp(w)
+            bps.append(None if t is None else [[float(x) for x in t[0]], float(t[1]), int(t[2])])
+        d["breakpoints"] = bps
+        if getattr(self, "lane_exprs", None) is not None:
+            d["lane_exprs"] = list(self.lane_exprs)
+        d["format"] = "cadnip-b200 lowered circuit v1"
+        return d
+
+    def save(self, path: str) -> None:
+        import gzip
+        import json
+        with gzip.GzipFile(path, "wb", mtime=0) as f:
+            f.write(json.dumps(self.to_dict(), sort_keys=True).encode())
+
+    @classmethod
+    def from_dict(cls, d: dict) -> "LoweredCircuit":
+        if d.get("format") != "cadnip-b200 lowered circuit v1":
+            raise ValueError("not a cadnip-b200 lowered-circuit file")
+        kw = {k: d[k] for k in cls._PLAIN}
+        for k, dt in cls._ARRAYS.items():
+            v = d.get(k)
+            if v is None:
+                kw[k] = None
+            elif dt is np.float64:
+                kw[k] = np.asarray([float.fromhex(x) for x in v], dtype=np.float64)
+            else:
+                kw[k] = np.asarray(v, dtype=dt)
+        cols = [[float.fromhex(x) for x in col] for col in d["lane_soa"]]
+        kw["lane_soa"] = (np.ascontiguousarray(cols, dtype=np.float64) if cols
+                          else np.zeros((0, int(d["P"])), dtype=np.float64))
+        kw["breakpoints"] = [None if b is None else (list(b[0]), float(b[1]), int(b[2])) for b in d["breakpoints"]]
+        lc = cls(**kw)
+        if "lane_exprs" in d:
+            lc.lane_exprs = list(d["lane_exprs"])
+        return lc
+
+    @classmethod
+    def load(cls, path: str) -> "LoweredCircuit":
+        import gzip
+        import json
+        with gzip.open(path, "rb") as f:
+            return cls.from_dict(json.loads(f.read().decode()))
+
     def param_value(self, ref: int) -> np.ndarray:
         """Value of a parameter reference for every lane, shape (P,)."""
         if ref >= 0:

@@ -2283,6 +2283,103 @@ typedef struct ora_va_api {
 """
 
 
+# --------------------------------------------------------------------------- #
+# FP64 operation counts of emitted code ("the emitter prints a static op count
+# per model (add/mul/fma = 1-2, div/sqrt/exp/log/pow counted separately)").
+# --------------------------------------------------------------------------- #
+_NUM_RE = re.compile(r"(?<![A-Za-z_0-9.])(?:\d+\.?\d*|\.\d+)(?:[eE][+-]?\d+)?")
+_TRANS_FNS = ("CB_EXP", "exp", "log", "log10", "sqrt", "pow", "sin", "cos", "tan", "atan", "atan2", "sinh",
+              "cosh", "tanh", "asin", "acos", "hypot")
+_CTRL_RE = re.compile(r"^(if\b|\}|else\b|while\b|for\b|switch\b|case\b|default\b|do\b|break\b|\{)")
+
+
+def _line_ops(stmt: str) -> Tuple[int, int]:
+    """(flops, transcendentals) of one emitted C statement: + - * count 1 each (so an FMA-shaped
+    a*b + c counts 2, the convention of a 2 x FMA/s peak); / and the libm calls are counted
+    separately.  Declarations without arithmetic, casts and comparisons count nothing."""
+    t = stmt.strip()
+    if not t or t.startswith("/*") or t.startswith("//") or t.startswith("#"):
+        return 0, 0
+    t = re.sub(r"/\*.*?\*/", " ", t)
+    t = re.sub(r"\(void\)\s*\w+\s*;", " ", t)
+    t = _NUM_RE.sub("N", t)
+    trans = 0
+    for fn in _TRANS_FNS:
+        trans += len(re.findall(rf"(?<![A-Za-z_0-9]){fn}\(", t))
+    trans += t.count("/") - t.count("/=") + t.count("/=")            # every division
+    flops = t.count("*")
+    flops += len(re.findall(r"(?<=[A-Za-z_0-9)\]N])\s*[+-](?![+\-=>])", t))      # binary + / -
+    flops += len(re.findall(r"[+\-*]=", t))                            # compound assignment
+    flops -= t.count("*=")                                             # counted twice above
+    return flops, trans
+
+
+def count_ops_static(c_text: str) -> Dict[str, Tuple[int, int]]:
+    """Static (all branches) op counts per emitted function: {function name: (flops, transcendentals)}.
+    An upper bound on what one evaluation executes; `instrument_ops` gives the executed count."""
+    out: Dict[str, Tuple[int, int]] = {}
+    cur = None
+    for ln in c_text.split("\n"):
+        m = re.match(r"(?:__device__ \w+ )?void (ora_va_\w+|va_stamp_\w+)\(", ln)
+        if m:
+            cur = m.group(1)
+            out[cur] = (0, 0)
+            continue
+        if cur is None or ln.startswith("#"):
+            continue
+        if ln.startswith("}"):
+            cur = None
+            continue
+        s2 = ln.strip()
+        if _CTRL_RE.match(s2) and not s2.startswith("{ "):
+            continue
+        f, t = _line_ops(ln)
+        out[cur] = (out[cur][0] + f, out[cur][1] + t)
+    return out
+
+
+def instrument_ops(c_text: str) -> str:
+    """The oracle's C with an op counter: after every straight-line run of statements a
+    ``VA_OPS(flops, transcendentals);`` adds that run's static count to the global
+    ``ora_va_ops[3]`` (third entry: number of model calls) -- so a run of the oracle yields the EXECUTED operation count of the
+    emitted model code (measurement support; the uninstrumented text is what is timed)."""
+    out: List[str] = []
+    infn = False
+    pf = pt = 0
+
+    def flush(indent="    "):
+        nonlocal pf, pt
+        if pf or pt:
+            out.append(f"{indent}VA_OPS({pf}, {pt});")
+        pf = pt = 0
+    sig = False
+    for ln in c_text.split("\n"):
+        if not infn:
+            out.append(ln)
+            if re.match(r"void ora_va_\w+\(", ln):
+                sig = True
+            elif sig and ln.startswith("{"):
+                sig, infn = False, True
+                out.append("    ora_va_ops[2] += 1;")
+            continue
+        if ln.startswith("}"):                   # end of the function
+            flush()
+            out.append(ln)
+            infn = False
+            continue
+        s2 = ln.strip()
+        if (_CTRL_RE.match(s2) and not s2.startswith("{ ")) or s2.endswith("{"):
+            flush()
+            out.append(ln)
+            continue
+        f, t = _line_ops(ln)
+        pf += f; pt += t
+        out.append(ln)
+    head = ("long long ora_va_ops[3] = {0, 0, 0};   /* flops, div/sqrt/exp/log/pow, model calls */\n"
+            "#define VA_OPS(f, t) (ora_va_ops[0] += (f), ora_va_ops[1] += (t))\n")
+    return head + "\n".join(out)
+
+
 def _limw_define(v: VAVariant, target: str) -> str:
     if target == "cuda":
         sel = " : ".join(f"(bi) == {b} ? n{v.lim_slot[b]}" for b in range(len(v.lim_branches)))
@@ -2296,7 +2393,12 @@ def cuda_header(models: Sequence[VAVariant]) -> str:
     out = [_CUDA_PRELUDE]
     for m in models:
         m = m.default if isinstance(m, VAModel) else m
-        out.append(_limw_define(m, "cuda") + m.emit_cuda() + "#undef VA_LIMSLOT\n")
+        body = m.emit_cuda()
+        # $abstime: the module's stamps depend on the time as well as on the iterate, so the time
+        # loops may not carry them from one step to the next (lane_kernels.cuh: kNlTimeDep)
+        if re.search(r"(?<![A-Za-z_0-9])t(?![A-Za-z_0-9(])", body.replace("double t,", "").replace("(void)t;", "")):
+            out.append("#ifndef CB200_VA_TIME_DEP\n#define CB200_VA_TIME_DEP 1\n#endif\n")
+        out.append(_limw_define(m, "cuda") + body + "#undef VA_LIMSLOT\n")
     out.append("template <int PASS, typename PG, typename W>\n"
                "__device__ __forceinline__ void va_dispatch(const PG &pg, W &w, int d, int model, double t,\n"
                "                                            int mode, bool initjct)\n{\n"

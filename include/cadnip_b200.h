@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CB200_ABI_VERSION 1
+#define CB200_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------- */
 #define CB200_OK            0
@@ -192,6 +192,11 @@ typedef struct cb200_stats {
     int64_t steps_accepted;    /* sum over lanes                                */
     int64_t steps_rejected;    /* sum over lanes (adaptive)                     */
     int64_t h2d_bytes, d2h_bytes;
+    int64_t device_evals;      /* transient: device-model evaluation passes executed, summed over
+                                  lanes (a step whose first residual re-uses the stamps of the
+                                  previous step's converged check does not count one)          */
+    int64_t dc_stepping_lanes; /* lanes the last DC / initialisation sent through gshunt / source
+                                  stepping (tiers 2-3 of solve.jl:871-929), on the device       */
 } cb200_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -300,6 +305,17 @@ int cb200_tran_fetch(cb200_handle *h, const cb200_spec *spec, double t0, double 
                      const double *u0, int32_t n_segments, double *t_out, double *u_out,
                      int32_t *count, int32_t *status, int32_t *newton_iters);
 
+/* Same, with a leading dimension: consecutive saved points of u_out (and, for adaptive runs, of
+ * t_out) are u_ld >= P doubles apart, i.e. this handle's P lanes are the column block
+ * [lane0, lane0 + P) of a waveform array of u_ld lanes that the caller addresses at
+ * u_out = base + lane0.  This is how a sweep sharded over several GPUs (one handle each, contiguous
+ * lane blocks in sweep order, src/sweeps.jl:272) delivers ONE [save][T][P_total] result --
+ * the final gather of north_star -- without a staging copy.  u_ld = 0 means P.            */
+int cb200_tran_fetch_ld(cb200_handle *h, const cb200_spec *spec, double t0, double t1,
+                        const cb200_tran_opts *opts, const int64_t *save_idx, int32_t n_save,
+                        const double *u0, int32_t n_segments, double *t_out, double *u_out,
+                        int64_t u_ld, int32_t *count, int32_t *status, int32_t *newton_iters);
+
 /* Adaptive stepping only: time points the integrator must hit exactly -- the source
  * breakpoints the host derives with expand_breakpoints (src/mna/solve.jl:1847-1918;
  * tran!'s auto_tstops, src/sweeps.jl:620-627).  Copied; persists until replaced.   */
@@ -312,11 +328,24 @@ int cb200_wave_info(const cb200_wave *w, int64_t *T, int64_t *P, int32_t *n_save
 int cb200_wave_fetch(cb200_wave *w, double *t /*[T] or [T][P]*/, double *u,
                      int32_t *count /*[P] or NULL*/, int32_t *status /*[P]*/,
                      int32_t *newton_iters /*[P]*/);
+/* cb200_wave_fetch with leading dimensions for u (and the adaptive t): see cb200_tran_fetch_ld. */
+int cb200_wave_fetch_ld(cb200_wave *w, double *t, double *u, int64_t u_ld, int64_t t_ld,
+                        int32_t *count, int32_t *status, int32_t *newton_iters);
 /* final state u(t1) of every lane, [n][P]                                      */
 int cb200_wave_final_state(cb200_wave *w, double *x_out);
 void cb200_wave_free(cb200_wave *w);
 
 int cb200_get_stats(const cb200_handle *h, cb200_stats *out);
+
+/* Measurement support (no reference counterpart).  cb200_measure_fp64_peak times a
+ * register-only FP64 FMA kernel (8 independent chains per thread, 64 warps per SM) on `device`
+ * and returns 2 x FMA/s in TFLOP/s: the denominator of the FP64 roofline of the fused,
+ * register-resident kernels.  cb200_flop_model returns the static flop counts of one Newton
+ * iteration's linear algebra for the handle's circuit: out[0..1] assembly + residual (DC,
+ * transient), out[2..3] numeric refactor, out[4..5] triangular solves, out[6] update, out[7]
+ * nonlinear device evaluations per iteration.                                             */
+int cb200_measure_fp64_peak(int32_t device, double *tflops, double *kernel_ms);
+int cb200_flop_model(const cb200_handle *h, int64_t out[8]);
 
 /* Test hook: y[i] = the device kernels' junction exp(x[i]) (accuracy tests).          */
 int cb200_debug_exp(const double *x, double *y, int32_t n);

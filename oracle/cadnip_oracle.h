@@ -144,6 +144,12 @@ typedef struct ora_tran_opts {
     double init_abstol; int32_t init_maxiters; int32_t flags;   /* bit 0: PCNR corrector in transient */
 } ora_tran_opts;
 
+/* Linear solver behind every Newton solve: 0 = dense LU with partial pivoting (default: the
+ * CHECKER of the parity tests), 1 = fixed-pattern sparse LU with a kept pivot sequence (what the
+ * timed CPU baseline uses; KLU's role at solve.jl:612-613, :667-670).  Process-wide.           */
+void ora_set_linear_solver(int kind);
+int ora_get_linear_solver(void);
+
 /* One circuit.  Fixed step: nsteps = round((t1-t0)/dt); saved points are k = 0,
  * save_every, 2*save_every, ... (the final step is always saved); out_u is
  * [T][n_save] row-major, out_t [T].  Adaptive: up to max_points points, *T_out

@@ -336,18 +336,26 @@ def sweep_tran(nl: OracleNetlist, spec: Spec, t0, t1, opts: TranOpts, save_idx, 
 _va_libs = []
 
 
-def load_va_models(models) -> None:
+def load_va_models(models, count_ops: bool = False) -> None:
     """Compile the C the product's emitter generated for these Verilog-A modules
     (gcc, cached under oracle/_gen) and register it with the oracle.  The model index
-    is the position in ``models`` (== dev_flags of the lowered circuit)."""
+    is the position in ``models`` (== dev_flags of the lowered circuit).
+    count_ops: build the op-counting variant (verilog_a.instrument_ops) -- `va_op_counts()` then
+    returns the flops / transcendentals the model code EXECUTED since `va_op_reset()`; counting
+    runs must be single-threaded (the counter is a plain global)."""
     import hashlib
     import sys
+    global _va_count_lib
     if isinstance(models, str):                  # LoweredCircuit.va_c_source
         src = models
     else:
         sys.path.insert(0, os.path.dirname(_HERE))
         import cadnip_b200.verilog_a as va
         src = va.c_source(models)
+    if count_ops:
+        sys.path.insert(0, os.path.dirname(_HERE))
+        import cadnip_b200.verilog_a as va
+        src = va.instrument_ops(src)
     gen = os.path.join(_HERE, "_gen")
     os.makedirs(gen, exist_ok=True)
     h = hashlib.sha256(src.encode()).hexdigest()[:16]
@@ -362,7 +370,28 @@ def load_va_models(models) -> None:
         os.replace(so + ".tmp", so)
     L = C.CDLL(so)
     _va_libs.append(L)
+    _va_count_lib = L if count_ops else None
     lib().ora_set_va_table(C.cast(L.ora_va_table, C.c_void_p))
+
+
+_va_count_lib = None
+
+
+def va_op_reset() -> None:
+    ops = (C.c_longlong * 3).in_dll(_va_count_lib, "ora_va_ops")
+    ops[0] = ops[1] = ops[2] = 0
+
+
+def va_op_counts():
+    """(flops, transcendentals, model calls) executed by the instrumented model code since
+    va_op_reset()."""
+    ops = (C.c_longlong * 3).in_dll(_va_count_lib, "ora_va_ops")
+    return int(ops[0]), int(ops[1]), int(ops[2])
+
+
+def set_linear_solver(kind: int) -> None:
+    """0: dense partial-pivot LU (the checker, default); 1: fixed-pattern sparse LU (timed baseline)."""
+    lib().ora_set_linear_solver(int(kind))
 
 
 def num_threads() -> int:

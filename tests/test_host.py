@@ -149,13 +149,13 @@ def test_structural_boundary_is_rejected():
 # ---- C ABI ------------------------------------------------------------------
 def test_c_abi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "cadnip_b200.h")).read()
-    declared = sorted(set(re.findall(r"\b(cb200_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(cb200_[a-z0-9_]+)\s*\(", hdr)))
     assert declared == sorted(backend.EXPORTED_SYMBOLS)
     backend.build_library()
     L = C.CDLL(backend.LIB_PATH)
     for sym in declared:
         assert hasattr(L, sym), sym
-    assert backend.lib().cb200_abi_version() == 1
+    assert backend.lib().cb200_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():
@@ -283,13 +283,9 @@ def test_level_schedule_equals_serial_schedule_on_host():
     """The level-scheduled refactor / solves of the lane-per-warp kernels (symbolic.cpp:
     build_level_schedule) run on the host next to the serial static-pivot schedule: identical bits,
     and both solve the system.  Covers the gf180 flip-flop (n = 145) and small circuits."""
-    import gzip
-    import pickle
     import test_gpu_parity as tg
     rng = np.random.default_rng(20261018)
-    cases = []
-    with gzip.open(os.path.join(os.path.dirname(__file__), "golden", "va_mos1_dff.pkl.gz"), "rb") as f:
-        cases.append(("dff", pickle.load(f)))
+    cases = [("dff", cb.LoweredCircuit.load(os.path.join(os.path.dirname(__file__), "golden", "va_mos1_dff.json.gz")))]
     for name, cs in tg.SWEEPS:
         params, P = cs.lane_params()
         cases.append((name, cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P)))
@@ -308,3 +304,104 @@ def test_level_schedule_equals_serial_schedule_on_host():
             assert 1 <= info["factor_levels"] <= info["n"] and info["nlu"] >= info["nnz"]
             if name == "dff":
                 assert info["n"] == 145 and info["factor_levels"] < 40      # 145 pivots, a few levels
+
+
+# ---- round-2 host logic -------------------------------------------------------
+def test_lowered_circuit_json_round_trip(tmp_path):
+    """LoweredCircuit.save / load (gzip'd JSON, the fixture format): every table bit-exact,
+    breakpoints usable by expand_breakpoints."""
+    from cadnip_b200.workloads import clipper_sweep, inverter_sweep
+    for cs in (clipper_sweep(3, 2), inverter_sweep(2, 2, 2)):
+        params, P = cs.lane_params()
+        lc = cb.lower(cs.builder, params, cb.MNASpec(mode="tran"), P=P)
+        path = str(tmp_path / "lc.json.gz")
+        lc.save(path)
+        l2 = cb.LoweredCircuit.load(path)
+        for k in cb.LoweredCircuit._ARRAYS:
+            a, b = getattr(lc, k), getattr(l2, k)
+            assert (a is None and b is None) or (a.dtype == b.dtype and np.array_equal(a, b)), k
+        assert np.array_equal(lc.lane_soa, l2.lane_soa) and l2.lane_soa.dtype == np.float64
+        assert lc.node_names == l2.node_names and lc.dev_user_nodes == l2.dev_user_nodes
+        assert cb.expand_breakpoints(lc.breakpoints, (0.0, 1.0)) == cb.expand_breakpoints(l2.breakpoints, (0.0, 1.0))
+        with pytest.raises(ValueError):
+            cb.LoweredCircuit.from_dict({"format": "something else"})
+
+
+def test_caller_buffers_are_validated():
+    """backend._check_f64 / _lane_block: wrong dtype, shape or layout raises before
+    anything reaches the C side; a column block of a wider array yields its leading dimension."""
+    x = np.zeros((2, 5, 7))
+    assert backend._lane_block(x, (2, 5), 7, "x") == 7
+    assert backend._lane_block(x[..., 2:5], (2, 5), 3, "x") == 7
+    assert backend._lane_block(x[:, :1, 2:5], (2, 1), 3, "x") == 35
+    for bad, lead, P in ((x.astype(np.float32), (2, 5), 7), (x[:, ::2, 2:5], (2, 3), 3), (x[..., ::2], (2, 5), 4),
+                         (x, (2, 4), 7), (x.T, (7, 5), 2)):
+        with pytest.raises(ValueError):
+            backend._lane_block(bad, lead, P, "x")
+    with pytest.raises(ValueError):
+        backend._check_f64(np.zeros((3, 4), dtype=np.float32), (3, 4), "u0")
+    with pytest.raises(ValueError):
+        backend._check_f64(np.zeros((3, 5)), (3, 4), "u0")
+    assert backend.fixed_step_points(0.0, 2e-3, 1e-6, 10) == 201
+    assert backend.fixed_step_points(0.0, 1.003e-3, 1e-6, 10) == 102
+    assert backend.fixed_step_points(0.0, 4e-7, 1e-10, 1) == 4001
+
+
+def _shared_buffer_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P, T = 11, 3
+        buf = distributed.SharedSweepBuffer((2, T, P), pin=False)
+        sl = distributed.shard_slice(P, rank, world)
+        blk = buf.lane_block(sl)
+        ld = backend._lane_block(blk, (2, T), sl.stop - sl.start, "block")
+        lanes = np.arange(sl.start, sl.stop, dtype=np.float64)
+        for s in range(2):
+            for t in range(T):
+                blk[s, t, :] = lanes + 100.0 * t + 1000.0 * s      # what cb200_tran_fetch_ld writes
+        dist.barrier()
+        full = buf.array.copy() if rank == 0 else None
+        buf.close()
+        q.put((rank, ld, None if full is None else full.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_sweep_buffer_world_size_2_gloo():
+    """The end-of-run gather of a sharded sweep: both ranks write their lane blocks into ONE
+    shared host array; rank 0 reads the full [save][T][P] result."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shared_buffer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: (ld, full) for r, ld, full in (q.get(timeout=120) for _ in range(2))}
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][0] == 11 and res[1][0] == 11
+    full = np.array(res[0][1])
+    want = np.arange(11.0)[None, None, :] + 100.0 * np.arange(3.0)[None, :, None] + 1000.0 * np.arange(2.0)[:, None, None]
+    assert np.array_equal(full, want)
+
+
+def test_emitter_op_counts():
+    """verilog_a.count_ops_static / instrument_ops on a small inline module: known counts."""
+    from cadnip_b200 import verilog_a
+    assert verilog_a._line_ops("const double t3 = t1 * t2 + 1.5e-3 * V0;") == (3, 0)
+    assert verilog_a._line_ops("const double t4 = CB_EXP(t3) / (t1 - 2.0);") == (1, 2)
+    assert verilog_a._line_ops("Ieq += -dI0 * V0;") == (2, 0)
+    assert verilog_a._line_ops("const double t5 = -t4;") == (0, 0)
+    assert verilog_a._line_ops("const double t6 = (t5 >= -80.0 && t5 <= 80.0) ? t4 : 0.0;") == (0, 0)
+    m = cb.va("""module res(a, b); inout a, b; electrical a, b; parameter real r = 1e3;
+                 analog begin if (r > 0) I(a, b) <+ V(a, b) / r; else I(a, b) <+ V(a, b) * 1e12; end endmodule""")
+    src = verilog_a.c_source([m.default])
+    st = verilog_a.count_ops_static(src)
+    assert len(st) == 1 and list(st.values())[0][0] > 0
+    inst = verilog_a.instrument_ops(src)
+    assert "ora_va_ops[2] += 1;" in inst and inst.count("VA_OPS(") >= 2

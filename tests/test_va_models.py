@@ -1,12 +1,10 @@
 """The reference's VADistiller models (sp_mos1, sp_diode: $limit / PCNR, node collapse,
 $param_given, analog functions, charge detection) through the emitter.  Circuits come from
-the committed fixtures (tests/golden/va_*.pkl.gz, made by tests/golden/make_va_fixtures.py from
+the committed fixtures (tests/golden/va_*.json.gz, made by tests/golden/make_va_fixtures.py from
 the reference's .va files); known answers are the reference's own (test/params.jl,
 test/sweep.jl, test/mna/oscillator_test.jl)."""
-import gzip
 import math
 import os
-import pickle
 import subprocess
 
 import numpy as np
@@ -27,8 +25,7 @@ GPU_FIXTURES = ["mos1_corner", "diode_chain", "mos1_inverter", "diode_rs_cap", "
 
 
 def fixture(name):
-    with gzip.open(os.path.join(HERE, "golden", f"va_{name}.pkl.gz"), "rb") as f:
-        return pickle.load(f)
+    return cb.LoweredCircuit.load(os.path.join(HERE, "golden", f"va_{name}.json.gz"))
 
 
 def oracle_of(lc):
@@ -286,7 +283,7 @@ def test_gpu_va_models_dc(name):
         comp.close()
     xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
     assert np.array_equal(st, sto) and (st == 0).all()
-    assert _close(x.T, xo, rtol=1e-8, atol=1e-10), float(np.max(np.abs(x.T - xo)))
+    assert _close(x.T, xo), float(np.max(np.abs(x.T - xo)))          # north_star: 1e-9 rel / 1e-12 abs
     assert np.array_equal(it, ito)
 
 
@@ -312,7 +309,7 @@ def test_gpu_va_models_transient(name, tspan, dt, method, spec):
     gpu = np.transpose(r["u"], (2, 1, 0))
     ref = ro["u"][:, :gpu.shape[1], :]
     assert np.array_equal(r["status"], ro["status"]) and (r["status"] == 0).all()
-    assert _close(gpu, ref, rtol=1e-7, atol=1e-9), float(np.max(np.abs(gpu - ref)))
+    assert _close(gpu, ref), float(np.max(np.abs(gpu - ref)))
     assert np.array_equal(r["newton_iters"], ro["newton_iters"])
     if name == "mos1_inverter":
         q = gpu[:, :, lc.index_of("q") - 1]
@@ -337,11 +334,11 @@ def test_gpu_global_workspace_path_with_ragged_lane_count(monkeypatch):
     finally:
         comp.close()
     xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
-    assert np.array_equal(st, sto) and _close(x.T, xo, rtol=1e-8, atol=1e-10) and np.array_equal(it, ito)
+    assert np.array_equal(st, sto) and _close(x.T, xo) and np.array_equal(it, ito)
     ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 4e-9, ora.make_tran_opts(method=1, dt=1e-11), save)
     gpu = np.transpose(r["u"], (2, 1, 0))
     assert (r["status"] == 0).all() and np.array_equal(r["newton_iters"], ro["newton_iters"])
-    assert _close(gpu, ro["u"][:, :gpu.shape[1], :], rtol=1e-7, atol=1e-9)
+    assert _close(gpu, ro["u"][:, :gpu.shape[1], :])
 
 
 @pytest.mark.gpu
@@ -359,39 +356,45 @@ def test_gpu_va_c3_corner_lanes_with_transient_limiting():
                         ora.make_tran_opts(method=0, dt=1e-10, save_every=10, limit=True), save)
     gpu = np.transpose(r["u"], (2, 1, 0))
     assert np.array_equal(r["status"], ro["status"]) and (r["status"] == 0).all()
-    assert _close(gpu, ro["u"][:, :gpu.shape[1], :], rtol=1e-6, atol=1e-8), float(np.max(np.abs(gpu - ro["u"][:, :gpu.shape[1], :])))
+    assert _close(gpu, ro["u"][:, :gpu.shape[1], :]), float(np.max(np.abs(gpu - ro["u"][:, :gpu.shape[1], :])))
     assert np.array_equal(r["newton_iters"], ro["newton_iters"])
 
 
 @pytest.mark.gpu
 def test_gpu_va_dff_adaptive():
     """C4 on the table-driven kernels (n = 145, ~5000 workspace doubles per lane: the lane-per-warp
-    mapping, workspace row in HBM / L2) against the oracle."""
+    mapping, workspace row in HBM / L2) against the oracle, adaptive mode at the north_star
+    tolerance: reltol 1e-6, time-point counts reported and equal, waveforms within reltol on the
+    lanes' own (identical) time grids."""
     lc = fixture("mos1_dff")
     nl = oracle_of(lc)
     save = [lc.index_of("Q"), lc.index_of("Q_neg"), lc.index_of("net0")]
+    reltol, lte_abstol, cap = 1e-6, 1e-9, 8000
     comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
     try:
         x, st, it = comp.dc()
-        wave = comp.tran_adaptive((0.0, 1.2e-7), dt0=1e-12, method="trap", save_idxs=save, reltol=1e-3,
-                                  lte_abstol=1e-5, max_points=4000, limit=True)
+        wave = comp.tran_adaptive((0.0, 1.2e-7), dt0=1e-12, method="trap", save_idxs=save, reltol=reltol,
+                                  lte_abstol=lte_abstol, max_points=cap, limit=True)
         r = wave.fetch(); wave.free()
     finally:
         comp.close()
     xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
-    assert np.array_equal(st, sto) and (st == 0).all() and _close(x.T, xo, rtol=1e-7, atol=1e-9)
-    o = ora.make_tran_opts(method=1, adaptive=1, dt=1e-12, reltol=1e-3, lte_abstol=1e-5, max_points=4000, limit=True)
+    assert np.array_equal(st, sto) and (st == 0).all() and _close(x.T, xo) and np.array_equal(it, ito)
+    o = ora.make_tran_opts(method=1, adaptive=1, dt=1e-12, reltol=reltol, lte_abstol=lte_abstol, max_points=cap,
+                           limit=True)
     ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 1.2e-7, o, save)
     assert (r["status"] == 0).all() and np.array_equal(r["status"], ro["status"])
-    tg = np.linspace(0.0, 1.2e-7, 600)
+    print("time points per lane: gpu", r["count"].tolist(), "oracle", ro["T"].tolist())
+    worst = 0.0
     for p in range(lc.P):
         ng, no = int(r["count"][p]), int(ro["T"][p])
-        assert abs(ng - no) <= max(3, no // 50), (ng, no)                # time-point counts reported and close
+        assert ng == no, (p, ng, no)                                      # same controller, same decisions
+        assert np.allclose(r["t"][:ng, p], ro["t"][p, :no], rtol=1e-9, atol=0.0)
         for k in range(len(save)):
-            a = np.interp(tg, r["t"][:ng, p], r["u"][k, :ng, p])
-            b = np.interp(tg, ro["t"][p, :no], ro["u"][p, :no, k])
-            # adaptive mode: agreement within the LTE tolerance class (north_star: reltol-level)
-            assert np.max(np.abs(a - b)) < 5e-2, (p, k, float(np.max(np.abs(a - b))))
+            a, b = r["u"][k, :ng, p], ro["u"][p, :no, k]
+            worst = max(worst, float(np.max(np.abs(a - b) / (lte_abstol / reltol + np.maximum(np.abs(a), np.abs(b))))))
+    print("max scaled waveform difference", worst)
+    assert worst <= reltol
 
 
 @pytest.mark.gpu
@@ -445,6 +448,8 @@ def test_gpu_va_ring_oscillator():
     ref = np.stack([ora.tran(nl.for_lane(p), ora.make_spec(mode="tran"), 0.0, 5e-9, o, save,
                              u0=u0[:, p].copy())["u"][:gpu.shape[1]] for p in range(lc.P)])
     assert (r["status"] == 0).all()
-    # an oscillator amplifies rounding differences: compare loosely, and the swing exactly
-    assert np.max(np.abs(gpu - ref)) < 1e-3
+    # a perturbation of 1e-13 of the start stays 1e-13 over this window (no amplification), so the
+    # fixed-step bar applies to the oscillator as to every other circuit
+    print("ring: max |gpu - oracle|", float(np.max(np.abs(gpu - ref))))
+    assert _close(gpu, ref), float(np.max(np.abs(gpu - ref)))
     assert gpu[:, :, 0].max() - gpu[:, :, 0].min() > 2.0
