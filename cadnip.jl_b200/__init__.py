@@ -21,7 +21,7 @@ from .sweeps import (Sweep, ProductSweep, TandemSweep, SerialSweep, CircuitSweep
                      sweepvars, split_axes, sweepify, find_param_ranges)
 from .lowering import lower, lower_circuit, LoweredCircuit, StructuralSweepError
 from .analysis import (dc, tran, DCSolution, TranSolution, CompiledSweep, compile_sweep,
-                       expand_breakpoints, breakpoints)
+                       expand_breakpoints, breakpoints, CedarTranOp, CedarUICOp, state_abstol)
 from .verilog_a import va, VAModel, VAError
 from . import backend
 

@@ -18,6 +18,45 @@ from .sweeps import CircuitSweep, SweepResult
 _RETCODES = {0: "Success", 1: "MaxIters", 2: "Unstable", 3: "Unstable", 4: "DtLessThanMin"}
 
 
+class CedarTranOp:
+    """``CedarTranOp`` (src/mna/dcop.jl:160-203): DC solve in ``:tranop`` mode from zeros with the
+    fallback chain -- the default initialisation of ``tran``."""
+
+    def __init__(self, abstol: float = 1e-9, maxiters: int = 500):
+        self.abstol, self.maxiters = abstol, maxiters
+
+
+class CedarUICOp:
+    """``CedarUICOp`` (src/mna/dcop.jl:145-151, :311-411): no DC solve; ``warmup_steps`` fixed
+    backward-Euler steps of ``dt`` relax the algebraic constraints from ``u0`` (zeros when none is
+    given).  For oscillators and circuits without a stable DC operating point."""
+
+    def __init__(self, warmup_steps: int = 10, dt: float = 1e-12, use_shampine: bool = False):
+        self.warmup_steps, self.dt, self.use_shampine = int(warmup_steps), float(dt), bool(use_shampine)
+
+
+def _init_fields(initializealg, u0, init_abstol, init_maxiters):
+    """(init, init_abstol, init_maxiters, uic_steps, uic_dt) of cb200_tran_opts."""
+    if isinstance(initializealg, CedarUICOp):
+        return 2, init_abstol, init_maxiters, initializealg.warmup_steps, initializealg.dt
+    if isinstance(initializealg, CedarTranOp):
+        return 0, initializealg.abstol, initializealg.maxiters, 10, 1e-12
+    if initializealg is not None:
+        raise TypeError("initializealg must be CedarTranOp(...) or CedarUICOp(...)")
+    return (0 if u0 is None else 1), init_abstol, init_maxiters, 10, 1e-12
+
+
+def state_abstol(lc: LoweredCircuit, vntol: float = 1e-6, iabstol: float = 1e-12,
+                 chgtol: float = 1e-14) -> np.ndarray:
+    """``state_abstol(sys; vntol, iabstol, chgtol)`` (src/mna/build.jl:276-283): per-class absolute
+    tolerance vector over ``[nodes | currents | charges | limits]``; limit unknowns are branch
+    voltages and share ``vntol``."""
+    tol = np.empty(lc.n)
+    a, b, c = lc.n_nodes, lc.n_nodes + lc.n_currents, lc.n_nodes + lc.n_currents + lc.n_charges
+    tol[:a], tol[a:b], tol[b:c], tol[c:] = vntol, iabstol, chgtol, vntol
+    return tol
+
+
 # --------------------------------------------------------------------------- #
 # breakpoints (src/mna/breakpoints.jl, src/mna/solve.jl:1847-1918)
 # --------------------------------------------------------------------------- #
@@ -131,9 +170,11 @@ class TranSolution:
 
 
 class _LazyTranSolutions:
-    def __init__(self, lc, save_idx, t, u, count, status, iters, adaptive):
+    def __init__(self, lc, save_idx, t, u, count, status, iters, adaptive, stats=None, retried=0):
         self.lc, self.save_idx, self.t, self.u = lc, save_idx, t, u
         self.count, self.status, self.iters, self.adaptive = count, status, iters, adaptive
+        self.stats = dict(stats or {})       # sweep-level counters (cb200_stats) of the solve
+        self.stats["lanes_repivoted"] = int(retried)
 
     def __len__(self):
         return self.u.shape[2]
@@ -209,15 +250,17 @@ class CompiledSweep:
 
     def tran(self, tspan, dt, method="be", save_idxs=None, save_every=1, abstol=1e-10,
              max_nl_iters=10, u0=None, init_abstol=1e-9, init_maxiters=500,
-             specialize=False, limit=False) -> backend.Wave:
+             specialize=False, limit=False, initializealg=None) -> backend.Wave:
         """limit=True applies the PCNR corrector inside the transient Newton loop too
-        (CB200_TRAN_LIMIT): the models' $limit functions then damp the iteration."""
+        (CB200_TRAN_LIMIT): the models' $limit functions then damp the iteration.
+        initializealg: None (CedarTranOp, or ``u0`` as given), CedarTranOp(...) or CedarUICOp(...)."""
         if specialize:
             self.specialize(dt, method, limit=limit, fixed_only=True)
+        init, ia, im, us, ud = _init_fields(initializealg, u0, init_abstol, init_maxiters)
         opts = backend.make_tran_opts(method=method, adaptive=False, dt=dt, abstol=abstol,
                                       max_nl_iters=max_nl_iters, save_every=save_every,
-                                      init=0 if u0 is None else 1, init_abstol=init_abstol,
-                                      init_maxiters=init_maxiters, limit=limit)
+                                      init=init, init_abstol=ia, init_maxiters=im, limit=limit,
+                                      uic_steps=us, uic_dt=ud)
         return self.handle.tran(self.spec, tspan[0], tspan[1], opts, self.save_indices(save_idxs), u0)
 
     def tran_fetch(self, tspan, dt, out_u, method="be", save_idxs=None, save_every=1, abstol=1e-10,
@@ -232,9 +275,12 @@ class CompiledSweep:
 
     def tran_adaptive(self, tspan, dt0=None, method="trap", save_idxs=None, abstol=1e-10,
                       reltol=1e-6, lte_abstol=1e-9, max_points=4096, dtmin=0.0, dtmax=0.0,
-                      max_nl_iters=10, tstops=None, u0=None, specialize=False, limit=False) -> backend.Wave:
+                      max_nl_iters=10, tstops=None, u0=None, specialize=False, limit=False,
+                      initializealg=None, class_abstol=None) -> backend.Wave:
         """LTE-controlled stepping, one time axis per lane.  ``tstops`` defaults to the
-        source breakpoints (``auto_tstops``, src/sweeps.jl:620-627)."""
+        source breakpoints (``auto_tstops``, src/sweeps.jl:620-627).  ``class_abstol`` =
+        (vntol, iabstol, chgtol): per-class absolute tolerances of the error test
+        (``state_abstol``, src/mna/build.jl:276-283) instead of the one ``lte_abstol``."""
         if tstops is None:
             try:
                 tstops = expand_breakpoints(self.lc.breakpoints, tspan)
@@ -244,10 +290,12 @@ class CompiledSweep:
         dt0 = float(dt0) if dt0 else (tspan[1] - tspan[0]) * 1e-4
         if specialize:
             self.specialize(dt0, method, limit=limit)
+        init, ia, im, us, ud = _init_fields(initializealg, u0, 1e-9, 500)
         opts = backend.make_tran_opts(method=method, adaptive=True, dt=dt0, abstol=abstol,
                                       reltol=reltol, lte_abstol=lte_abstol, dtmin=dtmin, dtmax=dtmax,
                                       max_nl_iters=max_nl_iters, max_points=max_points,
-                                      init=0 if u0 is None else 1, limit=limit)
+                                      init=init, init_abstol=ia, init_maxiters=im, limit=limit,
+                                      uic_steps=us, uic_dt=ud, class_abstol=class_abstol)
         return self.handle.tran(self.spec, tspan[0], tspan[1], opts, self.save_indices(save_idxs), u0)
 
     def close(self):
@@ -290,54 +338,113 @@ def dc(obj, u0=None, continuation: bool = True, abstol: float = 1e-10, maxiters:
         comp = compile_sweep(obj, spec=spec, device=device)
         try:
             x, st, it = comp.dc(None, abstol, maxiters)
+            r = dict(status=st, newton_iters=it, count=np.zeros_like(st), u=np.zeros((0, 0, len(st))),
+                     t=np.zeros(0), x=x, weak=comp.handle.weak_pivot_lanes())
+
+            def rerun(c):
+                x2, st2, it2 = c.dc(None, abstol, maxiters)
+                return dict(status=st2, newton_iters=it2, count=np.zeros_like(st2),
+                            u=np.zeros((0, 0, len(st2))), t=np.zeros(0), x=x2)
+            _retry_singular_lanes(comp, r, rerun)      # static-pivot safeguard: re-pivot on the failed lanes
         finally:
             comp.close()
         return SweepResult(obj.iterator.points(), _LazyDCSolutions(comp.lc, x, st, it))
     raise TypeError("dc expects an MNACircuit or CircuitSweep")
 
 
+def _retry_singular_lanes(comp: "CompiledSweep", r: dict, run) -> int:
+    """Static-pivot safeguard.  The pivot order is chosen once from magnitudes probed
+    on 16 sample lanes and reused for every lane, step and gamma; KLU in the reference re-pivots
+    when a refactor meets a vanishing pivot.  Lanes that end ``CB200_LANE_SINGULAR`` or were marked
+    by the kernels' multiplier check (``cb200_weak_pivot_lanes``: |l| > 1e8) are therefore solved again on a handle that holds ONLY those lanes, so the probe -- and the pivot order --
+    comes from their own parameter values; the results are merged back.  Returns the number of
+    lanes retried."""
+    bad = np.flatnonzero((r["status"] == backend.LANE_SINGULAR) | r.get("weak", False))
+    if bad.size == 0 or bad.size == comp.P:
+        return 0
+    lc = comp.lc
+    base = comp.lane_slice.start if comp.lane_slice is not None else 0
+    sub = LoweredCircuit(**{f: getattr(lc, f) for f in lc.__dataclass_fields__})
+    sub.lane_soa = np.ascontiguousarray(lc.lane_soa[:, base + bad])
+    sub.P = int(bad.size)
+    c2 = CompiledSweep(sub, comp.spec, comp.device)
+    try:
+        r2 = run(c2)
+    finally:
+        c2.close()
+    for key in ("status", "newton_iters", "count"):
+        r[key][bad] = r2[key]
+    r["u"][:, :, bad] = r2["u"]
+    if r["t"].ndim == 2:
+        r["t"][:, bad] = r2["t"]
+    if "x" in r:
+        r["x"][:, bad] = r2["x"]
+    return int(bad.size)
+
+
 def tran(obj, tspan: Tuple[float, float], solver: Optional[str] = None, abstol: float = 1e-10,
          reltol: float = 1e-8, dt: Optional[float] = None, adaptive: Optional[bool] = None,
          saveat: Optional[float] = None, save_idxs=None, max_nl_iters: int = 10, device: int = 0,
-         max_points: int = 4096):
+         max_points: int = 4096, initializealg=None, u0=None):
     """``tran!(circuit, tspan; solver, abstol, reltol, kw...)`` (sweeps.jl:588-601) and
     ``tran!(cs::CircuitSweep, tspan; kw...)`` (sweeps.jl:692-707).
 
     ``solver``: "ImplicitEuler" | "Trapezoid" | "gear2".  Fixed-step mode is the
-    reference's ``solver=ImplicitEuler()/Trapezoid(), adaptive=false, dt=h``."""
+    reference's ``solver=ImplicitEuler()/Trapezoid(), adaptive=false, dt=h``.
+    ``initializealg``: ``CedarTranOp()`` (default) or ``CedarUICOp(warmup_steps, dt)``
+    (src/mna/dcop.jl); ``u0`` ([n] or [n][P]) is the start state of the latter.
+    ``abstol``: a number, or -- adaptive mode -- a mapping with any of ``vntol`` / ``iabstol`` /
+    ``chgtol`` (defaults 1e-6 / 1e-12 / 1e-14): the reference's NamedTuple form, resolved per class
+    of unknown by ``state_abstol`` (sweeps.jl:556, 615-618; build.jl:276-283)."""
+    class_abstol = None
+    if isinstance(abstol, dict):
+        unknown = set(abstol) - {"vntol", "iabstol", "chgtol"}
+        if unknown:
+            raise ValueError(f"abstol: unknown tolerance class {sorted(unknown)}")
+        class_abstol = (float(abstol.get("vntol", 1e-6)), float(abstol.get("iabstol", 1e-12)),
+                        float(abstol.get("chgtol", 1e-14)))
+        abstol = 1e-10                                    # Newton residual test keeps the scalar default
     method = solver or "Trapezoid"
     single = isinstance(obj, MNACircuit)
     if not single and not isinstance(obj, CircuitSweep):
         raise TypeError("tran expects an MNACircuit or CircuitSweep")
-    if adaptive or (adaptive is None and dt is None):
-        # the reference's default is a variable-step integrator (IDA, sweeps.jl:599-601)
-        comp = compile_sweep(obj, device=device)
-        try:
-            save = comp.save_indices(save_idxs)
-            wave = comp.tran_adaptive(tspan, dt0=dt, method=method, save_idxs=save, abstol=abstol,
-                                      reltol=reltol, lte_abstol=max(abstol, 1e-12),
-                                      max_nl_iters=max_nl_iters, max_points=max_points)
-            r = wave.fetch()
-            wave.free()
-        finally:
-            comp.close()
-        sols = _LazyTranSolutions(comp.lc, save, r["t"], r["u"], r["count"], r["status"],
-                                  r["newton_iters"], True)
-        return sols[0] if single else SweepResult(obj.iterator.points(), sols)
+    is_adaptive = bool(adaptive or (adaptive is None and dt is None))
     save_every = 1
-    if saveat is not None:
+    if saveat is not None and not is_adaptive:
         save_every = max(1, int(round(saveat / dt)))
     comp = compile_sweep(obj, device=device)
-    try:
-        save = comp.save_indices(save_idxs)
-        wave = comp.tran(tspan, dt, method=method, save_idxs=save, save_every=save_every,
-                         abstol=abstol, max_nl_iters=max_nl_iters)
-        r = wave.fetch()
+    save = comp.save_indices(save_idxs)
+
+    def run(c: CompiledSweep) -> dict:
+        uu = None
+        if u0 is not None:
+            uu = np.asarray(u0, dtype=np.float64)
+            if uu.ndim == 1:
+                uu = np.repeat(uu[:, None], c.P, axis=1)
+            elif uu.shape[1] != c.P:                      # a retry handle holds a subset of the lanes
+                uu = uu[:, :c.P]
+            uu = np.ascontiguousarray(uu)
+        if is_adaptive:
+            # the reference's default is a variable-step integrator (IDA, sweeps.jl:599-601)
+            wave = c.tran_adaptive(tspan, dt0=dt, method=method, save_idxs=save, abstol=abstol,
+                                   reltol=reltol, lte_abstol=max(abstol, 1e-12), u0=uu,
+                                   max_nl_iters=max_nl_iters, max_points=max_points,
+                                   initializealg=initializealg, class_abstol=class_abstol)
+        else:
+            wave = c.tran(tspan, dt, method=method, save_idxs=save, save_every=save_every,
+                          abstol=abstol, max_nl_iters=max_nl_iters, u0=uu, initializealg=initializealg)
+        out = wave.fetch()
+        out["x"] = wave.final_state()
+        out["stats"] = c.handle.stats()
+        out["weak"] = c.handle.weak_pivot_lanes()
         wave.free()
+        return out
+
+    try:
+        r = run(comp)
+        retried = _retry_singular_lanes(comp, r, run) if u0 is None or np.ndim(u0) == 1 else 0
     finally:
         comp.close()
     sols = _LazyTranSolutions(comp.lc, save, r["t"], r["u"], r["count"], r["status"],
-                              r["newton_iters"], False)
-    if single:
-        return sols[0]
-    return SweepResult(obj.iterator.points(), sols)
+                              r["newton_iters"], is_adaptive, stats=r["stats"], retried=retried)
+    return sols[0] if single else SweepResult(obj.iterator.points(), sols)

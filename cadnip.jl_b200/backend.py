@@ -75,7 +75,9 @@ class TranOpts(C.Structure):
                 ("lte_abstol", C.c_double), ("dtmin", C.c_double), ("dtmax", C.c_double),
                 ("max_nl_iters", C.c_int32), ("save_every", C.c_int32),
                 ("max_points", C.c_int32), ("init", C.c_int32),
-                ("init_abstol", C.c_double), ("init_maxiters", C.c_int32), ("flags", C.c_int32)]
+                ("init_abstol", C.c_double), ("init_maxiters", C.c_int32), ("flags", C.c_int32),
+                ("uic_steps", C.c_int32), ("_pad", C.c_int32), ("uic_dt", C.c_double),
+                ("vntol", C.c_double), ("iabstol", C.c_double), ("chgtol", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -160,6 +162,8 @@ def lib():
     L.cb200_specialize.argtypes = [vp, C.POINTER(Spec), C.c_int32, C.c_double, C.c_char_p, C.c_char_p, C.c_int32]
     L.cb200_is_specialized.restype = C.c_int
     L.cb200_is_specialized.argtypes = [vp]
+    L.cb200_weak_pivot_lanes.restype = C.c_int
+    L.cb200_weak_pivot_lanes.argtypes = [vp, ip, lp]
     L.cb200_lane_mapping.restype = C.c_int
     L.cb200_lane_mapping.argtypes = [vp]
     L.cb200_host_lu_check.restype = C.c_int
@@ -210,7 +214,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "cb200_abi_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_pattern",
     "cb200_get_maps", "cb200_set_lanes", "cb200_analyze", "cb200_get_pivot_order", "cb200_eval",
-    "cb200_specialize", "cb200_is_specialized", "cb200_lane_mapping", "cb200_host_lu_check", "cb200_emit_source", "cb200_load_va_models",
+    "cb200_specialize", "cb200_is_specialized", "cb200_weak_pivot_lanes", "cb200_lane_mapping", "cb200_host_lu_check", "cb200_emit_source", "cb200_load_va_models",
     "cb200_dc", "cb200_tran", "cb200_tran_fetch", "cb200_tran_fetch_ld", "cb200_set_tstops", "cb200_wave_info",
     "cb200_wave_fetch", "cb200_wave_fetch_ld", "cb200_wave_final_state",
     "cb200_wave_free", "cb200_get_stats", "cb200_debug_exp", "cb200_measure_fp64_peak", "cb200_flop_model"]
@@ -503,6 +507,13 @@ class Handle:
     def is_specialized(self) -> bool:
         return bool(lib().cb200_is_specialized(self._p))
 
+    def weak_pivot_lanes(self) -> np.ndarray:
+        """bool[P]: lanes on which a refactor of the last dc / tran met a weak pivot under the
+        static order (cb200_weak_pivot_lanes)."""
+        f = np.zeros(self.P, np.int32)
+        self._check(lib().cb200_weak_pivot_lanes(self._p, _ip(f), None))
+        return f != 0
+
     def lane_mapping(self) -> str:
         """Mapping of the table-driven kernels for this circuit (cb200_lane_mapping)."""
         return {0: "thread/smem", 1: "thread/hbm", 2: "warp"}[lib().cb200_lane_mapping(self._p)]
@@ -604,8 +615,14 @@ def debug_exp(x: np.ndarray) -> np.ndarray:
 
 def make_tran_opts(method="be", adaptive=False, dt=0.0, abstol=1e-10, reltol=1e-8, lte_abstol=1e-10,
                    dtmin=0.0, dtmax=0.0, max_nl_iters=10, save_every=1, max_points=0, init=0,
-                   init_abstol=1e-9, init_maxiters=500, limit=False) -> TranOpts:
-    """limit: CB200_TRAN_LIMIT -- PCNR corrector inside the transient Newton loop."""
+                   init_abstol=1e-9, init_maxiters=500, limit=False, uic_steps=10, uic_dt=1e-12,
+                   class_abstol=None) -> TranOpts:
+    """limit: CB200_TRAN_LIMIT -- PCNR corrector inside the transient Newton loop.
+    init: 0 CedarTranOp, 1 u0 as given, 2 CedarUICOp warm-up (uic_steps BE steps of uic_dt).
+    class_abstol: (vntol, iabstol, chgtol) -- CB200_TRAN_CLASS_ABSTOL, state_abstol (build.jl:276-283)."""
     m = METHODS[method] if isinstance(method, str) else int(method)
+    v, i, q = class_abstol or (0.0, 0.0, 0.0)
     return TranOpts(m, int(adaptive), dt, abstol, reltol, lte_abstol, dtmin, dtmax, max_nl_iters,
-                    save_every, max_points, init, init_abstol, init_maxiters, 1 if limit else 0)
+                    save_every, max_points, init, init_abstol, init_maxiters,
+                    (1 if limit else 0) | (4 if class_abstol else 0), int(uic_steps), 0, float(uic_dt),
+                    float(v), float(i), float(q))

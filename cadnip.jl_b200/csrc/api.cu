@@ -183,6 +183,7 @@ struct cb200_handle {
     DevBuf<double> d_state;        // [n][P]
     DevBuf<double> d_ws_global;    // [n_slots][P] (eval path / shared-memory overflow)
     DevBuf<int> d_status, d_iters;
+    DevBuf<int> d_weak;            // [P] weak-pivot marks of the last cb200_dc / cb200_tran (lane_kernels.cuh: weak_pivot)
     DevBuf<unsigned char> d_conv, d_active;
     DevBuf<double> d_gshunt_lane, d_srcfact_lane;
     DevBuf<int> d_save, d_rejected, d_evals;
@@ -511,6 +512,7 @@ static int ensure_lane_buffers(cb200_handle *h)
     if (h->d_status.n != (size_t)P) {
         CUDA_TRY(h, h->d_status.alloc(P));
         CUDA_TRY(h, h->d_iters.alloc(P));
+        CUDA_TRY(h, h->d_weak.alloc(P));
         CUDA_TRY(h, h->d_conv.alloc(P));
         CUDA_TRY(h, h->d_active.alloc(P));
         CUDA_TRY(h, h->d_gshunt_lane.alloc(P));
@@ -766,7 +768,7 @@ static int dc_launch(DcRun &r, int algorithm, const unsigned char *d_active, con
     DcArgs a{};
     a.algorithm = algorithm; a.abstol = r.abstol; a.maxiters = r.maxiters; a.t = r.t;
     a.u = h->d_state.p; a.active = d_active; a.gshunt_lane = d_gshunt; a.srcfact_lane = d_srcfact;
-    a.status = h->d_status.p; a.iters = h->d_iters.p; a.converged = h->d_conv.p;
+    a.status = h->d_status.p; a.iters = h->d_iters.p; a.converged = h->d_conv.p; a.weak = h->d_weak.p;
     a.ws_global = nullptr;
     if (needs_global_ws(h)) {
         int rc = ensure_global_ws(h);
@@ -815,12 +817,15 @@ static int dc_chain(cb200_handle *h, const cb200_spec *spec, double t, double ab
     auto all_conv = [&]() { return std::all_of(conv.begin(), conv.end(), [](unsigned char c) { return c != 0; }); };
 
     const bool has_limits = h->st.n_limits > 0;
-    if (has_limits) {
+    // use_stepping 2 / 3: test hooks that enter the chain at tier 2 / tier 3 (cb200_dc_opts)
+    const bool direct = use_stepping < 2;
+    if (!direct) CUDA_TRY(h, cudaMemsetAsync(h->d_status.p, 0, P * sizeof(int), s));
+    if (direct && has_limits) {
         rc = dc_launch(r, 0, nullptr, nullptr, nullptr);                  // tier 0: PCNR
         if (rc != CB200_OK) return rc;
         if ((rc = fetch()) != CB200_OK) return rc;
     }
-    if (!has_limits || !all_conv()) {
+    if (direct && (!has_limits || !all_conv())) {
         // tier 1: plain Newton from u0 on the lanes PCNR left unconverged
         if (has_limits) {
             std::vector<double> cur((size_t)n * P);
@@ -849,9 +854,9 @@ static int dc_chain(cb200_handle *h, const cb200_spec *spec, double t, double ab
         CUDA_TRY(h, cudaMemcpyAsync(h->d_active.p, todo.data(), P, cudaMemcpyHostToDevice, s));
         {
             DcArgs a{};
-            a.algorithm = 2; a.abstol = r.abstol; a.maxiters = r.maxiters; a.t = r.t;
+            a.algorithm = use_stepping == 3 ? 3 : 2; a.abstol = r.abstol; a.maxiters = r.maxiters; a.t = r.t;
             a.u = h->d_state.p; a.active = h->d_active.p;
-            a.status = h->d_status.p; a.iters = h->d_iters.p; a.converged = h->d_conv.p;
+            a.status = h->d_status.p; a.iters = h->d_iters.p; a.converged = h->d_conv.p; a.weak = h->d_weak.p;
             if (needs_global_ws(h)) {
                 if ((rc = ensure_global_ws(h)) != CB200_OK) return rc;
                 a.ws_global = h->d_ws_global.p;
@@ -891,6 +896,7 @@ extern "C" int cb200_dc(cb200_handle *h, const cb200_spec *spec, const cb200_dc_
     h->stats = cb200_stats{};
     cudaStream_t s = h->stream;
     if (n == 0) { for (int64_t l = 0; l < P; l++) { if (status) status[l] = 0; if (iters) iters[l] = 0; } return CB200_OK; }
+    CUDA_TRY(h, cudaMemsetAsync(h->d_weak.p, 0, P * sizeof(int), s));
     if (u0) {
         CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, u0, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, s));
         h->stats.h2d_bytes += (int64_t)n * P * sizeof(double);
@@ -940,6 +946,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
     h->stats = cb200_stats{};
     cudaStream_t s = h->stream;
 
+    CUDA_TRY(h, cudaMemsetAsync(h->d_weak.p, 0, P * sizeof(int), s));
     // initialisation: CedarTranOp (dcop.jl:160-203) or caller-provided state
     std::vector<unsigned char> conv(P, 1);
     std::vector<int> st0(P, CB200_LANE_OK);
@@ -950,10 +957,14 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         int rc = dc_chain(h, &sdc, t0, o->init_abstol, o->init_maxiters, 1, nullptr, conv, st0);
         if (rc != CB200_OK) return rc;
     } else {
-        if (!u0) return fail(h, CB200_EINVAL, "cb200_tran: init=1 needs u0");
-        CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, u0, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (!u0 && o->init == 1) return fail(h, CB200_EINVAL, "cb200_tran: init=1 needs u0");
+        if (u0) {
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, u0, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, s));
+            h->stats.h2d_bytes += (int64_t)n * P * sizeof(double);
+        } else {
+            CUDA_TRY(h, cudaMemsetAsync(h->d_state.p, 0, (size_t)n * P * sizeof(double), s));
+        }
         CUDA_TRY(h, cudaMemsetAsync(h->d_iters.p, 0, P * sizeof(int), s));
-        h->stats.h2d_bytes += (int64_t)n * P * sizeof(double);
     }
     const double gamma_nom = (o->method == CB200_METHOD_BE ? 1.0 : o->method == CB200_METHOD_TRAP ? 2.0 : 1.5) / o->dt;
     int rc = ensure_lu(h, spec, 1, gamma_nom);
@@ -987,6 +998,24 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         ws_global = h->d_ws_global.p;
     }
     cudaError_t ce = cudaSuccess;
+    if (o->init == 2 && o->uic_steps > 0) {
+        // CedarUICOp (dcop.jl:311-411): uic_steps backward-Euler steps of uic_dt from the start state
+        // on the table-driven kernels (same pivot schedule), nothing saved; Newton failures are
+        // marched through (force_dtmin=true), so the lane status is reset afterwards.
+        DevBuf<double> scratch;
+        scratch.pool = h->pool;
+        if (scratch.alloc((size_t)2 * P) != cudaSuccess) { delete w; return fail(h, CB200_ENOMEM, "cb200_tran: allocation failed"); }
+        TranArgs a{};
+        a.method = CB200_METHOD_BE; a.t0 = t0; a.h = o->uic_dt > 0 ? o->uic_dt : 1e-12; a.nsteps = o->uic_steps;
+        a.k_begin = 1; a.k_end = o->uic_steps; a.tp_begin = 0;
+        a.abstol = o->abstol; a.max_nl = o->max_nl_iters; a.limit = o->flags & CB200_TRAN_LIMIT;
+        a.save_every = o->uic_steps; a.n_save = 0; a.save_idx = d_save.p; a.T = 2;
+        a.u = h->d_state.p; a.out = scratch.p; a.status = h->d_status.p; a.iters = h->d_iters.p;
+        a.evals = h->d_evals.p; a.weak = h->d_weak.p; a.ws_global = ws_global;
+        ce = h->k.tran_fixed(&h->prog, &h->lu[1].prog, &sa, &a, h->block_pref, h->smem_limit, s, &h->stats.launches);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(h->d_status.p, 0, P * sizeof(int), s);
+        if (ce != cudaSuccess) { delete w; return fail(h, CB200_ECUDA, std::string("cb200_tran: warm-up failed: ") + cudaGetErrorString(ce)); }
+    }
     if (!o->adaptive) {
         const int64_t nsteps = (int64_t)std::llround((t1 - t0) / o->dt);
         const int se = o->save_every > 0 ? o->save_every : 1;
@@ -999,7 +1028,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         a.method = o->method; a.t0 = t0; a.h = o->dt; a.nsteps = nsteps; a.abstol = o->abstol;
         a.max_nl = o->max_nl_iters; a.limit = o->flags & CB200_TRAN_LIMIT; a.save_every = se; a.n_save = n_save; a.save_idx = d_save.p;
         a.T = T; a.u = h->d_state.p; a.out = w->d_out.p; a.status = h->d_status.p; a.iters = h->d_iters.p;
-        a.evals = h->d_evals.p;
+        a.evals = h->d_evals.p; a.weak = h->d_weak.p;
         a.ws_global = ws_global;
         // Time segments: one launch each.  With a host destination the D2H copy of a finished
         // segment runs on the copy stream while the next segment computes.
@@ -1056,6 +1085,12 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         a.dtmin = o->dtmin > 0 ? o->dtmin : span * 1e-12;
         a.h0 = std::min(o->dt, a.dtmax);
         a.abstol = o->abstol; a.reltol = o->reltol; a.lte_abstol = o->lte_abstol;
+        const bool cls = (o->flags & CB200_TRAN_CLASS_ABSTOL) != 0;
+        a.tol_v = cls ? o->vntol : o->lte_abstol; a.tol_i = cls ? o->iabstol : o->lte_abstol;
+        a.tol_q = cls ? o->chgtol : o->lte_abstol;
+        a.cls_i0 = h->st.n_nodes; a.cls_q0 = h->st.n_nodes + h->st.n_currents;
+        a.cls_l0 = h->st.n_nodes + h->st.n_currents + h->st.n_charges;
+        if (cls && !(a.tol_v > 0 && a.tol_i > 0 && a.tol_q > 0)) { delete w; return fail(h, CB200_EINVAL, "cb200_tran: CB200_TRAN_CLASS_ABSTOL needs vntol, iabstol, chgtol > 0"); }
         a.max_nl = o->max_nl_iters; a.limit = o->flags & CB200_TRAN_LIMIT;
         a.n_save = n_save; a.save_idx = d_save.p; a.max_points = T;
         if (w->d_out.alloc((size_t)std::max(1, n_save) * T * P) != cudaSuccess ||
@@ -1066,7 +1101,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         a.tstops = h->d_tstops.p; a.n_tstops = (int)h->tstops.size();
         a.u = h->d_state.p; a.out_t = w->d_t.p; a.out = w->d_out.p; a.count = w->d_count.p;
         a.status = h->d_status.p; a.iters = h->d_iters.p; a.rejected = h->d_rejected.p;
-        a.evals = h->d_evals.p;
+        a.evals = h->d_evals.p; a.weak = h->d_weak.p;
         a.ws_global = ws_global;
         cudaEventRecord(h->ev0, s);
         if (spec_usable(h) && h->spec.tran_adaptive && h->spec_method == a.method && (!a.limit || h->spec_limit)) {
@@ -1234,6 +1269,22 @@ extern "C" int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t
     h->spec_gen[1] = h->lu_gen[1];
     h->spec_method = method;
     h->spec_limit = want_limit;
+    return CB200_OK;
+}
+
+// Lanes on which a refactor of the last cb200_dc / cb200_tran* met a weak pivot under the static
+// order (multiplier beyond 1e8; lane_kernels.cuh: weak_pivot).  Waits for the handle's stream.
+extern "C" int cb200_weak_pivot_lanes(cb200_handle *h, int32_t *flags, int64_t *count)
+{
+    if (!h || (!flags && !count)) return fail(h, CB200_EINVAL, "cb200_weak_pivot_lanes: null argument");
+    if (h->P <= 0) return fail(h, CB200_ESTATE, "cb200_weak_pivot_lanes: call cb200_set_lanes first");
+    cudaSetDevice(h->device);
+    std::vector<int> f((size_t)h->P);
+    CUDA_TRY(h, cudaMemcpyAsync(f.data(), h->d_weak.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int64_t c = 0;
+    for (int64_t l = 0; l < h->P; l++) { if (flags) flags[l] = f[l] != 0; c += f[l] != 0; }
+    if (count) *count = c;
     return CB200_OK;
 }
 

@@ -78,7 +78,8 @@ cudaError_t launch_eval(const Program &p, const SpecArgs &s, const EvalArgs &a, 
 
 // ---- DC: PCNR / plain Newton per lane (src/mna/solve.jl:542-698)
 struct DcArgs {
-    int algorithm;          // 0: PCNR (_dc_pcnr_newton), 1: plain Newton (_dc_newton_compiled)
+    int algorithm;          // 0: PCNR (_dc_pcnr_newton), 1: plain Newton (_dc_newton_compiled),
+                            // 2: gshunt stepping then source stepping (solve.jl:720-850), 3: source stepping only
     double abstol;
     int maxiters;
     double t;
@@ -89,6 +90,7 @@ struct DcArgs {
     int *status;            // [P] CB200_LANE_*
     int *iters;             // [P] (+= linear solves)
     unsigned char *converged;  // [P]
+    int *weak;              // [P] or null: set to 1 when a refactor of the lane met a weak pivot (see weak_pivot())
     double *ws_global;      // used when the lane workspace does not fit in shared memory
     int hot_smem;           // set by the launcher (lane-per-warp kernels: shared-memory configuration)
 };
@@ -115,6 +117,7 @@ struct TranArgs {
     int *status;            // [P]
     int *iters;             // [P]
     int *evals;             // [P] or null: += device-model evaluation passes executed for the lane
+    int *weak;              // [P] or null (see DcArgs)
     double *ws_global;
     int hot_smem;
 };
@@ -127,6 +130,10 @@ struct AdaptArgs {
     int method;
     double t0, t1, h0, dtmin, dtmax;
     double abstol, reltol, lte_abstol;
+    // absolute LTE tolerance per class of unknown [nodes | currents | charges | limits]
+    // (state_abstol, build.jl:276-283); all three = lte_abstol unless CB200_TRAN_CLASS_ABSTOL
+    double tol_v, tol_i, tol_q;
+    int cls_i0, cls_q0, cls_l0;      // first current / charge / limit unknown (0-based)
     int max_nl;
     int limit;
     int n_save;
@@ -140,6 +147,7 @@ struct AdaptArgs {
     int *count;             // [P]
     int *status, *iters, *rejected;
     int *evals;             // [P] or null (see TranArgs)
+    int *weak;              // [P] or null (see DcArgs)
     double *ws_global;
     int hot_smem;
 };

@@ -128,14 +128,28 @@ template <typename IdxT>
 struct LaneWs {
     double *ws;
     IdxT stride;
+    bool weak = false;              // a refactor of this lane met a weak pivot (weak_pivot())
     __device__ __forceinline__ double &operator()(int slot) const { return ws[(IdxT)slot * stride]; }
 };
 
 template <int N>
 struct RegWs {                      // specialised kernels: constant indices -> registers
     double r[N > 0 ? N : 1];
+    bool weak = false;
     __device__ __forceinline__ double &operator()(int slot) { return r[slot]; }
 };
+
+// Static-pivot safeguard.  The pivot order is chosen once on the host from sample
+// lanes; a lane whose values differ may meet a pivot that is tiny against its column -- not zero,
+// so the solve goes on, but with element growth 1/ratio.  A multiplier |l| = |a_ik / pivot| beyond
+// 1e8 (what partial pivoting would never produce: |l| <= 1, KLU's threshold: <= 1e3) marks the lane;
+// the mark is advisory -- the kernel carries on -- and the host re-solves marked lanes with a pivot
+// order chosen from their own values (cb200_weak_pivot_lanes).  Integer test on the high word: no
+// FP64 issue slot; NaN / Inf multipliers are marked too.
+__device__ __forceinline__ bool weak_pivot(double l)
+{
+    return (__double2hiint(l) & 0x7fffffff) > 0x4197d783;        // |l| > ~1e8
+}
 
 #define CB_UNROLL _Pragma("unroll (PG::kUnroll)")
 
@@ -715,6 +729,7 @@ __device__ __forceinline__ bool factor_and_solve(const PG &pg, const LU &lu, W &
             const int ls = pg.off_LU() + lu.L_slot(e);
             const double l = w(ls) * inv;
             w(ls) = l;
+            w.weak |= weak_pivot(l);
                     for (int q = u0; q < u1; q++) {
                 const int ts = pg.off_LU() + lu.tgt(t0 + (e - l0) * (u1 - u0) + (q - u0));
                 w(ts) = w(ts) - l * w(pg.off_LU() + lu.U_slot(q));
@@ -842,6 +857,7 @@ __device__ __forceinline__ void dc_body(const PG &pg, const LU &lu, W &w, const 
         CB_UNROLL
         for (int i = 0; i < pg.n(); i++) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
         a.status[lane] = status;
+        if (a.weak && w.weak) a.weak[lane] = 1;
         a.iters[lane] += solves;
         a.converged[lane] = conv ? 1 : 0;
     }
@@ -925,6 +941,7 @@ __device__ __forceinline__ void dc_stepping_body(const PG &pg, const LU &lu, W &
     eval_all(pg, w, a.t, sp.mode, false);
     StepCtl ctl;
     ctl.begin(sp.gshunt);
+    if (a.algorithm == 3) ctl.start_source();
     const double abstol2 = a.abstol * a.abstol;
     int iter = 0, solves = 0;
     bool fin = !act;
@@ -954,6 +971,7 @@ __device__ __forceinline__ void dc_stepping_body(const PG &pg, const LU &lu, W &
     if (act) {
         for (int i = 0; i < pg.n(); i++) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
         a.status[lane] = ctl.conv ? CB200_LANE_OK : CB200_LANE_MAXITER;
+        if (a.weak && w.weak) a.weak[lane] = 1;
         a.iters[lane] += solves;
         a.converged[lane] = ctl.conv ? 1 : 0;
     }
@@ -1093,6 +1111,7 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
             }
         }
         a.status[lane] = status;
+        if (a.weak && w.weak) a.weak[lane] = 1;
         a.iters[lane] += solves;
         if (a.evals != nullptr) a.evals[lane] += evals;
     }
@@ -1111,6 +1130,12 @@ __device__ __forceinline__ void tran_fixed_body(const PG &pg, const LU &lu, W &w
 //    h < dtmin ends the lane with CB200_LANE_DTMIN.
 // The same statement is the oracle's (oracle/cadnip_oracle.c: ora__tran_adaptive).
 // ---------------------------------------------------------------------------
+// absolute tolerance of unknown i in the LTE test: state_abstol (build.jl:276-283)
+__device__ __forceinline__ double lte_atol(const AdaptArgs &a, int i)
+{
+    return i < a.cls_i0 ? a.tol_v : i < a.cls_q0 ? a.tol_i : i < a.cls_l0 ? a.tol_q : a.tol_v;
+}
+
 template <typename PG, typename LU, typename W>
 __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W &w, const Program &p,
                                                    const SpecArgs &sp, const AdaptArgs &a)
@@ -1229,7 +1254,7 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
                 for (int i = 0; i < pg.n(); i++) {
                     const double ui = w(pg.off_u() + i), uni = w(pg.off_un() + i);
                     const double up = uni + r * (uni - w(pg.off_h1() + i));
-                    const double tol = a.lte_abstol + a.reltol * fmax(fabs(ui), fabs(uni));
+                    const double tol = lte_atol(a, i) + a.reltol * fmax(fabs(ui), fabs(uni));
                     const double e = c * (ui - up) / tol;
                     acc += e * e;
                 }
@@ -1244,7 +1269,7 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
                 for (int i = 0; i < pg.n(); i++) {
                     const double ui = w(pg.off_u() + i), uni = w(pg.off_un() + i);
                     const double up = la * w(pg.off_h2() + i) + lb * w(pg.off_h1() + i) + lc * uni;
-                    const double tol = a.lte_abstol + a.reltol * fmax(fabs(ui), fabs(uni));
+                    const double tol = lte_atol(a, i) + a.reltol * fmax(fabs(ui), fabs(uni));
                     const double e = c * (ui - up) / tol;
                     acc += e * e;
                 }
@@ -1292,6 +1317,7 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
         CB_UNROLL
         for (int i = 0; i < pg.n(); i++) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
         a.status[lane] = status;
+        if (a.weak && w.weak) a.weak[lane] = 1;
         a.iters[lane] += solves;
         a.rejected[lane] = rej;
         a.count[lane] = T < a.max_points ? T : a.max_points;

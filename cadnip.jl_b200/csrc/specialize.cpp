@@ -139,7 +139,8 @@ static void emit_factor_solve(std::ostringstream &o, const Program &p, const LuS
         int tq = S.tgt_ptr[k];
         for (int e = l0; e < l1; e++) {
             const int ls = LU + S.L_slot[e];
-            o << "            {\n                const double l = w(" << ls << ") * inv;\n                w(" << ls << ") = l;\n";
+            o << "            {\n                const double l = w(" << ls << ") * inv;\n                w(" << ls << ") = l;\n"
+                 "                w.weak |= weak_pivot(l);\n";
             for (int q = u0; q < u1; q++, tq++) {
                 const int ts = LU + S.tgt[tq];
                 o << "                w(" << ts << ") = w(" << ts << ") - l * w(" << LU + S.U_slot[q] << ");\n";

@@ -10,7 +10,7 @@
 
 namespace cb200 {
 
-constexpr int kSpecAbi = 6;
+constexpr int kSpecAbi = 7;
 
 struct SpecInput {
     const Structure *st;

@@ -231,7 +231,9 @@ __device__ __forceinline__ bool w_factor_and_solve(const PG &pg, const LU &lu, W
             const int s1 = tb.sc_ptr[v];
             for (int q = tb.sc_ptr[v - 1] + tl; q < s1; q += 32) {
                 const int2 e = tb.sc[q];
-                sLU[e.x] = sLU[e.x] * sDI[e.y];
+                const double lv = sLU[e.x] * sDI[e.y];
+                sLU[e.x] = lv;
+                w.weak |= weak_pivot(lv);
             }
         }
         __syncwarp();
@@ -372,8 +374,10 @@ __device__ __forceinline__ void w_dc_body(const PG &pg, const LU &lu, W &w, cons
     }
     __syncwarp();
     for (int i = tl; i < n; i += 32) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+    const bool any_weak = __any_sync(CB_FULL, w.weak);
     if (tl == 0) {
         a.status[lane] = status;
+        if (a.weak && any_weak) a.weak[lane] = 1;
         a.iters[lane] += solves;
         a.converged[lane] = conv ? 1 : 0;
     }
@@ -395,6 +399,7 @@ __device__ __forceinline__ void w_dc_stepping_body(const PG &pg, const LU &lu, W
     w_eval_all(pg, w, a.t, sp.mode, false);
     StepCtl ctl;
     ctl.begin(sp.gshunt);
+    if (a.algorithm == 3) ctl.start_source();
     const double abstol2 = a.abstol * a.abstol;
     int iter = 0, solves = 0;
     while (ctl.phase != 3) {
@@ -422,8 +427,10 @@ __device__ __forceinline__ void w_dc_stepping_body(const PG &pg, const LU &lu, W
     }
     __syncwarp();
     for (int i = tl; i < n; i += 32) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+    const bool any_weak = __any_sync(CB_FULL, w.weak);
     if (tl == 0) {
         a.status[lane] = ctl.conv ? CB200_LANE_OK : CB200_LANE_MAXITER;
+        if (a.weak && any_weak) a.weak[lane] = 1;
         a.iters[lane] += solves;
         a.converged[lane] = ctl.conv ? 1 : 0;
     }
@@ -537,8 +544,10 @@ __device__ __forceinline__ void w_tran_fixed_body(const PG &pg, const LU &lu, W 
             a.hist[(int64_t)(n + i) * p.P + lane] = w(pg.off_dterm() + i);
         }
     }
+    const bool any_weak = __any_sync(CB_FULL, w.weak);
     if (tl == 0) {
         a.status[lane] = status;
+        if (a.weak && any_weak) a.weak[lane] = 1;
         a.iters[lane] += solves;
         if (a.evals != nullptr) a.evals[lane] += evals;
     }
@@ -615,7 +624,7 @@ __device__ __forceinline__ void w_tran_adaptive_body(const PG &pg, const LU &lu,
                 for (int i = tl; i < n; i += 32) {
                     const double ui = w(pg.off_u() + i), uni = w(pg.off_un() + i);
                     const double up = uni + r * (uni - w(pg.off_h1() + i));
-                    const double tol = a.lte_abstol + a.reltol * fmax(fabs(ui), fabs(uni));
+                    const double tol = lte_atol(a, i) + a.reltol * fmax(fabs(ui), fabs(uni));
                     hot.wv[i] = c * (ui - up) / tol;
                 }
             } else {
@@ -628,7 +637,7 @@ __device__ __forceinline__ void w_tran_adaptive_body(const PG &pg, const LU &lu,
                 for (int i = tl; i < n; i += 32) {
                     const double ui = w(pg.off_u() + i), uni = w(pg.off_un() + i);
                     const double up = la * w(pg.off_h2() + i) + lb * w(pg.off_h1() + i) + lc * uni;
-                    const double tol = a.lte_abstol + a.reltol * fmax(fabs(ui), fabs(uni));
+                    const double tol = lte_atol(a, i) + a.reltol * fmax(fabs(ui), fabs(uni));
                     hot.wv[i] = c * (ui - up) / tol;
                 }
             }
@@ -679,8 +688,10 @@ __device__ __forceinline__ void w_tran_adaptive_body(const PG &pg, const LU &lu,
     }
     __syncwarp();
     for (int i = tl; i < n; i += 32) a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+    const bool any_weak = __any_sync(CB_FULL, w.weak);
     if (tl == 0) {
         a.status[lane] = status;
+        if (a.weak && any_weak) a.weak[lane] = 1;
         a.iters[lane] += solves;
         a.rejected[lane] = rej;
         a.count[lane] = T < a.max_points ? T : a.max_points;

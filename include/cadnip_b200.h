@@ -141,7 +141,8 @@ typedef struct cb200_wave   cb200_wave;
 typedef struct cb200_dc_opts {
     double  abstol;        /* 1e-10 (dc!) / 1e-9 (transient init)              */
     int32_t maxiters;      /* 100 / 500                                        */
-    int32_t use_stepping;  /* 1: gshunt + source stepping fallbacks            */
+    int32_t use_stepping;  /* 1: gshunt + source stepping fallbacks; 2 / 3 (test hooks):
+                              enter the chain at gshunt / source stepping directly    */
 } cb200_dc_opts;
 
 #define CB200_METHOD_BE    0
@@ -162,10 +163,19 @@ typedef struct cb200_tran_opts {
     int32_t max_nl_iters;  /* 10 (IDA max_nonlinear_iters, sweeps.jl:599)      */
     int32_t save_every;    /* fixed-step: keep every k-th point (saveat), >=1  */
     int32_t max_points;    /* adaptive: per-lane output capacity               */
-    int32_t init;          /* 0: CedarTranOp (dcop.jl:160); 1: u0 given (UIC)  */
+    int32_t init;          /* 0: CedarTranOp (dcop.jl:160); 1: u0 given, used as is;
+                              2: CedarUICOp (dcop.jl:311-411): no DC solve, uic_steps fixed
+                              backward-Euler steps of uic_dt from u0 (NULL = zeros) relax the
+                              algebraic constraints, marching on through Newton failures   */
     double  init_abstol;   /* 1e-9  */
     int32_t init_maxiters; /* 500   */
     int32_t flags;         /* CB200_TRAN_* bits                                */
+    int32_t uic_steps;     /* 10    (CedarUICOp warmup_steps)                  */
+    int32_t _pad;
+    double  uic_dt;        /* 1e-12 (CedarUICOp dt)                            */
+    double  vntol;         /* CB200_TRAN_CLASS_ABSTOL: absolute tolerance of the LTE test  */
+    double  iabstol;       /*   per class of unknown, state_abstol (build.jl:276-283):      */
+    double  chgtol;        /*   node voltages + limit unknowns / branch currents / charges  */
 } cb200_tran_opts;
 /* Apply the PCNR corrector inside the transient Newton loop as well: after every solve the
  * limit unknowns are set to the recorded limited voltages w (solve.jl:686-689), so the
@@ -173,6 +183,10 @@ typedef struct cb200_tran_opts {
  * ngspice's transient.  Off = the reference's formulation (limit rows are ordinary
  * algebraic unknowns in transient).  The converged step is the same either way.        */
 #define CB200_TRAN_LIMIT 1
+/* adaptive mode: the LTE test uses vntol / iabstol / chgtol per class of unknown instead of the
+ * one lte_abstol (the reference's `abstol = (vntol=..., iabstol=..., chgtol=...)`, sweeps.jl:556,
+ * 615-618; defaults 1e-6 / 1e-12 / 1e-14) */
+#define CB200_TRAN_CLASS_ABSTOL 4
 /* cb200_specialize flags */
 #define CB200_SPEC_COMPILE_ONLY 1   /* generate + compile into the cache, do not load          */
 #define CB200_SPEC_FIXED_ONLY   4   /* skip the adaptive transient kernel (a third of the compile time) */
@@ -254,6 +268,14 @@ int cb200_load_va_models(cb200_handle *h, const char *cuda_header, const char *c
 int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t method, double dt,
                      const char *csrc_dir, const char *cache_dir, int32_t flags);
 int cb200_is_specialized(const cb200_handle *h);
+/* Static-pivot safeguard.  The pivot order is chosen once from sample lanes and reused for every
+ * lane, step and gamma (klu_refactor's role, solve.jl:612-613); KLU re-pivots when a refactor meets
+ * a bad pivot.  Here every refactor checks its multipliers: a lane on which one exceeded 1e8 is
+ * MARKED (the solve carries on; a vanished pivot still ends the lane CB200_LANE_SINGULAR).
+ * flags[P] (may be NULL) receives 1 for the marked lanes of the last cb200_dc / cb200_tran* call,
+ * *count (may be NULL) their number.  The caller re-solves those lanes on a handle that holds only
+ * them, so the order comes from their own values (analysis._retry_lanes does). */
+int cb200_weak_pivot_lanes(cb200_handle *h, int32_t *flags, int64_t *count);
 /* Which mapping the table-driven kernels use for this circuit (the specialised kernels, when
  * loaded, are always lane-per-thread / registers): 0 = one lane per thread, workspace in
  * shared memory; 1 = one lane per thread, workspace column in HBM; 2 = one lane per WARP,

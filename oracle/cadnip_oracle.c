@@ -1423,6 +1423,12 @@ static int source_stepping(ora_workspace *w, const ora_structure *s, const ora_s
     return result;
 }
 
+/* which tier of the chain below produced the last result on this thread (0 PCNR, 1 Newton,
+ * 2 gshunt stepping, 3 source stepping, -1 none converged): lets the tests assert that their
+ * circuits really reach tiers 2 and 3 */
+static _Thread_local int g_last_dc_tier = -1;
+int ora_last_dc_tier(void) { return g_last_dc_tier; }
+
 /* _dc_solve_with_fallbacks  solve.jl:871-929 */
 int ora_dc_solve_with_fallbacks(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
                                 double *u, double abstol, int maxiters, int use_stepping,
@@ -1435,21 +1441,32 @@ int ora_dc_solve_with_fallbacks(ora_workspace *w, const ora_structure *s, const 
     double *u0 = (double *)xrealloc(NULL, sizeof(double) * (n + 1));
     memcpy(u0, u, sizeof(double) * n);
     int converged = 0;
+    /* use_stepping 2 / 3: test hooks that enter the chain at tier 2 / tier 3 directly, so that the
+     * success paths of both continuations can be exercised on circuits Newton would solve */
+    if (use_stepping == 2) goto tier2;
+    if (use_stepping == 3) goto tier3;
     if (s->n_limits > 0) {                           /* tier 0: PCNR :887-899 */
         int it = 0;
         converged = ora_dc_pcnr_newton(w, s, spec, u, abstol, maxiters, &it);
         solves += it;
+        g_last_dc_tier = 0;
         if (converged) goto out;
         memcpy(u, u0, sizeof(double) * n);           /* next tier restarts from u0 */
     }
     converged = dc_newton_compiled(w, s, spec, u, abstol, maxiters, &solves);   /* tier 1 */
+    g_last_dc_tier = 1;
     if (converged || !use_stepping) goto out;
+tier2:
     memset(u, 0, sizeof(double) * n);                /* tier 2 from zeros :911 */
     converged = gshunt_stepping(w, s, spec, u, abstol, maxiters, &solves);
+    g_last_dc_tier = 2;
     if (converged) goto out;
+tier3:
     memset(u, 0, sizeof(double) * n);                /* tier 3 from zeros :920 */
     converged = source_stepping(w, s, spec, u, abstol, maxiters, &solves);
+    g_last_dc_tier = 3;
 out:
+    if (!converged) g_last_dc_tier = -1;
     free(u0);
     if (total_iters) *total_iters = solves;
     return converged;
@@ -1625,6 +1642,19 @@ int ora_tran(const ora_netlist *nl, const ora_spec *spec_in, double t0, double t
         memcpy(u, u0, sizeof(double) * n);
     }
     spec.mode = ORA_MODE_TRAN;
+    if (o->init == 2) {
+        /* CedarUICOp  dcop.jl:311-411: no DC solve; `warmup_steps` fixed backward-Euler steps of
+         * `dt` from u0 (zeros when none is given) relax the algebraic constraints, marching on
+         * through Newton failures (force_dtmin=true); the result is the state at t0.          */
+        const double hw = o->uic_dt > 0 ? o->uic_dt : 1e-12;
+        for (int k = 1; k <= o->uic_steps; k++) {
+            memcpy(un, u, sizeof(double) * n);
+            for (int64_t i = 0; i < n; i++) hist[i] = 0.0;
+            int st = implicit_step(w, s, &spec, u, un, hist, 1.0 / hw, t0 + (double)k * hw, o->abstol,
+                                   o->max_nl_iters, &iters, o->flags & 1);
+            if (st == ORA_LANE_NONFINITE || st == ORA_LANE_SINGULAR) memcpy(u, un, sizeof(double) * n);
+        }
+    }
 
 #define SAVE_POINT(tt)                                                          \
     do {                                                                        \
@@ -1695,6 +1725,17 @@ int ora_tran(const ora_netlist *nl, const ora_spec *spec_in, double t0, double t
  *    predictor through the previous points (order 1 after a restart, else 2);
  *  - weighted RMS norm with abstol_i + reltol*max(|u_i|,|u_n,i|); accept if <= 1;
  *  - h_new = h*clamp(0.9*err^(-1/(p+1)), 0.2, 2); Newton failure: h /= 4.        */
+/* state_abstol  build.jl:276-283: vntol for node voltages and limit unknowns, iabstol for branch
+ * currents, chgtol for charge states (ora_tran_opts.flags bit 2); otherwise the one lte_abstol */
+static double state_abstol_i(const ora_structure *s, const ora_tran_opts *o, int64_t i)
+{
+    if (!(o->flags & 4)) return o->lte_abstol;
+    if (i < s->n_nodes) return o->vntol;
+    if (i < s->n_nodes + s->n_currents) return o->iabstol;
+    if (i < s->n_nodes + s->n_currents + s->n_charges) return o->chgtol;
+    return o->vntol;
+}
+
 int ora__tran_adaptive(ora_workspace *w, const ora_structure *s, const ora_spec *spec,
                        double t0, double t1, const ora_tran_opts *o, const int64_t *save_idx,
                        int n_save, double *u, double *out_t, double *out_u, int64_t cap_T,
@@ -1769,7 +1810,7 @@ int ora__tran_adaptive(ora_workspace *w, const ora_structure *s, const ora_spec 
             double acc = 0.0;
             for (int64_t i = 0; i < n; i++) {
                 double up = un[i] + r * (un[i] - unm1[i]);
-                double tol = o->lte_abstol + o->reltol * fmax(fabs(u[i]), fabs(un[i]));
+                double tol = state_abstol_i(s, o, i) + o->reltol * fmax(fabs(u[i]), fabs(un[i]));
                 double e = c * (u[i] - up) / tol;
                 acc += e * e;
             }
@@ -1785,7 +1826,7 @@ int ora__tran_adaptive(ora_workspace *w, const ora_structure *s, const ora_spec 
             double acc = 0.0;
             for (int64_t i = 0; i < n; i++) {
                 double up = la * unm2[i] + lb * unm1[i] + lc * un[i];
-                double tol = o->lte_abstol + o->reltol * fmax(fabs(u[i]), fabs(un[i]));
+                double tol = state_abstol_i(s, o, i) + o->reltol * fmax(fabs(u[i]), fabs(un[i]));
                 double e = c * (u[i] - up) / tol;
                 acc += e * e;
             }

@@ -142,11 +142,14 @@ typedef struct ora_tran_opts {
     double dt, abstol, reltol, lte_abstol, dtmin, dtmax;
     int32_t max_nl_iters, save_every, max_points, init;
     double init_abstol; int32_t init_maxiters; int32_t flags;   /* bit 0: PCNR corrector in transient */
+    int32_t uic_steps, _pad; double uic_dt;                     /* init == 2: CedarUICOp warm-up (dcop.jl:311-411) */
+    double vntol, iabstol, chgtol;                              /* flags bit 2: state_abstol per class (build.jl:276-283) */
 } ora_tran_opts;
 
 /* Linear solver behind every Newton solve: 0 = dense LU with partial pivoting (default: the
  * CHECKER of the parity tests), 1 = fixed-pattern sparse LU with a kept pivot sequence (what the
  * timed CPU baseline uses; KLU's role at solve.jl:612-613, :667-670).  Process-wide.           */
+int ora_last_dc_tier(void);      /* tier that produced the calling thread's last DC result (-1: none) */
 void ora_set_linear_solver(int kind);
 int ora_get_linear_solver(void);
 

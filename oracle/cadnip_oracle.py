@@ -48,7 +48,9 @@ class TranOpts(C.Structure):
                 ("lte_abstol", C.c_double), ("dtmin", C.c_double), ("dtmax", C.c_double),
                 ("max_nl_iters", C.c_int32), ("save_every", C.c_int32),
                 ("max_points", C.c_int32), ("init", C.c_int32),
-                ("init_abstol", C.c_double), ("init_maxiters", C.c_int32), ("flags", C.c_int32)]
+                ("init_abstol", C.c_double), ("init_maxiters", C.c_int32), ("flags", C.c_int32),
+                ("uic_steps", C.c_int32), ("_pad", C.c_int32), ("uic_dt", C.c_double),
+                ("vntol", C.c_double), ("iabstol", C.c_double), ("chgtol", C.c_double)]
 
 
 _MODES = {"dcop": 0, "tran": 1, "tranop": 2, "ac": 3}
@@ -150,9 +152,14 @@ def make_spec(spec=None, **over) -> Spec:
 
 def make_tran_opts(method=0, adaptive=0, dt=0.0, abstol=1e-10, reltol=1e-8, lte_abstol=1e-10,
                    dtmin=0.0, dtmax=0.0, max_nl_iters=10, save_every=1, max_points=0, init=0,
-                   init_abstol=1e-9, init_maxiters=500, limit=False) -> TranOpts:
+                   init_abstol=1e-9, init_maxiters=500, limit=False, uic_steps=10, uic_dt=1e-12,
+                   class_abstol=None) -> TranOpts:
+    """init: 0 CedarTranOp, 1 u0 given as is, 2 CedarUICOp warm-up (uic_steps BE steps of uic_dt).
+    class_abstol: (vntol, iabstol, chgtol) of state_abstol (build.jl:276-283) for the LTE test."""
+    v, i, q = class_abstol or (0.0, 0.0, 0.0)
     return TranOpts(method, adaptive, dt, abstol, reltol, lte_abstol, dtmin, dtmax, max_nl_iters,
-                    save_every, max_points, init, init_abstol, init_maxiters, 1 if limit else 0)
+                    save_every, max_points, init, init_abstol, init_maxiters,
+                    (1 if limit else 0) | (4 if class_abstol else 0), uic_steps, 0, uic_dt, v, i, q)
 
 
 class OracleNetlist:
@@ -387,6 +394,11 @@ def va_op_counts():
     va_op_reset()."""
     ops = (C.c_longlong * 3).in_dll(_va_count_lib, "ora_va_ops")
     return int(ops[0]), int(ops[1]), int(ops[2])
+
+
+def last_dc_tier() -> int:
+    """Tier of _dc_solve_with_fallbacks that produced this thread's last DC result (-1: none)."""
+    return int(lib().ora_last_dc_tier())
 
 
 def set_linear_solver(kind: int) -> None:

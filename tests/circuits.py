@@ -123,3 +123,34 @@ def mos_amp(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
 def clipper(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
     from cadnip_b200.workloads import clipper_builder
     return clipper_builder(params, spec, t, x, ctx)
+
+
+def rectifier_v(limit=False):
+    """The rectifier of test/mna/pcnr.jl:39-66 with the source voltage as a sweep parameter.  Without
+    limiting, PCNR is skipped and plain Newton from zeros overshoots the exponential for V >= 4:
+    the lanes fall through to gshunt / source stepping (solve.jl:871-929)."""
+    def build(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
+        ctx = _ctx(ctx)
+        vin = get_node(ctx, "vin"); out = get_node(ctx, "out")
+        stamp(VoltageSource(params.vsrc, name="V1"), ctx, vin, 0)
+        stamp(Resistor(1000.0), ctx, vin, out)
+        stamp(Diode(Is=1e-14, Vt=0.026, limit=limit, name="D1"), ctx, out, 0)
+        return ctx
+    return build
+
+
+def cancelling_vccs(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
+    """a -[R]- b -[R]- c -[R]- gnd, R from b to gnd, and a VCCS b->gnd controlled by V(b): the (b, b)
+    entry is 3/R - gm.  With R = 1024 (1/R exact in binary) and gm = 3/1024 the entry is EXACTLY zero,
+    so a pivot order chosen on lanes with another gm meets a vanishing pivot on that lane; the matrix
+    itself stays regular (b couples to a and c)."""
+    ctx = _ctx(ctx)
+    a = get_node(ctx, "a"); b = get_node(ctx, "b"); c = get_node(ctx, "c")
+    stamp(VoltageSource(1.0, name="V1"), ctx, a, 0)
+    stamp(Resistor(1024.0), ctx, a, b)
+    stamp(Resistor(1024.0), ctx, b, 0)
+    stamp(Resistor(1024.0), ctx, b, c)
+    stamp(Resistor(1024.0), ctx, c, 0)
+    stamp(VCCS(params.gm, name="G1"), ctx, b, 0, b, 0)
+    stamp(Capacitor(1e-9), ctx, c, 0)
+    return ctx

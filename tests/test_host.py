@@ -405,3 +405,25 @@ def test_emitter_op_counts():
     assert len(st) == 1 and list(st.values())[0][0] > 0
     inst = verilog_a.instrument_ops(src)
     assert "ora_va_ops[2] += 1;" in inst and inst.count("VA_OPS(") >= 2
+
+
+def test_state_abstol_layout_and_oracle_class_tolerances():
+    """state_abstol (src/mna/build.jl:276-283): vntol on nodes AND limit unknowns, iabstol on branch
+    currents, chgtol on charge states; the oracle's adaptive controller honours it (flags bit 2)."""
+    import cadnip_oracle as ora
+    import circuits
+    lc = cb.lower_circuit(cb.MNACircuit(circuits.rectifier(True)))
+    tol = cb.state_abstol(lc, vntol=1e-6, iabstol=1e-12, chgtol=1e-14)
+    assert (lc.n_nodes, lc.n_currents, lc.n_charges, lc.n_limits) == (2, 1, 0, 1)
+    assert tol.tolist() == [1e-6, 1e-6, 1e-12, 1e-6]
+    lc = cb.lower_circuit(cb.MNACircuit(circuits.mos_amp, vg=1.0, rd=2e3))
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    counts = {}
+    for name, kw in (("scalar", dict(lte_abstol=1e-6)), ("class", dict(class_abstol=(1e-6, 1e-12, 1e-14)))):
+        o = ora.make_tran_opts(method=1, adaptive=1, dt=1e-11, reltol=1e-5, max_points=20000, **kw)
+        r = ora.tran(nl, ora.make_spec(mode="tran"), 0.0, 3e-8, o, [lc.index_of("d")])
+        assert r["status"] == 0
+        counts[name] = r["T"]
+    assert counts["class"] > counts["scalar"]
+    with pytest.raises(ValueError):
+        cb.tran(cb.MNACircuit(circuits.mos_amp, vg=1.0, rd=2e3), (0.0, 1e-9), abstol=dict(vtol=1e-6))
