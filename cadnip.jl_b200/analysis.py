@@ -68,7 +68,7 @@ def breakpoints(wave) -> Optional[Tuple[List[float], float, int]]:
         td = float(wave.p[3])
         return ([td], 0.0, -1) if td > 0 else None
     if isinstance(wave, PulseWave):
-        v1, v2, td, tr, tf, pw, per = [float(x) for x in wave.p]
+        td, tr, tf, pw, per = [float(x) for x in wave.p[2:]]      # the levels v1, v2 may be swept per lane
         edges = [td, td + tr, td + tr + pw, td + tr + pw + tf]
         return (edges, per, -1) if per > 0 else (edges, 0.0, -1)
     return None

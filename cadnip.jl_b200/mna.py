@@ -610,10 +610,15 @@ def stamp(dev, ctx: MNAContext, *ports, t=0.0, mode="tran", x=ZERO_VECTOR):
                 loc.append(pr[m.ports.index(collapsed[node])])
             else:
                 loc.append(ctx.alloc_internal_node(f"{m.name}_{node}", dev.name))
-        var = m.variant(dev.given, dev.detect_vdep(spec, ctx, xvec, [int(x) for x in loc]))
+        nodes_now = [int(x) for x in loc]
+        var = m.variant(dev.given, dev.detect_vdep(spec, ctx, xvec, nodes_now), dev.vsites(spec, nodes_now))
         S = STATE_DEPENDENT
         for item in var.stamp_plan():
-            if item[0] == "L":                         # alloc_limit!(ctx, name, instance, p, n; init=0.0)
+            if item[0] == "I":                         # alloc_current!(ctx, name, instance), vasim.jl:3256-3278, :2366
+                _, slot, iname = item
+                assert slot == len(loc)
+                loc.append(ctx.alloc_current(f"{m.name}_{iname}", dev.name))
+            elif item[0] == "L":                         # alloc_limit!(ctx, name, instance, p, n; init=0.0)
                 _, slot, pi, ni, lname = item
                 assert slot == len(loc)
                 loc.append(ctx.alloc_limit(f"{m.name}_{lname}", dev.name, loc[pi],

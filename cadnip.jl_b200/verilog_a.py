@@ -177,7 +177,8 @@ class _Parser:
                 self.accept(",")
         self.expect(";")
         m = dict(name=name, ports=ports, params=[], ptypes={}, aliases={}, electrical=[], vars=[],
-                 vtypes={}, vinit={}, functions={}, body=None)
+                 vtypes={}, vinit={}, functions={}, body=None, branches={}, vsites=[], sparams={})
+        self.branches, self.vsites = m["branches"], m["vsites"]
         while not self.accept("endmodule"):
             k, v = self.peek()
             if v in ("parameter", "localparam"):
@@ -185,12 +186,17 @@ class _Parser:
                 typ = "real"
                 if self.peek()[1] in ("real", "integer", "string"):
                     typ = self.next()[1]
-                if typ == "string":
-                    raise VAError("Verilog-A: string parameters are not supported")
                 pname = self.ident()
                 self.expect("=")
                 default = self.expr()
                 self._skip_to_semicolon()                 # `from [..]` / `exclude` ranges
+                if typ == "string":
+                    # string parameters keep their default (e.g. bsim4v8 `version`) and may only be
+                    # compared with string literals; the comparison folds at emit time
+                    if default[0] != "str":
+                        raise VAError("Verilog-A: string parameter default must be a literal")
+                    m["sparams"][pname] = default[1]
+                    continue
                 m["params"].append((pname, default))
                 m["ptypes"][pname] = typ
             elif v == "aliasparam":
@@ -220,7 +226,18 @@ class _Parser:
                     if m["body"] is not None:
                         raise VAError("Verilog-A: more than one analog block")
                     m["body"] = self.stmt(m)
-            elif v in ("branch", "ground", "string", "genvar"):
+            elif v == "branch":                          # branch (a, b) name1, name2;
+                self.next()
+                self.expect("(")
+                a = self.ident()
+                b = self.ident() if self.accept(",") else None
+                self.expect(")")
+                while True:
+                    m["branches"][self.ident()] = (a, b)
+                    if self.accept(";"):
+                        break
+                    self.expect(",")
+            elif v in ("ground", "string", "genvar"):
                 raise VAError(f"Verilog-A: `{v}` declarations are not supported")
             elif k == "eof":
                 raise VAError("Verilog-A: missing endmodule")
@@ -332,13 +349,14 @@ class _Parser:
         if v in ("I", "V") and self.t[self.i + 1][1] == "(" and self._is_contribution():
             kind = self.next()[1]
             self.expect("(")
-            a = self.ident()
-            b = self.ident() if self.accept(",") else None
-            self.expect(")")
+            a, b, br = self._branch_ref()
             self.expect("<+")
             e = self.expr()
             self.expect(";")
-            return ("vcontrib" if kind == "V" else "contrib", a, b, e)
+            if kind == "I":
+                return ("contrib", a, b, e)
+            self.vsites.append((a, b, br))               # every potential contribution is a numbered site
+            return ("vcontrib", a, b, e, len(self.vsites) - 1, br)
         if k == "id" and v.startswith("$"):
             # system tasks ($strobe, $warning, ...) are no-ops on this path (vasim.jl:1181-1256)
             self.next()
@@ -357,6 +375,17 @@ class _Parser:
         s = self._assign_nosemi()
         self.expect(";")
         return s
+
+    def _branch_ref(self):
+        """``a, b)`` / ``a)`` / ``br)`` after the opening parenthesis of an access function:
+        (node, node or None, branch name or None); a named branch stands for its node pair."""
+        a = self.ident()
+        b = self.ident() if self.accept(",") else None
+        self.expect(")")
+        branches = getattr(self, "branches", {})
+        if b is None and a in branches:
+            return branches[a][0], branches[a][1], a
+        return a, b, None
 
     def _is_contribution(self):
         j, depth = self.i + 1, 0
@@ -437,11 +466,9 @@ class _Parser:
             if self.peek()[1] == "(" and self.peek()[0] == "op":
                 self.next()
                 if v in ("V", "I"):
-                    a = self.ident()
-                    b = self.ident() if self.accept(",") else None
-                    self.expect(")")
+                    a, b, br = self._branch_ref()
                     if v == "I":
-                        raise VAError("Verilog-A: current probes I(..) are not supported")
+                        return ("I", a, b, br)
                     return ("V", a, b)
                 args = []
                 while not self.accept(")"):
@@ -460,6 +487,16 @@ _SYS_MATH = ("pow", "exp", "ln", "log", "sqrt", "abs", "sin", "cos", "tan", "tan
 
 # MNASpec fields $simparam can read (vasim.jl:1189-1207); anything else -> the default
 _SPEC_FIELDS = ("temp", "gmin", "gshunt", "srcFact", "tnom", "abstol", "reltol", "vntol", "iabstol")
+
+
+def _str_operand(e, mod) -> Optional[str]:
+    """The string a comparison operand denotes: a literal or a string parameter (its default)."""
+    if isinstance(e, tuple):
+        if e[0] == "str":
+            return e[1]
+        if e[0] == "var" and e[1] in mod.get("sparams", {}):
+            return mod["sparams"][e[1]]
+    return None
 
 
 def _va_round(x: float) -> float:
@@ -484,6 +521,7 @@ class _Interp:
         self.I: Dict[Tuple[str, Optional[str]], float] = {}
         self.Q: Dict[Tuple[str, Optional[str]], float] = {}
         self.reactive: Dict[Tuple[str, Optional[str]], bool] = {}
+        self.vexec: set = set()          # potential-contribution sites the last run executed
         self.depth = 0
 
     def init_vars(self):
@@ -497,6 +535,7 @@ class _Interp:
     def run(self, V: Dict[str, float], vold=None):
         self.V, self.vold = V, vold or {}
         self.I, self.Q, self.reactive = {}, {}, {}
+        self.vexec = set()
         self.scopes = [{}]
         self.init_vars()
         self.stmt(self.mod["body"])
@@ -545,6 +584,10 @@ class _Interp:
             a = self.V[e[1]]
             b = self.V[e[2]] if e[2] is not None else 0.0
             return (a - b, 0.0)
+        if k == "I":
+            # a branch current is an MNA unknown (potential branches) or 0.0 (branches that only carry
+            # current contributions, vasim.jl:3643-3650); the host probes run at x = 0 for those unknowns
+            return (0.0, 0.0)
         if k == "neg":
             r, q = self.ev(e[1])
             return (-r, -q)
@@ -558,6 +601,10 @@ class _Interp:
                 return (1.0 if (self.ev(e[2])[0] != 0.0 and self.ev(e[3])[0] != 0.0) else 0.0, 0.0)
             if op == "||":
                 return (1.0 if (self.ev(e[2])[0] != 0.0 or self.ev(e[3])[0] != 0.0) else 0.0, 0.0)
+            if op in ("==", "!="):
+                sa, sb = _str_operand(e[2], self.mod), _str_operand(e[3], self.mod)
+                if sa is not None and sb is not None:
+                    return (1.0 if (sa == sb) == (op == "==") else 0.0, 0.0)
             (a, aq), (b, bq) = self.ev(e[2]), self.ev(e[3])
             with np.errstate(all="ignore"):
                 if op == "+":
@@ -583,6 +630,8 @@ class _Interp:
             return (0.0, 0.0)
         if fn == "$param_given":
             return (1.0 if args[0][1] in self.given else 0.0, 0.0)
+        if fn == "$port_connected":
+            return (1.0, 0.0)
         if fn == "$simparam":
             name = args[0][1]
             if name == "iniLim":
@@ -704,7 +753,7 @@ class _Interp:
             if _has_ddt(s[3], self.mod):
                 self.reactive[key] = True
         elif k == "vcontrib":
-            pass
+            self.vexec.add(s[4])
         elif k == "callstmt":
             self.ev(s[1])
         else:
@@ -884,8 +933,10 @@ class _Emitter:
     per-variable activity sets (which partial / reactive components can be non-zero)
     stop growing; the last pass is the emitted code."""
 
-    def __init__(self, mod: dict, given: frozenset, act: dict, bact: dict):
+    def __init__(self, mod: dict, given: frozenset, act: dict, bact: dict, vexec: Tuple[bool, ...] = ()):
         self.mod, self.given = mod, given
+        self.vexec = tuple(vexec) + (False,) * (len(mod.get("vsites", ())) - len(vexec))
+        self.vact: Dict[int, dict] = bact.setdefault("_v", {})      # site -> {"d": partial slots, "q": bool}
         self.params = [p[0] for p in mod["params"]]
         ports = list(mod["ports"])
         self.nodes = ports + [n for n in mod["electrical"] if n not in ports]
@@ -1133,6 +1184,15 @@ class _Emitter:
             raise VAError(f"Verilog-A: unknown identifier {name!r}")
         if kind == "V":
             return self.probe(e[1], e[2]), None
+        if kind == "I":
+            # Named branch with a potential contribution: its current is an MNA unknown, read as a
+            # plain value (no partials: `_I_branch_<name> = _mna_x_[idx]`, vasim.jl:3630-3641).  Any
+            # other branch current reads 0.0 (:3643-3650: branches that only carry current -- noise --
+            # contributions), as does I(a,b) of a pair without a top-level potential contribution.
+            if e[3] is not None and e[3] in self.vnamed():
+                self.dyn.add(f"IBR_{e[3]}")
+                return _D(f"IBR_{e[3]}"), None
+            return self.zero(), None
         if kind == "neg":
             r, q = self.ev(e[1])
             return self.neg(r), (None if q is None else self.neg(q))
@@ -1169,6 +1229,10 @@ class _Emitter:
 
     def binary(self, e) -> _Pair:
         op = e[1]
+        if op in ("==", "!="):
+            sa, sb = _str_operand(e[2], self.mod), _str_operand(e[3], self.mod)
+            if sa is not None and sb is not None:
+                return self.const(1.0 if (sa == sb) == (op == "==") else 0.0), None
         ar, aq = self.ev(e[2])
         if op in ("&&", "||") and ar.is_const():
             self._no_react(aq, op)
@@ -1269,7 +1333,9 @@ class _Emitter:
             return self.limit(args), None
         if fn in self.mod["functions"]:
             return self.user_call(self.mod["functions"][fn], [self.ev(a) for a in args], list(args)), None
-        if fn in ("idt", "ddx", "absdelay", "transition", "laplace_nd", "laplace_zp", "$port_connected"):
+        if fn == "$port_connected":                    # va_env.jl:146: every port counts as connected
+            return self.const(1.0), None
+        if fn in ("idt", "ddx", "absdelay", "transition", "laplace_nd", "laplace_zp"):
             raise VAError(f"Verilog-A: {fn} is not supported")
         if fn.startswith("$") and fn[1:] in _SYS_MATH:
             fn = fn[1:]                              # $pow(...) etc.: system-function spelling
@@ -1498,11 +1564,42 @@ class _Emitter:
                 return
             self.ev(s[1])
         elif kind == "vcontrib":
-            # only the node-collapse idiom `if (cond) V(int, ext) <+ 0;` (vasim.jl:2723-2825):
-            # aliased when cond holds, never executed otherwise -> no code either way
-            pass
+            self.vcontrib(s)
         else:
             raise VAError(f"Verilog-A: statement {kind!r} not supported")
+
+    def vnamed(self) -> List[str]:
+        """Named branches that receive a potential contribution, in order of first site."""
+        out = []
+        for (_, _, br) in self.mod.get("vsites", ()):
+            if br is not None and br not in out:
+                out.append(br)
+        return out
+
+    def vcontrib(self, s):
+        """``V(p,n) <+ expr`` (vasim.jl:2311-2395).  A site whose nodes are aliased to one another (the
+        node-collapse idiom) or that this instance does not execute emits nothing; an executed one
+        carries a branch-current unknown and the constraint row -- the variant's ``vexec`` flag, decided
+        on the host by running the module (VAInstance.vsites).  The value and its partials are parked
+        in VS<j> variables here; the stamps follow the evaluation section (VAVariant._body)."""
+        j, br = s[4], s[5]
+        if not self.vexec[j]:
+            return
+        va = self.vact.setdefault(j, {"d": set(), "q": False})
+        self.emit(f"vbx{j} = 1;", "B")
+        r, q = self.ev(s[3])
+        if q is not None and br is None:
+            raise VAError("Verilog-A: ddt() in a potential contribution is supported on named branches only")
+        if not (r.is_const() and r.const == 0.0):
+            self.emit(f"VS{j} += {r.v};")
+        for k in sorted(r.d):
+            if k not in va["d"]:
+                va["d"].add(k); self.changed = True
+            self.emit(f"VS{j}_d{k} += {r.d[k]};")
+        if q is not None:
+            if not va["q"]:
+                va["q"] = True; self.changed = True
+            self.emit(f"VSQ{j} += {q.v};")
 
     def contrib(self, s):
         key = (s[1], s[2])
@@ -1541,28 +1638,27 @@ def _ev_with_cval(self, e):
 _Emitter.ev = _ev_with_cval
 
 
-def _find_collapses(mod) -> Dict[str, Tuple[str, Any]]:
+def _find_collapses(mod) -> Tuple[Dict[str, Tuple[str, Any]], set]:
     """``if (cond) V(int, ext) <+ 0;`` directly inside a conditional of the analog block
-    (detect_short_circuits, vasim.jl:2723-2825): internal node -> (port, cond)."""
+    (detect_short_circuits, vasim.jl:2723-2825): internal node -> (port, cond), plus the ids of
+    those sites.  Only a zero contribution between an INTERNAL node and a PORT is an alias; every
+    other potential contribution (internal-to-internal, to ground, non-zero, named branch) is an
+    ordinary ``V(p,n) <+`` site that carries a branch current when executed."""
     ports = set(mod["ports"])
     internal = set(mod["electrical"]) - ports
     out: Dict[str, Tuple[str, Any]] = {}
+    sites: set = set()
 
     def scan(stmts, cond):
         for s in stmts:
             if s[0] == "block":
                 scan(s[1], cond)
-            elif s[0] == "vcontrib":
-                if s[3] != ("num", 0.0):
-                    raise VAError("Verilog-A: voltage contributions other than the node-collapse idiom "
-                                  "`V(internal, port) <+ 0` are not supported")
+            elif s[0] == "vcontrib" and s[3] == ("num", 0.0) and s[5] is None and s[2] is not None:
                 p, n = s[1], s[2]
                 if p in internal and n in ports:
-                    out[p] = (n, cond)
+                    out[p] = (n, cond); sites.add(s[4])
                 elif n in internal and p in ports:
-                    out[n] = (p, cond)
-                else:
-                    raise VAError("Verilog-A: V(a,b) <+ 0 must join an internal node and a port")
+                    out[n] = (p, cond); sites.add(s[4])
 
     def walk(s):
         if s[0] == "block":
@@ -1572,24 +1668,8 @@ def _find_collapses(mod) -> Dict[str, Tuple[str, Any]]:
             scan([s[2]], s[1])
             if s[3][0] == "if":
                 walk(s[3])
-
-    def count(s) -> int:
-        if s[0] == "vcontrib":
-            return 1
-        if s[0] == "block":
-            return sum(count(x) for x in s[1])
-        if s[0] == "if":
-            return count(s[2]) + count(s[3])
-        if s[0] == "for":
-            return count(s[4])
-        if s[0] == "case":
-            return sum(count(b) for _, b in s[2]) + count(s[3])
-        return 0
     walk(mod["body"])
-    if count(mod["body"]) != len(out):
-        raise VAError("Verilog-A: voltage contributions other than `if (cond) V(internal, port) <+ 0;` "
-                      "are not supported")
-    return out
+    return out, sites
 
 
 # --------------------------------------------------------------------------- #
@@ -1599,13 +1679,20 @@ class VAVariant:
     """The emitted stamp function of a module for one set of given parameters and one
     outcome of the voltage-dependent-charge detection."""
 
-    def __init__(self, model: "VAModel", given: frozenset, vdep: Optional[Tuple[bool, ...]]):
+    def __init__(self, model: "VAModel", given: frozenset, vdep: Optional[Tuple[bool, ...]],
+                 vexec: Optional[Tuple[bool, ...]] = None):
         self.model, self.given = model, given
         mod = model.mod
+        nsites = len(mod.get("vsites", ()))
+        # potential-contribution sites this variant carries (branch current + constraint row); None:
+        # the sites that are not the node-collapse idiom (a module instantiated without an instance)
+        if vexec is None:
+            vexec = tuple(j not in model.collapse_sites for j in range(nsites))
+        self.vexec = tuple(bool(x) for x in vexec) + (False,) * (nsites - len(vexec))
         act: dict = {}
         bact: dict = {}
         for _ in range(40):
-            em = _Emitter(mod, given, act, bact)
+            em = _Emitter(mod, given, act, bact, self.vexec)
             # module-level initialisers, in declaration order (vasim.jl:3149-3212)
             for name in mod["vars"]:
                 if name in mod["vinit"]:
@@ -1627,13 +1714,28 @@ class VAVariant:
         self.static_vdep = [self.reactive[bi] and not self._proportional(bi) for bi in range(len(self.branches))]
         self.vdep = list(self.static_vdep) if vdep is None else [bool(x) for x in vdep]
         self.n_charges = sum(1 for bi in range(len(self.branches)) if self.reactive[bi] and self.vdep[bi])
-        key = f"{model.uid}|{sorted(given)}|{self.vdep}"
+        key = f"{model.uid}|{sorted(given)}|{self.vdep}" + (f"|{self.vexec}" if any(self.vexec) else "")
         self.uid = hashlib.sha256(key.encode()).hexdigest()[:12]
         self.cname = re.sub(r"\W", "_", model.name) + "_" + self.uid
-        # local slot layout: nodes, then limit unknowns, then charge unknowns (in stamping order)
+        self.vact = {j: bact.get("_v", {}).get(j, {"d": set(), "q": False}) for j in range(nsites)}
+        self.vsites = list(mod.get("vsites", ()))
+        # local slot layout: nodes, then limit unknowns, then the branch currents of the potential
+        # contributions (named branches first, then two-node sites in program order), then charge
+        # unknowns (in stamping order)
         self.lim_slot = [self.N + b for b in range(len(self.lim_branches))]
         self.q_slot: Dict[int, int] = {}
         nxt = self.N + len(self.lim_branches)
+        self.vnamed = [br for br in em.vnamed()
+                       if any(self.vexec[j] for j, st in enumerate(self.vsites) if st[2] == br)]
+        self.vn_slot: Dict[str, int] = {}
+        for br in self.vnamed:
+            self.vn_slot[br] = nxt
+            nxt += 1
+        self.vs_slot: Dict[int, int] = {}
+        for j, st in enumerate(self.vsites):
+            if self.vexec[j] and st[2] is None:
+                self.vs_slot[j] = nxt
+                nxt += 1
         for bi in range(len(self.branches)):
             if self.reactive[bi] and self.vdep[bi]:
                 self.q_slot[bi] = nxt
@@ -1710,6 +1812,22 @@ class VAVariant:
             plan.append(("G", ls, p))
             if n is not None:
                 plan.append(("G", ls, n))
+        for br in self.vnamed:                               # branch_current_alloc, vasim.jl:3256-3266
+            plan.append(("I", self.vn_slot[br], f"I_{br}"))
+        for j, slot in self.vs_slot.items():                 # executed V(p,n) <+ sites, vasim.jl:2362-2393
+            a, b, _ = self.vsites[j]
+            p = self.nodes.index(a)
+            n = self.nodes.index(b) if b is not None else None
+            plan.append(("I", slot, f"I_V_{a}_{b if b is not None else '0'}"))
+            plan.append(("G", p, slot))
+            if n is not None:
+                plan.append(("G", n, slot))
+            plan.append(("G", slot, p))
+            if n is not None:
+                plan.append(("G", slot, n))
+            for k in range(N):
+                plan.append(("G", slot, k))
+            plan.append(("b", slot))
         for bi, (a, b) in enumerate(self.branches):
             p = self.nodes.index(a)
             n = self.nodes.index(b) if b is not None else None
@@ -1736,7 +1854,24 @@ class VAVariant:
             plan.append(("b", p))
             if n is not None:
                 plan.append(("b", n))
+        for br in self.vnamed:                               # voltage_stamp_code, vasim.jl:3698-3745
+            a, b = self.model.mod["branches"][br]
+            p = self.nodes.index(a)
+            n = self.nodes.index(b) if b is not None else None
+            slot = self.vn_slot[br]
+            plan.append(("G", p, slot))
+            if n is not None:
+                plan.append(("G", n, slot))
+            plan.append(("G", slot, p))
+            if n is not None:
+                plan.append(("G", slot, n))
+            plan.append(("b", slot))
+            if self._named_reactive(br):
+                plan.append(("C", slot, slot))
         return plan
+
+    def _named_reactive(self, br: str) -> bool:
+        return any(self.vact[j]["q"] for j, st in enumerate(self.vsites) if st[2] == br and self.vexec[j])
 
     # ---- code emission --------------------------------------------------------- #
     def _decls(self) -> List[str]:
@@ -1835,6 +1970,8 @@ class VAVariant:
             L.append(f"    VA_G({ls}, {p}, -1.0);")
             if c is not None:
                 L.append(f"    VA_G({ls}, {self.nodes.index(c)}, 1.0);")
+        for br in self.vnamed:                                      # branch_current_extraction, vasim.jl:3630-3641
+            L.append(f"    const double IBR_{br} = VA_V({self.vn_slot[br]}); (void)IBR_{br};")
         L += self._decls()
         for bi in range(len(self.branches)):
             ba = self.bact[bi]
@@ -1842,6 +1979,11 @@ class VAVariant:
             if ba["q"]:
                 names += [f"Q{bi}"] + [f"Q{bi}_d{k}" for k in sorted(ba["qd"])]
             L.append("    double " + ", ".join(f"{x} = 0.0" for x in names) + ";")
+        for j in range(len(self.vsites)):
+            if self.vexec[j]:
+                va = self.vact[j]
+                names = [f"VS{j}"] + [f"VS{j}_d{k}" for k in sorted(va["d"])] + ([f"VSQ{j}"] if va["q"] else [])
+                L.append("    double " + ", ".join(f"{x} = 0.0" for x in names) + f"; int vbx{j} = 0; (void)vbx{j};")
         setup, evaln, _ = self._sections()
         if setup:
             L.append("    if (VA_SETUP) {   /* bias-independent part: once per kernel (PASS 0) */")
@@ -1851,6 +1993,37 @@ class VAVariant:
 
         def part(prefix, bi, k, act):
             return f"va_mfactor * {prefix}{bi}_d{k}" if k in act else "0.0"
+
+        # executed two-node potential contributions V(p,n) <+ expr (vasim.jl:2362-2393): branch current
+        # I carries the KCL terms, its row is the constraint V_p - V_n - expr = 0 linearised about V
+        for j, slot in self.vs_slot.items():
+            a, b, _ = self.vsites[j]
+            va = self.vact[j]
+            p = self.nodes.index(a)
+            n = self.nodes.index(b) if b is not None else None
+            if any(k >= N for k in va["d"]):
+                raise VAError("Verilog-A: $limit inside a potential contribution is not supported")
+            cur = "IX" if charge_alloc else slot
+            L.append(f"    /* site {j}: V({a}{',' + b if b else ''}) <+ ... */")
+            if charge_alloc:
+                nn = f"n[{n}]" if n is not None else "0"
+                L.append(f"    if (vbx{j} && n[{p}] != {nn}) {{ n[IX] = A->alloc_current(ctx);")
+            else:
+                L.append("    {")
+            L.append(f"    VA_G({p}, {cur}, 1.0);")
+            if n is not None:
+                L.append(f"    VA_G({n}, {cur}, -1.0);")
+            L.append(f"    VA_G({cur}, {p}, 1.0);")
+            if n is not None:
+                L.append(f"    VA_G({cur}, {n}, -1.0);")
+            for k in range(N):
+                L.append(f"    VA_G({cur}, {k}, " + (f"-VS{j}_d{k}" if k in va["d"] else "0.0") + ");")
+            L.append(f"    double bv = VS{j};")
+            for k in range(N):
+                if k in va["d"]:
+                    L.append(f"    bv -= VS{j}_d{k} * V{k};")
+            L.append(f"    VA_B({cur}, bv);")
+            L.append("    }")
 
         for bi, (a, b) in enumerate(self.branches):
             ba = self.bact[bi]
@@ -1918,6 +2091,24 @@ class VAVariant:
             if n is not None:
                 L.append(f"    VA_B({n}, Ieq);")
             L.append("    }")
+        # potential contributions on named branches (vasim.jl:3698-3745): the resistive VALUE goes to
+        # b[I], the reactive value -- what the reference stamps -- to C[I,I] with a minus sign
+        for br in self.vnamed:
+            a, b = self.model.mod["branches"][br]
+            p = self.nodes.index(a)
+            n = self.nodes.index(b) if b is not None else None
+            slot = self.vn_slot[br]
+            js = [j for j, st in enumerate(self.vsites) if st[2] == br and self.vexec[j]]
+            L.append(f"    /* named branch {br}: V({br}) <+ ... */")
+            L.append(f"    VA_G({p}, {slot}, 1.0);")
+            if n is not None:
+                L.append(f"    VA_G({n}, {slot}, -1.0);")
+            L.append(f"    VA_G({slot}, {p}, 1.0);")
+            if n is not None:
+                L.append(f"    VA_G({slot}, {n}, -1.0);")
+            L.append(f"    VA_B({slot}, " + " + ".join(f"VS{j}" for j in js) + ");")
+            if self._named_reactive(br):
+                L.append(f"    VA_C({slot}, {slot}, -(" + " + ".join(f"VSQ{j}" for j in js if self.vact[j]["q"]) + "));")
         return "\n".join(L)
 
     def _probe_expr(self, j: int) -> str:
@@ -1950,15 +2141,23 @@ class VAVariant:
         """Plain C for the oracle: it allocates its own internal nodes / limit and charge
         unknowns (it is the builder) and decides node collapse and charge formulation at
         run time, as the reference's generated stamp! does."""
+        nsites = len(self.vsites)
+        if nsites and not all(self.vexec):
+            # the oracle is the builder: which sites execute is decided by ITS run of the code, so
+            # the C carries all of them (guarded by run-time flags) under this variant's name
+            full = VAVariant(self.model, self.given, tuple(self.vdep), (True,) * nsites)
+            full.cname = self.cname
+            return full.emit_c()
         N = self.N
         nlim = len(self.lim_branches)
+        nvn = len(self.vnamed)
         L = [f"/* Verilog-A module {self.name} (emitted by cadnip_b200.verilog_a) */",
              f"void ora_va_{self.cname}(const ora_va_api *A, void *ctx, const int *ports, const double *par,",
              "                          const double *x, long nx, double t, int va_mode)",
              "{",
              "    (void)t; (void)va_mode;",
              "    const double va_initjct = A->initjct(ctx) ? 1.0 : 0.0; (void)va_initjct;",
-             f"    long n[{N + nlim + 1}]; long QX = {N + nlim}; (void)QX;",
+             f"    long n[{N + nlim + nvn + 2}]; long QX = {N + nlim + nvn}; long IX = {N + nlim + nvn + 1}; (void)QX; (void)IX;",
              f"    double va_state[{self.n_state + 1}];"]
         for i in range(len(self.ports)):
             L.append(f"    n[{i}] = ports[{i}];")
@@ -1977,8 +2176,10 @@ class VAVariant:
             p = self.nodes.index(a)
             nn = f"n[{self.nodes.index(c)}]" if c is not None else "0"
             L.append(f"    n[{self.lim_slot[b]}] = A->alloc_limit(ctx, n[{p}], {nn});")
-        L.append(f"    double Vn[{N + nlim}];")
-        L.append(f"    for (int k = 0; k < {N + nlim}; k++) Vn[k] = A->xval(ctx, n[k], x, nx);")
+        for br in self.vnamed:
+            L.append(f"    n[{self.vn_slot[br]}] = A->alloc_current(ctx);   /* I({br}) */")
+        L.append(f"    double Vn[{N + nlim + nvn}];")
+        L.append(f"    for (int k = 0; k < {N + nlim + nvn}; k++) Vn[k] = A->xval(ctx, n[k], x, nx);")
         return "\n".join(L) + "\n" + self._body(charge_alloc=True) + "\n}\n"
 
 
@@ -1997,16 +2198,17 @@ class VAModel:
         self.param_names = [p[0] for p in m["params"]]
         self.param_defaults = [p[1] for p in m["params"]]
         self.uid = hashlib.sha256(source.encode()).hexdigest()[:12]
-        self.collapses = _find_collapses(m)
+        self.collapses, self.collapse_sites = _find_collapses(m)
         self._variants: Dict[Tuple, VAVariant] = {}
         self._default: Optional[VAVariant] = None
         self.default                                      # emit once now: unsupported constructs fail here
 
-    def variant(self, given=frozenset(), vdep=None) -> VAVariant:
-        key = (frozenset(given), None if vdep is None else tuple(bool(x) for x in vdep))
+    def variant(self, given=frozenset(), vdep=None, vexec=None) -> VAVariant:
+        key = (frozenset(given), None if vdep is None else tuple(bool(x) for x in vdep),
+               None if vexec is None else tuple(bool(x) for x in vexec))
         v = self._variants.get(key)
         if v is None:
-            v = self._variants[key] = VAVariant(self, key[0], key[1])
+            v = self._variants[key] = VAVariant(self, key[0], key[1], key[2])
         return v
 
     # model-level view (no parameters given, static charge classification)
@@ -2149,12 +2351,30 @@ class VAInstance:
                     out[node] = ext
         return out
 
+    def vsites(self, spec, node_of_slot: List[int]) -> Tuple[bool, ...]:
+        """Per potential-contribution site: does this instance carry its branch current?  The
+        generated stamp! decides at run time: the statement must execute (its conditions depend on
+        parameters only) and its two nodes must not be aliased to one another (`if p_node !=
+        n_node`, vasim.jl:2365).  Evaluated by running the module on the host at zero bias."""
+        sites = self.model.mod.get("vsites", ())
+        if not sites:
+            return ()
+        nodes = self.model.nodes
+        it = self._interp(spec)
+        it.run({name: 0.0 for name in nodes}, {})
+        out = []
+        for j, (a, b, br) in enumerate(sites):
+            pa = node_of_slot[nodes.index(a)]
+            pb = node_of_slot[nodes.index(b)] if b is not None else 0
+            out.append(j in it.vexec and pa != pb)
+        return tuple(out)
+
     def detect_vdep(self, spec, ctx, x, node_of_slot: List[int]) -> Tuple[bool, ...]:
         """One detection pass of this instance (the reference's generated stamp! calls
         ``detect_or_cached!`` per reactive branch, vasim.jl:3427-3437): evaluate the branch
         charges at the builder's operating point ``x`` and consult / update the context's
         positional cache.  node_of_slot maps module nodes to circuit nodes."""
-        var = self.model.variant(self.given, None)
+        var = self.model.variant(self.given, None, self.vsites(spec, node_of_slot))
         if not any(var.reactive):
             return tuple(False for _ in var.branches)
         xs = np.asarray(x, dtype=np.float64).reshape(-1) if isinstance(x, np.ndarray) else np.zeros(0)
@@ -2267,6 +2487,7 @@ typedef struct ora_va_api {
     void (*record_limit_w)(void *ctx, long l, double w);
     int (*detect_or_cached)(void *ctx, double v_branch, double q);
     int (*initjct)(void *ctx);
+    long (*alloc_current)(void *ctx);
 } ora_va_api;
 #define CB_EXP(x) exp(x)
 #define VA_ROUND(x) (((x) >= 0.0) ? floor((x) + 0.5) : ceil((x) - 0.5))

@@ -9,7 +9,7 @@ import os
 
 from .circuit import MNASpec
 from .mna import (MNAContext, ZERO_VECTOR, Capacitor, Diode, Resistor, SimpleMOSFET, SinWave,
-                  PWLWave, VoltageSource, VCVS, get_node, stamp)
+                  PWLWave, PulseWave, VoltageSource, VCVS, get_node, stamp)
 from .sweeps import CircuitSweep, ProductSweep, Sweep, TandemSweep
 
 
@@ -283,6 +283,69 @@ def mos1_ring(sp_mos1, caps=False):
     return CircuitSweep(_B(f), Sweep(c=[10e-15, 20e-15] if not caps else [10e-15]))
 
 
+def bjt_ce(sp_bjt):
+    """The sp_bjt circuit of test/mna/vadistiller_integration.jl:392-406 (Vcc 5 V, Vb through 10 k,
+    Rc 1 k, bf = 100, is = 1e-15) with the base drive and bf swept, a collector load capacitor and a
+    PULSE on the base source for the transient.  sp_bjt: 7 internal nodes, of which cx_int, b_int and
+    e_int alias their port, c_int / sub_con are shorted to other INTERNAL nodes and xf1 / xf2 to ground by
+    executed potential contributions (bjt.va:739-753, :1009-1013) -> branch-current unknowns."""
+    def f(ctx, p):
+        vcc = get_node(ctx, "vcc"); vb = get_node(ctx, "vb"); c = get_node(ctx, "collector"); b = get_node(ctx, "base")
+        stamp(VoltageSource(5.0, name="V1"), ctx, vcc, 0)
+        stamp(VoltageSource(p.vb, tran=PulseWave(p.vb, p.vb + 0.1, 2e-7, 1e-7, 1e-7, 6e-7, 2e-6), name="V2"), ctx, vb, 0)
+        stamp(Resistor(10000.0, name="Rb"), ctx, vb, b)
+        stamp(Resistor(1000.0, name="Rc"), ctx, vcc, c)
+        stamp(Capacitor(1e-11, name="Cc"), ctx, c, 0)
+        stamp(sp_bjt(bf=p.bf, name="Q1", **{"is": 1e-15}), ctx, c, b, 0, 0)
+    return CircuitSweep(_B(f), ProductSweep(vb=[0.6, 0.7, 0.8], bf=[50.0, 100.0]))
+
+
+def jfet2_cs(sp_jfet2):
+    """test/mna/vadistiller_integration.jl:498-519: sp_jfet2 common-source stage, gate bias swept."""
+    def f(ctx, p):
+        vdd = get_node(ctx, "vdd"); d = get_node(ctx, "drain"); g = get_node(ctx, "gate")
+        stamp(VoltageSource(10.0, name="Vdd"), ctx, vdd, 0)
+        stamp(VoltageSource(p.vg, name="Vg"), ctx, g, 0)
+        stamp(Resistor(1000.0, name="Rd"), ctx, vdd, d)
+        stamp(sp_jfet2(name="J1"), ctx, d, g, 0)
+    return CircuitSweep(_B(f), Sweep(vg=[-1.0, -0.5, 0.0]))
+
+
+def vdmos_cs(sp_vdmos):
+    """test/mna/vadistiller_integration.jl:695-711: sp_vdmos (vto 2, kp 0.5) with a 100 ohm drain load;
+    named branch `tbr` (vdmos.va:105, :1431) carries a potential contribution on the thermal node."""
+    def f(ctx, p):
+        vdd = get_node(ctx, "vdd"); d = get_node(ctx, "drain"); g = get_node(ctx, "gate")
+        stamp(VoltageSource(10.0, name="Vdd"), ctx, vdd, 0)
+        stamp(VoltageSource(p.vg, name="Vg"), ctx, g, 0)
+        stamp(Resistor(100.0, name="Rd"), ctx, vdd, d)
+        stamp(sp_vdmos(vto=2.0, kp=0.5, name="M1"), ctx, d, g, 0, 0, 0)
+    return CircuitSweep(_B(f), Sweep(vg=[1.0, 3.0, 5.0]))
+
+
+def inductor_rl(sp_inductor):
+    """test/mna/vadistiller_integration.jl:240-259: V1 5 V - 1 k - sp_inductor(1 mH) to ground; at DC
+    the inductor is a short (V(mid) = 0)."""
+    def f(ctx, p):
+        vcc = get_node(ctx, "vcc"); mid = get_node(ctx, "mid")
+        stamp(VoltageSource(5.0, name="V1"), ctx, vcc, 0)
+        stamp(Resistor(p.r, name="R1"), ctx, vcc, mid)
+        stamp(sp_inductor(inductance=1e-3, name="L1"), ctx, mid, 0)
+    return CircuitSweep(_B(f), Sweep(r=[500.0, 1000.0]))
+
+
+def bsim4_stage(sp_bsim4v8):
+    """test/mna/vadistiller_integration.jl:758-775: sp_bsim4v8 (l = 100 nm, w = 1 um) with a 1 k drain
+    load on 1 V, gate at 0.5 V: the reference expects 0.9 < V(drain) < 1.0.  Gate bias swept."""
+    def f(ctx, p):
+        vdd = get_node(ctx, "vdd"); d = get_node(ctx, "drain"); g = get_node(ctx, "gate")
+        stamp(VoltageSource(1.0, name="Vdd"), ctx, vdd, 0)
+        stamp(VoltageSource(p.vg, name="Vg"), ctx, g, 0)
+        stamp(Resistor(1000.0, name="Rd"), ctx, vdd, d)
+        stamp(sp_bsim4v8(l=100e-9, w=1e-6, name="M1"), ctx, d, g, 0, 0)
+    return CircuitSweep(_B(f), Sweep(vg=[0.3, 0.5, 0.8, 1.0]))
+
+
 FIXTURES = {
     "mos1_corner": ("mos1", mos1_corner),
     "diode_chain": ("diode", diode_chain),
@@ -292,6 +355,11 @@ FIXTURES = {
     "mos1_dff": ("mos1", mos1_dff),
     "mos1_ring": ("mos1", mos1_ring),
     "mos1_ring_caps": ("mos1", lambda m: mos1_ring(m, caps=True)),
+    "bjt_ce": ("bjt", bjt_ce),
+    "jfet2_cs": ("jfet2", jfet2_cs),
+    "vdmos_cs": ("vdmos", vdmos_cs),
+    "inductor_rl": ("inductor", inductor_rl),
+    "bsim4_stage": ("bsim4v8", bsim4_stage),
 }
 
 
@@ -317,7 +385,7 @@ def lower_fixture(name, models=None):
 FIXTURE_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 # circuits whose kernel sets __graft_entry__.build() prebuilds (the GPU parity tests and bench.py)
 GPU_VA_FIXTURES = ["mos1_corner", "diode_chain", "diode_rs_cap", "mos1_inverter", "mos1_c3", "mos1_dff",
-                   "mos1_ring", "mos1_ring_caps"]
+                   "mos1_ring", "mos1_ring_caps", "bjt_ce", "jfet2_cs", "vdmos_cs", "inductor_rl"]
 
 
 def fixture_path(name: str) -> str:

@@ -419,6 +419,7 @@ typedef struct ora_va_api {
     void (*record_limit_w)(void *ctx, long l, double w);
     int (*detect_or_cached)(void *ctx, double v_branch, double q);
     int (*initjct)(void *ctx);
+    long (*alloc_current)(void *ctx);     /* branch current of a potential contribution, vasim.jl:2366, :3256-3278 */
 } ora_va_api;
 typedef void (*ora_va_fn)(const ora_va_api *, void *, const int *, const double *, const double *, long,
                           double, int);
@@ -427,9 +428,11 @@ static ora_va_fn (*g_va_table)(int) = NULL;
 void ora_set_va_table(void *table_fn) { g_va_table = (ora_va_fn (*)(int))table_fn; }
 
 #define VA_LIM_BASE (1L << 30)        /* handles <= -VA_LIM_BASE: limit unknown -(h) - VA_LIM_BASE */
+#define VA_CUR_BASE (1L << 40)        /* handles <= -VA_CUR_BASE: current unknown -(h) - VA_CUR_BASE */
 static mna_index va_index(long h)
 {
     if (h > 0) return ix_make(IX_NODE, h);
+    if (h <= -VA_CUR_BASE) return ix_make(IX_CURRENT, -h - VA_CUR_BASE);
     if (h <= -VA_LIM_BASE) return ix_make(IX_LIMIT, -h - VA_LIM_BASE);
     if (h < 0) return ix_make(IX_CHARGE, -h);
     return ix_make(IX_GROUND, 0);
@@ -460,9 +463,14 @@ static long va_alloc_limit(void *vc, long p, long n)
 }
 /* V_k = node_k == 0 ? 0.0 : x[node_k]; limit unknowns: vold = li <= length(x) ? x[li] : 0.0,
  * both tolerant of an x shorter than the system (vasim.jl:3123-3133)                  */
+static long va_alloc_current(void *vc)
+{
+    mna_index i = alloc_current((ora_ctx *)vc);
+    return -(VA_CUR_BASE + (long)i.k);
+}
 static double va_xval(void *vc, long node, const double *x, long nx)
 {
-    if (node <= -VA_LIM_BASE) {
+    if (node <= -VA_LIM_BASE) {       /* limit and current unknowns: resolved against the context */
         int64_t li = resolve_index((ora_ctx *)vc, va_index(node));
         if (x == NULL || nx == 0 || li > nx) return 0.0;
         return x[li - 1];
@@ -508,7 +516,7 @@ static int va_detect_or_cached(void *vc, double V, double Q)
 static int va_initjct(void *vc) { return ((ora_ctx *)vc)->initjct; }
 static const ora_va_api g_va_api = {va_alloc_internal_node, va_alloc_charge, va_alloc_limit, va_xval,
                                     va_stamp_G, va_stamp_C, va_stamp_b, va_record_limit_w,
-                                    va_detect_or_cached, va_initjct};
+                                    va_detect_or_cached, va_initjct, va_alloc_current};
 
 /* ------------------------------------------------------------------------- */
 /* the builder: one stamp! call per netlist row, in order                      */

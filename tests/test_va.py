@@ -108,6 +108,55 @@ module JunctionCap(p, n);
 endmodule""")                                   # va_mosfet.jl:465-484
 
 
+# ---- potential contributions, named branches, current probes (vasim.jl:2311-2395, :3225-3279,
+# :3630-3745).  RShort: a resistor chain whose middle section is either a resistor or -- rm == 0 -- a
+# zero-volt potential contribution between two INTERNAL nodes, which is not the alias idiom
+# (detect_short_circuits only aliases internal <-> port) and therefore carries a branch current.
+RShort = cb.va("""
+module RShort(a, c);
+    parameter real r1 = 1e3;
+    parameter real rm = 0.0;
+    parameter real r2 = 1e3;
+    inout a, c;
+    electrical a, c, m1, m2;
+    analog begin
+        if (rm == 0) begin
+            V(m1, m2) <+ 0;
+        end else begin
+            I(m1, m2) <+ V(m1, m2) / rm;
+        end
+        I(a, m1) <+ V(a, m1) / r1;
+        I(m2, c) <+ V(m2, c) / r2;
+    end
+endmodule""")
+# VRef: a bias-dependent potential contribution to ground, V(o) = gain * V(i) + vofs
+VRef = cb.va("""
+module VRef(i, o);
+    parameter real gain = 2.0;
+    parameter real vofs = 0.25;
+    inout i, o;
+    electrical i, o;
+    analog begin
+        V(o) <+ gain * V(i) * V(i) + vofs;
+    end
+endmodule""")
+# LBranch: potential contribution on a named branch with a current probe and ddt (the inductor idiom
+# of models/VADistillerModels.jl/va/inductor.va:61, :266-272) plus a series resistance
+LBranch = cb.va("""
+module LBranch(p, n);
+    parameter real L = 1e-3;
+    parameter real rs = 5.0;
+    inout p, n;
+    electrical p, n;
+    branch (p, n) br;
+    real flux;
+    analog begin
+        flux = L * I(br);
+        V(br) <+ rs * I(br) + ddt(flux);
+    end
+endmodule""")
+
+
 def B(f):
     def build(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
         ctx = MNAContext() if ctx is None else ctx
@@ -164,10 +213,13 @@ def test_parser_and_structure():
     assert SimpleMOS(K=2e-3).params == [2e-3, 0.5] and SimpleMOS(k=2e-3, vth=0.7).params == [2e-3, 0.7]
     with pytest.raises(cb.VAError):
         SimpleMOS(W=1.0)
-    for bad in ("module m(a); electrical a; analog V(a) <+ 1.0; endmodule",
-                "module m(a,b); electrical a,b; analog I(a,b) <+ $limit(V(a,b), 1, 2); endmodule"):
+    for bad in ("module m(a,b); electrical a,b; analog I(a,b) <+ $limit(V(a,b), 1, 2); endmodule",):
         with pytest.raises(cb.VAError):
             cb.va(bad)
+    # a potential contribution carries a branch-current unknown and the constraint row
+    # (vasim.jl:2362-2393): alloc_current!, G[p,I], G[I,p], G[I,k] for every module node, b[I]
+    vs = cb.va("module vsrc(a); electrical a; analog V(a) <+ 1.0; endmodule")
+    assert [p[0] for p in vs.stamp_plan()] == ["I", "G", "G", "G", "b"]
     src = SimpleMOS.emit_cuda()
     assert "va_stamp_SimpleMOS_" in src and "VA_G(0, 0, dI0);" in src and "VA_B(2, Ieq);" in src
 
@@ -284,6 +336,57 @@ def test_voltage_dependent_charge_uses_charge_state_formulation():
     assert b[q] == pytest.approx(CS * (Cj * v - (Cj + v * dC) * v), rel=1e-9)
 
 
+# ---- potential contributions: structure and known answers ------------------------------
+def _rshort(rm):
+    def f(ctx, params):
+        vin = get_node(ctx, "vin"); out = get_node(ctx, "out")
+        stamp(VoltageSource(3.0, name="V1"), ctx, vin, 0)
+        stamp(RShort(r1=1e3, rm=params.rm if "rm" in params else rm, r2=2e3, name="X1"), ctx, vin, out)
+        stamp(Resistor(3e3, name="RL"), ctx, out, 0)
+    return B(f)
+
+
+def _vref(ctx, params):
+    a = get_node(ctx, "a"); o = get_node(ctx, "o")
+    stamp(VoltageSource(params.va if "va" in params else 1.5, name="V1"), ctx, a, 0)
+    stamp(VRef(gain=2.0, vofs=0.25, name="X1"), ctx, a, o)
+    stamp(Resistor(1e3, name="RL"), ctx, o, 0)
+
+
+def _lbranch(ctx, params):
+    vin = get_node(ctx, "vin"); mid = get_node(ctx, "mid")
+    stamp(VoltageSource(5.0, name="V1"), ctx, vin, 0)
+    stamp(Resistor(params.r if "r" in params else 95.0, name="R1"), ctx, vin, mid)
+    stamp(LBranch(L=1e-3, rs=5.0, name="L1"), ctx, mid, 0)
+
+
+def test_potential_contributions_structure_and_dc():
+    # executed internal-to-internal short: one branch current, 2 + 2 + N stamps and a b stamp
+    lc0, nl0, x0, ok0 = oracle_dc(_rshort(0.0))
+    lc1, nl1, x1, ok1 = oracle_dc(_rshort(500.0))
+    assert ok0 and ok1
+    assert (lc0.n_nodes, lc0.n_currents) == (4, 2) and (lc1.n_nodes, lc1.n_currents) == (4, 1)
+    assert x0[lc0.index_of("out") - 1] == pytest.approx(3.0 * 3e3 / 6e3, rel=1e-12)
+    assert x1[lc1.index_of("out") - 1] == pytest.approx(3.0 * 3e3 / 6.5e3, rel=1e-12)
+    i_br = x0[lc0.n_nodes + 1]                            # the site's branch current carries the chain current
+    assert i_br == pytest.approx(3.0 / 6e3, rel=1e-12)
+    for lc, nl in ((lc0, nl0), (lc1, nl1)):               # host structure == the oracle's own run of the builder
+        coo = ora.Structure(nl, ora.make_spec(mode="dcop")).coo()
+        assert np.array_equal(coo["G_I"], lc.G_I) and np.array_equal(coo["G_J"], lc.G_J)
+        assert np.array_equal(coo["b_I"], lc.b_I)
+    # bias-dependent potential contribution: Newton on the linearised constraint row
+    lc, nl, x, ok = oracle_dc(B(_vref))
+    assert ok and x[lc.index_of("o") - 1] == pytest.approx(2.0 * 1.5 ** 2 + 0.25, rel=1e-12)
+    # named branch: DC short through rs (I = 5 / (95 + 5)), current probe = the branch unknown
+    lc, nl, x, ok = oracle_dc(B(_lbranch))
+    assert ok and lc.n_currents == 2
+    assert x[lc.index_of("mid") - 1] == pytest.approx(5.0 * 5.0 / 100.0, rel=1e-9)
+    assert [p[0] for p in LBranch.stamp_plan()] == ["I", "G", "G", "G", "G", "b", "C"]
+    assert RShort(rm=0.0).vsites(cb.MNASpec(), [1, 2, 3, 4]) == (True,)
+    assert RShort(rm=0.0).vsites(cb.MNASpec(), [1, 2, 3, 3]) == (False,)      # nodes aliased: nothing to stamp
+    assert RShort(rm=1.0).vsites(cb.MNASpec(), [1, 2, 3, 4]) == (False,)      # not executed
+
+
 # ---- GPU parity -----------------------------------------------------------------
 def _sweep_vs_oracle(cs, tran=None):
     params, P = cs.lane_params()
@@ -328,6 +431,9 @@ GPU_SWEEPS = {
                                                                         kn=[0.5e-3, 1e-3, 2e-3])),
     "capmos": lambda: cb.CircuitSweep(B(_capmos_stage), cb.ProductSweep(rg=[500.0, 1e3, 2e3], k=[0.5e-3, 1e-3])),
     "chain": lambda: cb.CircuitSweep(B(chain), cb.Sweep(dummy=[0.0, 1.0]), dummy=0.0),
+    "rshort": lambda: cb.CircuitSweep(_rshort(0.0), cb.Sweep(dummy=[0.0, 1.0, 2.0]), dummy=0.0),
+    "vref": lambda: cb.CircuitSweep(B(_vref), cb.Sweep(va=np.linspace(-1.0, 2.0, 7))),
+    "lbranch": lambda: cb.CircuitSweep(B(_lbranch), cb.Sweep(r=[45.0, 95.0, 195.0])),
 }
 
 
@@ -381,6 +487,25 @@ def test_gpu_va_chain_dc():
     assert np.allclose(x, xo, rtol=0.0, atol=1e-3)
     for name in ("na", "nb", "nc"):
         assert np.allclose(x[:, lc.index_of(name) - 1], 50.0, atol=2e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["rshort", "vref", "lbranch"])
+def test_gpu_va_potential_contributions(name):
+    """Branch-current unknowns of potential contributions (internal-to-internal short, bias-dependent
+    V(o) <+ f(V(i)), named branch with current probe and ddt): DC and a BE transient vs the oracle."""
+    cs = GPU_SWEEPS[name]()
+    lc, out = _sweep_vs_oracle(cs, tran=((0.0, 2e-5), 2e-7, "be", False))
+    x, xo, st, sto = out["dc"]
+    assert np.array_equal(st, sto) and (st == 0).all()
+    assert _close(x, xo), float(np.max(np.abs(x - xo)))
+    gpu, ref, r, ro, _ = out["tran"]
+    assert np.array_equal(r["status"], ro["status"]) and (r["status"] == 0).all()
+    assert _close(gpu, ref[:, :gpu.shape[1], :]), float(np.max(np.abs(gpu - ref[:, :gpu.shape[1], :])))
+    assert np.array_equal(r["newton_iters"], ro["newton_iters"])
+    if name == "vref":
+        va = np.linspace(-1.0, 2.0, 7)
+        assert np.allclose(x[:, lc.index_of("o") - 1], 2.0 * va ** 2 + 0.25, rtol=1e-12)
 
 
 @pytest.mark.gpu

@@ -18,7 +18,7 @@ HAVE_REF = os.path.isdir("/root/reference/models/VADistillerModels.jl/va")
 needs_ref = pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
 
 FIXTURE_NAMES = ["mos1_corner", "diode_chain", "diode_rs_cap", "mos1_inverter", "mos1_c3", "mos1_dff", "mos1_ring",
-                 "mos1_ring_caps"]
+                 "mos1_ring_caps", "bjt_ce", "jfet2_cs", "vdmos_cs", "inductor_rl"]
 
 
 GPU_FIXTURES = ["mos1_corner", "diode_chain", "mos1_inverter", "diode_rs_cap", "mos1_ring", "mos1_c3", "mos1_dff"]   # used by -m gpu tests
@@ -35,8 +35,8 @@ def oracle_of(lc):
 
 # ---- emitter over the reference's model files ---------------------------------------
 @needs_ref
-@pytest.mark.parametrize("name", ["resistor", "capacitor", "diode", "mos1", "mos2", "mos3", "mos6", "mos9",
-                                  "jfet1", "mes1"])
+@pytest.mark.parametrize("name", ["resistor", "capacitor", "inductor", "diode", "bjt", "mos1", "mos2", "mos3", "mos6",
+                                  "mos9", "jfet1", "jfet2", "mes1", "vdmos"])
 def test_vadistiller_model_emits_compilable_c(name, tmp_path):
     from cadnip_b200 import verilog_a
     import va_circuits
@@ -49,6 +49,66 @@ def test_vadistiller_model_emits_compilable_c(name, tmp_path):
     subprocess.run(["gcc", "-O0", "-fsyntax-only", "-Wall", "-Werror=implicit-function-declaration", str(c)],
                    check=True)
     assert f"va_stamp_{v.cname}" in verilog_a.cuda_header([v])
+
+
+def test_new_vadistiller_models_known_answers():
+    """sp_inductor / sp_bjt / sp_jfet2 / sp_vdmos -- the models that need potential contributions with
+    branch currents (internal-to-internal and to-ground shorts, named branches: bjt.va:739-753,
+    :1009-1013; jfet2.va:653-663; vdmos.va:105, :855-868, :1431; inductor.va:61, :272) -- in the
+    reference's own test circuits (test/mna/vadistiller_integration.jl:240-259, :390-416, :498-519,
+    :694-711) with the reference's expected ranges."""
+    want = {"inductor_rl": ("mid", -0.01, 0.01), "bjt_ce": ("collector", 0.0, 5.0),
+            "jfet2_cs": ("drain", 0.0, 10.0), "vdmos_cs": ("drain", 0.0, 10.0)}
+    for name, (node, lo, hi) in want.items():
+        lc = fixture(name)
+        xo, sto, ito = ora.sweep_dc(oracle_of(lc), ora.make_spec(mode="dcop"), lc.n)
+        v = xo[:, lc.index_of(node) - 1]
+        assert (sto == 0).all() and np.all(np.isfinite(xo)), name
+        assert np.all((v > lo) & (v < hi)) or name == "vdmos_cs", (name, v)
+    lc = fixture("bjt_ce")
+    # 8 nodes (4 user + c_int, sub_con, xf1, xf2: the other three internals alias their port), 2 source
+    # currents + 4 branch currents of the executed shorts, 3 $limit unknowns (bjt.va:1040-1042)
+    assert (lc.n_nodes, lc.n_currents, lc.n_charges, lc.n_limits) == (8, 6, 0, 3)
+    xo, _, _ = ora.sweep_dc(oracle_of(lc), ora.make_spec(mode="dcop"), lc.n)
+    vc = xo[:, lc.index_of("collector") - 1].reshape(2, 3)          # [bf][vb]
+    assert np.all(np.diff(vc, axis=1) < 0) and np.all(vc[1] < vc[0])   # more base drive / more gain: lower collector
+    assert np.allclose(xo[:, lc.index_of("Q1_sp_bjt_c_int") - 1], xo[:, lc.index_of("collector") - 1], atol=1e-12)
+    lc = fixture("vdmos_cs")
+    vd = ora.sweep_dc(oracle_of(lc), ora.make_spec(mode="dcop"), lc.n)[0][:, lc.index_of("drain") - 1]
+    assert vd[0] == pytest.approx(10.0, abs=1e-6) and 0.0 < vd[2] < 1.0 and np.all(np.diff(vd) < 0)   # off below vto = 2 V
+
+
+@needs_ref
+def test_sp_bsim4v8_and_bsim3v3_known_answers():
+    """The two large VADistiller MOSFETs through the emitter and the oracle: string parameter
+    (`version`), named noise branches with current probes, 9 $limit branches, internal-to-internal
+    shorts (bsim4v8.va:98-100, :163, :4539-4574, :5992-6000, :9836-9845).  Known answer of the reference:
+    0.9 < V(drain) < 1.0 for l = 100 nm, w = 1 um, 1 k load on 1 V, gate at 0.5 V
+    (test/mna/vadistiller_integration.jl:758-775); sp_bsim3v3: 0 < V(drain) < 1.8 (:718-741)."""
+    from cadnip_b200 import verilog_a
+    import va_circuits
+    from cadnip_b200 import MNAContext, ZERO_VECTOR, get_node, stamp, VoltageSource, Resistor
+    for fname, vdd_v, vg_v, lo, hi in (("bsim4v8", 1.0, 0.5, 0.9, 1.0), ("bsim3v3", 1.8, 1.0, 0.0, 1.8)):
+        m = verilog_a.load_va(va_circuits.VA_DIR + fname + ".va")
+
+        def build(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
+            ctx = MNAContext() if ctx is None else ctx
+            vdd = get_node(ctx, "vdd"); d = get_node(ctx, "drain"); g = get_node(ctx, "gate")
+            stamp(VoltageSource(vdd_v, name="Vdd"), ctx, vdd, 0)
+            stamp(VoltageSource(vg_v, name="Vg"), ctx, g, 0)
+            stamp(Resistor(1000.0, name="Rd"), ctx, vdd, d)
+            stamp(m(l=100e-9, w=1e-6, name="M1"), ctx, d, g, 0, 0)
+            return ctx
+        lc = cb.lower_circuit(cb.MNACircuit(build))
+        nl = oracle_of(lc)
+        coo = ora.Structure(nl, ora.make_spec(mode="dcop")).coo()
+        assert np.array_equal(coo["G_I"], lc.G_I) and np.array_equal(coo["G_J"], lc.G_J)      # host == oracle builder
+        assert np.array_equal(coo["C_I"], lc.C_I) and np.array_equal(coo["b_I"], lc.b_I)
+        x, ok, it = ora.solve_dc(nl, ora.make_spec(mode="dcop"))
+        assert ok and lo < x[lc.index_of("drain") - 1] < hi, (fname, x[lc.index_of("drain") - 1])
+        if fname == "bsim4v8":
+            assert lc.n_limits == 9 and m.mod["sparams"] == {"version": "4.8.3"}
+            assert x[lc.index_of("drain") - 1] == pytest.approx(0.9066, abs=2e-4)
 
 
 @needs_ref
@@ -272,7 +332,8 @@ def _close(a, b, rtol=1e-9, atol=1e-12):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["mos1_corner", "diode_chain", "mos1_inverter"])
+@pytest.mark.parametrize("name", ["mos1_corner", "diode_chain", "mos1_inverter", "bjt_ce", "jfet2_cs", "vdmos_cs",
+                                  "inductor_rl"])
 def test_gpu_va_models_dc(name):
     lc = fixture(name)
     nl = oracle_of(lc)
@@ -292,6 +353,10 @@ def test_gpu_va_models_dc(name):
     ("mos1_inverter", (0.0, 10e-9), 1e-11, "trap", False),
     ("mos1_inverter", (0.0, 10e-9), 1e-11, "be", True),
     ("diode_rs_cap", (0.0, 10e-9), 1e-11, "trap", True),
+    ("bjt_ce", (0.0, 2e-6), 1e-8, "be", False),
+    ("bjt_ce", (0.0, 2e-6), 1e-8, "trap", True),
+    ("vdmos_cs", (0.0, 1e-7), 1e-9, "be", False),
+    ("inductor_rl", (0.0, 1e-5), 1e-7, "trap", False),
 ])
 def test_gpu_va_models_transient(name, tspan, dt, method, spec):
     lc = fixture(name)
