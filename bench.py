@@ -57,6 +57,14 @@ WORKLOADS = {
                     "sp_mos1 Verilog-A model, synthetic 5 V card, 5 fF parasitic per net): 16384 points (4 corners x "
                     "4096 draws), DC op (PCNR + fallbacks) + adaptive trapezoidal/LTE transient (0, 6e-7); "
                     "table-driven kernels, one lane per warp"),
+    "c5": dict(tspan=(0.0, 2e-9), dt=1e-12, save_every=1, save="p0", steps=0, limit=True, adaptive=True,
+               reltol=float(os.environ.get("CB200_C5_RELTOL", "1e-5")), lte_abstol=1e-6,
+               max_points=int(os.environ.get("CB200_C5_MAXPOINTS", "4096")), fixture="mos1_c6288", lanes=1,
+               text="C5 ISCAS c6288 16x16 multiplier (benchmarks/vacask/c6288/cedarsim: 10112 FETs, 32 pulse drivers), "
+                    "single large circuit on 1 GPU; the emitter does not read PSP103 yet -> FALLBACK tier: sp_mos1 cards "
+                    "(vto +-0.4 V, kp 200u/100u, 1 fF per net), n = 45604 (reference with PSP103: 212228), nnz 158870; DC op "
+                    "(PCNR + fallbacks) + adaptive trapezoidal/LTE transient (0, 2e-9), lte abstol 1e-6; sparse symbolic "
+                    "analysis (matching + Markowitz), level-scheduled LU, one lane per warp"),
 }
 W = WORKLOADS["c3"]
 TSPAN, DT, SAVE_EVERY, WORKLOAD = W["tspan"], W["dt"], W["save_every"], W["text"]
@@ -134,6 +142,10 @@ def build_sweep(args):
     if args.workload == "c4":
         lc = workloads.load_workload(W["fixture"])
         lc.lane_soa, lc.P = workloads.c4_lanes(lc, args.lanes)
+        return cb, lc, lc.P
+    if args.workload == "c5":
+        lc = workloads.load_fixture(W["fixture"]) if os.path.exists(workloads.fixture_path(W["fixture"])) \
+            else workloads.load_workload(W["fixture"])
         return cb, lc, lc.P
     if args.workload in ("c3", "c1"):
         lc = workloads.load_workload(W["fixture"])
@@ -265,6 +277,12 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     cb, lc, P = build_sweep(args)
+    if args.workload == "c5":
+        # a single large circuit does not shard ("1 GPU, replicas only"); the CPU oracle's
+        # linear solvers (dense O(n^3), dense-bookkeeping sparse analysis) do not reach n = 45604
+        if world > 1:
+            raise SystemExit("bench.py: C5 is a single large circuit on 1 GPU (replicas only); run with --gpus 1")
+        args.no_cpu_baseline = True
     # strong scaling: the ONE sweep is block-partitioned over the ranks in sweep order
     sl = distributed.shard_slice(P, rank, world)
     Pl = sl.stop - sl.start
@@ -519,6 +537,21 @@ def run_b200(args):
                                               f"OpenMP over lanes, {secs:.1f} s"}
         if args.workload == "c1" and world == 1:
             line["c1"] = c1_eval_times(cb, backend)
+        if args.workload == "c5":
+            ms_iter = 1e3 * wall / args.steps / max(iters_per_step, 1)
+            line["c5"] = {"n": lc.n, "nnz_J": nnz_j, "nnz_LU": int(nnz_lu), "timepoints": int(first_count[0]),
+                          "newton_iters": iters_per_step, "ms_per_newton_iter": ms_iter,
+                          "reference_published": {"per_newton_iter_s": {"rebuild": 0.480, "residual": 0.657, "jacobian": 1.017,
+                                                                         "klu_factor_solve": 2.72},
+                                                  "n": 212228, "nnz_J": 2452148, "model": "PSP103",
+                                                  "timepoints_reltol_1e-5": 118,
+                                                  "source": "doc/c6288_bottleneck_findings.md:87-91,111-118; "
+                                                            "benchmarks/vacask/c6288/cedarsim/runme.jl:60-66"},
+                          "note": "same topology, different device model (sp_mos1 fallback) and therefore a 4.7x smaller "
+                                  "system: the per-iteration times are not like for like"}
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                    "sample": "not run: the oracle's linear solvers do not reach n = 45604; the DC point is "
+                                              "checked through the oracle's own rebuild (tests/test_va_models.py)"}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)

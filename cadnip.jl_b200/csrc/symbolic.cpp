@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <numeric>
 
 #include "cb200_internal.h"
@@ -93,6 +94,284 @@ std::string build_structure(const cb200_desc &d, Structure &s)
 }
 
 // ---------------------------------------------------------------------------
+// analyze_lu_sparse: the same job as the dense-bookkeeping analysis below for circuits of any
+// size (c6288-class: n ~ 1e5, nnz ~ 1e6).  KLU's recipe restated for a STATIC pivot sequence:
+//   1. zero-free diagonal: a row <-> column matching that prefers the (strong) diagonal and pairs
+//      the structurally-zero-diagonal rows (voltage-source / branch-current rows) by augmenting
+//      paths over entries that pass the magnitude threshold (MC21-style);
+//   2. Markowitz minimum (r-1)(c-1) over the matched entries with a lazy heap, sparse rows kept as
+//      sorted (column, magnitude) lists and merged at every elimination -- ordering and symbolic
+//      fill in one pass, with the magnitude bound |a_ij| += |l| |a_pj| carried along so that a
+//      matched entry that has become weak against its column (threshold 1e-3, as below) is replaced
+//      by the column's largest entry (off-diagonal pivot, rows re-matched);
+//   3. the factor pattern in pivot coordinates, slots, update targets, scatter map.
+// Same LuSchedule as the dense path; the level schedule and every kernel are unchanged.
+// ---------------------------------------------------------------------------
+namespace {
+struct SpEntry { int col; double mag; };
+typedef std::vector<SpEntry> SpRow;
+
+static int sp_find(const SpRow &r, int col)
+{
+    int lo = 0, hi = (int)r.size();
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (r[mid].col < col) lo = mid + 1; else hi = mid; }
+    return (lo < (int)r.size() && r[lo].col == col) ? lo : -1;
+}
+}  // namespace
+
+static std::string analyze_lu_sparse(const Structure &s, const std::vector<double> &absJ, double threshold,
+                                     LuSchedule &out)
+{
+    const int n = s.n;
+    std::vector<SpRow> rows(n);
+    std::vector<std::vector<int>> cols(n);          // rows with an entry in the column (may hold finished rows)
+    {
+        std::vector<int> cnt(n, 0);
+        for (int64_t q = 0; q < s.nnz; q++) cnt[s.nz_row[q]]++;
+        for (int i = 0; i < n; i++) rows[i].reserve(cnt[i] + 4);
+    }
+    for (int j = 0; j < n; j++)                      // CSC order: every row list ends up sorted by column
+        for (int q = s.colptr[j]; q < s.colptr[j + 1]; q++) {
+            const double m = std::isfinite(absJ[q]) ? absJ[q] : 0.0;
+            rows[s.rowval[q]].push_back({j, m});
+            cols[j].push_back(s.rowval[q]);
+        }
+    std::vector<double> colmax0(n, 0.0);
+    for (int i = 0; i < n; i++) for (const SpEntry &e : rows[i]) colmax0[e.col] = std::max(colmax0[e.col], e.mag);
+
+    // ---- 1. matching: row_col[i] = column paired with row i
+    std::vector<int> row_col(n, -1), col_row(n, -1);
+    for (int i = 0; i < n; i++) {
+        const int d = sp_find(rows[i], i);
+        if (d >= 0 && rows[i][d].mag > 0.0 && rows[i][d].mag >= threshold * colmax0[i]) { row_col[i] = i; col_row[i] = i; }
+    }
+    {
+        std::vector<int> seen(n, -1), fr_row, fr_k, via;
+        for (int pass = 0; pass < 2; pass++) {       // pass 0: strong entries only, pass 1: any numerically present entry
+            for (int r0 = 0; r0 < n; r0++) {
+                if (row_col[r0] >= 0) continue;
+                const int stamp = pass * n + r0;
+                fr_row.assign(1, r0); fr_k.assign(1, 0); via.clear();
+                seen[r0] = stamp;
+                bool found = false;
+                while (!fr_row.empty() && !found) {   // iterative depth-first search for an augmenting path
+                    const int r = fr_row.back();
+                    const size_t top = fr_k.size() - 1;
+                    bool advanced = false;
+                    if (fr_k[top] == 0) {             // cheap assignment first: a free column in this very row
+                        for (const SpEntry &e : rows[r]) {
+                            if (!(e.mag > 0.0) || col_row[e.col] >= 0) continue;
+                            if (pass == 0 && e.mag < threshold * colmax0[e.col]) continue;
+                            via.push_back(e.col);
+                            for (size_t t = 0; t < fr_row.size(); t++) { row_col[fr_row[t]] = via[t]; col_row[via[t]] = fr_row[t]; }
+                            found = true;
+                            break;
+                        }
+                        if (found) break;
+                    }
+                    for (int k = fr_k[top]; k < (int)rows[r].size(); k++) {
+                        const SpEntry &e = rows[r][k];
+                        if (!(e.mag > 0.0)) continue;
+                        if (pass == 0 && e.mag < threshold * colmax0[e.col]) continue;
+                        const int owner = col_row[e.col];
+                        if (owner < 0) {              // free column: shift every row of the path to its `via` column
+                            via.push_back(e.col);
+                            for (size_t t = 0; t < fr_row.size(); t++) { row_col[fr_row[t]] = via[t]; col_row[via[t]] = fr_row[t]; }
+                            found = true;
+                            break;
+                        }
+                        if (seen[owner] == stamp) continue;
+                        seen[owner] = stamp;
+                        fr_k[top] = k + 1;
+                        via.push_back(e.col);
+                        fr_row.push_back(owner); fr_k.push_back(0);
+                        advanced = true;
+                        break;
+                    }
+                    if (!found && !advanced) {
+                        fr_row.pop_back(); fr_k.pop_back();
+                        if (!via.empty()) via.pop_back();
+                    }
+                }
+            }
+        }
+    }
+    for (int i = 0; i < n; i++)
+        if (row_col[i] < 0) return "analyze_lu: matrix is structurally or numerically singular at the probe points (row " +
+                                   std::to_string(i) + " cannot be paired with a column)";
+
+    // ---- 2. Markowitz elimination over the matched entries
+    std::vector<uint8_t> row_done(n, 0), col_done(n, 0);
+    std::vector<int> ccount(n, 0), ver(n, 0);
+    for (int j = 0; j < n; j++) ccount[j] = (int)cols[j].size();
+    typedef std::pair<int64_t, std::pair<int, int>> HeapItem;     // (cost, (row, version)), min-heap
+    std::vector<HeapItem> heap;
+    auto cost_of = [&](int i) { return (int64_t)((int)rows[i].size() - 1) * (int64_t)(ccount[row_col[i]] - 1); };
+    auto push = [&](int i) {
+        heap.push_back({cost_of(i), {i, ++ver[i]}});
+        std::push_heap(heap.begin(), heap.end(), std::greater<HeapItem>());
+    };
+    heap.reserve((size_t)n * 4);
+    for (int i = 0; i < n; i++) { heap.push_back({cost_of(i), {i, ver[i]}}); }
+    std::make_heap(heap.begin(), heap.end(), std::greater<HeapItem>());
+
+    out.rowperm.assign(n, -1); out.colperm.assign(n, -1);
+    std::vector<std::vector<int>> Ucols(n), Lrows(n);            // per pivot, ORIGINAL indices
+    SpRow merged;
+    int n_offdiag = 0;
+    for (int k = 0; k < n; k++) {
+        int pr = -1;
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end(), std::greater<HeapItem>());
+            const HeapItem it = heap.back(); heap.pop_back();
+            const int i = it.second.first;
+            if (row_done[i] || it.second.second != ver[i]) continue;
+            if (it.first != cost_of(i)) { push(i); continue; }
+            pr = i; break;
+        }
+        if (pr < 0) return "analyze_lu: internal error (empty pivot heap)";
+        int pc = row_col[pr];
+        // threshold test of the matched entry against its column's largest active magnitude
+        double cmax = 0.0, best = 0.0; int best_row = -1;
+        {
+            std::vector<int> &cl = cols[pc];
+            size_t w = 0;
+            for (size_t t = 0; t < cl.size(); t++) {
+                const int r = cl[t];
+                if (row_done[r]) continue;
+                cl[w++] = r;
+                const int q = sp_find(rows[r], pc);
+                const double m = q >= 0 ? rows[r][q].mag : 0.0;
+                if (m > cmax) cmax = m;
+                if (m > best) { best = m; best_row = r; }
+            }
+            cl.resize(w);
+        }
+        if (!(cmax > 0.0)) return "analyze_lu: matrix is singular at the probe points (no admissible pivot at step " +
+                                  std::to_string(k) + ")";
+        const int qd = sp_find(rows[pr], pc);
+        const double mpiv = qd >= 0 ? rows[pr][qd].mag : 0.0;
+        if (!(mpiv > 0.0) || mpiv < threshold * cmax) {
+            // off-diagonal pivot: the column's largest entry; the two orphans are paired with each other
+            const int r2 = best_row, c2 = row_col[r2];
+            n_offdiag++;
+            if (getenv("CB200_ANALYZE_DEBUG") && n_offdiag <= 5)
+                fprintf(stderr, "  off-diagonal pivot at step %d: row %d col %d matched mag %g colmax %g -> row %d (its col %d)\n",
+                        k, pr, pc, mpiv, cmax, r2, c2);
+            row_col[pr] = c2; col_row[c2] = pr;
+            row_col[r2] = pc; col_row[pc] = r2;
+            push(pr);
+            pr = r2;
+        }
+        out.rowperm[k] = pr; out.colperm[k] = pc;
+        row_done[pr] = 1; col_done[pc] = 1;
+        const SpRow prow = rows[pr];                                 // copy: the pivot row (U row k + diagonal)
+        const int qp = sp_find(prow, pc);
+        const double piv = prow[qp].mag;
+        for (const SpEntry &e : prow) if (e.col != pc) { Ucols[k].push_back(e.col); ccount[e.col]--; }
+        // eliminate column pc from every other active row
+        for (int r : cols[pc]) {
+            if (row_done[r]) continue;
+            SpRow &rr = rows[r];
+            const int q = sp_find(rr, pc);
+            if (q < 0) continue;
+            Lrows[k].push_back(r);
+            const double l = rr[q].mag / piv;
+            merged.clear();
+            merged.reserve(rr.size() + prow.size());
+            size_t a = 0, b = 0;
+            while (a < rr.size() || b < prow.size()) {
+                if (b >= prow.size() || (a < rr.size() && rr[a].col < prow[b].col)) {
+                    if (rr[a].col != pc) merged.push_back(rr[a]);
+                    a++;
+                } else if (a >= rr.size() || prow[b].col < rr[a].col) {
+                    if (prow[b].col != pc) {                         // fill
+                        merged.push_back({prow[b].col, l * prow[b].mag});
+                        cols[prow[b].col].push_back(r);
+                        ccount[prow[b].col]++;
+                    }
+                    b++;
+                } else {
+                    if (rr[a].col != pc) merged.push_back({rr[a].col, rr[a].mag + l * prow[b].mag});
+                    a++; b++;
+                }
+            }
+            rr.swap(merged);
+            push(r);
+        }
+        for (int c : Ucols[k]) { const int r = col_row[c]; if (r >= 0 && !row_done[r]) push(r); }
+        std::vector<int>().swap(cols[pc]);
+        SpRow().swap(rows[pr]);
+    }
+
+    if (getenv("CB200_ANALYZE_DEBUG")) {
+        int64_t nl = 0, nu = 0;
+        for (int k = 0; k < n; k++) { nl += (int64_t)Lrows[k].size(); nu += (int64_t)Ucols[k].size(); }
+        fprintf(stderr, "analyze_lu_sparse: n %d nnz %lld L %lld U %lld off-diagonal pivots %d\n", n, (long long)s.nnz,
+                (long long)nl, (long long)nu, n_offdiag);
+    }
+    // ---- 3. factor pattern in pivot coordinates
+    std::vector<int> rinv(n), cinv(n);
+    for (int k = 0; k < n; k++) { rinv[out.rowperm[k]] = k; cinv[out.colperm[k]] = k; }
+    out.diag_slot.resize(n);
+    out.Uptr.assign(n + 1, 0);
+    out.Lptr.assign(n + 1, 0);
+    int64_t nlu = 0;
+    for (int k = 0; k < n; k++) {
+        for (int &c : Ucols[k]) c = cinv[c];
+        for (int &r : Lrows[k]) r = rinv[r];
+        std::sort(Ucols[k].begin(), Ucols[k].end());
+        std::sort(Lrows[k].begin(), Lrows[k].end());
+        out.diag_slot[k] = (int)nlu++;
+        for (int b : Ucols[k]) { out.U_slot.push_back((int)nlu++); out.U_col.push_back(b); }
+        out.Uptr[k + 1] = (int)out.U_slot.size();
+        for (int a : Lrows[k]) { out.L_slot.push_back((int)nlu++); out.L_row.push_back(a); }
+        out.Lptr[k + 1] = (int)out.L_slot.size();
+        if (nlu > (int64_t)2000000000) return "analyze_lu: factor too large for 32-bit slots";
+    }
+    out.nlu = nlu;
+    auto slot_of = [&](int a, int b) -> int {                        // (a, b) in pivot coordinates
+        if (a == b) return out.diag_slot[a];
+        if (a < b) {
+            const int *lo = &out.U_col[0] + out.Uptr[a], *hi = &out.U_col[0] + out.Uptr[a + 1];
+            const int *it = std::lower_bound(lo, hi, b);
+            return (it != hi && *it == b) ? out.U_slot[it - &out.U_col[0]] : -1;
+        }
+        const int *lo = &out.L_row[0] + out.Lptr[b], *hi = &out.L_row[0] + out.Lptr[b + 1];
+        const int *it = std::lower_bound(lo, hi, a);
+        return (it != hi && *it == a) ? out.L_slot[it - &out.L_row[0]] : -1;
+    };
+    out.tgt_ptr.assign(n + 1, 0);
+    int64_t ntgt = 0;
+    for (int k = 0; k < n; k++) ntgt += (int64_t)(out.Lptr[k + 1] - out.Lptr[k]) * (out.Uptr[k + 1] - out.Uptr[k]);
+    if (ntgt > (int64_t)2000000000) return "analyze_lu: update list too large";
+    out.tgt.reserve((size_t)ntgt);
+    for (int k = 0; k < n; k++) {
+        const int nL = out.Lptr[k + 1] - out.Lptr[k], nU = out.Uptr[k + 1] - out.Uptr[k];
+        for (int e = 0; e < nL; e++) {
+            const int a = out.L_row[out.Lptr[k] + e];
+            for (int q = 0; q < nU; q++) {
+                const int t = slot_of(a, out.U_col[out.Uptr[k] + q]);
+                if (t < 0) return "analyze_lu: internal error (missing fill slot)";
+                out.tgt.push_back(t);
+            }
+        }
+        out.tgt_ptr[k + 1] = (int)out.tgt.size();
+        out.flops += (int64_t)nL * nU;
+    }
+    out.jmap.resize(s.nnz);
+    std::vector<uint8_t> has_src((size_t)nlu, 0);
+    for (int64_t q = 0; q < s.nnz; q++) {
+        const int t = slot_of(rinv[s.nz_row[q]], cinv[s.nz_col[q]]);
+        if (t < 0) return "analyze_lu: internal error (pattern entry without slot)";
+        out.jmap[q] = t; has_src[t] = 1;
+    }
+    for (int64_t t = 0; t < nlu; t++) if (!has_src[t]) out.fill_slots.push_back((int)t);
+    out.valid = true;
+    return "";
+}
+
+// ---------------------------------------------------------------------------
 // analyze_lu: threshold Markowitz pivoting on nominal magnitudes, symbolic fill,
 // elimination schedule.  The pivot sequence is fixed for every lane and every
 // Newton iteration (klu_refactor-style reuse); the numeric kernels flag lanes whose
@@ -110,8 +389,8 @@ std::string analyze_lu(const Structure &s, const std::vector<double> &absJ, doub
     out = LuSchedule();
     out.n = n;
     if (n == 0) { out.valid = true; return ""; }
-    if (n > kDenseLimit) return "analyze_lu: n exceeds the small/medium-circuit symbolic path";
     if ((int64_t)absJ.size() != s.nnz) return "analyze_lu: magnitude array has wrong length";
+    if (n > kDenseLimit || getenv("CB200_SPARSE_ANALYZE")) return analyze_lu_sparse(s, absJ, threshold, out);
 
     // pat: 0 absent, 1 structural; mag: nominal magnitude
     std::vector<uint8_t> pat((size_t)n * n, 0);

@@ -2199,6 +2199,7 @@ class VAModel:
         self.param_defaults = [p[1] for p in m["params"]]
         self.uid = hashlib.sha256(source.encode()).hexdigest()[:12]
         self.collapses, self.collapse_sites = _find_collapses(m)
+        self._host_cache: Dict[Tuple, Any] = {}            # per parameter set: executed sites, charge-free flag
         self._variants: Dict[Tuple, VAVariant] = {}
         self._default: Optional[VAVariant] = None
         self.default                                      # emit once now: unsupported constructs fail here
@@ -2337,8 +2338,6 @@ class VAInstance:
         """internal node -> port it aliases (conditions evaluated at allocation time)."""
         out = {}
         if self.model.collapses:
-            it = self._interp(spec)
-            it.init_vars()
             for node, (ext, cond) in self.model.collapses.items():
                 vals = self.values
                 for name in _names_in(cond):
@@ -2347,8 +2346,17 @@ class VAInstance:
                         from .lowering import StructuralSweepError
                         raise StructuralSweepError(
                             f"{self.model.name}: node-collapse condition depends on swept parameter {name!r}")
-                if it.ev(cond)[0] != 0.0:
-                    out[node] = ext
+            key = ("collapsed", self._param_key(spec))
+            hit = self.model._host_cache.get(key)
+            if hit is None:
+                it = self._interp(spec)
+                it.init_vars()
+                hit = {}
+                for node, (ext, cond) in self.model.collapses.items():
+                    if it.ev(cond)[0] != 0.0:
+                        hit[node] = ext
+                self.model._host_cache[key] = hit
+            out = dict(hit)
         return out
 
     def vsites(self, spec, node_of_slot: List[int]) -> Tuple[bool, ...]:
@@ -2360,14 +2368,54 @@ class VAInstance:
         if not sites:
             return ()
         nodes = self.model.nodes
-        it = self._interp(spec)
-        it.run({name: 0.0 for name in nodes}, {})
+        # which statements execute depends on the parameter values only: one interpreter run per
+        # distinct parameter set of the model (a 10 000-FET netlist has a handful)
+        key = ("vexec", self._param_key(spec))
+        executed = self.model._host_cache.get(key)
+        if executed is None:
+            it = self._interp(spec)
+            it.run({name: 0.0 for name in nodes}, {})
+            executed = self.model._host_cache[key] = frozenset(it.vexec)
         out = []
         for j, (a, b, br) in enumerate(sites):
             pa = node_of_slot[nodes.index(a)]
             pb = node_of_slot[nodes.index(b)] if b is not None else 0
-            out.append(j in it.vexec and pa != pb)
+            out.append(j in executed and pa != pb)
         return tuple(out)
+
+    def _param_key(self, spec) -> Tuple:
+        memo = self.__dict__.setdefault("_pk_memo", {})
+        hit = memo.get(id(spec))
+        if hit is not None:
+            return hit
+        memo[id(spec)] = key = self._param_key_uncached(spec)
+        return key
+
+    def _param_key_uncached(self, spec) -> Tuple:
+        vals = tuple((k, _lane0(v)) for k, v in sorted(self.values.items()))
+        sim = tuple((f, getattr(spec, f)) for f in _SPEC_FIELDS if hasattr(spec, f))
+        return (vals, tuple(sorted(self.given)), sim, getattr(spec, "mode", "dcop"), _lane0(self.mfactor))
+
+    def _charge_free(self, spec, var) -> bool:
+        """True when every reactive branch of this parameter set carries the charge 0.0 at three
+        random bias points (e.g. sp_mos1 without capacitance parameters: Q = 0 * f(V)).  Such an
+        instance cannot be voltage-dependent under the reference's Q/V probe (contrib.jl:214-257),
+        so the per-instance interpreter run of the detection passes is skipped."""
+        key = ("qfree", self._param_key(spec), tuple(var.vexec))
+        hit = self.model._host_cache.get(key)
+        if hit is None:
+            rng = np.random.default_rng(0xC0FFEE)
+            hit = True
+            for _ in range(3):
+                volt = {name: float(rng.uniform(-1.0, 1.0)) for name in var.nodes}
+                vold = {k: float(rng.uniform(-1.0, 1.0)) for k in var.lim_branches}
+                it = self._interp(spec)
+                it.run(volt, vold)
+                if any(it.Q.get(k, 0.0) != 0.0 for bi, k in enumerate(var.branches) if var.reactive[bi]):
+                    hit = False
+                    break
+            self.model._host_cache[key] = hit
+        return hit
 
     def detect_vdep(self, spec, ctx, x, node_of_slot: List[int]) -> Tuple[bool, ...]:
         """One detection pass of this instance (the reference's generated stamp! calls
@@ -2382,6 +2430,15 @@ class VAInstance:
         def xval(i):
             return float(xs[i - 1]) if 0 < i <= len(xs) else 0.0
         volt = {name: xval(cn) for name, cn in zip(var.nodes, node_of_slot)}
+        if self._charge_free(spec, var):
+            flags = []
+            for bi, key in enumerate(var.branches):
+                if not var.reactive[bi]:
+                    flags.append(False)
+                    continue
+                v = volt[key[0]] - (volt[key[1]] if key[1] is not None else 0.0)
+                flags.append(ctx.detect_or_cached(v, 0.0))
+            return tuple(flags)
         # limit unknowns of THIS instance are allocated next, in order (vasim.jl:3121-3133):
         # vold = li <= length(x) ? x[li] : 0.0 with li resolved against the context so far
         vold = {}

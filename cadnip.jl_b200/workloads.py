@@ -346,6 +346,100 @@ def bsim4_stage(sp_bsim4v8):
     return CircuitSweep(_B(f), Sweep(vg=[0.3, 0.5, 0.8, 1.0]))
 
 
+C6288_DIR = "/root/reference/benchmarks/vacask/c6288/cedarsim/"
+
+
+def c6288_netlist(path=C6288_DIR):
+    """Flat device list of the ISCAS c6288 16x16 multiplier deck (SURVEY 8d config C5:
+    benchmarks/vacask/c6288/cedarsim/{runme.sp, multiplier.inc}): (fets, drivers) with
+    fets = [(name, d, g, s, b, type +1/-1, w, l)] -- the not / nor / and gate sub-circuits expanded,
+    `.global vdd vss` honoured -- and drivers = [node] for the 32 `v01` pulse sources (0 -> 1.2 V,
+    td = tr = 0.1 ns, 1 ohm series resistor)."""
+    subckts, cur = {}, None
+    top = []
+    for fname in ("multiplier.inc", "runme.sp"):
+        for ln in _spice_lines(path + fname)[(1 if fname == "runme.sp" else 0):]:
+            f = ln.split()
+            key = f[0].lower()
+            if key == ".subckt":
+                cur = dict(name=f[1].lower(), ports=[x for x in f[2:] if "=" not in x], body=[])
+                continue
+            if key == ".ends":
+                subckts[cur["name"]] = cur
+                cur = None
+                continue
+            if key.startswith("."):
+                continue
+            (cur["body"] if cur is not None else top).append(f)
+    glob = {"vdd", "vss", "0"}
+    fets, drivers = [], []
+
+    def expand(inst, conn, prefix):
+        sc = subckts[inst]
+        env = dict(zip(sc["ports"], conn))
+        for f in sc["body"]:
+            name = prefix + f[0]
+            args = [x for x in f[1:] if "=" not in x]
+            kw = dict(x.split("=") for x in f[1:] if "=" in x)
+            if f[0][0] in "xX":
+                sub = args[-1].lower()
+                nodes = [env.get(a, a if a.lower() in glob else prefix + a) for a in args[:-1]]
+                if sub in ("nmos", "pmos"):
+                    def num(v):
+                        v = v.lower()
+                        return float(v[:-1]) * 1e-6 if v.endswith("u") else float(v)
+                    fets.append((name, nodes[0], nodes[1], nodes[2], nodes[3], 1 if sub == "nmos" else -1,
+                                 num(kw.get("w", "1u")), num(kw.get("l", "0.2u"))))
+                else:
+                    expand(sub, nodes, name + ".")
+    for f in top:
+        if f[0][0] in "xX":
+            args = [x for x in f[1:] if "=" not in x]
+            sub = args[-1].lower()
+            if sub == "v01":
+                drivers.append(args[0])
+            else:
+                expand(sub, args[:-1], f[0] + ".")
+    assert len(drivers) == 32, len(drivers)
+    return fets, drivers
+
+
+def mos1_c6288(sp_mos1, n_fets=None):
+    """C5 on the FALLBACK tier: the c6288 multiplier with its 10 112 PSP103 FETs replaced by sp_mos1
+    cards (vto = +-0.4 V for the 1.2 V supply, kp = 200u / 100u, 1 fF per net to ground standing in
+    for the device capacitances PSP103 would bring) -- the emitter does not read PSP103 yet, so this
+    exercises the LARGE-circuit path (sparse symbolic analysis, one lane on many threads) on the
+    reference's own topology, not its device physics.  n_fets: keep only the first gates (tests)."""
+    fets, drivers = c6288_netlist()
+    if n_fets:
+        fets = fets[:n_fets]
+    nets = []
+    seen = set()
+    for _, d, g, s_, b, *_ in fets:
+        for x in (d, g, s_, b):
+            if x not in seen and x != "0":
+                seen.add(x); nets.append(x)
+    used_drivers = [x for x in drivers if x in seen]
+
+    def f(ctx, p):
+        node = {"0": 0}
+        for x in nets:
+            node[x] = get_node(ctx, x)
+        stamp(VoltageSource(1.2, name="vdd"), ctx, node["vdd"], 0)
+        stamp(VoltageSource(0.0, name="vss"), ctx, node["vss"], 0)
+        for x in used_drivers:
+            n_int = get_node(ctx, x + "_drv")
+            stamp(VoltageSource(0.0, tran=PulseWave(0.0, 1.2, 1e-10, 1e-10, 1e-10, 1.0, 2.0), name="vdrv_" + x), ctx, n_int, 0)
+            stamp(Resistor(1.0, name="rdrv_" + x), ctx, n_int, node[x])
+        for x in nets:
+            if x not in ("vdd", "vss"):
+                stamp(Capacitor(1e-15, name="cpar_" + x), ctx, node[x], 0)
+        for name, d, g, s_, b, typ, w, l in fets:
+            card = dict(type=typ, vto=0.4 * typ, kp=200e-6 if typ > 0 else 100e-6)
+            stamp(sp_mos1(w=w, l=l, name=name, **card), ctx, node[d], node[g], node[s_], node[b])
+    return CircuitSweep(_B(f), Sweep(dummy=[0.0]), dummy=0.0)
+
+
 FIXTURES = {
     "mos1_corner": ("mos1", mos1_corner),
     "diode_chain": ("diode", diode_chain),
@@ -360,6 +454,8 @@ FIXTURES = {
     "vdmos_cs": ("vdmos", vdmos_cs),
     "inductor_rl": ("inductor", inductor_rl),
     "bsim4_stage": ("bsim4v8", bsim4_stage),
+    "mos1_c6288": ("mos1", mos1_c6288),
+    "mos1_c6288_slice": ("mos1", lambda m: mos1_c6288(m, 420)),
 }
 
 
@@ -385,7 +481,8 @@ def lower_fixture(name, models=None):
 FIXTURE_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 # circuits whose kernel sets __graft_entry__.build() prebuilds (the GPU parity tests and bench.py)
 GPU_VA_FIXTURES = ["mos1_corner", "diode_chain", "diode_rs_cap", "mos1_inverter", "mos1_c3", "mos1_dff",
-                   "mos1_ring", "mos1_ring_caps", "bjt_ce", "jfet2_cs", "vdmos_cs", "inductor_rl"]
+                   "mos1_ring", "mos1_ring_caps", "bjt_ce", "jfet2_cs", "vdmos_cs", "inductor_rl", "bsim4_stage",
+                   "mos1_c6288"]
 
 
 def fixture_path(name: str) -> str:

@@ -18,7 +18,7 @@ HAVE_REF = os.path.isdir("/root/reference/models/VADistillerModels.jl/va")
 needs_ref = pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
 
 FIXTURE_NAMES = ["mos1_corner", "diode_chain", "diode_rs_cap", "mos1_inverter", "mos1_c3", "mos1_dff", "mos1_ring",
-                 "mos1_ring_caps", "bjt_ce", "jfet2_cs", "vdmos_cs", "inductor_rl"]
+                 "mos1_ring_caps", "bjt_ce", "jfet2_cs", "vdmos_cs", "inductor_rl", "mos1_c6288_slice"]
 
 
 GPU_FIXTURES = ["mos1_corner", "diode_chain", "mos1_inverter", "diode_rs_cap", "mos1_ring", "mos1_c3", "mos1_dff"]   # used by -m gpu tests
@@ -333,7 +333,7 @@ def _close(a, b, rtol=1e-9, atol=1e-12):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["mos1_corner", "diode_chain", "mos1_inverter", "bjt_ce", "jfet2_cs", "vdmos_cs",
-                                  "inductor_rl"])
+                                  "inductor_rl", "bsim4_stage"])
 def test_gpu_va_models_dc(name):
     lc = fixture(name)
     nl = oracle_of(lc)
@@ -518,3 +518,72 @@ def test_gpu_va_ring_oscillator():
     print("ring: max |gpu - oracle|", float(np.max(np.abs(gpu - ref))))
     assert _close(gpu, ref), float(np.max(np.abs(gpu - ref)))
     assert gpu[:, :, 0].max() - gpu[:, :, 0].min() > 2.0
+
+
+# ---- large circuits: sparse symbolic analysis + one lane on a warp (C5, fallback tier) ----------
+@pytest.mark.gpu
+def test_gpu_c6288_slice_matches_oracle():
+    """The first 70 gates (420 FETs) of the c6288 multiplier deck (benchmarks/vacask/c6288/cedarsim) on
+    sp_mos1 cards: n = 1957 > 1536, so the pivot order comes from analyze_lu_sparse and the lane runs
+    on the level-scheduled kernels.  DC (PCNR, 1680 limit unknowns) and 40 BE steps against the oracle
+    (its fixed-pattern sparse LU: the dense checker is O(n^3) here)."""
+    lc = fixture("mos1_c6288_slice")
+    assert lc.n == 1957 and lc.n_limits == 1680
+    nl = oracle_of(lc)
+    save = list(range(1, lc.n_nodes + 1))
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        assert comp.handle.lane_mapping() == "warp"
+        x, st, it = comp.dc()
+        wave = comp.tran((0.0, 4e-10), 1e-11, method="be", save_idxs=save)
+        r = wave.fetch(); wave.free()
+    finally:
+        comp.close()
+    ora.set_linear_solver(1)
+    try:
+        xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
+        o = ora.make_tran_opts(method=0, dt=1e-11)
+        ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 4e-10, o, save)
+    finally:
+        ora.set_linear_solver(0)
+    assert np.array_equal(st, sto) and (st == 0).all() and np.array_equal(it, ito)
+    assert _close(x.T, xo), float(np.max(np.abs(x.T - xo)))
+    gpu = np.transpose(r["u"], (2, 1, 0))
+    ref = ro["u"][:, :gpu.shape[1], :]
+    assert np.array_equal(r["status"], ro["status"]) and (r["status"] == 0).all()
+    assert _close(gpu, ref), float(np.max(np.abs(gpu - ref)))
+    assert np.array_equal(r["newton_iters"], ro["newton_iters"])
+
+
+@pytest.mark.gpu
+def test_gpu_c6288_full_dc_residual_and_transient():
+    """The whole multiplier: 10 112 FETs, n = 45 604 (5 122 nodes, 34 source currents, 40 448 limit
+    unknowns), nnz 158 870.  The oracle's LU does not reach this size, so the GPU's DC point is checked
+    through the oracle's OWN rebuild: || G(x) x - b(x) ||_2 < abstol at the GPU's x (the reference's
+    convergence criterion, solve.jl:552), every gate output at a rail; then 20 BE steps run."""
+    lc = fixture("mos1_c6288")
+    assert (lc.n, lc.n_nodes, lc.n_limits) == (45604, 5122, 40448)
+    nl = oracle_of(lc)
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        x, st, it = comp.dc(abstol=1e-9, maxiters=200)
+        stats = comp.handle.stats()
+        wave = comp.tran((0.0, 2e-10), 1e-11, method="be", save_idxs=[lc.index_of("p0"), lc.index_of("p31")])
+        r = wave.fetch(); wave.free()
+        tstats = comp.handle.stats()
+    finally:
+        comp.close()
+    assert st[0] == 0, st
+    S = ora.Structure(nl, ora.make_spec(mode="dcop"))
+    G, C, b, lw = S.rebuild(x[:, 0])
+    a = S.arrays()
+    cols = np.repeat(np.arange(lc.n), np.diff(a["colptr"]))
+    F = np.zeros(lc.n)
+    np.add.at(F, a["rowval"] - 1, G * x[cols, 0])
+    F -= b
+    assert np.linalg.norm(F) < 1e-8, np.linalg.norm(F)
+    v = x[:lc.n_nodes, 0]
+    assert v.min() > -0.05 and v.max() < 1.25
+    assert (r["status"] == 0).all() and np.all(np.isfinite(r["u"]))
+    print(f"c6288 (sp_mos1): DC {int(it[0])} PCNR iterations, kernel {stats['kernel_ms']:.1f} ms; "
+          f"20 BE steps: {int(r['newton_iters'][0])} Newton iterations, kernel {tstats['tran_kernel_ms']:.1f} ms")
