@@ -168,6 +168,8 @@ def lib():
     L.cb200_lane_mapping.argtypes = [vp]
     L.cb200_host_lu_check.restype = C.c_int
     L.cb200_host_lu_check.argtypes = [C.POINTER(Desc), dp, dp, dp, dp, lp, lp, ip]
+    L.cb200_host_lu_check_static.restype = C.c_int
+    L.cb200_host_lu_check_static.argtypes = [C.POINTER(Desc), dp, dp, dp, dp, dp, dp, ip]
     L.cb200_load_va_models.restype = C.c_int
     L.cb200_load_va_models.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
     L.cb200_emit_source.restype = C.c_int64
@@ -214,7 +216,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "cb200_abi_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_pattern",
     "cb200_get_maps", "cb200_set_lanes", "cb200_analyze", "cb200_get_pivot_order", "cb200_eval",
-    "cb200_specialize", "cb200_is_specialized", "cb200_weak_pivot_lanes", "cb200_lane_mapping", "cb200_host_lu_check", "cb200_emit_source", "cb200_load_va_models",
+    "cb200_specialize", "cb200_is_specialized", "cb200_weak_pivot_lanes", "cb200_lane_mapping", "cb200_host_lu_check", "cb200_host_lu_check_static", "cb200_emit_source", "cb200_load_va_models",
     "cb200_dc", "cb200_tran", "cb200_tran_fetch", "cb200_tran_fetch_ld", "cb200_set_tstops", "cb200_wave_info",
     "cb200_wave_fetch", "cb200_wave_fetch_ld", "cb200_wave_final_state",
     "cb200_wave_free", "cb200_get_stats", "cb200_debug_exp", "cb200_measure_fp64_peak", "cb200_flop_model"]
@@ -344,6 +346,24 @@ def emit_source(lc: LoweredCircuit, absJ_dc: np.ndarray, absJ_tr: np.ndarray, P:
     buf = C.create_string_buffer(n + 1)
     L.cb200_emit_source(C.byref(desc), _dp(a0), _dp(a1), m, P, num_sms, buf, n + 1)
     return buf.value.decode()
+
+
+def host_lu_check_static(lc: LoweredCircuit, absJ: np.ndarray, J_nz: np.ndarray, rhs: np.ndarray,
+                         absJmin: Optional[np.ndarray] = None):
+    """cb200_host_lu_check_static: pivot order from ``absJ`` / ``absJmin`` (largest / smallest magnitude
+    over probe states), numeric factor + solves on ``J_nz``."""
+    L = lib()
+    desc, keep = make_desc(lc)
+    info = np.zeros(6, dtype=np.int32)
+    a = np.ascontiguousarray(absJ, dtype=np.float64)
+    J = np.ascontiguousarray(J_nz, dtype=np.float64)
+    r = np.ascontiguousarray(rhs, dtype=np.float64)
+    xs, xl = np.zeros(len(r)), np.zeros(len(r))
+    amin = None if absJmin is None else np.ascontiguousarray(absJmin, dtype=np.float64)
+    rc = L.cb200_host_lu_check_static(C.byref(desc), _dp(a), _dp(amin), _dp(J), _dp(r), _dp(xs), _dp(xl), _ip(info))
+    if rc != OK:
+        raise CB200Error(rc, (L.cb200_last_error(None) or b"").decode())
+    return xs, xl, dict(n=int(info[0]), nnz=int(info[1]), nlu=int(info[2]), factor_levels=int(info[3]))
 
 
 def host_lu_check(lc: LoweredCircuit, J_nz: Optional[np.ndarray] = None, rhs: Optional[np.ndarray] = None):

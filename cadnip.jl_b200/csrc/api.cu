@@ -611,7 +611,7 @@ static int require_models(cb200_handle *h)
 // maxima per pattern entry.  Runs the K1/K2 evaluation kernels on a temporary
 // program whose lane SoA holds only the samples.
 static int probe_magnitudes(cb200_handle *h, const cb200_spec *spec, double gamma,
-                            std::vector<double> &absJ)
+                            std::vector<double> &absJ, std::vector<double> *absJmin = nullptr)
 {
     const int64_t P = h->P;
     const int n = h->st.n;
@@ -630,6 +630,7 @@ static int probe_magnitudes(cb200_handle *h, const cb200_spec *spec, double gamm
     CUDA_TRY(h, d_G.alloc((size_t)nnz * ns));
     CUDA_TRY(h, d_C.alloc((size_t)nnz * ns));
     absJ.assign(nnz, 0.0);
+    if (absJmin) absJmin->assign(nnz, 1.0 / 0.0);
     std::vector<double> hG((size_t)nnz * ns), hC((size_t)nnz * ns), ws_host((size_t)p.n_slots * ns, 0.0);
     // probe states: ZERO_VECTOR with the PCNR seeds (initjct), ZERO_VECTOR, and two
     // deterministic pseudo-random states in [-1, 1] (cf. solve.jl:992-1015).
@@ -656,6 +657,7 @@ static int probe_magnitudes(cb200_handle *h, const cb200_spec *spec, double gamm
             for (int l = 0; l < ns; l++) {
                 double v = std::fabs(hG[(size_t)q * ns + l] + gamma * hC[(size_t)q * ns + l]);
                 if (std::isfinite(v) && v > absJ[q]) absJ[q] = v;
+                if (absJmin && !(v >= (*absJmin)[q])) (*absJmin)[q] = std::isfinite(v) ? v : 0.0;
             }
     }
     return CB200_OK;
@@ -668,11 +670,11 @@ extern "C" int cb200_analyze(cb200_handle *h, const cb200_spec *spec, double gam
     if (require_models(h) != CB200_OK) return CB200_ESTATE;
     cudaSetDevice(h->device);
     const int which = gamma == 0.0 ? 0 : 1;
-    std::vector<double> absJ;
-    int rc = probe_magnitudes(h, spec, gamma, absJ);
+    std::vector<double> absJ, absJmin;
+    int rc = probe_magnitudes(h, spec, gamma, absJ, &absJmin);
     if (rc != CB200_OK) return rc;
     DevLu &L = h->lu[which];
-    std::string e = analyze_lu(h->st, absJ, 1e-3, L.host);
+    std::string e = analyze_lu(h->st, absJ, 1e-3, L.host, &absJmin);
     if (!e.empty()) return fail(h, CB200_ESINGULAR, e);
     L.host.gamma = gamma;
     rc = upload_lu(h, L);
@@ -1293,9 +1295,30 @@ extern "C" int cb200_is_specialized(const cb200_handle *h) { return h && spec_us
 // Host-only test hook (no device): pattern + static-pivot schedule + level schedule of a
 // description, and both schedules executed on the host for one matrix.  info = {n, nnz, nlu,
 // factor levels, forward levels, backward levels}.
+static int host_lu_check_impl(const cb200_desc *d, const double *absJ, const double *absJmin, const double *J_nz,
+                              const double *rhs, double *x_serial, double *x_level, int64_t *colptr, int64_t *rowval,
+                              int32_t *info);
+
 extern "C" int cb200_host_lu_check(const cb200_desc *d, const double *J_nz, const double *rhs,
                                    double *x_serial, double *x_level, int64_t *colptr, int64_t *rowval,
                                    int32_t *info)
+{
+    return host_lu_check_impl(d, nullptr, nullptr, J_nz, rhs, x_serial, x_level, colptr, rowval, info);
+}
+
+// The same with the pivot order chosen from OTHER magnitudes than the matrix that is factored: absJ
+// plays the probed magnitudes of cb200_analyze, J_nz a Jacobian met later in the Newton loop.
+extern "C" int cb200_host_lu_check_static(const cb200_desc *d, const double *absJ, const double *absJmin,
+                                          const double *J_nz, const double *rhs, double *x_serial,
+                                          double *x_level, int32_t *info)
+{
+    if (!absJ) { g_last_error = "cb200_host_lu_check_static: null argument"; return CB200_EINVAL; }
+    return host_lu_check_impl(d, absJ, absJmin, J_nz, rhs, x_serial, x_level, nullptr, nullptr, info);
+}
+
+static int host_lu_check_impl(const cb200_desc *d, const double *absJ, const double *absJmin, const double *J_nz,
+                              const double *rhs, double *x_serial, double *x_level, int64_t *colptr, int64_t *rowval,
+                              int32_t *info)
 {
     if (!d || !info) { g_last_error = "cb200_host_lu_check: null argument"; return CB200_EINVAL; }
     Structure st;
@@ -1307,9 +1330,11 @@ extern "C" int cb200_host_lu_check(const cb200_desc *d, const double *J_nz, cons
     if (!J_nz) return CB200_OK;
     if (!rhs || !x_serial || !x_level) { g_last_error = "cb200_host_lu_check: null argument"; return CB200_EINVAL; }
     std::vector<double> J(J_nz, J_nz + st.nnz), a(st.nnz), r(rhs, rhs + st.n), xs, xl;
-    for (int64_t q = 0; q < st.nnz; q++) a[q] = std::fabs(J[q]);
+    for (int64_t q = 0; q < st.nnz; q++) a[q] = absJ ? absJ[q] : std::fabs(J[q]);
+    std::vector<double> amin;
+    if (absJmin) amin.assign(absJmin, absJmin + st.nnz);
     LuSchedule S;
-    e = analyze_lu(st, a, 1e-3, S);
+    e = analyze_lu(st, a, 1e-3, S, absJmin ? &amin : nullptr);
     if (!e.empty()) { g_last_error = e; return CB200_ESINGULAR; }
     LevelSchedule V;
     build_level_schedule(S, V);

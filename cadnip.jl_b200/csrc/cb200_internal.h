@@ -47,8 +47,10 @@ struct LuSchedule {
 
 // absJ: nominal magnitude of every pattern entry (max over probes; 0 = numerically
 // absent at the probes).  Threshold Markowitz on the magnitudes, then symbolic fill.
+// absJmin (optional): the SMALLEST magnitude of every entry over the probes; the sparse analysis
+// (n > 1536) admits a pivot on its smallest value against its column's largest.
 std::string analyze_lu(const Structure &s, const std::vector<double> &absJ, double threshold,
-                       LuSchedule &out);
+                       LuSchedule &out, const std::vector<double> *absJmin = nullptr);
 
 // Level schedule of the same factorisation for the lane-per-warp kernels (warp_kernels.cuh):
 // the elimination DAG cut into levels whose operations are independent, so that the 32 threads

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <functional>
 #include <numeric>
+#include <set>
 
 #include "cb200_internal.h"
 
@@ -108,7 +109,8 @@ std::string build_structure(const cb200_desc &d, Structure &s)
 // Same LuSchedule as the dense path; the level schedule and every kernel are unchanged.
 // ---------------------------------------------------------------------------
 namespace {
-struct SpEntry { int col; double mag; };
+const double kOffDiagThreshold = 0.1;
+struct SpEntry { int col; double mag, lo; };     // upper / lower bound of |a_ij| over the probes and the elimination
 typedef std::vector<SpEntry> SpRow;
 
 static int sp_find(const SpRow &r, int col)
@@ -119,8 +121,8 @@ static int sp_find(const SpRow &r, int col)
 }
 }  // namespace
 
-static std::string analyze_lu_sparse(const Structure &s, const std::vector<double> &absJ, double threshold,
-                                     LuSchedule &out)
+static std::string analyze_lu_sparse(const Structure &s, const std::vector<double> &absJ,
+                                     const std::vector<double> *absJmin, double threshold, LuSchedule &out)
 {
     const int n = s.n;
     std::vector<SpRow> rows(n);
@@ -133,142 +135,113 @@ static std::string analyze_lu_sparse(const Structure &s, const std::vector<doubl
     for (int j = 0; j < n; j++)                      // CSC order: every row list ends up sorted by column
         for (int q = s.colptr[j]; q < s.colptr[j + 1]; q++) {
             const double m = std::isfinite(absJ[q]) ? absJ[q] : 0.0;
-            rows[s.rowval[q]].push_back({j, m});
+            double lo = absJmin ? (*absJmin)[q] : m;
+            if (!std::isfinite(lo) || lo > m) lo = m;
+            rows[s.rowval[q]].push_back({j, m, lo});
             cols[j].push_back(s.rowval[q]);
         }
-    std::vector<double> colmax0(n, 0.0);
-    for (int i = 0; i < n; i++) for (const SpEntry &e : rows[i]) colmax0[e.col] = std::max(colmax0[e.col], e.mag);
-
-    // ---- 1. matching: row_col[i] = column paired with row i
-    std::vector<int> row_col(n, -1), col_row(n, -1);
-    for (int i = 0; i < n; i++) {
-        const int d = sp_find(rows[i], i);
-        if (d >= 0 && rows[i][d].mag > 0.0 && rows[i][d].mag >= threshold * colmax0[i]) { row_col[i] = i; col_row[i] = i; }
-    }
-    {
-        std::vector<int> seen(n, -1), fr_row, fr_k, via;
-        for (int pass = 0; pass < 2; pass++) {       // pass 0: strong entries only, pass 1: any numerically present entry
-            for (int r0 = 0; r0 < n; r0++) {
-                if (row_col[r0] >= 0) continue;
-                const int stamp = pass * n + r0;
-                fr_row.assign(1, r0); fr_k.assign(1, 0); via.clear();
-                seen[r0] = stamp;
-                bool found = false;
-                while (!fr_row.empty() && !found) {   // iterative depth-first search for an augmenting path
-                    const int r = fr_row.back();
-                    const size_t top = fr_k.size() - 1;
-                    bool advanced = false;
-                    if (fr_k[top] == 0) {             // cheap assignment first: a free column in this very row
-                        for (const SpEntry &e : rows[r]) {
-                            if (!(e.mag > 0.0) || col_row[e.col] >= 0) continue;
-                            if (pass == 0 && e.mag < threshold * colmax0[e.col]) continue;
-                            via.push_back(e.col);
-                            for (size_t t = 0; t < fr_row.size(); t++) { row_col[fr_row[t]] = via[t]; col_row[via[t]] = fr_row[t]; }
-                            found = true;
-                            break;
-                        }
-                        if (found) break;
-                    }
-                    for (int k = fr_k[top]; k < (int)rows[r].size(); k++) {
-                        const SpEntry &e = rows[r][k];
-                        if (!(e.mag > 0.0)) continue;
-                        if (pass == 0 && e.mag < threshold * colmax0[e.col]) continue;
-                        const int owner = col_row[e.col];
-                        if (owner < 0) {              // free column: shift every row of the path to its `via` column
-                            via.push_back(e.col);
-                            for (size_t t = 0; t < fr_row.size(); t++) { row_col[fr_row[t]] = via[t]; col_row[via[t]] = fr_row[t]; }
-                            found = true;
-                            break;
-                        }
-                        if (seen[owner] == stamp) continue;
-                        seen[owner] = stamp;
-                        fr_k[top] = k + 1;
-                        via.push_back(e.col);
-                        fr_row.push_back(owner); fr_k.push_back(0);
-                        advanced = true;
-                        break;
-                    }
-                    if (!found && !advanced) {
-                        fr_row.pop_back(); fr_k.pop_back();
-                        if (!via.empty()) via.pop_back();
-                    }
-                }
-            }
-        }
-    }
-    for (int i = 0; i < n; i++)
-        if (row_col[i] < 0) return "analyze_lu: matrix is structurally or numerically singular at the probe points (row " +
-                                   std::to_string(i) + " cannot be paired with a column)";
-
-    // ---- 2. Markowitz elimination over the matched entries
+    // ---- 1 + 2. threshold Markowitz over the sparse rows.  Candidates are the entries of the few
+    // rows and the few columns with the smallest active counts (the MA28 / Zlatev search: the entry
+    // minimising (r-1)(c-1) sits in a short row or a short column); among the cheapest, an entry is
+    // admissible when its magnitude bound reaches `threshold` of its column's largest; ties go to
+    // the diagonal, then to the relatively larger entry -- the rule of the dense analysis below.
     std::vector<uint8_t> row_done(n, 0), col_done(n, 0);
-    std::vector<int> ccount(n, 0), ver(n, 0);
+    std::vector<int> ccount(n, 0);
     for (int j = 0; j < n; j++) ccount[j] = (int)cols[j].size();
-    typedef std::pair<int64_t, std::pair<int, int>> HeapItem;     // (cost, (row, version)), min-heap
-    std::vector<HeapItem> heap;
-    auto cost_of = [&](int i) { return (int64_t)((int)rows[i].size() - 1) * (int64_t)(ccount[row_col[i]] - 1); };
-    auto push = [&](int i) {
-        heap.push_back({cost_of(i), {i, ++ver[i]}});
-        std::push_heap(heap.begin(), heap.end(), std::greater<HeapItem>());
+    std::set<std::pair<int, int>> rowset, colset;                  // (active count, index)
+    for (int i = 0; i < n; i++) { rowset.insert({(int)rows[i].size(), i}); colset.insert({ccount[i], i}); }
+    std::vector<double> cmax_val(n, 0.0);
+    std::vector<uint8_t> cmax_ok(n, 0);
+    auto colmax = [&](int j) -> double {
+        if (cmax_ok[j]) return cmax_val[j];
+        std::vector<int> &cl = cols[j];
+        size_t w = 0;
+        double m = 0.0;
+        for (size_t t = 0; t < cl.size(); t++) {
+            const int r = cl[t];
+            if (row_done[r]) continue;
+            const int q = sp_find(rows[r], j);
+            if (q < 0) continue;
+            cl[w++] = r;
+            if (rows[r][q].mag > m) m = rows[r][q].mag;
+        }
+        cl.resize(w);
+        cmax_val[j] = m; cmax_ok[j] = 1;
+        return m;
     };
-    heap.reserve((size_t)n * 4);
-    for (int i = 0; i < n; i++) { heap.push_back({cost_of(i), {i, ver[i]}}); }
-    std::make_heap(heap.begin(), heap.end(), std::greater<HeapItem>());
+    struct Cand { int64_t cost; int row, col; double mag, lo; };
+    std::vector<Cand> cand;
 
     out.rowperm.assign(n, -1); out.colperm.assign(n, -1);
     std::vector<std::vector<int>> Ucols(n), Lrows(n);            // per pivot, ORIGINAL indices
     SpRow merged;
     int n_offdiag = 0;
     for (int k = 0; k < n; k++) {
-        int pr = -1;
-        while (!heap.empty()) {
-            std::pop_heap(heap.begin(), heap.end(), std::greater<HeapItem>());
-            const HeapItem it = heap.back(); heap.pop_back();
-            const int i = it.second.first;
-            if (row_done[i] || it.second.second != ver[i]) continue;
-            if (it.first != cost_of(i)) { push(i); continue; }
-            pr = i; break;
-        }
-        if (pr < 0) return "analyze_lu: internal error (empty pivot heap)";
-        int pc = row_col[pr];
-        // threshold test of the matched entry against its column's largest active magnitude
-        double cmax = 0.0, best = 0.0; int best_row = -1;
-        {
-            std::vector<int> &cl = cols[pc];
-            size_t w = 0;
-            for (size_t t = 0; t < cl.size(); t++) {
-                const int r = cl[t];
-                if (row_done[r]) continue;
-                cl[w++] = r;
-                const int q = sp_find(rows[r], pc);
-                const double m = q >= 0 ? rows[r][q].mag : 0.0;
-                if (m > cmax) cmax = m;
-                if (m > best) { best = m; best_row = r; }
+        int pr = -1, pc = -1;
+        // admissibility, strictest first.  Levels 0-2 hold the candidate at its SMALLEST against the column
+        // at its LARGEST: 0 -- diagonal entries only, `threshold` of the column (KLU's diagonal preference:
+        // an MNA matrix eliminated along its diagonal stays diagonally dominant); 1 -- any entry comparable
+        // with its column's largest (0.1); 2 -- any entry at `threshold`; 3 -- upper bounds only (the rule
+        // of the dense analysis).  Levels 0-2 look at the 64 shortest rows / columns, level 3 at everything.
+        for (int level = 0; level < 4 && pr < 0; level++) {
+        for (int K = 4; pr < 0; K *= 4) {
+            cand.clear();
+            int taken = 0;
+            for (auto it = rowset.begin(); it != rowset.end() && taken < K; ++it, ++taken) {
+                const int i = it->second;
+                for (const SpEntry &e : rows[i])
+                    cand.push_back({(int64_t)((int)rows[i].size() - 1) * (int64_t)(ccount[e.col] - 1), i, e.col, e.mag, e.lo});
             }
-            cl.resize(w);
+            taken = 0;
+            for (auto it = colset.begin(); it != colset.end() && taken < K; ++it, ++taken) {
+                const int j = it->second;
+                colmax(j);                                        // compacts cols[j] to its active rows
+                for (int r : cols[j]) {
+                    const int q = sp_find(rows[r], j);
+                    cand.push_back({(int64_t)((int)rows[r].size() - 1) * (int64_t)(ccount[j] - 1), r, j, rows[r][q].mag, rows[r][q].lo});
+                }
+            }
+            std::sort(cand.begin(), cand.end(), [](const Cand &x, const Cand &y) { return x.cost < y.cost; });
+            size_t g0 = 0;
+            while (g0 < cand.size() && pr < 0) {
+                size_t g1 = g0;
+                while (g1 < cand.size() && cand[g1].cost == cand[g0].cost) g1++;
+                bool best_diag = false; double best_rel = -1.0;
+                for (size_t t = g0; t < g1; t++) {
+                    const Cand &c = cand[t];
+                    const double val = level == 3 ? c.mag : c.lo;
+                    if (!(val > 0.0)) continue;
+                    const bool diag = c.row == c.col;
+                    if (level == 0 && !diag) continue;
+                    const double cm = colmax(c.col);
+                    if (val < ((level == 1 && !diag) ? kOffDiagThreshold : threshold) * cm) continue;
+                    const double rel = val / cm;
+                    if (pr < 0 || (diag && !best_diag) || (diag == best_diag && rel > best_rel * (1.0 + 1e-12))) {
+                        pr = c.row; pc = c.col; best_diag = diag; best_rel = rel;
+                    }
+                }
+                g0 = g1;
+            }
+            if (pr < 0 && (K >= n || (level < 3 && K >= 64))) break;
         }
-        if (!(cmax > 0.0)) return "analyze_lu: matrix is singular at the probe points (no admissible pivot at step " +
-                                  std::to_string(k) + ")";
-        const int qd = sp_find(rows[pr], pc);
-        const double mpiv = qd >= 0 ? rows[pr][qd].mag : 0.0;
-        if (!(mpiv > 0.0) || mpiv < threshold * cmax) {
-            // off-diagonal pivot: the column's largest entry; the two orphans are paired with each other
-            const int r2 = best_row, c2 = row_col[r2];
-            n_offdiag++;
-            if (getenv("CB200_ANALYZE_DEBUG") && n_offdiag <= 5)
-                fprintf(stderr, "  off-diagonal pivot at step %d: row %d col %d matched mag %g colmax %g -> row %d (its col %d)\n",
-                        k, pr, pc, mpiv, cmax, r2, c2);
-            row_col[pr] = c2; col_row[c2] = pr;
-            row_col[r2] = pc; col_row[pc] = r2;
-            push(pr);
-            pr = r2;
         }
+        if (pr < 0) return "analyze_lu: matrix is singular at the probe points (no admissible pivot at step " +
+                           std::to_string(k) + ")";
+        if (pr != pc) n_offdiag++;
         out.rowperm[k] = pr; out.colperm[k] = pc;
         row_done[pr] = 1; col_done[pc] = 1;
+        rowset.erase({(int)rows[pr].size(), pr});
+        colset.erase({ccount[pc], pc});
         const SpRow prow = rows[pr];                                 // copy: the pivot row (U row k + diagonal)
         const int qp = sp_find(prow, pc);
-        const double piv = prow[qp].mag;
-        for (const SpEntry &e : prow) if (e.col != pc) { Ucols[k].push_back(e.col); ccount[e.col]--; }
+        const double piv_hi = prow[qp].mag, piv_lo = prow[qp].lo;
+        for (const SpEntry &e : prow)
+            if (e.col != pc) {
+                Ucols[k].push_back(e.col);
+                colset.erase({ccount[e.col], e.col});
+                ccount[e.col]--;                                     // re-inserted below, after the fill is known
+                cmax_ok[e.col] = 0;
+            }
         // eliminate column pc from every other active row
         for (int r : cols[pc]) {
             if (row_done[r]) continue;
@@ -276,7 +249,8 @@ static std::string analyze_lu_sparse(const Structure &s, const std::vector<doubl
             const int q = sp_find(rr, pc);
             if (q < 0) continue;
             Lrows[k].push_back(r);
-            const double l = rr[q].mag / piv;
+            rowset.erase({(int)rr.size(), r});
+            const double l = rr[q].mag / piv_lo, l_lo = rr[q].lo / piv_hi;      // multiplier at its largest / smallest
             merged.clear();
             merged.reserve(rr.size() + prow.size());
             size_t a = 0, b = 0;
@@ -286,20 +260,23 @@ static std::string analyze_lu_sparse(const Structure &s, const std::vector<doubl
                     a++;
                 } else if (a >= rr.size() || prow[b].col < rr[a].col) {
                     if (prow[b].col != pc) {                         // fill
-                        merged.push_back({prow[b].col, l * prow[b].mag});
+                        merged.push_back({prow[b].col, l * prow[b].mag, l_lo * prow[b].lo});
                         cols[prow[b].col].push_back(r);
                         ccount[prow[b].col]++;
                     }
                     b++;
                 } else {
-                    if (rr[a].col != pc) merged.push_back({rr[a].col, rr[a].mag + l * prow[b].mag});
+                    // the lower bound of an updated entry is kept (the updates of an MNA matrix add to the
+                    // off-diagonals and leave the diagonals dominant; cancellation is what the run-time
+                    // weak-pivot check is for)
+                    if (rr[a].col != pc) merged.push_back({rr[a].col, rr[a].mag + l * prow[b].mag, rr[a].lo});
                     a++; b++;
                 }
             }
             rr.swap(merged);
-            push(r);
+            rowset.insert({(int)rr.size(), r});
         }
-        for (int c : Ucols[k]) { const int r = col_row[c]; if (r >= 0 && !row_done[r]) push(r); }
+        for (int c : Ucols[k]) colset.insert({ccount[c], c});
         std::vector<int>().swap(cols[pc]);
         SpRow().swap(rows[pr]);
     }
@@ -383,14 +360,14 @@ static std::string analyze_lu_sparse(const Structure &s, const std::vector<doubl
 static const int kDenseLimit = 1536;
 
 std::string analyze_lu(const Structure &s, const std::vector<double> &absJ, double threshold,
-                       LuSchedule &out)
+                       LuSchedule &out, const std::vector<double> *absJmin)
 {
     const int n = s.n;
     out = LuSchedule();
     out.n = n;
     if (n == 0) { out.valid = true; return ""; }
     if ((int64_t)absJ.size() != s.nnz) return "analyze_lu: magnitude array has wrong length";
-    if (n > kDenseLimit || getenv("CB200_SPARSE_ANALYZE")) return analyze_lu_sparse(s, absJ, threshold, out);
+    if (n > kDenseLimit || getenv("CB200_SPARSE_ANALYZE")) return analyze_lu_sparse(s, absJ, absJmin, threshold, out);
 
     // pat: 0 absent, 1 structural; mag: nominal magnitude
     std::vector<uint8_t> pat((size_t)n * n, 0);

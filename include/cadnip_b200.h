@@ -291,6 +291,11 @@ int cb200_lane_mapping(const cb200_handle *h);
 int cb200_host_lu_check(const cb200_desc *desc, const double *J_nz, const double *rhs,
                         double *x_serial, double *x_level, int64_t *colptr, int64_t *rowval,
                         int32_t *info);
+/* The same with the pivot order taken from absJ / absJmin (the largest / smallest magnitude of every
+ * entry over the probe states of cb200_analyze; absJmin may be NULL) and the numeric phase run on
+ * J_nz, a matrix met later in the Newton loop: checks a STATIC order. */
+int cb200_host_lu_check_static(const cb200_desc *d, const double *absJ, const double *absJmin, const double *J_nz,
+                               const double *rhs, double *x_serial, double *x_level, int32_t *info);
 /* Host-only emitter entry (no device): description + nominal |J| magnitudes for the DC
  * and transient schedules -> generated CUDA source (returns its length; negative =
  * error).  Lets the emitter be tested where no GPU is present.                      */

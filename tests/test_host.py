@@ -494,3 +494,25 @@ def test_sparse_symbolic_analysis_large_circuit():
     # a planar mesh under a fill-reducing order: the factor stays within a small multiple of the pattern
     assert info["nlu"] < 12 * info["nnz"] and info["factor_levels"] < info["n"] // 4
     print(f"n {n} nnz {nnz} nlu {info['nlu']} levels {info['factor_levels']} analysis+solve {dt:.2f} s")
+
+
+def test_julia_shim_matches_header():
+    """julia/CadnipB200.jl (the ccall binding a Cadnip.jl maintainer adds; cannot run here -- no Julia
+    in the image) mirrors the C structs field by field: names, order and sizes must equal the ctypes
+    structures the tests drive the library with, and every symbol it calls must be exported."""
+    import ctypes as C
+    import re
+    from cadnip_b200 import backend
+    src = open(os.path.join(ROOT, "julia", "CadnipB200.jl")).read()
+    size = {"Int32": 4, "Int64": 8, "Cdouble": 8}
+    for jname, ct in (("Spec", backend.Spec), ("DcOpts", backend.DcOpts), ("TranOpts", backend.TranOpts),
+                      ("Desc", backend.Desc)):
+        body = re.search(rf"^struct {jname}\b[^\n]*\n(.*?)^end", src, re.S | re.M).group(1)
+        fields = re.findall(r"(\w+)::((?:Ptr\{\w+\})|\w+)", body)
+        want = [(n, C.sizeof(t)) for n, t in ct._fields_]
+        got = [(n, 8 if t.startswith("Ptr") else size[t]) for n, t in fields]
+        assert [g[1] for g in got] == [w[1] for w in want], (jname, got, want)
+        assert [g[0].lower() for g in got] == [w[0].lower() for w in want], (jname, got, want)
+        assert sum(g[1] for g in got) == C.sizeof(ct), jname          # no implicit padding on either side
+    for sym in set(re.findall(r"\(:(cb200_\w+), LIB\[\]\)", src)):
+        assert sym in backend.EXPORTED_SYMBOLS, sym
