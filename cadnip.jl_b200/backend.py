@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_CSRC, "libcadnip_b200.so")
 _SOURCES = ["api.cu", "kernels.cu", "symbolic.cpp", "specialize.cpp"]
-_HEADERS = ["kernels.h", "cb200_internal.h", "lane_kernels.cuh", "warp_kernels.cuh", "specialize.h",
+_HEADERS = ["kernels.h", "cb200_internal.h", "lane_kernels.cuh", "warp_kernels.cuh", "group_kernels.inc", "specialize.h",
             os.path.join("..", "..", "include", "cadnip_b200.h")]
 GEN_DIR = os.path.join(_HERE, "_gen")
 
@@ -536,7 +536,7 @@ class Handle:
 
     def lane_mapping(self) -> str:
         """Mapping of the table-driven kernels for this circuit (cb200_lane_mapping)."""
-        return {0: "thread/smem", 1: "thread/hbm", 2: "warp"}[lib().cb200_lane_mapping(self._p)]
+        return {0: "thread/smem", 1: "thread/hbm", 2: "warp", 3: "block"}[lib().cb200_lane_mapping(self._p)]
 
     def pivot_order(self):
         r = np.zeros(self.n, np.int64); c = np.zeros(self.n, np.int64); nlu = C.c_int64()

@@ -1348,6 +1348,7 @@ static int host_lu_check_impl(const cb200_desc *d, const double *absJ, const dou
 extern "C" int cb200_lane_mapping(const cb200_handle *h)
 {
     if (!h) return CB200_EINVAL;
+    if (use_block_kernels(h->prog, h->smem_limit, h->block_pref)) return 3;
     if (use_warp_kernels(h->prog.n_slots, h->smem_limit, h->block_pref)) return 2;
     return choose_block(h->prog.n_slots, h->smem_limit, h->block_pref) == 0 ? 1 : 0;
 }

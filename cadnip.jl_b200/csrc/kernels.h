@@ -161,6 +161,8 @@ cudaError_t launch_debug_exp(const double *x, double *y, int n, cudaStream_t st)
 int choose_block(int n_slots, size_t smem_limit, int preferred);
 // true: the circuit runs on the lane-per-warp kernels (workspace [lane][n_slots_w] in HBM / L2)
 bool use_warp_kernels(int n_slots, size_t smem_limit, int preferred);
+// true: ... on the lane-per-BLOCK kernels (large circuits on few lanes)
+bool use_block_kernels(const Program &p, size_t smem_limit, int preferred);
 
 }  // namespace cb200
 

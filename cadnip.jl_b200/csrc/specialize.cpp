@@ -377,7 +377,7 @@ std::string build_va_kernel_set(const std::string &va_header_text, const std::st
     }
     // the kernel set also depends on the sources it is rebuilt from
     uint64_t hk = h;
-    for (const char *f : {"/kernels.cu", "/lane_kernels.cuh", "/warp_kernels.cuh", "/kernels.h", "/../../include/cadnip_b200.h"}) {
+    for (const char *f : {"/kernels.cu", "/lane_kernels.cuh", "/warp_kernels.cuh", "/group_kernels.inc", "/kernels.h", "/../../include/cadnip_b200.h"}) {
         std::string body = slurp(csrc_dir + f);
         if (body.empty()) return "va models: cannot read " + csrc_dir + f;
         hk = fnv1a(hk, body);

@@ -181,9 +181,12 @@ static std::string analyze_lu_sparse(const Structure &s, const std::vector<doubl
         // admissibility, strictest first.  Levels 0-2 hold the candidate at its SMALLEST against the column
         // at its LARGEST: 0 -- diagonal entries only, `threshold` of the column (KLU's diagonal preference:
         // an MNA matrix eliminated along its diagonal stays diagonally dominant); 1 -- any entry comparable
-        // with its column's largest (0.1); 2 -- any entry at `threshold`; 3 -- upper bounds only (the rule
-        // of the dense analysis).  Levels 0-2 look at the 64 shortest rows / columns, level 3 at everything.
-        for (int level = 0; level < 4 && pr < 0; level++) {
+        // with its column's largest (0.1); 2 -- any entry at `threshold`; 3 -- any entry that is non-zero at
+        // EVERY probe, however small against its column (a switching circuit's off-state conductances:
+        // gmin-sized but never zero -- growth is preferable to a pivot that vanishes with the state);
+        // 4 -- upper bounds only (the rule of the dense analysis).  Levels 0-3 look at the 64 shortest
+        // rows / columns, level 4 at everything.
+        for (int level = 0; level < 5 && pr < 0; level++) {
         for (int K = 4; pr < 0; K *= 4) {
             cand.clear();
             int taken = 0;
@@ -209,12 +212,12 @@ static std::string analyze_lu_sparse(const Structure &s, const std::vector<doubl
                 bool best_diag = false; double best_rel = -1.0;
                 for (size_t t = g0; t < g1; t++) {
                     const Cand &c = cand[t];
-                    const double val = level == 3 ? c.mag : c.lo;
+                    const double val = level == 4 ? c.mag : c.lo;
                     if (!(val > 0.0)) continue;
                     const bool diag = c.row == c.col;
                     if (level == 0 && !diag) continue;
                     const double cm = colmax(c.col);
-                    if (val < ((level == 1 && !diag) ? kOffDiagThreshold : threshold) * cm) continue;
+                    if (level != 3 && val < ((level == 1 && !diag) ? kOffDiagThreshold : threshold) * cm) continue;
                     const double rel = val / cm;
                     if (pr < 0 || (diag && !best_diag) || (diag == best_diag && rel > best_rel * (1.0 + 1e-12))) {
                         pr = c.row; pc = c.col; best_diag = diag; best_rel = rel;
@@ -222,7 +225,7 @@ static std::string analyze_lu_sparse(const Structure &s, const std::vector<doubl
                 }
                 g0 = g1;
             }
-            if (pr < 0 && (K >= n || (level < 3 && K >= 64))) break;
+            if (pr < 0 && (K >= n || (level < 4 && K >= 64))) break;
         }
         }
         if (pr < 0) return "analyze_lu: matrix is singular at the probe points (no admissible pivot at step " +
@@ -250,7 +253,9 @@ static std::string analyze_lu_sparse(const Structure &s, const std::vector<doubl
             if (q < 0) continue;
             Lrows[k].push_back(r);
             rowset.erase({(int)rr.size(), r});
-            const double l = rr[q].mag / piv_lo, l_lo = rr[q].lo / piv_hi;      // multiplier at its largest / smallest
+            // multiplier at its largest / smallest; a pivot admitted on its upper bound only (level 3)
+            // has no usable lower bound: the optimistic value stands in
+            const double l = rr[q].mag / (piv_lo > 0.0 ? piv_lo : piv_hi), l_lo = rr[q].lo / piv_hi;
             merged.clear();
             merged.reserve(rr.size() + prow.size());
             size_t a = 0, b = 0;

@@ -447,6 +447,13 @@ def test_lane_per_warp_kernels_equal_lane_per_thread_bitwise(name, cs, tspan, dt
     # and the segmented run equals the single launch under the warp mapping too
     for method in ("be", "trap", "gear2"):
         assert np.array_equal(got["fixed_" + method][0], got["segments_" + method][0])
+    # the large-circuit mapping (one lane per BLOCK of 512 threads: group_kernels.inc instantiated with
+    # block-wide barriers and votes) performs the same operations again
+    monkeypatch.setenv("CB200_LANE_PER_BLOCK", "1")
+    blk = _run_all_analyses(lc, tspan, dt, dt0)
+    for key in ref:
+        for a, b in zip(ref[key], blk[key]):
+            assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), (name, key, "block")
 
 
 # ---- DC fallback chain, CedarUICOp, static-pivot safeguard -------------------------------

@@ -572,6 +572,7 @@ def test_gpu_c6288_full_dc_residual_and_transient():
     nl = oracle_of(lc)
     comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
     try:
+        assert comp.handle.lane_mapping() == "block"          # one lane on the 512 threads of a block
         x, st, it = comp.dc(abstol=1e-9, maxiters=200)
         stats = comp.handle.stats()
         wave = comp.tran((0.0, 2e-10), 1e-11, method="be", save_idxs=[lc.index_of("p0"), lc.index_of("p31")])
