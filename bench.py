@@ -57,6 +57,14 @@ WORKLOADS = {
                     "sp_mos1 Verilog-A model, synthetic 5 V card, 5 fF parasitic per net): 16384 points (4 corners x "
                     "4096 draws), DC op (PCNR + fallbacks) + adaptive trapezoidal/LTE transient (0, 6e-7); "
                     "table-driven kernels, one lane per warp"),
+    "ring": dict(tspan=(0.0, float(os.environ.get("CB200_RING_TSTOP", "1e-6"))), dt=1e-12, save_every=1, save="1", steps=0,
+                 limit=False, adaptive=True, reltol=1e-2, lte_abstol=1e-4, dtmax=0.05e-9, cpu_tstop=2e-8,
+                 max_points=int(os.environ.get("CB200_RING_MAXPOINTS", "49152")), probe_per_core=1, fixture="psp_ring",
+                 lanes=int(os.environ.get("CB200_RING_LANES", "1024")),
+                 text="9-stage PSP103 ring oscillator (benchmarks/vacask/ring/cedarsim: 18 PSP103VA FETs with the deck's "
+                      "psp103n / psp103p cards through the emitter, n = 370), swept over the supply voltage (1.0 .. 1.4 V); "
+                      "CedarTranOp + adaptive trapezoidal/LTE transient (0, 1e-6), reltol 1e-2, abstol 1e-4, dtmax 0.05 ns "
+                      "(the reference's benchmark settings, runme.jl:47-67); table-driven kernels, one lane per warp"),
     "c5": dict(tspan=(0.0, 2e-9), dt=1e-12, save_every=1, save="p0", steps=0, limit=True, adaptive=True,
                reltol=float(os.environ.get("CB200_C5_RELTOL", "1e-5")), lte_abstol=1e-6,
                max_points=int(os.environ.get("CB200_C5_MAXPOINTS", "4096")), fixture="mos1_c6288", lanes=1,
@@ -147,6 +155,13 @@ def build_sweep(args):
         lc = workloads.load_fixture(W["fixture"]) if os.path.exists(workloads.fixture_path(W["fixture"])) \
             else workloads.load_workload(W["fixture"])
         return cb, lc, lc.P
+    if args.workload == "ring":
+        lc = workloads.load_fixture(W["fixture"]) if os.path.exists(workloads.fixture_path(W["fixture"])) \
+            else workloads.load_workload(W["fixture"])
+        P = args.lanes or W["lanes"]
+        assert lc.lane_soa.shape[0] == 1, "the ring fixture sweeps the supply voltage only"
+        lc.lane_soa, lc.P = np.ascontiguousarray(np.linspace(1.0, 1.4, P)[None, :]), P
+        return cb, lc, P
     if args.workload in ("c3", "c1"):
         lc = workloads.load_workload(W["fixture"])
         if args.workload == "c1":
@@ -175,7 +190,7 @@ def oracle_opts():
     import cadnip_oracle as ora
     if W.get("adaptive"):
         return ora.make_tran_opts(method=1, adaptive=1, dt=DT, reltol=W["reltol"], lte_abstol=W["lte_abstol"],
-                                  max_points=W["max_points"], limit=W["limit"])
+                                  max_points=W["max_points"], limit=W["limit"], dtmax=W.get("dtmax", 0.0))
     return ora.make_tran_opts(method=0, dt=DT, save_every=SAVE_EVERY, limit=W["limit"])
 
 
@@ -187,11 +202,21 @@ def cpu_oracle_rate(lc, sample_lanes, nthreads=0):
         ora.load_va_models(lc.va_c_source)
     sub = dict(lc.netlist_tables()); sub["par"] = np.ascontiguousarray(sub["par"][sample_lanes])
     nls = ora.OracleNetlist(sub)
-    t0 = time.perf_counter()
-    r = ora.sweep_tran(nls, ora.make_spec(mode="tran"), TSPAN[0], TSPAN[1], oracle_opts(), [lc.index_of(W["save"])],
-                       nthreads=nthreads)
-    dt = time.perf_counter() - t0
-    return len(sample_lanes) / dt, int(r["newton_iters"].sum()), dt
+    # "cpu_tstop": the oracle integrates only the first part of the transient (a periodic steady
+    # state: every part costs the same) and the rate is scaled to the whole span
+    tstop = W.get("cpu_tstop", TSPAN[1])
+    frac = (tstop - TSPAN[0]) / (TSPAN[1] - TSPAN[0])
+    # the TIMED leg uses the oracle's fixed-pattern sparse LU (what KLU does for the reference); its dense
+    # partial-pivot LU stays the checker of the parity tests and of the spot check below
+    ora.set_linear_solver(1)
+    try:
+        t0 = time.perf_counter()
+        r = ora.sweep_tran(nls, ora.make_spec(mode="tran"), TSPAN[0], tstop, oracle_opts(), [lc.index_of(W["save"])],
+                           nthreads=nthreads)
+        dt = time.perf_counter() - t0
+    finally:
+        ora.set_linear_solver(0)
+    return len(sample_lanes) * frac / dt, int(r["newton_iters"].sum()), dt
 
 
 def model_op_counts(lc, lanes):
@@ -311,7 +336,8 @@ def run_b200(args):
     def tran_resident():
         if adaptive:
             return comp.tran_adaptive(TSPAN, dt0=DT, method="trap", save_idxs=save, reltol=W["reltol"],
-                                      lte_abstol=W["lte_abstol"], max_points=W["max_points"], limit=W["limit"])
+                                      lte_abstol=W["lte_abstol"], max_points=W["max_points"], limit=W["limit"],
+                                      dtmax=W.get("dtmax", 0.0))
         return comp.tran(TSPAN, DT, method="be", save_idxs=save, save_every=SAVE_EVERY, limit=W["limit"])
 
     def step_resident():
@@ -505,7 +531,8 @@ def run_b200(args):
             # spot check of the measured pass against the oracle (8 lanes spread over the sweep)
             chk = np.linspace(0, P - 1, min(P, 8), dtype=np.int64)
             sub = dict(lc.netlist_tables()); sub["par"] = np.ascontiguousarray(sub["par"][chk])
-            ro = ora.sweep_tran(ora.OracleNetlist(sub), ora.make_spec(mode="tran"), TSPAN[0], TSPAN[1], oracle_opts(),
+            chk_tstop = W.get("cpu_tstop", TSPAN[1])        # ring: the first 20 ns (5 periods) of the microsecond
+            ro = ora.sweep_tran(ora.OracleNetlist(sub), ora.make_spec(mode="tran"), TSPAN[0], chk_tstop, oracle_opts(),
                                 [lc.index_of(W["save"])])
             if adaptive:                                  # ragged time axes: same grid expected, compare point by point
                 diff, tdiff, same_counts = 0.0, 0.0, True
@@ -513,6 +540,8 @@ def run_b200(args):
                     ng, no = int(first_count[lane]), int(ro["T"][q])
                     same_counts &= (ng == no)
                     m = min(ng, no)
+                    if chk_tstop < TSPAN[1]:
+                        m = max(1, no - 2)          # the oracle's last step is cut to its shorter span
                     tdiff = max(tdiff, float(np.max(np.abs(first_t[:m, lane] - ro["t"][q, :m]))))
                     a, b = first_u[:m, lane], ro["u"][q, :m, 0]
                     diff = max(diff, float(np.max(np.abs(a - b) / (ATOL / W["reltol"] + np.maximum(np.abs(a), np.abs(b))))))
@@ -532,11 +561,25 @@ def run_b200(args):
                     raise SystemExit(f"bench.py: GPU waveform differs from the oracle by {diff}")
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "newton_iters_per_sec": it / secs,
-                                    "sample": f"{n_sample} of {P} lanes (strided over the sweep), full "
+                                    "linear_solver": "fixed-pattern sparse LU (oracle linear solver 1)",
+                                    "sample": f"{n_sample} of {P} lanes (strided over the sweep), " +
+                                              (f"the first {W['cpu_tstop']:g} s of the {TSPAN[1]:g} s transient (periodic steady state; "
+                                               f"rate scaled to the full span), " if "cpu_tstop" in W else "full ") +
                                               f"{'adaptive' if adaptive else str(W['steps']) + '-step'} transient each, "
                                               f"OpenMP over lanes, {secs:.1f} s"}
         if args.workload == "c1" and world == 1:
             line["c1"] = c1_eval_times(cb, backend)
+        if args.workload == "ring":
+            us_iter_lane = 1e6 * wall / args.steps / max(iters_per_step, 1)
+            line["ring"] = {"n": lc.n, "lanes": P, "newton_iters_per_lane": iters_per_step / P,
+                            "timepoints_per_lane": float(np.mean(first_count)),
+                            "us_per_newton_iter_amortised": us_iter_lane,
+                            "us_per_newton_iter_one_lane_latency": us_iter_lane * P,
+                            "reference_published": {"cadnip_us_per_iter": 1376.0, "vacask_us_per_iter": 27.8,
+                                                    "cadnip_points": 43968, "cadnip_newton_iters": 242293, "cadnip_wall_s": 333.5,
+                                                    "source": "doc/ring_oscillator_investigation.md:297-313 (dev box, 1 thread)"},
+                            "note": "amortised = wall / (Newton iterations of ALL lanes): the throughput figure of a sweep; "
+                                    "one-lane latency = wall / iterations of ONE lane (every lane advances concurrently)"}
         if args.workload == "c5":
             ms_iter = 1e3 * wall / args.steps / max(iters_per_step, 1)
             line["c5"] = {"n": lc.n, "nnz_J": nnz_j, "nnz_LU": int(nnz_lu), "timepoints": int(first_count[0]),

@@ -612,12 +612,16 @@ def stamp(dev, ctx: MNAContext, *ports, t=0.0, mode="tran", x=ZERO_VECTOR):
                 loc.append(ctx.alloc_internal_node(f"{m.name}_{node}", dev.name))
         nodes_now = [int(x) for x in loc]
         var = m.variant(dev.given, dev.detect_vdep(spec, ctx, xvec, nodes_now), dev.vsites(spec, nodes_now))
+        aliased = dev.aliased_sites(nodes_now)
         S = STATE_DEPENDENT
         for item in var.stamp_plan():
             if item[0] == "I":                         # alloc_current!(ctx, name, instance), vasim.jl:3256-3278, :2366
-                _, slot, iname = item
+                _, slot, iname, site = item
                 assert slot == len(loc)
-                loc.append(ctx.alloc_current(f"{m.name}_{iname}", dev.name))
+                if site is not None and aliased[site]:     # `if p_node != n_node`: nothing allocated, nothing stamped
+                    loc.append(0)
+                else:
+                    loc.append(ctx.alloc_current(f"{m.name}_{iname}", dev.name))
             elif item[0] == "L":                         # alloc_limit!(ctx, name, instance, p, n; init=0.0)
                 _, slot, pi, ni, lname = item
                 assert slot == len(loc)

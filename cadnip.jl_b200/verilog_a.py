@@ -38,6 +38,7 @@ from __future__ import annotations
 
 import hashlib
 import math
+import os
 import re
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple
@@ -45,6 +46,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 CHARGE_SCALE = 1e12          # src/mna/contrib.jl:39
+_BULK_AFTER = 64             # instances of one parameter set after which the Q/V probe is decided per set
 
 # Emit the bias-independent part of a module (parameter / temperature preprocessing) as a separate
 # set-up section that runs once per kernel and hands its results to the per-iteration code through
@@ -75,33 +77,169 @@ _SCALE = {"T": 1e12, "G": 1e9, "M": 1e6, "K": 1e3, "k": 1e3, "m": 1e-3, "u": 1e-
           "p": 1e-12, "f": 1e-15, "a": 1e-18}
 
 
-def _preprocess(src: str) -> str:
-    """`ifdef/`ifndef/`else/`endif with nothing defined (the reference defines no macros
-    for these models); object-like `define NAME value."""
-    out, stack, defs = [], [], {}
-    for line in src.split("\n"):
-        s = line.strip()
-        if s.startswith("`ifdef"):
-            stack.append(s.split()[1] in defs); continue
-        if s.startswith("`ifndef"):
-            stack.append(s.split()[1] not in defs); continue
-        if s.startswith("`else"):
-            stack[-1] = not stack[-1]; continue
-        if s.startswith("`endif"):
-            stack.pop(); continue
-        if not all(stack):
+_STD_INCLUDES = ("discipline.h", "disciplines.vams", "constants.h", "constants.vams")
+_STD_DEFINES = {"M_PI": "3.14159265358979323846", "M_TWO_PI": "6.28318530717958647652", "M_E": "2.7182818284590452354",
+                "M_SQRT2": "1.41421356237309504880", "M_LN2": "0.69314718055994530942", "M_LN10": "2.30258509299404568402",
+                "P_Q": "1.602176462e-19", "P_K": "1.3806503e-23", "P_EPS0": "8.854187817e-12", "P_CELSIUS0": "273.15",
+                "P_H": "6.62606876e-34", "P_C": "2.99792458e8", "P_U0": "1.2566370614e-6"}
+
+
+def _strip_comments(text: str) -> str:
+    """// and /* */ comments out (string literals respected), newlines kept."""
+    out, i, n = [], 0, len(text)
+    while i < n:
+        c = text[i]
+        if c == '"':
+            j = i + 1
+            while j < n and text[j] != '"':
+                j += 2 if text[j] == "\\" else 1
+            out.append(text[i:j + 1]); i = j + 1
+        elif text.startswith("//", i):
+            j = text.find("\n", i)
+            i = n if j < 0 else j
+        elif text.startswith("/*", i):
+            j = text.find("*/", i + 2)
+            seg = text[i:(n if j < 0 else j + 2)]
+            out.append("\n" * seg.count("\n")); i = n if j < 0 else j + 2
+        else:
+            out.append(c); i += 1
+    return "".join(out)
+
+
+def _preprocess(src: str, base_dir: Optional[str] = None, defs: Optional[Dict[str, Tuple]] = None) -> str:
+    """The Verilog-A compiler directives the model sources use: `include (relative to the including
+    file; the standard discipline / constants headers are built in), `define -- object-like and
+    FUNCTION-like with arguments, multi-line with backslash continuation, nested use --, `undef,
+    `ifdef / `ifndef / `else / `endif.  PSP103 is written in this macro language
+    (models/PSPModels.jl/va/Common103_macrodefs.include, PSP103_macrodefs.include)."""
+    defs = {k: (None, v) for k, v in _STD_DEFINES.items()} if defs is None else defs
+    text = _strip_comments(src.replace("\\\r\n", " ").replace("\\\n", " "))
+    out: List[str] = []
+    frames: List[List] = [[text, 0]]             # (text, position): macro bodies are pushed for rescanning
+    cond: List[bool] = []
+    ident = re.compile(r"[A-Za-z_][A-Za-z0-9_$]*")
+    depth_guard = 0
+
+    def rest_of_line(fr):
+        t, i = fr
+        j = t.find("\n", i)
+        j = len(t) if j < 0 else j
+        fr[1] = j
+        return t[i:j]
+
+    while frames:
+        fr = frames[-1]
+        t, i = fr
+        if i >= len(t):
+            frames.pop()
             continue
-        if s.startswith("`define"):
-            parts = s.split(None, 2)
-            if "(" in parts[1]:
-                raise VAError("Verilog-A: function-like `define macros are not supported")
-            defs[parts[1]] = parts[2] if len(parts) > 2 else ""
+        c = t[i]
+        active = all(cond)
+        if c == '"':
+            j = i + 1
+            while j < len(t) and t[j] != '"':
+                j += 2 if t[j] == "\\" else 1
+            if active:
+                out.append(t[i:j + 1])
+            fr[1] = j + 1
             continue
-        out.append(line)
-    text = "\n".join(out)
-    for k, v in defs.items():
-        text = re.sub(r"`" + re.escape(k) + r"\b", v, text)
-    return text
+        if c != "`":
+            if active or c == "\n":
+                out.append(c)
+            fr[1] = i + 1
+            continue
+        m = ident.match(t, i + 1)
+        if not m:
+            raise VAError("Verilog-A: stray backtick")
+        name = m.group(0)
+        fr[1] = m.end()
+        if name in ("ifdef", "ifndef"):
+            arg = rest_of_line(fr).split()
+            cond.append((arg[0] in defs) == (name == "ifdef") if arg else False)
+            continue
+        if name == "else":
+            rest_of_line(fr)
+            cond[-1] = not cond[-1]
+            continue
+        if name == "endif":
+            rest_of_line(fr)
+            cond.pop()
+            continue
+        if not active:
+            continue
+        if name == "define":
+            line = rest_of_line(fr).strip()
+            dm = ident.match(line)
+            if not dm:
+                raise VAError("Verilog-A: malformed `define")
+            params = None
+            k = dm.end()
+            if k < len(line) and line[k] == "(":           # function-like: the parenthesis follows immediately
+                close = line.index(")", k)
+                params = [x.strip() for x in line[k + 1:close].split(",") if x.strip()]
+                k = close + 1
+            defs[dm.group(0)] = (params, line[k:].strip())
+            continue
+        if name == "undef":
+            defs.pop(rest_of_line(fr).strip(), None)
+            continue
+        if name == "include":
+            line = rest_of_line(fr).strip()
+            fname = line.strip('"<> ')
+            if os.path.basename(fname) in _STD_INCLUDES:
+                continue
+            if base_dir is None:
+                raise VAError(f"Verilog-A: `include \"{fname}\" needs the directory of the source (load_va)")
+            with open(os.path.join(base_dir, fname)) as f:
+                inc = _strip_comments(f.read().replace("\\\r\n", " ").replace("\\\n", " "))
+            frames.append([inc + "\n", 0])
+            continue
+        if name in ("timescale", "resetall", "default_discipline", "default_transition"):
+            rest_of_line(fr)
+            continue
+        if name not in defs:
+            raise VAError(f"Verilog-A: macro `{name} is not defined")
+        params, body = defs[name]
+        if params is not None:
+            t, i = fr
+            while i < len(t) and t[i] in " \t\n":
+                i += 1
+            if i >= len(t) or t[i] != "(":
+                raise VAError(f"Verilog-A: macro `{name} needs arguments")
+            args, cur, depth, j = [], [], 0, i + 1
+            while True:
+                if j >= len(t):
+                    raise VAError(f"Verilog-A: unterminated argument list of `{name}")
+                ch = t[j]
+                if ch == '"':
+                    e = j + 1
+                    while t[e] != '"':
+                        e += 2 if t[e] == "\\" else 1
+                    cur.append(t[j:e + 1]); j = e + 1
+                    continue
+                if ch in "([{":
+                    depth += 1
+                elif ch in ")]}":
+                    if depth == 0:
+                        break
+                    depth -= 1
+                elif ch == "," and depth == 0:
+                    args.append("".join(cur).strip()); cur = []; j += 1
+                    continue
+                cur.append(ch); j += 1
+            args.append("".join(cur).strip())
+            fr[1] = j + 1
+            if len(args) != len(params) and not (len(params) == 0 and args == [""]):
+                raise VAError(f"Verilog-A: macro `{name} takes {len(params)} arguments, got {len(args)}")
+            amap = dict(zip(params, args))
+            body = ident.sub(lambda mm: amap.get(mm.group(0), mm.group(0)), body)
+        depth_guard += 1
+        if len(frames) > 200:
+            raise VAError(f"Verilog-A: macro `{name} expands recursively")
+        frames.append([" " + body + " ", 0])
+    if cond:
+        raise VAError("Verilog-A: unterminated `ifdef")
+    return "".join(out)
 
 
 def _lex(src: str) -> List[Tuple[str, str]]:
@@ -128,8 +266,8 @@ def _number(tok: str) -> float:
 # parser -> tiny AST (tuples)
 # --------------------------------------------------------------------------- #
 class _Parser:
-    def __init__(self, src: str):
-        self.t = _lex(_preprocess(src))
+    def __init__(self, src: str, base_dir: Optional[str] = None):
+        self.t = _lex(_preprocess(src, base_dir))
         self.i = 0
 
     def peek(self):
@@ -251,7 +389,12 @@ class _Parser:
         typ = self.next()[1]
         while True:
             name = self.ident()
-            names.append(name)
+            # block-local declarations (`begin : name  real x; ...`) land in the enclosing scope; two
+            # blocks declaring the same temporary share one variable (each assigns before it reads)
+            if name not in types:
+                names.append(name)
+            elif types[name] != typ:
+                raise VAError(f"Verilog-A: {name!r} is declared both {types[name]} and {typ}")
             types[name] = typ
             if self.accept("="):
                 inits[name] = self.expr()
@@ -416,14 +559,15 @@ class _Parser:
         left = sub()
         while self.peek()[1] in ops and self.peek()[0] == "op":
             op = self.next()[1]
+            op = {"&": "&&", "|": "||"}.get(op, op)      # bitwise and / or of 0/1 comparison results
             left = ("bin", op, left, sub())
         return left
 
     def lor(self):
-        return self._binary(self.land, ("||",))
+        return self._binary(self.land, ("||", "|"))
 
     def land(self):
-        return self._binary(self.eq, ("&&",))
+        return self._binary(self.eq, ("&&", "&"))
 
     def eq(self):
         return self._binary(self.cmp, ("==", "!="))
@@ -632,6 +776,8 @@ class _Interp:
             return (1.0 if args[0][1] in self.given else 0.0, 0.0)
         if fn == "$port_connected":
             return (1.0, 0.0)
+        if fn == "ddx":
+            return (0.0, 0.0)                             # operating-point outputs only; not on the value path
         if fn == "$simparam":
             name = args[0][1]
             if name == "iniLim":
@@ -1335,7 +1481,16 @@ class _Emitter:
             return self.user_call(self.mod["functions"][fn], [self.ev(a) for a in args], list(args)), None
         if fn == "$port_connected":                    # va_env.jl:146: every port counts as connected
             return self.const(1.0), None
-        if fn in ("idt", "ddx", "absdelay", "transition", "laplace_nd", "laplace_zp"):
+        if fn == "ddx":
+            # ddx(expr, V(node)): the partial the emit-time differentiation already carries.  Its own
+            # partials (second derivatives) are not: the models use ddx for operating-point outputs only
+            # (PSP103 `OPderiv), which never reach a contribution
+            r, q = self.ev(args[0])
+            if args[1][0] != "V" or args[1][2] is not None:
+                raise VAError("Verilog-A: ddx needs a node potential V(n) as its second argument")
+            k = self._node(args[1][1])
+            return (_D(self.temp(r.d[k])) if k in r.d else self.zero()), None
+        if fn in ("idt", "absdelay", "transition", "laplace_nd", "laplace_zp"):
             raise VAError(f"Verilog-A: {fn} is not supported")
         if fn.startswith("$") and fn[1:] in _SYS_MATH:
             fn = fn[1:]                              # $pow(...) etc.: system-function spelling
@@ -1813,12 +1968,12 @@ class VAVariant:
             if n is not None:
                 plan.append(("G", ls, n))
         for br in self.vnamed:                               # branch_current_alloc, vasim.jl:3256-3266
-            plan.append(("I", self.vn_slot[br], f"I_{br}"))
+            plan.append(("I", self.vn_slot[br], f"I_{br}", None))
         for j, slot in self.vs_slot.items():                 # executed V(p,n) <+ sites, vasim.jl:2362-2393
             a, b, _ = self.vsites[j]
             p = self.nodes.index(a)
             n = self.nodes.index(b) if b is not None else None
-            plan.append(("I", slot, f"I_V_{a}_{b if b is not None else '0'}"))
+            plan.append(("I", slot, f"I_V_{a}_{b if b is not None else '0'}", j))
             plan.append(("G", p, slot))
             if n is not None:
                 plan.append(("G", n, slot))
@@ -2187,9 +2342,9 @@ class VAModel:
     """A parsed Verilog-A module.  ``model(**params)`` makes an instance; the emitted code
     lives in per-(given-set, detection outcome) variants."""
 
-    def __init__(self, source: str):
+    def __init__(self, source: str, base_dir: Optional[str] = None):
         self.source = source
-        self.mod = _Parser(source).module()
+        self.mod = _Parser(source, base_dir).module()
         m = self.mod
         self.name = m["name"]
         self.ports = list(m["ports"])
@@ -2360,10 +2515,9 @@ class VAInstance:
         return out
 
     def vsites(self, spec, node_of_slot: List[int]) -> Tuple[bool, ...]:
-        """Per potential-contribution site: does this instance carry its branch current?  The
-        generated stamp! decides at run time: the statement must execute (its conditions depend on
-        parameters only) and its two nodes must not be aliased to one another (`if p_node !=
-        n_node`, vasim.jl:2365).  Evaluated by running the module on the host at zero bias."""
+        """Per potential-contribution site: does this instance EXECUTE it?  (Conditions depend on
+        parameters only; evaluated by running the module on the host at zero bias, once per parameter
+        set.)  Whether an executed site's nodes are aliased to one another is `aliased_sites`."""
         sites = self.model.mod.get("vsites", ())
         if not sites:
             return ()
@@ -2376,11 +2530,23 @@ class VAInstance:
             it = self._interp(spec)
             it.run({name: 0.0 for name in nodes}, {})
             executed = self.model._host_cache[key] = frozenset(it.vexec)
+        # the alias idiom (`V(int, port) <+ 0`, detect_short_circuits): executed AND aliased means the site
+        # produced the alias and nothing else -- it is left out of the variant altogether
+        alias = self.aliased_sites(node_of_slot)
+        idiom = self.model.collapse_sites
+        return tuple(j in executed and not (j in idiom and alias[j]) for j in range(len(sites)))
+
+    def aliased_sites(self, node_of_slot: List[int]) -> Tuple[bool, ...]:
+        """Per potential-contribution site: are its two nodes the same circuit node for THIS instance
+        (`if p_node != n_node`, vasim.jl:2365)?  Such a site allocates no branch current and stamps
+        nothing; the emitted code is the same -- the site's current slot is bound to ground (0), and
+        every stamp that touches ground is dropped, on the host and on the device alike."""
+        nodes = self.model.nodes
         out = []
-        for j, (a, b, br) in enumerate(sites):
+        for a, b, br in self.model.mod.get("vsites", ()):
             pa = node_of_slot[nodes.index(a)]
             pb = node_of_slot[nodes.index(b)] if b is not None else 0
-            out.append(j in executed and pa != pb)
+            out.append(pa == pb)
         return tuple(out)
 
     def _param_key(self, spec) -> Tuple:
@@ -2395,6 +2561,50 @@ class VAInstance:
         vals = tuple((k, _lane0(v)) for k, v in sorted(self.values.items()))
         sim = tuple((f, getattr(spec, f)) for f in _SPEC_FIELDS if hasattr(spec, f))
         return (vals, tuple(sorted(self.given)), sim, getattr(spec, "mode", "dcop"), _lane0(self.mfactor))
+
+    def _vdep_by_parameter_set(self, spec, var) -> Optional[Tuple[bool, ...]]:
+        """Large netlists (c6288: 10 112 instances of two parameter sets): the outcome of the reference's
+        Q/V probe (contrib.jl:214-257) is a property of the parameter set for every model met so far -- a
+        charge that is non-linear in the branch voltage is detected at any pair of random operating
+        points.  Once a parameter set has been stamped _BULK_AFTER times the probe is run ON THAT SET at
+        eight random bias points with the reference's criterion (sticky over consecutive pairs, as its
+        detection passes are); the verdict is used for all further instances of the set, which then skip
+        the per-instance interpreter run.  None: probe per instance."""
+        key = ("vdep", self._param_key(spec), tuple(var.vexec))
+        ent = self.model._host_cache.get(key)
+        if ent is None:
+            ent = self.model._host_cache[key] = {"count": 0, "flags": None, "tried": False}
+        ent["count"] += 1
+        if ent["flags"] is not None:
+            return ent["flags"]
+        if ent["count"] <= _BULK_AFTER or ent["tried"]:
+            return None
+        ent["tried"] = True
+
+        # sticky OR over consecutive pairs of eight random operating points, like the reference's passes
+        rng = np.random.default_rng(0xBADC0DE)
+        prev: Dict[int, Tuple[float, float]] = {}
+        numeric = [False] * len(var.branches)
+        for _ in range(8):
+            volt = {name: float(rng.uniform(-1.0, 1.0)) for name in var.nodes}
+            vold = {k: float(rng.uniform(-1.0, 1.0)) for k in var.lim_branches}
+            it = self._interp(spec)
+            it.run(volt, vold)
+            for bi, k in enumerate(var.branches):
+                if not var.reactive[bi]:
+                    continue
+                v = volt[k[0]] - (volt[k[1]] if k[1] is not None else 0.0)
+                q = it.mfactor * it.Q.get(k, 0.0)
+                if bi in prev:
+                    v0, q0 = prev[bi]
+                    if abs(v) > 1e-6 and abs(v0) > 1e-6:
+                        c1, c0 = q / v, q0 / v0
+                        diff, mx = abs(c1 - c0), max(abs(c1), abs(c0))
+                        if diff > 1e-15 and (mx < 1e-30 or diff / mx > 1e-6):
+                            numeric[bi] = True
+                prev[bi] = (v, q)
+        ent["flags"] = tuple(numeric)
+        return ent["flags"]
 
     def _charge_free(self, spec, var) -> bool:
         """True when every reactive branch of this parameter set carries the charge 0.0 at three
@@ -2430,6 +2640,9 @@ class VAInstance:
         def xval(i):
             return float(xs[i - 1]) if 0 < i <= len(xs) else 0.0
         volt = {name: xval(cn) for name, cn in zip(var.nodes, node_of_slot)}
+        flags_by_key = self._vdep_by_parameter_set(spec, var)
+        if flags_by_key is not None:
+            return flags_by_key
         if self._charge_free(spec, var):
             flags = []
             for bi, key in enumerate(var.branches):
@@ -2493,7 +2706,7 @@ def va(source: str) -> VAModel:
 def load_va(path: str) -> VAModel:
     """A module from a ``.va`` file (e.g. the VADistiller models)."""
     with open(path) as f:
-        return VAModel(f.read())
+        return VAModel(f.read(), base_dir=_os.path.dirname(_os.path.abspath(path)))
 
 
 # --------------------------------------------------------------------------- #

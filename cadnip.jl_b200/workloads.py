@@ -440,6 +440,87 @@ def mos1_c6288(sp_mos1, n_fets=None):
     return CircuitSweep(_B(f), Sweep(dummy=[0.0]), dummy=0.0)
 
 
+PSP_DIR = "/root/reference/models/PSPModels.jl/va/"
+RING_DIR = "/root/reference/benchmarks/vacask/ring/cedarsim/"
+
+
+def spice_model_cards(path):
+    """`.model name type key=value ...` cards of a SPICE include file -> {name: (type, {key: float})}."""
+    cards = {}
+    for ln in _spice_lines(path):
+        f = ln.split()
+        if f[0].lower() != ".model":
+            continue
+        kv = {}
+        for tok in f[3:]:
+            k, v = tok.split("=")
+            kv[k.lower()] = float(v)
+        cards[f[1].lower()] = (f[2].lower(), kv)
+    return cards
+
+
+def psp_ring(psp103, stages=9, lanes=None):
+    """The 9-stage PSP103 ring oscillator of benchmarks/vacask/ring/cedarsim/{runme.sp, models.inc}: the
+    one small circuit the reference publishes a per-Newton-iteration time for (1376 us, VACASK 27.8 us;
+    doc/ring_oscillator_investigation.md:297-313).  Inverters of pmos w = 20u / nmos w = 10u, l = 1u with
+    the deck's psp103p / psp103n cards (ad / as / pd / ps from the nmos / pmos wrappers: ld = ls = 0.5u),
+    vdd 1.2 V, a 10 uA / 1 ns current pulse into node 1 to start it.  Lanes: supply voltage."""
+    cards = spice_model_cards(RING_DIR + "models.inc")
+    card_n, card_p = cards["psp103n"][1], cards["psp103p"][1]
+    vdds = [1.2] if lanes is None else list(lanes)
+
+    def fet(card, name, w, l):
+        ld = 0.5e-6
+        return psp103(name=name, w=w, l=l, ad=w * ld, **{"as": w * ld}, pd=2 * (w + ld), ps=2 * (w + ld), **card)
+
+    def f(ctx, p):
+        vdd = get_node(ctx, "vdd")
+        nodes = [get_node(ctx, str(k + 1)) for k in range(stages)]
+        from .mna import CurrentSource
+        stamp(CurrentSource(0.0, tran=PulseWave(0.0, 10e-6, 1e-9, 1e-9, 1e-9, 1e-9, 1.0), name="i0"), ctx, 0, nodes[0])
+        for k in range(stages):
+            i, o = nodes[k], nodes[(k + 1) % stages]
+            stamp(fet(card_p, f"xu{k + 1}.xmp", 20e-6, 1e-6), ctx, o, i, vdd, vdd)
+            stamp(fet(card_n, f"xu{k + 1}.xmn", 10e-6, 1e-6), ctx, o, i, 0, 0)
+        stamp(VoltageSource(p.vdd, name="vdd"), ctx, vdd, 0)
+    return CircuitSweep(_B(f), Sweep(vdd=vdds))
+
+
+def psp_c6288(psp103, n_fets=None):
+    """SURVEY 8d config C5 as the reference runs it: the c6288 16x16 multiplier with its 10 112 PSP103VA
+    FETs and the deck's model cards (benchmarks/vacask/c6288/cedarsim/{runme.sp, multiplier.inc,
+    models.inc}; nmos w = 0.5u, pmos w = 1u, l = 0.2u, ad / as / pd / ps from ld = ls = 0.5u), vdd 1.2 V,
+    32 pulse drivers 0 -> 1.2 V (td = tr = 0.1 ns) behind 1 ohm.  The reference reports 212 228 unknowns
+    for it (90 850 nodes + 70 818 currents + 50 560 charges)."""
+    fets, drivers = c6288_netlist()
+    if n_fets:
+        fets = fets[:n_fets]
+    cards = spice_model_cards(C6288_DIR + "models.inc")
+    card = {1: cards["psp103n"][1], -1: cards["psp103p"][1]}
+    nets, seen = [], set()
+    for _, d, g, s_, b, *_ in fets:
+        for x in (d, g, s_, b):
+            if x not in seen and x != "0":
+                seen.add(x); nets.append(x)
+    used_drivers = [x for x in drivers if x in seen]
+
+    def f(ctx, p):
+        node = {"0": 0}
+        for x in nets:
+            node[x] = get_node(ctx, x)
+        stamp(VoltageSource(1.2, name="vdd"), ctx, node["vdd"], 0)
+        stamp(VoltageSource(0.0, name="vss"), ctx, node["vss"], 0)
+        for x in used_drivers:
+            n_int = get_node(ctx, x + "_drv")
+            stamp(VoltageSource(0.0, tran=PulseWave(0.0, 1.2, 1e-10, 1e-10, 1e-10, 1.0, 2.0), name="vdrv_" + x), ctx, n_int, 0)
+            stamp(Resistor(1.0, name="rdrv_" + x), ctx, n_int, node[x])
+        ld = 0.5e-6
+        for name, d, g, s_, b, typ, w, l in fets:
+            stamp(psp103(name=name, w=w, l=l, ad=w * ld, **{"as": w * ld}, pd=2 * (w + ld), ps=2 * (w + ld), **card[typ]),
+                  ctx, node[d], node[g], node[s_], node[b])
+    return CircuitSweep(_B(f), Sweep(dummy=[0.0]), dummy=0.0)
+
+
 FIXTURES = {
     "mos1_corner": ("mos1", mos1_corner),
     "diode_chain": ("diode", diode_chain),
@@ -456,6 +537,8 @@ FIXTURES = {
     "bsim4_stage": ("bsim4v8", bsim4_stage),
     "mos1_c6288": ("mos1", mos1_c6288),
     "mos1_c6288_slice": ("mos1", lambda m: mos1_c6288(m, 420)),
+    "psp_ring": ("psp103", lambda m: psp_ring(m, lanes=[1.1, 1.2])),
+    "psp_c6288": ("psp103", lambda m: psp_c6288(m)),
 }
 
 
@@ -465,11 +548,17 @@ def lower_fixture(name, models=None):
     model_file, make = FIXTURES[name]
     models = {} if models is None else models
     if model_file not in models:
-        models[model_file] = verilog_a.load_va(VA_DIR + model_file + ".va")
+        models[model_file] = verilog_a.load_va((PSP_DIR if model_file.startswith("psp") else VA_DIR) + model_file + ".va")
     cs = make(models[model_file])
     from .lowering import lower
     params, P = cs.lane_params()
-    lc = lower(cs.builder, params, MNASpec(mode="tran"), P=P)
+    # 10 112 instances of two parameter sets: the voltage-dependent-charge verdict is taken per SET from the
+    # first instance on, so that the circuit carries one emitted variant per set (verilog_a._BULK_AFTER)
+    bulk, verilog_a._BULK_AFTER = verilog_a._BULK_AFTER, (0 if "c6288" in name else verilog_a._BULK_AFTER)
+    try:
+        lc = lower(cs.builder, params, MNASpec(mode="tran"), P=P)
+    finally:
+        verilog_a._BULK_AFTER = bulk
     if name == "mos1_c3":
         lc.lane_exprs = c3_lane_exprs(lc, cs)
     if name == "mos1_dff":
@@ -482,7 +571,7 @@ FIXTURE_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__fil
 # circuits whose kernel sets __graft_entry__.build() prebuilds (the GPU parity tests and bench.py)
 GPU_VA_FIXTURES = ["mos1_corner", "diode_chain", "diode_rs_cap", "mos1_inverter", "mos1_c3", "mos1_dff",
                    "mos1_ring", "mos1_ring_caps", "bjt_ce", "jfet2_cs", "vdmos_cs", "inductor_rl", "bsim4_stage",
-                   "mos1_c6288"]
+                   "mos1_c6288", "psp_ring"]
 
 
 def fixture_path(name: str) -> str:
@@ -498,7 +587,8 @@ def load_workload(name: str, from_source=None):
     """Lowered circuit ``name`` (a key of FIXTURES): va source -> emitter -> lower when the
     reference's .va files are present (from_source=None: auto), else the committed fixture."""
     model_file = FIXTURES[name][0]
-    have = os.path.exists(VA_DIR + model_file + ".va") and (name != "mos1_dff" or os.path.isdir(DFF_DIR))
+    have = os.path.exists((PSP_DIR if model_file.startswith("psp") else VA_DIR) + model_file + ".va") and \
+        (name != "mos1_dff" or os.path.isdir(DFF_DIR))
     if from_source is None:
         from_source = have
     if from_source:

@@ -383,8 +383,9 @@ def test_potential_contributions_structure_and_dc():
     assert x[lc.index_of("mid") - 1] == pytest.approx(5.0 * 5.0 / 100.0, rel=1e-9)
     assert [p[0] for p in LBranch.stamp_plan()] == ["I", "G", "G", "G", "G", "b", "C"]
     assert RShort(rm=0.0).vsites(cb.MNASpec(), [1, 2, 3, 4]) == (True,)
-    assert RShort(rm=0.0).vsites(cb.MNASpec(), [1, 2, 3, 3]) == (False,)      # nodes aliased: nothing to stamp
     assert RShort(rm=1.0).vsites(cb.MNASpec(), [1, 2, 3, 4]) == (False,)      # not executed
+    assert RShort(rm=0.0).aliased_sites([1, 2, 3, 3]) == (True,)              # same circuit node: nothing to stamp
+    assert RShort(rm=0.0).aliased_sites([1, 2, 3, 4]) == (False,)
 
 
 # ---- GPU parity -----------------------------------------------------------------
