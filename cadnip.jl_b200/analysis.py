@@ -137,8 +137,66 @@ class DCSolution:
     def __getitem__(self, name):
         return float(self.x[self._lc.index_of(name) - 1])
 
+    def terminal_currents(self) -> dict:
+        """Operating-point info: the current flowing INTO every terminal of every device that reports
+        one, ``{"i_<device>_<terminal>": amperes}`` (``terminal_currents(ctx, x)``,
+        src/mna/context.jl:1190-1270; registrations devices.jl:706-707, :733-734, :1424-1425, :1589-1590,
+        :1737-1739, :1759, resistor: ohmic).  Evaluated on the host at the converged ``x`` from the
+        lowered device table -- a handful of flops per device, not part of the batched hot path."""
+        return terminal_currents(self._lc, self.x, getattr(self, "_lane", 0))
+
     def __repr__(self):
         return f"DCSolution(n={len(self.x)}, converged={self.converged})"
+
+
+def terminal_currents(lc: LoweredCircuit, x: np.ndarray, lane: int = 0) -> dict:
+    """``terminal_currents(ctx, x)`` (src/mna/context.jl:1251-1270) for one lane of a lowered circuit:
+    entries in registration (device) order, repeated names summed.  Resistors report G (V_p - V_n)
+    (``register_ohmic_terminal_current!``); current sources their DC value; the native diodes the
+    junction current at the solution (the PCNR limit voltage equals V at convergence); SimpleMOSFET the
+    square-law drain current.  (Verilog-A instances are not reported yet.)"""
+    from . import mna as M
+    x = np.asarray(x, dtype=np.float64)
+    out: dict = {}
+
+    def add(dev, term, val):
+        key = f"i_{dev}_{term}"
+        out[key] = out.get(key, 0.0) + float(val)
+
+    def v(i):
+        return 0.0 if i == 0 else float(x[i - 1])
+
+    def par(d, k):
+        r = int(lc.dev_params[lc.dev_param_ptr[d] + k])
+        return float(lc.uniform[r]) if r >= 0 else float(lc.lane_soa[~r][lane])
+
+    for d, kind in enumerate(lc.dev_kind):
+        nb = int(lc.dev_node_ptr[d])
+        nodes = [int(q) for q in lc.dev_nodes[nb:int(lc.dev_node_ptr[d + 1])]]
+        name = lc.dev_names[d]
+        if kind == M.DEV_RESISTOR:
+            g = 1.0 / par(d, 0)
+            add(name, "p", g * (v(nodes[0]) - v(nodes[1])))
+            add(name, "n", g * (v(nodes[1]) - v(nodes[0])))
+        elif kind == M.DEV_ISOURCE:
+            i = par(d, 0)
+            add(name, "p", -i); add(name, "n", i)
+        elif kind in (M.DEV_DIODE, M.DEV_DIODECAP):
+            Is, nVt = par(d, 0), par(d, 1) * par(d, 2)
+            a = (v(nodes[0]) - v(nodes[1])) / nVt
+            i0 = Is * (math.exp(80.0) * (1.0 + (a - 80.0)) - 1.0) if a > 80.0 else Is * (math.exp(a) - 1.0)
+            add(name, "p", i0); add(name, "n", -i0)
+        elif kind == M.DEV_SIMPLEMOS:
+            vgs, vds = v(nodes[1]) - v(nodes[2]), v(nodes[0]) - v(nodes[2])
+            vth, K, lam = par(d, 0), par(d, 1), par(d, 2)
+            if vgs <= vth:
+                ids = 0.0
+            elif vds <= vgs - vth:
+                ids = K * ((vgs - vth) * vds - vds * vds / 2)
+            else:
+                ids = K / 2 * (vgs - vth) ** 2 * (1 + lam * vds)
+            add(name, "d", ids); add(name, "g", 0.0); add(name, "s", -ids)
+    return out
 
 
 class TranSolution:
@@ -205,7 +263,9 @@ class _LazyDCSolutions:
             i += len(self)
         if not 0 <= i < len(self):
             raise IndexError(i)
-        return DCSolution(self.lc, self.x[:, i].copy(), self.status[i] == 0, self.iters[i])
+        sol = DCSolution(self.lc, self.x[:, i].copy(), self.status[i] == 0, self.iters[i])
+        sol._lane = i
+        return sol
 
     def __iter__(self):
         for i in range(len(self)):

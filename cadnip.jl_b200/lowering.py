@@ -62,6 +62,11 @@ class LoweredCircuit:
     dev_state_ptr: Optional[np.ndarray] = None   # [n_dev+1] private state slots per device (VA set-up values)
     va_cuda_header: str = ""        # emitted CUDA for the circuit's Verilog-A modules (cb200_load_va_models)
     va_c_source: str = ""           # the same modules as plain C: input of the CPU oracle, never run by the product
+    # outcome of the voltage-dependent-charge detection per detect_or_cached! call of one builder pass
+    # (VA devices in stamping order, their reactive branches in branch order).  "Outcome only" is what
+    # SURVEY 8c asks to carry over from the host; a checker that wants the SAME structure for a bulk
+    # netlist (per-parameter-set verdicts, verilog_a._BULK_AFTER) replays it instead of probing.
+    va_detect_seq: Optional[np.ndarray] = None
 
     @property
     def n(self) -> int:
@@ -90,7 +95,7 @@ class LoweredCircuit:
     _ARRAYS = {"G_I": np.int64, "G_J": np.int64, "C_I": np.int64, "C_J": np.int64, "b_I": np.int64,
                "dev_kind": np.int32, "dev_flags": np.int32, "dev_node_ptr": np.int32, "dev_nodes": np.int32,
                "dev_param_ptr": np.int32, "dev_params": np.int32, "dev_gbase": np.int64, "dev_cbase": np.int64,
-               "dev_bbase": np.int64, "uniform": np.float64, "limit_init_ref": np.int32,
+               "dev_bbase": np.int64, "uniform": np.float64, "limit_init_ref": np.int32, "va_detect_seq": np.int32,
                "dev_state_ptr": np.int32}
     _PLAIN = ("n_nodes", "n_currents", "n_charges", "n_limits", "node_names", "current_names", "charge_names",
               "limit_names", "P", "dev_names", "dev_user_nodes", "n_user_nodes", "va_cuda_header", "va_c_source")
@@ -318,6 +323,8 @@ def lower(builder, params: Params, spec: MNASpec, P: int = 1) -> LoweredCircuit:
         lane_soa=np.ascontiguousarray(soa, dtype=np.float64), P=P,
         dev_names=names, dev_user_nodes=user_nodes, breakpoints=list(ctx.breakpoints),
         va_models=va_models, n_user_nodes=_user_node_count(ctx),
+        va_detect_seq=np.asarray([int(d.model.vdep[bi]) for d in ctx.devices if d.model is not None
+                                  for bi in range(len(d.model.branches)) if d.model.reactive[bi]], dtype=np.int32),
         dev_state_ptr=np.asarray(state_ptr, dtype=np.int32),
         va_cuda_header=_va.cuda_header(va_models) if va_models else "",
         va_c_source=_va.c_source(va_models) if va_models else "")

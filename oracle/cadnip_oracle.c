@@ -483,8 +483,20 @@ static void va_stamp_C(void *vc, long i, long j, double v) { stamp_C((ora_ctx *)
 static void va_stamp_b(void *vc, long i, double v) { stamp_b((ora_ctx *)vc, va_index(i), v); }
 static void va_record_limit_w(void *vc, long l, double w) { record_limit_w((ora_ctx *)vc, va_index(l), w); }
 /* detect_or_cached!  contrib.jl:214-296 */
+/* Test hook: replay a recorded detection outcome (one flag per detect_or_cached! call of a builder
+ * pass, in call order) instead of probing -- the "outcome only" hand-over of SURVEY 8c for netlists
+ * whose host lowering takes the verdict per parameter set.  NULL / 0 = probe (default).           */
+static const int32_t *g_detect_override = NULL;
+static int64_t g_detect_override_n = 0;
+void ora_set_detect_override(const int32_t *flags, int64_t n) { g_detect_override = flags; g_detect_override_n = n; }
+
 static int va_detect_or_cached(void *vc, double V, double Q)
 {
+    if (g_detect_override) {
+        ora_ctx *c0 = (ora_ctx *)vc;
+        int64_t pos = c0->charge_detection_pos++;
+        return (pos >= 1 && pos <= g_detect_override_n) ? g_detect_override[pos - 1] != 0 : 0;
+    }
     ora_ctx *c = (ora_ctx *)vc;
     int64_t pos = c->charge_detection_pos++;
     if (c->direct) return c->charge_is_vdep[pos - 1];

@@ -149,6 +149,7 @@ typedef struct ora_tran_opts {
 /* Linear solver behind every Newton solve: 0 = dense LU with partial pivoting (default: the
  * CHECKER of the parity tests), 1 = fixed-pattern sparse LU with a kept pivot sequence (what the
  * timed CPU baseline uses; KLU's role at solve.jl:612-613, :667-670).  Process-wide.           */
+void ora_set_detect_override(const int32_t *flags, int64_t n);   /* replay a detection outcome (test hook) */
 int ora_last_dc_tier(void);      /* tier that produced the calling thread's last DC result (-1: none) */
 void ora_set_linear_solver(int kind);
 int ora_get_linear_solver(void);

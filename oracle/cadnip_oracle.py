@@ -396,6 +396,24 @@ def va_op_counts():
     return int(ops[0]), int(ops[1]), int(ops[2])
 
 
+_detect_keep = None
+
+
+def set_detect_override(seq) -> None:
+    """Replay a recorded voltage-dependent-charge detection outcome (LoweredCircuit.va_detect_seq)
+    instead of probing; None restores the probe."""
+    global _detect_keep
+    L = lib()
+    L.ora_set_detect_override.argtypes = [C.POINTER(C.c_int32), C.c_int64]
+    L.ora_set_detect_override.restype = None
+    if seq is None:
+        _detect_keep = None
+        L.ora_set_detect_override(None, 0)
+        return
+    _detect_keep = np.ascontiguousarray(seq, dtype=np.int32)
+    L.ora_set_detect_override(_detect_keep.ctypes.data_as(C.POINTER(C.c_int32)), len(_detect_keep))
+
+
 def last_dc_tier() -> int:
     """Tier of _dc_solve_with_fallbacks that produced this thread's last DC result (-1: none)."""
     return int(lib().ora_last_dc_tier())

@@ -2,6 +2,7 @@
 recording MNAContext (test/mna/core.jl:53-233), lowering, the C-ABI surface, and the
 multi-GPU sharding plumbing under gloo (world_size 2)."""
 import ctypes as C
+import math
 import os
 import re
 
@@ -516,3 +517,25 @@ def test_julia_shim_matches_header():
         assert sum(g[1] for g in got) == C.sizeof(ct), jname          # no implicit padding on either side
     for sym in set(re.findall(r"\(:(cb200_\w+), LIB\[\]\)", src)):
         assert sym in backend.EXPORTED_SYMBOLS, sym
+
+
+def test_terminal_currents_operating_point_info():
+    """``terminal_currents`` (src/mna/context.jl:1251-1270): device terminal currents at the DC point,
+    names ``i_<device>_<terminal>``; KCL closes at every node."""
+    import cadnip_oracle as ora
+    from cadnip_b200.analysis import terminal_currents
+    lc = cb.lower_circuit(cb.MNACircuit(circuits.rectifier(True)))
+    x, ok, it = ora.solve_dc(ora.OracleNetlist(lc.netlist_tables()), ora.make_spec(mode="dcop"))
+    assert ok
+    tc = terminal_currents(lc, x)
+    vout = x[lc.index_of("out") - 1]
+    assert tc["i_R_p"] == pytest.approx((5.0 - vout) / 1000.0, rel=1e-12) and tc["i_R_n"] == -tc["i_R_p"]
+    assert tc["i_D1_p"] == pytest.approx(tc["i_R_p"], rel=1e-6)            # series loop: same current
+    assert tc["i_D1_p"] == pytest.approx(1e-14 * (math.exp(vout / 0.026) - 1.0), rel=1e-9)
+    assert -x[lc.index_of("I_V1") - 1] == pytest.approx(tc["i_R_p"], rel=1e-9)
+    lc = cb.lower_circuit(cb.MNACircuit(circuits.mos_amp, vg=1.5, rd=2e3))
+    x, ok, it = ora.solve_dc(ora.OracleNetlist(lc.netlist_tables()), ora.make_spec(mode="dcop"))
+    tc = terminal_currents(lc, x)
+    vd = x[lc.index_of("d") - 1]
+    assert tc["i_M1_d"] == pytest.approx((3.3 - vd) / 2e3 + tc["i_DC1_p"], rel=1e-6)   # KCL at the drain node
+    assert tc["i_M1_g"] == 0.0 and tc["i_M1_s"] == -tc["i_M1_d"]
