@@ -222,6 +222,19 @@ EXPORTED_SYMBOLS = [
     "cb200_wave_free", "cb200_get_stats", "cb200_debug_exp", "cb200_measure_fp64_peak", "cb200_flop_model"]
 
 
+def va_models_cached(models) -> bool:
+    """Is the kernel set of these models already built (in-tree cache)?  PSP103's takes ~45 minutes of
+    ptxas, sp_bsim4v8's ~20: callers that cannot wait check first."""
+    L = lib()
+    L.cb200_va_models_cached.restype = C.c_int
+    L.cb200_va_models_cached.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    text = models if isinstance(models, str) else None
+    if text is None:
+        from . import verilog_a
+        text = verilog_a.cuda_header(models)
+    return bool(L.cb200_va_models_cached(text.encode(), _CSRC.encode(), GEN_DIR.encode()))
+
+
 def prebuild_va_models(models) -> None:
     """Build the kernel set for a circuit's Verilog-A models into the in-tree cache
     (no GPU needed; what Handle.load_va_models would otherwise build on first use).

@@ -1210,6 +1210,13 @@ extern "C" int cb200_load_va_models(cb200_handle *h, const char *cuda_header, co
     return CB200_OK;
 }
 
+// 1 when the kernel set of this header is already in the cache (no nvcc run needed), else 0
+extern "C" int cb200_va_models_cached(const char *cuda_header, const char *csrc_dir, const char *cache_dir)
+{
+    if (!cuda_header || !csrc_dir || !cache_dir) return 0;
+    return va_kernel_set_cached(cuda_header, csrc_dir, cache_dir) ? 1 : 0;
+}
+
 extern "C" int cb200_set_tstops(cb200_handle *h, const double *tstops, int32_t n)
 {
     if (!h || n < 0 || (n > 0 && !tstops)) return fail(h, CB200_EINVAL, "cb200_set_tstops: bad arguments");

@@ -361,33 +361,51 @@ void unload_kernel_set(KernelSet &k)
     k = KernelSet();
 }
 
-std::string build_va_kernel_set(const std::string &va_header_text, const std::string &csrc_dir,
-                                const std::string &cache_dir, KernelSet &out)
+// Cache key of a kernel set: the emitted header, the sources it is rebuilt from, and CB200_NVCC_FLAGS
+// (extra compiler flags for tuning experiments, e.g. -DCB200_WARP_MIN_BLOCKS=8).
+static std::string va_kernel_set_keys(const std::string &va_header_text, const std::string &csrc_dir,
+                                      std::string &hdr_hex, std::string &so_hex, std::string &extra)
 {
     uint64_t h = 1469598103934665603ULL;
     h = fnv1a(h, va_header_text);
     char hex[32];
     snprintf(hex, sizeof hex, "%016llx", (unsigned long long)h);
-    mkdir(cache_dir.c_str(), 0755);
-    const std::string hdr = cache_dir + "/va_" + hex + ".cuh";
-    if (!exists(hdr)) {
-        const std::string tmp = hdr + ".tmp" + std::to_string((long)getpid());
-        { std::ofstream f(tmp); f << va_header_text; if (!f) return "va models: cannot write " + tmp; }
-        if (rename(tmp.c_str(), hdr.c_str()) != 0) return "va models: cannot move " + tmp;
-    }
-    // the kernel set also depends on the sources it is rebuilt from
+    hdr_hex = hex;
     uint64_t hk = h;
     for (const char *f : {"/kernels.cu", "/lane_kernels.cuh", "/warp_kernels.cuh", "/group_kernels.inc", "/kernels.h", "/../../include/cadnip_b200.h"}) {
         std::string body = slurp(csrc_dir + f);
         if (body.empty()) return "va models: cannot read " + csrc_dir + f;
         hk = fnv1a(hk, body);
     }
-    // CB200_NVCC_FLAGS: extra compiler flags for the kernel set (tuning experiments, e.g.
-    // -DCB200_WARP_MIN_BLOCKS=8); part of the cache key
     const char *extra_env = getenv("CB200_NVCC_FLAGS");
-    const std::string extra = extra_env ? extra_env : "";
+    extra = extra_env ? extra_env : "";
     hk = fnv1a(hk, extra);
     snprintf(hex, sizeof hex, "%016llx", (unsigned long long)hk);
+    so_hex = hex;
+    return "";
+}
+
+bool va_kernel_set_cached(const std::string &va_header_text, const std::string &csrc_dir, const std::string &cache_dir)
+{
+    std::string hdr_hex, so_hex, extra;
+    if (!va_kernel_set_keys(va_header_text, csrc_dir, hdr_hex, so_hex, extra).empty()) return false;
+    return exists(cache_dir + "/kern_" + so_hex + ".so");
+}
+
+std::string build_va_kernel_set(const std::string &va_header_text, const std::string &csrc_dir,
+                                const std::string &cache_dir, KernelSet &out)
+{
+    std::string hdr_hex, so_hex, extra;
+    std::string ke = va_kernel_set_keys(va_header_text, csrc_dir, hdr_hex, so_hex, extra);
+    if (!ke.empty()) return ke;
+    mkdir(cache_dir.c_str(), 0755);
+    const std::string hdr = cache_dir + "/va_" + hdr_hex + ".cuh";
+    if (!exists(hdr)) {
+        const std::string tmp = hdr + ".tmp" + std::to_string((long)getpid());
+        { std::ofstream f(tmp); f << va_header_text; if (!f) return "va models: cannot write " + tmp; }
+        if (rename(tmp.c_str(), hdr.c_str()) != 0) return "va models: cannot move " + tmp;
+    }
+    const char *hex = so_hex.c_str();
     const std::string so = cache_dir + "/kern_" + hex + ".so", log = cache_dir + "/kern_" + hex + ".log";
     if (!exists(so)) {
         const std::string tmp = cache_dir + "/kern_" + hex + ".tmp" + std::to_string((long)getpid()) + ".so";

@@ -60,6 +60,7 @@ struct KernelSet {
 };
 // Writes the emitted Verilog-A header into cache_dir, rebuilds kernels.cu against it
 // (nvcc, cached by content hash) and loads the result.  Returns "" on success.
+bool va_kernel_set_cached(const std::string &va_header_text, const std::string &csrc_dir, const std::string &cache_dir);
 std::string build_va_kernel_set(const std::string &va_header_text, const std::string &csrc_dir,
                                 const std::string &cache_dir, KernelSet &out);
 void unload_kernel_set(KernelSet &k);

@@ -2297,10 +2297,15 @@ class VAVariant:
         unknowns (it is the builder) and decides node collapse and charge formulation at
         run time, as the reference's generated stamp! does."""
         nsites = len(self.vsites)
-        if nsites and not all(self.vexec):
+        want = tuple(j not in self.model.collapse_sites for j in range(nsites))
+        if nsites and tuple(self.vexec) != want:
             # the oracle is the builder: which sites execute is decided by ITS run of the code, so
-            # the C carries all of them (guarded by run-time flags) under this variant's name
-            full = VAVariant(self.model, self.given, tuple(self.vdep), (True,) * nsites)
+            # the C carries every potential-contribution site that can allocate a branch current
+            # (guarded by run-time flags) under this variant's name.  The alias idiom sites never do
+            # -- executed means aliased means nothing to stamp -- and stay out, so that a module whose
+            # only sites are idiom sites (sp_mos1, sp_diode) yields the SAME statements, hence the same
+            # rounding, in the C and the CUDA text
+            full = VAVariant(self.model, self.given, tuple(self.vdep), want)
             full.cname = self.cname
             return full.emit_c()
         N = self.N

@@ -393,6 +393,9 @@ def _close(a, b, rtol=1e-9, atol=1e-12):
                                   "inductor_rl", "bsim4_stage"])
 def test_gpu_va_models_dc(name):
     lc = fixture(name)
+    from cadnip_b200 import backend
+    if name == "bsim4_stage" and not backend.va_models_cached(lc.va_cuda_header):
+        pytest.skip("the sp_bsim4v8 kernel set is not in the in-tree cache (nvcc needs ~20 minutes for it)")
     nl = oracle_of(lc)
     comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
     try:
@@ -622,7 +625,10 @@ def test_gpu_c6288_slice_matches_oracle():
 def test_gpu_psp103_ring_matches_oracle():
     """PSP103 on the GPU: the ring's operating point (CedarTranOp) and the first 5 ns of its trapezoidal
     transient against the oracle, 1e-9 relative / 1e-12 absolute, equal Newton counts."""
+    from cadnip_b200 import backend
     lc = fixture("psp_ring")
+    if not backend.va_models_cached(lc.va_cuda_header):
+        pytest.skip("the PSP103 kernel set is not in the in-tree cache (ptxas needs ~45 minutes for it)")
     nl = oracle_of(lc)
     save = [lc.index_of(str(k)) for k in range(1, 10)]
     comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
