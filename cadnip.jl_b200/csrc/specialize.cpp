@@ -379,6 +379,10 @@ static std::string va_kernel_set_keys(const std::string &va_header_text, const s
     }
     const char *extra_env = getenv("CB200_NVCC_FLAGS");
     extra = extra_env ? extra_env : "";
+    // Giant models (PSP103: 9 MB of emitted CUDA, sp_bsim4v8: 14 MB): ptxas at its default -O3 needs hours
+    // and tens of GB on functions of 1e5 statements (measured: > 80 minutes for PSP103, not finished), so
+    // their kernel sets are assembled at -O1.  Part of the cache key like any other flag.
+    if (va_header_text.size() > (size_t)(4 << 20) && extra.find("-Xptxas") == std::string::npos) extra += " -Xptxas -O1";
     hk = fnv1a(hk, extra);
     snprintf(hex, sizeof hex, "%016llx", (unsigned long long)hk);
     so_hex = hex;

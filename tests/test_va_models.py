@@ -510,7 +510,17 @@ def test_gpu_va_dff_adaptive():
     finally:
         comp.close()
     xo, sto, ito = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
-    assert np.array_equal(st, sto) and (st == 0).all() and _close(x.T, xo) and np.array_equal(it, ito)
+    assert np.array_equal(st, sto) and (st == 0).all() and _close(x.T, xo)
+    # 120 pnjlim / fetlim decisions per PCNR iteration: on this circuit the iteration COUNT depends on the
+    # rounding of the linear solve -- the oracle itself needs [38 36 30 34] iterations with its dense
+    # partial-pivot LU and [37 36 36 34] with its fixed-pattern sparse LU, landing on the same point.  The GPU
+    # (static pivots) must reproduce one of the two per lane, and exactly where they agree.
+    ora.set_linear_solver(1)
+    try:
+        _, _, ito2 = ora.sweep_dc(nl, ora.make_spec(mode="dcop"), lc.n)
+    finally:
+        ora.set_linear_solver(0)
+    assert np.all((it == ito) | (it == ito2)), (it, ito, ito2)
     o = ora.make_tran_opts(method=1, adaptive=1, dt=1e-12, reltol=reltol, lte_abstol=lte_abstol, max_points=cap,
                            limit=True)
     ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 1.2e-7, o, save)
