@@ -23,6 +23,7 @@ from .lowering import lower, lower_circuit, LoweredCircuit, StructuralSweepError
 from .analysis import (dc, tran, DCSolution, TranSolution, CompiledSweep, compile_sweep,
                        expand_breakpoints, breakpoints, CedarTranOp, CedarUICOp, state_abstol)
 from .verilog_a import va, VAModel, VAError
+from .behavioral import BehavioralVoltageSource, BehavioralCurrentSource
 from . import backend
 
 __all__ = [n for n in dir() if not n.startswith("_")]

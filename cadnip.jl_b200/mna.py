@@ -468,6 +468,15 @@ def stamp(dev, ctx: MNAContext, *ports, t=0.0, mode="tran", x=ZERO_VECTOR):
     if isinstance(dev, _Source) and len(ports) == 4 and isinstance(ports[3], str) \
             and ports[3] in ("dcop", "tran", "tranop", "ac"):
         ports = ports[:2]
+    from .behavioral import _Behavioral
+    if isinstance(dev, _Behavioral):                   # devices.jl:1079-1131 (traced closure -> emitted module)
+        inst, ctrl = dev.lower()
+        before = ctx.n_currents
+        stamp(inst, ctx, *ports, *ctrl)
+        if dev.kind == "V" and ctx.n_currents == before + 1:
+            ctx.current_names[-1] = "I_" + dev.name    # alloc_current!(ctx, :I_, B.name)
+            return CurrentIndex(ctx.n_currents)
+        return None
     pr: List[Index] = []
     for p in ports:
         if isinstance(p, (CurrentIndex, ChargeIndex, LimitIndex)):

@@ -776,6 +776,8 @@ class _Interp:
             return (1.0 if args[0][1] in self.given else 0.0, 0.0)
         if fn == "$port_connected":
             return (1.0, 0.0)
+        if fn == "$explicit":
+            return (self.ev(args[0])[0], 0.0)
         if fn == "ddx":
             return (0.0, 0.0)                             # operating-point outputs only; not on the value path
         if fn == "$simparam":
@@ -1450,6 +1452,13 @@ class _Emitter:
             return self.const(1.0 if args[0][1] in self.given else 0.0), None
         if fn == "$mfactor":
             return _D("va_mfactor"), None
+        if fn == "$explicit":
+            # value of the argument with NO partials: the contribution then carries the value in b and nothing
+            # in G -- the explicit stamping of the behavioural sources (devices.jl:1079-1131: value_fn evaluated
+            # at the current iterate, stamp_b! only).  Not Verilog-A; used by cadnip_b200.behavioral only.
+            r, q = self.ev(args[0])
+            self._no_react(q, "$explicit")
+            return _D(r.v, {}, r.const), None
         if fn == "$temperature":                       # _mna_spec_.temp + 273.15 (vasim.jl:1181)
             return self.extra(("temperature",)), None
         if fn == "$vt":                                # (temp + 273.15) * 8.617333262e-5 (vasim.jl:1183)

@@ -388,6 +388,34 @@ def test_potential_contributions_structure_and_dc():
     assert RShort(rm=0.0).aliased_sites([1, 2, 3, 4]) == (False,)
 
 
+def test_behavioral_sources_trace_and_explicit_stamping():
+    """BehavioralVoltageSource / BehavioralCurrentSource (devices.jl:1003-1131): the closure is traced into a
+    one-statement module; the value lands in b only (no Jacobian entries), the current of the voltage form is
+    named I_<name>, current flows from n to p."""
+    cs = GPU_SWEEPS["bsrc"]()
+    params, P = cs.lane_params()
+    lc = cb.lower(cs.builder, params, cb.MNASpec(mode="dcop"), P=P)
+    assert lc.current_names == ["I_V1", "I_Vb", "I_B1"]
+    ora.load_va_models(lc.va_c_source)
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    x, st, it = ora.sweep_dc(nl, ora.make_spec(mode="dcop", ), lc.n)
+    assert (st == 0).all()
+    gain = np.asarray(params.gain)
+    # DC: the pulse is at 0 -> mid = 0; out = gain tanh(-0.2) + 0.1; sq = 0; fb: v = -1e3 (1e-3 + gfb v) -> v = -1 / 1.25
+    assert np.allclose(x[:, lc.index_of("out") - 1], gain * np.tanh(-0.2) + 0.1, rtol=1e-12)
+    assert np.allclose(x[:, lc.index_of("sq") - 1], 0.0, atol=1e-15)
+    # (I1 pulls 1 mA out of fb; the fixed-point iteration stops at the Newton tolerance, not at rounding)
+    assert np.allclose(x[:, lc.index_of("fb") - 1], -0.8, rtol=1e-6)
+    assert np.allclose(x[:, lc.index_of("I_B1") - 1], -(gain * np.tanh(-0.2) + 0.1) / 2e3, rtol=1e-12)
+    # explicit stamping: v_{k+1} = 1 - 0.25 v_k contracts by 4 per iteration -- a Newton iteration with the
+    # partial in G would need two
+    assert np.all(it > 8)
+    with pytest.raises(cb.VAError):
+        cb.BehavioralCurrentSource(lambda V: math.exp(V("a"))).lower()
+    with pytest.raises(cb.VAError):
+        cb.BehavioralCurrentSource(lambda V: 1.0 if V("a") > 0 else 0.0).lower()
+
+
 # ---- GPU parity -----------------------------------------------------------------
 def _sweep_vs_oracle(cs, tran=None):
     params, P = cs.lane_params()
@@ -427,7 +455,28 @@ def _capmos_stage(ctx, params):
     stamp(JunctionCap(Cj0=2e-13, phi=0.8, m=0.5, name="Jdb"), ctx, 0, d)     # reverse-biased drain junction
 
 
+def _bsrc(ctx, params):
+    """Behavioural sources (devices.jl:1003-1131): a voltage B-source driven by a filtered pulse, a current
+    B-source with np.where, and a current B-source that senses its own node (explicit stamping -> the
+    Newton loop is a fixed-point iteration with loop gain gfb * 1 kOhm)."""
+    stamp(VoltageSource(0.0, tran=cb.PulseWave(0.0, params.va, 2e-6, 1e-6, 1e-6, 6e-6, 20e-6), name="V1"), ctx, "in", 0)
+    stamp(Resistor(1e3, name="R1"), ctx, "in", "mid")
+    stamp(cb.Capacitor(1e-9, name="C1"), ctx, "mid", 0)
+    stamp(Resistor(1e3, name="R2"), ctx, "mid", 0)
+    stamp(VoltageSource(1.0, name="Vb"), ctx, "bias", 0)
+    stamp(cb.BehavioralVoltageSource(lambda V: params.gain * np.tanh(V("mid") - 0.2) + 0.1 * V("bias"), name="B1"),
+          ctx, "out", 0)
+    stamp(Resistor(2e3, name="RL"), ctx, "out", 0)
+    stamp(cb.BehavioralCurrentSource(lambda V: np.where(V("mid") > 0.3, 1e-3 * (V("mid") - 0.3) ** 2, 0.0), name="B2"),
+          ctx, "sq", 0)
+    stamp(Resistor(1e3, name="Rsq"), ctx, "sq", 0)
+    stamp(cb.CurrentSource(1e-3, name="I1"), ctx, 0, "fb")
+    stamp(Resistor(1e3, name="Rfb"), ctx, "fb", 0)
+    stamp(cb.BehavioralCurrentSource(lambda V: -params.gfb * V("fb"), name="B3"), ctx, "fb", 0)
+
+
 GPU_SWEEPS = {
+    "bsrc": lambda: cb.CircuitSweep(B(_bsrc), cb.ProductSweep(va=[0.5, 1.0, 2.0], gain=[1.0, 2.5]), gfb=0.25e-3),
     "inverter": lambda: cb.CircuitSweep(inverter(0.0), cb.ProductSweep(vin=np.linspace(0.0, 3.0, 13),
                                                                         kn=[0.5e-3, 1e-3, 2e-3])),
     "capmos": lambda: cb.CircuitSweep(B(_capmos_stage), cb.ProductSweep(rg=[500.0, 1e3, 2e3], k=[0.5e-3, 1e-3])),
@@ -507,6 +556,24 @@ def test_gpu_va_potential_contributions(name):
     if name == "vref":
         va = np.linspace(-1.0, 2.0, 7)
         assert np.allclose(x[:, lc.index_of("o") - 1], 2.0 * va ** 2 + 0.25, rtol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec", [False, True], ids=["table", "specialised"])
+def test_gpu_behavioral_sources(spec):
+    """B-sources (traced closures, explicit stamping) on the device: DC and a BE transient vs the oracle."""
+    cs = GPU_SWEEPS["bsrc"]()
+    lc, out = _sweep_vs_oracle(cs, tran=((0.0, 2e-5), 1e-7, "be", spec))
+    x, xo, st, sto = out["dc"]
+    assert np.array_equal(st, sto) and (st == 0).all()
+    assert _close(x, xo), float(np.max(np.abs(x - xo)))
+    gpu, ref, r, ro, is_spec = out["tran"]
+    assert is_spec == spec
+    assert np.array_equal(r["status"], ro["status"]) and (r["status"] == 0).all()
+    assert _close(gpu, ref[:, :gpu.shape[1], :]), float(np.max(np.abs(gpu - ref[:, :gpu.shape[1], :])))
+    assert np.array_equal(r["newton_iters"], ro["newton_iters"])
+    sq = gpu[:, :, lc.index_of("sq") - 1]
+    assert sq.max() > 0.05                                 # the squarer switched on during the pulse
 
 
 @pytest.mark.gpu

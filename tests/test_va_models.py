@@ -523,19 +523,46 @@ def test_gpu_va_dff_adaptive():
     assert np.all((it == ito) | (it == ito2)), (it, ito, ito2)
     o = ora.make_tran_opts(method=1, adaptive=1, dt=1e-12, reltol=reltol, lte_abstol=lte_abstol, max_points=cap,
                            limit=True)
-    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 1.2e-7, o, save)
-    assert (r["status"] == 0).all() and np.array_equal(r["status"], ro["status"])
-    print("time points per lane: gpu", r["count"].tolist(), "oracle", ro["T"].tolist())
-    worst = 0.0
+    # The same sensitivity carries into the adaptive transient: a Newton solve that needs 10 iterations with one
+    # LU rounding and 11 (= a rejected step) with the other changes the time grid from there on.  The oracle's own
+    # two linear solvers give [2441 2378 2376 2340] and [2420 2377 2376 2340] points, identical grids for the
+    # first ~1600 points and waveforms within 2e-10 V of each other over the whole span.  So per lane: the GPU
+    # grid must coincide with one of the oracle's over a long common prefix (same controller, same decisions),
+    # agree there within reltol, have a point count inside the oracle's own spread (2 %), and agree over the
+    # whole span (oracle interpolated onto the GPU grid) within 10 reltol.
+    ros = []
+    for solver in (0, 1):
+        ora.set_linear_solver(solver)
+        try:
+            ros.append(ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 1.2e-7, o, save))
+        finally:
+            ora.set_linear_solver(0)
+    assert (r["status"] == 0).all() and all(np.array_equal(r["status"], ro["status"]) for ro in ros)
+    print("time points per lane: gpu", r["count"].tolist(), "oracle", [ro["T"].tolist() for ro in ros])
+    scale = lte_abstol / reltol
+    worst = worst_span = 0.0
     for p in range(lc.P):
-        ng, no = int(r["count"][p]), int(ro["T"][p])
-        assert ng == no, (p, ng, no)                                      # same controller, same decisions
-        assert np.allclose(r["t"][:ng, p], ro["t"][p, :no], rtol=1e-9, atol=0.0)
+        ng = int(r["count"][p])
+        tg = r["t"][:ng, p]
+        best = None
+        for ro in ros:
+            no = int(ro["T"][p])
+            m = min(ng, no)
+            same = np.isclose(tg[:m], ro["t"][p, :m], rtol=1e-9, atol=0.0)
+            prefix = m if same.all() else int(np.argmin(same))
+            if best is None or prefix > best[0]:
+                best = (prefix, no, ro)
+        prefix, no, ro = best
+        assert abs(ng - no) <= 0.02 * no, (p, ng, no)
+        assert prefix >= min(ng, no) // 2, (p, prefix, ng, no)
         for k in range(len(save)):
-            a, b = r["u"][k, :ng, p], ro["u"][p, :no, k]
-            worst = max(worst, float(np.max(np.abs(a - b) / (lte_abstol / reltol + np.maximum(np.abs(a), np.abs(b))))))
-    print("max scaled waveform difference", worst)
-    assert worst <= reltol
+            a, b = r["u"][k, :prefix, p], ro["u"][p, :prefix, k]
+            worst = max(worst, float(np.max(np.abs(a - b) / (scale + np.maximum(np.abs(a), np.abs(b))))))
+            a = r["u"][k, :ng, p]
+            b = np.interp(tg, ro["t"][p, :no], ro["u"][p, :no, k])
+            worst_span = max(worst_span, float(np.max(np.abs(a - b) / (scale + np.maximum(np.abs(a), np.abs(b))))))
+    print("max scaled waveform difference: common prefix", worst, "whole span (interpolated)", worst_span)
+    assert worst <= reltol and worst_span <= 10 * reltol
 
 
 @pytest.mark.gpu
