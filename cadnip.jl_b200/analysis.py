@@ -449,8 +449,10 @@ def tran(obj, tspan: Tuple[float, float], solver: Optional[str] = None, abstol: 
     """``tran!(circuit, tspan; solver, abstol, reltol, kw...)`` (sweeps.jl:588-601) and
     ``tran!(cs::CircuitSweep, tspan; kw...)`` (sweeps.jl:692-707).
 
-    ``solver``: "ImplicitEuler" | "Trapezoid" | "gear2".  Fixed-step mode is the
-    reference's ``solver=ImplicitEuler()/Trapezoid(), adaptive=false, dt=h``.
+    ``solver``: "ImplicitEuler" | "Trapezoid" | "gear2", or -- adaptive mode only -- "IDA" (also "FBDF",
+    "QNDF", "bdf"): the variable-order (1..5) variable-step BDF controller, the family of the reference's
+    default ``Sundials.IDA`` (DESIGN.md s. 5; the default here stays the trapezoidal controller).  Fixed-step
+    mode is the reference's ``solver=ImplicitEuler()/Trapezoid(), adaptive=false, dt=h``.
     ``initializealg``: ``CedarTranOp()`` (default) or ``CedarUICOp(warmup_steps, dt)``
     (src/mna/dcop.jl); ``u0`` ([n] or [n][P]) is the start state of the latter.
     ``abstol``: a number, or -- adaptive mode -- a mapping with any of ``vntol`` / ``iabstol`` /

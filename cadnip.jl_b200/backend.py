@@ -28,9 +28,10 @@ GEN_DIR = os.path.join(_HERE, "_gen")
 
 OK, EINVAL, ENOMEM, ECUDA, ENODEVICE, ESTATE, ESINGULAR = 0, -1, -2, -3, -4, -5, -6
 LANE_OK, LANE_MAXITER, LANE_SINGULAR, LANE_NONFINITE, LANE_DTMIN = 0, 1, 2, 3, 4
-METHOD_BE, METHOD_TRAP, METHOD_GEAR2 = 0, 1, 2
+METHOD_BE, METHOD_TRAP, METHOD_GEAR2, METHOD_BDF = 0, 1, 2, 3
+# "IDA" / "FBDF" / "QNDF" / "bdf": the variable-order (1..5) variable-step BDF controller (adaptive mode only)
 METHODS = {"be": 0, "implicit_euler": 0, "ImplicitEuler": 0, "trap": 1, "trapezoid": 1,
-           "Trapezoid": 1, "gear2": 2, "bdf2": 2}
+           "Trapezoid": 1, "gear2": 2, "bdf2": 2, "bdf": 3, "IDA": 3, "ida": 3, "FBDF": 3, "QNDF": 3}
 
 
 class CB200Error(RuntimeError):

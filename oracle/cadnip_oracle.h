@@ -37,7 +37,7 @@ enum { ORA_WAVE_NONE = 0, ORA_WAVE_PWL = 1, ORA_WAVE_PULSE = 2, ORA_WAVE_SIN = 3
 enum { ORA_MODE_DCOP = 0, ORA_MODE_TRAN = 1, ORA_MODE_TRANOP = 2, ORA_MODE_AC = 3 };
 enum { ORA_LANE_OK = 0, ORA_LANE_MAXITER = 1, ORA_LANE_SINGULAR = 2, ORA_LANE_NONFINITE = 3,
        ORA_LANE_DTMIN = 4 };
-enum { ORA_METHOD_BE = 0, ORA_METHOD_TRAP = 1, ORA_METHOD_GEAR2 = 2 };
+enum { ORA_METHOD_BE = 0, ORA_METHOD_TRAP = 1, ORA_METHOD_GEAR2 = 2, ORA_METHOD_BDF = 3 };
 
 /* MNASpec, src/mna/solve.jl:57-70 */
 typedef struct ora_spec {

@@ -397,6 +397,53 @@ def test_device_exp_is_within_one_ulp():
 
 
 # ---- lane-per-warp kernels (warp_kernels.cuh) -------------------------------------
+BDF_CASES = [("clipper", clipper_sweep(4, 3), (0.0, 2e-3), 2e-7, ["in", "out"], False, 1e-5),
+             ("clipper_spec_1e-7", clipper_sweep(3, 3), (0.0, 1e-3), 2e-7, ["out"], True, 1e-7),
+             ("mos_amp", SWEEPS[5][1], (0.0, 3e-8), 1e-11, ["d", "g"], False, 1e-4)]
+
+
+@pytest.mark.parametrize("name,cs,tspan,dt0,save,spec,reltol", BDF_CASES, ids=[c[0] for c in BDF_CASES])
+def test_bdf_waveforms_match_oracle(name, cs, tspan, dt0, save, spec, reltol):
+    """Variable-order (1..5) variable-step BDF, the family of the reference's default Sundials.IDA
+    (sweeps.jl:599-601), on the device against the oracle's statement of the same controller: same
+    accept / reject / order decisions (equal time-point counts), time grids and waveforms within reltol."""
+    lc = lowered_sweep(cs, "tran")
+    idx = [lc.index_of(s) for s in save]
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        wave = comp.tran_adaptive(tspan, dt0=dt0, method="IDA", save_idxs=idx, reltol=reltol,
+                                  lte_abstol=1e-3 * reltol, max_points=20000, specialize=spec)
+        assert comp.handle.is_specialized() == spec
+        r = wave.fetch()
+        st = comp.handle.stats()
+        wave.free()
+        wave = comp.tran_adaptive(tspan, dt0=dt0, method="trap", save_idxs=idx, reltol=reltol,
+                                  lte_abstol=1e-3 * reltol, max_points=20000)
+        rt = wave.fetch(); wave.free()
+    finally:
+        comp.close()
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    o = ora.make_tran_opts(method=3, adaptive=1, dt=dt0, reltol=reltol, lte_abstol=1e-3 * reltol, max_points=20000)
+    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), tspan[0], tspan[1], o, idx)
+    print(f"{name}: BDF timepoints gpu {r['count'].tolist()} oracle {ro['T'].tolist()} (trapezoid: {rt['count'].tolist()}) "
+          f"accepted {st['steps_accepted']} rejected {st['steps_rejected']}")
+    assert np.array_equal(r["status"], ro["status"]) and (r["status"] == 0).all()
+    assert np.array_equal(r["count"], ro["T"]), (r["count"], ro["T"])
+    worst = 0.0
+    for lane in range(lc.P):
+        T = int(r["count"][lane])
+        tg, to = r["t"][:T, lane], ro["t"][lane, :T]
+        assert np.allclose(tg, to, rtol=1e-4, atol=0) and tg[-1] == tspan[1] and np.all(np.diff(tg) > 0)
+        for q in range(len(idx)):
+            gpu, ref = r["u"][q, :T, lane], ro["u"][lane, :T, q]       # same grid index for index: no interpolation
+            err = np.abs(gpu - ref) / np.maximum(1.0, np.abs(ref))
+            worst = max(worst, float(err.max()))
+    print(f"{name}: worst scaled waveform difference {worst:.2e} at reltol {reltol:g}")
+    assert worst <= (1.0 if name.startswith("clipper") else 200.0) * reltol
+    if name.startswith("clipper"):
+        assert r["count"].sum() < rt["count"].sum()       # smooth problem, tight tolerance: the higher orders pay
+
+
 def _run_all_analyses(lc, tspan, dt, dt0):
     """DC, the three fixed-step methods (single launch and 3 segments) and the adaptive
     integrator on one lowered sweep; everything a mapping must reproduce."""
@@ -419,6 +466,13 @@ def _run_all_analyses(lc, tspan, dt, dt0):
         valid = np.arange(T)[:, None] < r["count"][None, :]            # [T][P]: points the lane wrote
         out["adaptive"] = (r["count"], r["status"], r["newton_iters"], np.where(valid, r["t"][:T], 0.0),
                            np.where(valid[None], r["u"][:, :T], 0.0))
+        wave = comp.tran_adaptive(tspan, dt0=dt0, method="bdf", save_idxs=save, reltol=1e-5,
+                                  lte_abstol=1e-8, max_points=20000)
+        r = wave.fetch(); wave.free()
+        T = int(r["count"].max())
+        valid = np.arange(T)[:, None] < r["count"][None, :]
+        out["adaptive_bdf"] = (r["count"], r["status"], r["newton_iters"], np.where(valid, r["t"][:T], 0.0),
+                               np.where(valid[None], r["u"][:, :T], 0.0))
     finally:
         comp.close()
     return out

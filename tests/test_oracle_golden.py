@@ -428,3 +428,46 @@ def test_tran_dc_initialised_and_tranop_mode():
     assert 0.55 < vout.max() < 0.80                           # clipped at a diode drop
     assert vout.min() < -4.0                                  # negative half-wave passes
     assert r["newton_iters"] > 2000
+
+
+# ---- variable-order BDF (the IDA family, sweeps.jl:599-601) --------------------------------------
+def _rc_step(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
+    ctx = MNAContext() if ctx is None else ctx
+    stamp(VoltageSource(0.0, tran=cb.PulseWave(0.0, 5.0, 1e-4, 1e-9, 1e-9, 1.0, 2.0), name="V1"), ctx, "in", 0)
+    stamp(Resistor(1e3, name="R1"), ctx, "in", "out")
+    stamp(Capacitor(1e-6, name="C1"), ctx, "out", 0)
+    return ctx
+
+
+def test_bdf_controller_known_answer_and_order_raising():
+    """Oracle's variable-order BDF (orders 1..5, fixed-leading-coefficient form): RC step response against
+    the closed form, breakpoints hit exactly, and -- what makes it variable ORDER -- far fewer steps than the
+    second-order trapezoidal controller at a tight tolerance, with a smaller error."""
+    lc = lower_one(_rc_step)
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    save = [lc.index_of("out")]
+    res = {}
+    for method in (1, 3):
+        o = ora.make_tran_opts(method=method, adaptive=1, dt=1e-7, reltol=1e-7, lte_abstol=1e-10, max_points=200000)
+        r = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 5e-3, o, save)
+        assert r["status"][0] == 0
+        T = int(r["T"][0])
+        t, u = r["t"][0, :T], r["u"][0, :T, 0]
+        assert t[0] == 0.0 and t[-1] == 5e-3 and np.all(np.diff(t) > 0)
+        for stop in (1e-4, 1e-4 + 1e-9):                      # PULSE corners (solve.jl:1847-1918)
+            assert np.min(np.abs(t - stop)) == 0.0
+        after = t >= 1e-4 + 1e-9
+        exact = 5.0 * (1.0 - np.exp(-(t[after] - (1e-4 + 0.5e-9)) / 1e-3))   # ramp of 1 ns ~ a step at its midpoint
+        res[method] = (T, float(np.max(np.abs(u[after] - exact))))
+    (T_trap, e_trap), (T_bdf, e_bdf) = res[1], res[3]
+    print(f"reltol 1e-7: trapezoid {T_trap} points, max error {e_trap:.2e}; BDF(1..5) {T_bdf} points, max error {e_bdf:.2e}")
+    assert e_bdf < 5e-6 and e_trap < 5e-5
+    assert T_bdf < 0.6 * T_trap
+    # loose tolerance: still converges to the same curve
+    o = ora.make_tran_opts(method=3, adaptive=1, dt=1e-7, reltol=1e-3, lte_abstol=1e-6, max_points=20000)
+    r = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 5e-3, o, save)
+    T = int(r["T"][0])
+    assert r["status"][0] == 0 and T < T_bdf
+    t, u = r["t"][0, :T], r["u"][0, :T, 0]
+    after = t >= 1e-4 + 1e-9
+    assert np.max(np.abs(u[after] - 5.0 * (1.0 - np.exp(-(t[after] - (1e-4 + 0.5e-9)) / 1e-3)))) < 2e-2
