@@ -31,6 +31,10 @@ import numpy as np
 
 N_R, N_C = 256, 256
 N_SEGMENTS = int(os.environ.get("CB200_SEGMENTS", "8"))
+# integrator of the adaptive workloads (c4, ring, c5): "trap" (LTE-controlled trapezoid, default) or "bdf" (the
+# variable-order BDF controller of the IDA family, DESIGN.md s. 5)
+ADAPTIVE_METHOD = os.environ.get("CB200_ADAPTIVE_METHOD", "trap")
+assert ADAPTIVE_METHOD in ("trap", "bdf")
 METRIC = "transient_sweep_points_per_sec"
 UNIT = "points/s"
 # parity gate of the same-run spot check against the oracle (north_star, fixed step)
@@ -69,8 +73,9 @@ WORKLOADS = {
                reltol=float(os.environ.get("CB200_C5_RELTOL", "1e-5")), lte_abstol=1e-6,
                max_points=int(os.environ.get("CB200_C5_MAXPOINTS", "4096")), fixture="mos1_c6288", lanes=1, init="uic",
                text="C5 ISCAS c6288 16x16 multiplier (benchmarks/vacask/c6288/cedarsim: 10112 FETs, 32 pulse drivers), "
-                    "single large circuit on 1 GPU; the emitter does not read PSP103 yet -> FALLBACK tier: sp_mos1 cards "
-                    "(vto +-0.4 V, kp 200u/100u, 1 fF per net), n = 45604 (reference with PSP103: 212228), nnz 158870; CedarUICOp "
+                    "single large circuit on 1 GPU; FALLBACK tier: sp_mos1 cards (vto +-0.4 V, kp 200u/100u, 1 fF per net) instead "
+                    "of PSP103 (which emits and lowers -- workloads.psp_c6288, n = 212228 -- but whose 10112-instance kernel "
+                    "set is not built here), n = 45604, nnz 158870; CedarUICOp "
                     "(the reference's DC chain fails on this fallback-tier circuit: undamped Newton overshoots the junction "
                     "exponentials -- restated with SciPy on the host it fails the same way) + adaptive trapezoidal/LTE "
                     "transient (0, 2e-9), lte abstol 1e-6; sparse symbolic analysis (threshold Markowitz on sparse rows), "
@@ -191,7 +196,7 @@ def host_threads() -> int:
 def oracle_opts():
     import cadnip_oracle as ora
     if W.get("adaptive"):
-        return ora.make_tran_opts(method=1, adaptive=1, dt=DT, reltol=W["reltol"], lte_abstol=W["lte_abstol"],
+        return ora.make_tran_opts(method=3 if ADAPTIVE_METHOD == "bdf" else 1, adaptive=1, dt=DT, reltol=W["reltol"], lte_abstol=W["lte_abstol"],
                                   max_points=W["max_points"], limit=W["limit"], dtmax=W.get("dtmax", 0.0))
     return ora.make_tran_opts(method=0, dt=DT, save_every=SAVE_EVERY, limit=W["limit"])
 
@@ -338,7 +343,7 @@ def run_b200(args):
 
     def tran_resident():
         if adaptive:
-            return comp.tran_adaptive(TSPAN, dt0=DT, method="trap", save_idxs=save, reltol=W["reltol"],
+            return comp.tran_adaptive(TSPAN, dt0=DT, method=ADAPTIVE_METHOD, save_idxs=save, reltol=W["reltol"],
                                       lte_abstol=W["lte_abstol"], max_points=W["max_points"], limit=W["limit"],
                                       dtmax=W.get("dtmax", 0.0),
                                       initializealg=cb.CedarUICOp(10, 1e-13) if W.get("init") == "uic" else None)
@@ -513,7 +518,7 @@ def run_b200(args):
                                        f"(rank g: lanes [g*{-(-P // world)}, (g+1)*{-(-P // world)})), structure replicated, "
                                        "no hot-path collective; every rank's waveform block lands in ONE shared "
                                        "page-locked host array [save][T][P] (final gather)") if world > 1 else "1 GPU",
-                       "method": (f"adaptive trapezoidal + LTE, reltol {W['reltol']:g}, <= {W['max_points']} points/lane"
+                       "method": (f"adaptive {'variable-order BDF (1..5, IDA family)' if ADAPTIVE_METHOD == 'bdf' else 'trapezoidal + LTE'}, reltol {W['reltol']:g}, <= {W['max_points']} points/lane"
                                   if adaptive else f"BE fixed dt={DT:g}, {W['steps']} steps"),
                        "numa_cpus": numa,
                        "l2": "256 MiB device memset between steps (inside the timed region)"},

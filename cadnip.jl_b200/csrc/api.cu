@@ -272,6 +272,7 @@ static void layout_workspace(cb200_handle *h)
     p.off_srcc = o; o += (int)h->src_list.size();
     p.off_h1 = o; o += n;
     p.off_h2 = o; o += n;
+    p.off_phi = o; o += 6 * n;
     p.off_LU = o;                       // LU last: its size depends on the schedule
     int64_t nlu = std::max(h->lu[0].host.nlu, h->lu[1].host.nlu);
     if (nlu == 0) nlu = h->st.nnz;
@@ -940,6 +941,9 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
     if (h->P <= 0) return fail(h, CB200_ESTATE, "cb200_tran: call cb200_set_lanes first");
     if (!(t1 > t0) || !(o->dt > 0.0)) return fail(h, CB200_EINVAL, "cb200_tran: need t1 > t0 and dt > 0");
     if (n_save < 0 || (n_save > 0 && !save_idx)) return fail(h, CB200_EINVAL, "cb200_tran: bad save list");
+    if (o->method < CB200_METHOD_BE || o->method > CB200_METHOD_BDF) return fail(h, CB200_EINVAL, "cb200_tran: unknown method");
+    if (o->method == CB200_METHOD_BDF && !o->adaptive)
+        return fail(h, CB200_EINVAL, "cb200_tran: CB200_METHOD_BDF is a variable-step method (adaptive = 1)");
     cudaSetDevice(h->device);
     const int64_t P = h->P;
     const int n = h->st.n;
@@ -968,7 +972,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         }
         CUDA_TRY(h, cudaMemsetAsync(h->d_iters.p, 0, P * sizeof(int), s));
     }
-    const double gamma_nom = (o->method == CB200_METHOD_BE ? 1.0 : o->method == CB200_METHOD_TRAP ? 2.0 : 1.5) / o->dt;
+    const double gamma_nom = (o->method == CB200_METHOD_BE || o->method == CB200_METHOD_BDF ? 1.0 : o->method == CB200_METHOD_TRAP ? 2.0 : 1.5) / o->dt;
     int rc = ensure_lu(h, spec, 1, gamma_nom);
     if (rc != CB200_OK) return rc;
 
@@ -1081,7 +1085,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
         w->T = T;
         const double span = t1 - t0;
         AdaptArgs a{};
-        a.method = o->method == CB200_METHOD_BE ? CB200_METHOD_BE : CB200_METHOD_TRAP;
+        a.method = o->method == CB200_METHOD_BE ? CB200_METHOD_BE : o->method == CB200_METHOD_BDF ? CB200_METHOD_BDF : CB200_METHOD_TRAP;
         a.t0 = t0; a.t1 = t1;
         a.dtmax = o->dtmax > 0 ? o->dtmax : span / 50.0;
         a.dtmin = o->dtmin > 0 ? o->dtmin : span * 1e-12;
@@ -1234,8 +1238,8 @@ extern "C" int cb200_set_tstops(cb200_handle *h, const double *tstops, int32_t n
 extern "C" int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t method, double dt,
                                 const char *csrc_dir, const char *cache_dir, int32_t flags)
 {
-    if (method < 0 || method > 2 || !(dt > 0.0)) return fail(h, CB200_EINVAL, "cb200_specialize: bad method / dt");
-    const double gamma = (method == CB200_METHOD_BE ? 1.0 : method == CB200_METHOD_TRAP ? 2.0 : 1.5) / dt;
+    if (method < 0 || method > 3 || !(dt > 0.0)) return fail(h, CB200_EINVAL, "cb200_specialize: bad method / dt");
+    const double gamma = (method == CB200_METHOD_BE || method == CB200_METHOD_BDF ? 1.0 : method == CB200_METHOD_TRAP ? 2.0 : 1.5) / dt;
     if (!h || !spec || !csrc_dir || !cache_dir) return fail(h, CB200_EINVAL, "cb200_specialize: null argument");
     if (h->P <= 0) return fail(h, CB200_ESTATE, "cb200_specialize: call cb200_set_lanes first");
     cudaSetDevice(h->device);

@@ -30,6 +30,7 @@ struct Program {
     int off_DS;                     // private device state (Verilog-A set-up values)
     int off_srcc;                   // [n_src] warp-cooperative source value cache
     int off_h1, off_h2;             // adaptive history (u_{n-1}, u_{n-2})
+    int off_phi;                    // variable-order BDF: modified divided differences phi[0..5], 6 n slots
     int n_slots;
     // lane-per-warp kernels (warp_kernels.cuh): CSR view of the pattern (row -> nz indices in
     // column order, nz -> column) and three more workspace arrays behind the n_slots above:

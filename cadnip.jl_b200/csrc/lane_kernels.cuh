@@ -92,6 +92,7 @@ struct DynProg {
     __device__ __forceinline__ int off_srcc() const { return p.off_srcc; }
     __device__ __forceinline__ int off_h1() const { return p.off_h1; }
     __device__ __forceinline__ int off_h2() const { return p.off_h2; }
+    __device__ __forceinline__ int off_phi() const { return p.off_phi; }
     // lane-per-warp kernels only (warp_kernels.cuh)
     __device__ __forceinline__ int rowptr(int r) const { return __ldg(p.rowptr + r); }
     __device__ __forceinline__ int row_nz(int q) const { return __ldg(p.row_nz + q); }
@@ -1136,6 +1137,222 @@ __device__ __forceinline__ double lte_atol(const AdaptArgs &a, int i)
     return i < a.cls_i0 ? a.tol_v : i < a.cls_q0 ? a.tol_i : i < a.cls_l0 ? a.tol_q : a.tol_v;
 }
 
+// ---------------------------------------------------------------------------
+// Variable-order, variable-step BDF (orders 1..5), fixed-leading-coefficient form: the integrator
+// family of the reference's default Sundials.IDA (sweeps.jl:599-601).  Scalar state of one lane;
+// the modified divided differences phi[0..5] live in the lane workspace (off_phi + j n).
+// Restated from the published algorithm (Brenan / Campbell / Petzold ch. 5; SUNDIALS, ACM TOMS 31):
+// coefficient recurrences, error estimates at orders k-2 .. k+1, order / step selection, failure
+// rules.  Statement for statement the oracle's (oracle/cadnip_oracle.c: ora_bdf, tran_bdf).
+// ---------------------------------------------------------------------------
+constexpr int kBdfMaxOrd = 5;
+struct Bdf {
+    int kk, kused, knew, ns, phase, nef;
+    double hused, cj, ck;
+    double est, terk, terkm1, erkm1, erkp1;                // of the last error test
+    double psi[kBdfMaxOrd + 1], alpha[kBdfMaxOrd + 1], beta[kBdfMaxOrd + 1];
+    double sigma[kBdfMaxOrd + 1], gam[kBdfMaxOrd + 1];
+
+    __device__ __forceinline__ void restart(double hh)
+    {
+        kk = 1; kused = 0; knew = 1; ns = 0; phase = 0; nef = 0; hused = 0.0; cj = 1.0 / hh; ck = 1.0;
+        est = terk = terkm1 = erkm1 = erkp1 = 0.0;
+        for (int i = 0; i <= kBdfMaxOrd; i++) { psi[i] = hh; alpha[i] = beta[i] = sigma[i] = gam[i] = 0.0; }
+    }
+    // IDASetCoeffs
+    __device__ __forceinline__ void set_coeffs(double hh)
+    {
+        if (hh != hused || kk != kused) ns = 0;
+        ns = ns + 1 < kused + 2 ? ns + 1 : kused + 2;
+        if (kk + 1 >= ns) {
+            beta[0] = 1.0; alpha[0] = 1.0; gam[0] = 0.0; sigma[0] = 1.0;
+            double temp1 = hh;
+            for (int i = 1; i <= kk; i++) {
+                const double temp2 = psi[i - 1];
+                psi[i - 1] = temp1;
+                beta[i] = beta[i - 1] * psi[i - 1] / temp2;
+                temp1 = temp2 + hh;
+                alpha[i] = hh / temp1;
+                sigma[i] = (double)i * sigma[i - 1] * alpha[i];
+                gam[i] = gam[i - 1] + alpha[i - 1] / hh;
+            }
+            psi[kk] = temp1;
+        }
+        double alphas = 0.0, alpha0 = 0.0;
+        for (int i = 0; i < kk; i++) { alphas -= 1.0 / (double)(i + 1); alpha0 -= alpha[i]; }
+        cj = -alphas / hh;
+        ck = fabs(alpha[kk] + alphas - alpha0);
+        if (ck < alpha[kk]) ck = alpha[kk];
+    }
+    // IDARestore (the phi are un-scaled by the caller)
+    __device__ __forceinline__ void restore(double hh)
+    {
+        for (int j = 1; j <= kk; j++) psi[j - 1] = psi[j] - hh;
+    }
+    // IDATestError from the four sums of squares: |ee|, |ee + phi[k]|, |ee + phi[k] + phi[k-1]|, |ee - phi[k+1]|
+    // (each already divided by the weights); true = the step fails the error test
+    __device__ __forceinline__ bool test(double a0, double a1, double a2, double ap, int n)
+    {
+        const double enorm = sqrt(a0 / (double)n);
+        const double erk = sigma[kk] * enorm;
+        terk = (double)(kk + 1) * erk;
+        est = erk; knew = kk;
+        terkm1 = 0.0; erkm1 = 0.0;
+        if (kk > 1) {
+            erkm1 = sigma[kk - 1] * sqrt(a1 / (double)n);
+            terkm1 = (double)kk * erkm1;
+            if (kk > 2) {
+                const double erkm2 = sigma[kk - 2] * sqrt(a2 / (double)n);
+                const double terkm2 = (double)(kk - 1) * erkm2;
+                if (fmax(terkm1, terkm2) <= terk) { knew = kk - 1; est = erkm1; }
+            } else if (terkm1 <= 0.5 * terk) { knew = kk - 1; est = erkm1; }
+        }
+        erkp1 = sqrt(ap / (double)n) / (double)(kk + 2);
+        return ck * enorm > 1.0;
+    }
+    // IDAHandleNFlag after an error-test failure: new order and step
+    __device__ __forceinline__ double after_error_fail(double hh)
+    {
+        nef++;
+        if (nef == 1) {
+            kk = knew;
+            double rr = 0.9 * pow(2.0 * est + 0.0001, -1.0 / (double)(kk + 1));
+            rr = fmax(0.25, fmin(0.9, rr));
+            return hh * rr;
+        }
+        if (nef == 2) { kk = knew; return hh * 0.25; }
+        kk = 1;
+        return hh * 0.25;
+    }
+    // IDACompleteStep (scalar part): order of the next step and its size; `kdone` = order just used
+    __device__ __forceinline__ double complete(double hh)
+    {
+        const int kdone = kk;
+        const int kdiff = kdone - kused;
+        kused = kdone; hused = hh; nef = 0;
+        if (knew == kdone - 1 || kdone == kBdfMaxOrd) phase = 1;
+        if (phase == 0) { kk = kdone + 1; return 2.0 * hh; }
+        int action;                                        // -1 lower, 0 maintain, +1 raise
+        if (knew == kdone - 1) action = -1;
+        else if (kdone == kBdfMaxOrd) action = 0;
+        else if (kdone + 1 >= ns || kdiff == 1) action = 0;
+        else {
+            const double terkp1 = (double)(kdone + 2) * erkp1;
+            if (kdone == 1) action = terkp1 >= 0.5 * terk ? 0 : 1;
+            else if (terkm1 <= fmin(terk, terkp1)) action = -1;
+            else if (terkp1 >= terk) action = 0;
+            else action = 1;
+        }
+        double e = est;
+        if (action == 1) { kk = kdone + 1; e = erkp1; }
+        else if (action == -1) { kk = kdone - 1; e = erkm1; }
+        double hnew = hh;
+        double rr = pow(2.0 * e + 0.0001, -1.0 / (double)(kk + 1));
+        if (rr >= 2.0) hnew = 2.0 * hh;
+        else if (rr <= 1.0) { rr = fmax(0.5, fmin(0.9, rr)); hnew = hh * rr; }
+        return hnew;
+    }
+};
+
+// one attempt begins: scale phi[ns..kk] by beta, predict (IDAPredict): un <- sum phi, dterm <- sum gam phi, u <- un
+template <typename PG, typename W>
+__device__ __forceinline__ void bdf_predict(const PG &pg, W &w, const Bdf &B)
+{
+    const int n = pg.n();
+    #pragma unroll
+    for (int j = 1; j <= kBdfMaxOrd; j++) {
+        if (j >= B.ns && j <= B.kk) {
+            const double bj = B.beta[j];
+            CB_UNROLL
+            for (int i = 0; i < n; i++) w(pg.off_phi() + j * n + i) *= bj;
+        }
+    }
+    CB_UNROLL
+    for (int i = 0; i < n; i++) {
+        double yy = w(pg.off_phi() + i), yp = 0.0;
+        #pragma unroll
+        for (int j = 1; j <= kBdfMaxOrd; j++) {
+            if (j <= B.kk) { const double f = w(pg.off_phi() + j * n + i); yy += f; yp = fma(B.gam[j], f, yp); }
+        }
+        w(pg.off_un() + i) = yy; w(pg.off_dterm() + i) = yp; w(pg.off_u() + i) = yy;
+    }
+}
+
+// a failed attempt (Newton or error test): IDARestore; u <- phi[0] (the last accepted point)
+// `reseed`: the first step after a (re)start failed its error test -- phi[1] = h y' was seeded with y' = 0; the
+// failed solution gives the secant slope, phi[1] <- y_failed - y_0 (see the oracle, tran_bdf)
+template <typename PG, typename W>
+__device__ __forceinline__ void bdf_undo(const PG &pg, W &w, Bdf &B, double hh, bool reseed)
+{
+    const int n = pg.n();
+    B.restore(hh);
+    if (reseed) B.psi[0] = hh;                             // the step the reseeded phi[1] belongs to
+    #pragma unroll
+    for (int j = 1; j <= kBdfMaxOrd; j++) {
+        if (j >= B.ns && j <= B.kk) {
+            const double bj = B.beta[j];
+            CB_UNROLL
+            for (int i = 0; i < n; i++) w(pg.off_phi() + j * n + i) /= bj;
+        }
+    }
+    CB_UNROLL
+    for (int i = 0; i < n; i++) {
+        const double y0 = w(pg.off_phi() + i);
+        if (reseed) w(pg.off_phi() + n + i) = w(pg.off_u() + i) - y0;
+        w(pg.off_u() + i) = y0;
+    }
+}
+
+// phi[j] by run-time order with compile-time slot arithmetic (a specialised kernel's workspace is a register file)
+template <typename PG, typename W>
+__device__ __forceinline__ double bdf_phi(const PG &pg, W &w, int j, int i)
+{
+    const int n = pg.n();
+    double v = 0.0;
+    #pragma unroll
+    for (int q = 0; q <= kBdfMaxOrd; q++) if (q == j) v = w(pg.off_phi() + q * n + i);
+    return v;
+}
+
+template <typename PG, typename W>
+__device__ __forceinline__ bool bdf_error_test(const PG &pg, W &w, const AdaptArgs &a, Bdf &B)
+{
+    const int n = pg.n(), kk = B.kk;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, ap = 0.0;
+    CB_UNROLL
+    for (int i = 0; i < n; i++) {
+        const double ui = w(pg.off_u() + i), yi = w(pg.off_un() + i);
+        const double tol = lte_atol(a, i) + a.reltol * fmax(fabs(ui), fabs(yi));
+        const double ee = ui - yi;
+        double e = ee / tol;
+        a0 += e * e;
+        if (kk > 1) {
+            double d = ee + bdf_phi(pg, w, kk, i);
+            e = d / tol; a1 += e * e;
+            if (kk > 2) { d += bdf_phi(pg, w, kk - 1, i); e = d / tol; a2 += e * e; }
+        }
+        if (kk < kBdfMaxOrd) { e = (ee - bdf_phi(pg, w, kk + 1, i)) / tol; ap += e * e; }
+    }
+    return B.test(a0, a1, a2, ap, n);
+}
+
+// accepted step of order kdone: phi[kdone+1] = ee, phi[kdone] += ee, running sums downwards
+template <typename PG, typename W>
+__device__ __forceinline__ void bdf_advance(const PG &pg, W &w, int kdone)
+{
+    const int n = pg.n();
+    CB_UNROLL
+    for (int i = 0; i < n; i++) {
+        const double ee = w(pg.off_u() + i) - w(pg.off_un() + i);
+        double acc = ee;
+        #pragma unroll
+        for (int j = kBdfMaxOrd; j >= 0; j--) {
+            if (j == kdone + 1) w(pg.off_phi() + j * n + i) = ee;
+            else if (j <= kdone) { acc += w(pg.off_phi() + j * n + i); w(pg.off_phi() + j * n + i) = acc; }
+        }
+    }
+}
+
 template <typename PG, typename LU, typename W>
 __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W &w, const Program &p,
                                                    const SpecArgs &sp, const AdaptArgs &a)
@@ -1164,10 +1381,13 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
     }
     T++;
     const int amethod = PG::kMethod >= 0 ? PG::kMethod : a.method;
+    const bool bdf = amethod == CB200_METHOD_BDF;
     const double abstol2 = a.abstol * a.abstol;
     double t = a.t0, h = a.h0, h1 = 0.0, h2 = 0.0;
     int nhist = 0, istop = 0;
     bool finished = !(t < a.t1);
+    Bdf B;
+    if (bdf) B.restart(h);
     while (true) {
         if (__all_sync(0xffffffffu, finished)) break;
         // ---- choose the step
@@ -1179,8 +1399,25 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
         if (t + hh >= tnext - 1e-3 * hh) { hh = tnext - t; hit = true; }
         const double tn = hit ? tnext : t + hh;
         const bool be = (nhist == 0 || amethod == CB200_METHOD_BE);
-        const double gamma = be ? 1.0 / hh : 2.0 / hh;
-        if (!finished) {
+        double gamma = be ? 1.0 / hh : 2.0 / hh;
+        if (bdf) {
+            if (!finished) {
+                if (nhist == 0) {                          // (re)start: order 1, phi[0] = y, phi[1] = h y' = 0
+                    B.restart(hh);
+                    CB_UNROLL
+                    for (int i = 0; i < pg.n(); i++) {
+                        w(pg.off_phi() + i) = w(pg.off_u() + i);
+                        #pragma unroll
+                        for (int j = 1; j <= kBdfMaxOrd; j++) w(pg.off_phi() + j * pg.n() + i) = 0.0;
+                    }
+                    nhist = 1;
+                }
+                B.set_coeffs(hh);
+                bdf_predict(pg, w, B);
+                fresh = false;                             // the predictor is not the point last evaluated
+            }
+            gamma = B.cj;
+        } else if (!finished) {
             CB_UNROLL
             for (int i = 0; i < pg.n(); i++) {
                 w(pg.off_un() + i) = w(pg.off_u() + i);
@@ -1231,6 +1468,43 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
             }
         }
         if (finished) continue;
+        if (bdf) {
+            bool fail = st != CB200_LANE_OK;
+            if (fail) {                                       // Newton failed: quarter the step
+                bdf_undo(pg, w, B, hh, false);
+                fresh = false;
+                rej++;
+                h = hh / 4.0;
+                if (h < a.dtmin) {
+                    if (status == CB200_LANE_OK) status = (st == CB200_LANE_MAXITER) ? CB200_LANE_DTMIN : st;
+                    finished = true;
+                }
+                continue;
+            }
+            if (bdf_error_test(pg, w, a, B)) {                // IDATestError failed
+                bdf_undo(pg, w, B, hh, B.kused == 0 && B.nef == 0);
+                fresh = false;
+                rej++;
+                h = B.after_error_fail(hh);
+                if (h < a.dtmin || B.nef >= 20) { if (status == CB200_LANE_OK) status = CB200_LANE_DTMIN; finished = true; }
+                continue;
+            }
+            const int kdone = B.kk;
+            const double hnew = B.complete(hh);
+            bdf_advance(pg, w, kdone);
+            t = tn;
+            if (act && T < a.max_points) {
+                a.out_t[(int64_t)T * p.P + lane] = t;
+                for (int q = 0; q < a.n_save; q++)
+                    a.out[((int64_t)q * a.max_points + T) * p.P + lane] = read_u(pg, w, __ldg(a.save_idx + q));
+            }
+            T++;
+            h = hnew > a.dtmax ? a.dtmax : hnew;
+            if (hit && tn < a.t1) nhist = 0;                  // restart after a breakpoint
+            if (!(t < a.t1)) finished = true;
+            else if (T >= a.max_points) { if (status == CB200_LANE_OK) status = CB200_LANE_MAXITER; finished = true; }
+            continue;
+        }
         if (st != CB200_LANE_OK) {                            // Newton failed: shrink and retry
             CB_UNROLL
             for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);

@@ -268,6 +268,7 @@ std::string generate_spec_source(const SpecInput &in)
     emit_const(o, "off_DS", p.off_DS);
     emit_const(o, "off_h1", p.off_h1);
     emit_const(o, "off_h2", p.off_h2);
+    emit_const(o, "off_phi", p.off_phi);
     emit_const(o, "off_GS", p.off_GS);
     emit_const(o, "off_CS", p.off_CS);
     emit_accumulate(o, st, p);

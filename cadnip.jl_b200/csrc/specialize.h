@@ -10,7 +10,7 @@
 
 namespace cb200 {
 
-constexpr int kSpecAbi = 7;
+constexpr int kSpecAbi = 8;
 
 struct SpecInput {
     const Structure *st;

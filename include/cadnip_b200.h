@@ -148,6 +148,8 @@ typedef struct cb200_dc_opts {
 #define CB200_METHOD_BE    0
 #define CB200_METHOD_TRAP  1
 #define CB200_METHOD_GEAR2 2
+#define CB200_METHOD_BDF   3   /* adaptive only: variable-order (1..5) variable-step BDF, the IDA family
+                                  (src/sweeps.jl:599-601); see DESIGN.md s. 5 */
 
 /* Transient options: the keyword surface of tran! that reaches the integrator
  * (src/sweeps.jl:588-665): solver choice (method), adaptive/dt, tolerances,

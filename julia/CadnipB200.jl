@@ -252,7 +252,12 @@ end
 B200() = B200(0)
 
 const RETCODES = Dict(0 => :Success, 1 => :MaxIters, 2 => :Unstable, 3 => :Unstable, 4 => :DtLessThanMin)
-method_id(solver) = solver isa Cadnip.ImplicitEuler ? Int32(0) : solver isa Cadnip.Trapezoid ? Int32(1) : Int32(2)
+# 0 backward Euler, 1 trapezoidal, 2 Gear-2; 3 = the variable-order (1..5) variable-step BDF controller for the
+# IDA / FBDF / QNDF family (adaptive only; `nothing` = tran!'s default Sundials.IDA, src/sweeps.jl:599-601)
+method_id(solver) = solver === nothing ? Int32(3) :
+                    solver isa Cadnip.ImplicitEuler ? Int32(0) : solver isa Cadnip.Trapezoid ? Int32(1) :
+                    (occursin("IDA", string(typeof(solver))) || occursin("BDF", string(typeof(solver))) ||
+                     occursin("QNDF", string(typeof(solver)))) ? Int32(3) : Int32(2)
 
 "`dc!(cs::CircuitSweep; backend = B200())`: all lanes at once, cold start (sweeps.jl:511-532)"
 function Cadnip.dc!(cs::CircuitSweep; backend::B200, abstol = 1e-10, maxiters = 100, continuation = true)
