@@ -1583,7 +1583,9 @@ __device__ __forceinline__ void tran_adaptive_body(const PG &pg, const LU &lu, W
         if (f < 0.2) f = 0.2;
         h = hh * f;
         if (h > a.dtmax) h = a.dtmax;
-        if (hit && tn < a.t1) nhist = 0;                      // restart after a breakpoint
+        // restart after a breakpoint: the first step after it is accepted without an error estimate (no
+        // history), so it is no longer than the initial step the caller asked for
+        if (hit && tn < a.t1) { nhist = 0; h = fmin(h, a.h0); }
         if (!(t < a.t1)) finished = true;
         else if (T >= a.max_points) { if (status == CB200_LANE_OK) status = CB200_LANE_MAXITER; finished = true; }
     }

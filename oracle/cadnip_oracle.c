@@ -2007,6 +2007,7 @@ int ora__tran_adaptive(ora_workspace *w, const ora_structure *s, const ora_spec 
     double dtmin = o->dtmin > 0 ? o->dtmin : span * 1e-12;
     double h = o->dt > 0 ? o->dt : span * 1e-4;
     if (h > dtmax) h = dtmax;
+    const double h0 = h;
     double t = t0, h1 = 0.0, h2 = 0.0;
     int nhist = 0;          /* accepted points since last restart (0: only u_n known) */
     int64_t istop = 0;
@@ -2097,9 +2098,9 @@ int ora__tran_adaptive(ora_workspace *w, const ora_structure *s, const ora_spec 
         if (f < 0.2) f = 0.2;
         h = hh * f;
         if (h > dtmax) h = dtmax;
-        if (hit_stop && tn < t1) {        /* restart after a breakpoint */
-            nhist = 0;
-            h = fmin(h, dtmax);
+        if (hit_stop && tn < t1) {        /* restart after a breakpoint: the first step after it is accepted */
+            nhist = 0;                    /* without an error estimate (no history), so it is no longer than */
+            h = fmin(h, h0);              /* the initial step the caller asked for                           */
         }
         if (T >= cap_T && t < t1) { status = ORA_LANE_MAXITER; break; }
     }
