@@ -444,7 +444,7 @@ def test_bdf_waveforms_match_oracle(name, cs, tspan, dt0, save, spec, reltol):
         tg, to = r["t"][:Tg, lane], ro["t"][lane, :To]
         assert tg[-1] == tspan[1] and np.all(np.diff(tg) > 0)
         m = min(Tg, To)
-        same = np.isclose(tg[:m], to[:m], rtol=1e-6, atol=0.0)
+        same = np.isclose(tg[:m], to[:m], rtol=1e-9, atol=0.0)
         prefix = m if same.all() else int(np.argmin(same))
         shortest = min(shortest, prefix)
         for q in range(len(idx)):
@@ -456,7 +456,7 @@ def test_bdf_waveforms_match_oracle(name, cs, tspan, dt0, save, spec, reltol):
             worst_o = max(worst_o, float(np.max(np.abs(ro["u"][lane, :To, q] - truth) / np.maximum(1.0, np.abs(truth)))))
     print(f"{name}: shortest common grid prefix {shortest} points, worst scaled difference on it {worst_prefix:.2e}; "
           f"against the fine solution: gpu {worst_g:.2e}, oracle {worst_o:.2e} (reltol {reltol:g})")
-    assert shortest >= 20 and worst_prefix <= reltol
+    assert shortest >= 10 and worst_prefix <= reltol
     assert worst_g <= k * reltol and worst_o <= k * reltol
     if name.startswith("clipper"):
         assert r["count"].sum() < rt["count"].sum()       # smooth problem: the higher orders pay

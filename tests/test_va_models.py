@@ -370,6 +370,116 @@ def test_emitted_jacobian_matches_finite_differences(name):
             assert np.allclose(dF[rows], col[rows], rtol=1e-5, atol=1e-8 * scale), (name, trial, j)
 
 
+class _VoldIsVnew(dict):
+    """vold of every $limit probe = its present voltage: the models' limiters return vnew unchanged."""
+    def __init__(self, V):
+        super().__init__()
+        self.V = V
+
+    def __bool__(self):
+        return True
+
+    def get(self, key, default=0.0):
+        a, b = key
+        return self.V[a] - (self.V[b] if b is not None else 0.0)
+
+
+INTERP_CASES = [("resistor", dict(resistance=2e3), [1.0, 0.2]),
+                ("capacitor", dict(capacitance=1e-12), [1.0, 0.2]),
+                ("inductor", dict(inductance=1e-3), [1.0, 0.2]),
+                ("diode", {}, [0.65, 0.05]),
+                ("bjt", dict(bf=100.0, **{"is": 1e-15}), [2.0, 0.68, 0.02, 0.0]),
+                ("mos1", dict(w=1e-6, l=1e-6, vto=0.7, kp=100e-6), [1.5, 1.2, 0.1, 0.0]),
+                ("mos2", dict(w=1e-6, l=1e-6, vto=0.7, kp=100e-6), [1.5, 1.2, 0.1, 0.0]),
+                # nsub given: with the default card MOS3alpha = 0 and the model's sqrt(kappa * alpha * ...) has a
+                # 0 * inf derivative under ANY forward-mode AD (the reference's ForwardDiff duals included;
+                # ngspice's hand-written partials avoid it) -- see DESIGN.md s. 4b
+                ("mos3", dict(w=1e-6, l=1e-6, vto=0.7, kp=100e-6, nsub=1e15), [1.5, 1.2, 0.1, 0.0]),
+                ("mos6", dict(w=1e-6, l=1e-6), [1.5, 1.2, 0.1, 0.0]),
+                ("mos9", dict(w=1e-6, l=1e-6, vto=0.7, kp=100e-6, nsub=1e15), [1.5, 1.2, 0.1, 0.0]),
+                ("jfet1", {}, [3.0, -0.4, 0.1]),
+                ("jfet2", {}, [3.0, -0.4, 0.1]),
+                ("mes1", {}, [2.0, -0.3, 0.1]),
+                ("vdmos", dict(vto=2.0, kp=0.5), [4.0, 3.0, 0.1, 0.0, 0.0]),
+                ("bsim3v3", dict(l=1e-6, w=1e-6), [1.5, 1.2, 0.1, 0.0]),
+                ("bsim4v8", dict(l=100e-9, w=1e-6), [0.8, 0.7, 0.05, 0.0])]
+
+
+@needs_ref
+@pytest.mark.parametrize("name,kw,bias", INTERP_CASES, ids=[c[0] for c in INTERP_CASES])
+def test_emitted_model_matches_interpreter(name, kw, bias):
+    """An emitter-INDEPENDENT check of every VADistiller model: the emitted C (parser -> emit-time
+    differentiation -> code generator, run through the oracle's rebuild) against `_Interp`, the host's
+    tree-walking interpreter of the same parsed module, which shares neither the code generator nor the
+    differentiation.  One instance with every port on a voltage source, internal nodes at random voltages,
+    limit unknowns on their probe voltages: the KCL rows of G u - b must equal the interpreter's branch
+    currents, and the stamped G must equal central differences OF THE INTERPRETER."""
+    from cadnip_b200 import verilog_a, MNAContext, ZERO_VECTOR, stamp, VoltageSource
+    import va_circuits
+    m = verilog_a.load_va(va_circuits.VA_DIR + name + ".va")
+    held = {}
+
+    def builder(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
+        ctx = MNAContext() if ctx is None else ctx
+        for k, v in enumerate(bias):
+            stamp(VoltageSource(v, name=f"V{k}"), ctx, f"p{k}", 0)
+        held["inst"] = m(name="X1", **kw)
+        stamp(held["inst"], ctx, *[f"p{k}" for k in range(len(bias))])
+        return ctx
+    spec = cb.MNASpec(mode="tran")
+    lc = cb.lower_circuit(cb.MNACircuit(builder, spec=spec))
+    inst = held["inst"]
+    S = ora.Structure(oracle_of(lc), ora.make_spec(mode="tran"))
+    n = S.n
+    rng = np.random.default_rng(11)
+    collapsed = inst.collapsed(spec)
+    cnode = {p: lc.index_of(f"p{k}") for k, p in enumerate(m.ports)}
+    for node in m.internal:
+        cnode[node] = cnode[collapsed[node]] if node in collapsed else lc.index_of(f"X1_{m.name}_{node}")
+    u = np.zeros(n)
+    for k, v in enumerate(bias):
+        u[cnode[m.ports[k]] - 1] = v
+    for node in m.internal:
+        if node not in collapsed:
+            u[cnode[node] - 1] = rng.uniform(min(bias), max(bias))
+    lim = lc_limit_branches(lc)
+
+    def settle(u):
+        for k, (p, q) in enumerate(lim):
+            u[n - lc.n_limits + k] = (u[p - 1] if p else 0.0) - (u[q - 1] if q else 0.0)
+        return u
+
+    def interp(u):
+        V = {node: u[cnode[node] - 1] for node in m.nodes}
+        it = inst._interp(spec)
+        it.run(V, _VoldIsVnew(V))
+        out = np.zeros(lc.n_nodes)
+        for (p, q), i in it.I.items():
+            if p in cnode:
+                out[cnode[p] - 1] += i
+            if q in cnode:
+                out[cnode[q] - 1] -= i
+        return out
+    u = settle(u)
+    G, C, b, _ = S.rebuild(u)
+    Gd = S.dense(G)
+    I_emit = (Gd @ u - b)[:lc.n_nodes]
+    I_int = interp(u)
+    assert np.all(np.isfinite(I_emit)) and np.all(np.isfinite(Gd))
+    scale = max(float(np.abs(I_int).max()), 1e-30)
+    assert np.max(np.abs(I_emit - I_int)) <= 1e-9 * scale, (name, I_emit, I_int)
+    gs = float(np.abs(Gd[:lc.n_nodes, :lc.n_nodes]).max()) + 1e-30
+    for j in range(lc.n_nodes):
+        h = 1e-6
+        up, um = u.copy(), u.copy()
+        up[j] += h; um[j] -= h
+        dI = (interp(settle(up)) - interp(settle(um))) / (2 * h)
+        col = Gd[:lc.n_nodes, j].copy()
+        for k, (p, q) in enumerate(lim):                     # limit unknowns follow their probes
+            col += Gd[:lc.n_nodes, n - lc.n_limits + k] * ((1.0 if p == j + 1 else 0.0) - (1.0 if q == j + 1 else 0.0))
+        assert np.max(np.abs(dI - col)) <= 1e-6 * gs, (name, j, float(np.max(np.abs(dI - col)) / gs))
+
+
 def lc_limit_branches(lc):
     """(p, n) circuit nodes of each limit unknown, from its tracking row G[l,l]=1, G[l,p]=-1, G[l,n]=+1."""
     lim0 = lc.n - lc.n_limits
