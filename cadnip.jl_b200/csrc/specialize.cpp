@@ -201,6 +201,78 @@ static void emit_lu(std::ostringstream &o, const char *sname, const Structure &s
     o << "};\n";
 }
 
+// ---------------------------------------------------------------------------
+// Pair mode (small sweeps): TWO warps per 32 lanes.  A lane-per-thread kernel is latency-bound on one
+// warp's dependent chain once a GPU holds fewer lanes than fill it (C3: 12 500 lanes per GPU under
+// 8-way strong scaling run as long as 25 000); most of that chain is the nonlinear device models.  In
+// pair mode a block is dim3(32, 2): both warps carry the SAME 32 lanes with identical register state,
+// each evaluates every second nonlinear device of the lane -- different warps, so the two straight-line
+// model bodies run concurrently instead of one after the other -- and the stamp values cross through
+// shared memory (one [slot][32] row per stamp, two block barriers per Newton iteration).  Everything
+// else (assembly, LU, solves, step control) is computed redundantly by both warps on identical data, so
+// the control flow of the two warps is identical and the results are bit-identical to the single-warp
+// kernel.  Only role 0 accumulates the per-lane counters.  Generated when every nonlinear device is an
+// emitted Verilog-A module (their iterate-dependent pass writes stamp slots and limit-corrector slots only).
+// MEASURED (C3, one B200, profiles/README.md r02r): bit-identical, and SLOWER -- 12 500 lanes 30.4 ms against
+// 15.7 ms, 3 125 lanes 22.9 against 15.4, one lane 8.4 against 6.0: an evaluation pass of ONE body per warp plus
+// the exchange takes twice as long as both bodies in one warp (ptxas: 2072 bytes of spill stack against 408; the
+// 262 exchanged values are all live across the barrier).  So it is opt-in (CB200_PAIR=1), kept for the test
+// that pins its equivalence; the intra-lane parallelism that would pay needs ONE shared model body executed
+// by both threads on per-thread operands (DESIGN.md s. 7).
+struct PairPlan {
+    bool ok = false;
+    std::vector<int> dev[2];       // nonlinear devices of each role
+    std::vector<int> slots[2];     // workspace slots each role's devices write in the iterate-dependent pass
+};
+
+static PairPlan plan_pair(const SpecInput &in)
+{
+    PairPlan pl;
+    const Structure &st = *in.st;
+    const Program &p = *in.prog;
+    if (in.nl_list->size() < 2 || getenv("CB200_NO_PAIR")) return pl;
+    for (int d : *in.nl_list)
+        if ((*in.dev_kind)[d] != CB200_DEV_VA) return pl;
+    const int lim_lo = st.n - st.n_limits;      // limit unknowns: 1-based indices (lim_lo, n]
+    for (size_t q = 0; q < in.nl_list->size(); q++) {
+        const int d = (*in.nl_list)[q], r = (int)(q & 1);
+        pl.dev[r].push_back(d);
+        for (int g = (*in.dev_gbase)[d]; g < (*in.dev_gbase)[d + 1]; g++) pl.slots[r].push_back(p.off_SG + g);
+        for (int c = (*in.dev_cbase)[d]; c < (*in.dev_cbase)[d + 1]; c++) pl.slots[r].push_back(p.off_SC + c);
+        for (int b = (*in.dev_bbase)[d]; b < (*in.dev_bbase)[d + 1]; b++) pl.slots[r].push_back(p.off_SB + b);
+        for (int i = (*in.dev_node_ptr)[d]; i < (*in.dev_node_ptr)[d + 1]; i++) {
+            const int v = (*in.dev_nodes)[i];
+            if (v > lim_lo) pl.slots[r].push_back(p.off_limw + v - 1 - lim_lo);
+        }
+    }
+    pl.ok = true;
+    return pl;
+}
+
+static void emit_pair_program(std::ostringstream &o, const PairPlan &pl)
+{
+    o << "struct SProgP : SProg {\n";
+    o << "    template <typename W>\n    __device__ static __forceinline__ void eval_nonlinear(W &w, double t, int mode, bool initjct)\n    {\n";
+    o << "        SProgP pg;\n        extern __shared__ double cb200_xch[];\n        const int ln = threadIdx.x;\n";
+    const int n0 = (int)pl.slots[0].size();
+    o << "        if (threadIdx.y == 0) {\n";
+    for (int d : pl.dev[0]) o << "            eval_device<1>(pg, w, " << d << ", t, mode, initjct);\n";
+    for (size_t k = 0; k < pl.slots[0].size(); k++)
+        o << "            cb200_xch[" << k * 32 << " + ln] = w(" << pl.slots[0][k] << ");\n";
+    o << "        } else {\n";
+    for (int d : pl.dev[1]) o << "            eval_device<1>(pg, w, " << d << ", t, mode, initjct);\n";
+    for (size_t k = 0; k < pl.slots[1].size(); k++)
+        o << "            cb200_xch[" << (n0 + k) * 32 << " + ln] = w(" << pl.slots[1][k] << ");\n";
+    o << "        }\n        __syncthreads();\n        if (threadIdx.y == 0) {\n";
+    for (size_t k = 0; k < pl.slots[1].size(); k++)
+        o << "            w(" << pl.slots[1][k] << ") = cb200_xch[" << (n0 + k) * 32 << " + ln];\n";
+    o << "        } else {\n";
+    for (size_t k = 0; k < pl.slots[0].size(); k++)
+        o << "            w(" << pl.slots[0][k] << ") = cb200_xch[" << k * 32 << " + ln];\n";
+    o << "        }\n        __syncthreads();\n    }\n};\n";
+    o << "constexpr int kPairSmemBytes = " << (pl.slots[0].size() + pl.slots[1].size()) * 32 * 8 << ";\n";
+}
+
 std::string generate_spec_source(const SpecInput &in)
 {
     const Structure &st = *in.st;
@@ -212,7 +284,7 @@ std::string generate_spec_source(const SpecInput &in)
     if (!in.va_header_path.empty())
         head << "#define CB200_VA_FN " << (getenv("CB200_SPEC_VA_NOINLINE") ? "__noinline__" : "__forceinline__")
              << "\n#define CB200_VA_HEADER \"" << in.va_header_path << "\"\n";
-    head << "#include \"lane_kernels.cuh\"\n";
+    head << "#include <cstdlib>\n#include \"lane_kernels.cuh\"\n";
     head << "namespace {\nusing namespace cb200;\n";
     o << "struct SProg {\n";
     o << "    static constexpr bool kStatic = true;\n    static constexpr int kUnroll = 4096;\n";
@@ -297,6 +369,16 @@ std::string generate_spec_source(const SpecInput &in)
          "{\n    SProg pg; SLuDc lu; RegWs<kSlots> w;\n    dc_body(pg, lu, w, p, sp, a);\n}\n";
     o << "__global__ void __launch_bounds__(kBlock, kMinBlocks) cb200_spec_tran_fixed_kernel(Program p, SpecArgs sp, TranArgs a)\n"
          "{\n    SProg pg; SLuTr lu; RegWs<kSlots> w;\n    tran_fixed_body(pg, lu, w, p, sp, a);\n}\n";
+    const PairPlan pair = plan_pair(in);
+    if (pair.ok) {
+        emit_pair_program(o, pair);
+        // role 1 computes the same lanes: its read-modify-write counters go to a scratch array
+        o << "__device__ int *cb200_pair_scratch;\n";
+        o << "__global__ void __launch_bounds__(64, 1) cb200_spec_tran_fixed_pair_kernel(Program p, SpecArgs sp, TranArgs a)\n"
+             "{\n    SProgP pg; SLuTr lu; RegWs<kSlots> w;\n"
+             "    if (threadIdx.y != 0) { a.iters = cb200_pair_scratch; a.evals = nullptr; }\n"
+             "    tran_fixed_body(pg, lu, w, p, sp, a);\n}\n";
+    }
     if (in.with_adaptive)
         o << "__global__ void __launch_bounds__(kBlock, kMinBlocks) cb200_spec_tran_adaptive_kernel(Program p, SpecArgs sp, AdaptArgs a)\n"
              "{\n    SProg pg; SLuTr lu; RegWs<kSlots> w;\n    tran_adaptive_body(pg, lu, w, p, sp, a);\n}\n";
@@ -307,10 +389,32 @@ std::string generate_spec_source(const SpecInput &in)
          "                                     const cb200::DcArgs *a, cudaStream_t st)\n{\n"
          "    const unsigned grid = (unsigned)((p->P + kBlock - 1) / kBlock);\n"
          "    cb200_spec_dc_kernel<<<grid, kBlock, 0, st>>>(*p, *s, *a);\n    return cudaGetLastError();\n}\n";
+    o << "extern \"C\" int cb200_spec_pair_lanes(void);\n";
     o << "extern \"C\" cudaError_t cb200_spec_tran_fixed(const cb200::Program *p, const cb200::SpecArgs *s,\n"
-         "                                             const cb200::TranArgs *a, cudaStream_t st)\n{\n"
-         "    const unsigned grid = (unsigned)((p->P + kBlock - 1) / kBlock);\n"
+         "                                             const cb200::TranArgs *a, cudaStream_t st)\n{\n";
+    if (pair.ok)
+        o << "    // pair mode is OPT-IN (CB200_PAIR=1): measured on a B200 it loses to the single-warp kernel at every\n"
+             "    // sweep size (profiles/README.md, r02r)\n"
+             "    static int wave = -1;\n    static int *scratch = nullptr;\n    static int64_t scratch_n = 0;\n"
+             "    if (wave < 0) {\n"
+             "        int dev = 0, sms = 0, nb = 0;\n        cudaGetDevice(&dev);\n"
+             "        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);\n"
+             "        cudaFuncSetAttribute(cb200_spec_tran_fixed_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes);\n"
+             "        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb200_spec_tran_fixed_pair_kernel, 64, kPairSmemBytes);\n"
+             "        wave = nb * sms * 32;\n    }\n"
+             "    const char *force = getenv(\"CB200_PAIR\");\n"
+             "    const bool use_pair = force && force[0] == '1' && wave > 0;\n"
+             "    if (use_pair) {\n"
+             "        if (scratch_n < p->P) {\n            if (scratch) cudaFree(scratch);\n"
+             "            if (cudaMalloc(&scratch, sizeof(int) * (size_t)p->P) != cudaSuccess) return cudaGetLastError();\n"
+             "            scratch_n = p->P;\n"
+             "            cudaMemcpyToSymbolAsync(cb200_pair_scratch, &scratch, sizeof(int *), 0, cudaMemcpyHostToDevice, st);\n        }\n"
+             "        const unsigned grid = (unsigned)((p->P + 31) / 32);\n"
+             "        cb200_spec_tran_fixed_pair_kernel<<<grid, dim3(32, 2, 1), kPairSmemBytes, st>>>(*p, *s, *a);\n"
+             "        return cudaGetLastError();\n    }\n";
+    o << "    const unsigned grid = (unsigned)((p->P + kBlock - 1) / kBlock);\n"
          "    cb200_spec_tran_fixed_kernel<<<grid, kBlock, 0, st>>>(*p, *s, *a);\n    return cudaGetLastError();\n}\n";
+    o << "extern \"C\" int cb200_spec_pair_lanes(void) { return " << (pair.ok ? 1 : 0) << "; }\n";
     if (in.with_adaptive)
     o << "extern \"C\" cudaError_t cb200_spec_tran_adaptive(const cb200::Program *p, const cb200::SpecArgs *s,\n"
          "                                                const cb200::AdaptArgs *a, cudaStream_t st)\n{\n"

@@ -155,7 +155,9 @@ class SharedSweepBuffer:
             try:
                 self._shm.close()
             except BufferError:
-                pass
+                # a caller still holds a view of the array: leave the mapping to process exit (and keep
+                # SharedMemory.__del__ from retrying the close and reporting the same error)
+                self._shm._mmap = None
             if rank == 0:
                 self._shm.unlink()
             self._shm = None

@@ -602,6 +602,40 @@ def test_gpu_va_c3_corner_lanes_with_transient_limiting():
 
 
 @pytest.mark.gpu
+def test_gpu_pair_mode_equals_single_warp(monkeypatch):
+    """Pair mode of the specialised fixed-step kernel (two warps per 32 lanes, one sp_mos1 body each, stamps
+    exchanged through shared memory: specialize.cpp, plan_pair) must reproduce the single-warp kernel bit for
+    bit -- waveforms, statuses, Newton counts -- and both must match the oracle."""
+    lc = fixture("mos1_c3")
+    nl = oracle_of(lc)
+    save = [lc.index_of("q"), lc.index_of("d")]
+    out = {}
+    for pair in ("0", "1"):
+        monkeypatch.setenv("CB200_PAIR", pair)
+        comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+        try:
+            comp.specialize(1e-10, "be", limit=True, fixed_only=True)
+            assert comp.handle.is_specialized()
+            wave = comp.tran((0.0, 1.3e-7), 1e-10, method="be", save_idxs=save, save_every=10, limit=True)
+            r = wave.fetch(); wave.free()
+            host = np.full_like(r["u"], np.nan)
+            r3 = comp.tran_fetch((0.0, 1.3e-7), 1e-10, host, method="be", save_idxs=save, save_every=10, limit=True,
+                                 n_segments=3)
+            out[pair] = (r["u"], r["status"], r["newton_iters"], r3["u"], r3["newton_iters"], comp.handle.stats())
+        finally:
+            comp.close()
+    for a, b in zip(out["0"][:5], out["1"][:5]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(out["1"][0], out["1"][3])            # segmented = single launch in pair mode too
+    ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 1.3e-7,
+                        ora.make_tran_opts(method=0, dt=1e-10, save_every=10, limit=True), save)
+    gpu = np.transpose(out["1"][0], (2, 1, 0))
+    assert (out["1"][1] == 0).all() and _close(gpu, ro["u"][:, :gpu.shape[1], :])
+    assert np.array_equal(out["1"][2], ro["newton_iters"])
+    print("pair mode: kernel", out["1"][5]["tran_kernel_ms"], "ms; single warp:", out["0"][5]["tran_kernel_ms"], "ms")
+
+
+@pytest.mark.gpu
 def test_gpu_va_dff_adaptive():
     """C4 on the table-driven kernels (n = 145, ~5000 workspace doubles per lane: the lane-per-warp
     mapping, workspace row in HBM / L2) against the oracle, adaptive mode at the north_star
