@@ -382,6 +382,7 @@ def run_b200(args):
             first_t, first_count = (r["t"].copy(), r["count"].copy()) if adaptive else (None, None)
             iters_local = int(r["newton_iters"].astype(np.int64).sum())
             evals_local = int(st["device_evals"])
+            exec_local = int(st["steps_accepted"])          # fixed step: lane-steps the kernel executed
             bad = int((r["status"] != 0).sum())
             if bad:
                 raise SystemExit(f"bench.py: {bad} lanes did not converge")
@@ -413,14 +414,14 @@ def run_b200(args):
     wall_e2e = time.perf_counter() - t1
     clocks = sampler.stop()
 
-    tot = torch.tensor([float(iters_local), float(evals_local), float(h2d), float(d2h), float(launches)],
+    tot = torch.tensor([float(iters_local), float(evals_local), float(h2d), float(d2h), float(launches), float(exec_local)],
                        dtype=torch.float64, device="cuda")
     if world > 1:
         tt = torch.tensor([wall, wall_e2e, tran_ms, kern_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         wall, wall_e2e, tran_ms, kern_ms = [float(x) for x in tt]
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    iters_per_step, evals_per_step, h2d_all, d2h_all, launches_all = [int(x) for x in tot.tolist()]
+    iters_per_step, evals_per_step, h2d_all, d2h_all, launches_all, executed_steps = [int(x) for x in tot.tolist()]
     value = P * args.steps / wall
     e2e = P * args.steps / wall_e2e
     gathered_ok = True
@@ -487,18 +488,28 @@ def run_b200(args):
         else:
             f_eval = float(sum(NATIVE_EVAL_FLOPS.get(int(k), 0) for k in lc.dev_kind))
             eval_note = "native device models: static estimate per evaluation pass (exp counted as one flop)"
-        flops = (evals_per_step * f_eval + (iters_per_step + nsteps_total) * fm["assemble_tran"] +
+        # assemblies executed: one per EXECUTED lane-step + one per Newton solve.  The specialised kernel's
+        # quiescent-step bypass does not execute steps whose first residual would be bitwise the one that just
+        # converged; the lane-steps it did execute are counted on the device (cb200_stats.steps_accepted)
+        bypass = comp.handle.is_specialized() and not adaptive and os.environ.get("CB200_NO_BYPASS") is None
+        assemblies = iters_per_step + (executed_steps if bypass else nsteps_total)
+        flops = (evals_per_step * f_eval + assemblies * fm["assemble_tran"] +
                  iters_per_step * (fm["factor_tran"] + fm["solve_tran"] + fm["update"]))
         achieved = flops / world / tran_s / 1e12 if tran_s > 0 else 0.0
         roof = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic, "kernel": kernel_name,
                 "flops_per_launch_per_gpu": int(flops // world),
                 "device_eval_passes_per_launch": evals_per_step, "flops_per_eval_pass": f_eval,
+                "assemblies_counted": int(assemblies), "quiescent_step_bypass": bool(bypass),
+                "lane_steps_executed": int(executed_steps), "lane_steps_total": int(nsteps_total),
                 "linear_algebra_flops_per_iter": fm,
                 "peak_source": f"measured in this run: cb200_measure_fp64_peak, register-only FMA kernel, 8 chains/thread, "
                                f"64 warps/SM, {peak_ms:.2f} ms (2 flops per FMA)",
                 "note": eval_note + "; evaluation passes counted on the device (cb200_stats.device_evals): a step "
-                        "whose first residual re-uses the stamps of the previous step's converged check executes none",
+                        "whose first residual re-uses the stamps of the previous step's converged check executes none"
+                        + ("; quiescent-step bypass on: a backward-Euler step whose sources are bitwise unchanged after a "
+                           "step that converged without a solve is not executed (bit-identical results); executed lane-steps "
+                           "counted on the device" if bypass else ""),
                 "hbm_algorithmic": hbm_obj}
     else:
         roof = {"bound": "hbm", **hbm_obj, "traffic": traffic, "kernel": kernel_name,

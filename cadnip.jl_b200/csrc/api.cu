@@ -976,6 +976,7 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
     int rc = ensure_lu(h, spec, 1, gamma_nom);
     if (rc != CB200_OK) return rc;
 
+    bool used_spec = false;            // the fixed-step launches went to the circuit-specialised kernels
     cb200_wave *w = new cb200_wave();
     w->h = h; w->P = P; w->n_save = n_save; w->n = n; w->adaptive = o->adaptive; w->t0 = t0; w->dt = o->dt;
     w->d_out.pool = w->d_t.pool = w->d_final.pool = h->pool;
@@ -1055,6 +1056,8 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
             a.tp_begin = g == 0 ? 0 : 1 + (a.k_begin - 1) / se;
             if (spec_usable(h) && h->spec_method == o->method && (!a.limit || h->spec_limit)) {
                 h->stats.launches += 1;
+                if (!used_spec && h->spec.take_counters) h->spec.take_counters(nullptr, s);   // reset
+                used_spec = true;
                 ce = h->spec.tran_fixed(&h->prog, &sa, &a, s);
             } else {
                 ce = h->k.tran_fixed(&h->prog, &h->lu[1].prog, &sa, &a, h->block_pref, h->smem_limit, s, &h->stats.launches);
@@ -1144,6 +1147,12 @@ static int tran_impl(cb200_handle *h, const cb200_spec *spec, double t0, double 
     ce = cudaStreamSynchronize(s);
     if (ce != cudaSuccess) { delete w; return fail(h, CB200_ECUDA, cudaGetErrorString(ce)); }
     if (!o->adaptive) h->stats.steps_accepted = w->nsteps * P;
+    if (!o->adaptive && used_spec && h->spec.take_counters) {
+        // specialised kernels skip quiescent steps bit-exactly (specialize.cpp, kSpecTranFixedBody): the
+        // lane-steps actually executed
+        unsigned long long nexec = 0;
+        if (h->spec.take_counters(&nexec, s) == cudaSuccess) h->stats.steps_accepted = (int64_t)nexec;
+    }
     {   // device-model evaluation passes executed (sum over lanes): the work the FP64 roofline counts
         std::vector<int> ev(P);
         cudaMemcpyAsync(ev.data(), h->d_evals.p, P * sizeof(int), cudaMemcpyDeviceToHost, s);

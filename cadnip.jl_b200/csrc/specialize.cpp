@@ -202,6 +202,193 @@ static void emit_lu(std::ostringstream &o, const char *sname, const Structure &s
 }
 
 // ---------------------------------------------------------------------------
+// The fixed-step time loop of the SPECIALISED kernels: tran_fixed_body of lane_kernels.cuh, statement for
+// statement, plus the quiescent-step bypass described in the text below (a circuit-specialised kernel knows
+// its source stamp slots at compile time, which is what the test needs).  The table-driven kernels keep the
+// plain loop; both produce identical results (tests/test_gpu_parity.py: specialised vs table-driven vs oracle).
+// @SRC_OLD@ / @SRC_SAME@ are filled per circuit; CB200_NO_BYPASS=1 generates kernels on the plain loop.
+// ---------------------------------------------------------------------------
+static const char *kSpecTranFixedBody = R"CB200(
+template <typename PG, typename LU, typename W>
+__device__ __forceinline__ void spec_tran_fixed_body(const PG &pg, const LU &lu, W &w, const Program &p,
+                                                const SpecArgs &sp, const TranArgs &a)
+{
+    const int64_t lane0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = lane0 < p.P;
+    const int64_t lane = act ? lane0 : p.P - 1;
+
+    // The time loop may be cut into segments [k_begin, k_end] (one launch each) so that the
+    // copy of a finished segment's waveform to the host overlaps the next segment's compute;
+    // a resumed segment reloads the integrator history (u_n, dterm) the previous one stored.
+    const bool resume = a.k_begin > 1;
+    load_lane_params(pg, w, p.lanes, p.P, lane);
+    CB_UNROLL
+    for (int i = 0; i < pg.n(); i++) {
+        w(pg.off_u() + i) = a.u[(int64_t)i * p.P + lane];
+        w(pg.off_dterm() + i) = resume ? a.hist[(int64_t)(pg.n() + i) * p.P + lane] : 0.0;
+        w(pg.off_un() + i) = resume ? a.hist[(int64_t)i * p.P + lane] : 0.0;
+    }
+    eval_all(pg, w, a.t0, CB200_MODE_TRAN, false);
+
+    int status = a.status[lane], solves = 0;       // keeps an InitialFailure from the DC init
+    int evals = 0;                                 // device-model evaluation passes this thread executed
+    int64_t tp = a.tp_begin;
+    if (!resume) {
+        if (act)
+            for (int q = 0; q < a.n_save; q++)
+                a.out[((int64_t)q * a.T + tp) * p.P + lane] = read_u(pg, w, __ldg(a.save_idx + q));
+        tp++;
+    }
+    const double h = a.h;
+    const double abstol2 = a.abstol * a.abstol;
+    // a specialised kernel is generated for one integration method: branches on it fold
+    const int amethod = PG::kMethod >= 0 ? PG::kMethod : a.method;
+    // `fresh`: the stamp slots of the nonlinear devices hold their values AT the current iterate.
+    // A step that converged ends with an evaluation at its final u, and the next step starts its
+    // Newton iteration from that same u: G(u), C(u) and the companion currents are functions of
+    // u alone, so the first residual of a step re-assembles them with the new source values and
+    // history terms instead of evaluating every device model again for identical values.
+    bool fresh = false;
+    // Quiescent-step bypass (backward Euler).  `quiet`: the previous step of this lane converged at its first
+    // residual -- no solve, so u == u_n, d == 0 and the stamps are those of u.  If in addition every source stamp
+    // of the new step is bitwise what it was, the new step's first residual F = G u - b is bit for bit the one
+    // that just passed the test: the step would assemble the same numbers, find them converged and change
+    // nothing.  When that holds for all 32 lanes of the warp the step is not executed (its saved point is
+    // written from the unchanged u).  Identical waveforms, statuses and Newton counts by construction; a lane
+    // that could not skip alone executes the step as usual.
+    bool quiet = false;
+    int nexec = 0;                                 // steps this lane executed (not bypassed)
+    for (int64_t k = a.k_begin; k <= a.k_end; k++) {
+        const double t = a.t0 + (double)k * h;
+        const int method = (k == 1) ? CB200_METHOD_BE : amethod;
+        const double gamma = method == CB200_METHOD_BE ? 1.0 / h
+                           : method == CB200_METHOD_TRAP ? 2.0 / h : 3.0 / (2.0 * h);
+@SRC_OLD@
+        eval_sources_step(pg, w, k, k == a.k_begin, a.t0, h, CB200_MODE_TRAN);
+        if (PG::kMethod == CB200_METHOD_BE && !kNlTimeDep) {
+            bool same = quiet && k != a.k_begin;
+@SRC_SAME@
+            if (__all_sync(0xffffffffu, same)) {
+                if (k % a.save_every == 0 || k == a.nsteps) {
+                    if (act)
+                        for (int q = 0; q < a.n_save; q++)
+                            a.out[((int64_t)q * a.T + tp) * p.P + lane] = read_u(pg, w, __ldg(a.save_idx + q));
+                    tp++;
+                }
+                continue;
+            }
+        }
+        const int solves0 = solves;
+        nexec++;
+        // history terms; un <- u
+        CB_UNROLL
+        for (int i = 0; i < pg.n(); i++) {
+            const double ui = w(pg.off_u() + i);
+            if (method == CB200_METHOD_GEAR2) w(pg.off_dterm() + i) = -(ui - w(pg.off_un() + i)) / (2.0 * h);
+            else if (method == CB200_METHOD_BE) w(pg.off_dterm() + i) = 0.0;
+            /* trap: dterm already holds -du_n */
+            w(pg.off_un() + i) = ui;
+        }
+        bool done = false;
+        int st = CB200_LANE_OK;
+        // a.limit (CB200_TRAN_LIMIT): a step the plain iteration does not finish in max_nl solves
+        // is redone from u_n with the PCNR corrector after every solve (4*max_nl solves allowed)
+        bool lim_on = false;
+        int it0 = 0;
+        for (int it = 0;; it++) {
+            // lanes that are fresh recompute identical values when another lane of the warp is not
+            if (__any_sync(0xffffffffu, kNlTimeDep || !fresh)) { eval_nonlinear(pg, w, t, CB200_MODE_TRAN, false); evals++; }
+            fresh = true;
+            bool bad;
+            const double nrm2 = assemble<true>(pg, lu, w, gamma, sp.gshunt, sp.srcFact, bad);
+            bool restart = false;
+            if (!done) {
+                if (bad) { done = true; st = CB200_LANE_NONFINITE; }
+                else if (nrm2 < abstol2) { done = true; }
+                else if (it - it0 >= (lim_on ? 4 * a.max_nl : a.max_nl)) {
+                    if (PG::kTranLimit && a.limit && !lim_on) { lim_on = true; it0 = it + 1; restart = true; }
+                    else { done = true; st = CB200_LANE_MAXITER; }
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+            bool singular;
+            const bool ok = factor_and_solve(pg, lu, w, singular);
+            if (!done) {
+                if (restart) {                             // redo the step from u_n, limiting on
+                    CB_UNROLL
+                    for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
+                    fresh = false;
+                } else if (!ok) { done = true; st = singular ? CB200_LANE_SINGULAR : CB200_LANE_NONFINITE; }
+                else {
+                    apply_update(pg, lu, w);
+                    fresh = false;
+                    solves++;
+                    if (lim_on) {                          // PCNR corrector, solve.jl:686-689
+                        const int lim0 = pg.n() - pg.n_limits();
+                        CB_UNROLL
+                        for (int q = 0; q < pg.n_limits(); q++) w(pg.off_u() + lim0 + q) = w(pg.off_limw() + q);
+                    }
+                }
+            }
+        }
+        quiet = st == CB200_LANE_OK && solves == solves0 && !lim_on;
+        if (st != CB200_LANE_OK && status == CB200_LANE_OK) status = st;
+        if (st != CB200_LANE_OK) fresh = false;           // the last evaluation was not at the state kept
+        if (st == CB200_LANE_NONFINITE || st == CB200_LANE_SINGULAR) {  // dead lane: hold last state
+            CB_UNROLL
+            for (int i = 0; i < pg.n(); i++) w(pg.off_u() + i) = w(pg.off_un() + i);
+        }
+        if (amethod == CB200_METHOD_TRAP) {               // dterm <- -du_{n+1}
+            CB_UNROLL
+            for (int i = 0; i < pg.n(); i++)
+                w(pg.off_dterm() + i) = -(gamma * (w(pg.off_u() + i) - w(pg.off_un() + i)) + w(pg.off_dterm() + i));
+        }
+        if (k % a.save_every == 0 || k == a.nsteps) {
+            if (act)
+                for (int q = 0; q < a.n_save; q++)
+                    a.out[((int64_t)q * a.T + tp) * p.P + lane] = read_u(pg, w, __ldg(a.save_idx + q));
+            tp++;
+        }
+    }
+    if (act) {
+        CB_UNROLL
+        for (int i = 0; i < pg.n(); i++) {
+            a.u[(int64_t)i * p.P + lane] = w(pg.off_u() + i);
+            if (a.hist != nullptr) {                     // history for a resumed segment
+                a.hist[(int64_t)i * p.P + lane] = w(pg.off_un() + i);
+                a.hist[(int64_t)(pg.n() + i) * p.P + lane] = w(pg.off_dterm() + i);
+            }
+        }
+        a.status[lane] = status;
+        if (a.weak && w.weak) a.weak[lane] = 1;
+        a.iters[lane] += solves;
+        if (a.evals != nullptr) a.evals[lane] += evals;
+        if (threadIdx.y == 0) atomicAdd(&cb200_spec_nexec, (unsigned long long)nexec);
+    }
+}
+)CB200";
+
+static std::string spec_tran_body_text(const SpecInput &in)
+{
+    const Program &p = *in.prog;
+    std::ostringstream so, ss;
+    int q = 0;
+    for (int d : *in.src_list)
+        for (int b = (*in.dev_bbase)[d]; b < (*in.dev_bbase)[d + 1]; b++, q++) {
+            so << "        const double src_old" << q << " = w(" << p.off_SB + b << ");\n";
+            ss << "            same = same && (w(" << p.off_SB + b << ") == src_old" << q << ");\n";
+        }
+    std::string t = kSpecTranFixedBody;
+    auto put = [&t](const std::string &key, const std::string &val) {
+        const size_t at = t.find(key);
+        if (at != std::string::npos) t.replace(at, key.size(), val);
+    };
+    put("@SRC_OLD@\n", so.str());
+    put("@SRC_SAME@\n", ss.str());
+    return t;
+}
+
+// ---------------------------------------------------------------------------
 // Pair mode (small sweeps): TWO warps per 32 lanes.  A lane-per-thread kernel is latency-bound on one
 // warp's dependent chain once a GPU holds fewer lanes than fill it (C3: 12 500 lanes per GPU under
 // 8-way strong scaling run as long as 25 000); most of that chain is the nonlinear device models.  In
@@ -367,8 +554,12 @@ std::string generate_spec_source(const SpecInput &in)
     o << "constexpr int kBlock = " << in.block << ";\nconstexpr int kMinBlocks = " << in.min_blocks << ";\n";
     o << "__global__ void __launch_bounds__(kBlock, kMinBlocks) cb200_spec_dc_kernel(Program p, SpecArgs sp, DcArgs a)\n"
          "{\n    SProg pg; SLuDc lu; RegWs<kSlots> w;\n    dc_body(pg, lu, w, p, sp, a);\n}\n";
+    const bool bypass = getenv("CB200_NO_BYPASS") == nullptr;
+    const char *tran_body = bypass ? "spec_tran_fixed_body" : "tran_fixed_body";
+    if (bypass) o << "__device__ unsigned long long cb200_spec_nexec;   // lane-steps executed (not bypassed) since last read\n"
+                  << spec_tran_body_text(in);
     o << "__global__ void __launch_bounds__(kBlock, kMinBlocks) cb200_spec_tran_fixed_kernel(Program p, SpecArgs sp, TranArgs a)\n"
-         "{\n    SProg pg; SLuTr lu; RegWs<kSlots> w;\n    tran_fixed_body(pg, lu, w, p, sp, a);\n}\n";
+         "{\n    SProg pg; SLuTr lu; RegWs<kSlots> w;\n    " << tran_body << "(pg, lu, w, p, sp, a);\n}\n";
     const PairPlan pair = plan_pair(in);
     if (pair.ok) {
         emit_pair_program(o, pair);
@@ -377,7 +568,7 @@ std::string generate_spec_source(const SpecInput &in)
         o << "__global__ void __launch_bounds__(64, 1) cb200_spec_tran_fixed_pair_kernel(Program p, SpecArgs sp, TranArgs a)\n"
              "{\n    SProgP pg; SLuTr lu; RegWs<kSlots> w;\n"
              "    if (threadIdx.y != 0) { a.iters = cb200_pair_scratch; a.evals = nullptr; }\n"
-             "    tran_fixed_body(pg, lu, w, p, sp, a);\n}\n";
+             "    " << tran_body << "(pg, lu, w, p, sp, a);\n}\n";
     }
     if (in.with_adaptive)
         o << "__global__ void __launch_bounds__(kBlock, kMinBlocks) cb200_spec_tran_adaptive_kernel(Program p, SpecArgs sp, AdaptArgs a)\n"
@@ -415,6 +606,15 @@ std::string generate_spec_source(const SpecInput &in)
     o << "    const unsigned grid = (unsigned)((p->P + kBlock - 1) / kBlock);\n"
          "    cb200_spec_tran_fixed_kernel<<<grid, kBlock, 0, st>>>(*p, *s, *a);\n    return cudaGetLastError();\n}\n";
     o << "extern \"C\" int cb200_spec_pair_lanes(void) { return " << (pair.ok ? 1 : 0) << "; }\n";
+    if (bypass)
+        o << "// lane-steps the fixed-step kernels executed since the last call (then reset): the bypass makes it less than\n"
+             "// steps x lanes, and the FP64 roofline counts one assembly per EXECUTED step\n"
+             "extern \"C\" cudaError_t cb200_spec_take_counters(unsigned long long *executed, cudaStream_t st)\n{\n"
+             "    unsigned long long v = 0, zero = 0;\n"
+             "    cudaError_t e = cudaMemcpyFromSymbolAsync(&v, cb200_spec_nexec, sizeof v, 0, cudaMemcpyDeviceToHost, st);\n"
+             "    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(cb200_spec_nexec, &zero, sizeof zero, 0, cudaMemcpyHostToDevice, st);\n"
+             "    if (e == cudaSuccess) e = cudaStreamSynchronize(st);\n"
+             "    if (executed) *executed = v;\n    return e;\n}\n";
     if (in.with_adaptive)
     o << "extern \"C\" cudaError_t cb200_spec_tran_adaptive(const cb200::Program *p, const cb200::SpecArgs *s,\n"
          "                                                const cb200::AdaptArgs *a, cudaStream_t st)\n{\n"
@@ -591,6 +791,7 @@ std::string build_and_load_spec(const std::string &src, const std::string &csrc_
     out.dc = (spec_dc_fn)dlsym(dl, "cb200_spec_dc");
     out.tran_fixed = (spec_tran_fn)dlsym(dl, "cb200_spec_tran_fixed");
     out.tran_adaptive = (spec_adapt_fn)dlsym(dl, "cb200_spec_tran_adaptive");
+    out.take_counters = (spec_counters_fn)dlsym(dl, "cb200_spec_take_counters");      // optional
     if (!abi || !blk || !out.dc || !out.tran_fixed || abi() != kSpecAbi) {       // tran_adaptive is optional
         out = SpecModule();
         return "specialize: " + so + " does not export the expected entry points";

@@ -31,12 +31,14 @@ struct SpecInput {
 typedef cudaError_t (*spec_dc_fn)(const Program *, const SpecArgs *, const DcArgs *, cudaStream_t);
 typedef cudaError_t (*spec_tran_fn)(const Program *, const SpecArgs *, const TranArgs *, cudaStream_t);
 typedef cudaError_t (*spec_adapt_fn)(const Program *, const SpecArgs *, const AdaptArgs *, cudaStream_t);
+typedef cudaError_t (*spec_counters_fn)(unsigned long long *, cudaStream_t);
 
 struct SpecModule {
     void *dl = nullptr;
     spec_dc_fn dc = nullptr;
     spec_tran_fn tran_fixed = nullptr;
     spec_adapt_fn tran_adaptive = nullptr;
+    spec_counters_fn take_counters = nullptr;   // lane-steps executed by the fixed-step kernels (bypass), or null
     int block = 0;
     std::string path;
 };

@@ -1,6 +1,6 @@
 # pair mode (two warps per 32 lanes) of the specialised fixed-step kernel: parity and the small-sweep regime
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_va_models.py tests/test_gpu_parity.py -q -m gpu -k "pair_mode or bdf" -s 2>&1 | tail -25 > gpurun_out/r02r_tests.log
+python -m pytest tests/test_va_models.py tests/test_gpu_parity.py -q -m gpu -k "pair_mode or bdf or specialised or spec" -s 2>&1 | tail -25 > gpurun_out/r02r_tests.log
 tail -8 gpurun_out/r02r_tests.log
 for L in 3125 6250 12500 25000; do
 CB200_PAIR=0 python bench.py --lanes $L --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02r_c3_${L}_single.json 2> gpurun_out/r02r_c3_${L}_single.err

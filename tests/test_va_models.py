@@ -602,16 +602,23 @@ def test_gpu_va_c3_corner_lanes_with_transient_limiting():
 
 
 @pytest.mark.gpu
-def test_gpu_pair_mode_equals_single_warp(monkeypatch):
-    """Pair mode of the specialised fixed-step kernel (two warps per 32 lanes, one sp_mos1 body each, stamps
-    exchanged through shared memory: specialize.cpp, plan_pair) must reproduce the single-warp kernel bit for
-    bit -- waveforms, statuses, Newton counts -- and both must match the oracle."""
+def test_gpu_pair_mode_and_bypass_equal_plain_kernel(monkeypatch):
+    """Three builds of the specialised fixed-step kernel on the C3 corner lanes must agree bit for bit --
+    waveforms, statuses, Newton counts, segmented or not -- and match the oracle: the plain time loop
+    (CB200_NO_BYPASS=1), the default one with the quiescent-step bypass (steps whose first residual would be
+    bitwise the one that just converged are not executed: specialize.cpp, kSpecTranFixedBody), and pair mode
+    (two warps per 32 lanes, one sp_mos1 body each, stamps exchanged through shared memory: plan_pair)."""
     lc = fixture("mos1_c3")
     nl = oracle_of(lc)
     save = [lc.index_of("q"), lc.index_of("d")]
     out = {}
-    for pair in ("0", "1"):
-        monkeypatch.setenv("CB200_PAIR", pair)
+    for pair in ("plain", "0", "1"):
+        if pair == "plain":
+            monkeypatch.setenv("CB200_NO_BYPASS", "1")
+            monkeypatch.setenv("CB200_PAIR", "0")
+        else:
+            monkeypatch.delenv("CB200_NO_BYPASS", raising=False)
+            monkeypatch.setenv("CB200_PAIR", pair)
         comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
         try:
             comp.specialize(1e-10, "be", limit=True, fixed_only=True)
@@ -624,15 +631,18 @@ def test_gpu_pair_mode_equals_single_warp(monkeypatch):
             out[pair] = (r["u"], r["status"], r["newton_iters"], r3["u"], r3["newton_iters"], comp.handle.stats())
         finally:
             comp.close()
-    for a, b in zip(out["0"][:5], out["1"][:5]):
-        assert np.array_equal(a, b, equal_nan=True)
+    for other in ("0", "1"):
+        for a, b in zip(out["plain"][:5], out[other][:5]):
+            assert np.array_equal(a, b, equal_nan=True), other
+    assert out["0"][5]["device_evals"] == out["plain"][5]["device_evals"]
     assert np.array_equal(out["1"][0], out["1"][3])            # segmented = single launch in pair mode too
     ro = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 1.3e-7,
                         ora.make_tran_opts(method=0, dt=1e-10, save_every=10, limit=True), save)
     gpu = np.transpose(out["1"][0], (2, 1, 0))
     assert (out["1"][1] == 0).all() and _close(gpu, ro["u"][:, :gpu.shape[1], :])
     assert np.array_equal(out["1"][2], ro["newton_iters"])
-    print("pair mode: kernel", out["1"][5]["tran_kernel_ms"], "ms; single warp:", out["0"][5]["tran_kernel_ms"], "ms")
+    print("kernel ms: plain loop", out["plain"][5]["tran_kernel_ms"], "with bypass", out["0"][5]["tran_kernel_ms"],
+          "pair mode", out["1"][5]["tran_kernel_ms"])
 
 
 @pytest.mark.gpu
