@@ -1282,6 +1282,10 @@ extern "C" int cb200_specialize(cb200_handle *h, const cb200_spec *spec, int32_t
     // inverter, 432 slots) 4 resident blocks x 255 registers beat 11 x 93 by 1.6x
     if (h->prog.n_slots > 120) in.min_blocks = std::min(in.min_blocks, 4);
     if (const char *e = getenv("CB200_SPEC_MINBLOCKS")) in.min_blocks = std::max(1, atoi(e));   // tuning knob
+    if (getenv("CB200_LOCKSTEP")) {                // experiment: one block of 8 lockstep warps per SM (specialize.cpp)
+        in.block = getenv("CB200_SPEC_BLOCK") ? std::max(32, atoi(getenv("CB200_SPEC_BLOCK"))) : 256;
+        in.min_blocks = 1;
+    }
     if (h->prog.n_slots > 4096) return fail(h, CB200_EINVAL, "cb200_specialize: circuit too large for a register-resident kernel");
     const std::string src = generate_spec_source(in);
     unload_spec(h->spec);

@@ -268,7 +268,7 @@ __device__ __forceinline__ void spec_tran_fixed_body(const PG &pg, const LU &lu,
         if (PG::kMethod == CB200_METHOD_BE && !kNlTimeDep) {
             bool same = quiet && k != a.k_begin;
 @SRC_SAME@
-            if (__all_sync(0xffffffffu, same)) {
+            if (CB_GROUP_ALL(same)) {
                 if (k % a.save_every == 0 || k == a.nsteps) {
                     if (act)
                         for (int q = 0; q < a.n_save; q++)
@@ -310,7 +310,7 @@ __device__ __forceinline__ void spec_tran_fixed_body(const PG &pg, const LU &lu,
                     else { done = true; st = CB200_LANE_MAXITER; }
                 }
             }
-            if (__all_sync(0xffffffffu, done)) break;
+            if (CB_GROUP_ALL(done)) break;
             bool singular;
             const bool ok = factor_and_solve(pg, lu, w, singular);
             if (!done) {
@@ -556,6 +556,10 @@ std::string generate_spec_source(const SpecInput &in)
          "{\n    SProg pg; SLuDc lu; RegWs<kSlots> w;\n    dc_body(pg, lu, w, p, sp, a);\n}\n";
     const bool bypass = getenv("CB200_NO_BYPASS") == nullptr;
     const char *tran_body = bypass ? "spec_tran_fixed_body" : "tran_fixed_body";
+    // CB200_LOCKSTEP=1: the warps of a block walk the time loop together (block-wide votes, which are barriers):
+    // they then execute the straight-line model bodies at the same time and share instruction fetches -- the
+    // kernel is bound by instruction fetch (profiles/README.md: icc hit rate 73 %, no_instructions 25 %)
+    if (bypass) o << "#define CB_GROUP_ALL(x) " << (getenv("CB200_LOCKSTEP") ? "(__syncthreads_and(x) != 0)" : "__all_sync(0xffffffffu, (x))") << "\n";
     if (bypass) o << "__device__ unsigned long long cb200_spec_nexec;   // lane-steps executed (not bypassed) since last read\n"
                   << spec_tran_body_text(in);
     o << "__global__ void __launch_bounds__(kBlock, kMinBlocks) cb200_spec_tran_fixed_kernel(Program p, SpecArgs sp, TranArgs a)\n"
