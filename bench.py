@@ -33,8 +33,8 @@ N_R, N_C = 256, 256
 N_SEGMENTS = int(os.environ.get("CB200_SEGMENTS", "8"))
 # integrator of the adaptive workloads (c4, ring, c5): "trap" (LTE-controlled trapezoid, default) or "bdf" (the
 # variable-order BDF controller of the IDA family, DESIGN.md s. 5)
-ADAPTIVE_METHOD = os.environ.get("CB200_ADAPTIVE_METHOD", "trap")
-assert ADAPTIVE_METHOD in ("trap", "bdf")
+ADAPTIVE_METHOD = os.environ.get("CB200_ADAPTIVE_METHOD", "")       # "" = the workload's own choice
+assert ADAPTIVE_METHOD in ("", "trap", "bdf")
 METRIC = "transient_sweep_points_per_sec"
 UNIT = "points/s"
 # parity gate of the same-run spot check against the oracle (north_star, fixed step)
@@ -62,12 +62,12 @@ WORKLOADS = {
                     "4096 draws), DC op (PCNR + fallbacks) + adaptive trapezoidal/LTE transient (0, 6e-7); "
                     "table-driven kernels, one lane per warp"),
     "ring": dict(tspan=(0.0, float(os.environ.get("CB200_RING_TSTOP", "1e-6"))), dt=1e-12, save_every=1, save="1", steps=0,
-                 limit=False, adaptive=True, reltol=1e-2, lte_abstol=1e-4, dtmax=0.05e-9, cpu_tstop=2e-8,
+                 limit=False, adaptive=True, method="bdf", reltol=1e-2, lte_abstol=1e-4, dtmax=0.05e-9, cpu_tstop=2e-8,
                  max_points=int(os.environ.get("CB200_RING_MAXPOINTS", "49152")), probe_per_core=1, fixture="psp_ring",
                  lanes=int(os.environ.get("CB200_RING_LANES", "1024")),
                  text="9-stage PSP103 ring oscillator (benchmarks/vacask/ring/cedarsim: 18 PSP103VA FETs with the deck's "
                       "psp103n / psp103p cards through the emitter, n = 370), swept over the supply voltage (1.0 .. 1.4 V); "
-                      "CedarTranOp + adaptive trapezoidal/LTE transient (0, 1e-6), reltol 1e-2, abstol 1e-4, dtmax 0.05 ns "
+                      "CedarTranOp + adaptive variable-order BDF transient (0, 1e-6), reltol 1e-2, abstol 1e-4, dtmax 0.05 ns "
                       "(the reference's benchmark settings, runme.jl:47-67); table-driven kernels, one lane per warp"),
     "c5": dict(tspan=(0.0, 2e-9), dt=1e-12, save_every=1, save="p0", steps=0, limit=True, adaptive=True,
                reltol=float(os.environ.get("CB200_C5_RELTOL", "1e-5")), lte_abstol=1e-6,
@@ -89,6 +89,12 @@ def select_workload(name):
     global W, TSPAN, DT, SAVE_EVERY, WORKLOAD
     W = WORKLOADS[name]
     TSPAN, DT, SAVE_EVERY, WORKLOAD = W["tspan"], W["dt"], W["save_every"], W["text"]
+    global ADAPTIVE_METHOD
+    if not ADAPTIVE_METHOD:
+        # the PSP103 ring rings under the trapezoidal rule (the LTE estimate stops shrinking with h at
+        # t = 11 ns and the controller walks h down to dtmin, in the oracle as on the device); the
+        # variable-order BDF controller -- the reference's own solver family -- integrates it
+        ADAPTIVE_METHOD = W.get("method", "trap")
     if W.get("adaptive"):
         WORKLOAD += f"; reltol {W['reltol']:g}"
 

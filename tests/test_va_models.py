@@ -166,6 +166,20 @@ def test_psp103_ring_oscillator_known_behaviour():
     u = ro["u"][1, :, 0]
     assert u.min() < 0.1 and u.max() > 1.1
     assert 3 <= int(np.sum((u[1:] > 0.6) & (u[:-1] <= 0.6))) <= 8
+    # the reference's benchmark settings (benchmarks/vacask/ring/cedarsim/runme.jl:47-67: reltol 1e-2, abstol 1e-4,
+    # dtmax 0.05 ns) on the variable-order BDF controller, the reference's own solver family (IDA): the adaptive
+    # run completes and oscillates.  (The trapezoidal controller does not get through this circuit: the rule's
+    # undamped ringing on the charge-state constraints keeps the error estimate from shrinking with h.)
+    ora.set_linear_solver(1)
+    try:
+        o = ora.make_tran_opts(method=3, adaptive=1, dt=1e-12, reltol=1e-2, lte_abstol=1e-4, dtmax=0.05e-9, max_points=20000)
+        rb = ora.sweep_tran(nl, ora.make_spec(mode="tran"), 0.0, 3e-8, o, [lc.index_of("5")])
+    finally:
+        ora.set_linear_solver(0)
+    assert (rb["status"] == 0).all()
+    T = int(rb["T"][1])
+    ub = rb["u"][1, :T, 0]
+    assert rb["t"][1, T - 1] == 3e-8 and ub.min() < 0.1 and ub.max() > 1.1
 
 
 @needs_ref
@@ -819,7 +833,7 @@ def test_gpu_psp103_ring_matches_oracle():
     from cadnip_b200 import backend
     lc = fixture("psp_ring")
     if not backend.va_models_cached(lc.va_cuda_header):
-        pytest.skip("the PSP103 kernel set is not in the in-tree cache (ptxas needs ~45 minutes for it)")
+        pytest.skip("the PSP103 kernel set is not in the in-tree cache (ptxas needs more than two hours for it)")
     nl = oracle_of(lc)
     save = [lc.index_of(str(k)) for k in range(1, 10)]
     comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
