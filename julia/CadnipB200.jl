@@ -192,6 +192,56 @@ wave_kind(::MNA.PWLWave) = 1; wave_params(w::MNA.PWLWave) = (w.ts..., w.ys...)
 wave_kind(::MNA.PulseWave) = 2; wave_params(w::MNA.PulseWave) = (w.v1, w.v2, w.td, w.tr, w.tf, w.pw, w.per)
 wave_kind(::MNA.SinWave) = 3; wave_params(w::MNA.SinWave) = (w.vo, w.va, w.freq, w.td, w.theta, w.phase)
 
+# Behavioural sources (src/mna/devices.jl:1003-1131).  The closure `value_fn(get_voltage)` cannot be called from
+# the device, so it is TRACED once: `get_voltage(name)` returns a `SymV` whose arithmetic builds Verilog-A
+# text; the text becomes the one-statement module `V(p,n) <+ $explicit(expr)` / `I(n,p) <+ $explicit(expr)` that
+# goes to the emitter like any other model (INTEGRATION.md section 5b; cadnip_b200/behavioral.py is the Python
+# statement of the same tracer).  `$explicit` = value without partials: the reference's b-only stamping.
+struct SymV
+    text::String
+end
+const BehaviouralTrace = Vector{Symbol}                 # controlling nodes in order of first use
+sym(x::SymV) = x
+sym(x::Real) = SymV("(" * repr(Float64(x)) * ")")
+for (op, va) in ((:+, "+"), (:-, "-"), (:*, "*"), (:/, "/"))
+    @eval Base.$op(a::SymV, b::SymV) = SymV("(" * a.text * " " * $va * " " * b.text * ")")
+    @eval Base.$op(a::SymV, b::Real) = $op(a, sym(b))
+    @eval Base.$op(a::Real, b::SymV) = $op(sym(a), b)
+end
+Base.:-(a::SymV) = SymV("(-" * a.text * ")")
+Base.:^(a::SymV, b::Real) = SymV("pow(" * a.text * ", " * sym(b).text * ")")
+Base.:^(a::SymV, b::SymV) = SymV("pow(" * a.text * ", " * b.text * ")")
+for (fn, va) in ((:exp, "exp"), (:log, "ln"), (:log10, "log"), (:sqrt, "sqrt"), (:sin, "sin"), (:cos, "cos"),
+                 (:tan, "tan"), (:tanh, "tanh"), (:sinh, "sinh"), (:cosh, "cosh"), (:atan, "atan"), (:abs, "abs"))
+    @eval Base.$fn(a::SymV) = SymV($va * "(" * a.text * ")")
+end
+Base.min(a::SymV, b) = SymV("min(" * a.text * ", " * sym(b).text * ")")
+Base.max(a::SymV, b) = SymV("max(" * a.text * ", " * sym(b).text * ")")
+Base.:<(a::SymV, b) = SymV("(" * a.text * " < " * sym(b).text * ")")
+Base.:>(a::SymV, b) = SymV("(" * a.text * " > " * sym(b).text * ")")
+Base.ifelse(c::SymV, a, b) = SymV("((" * c.text * ") ? " * sym(a).text * " : " * sym(b).text * ")")
+
+"""
+    trace_behavioral(B) -> (va_source, controlling_nodes)
+
+The module text for a `BehavioralVoltageSource` / `BehavioralCurrentSource` and the nodes its value reads
+(they become the extra ports c0, c1, ... of the module, after p and n).
+"""
+function trace_behavioral(B::Union{MNA.BehavioralVoltageSource, MNA.BehavioralCurrentSource})
+    nodes = BehaviouralTrace()
+    function get_voltage(name)
+        i = findfirst(==(Symbol(name)), nodes)
+        i === nothing && (push!(nodes, Symbol(name)); i = length(nodes))
+        SymV("V(c$(i - 1))")
+    end
+    expr = sym(B.value_fn(get_voltage)).text
+    ports = join(vcat(["p", "n"], ["c$(k - 1)" for k in 1:length(nodes)]), ", ")
+    contrib = B isa MNA.BehavioralVoltageSource ? "V(p, n) <+ \$explicit($expr);" : "I(n, p) <+ \$explicit($expr);"
+    name = "bsrc_" * string(hash(expr), base = 16)
+    src = "module $name($ports);\n    inout $ports;\n    electrical $ports;\n    analog begin\n        $contrib\n    end\nendmodule\n"
+    return src, nodes
+end
+
 """
     export_device_table(circuit_or_sweep) -> (Desc, keepalive, lane_matrix, names)
 
