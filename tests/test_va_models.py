@@ -894,3 +894,41 @@ def test_gpu_c6288_full_transient_residual():
     assert np.linalg.norm(F) < 1e-9, np.linalg.norm(F)
     print(f"c6288 (sp_mos1): 20 BE steps, {int(r['newton_iters'][0])} Newton iterations, "
           f"kernel {tstats['tran_kernel_ms']:.1f} ms")
+
+
+# ---- C3 at BASELINE size (last on purpose: the longest single test) ------------------------------
+@pytest.mark.gpu
+def test_full_size_properties_c3():
+    """BASELINE config C3 at full size -- the 50 x 50 x 40 grid, 100 000 lanes x 4000 BE steps on the specialised
+    kernels, exactly what bench.py measures -- against the oracle on 24 SEEDED lanes of the grid (1e-9 / 1e-12 on
+    every saved point, equal Newton counts), plus what must hold for every lane whatever its parameters."""
+    from cadnip_b200 import workloads
+    lc = workloads.load_workload("mos1_c3")
+    lc.lane_soa, lc.P = workloads.c3_lanes(lc)
+    assert lc.P == 100000
+    save = [lc.index_of("q")]
+    comp = cb.CompiledSweep(lc, cb.MNASpec(mode="tran"))
+    try:
+        comp.specialize(1e-10, "be", limit=True, fixed_only=True)
+        wave = comp.tran((0.0, 4e-7), 1e-10, method="be", save_idxs=save, save_every=10, limit=True)
+        r = wave.fetch(); wave.free()
+        st = comp.handle.stats()
+    finally:
+        comp.close()
+    u = r["u"][0]                                           # [T][P]
+    assert u.shape == (401, 100000) and (r["status"] == 0).all() and np.all(np.isfinite(u))
+    # the bypass skipped work, never results: executed lane-steps are counted, every point is there
+    assert 0 < st["steps_accepted"] <= 4000 * 100000
+    assert np.all(r["newton_iters"] > 0)
+    rng = np.random.default_rng(20261019)
+    lanes = np.sort(rng.choice(100000, 24, replace=False))
+    sub = dict(lc.netlist_tables()); sub["par"] = np.ascontiguousarray(sub["par"][lanes])
+    ora.load_va_models(lc.va_c_source)
+    ro = ora.sweep_tran(ora.OracleNetlist(sub), ora.make_spec(mode="tran"), 0.0, 4e-7,
+                        ora.make_tran_opts(method=0, dt=1e-10, save_every=10, limit=True), save)
+    a, b = ro["u"][:, :401, 0], u[:, lanes].T
+    assert (ro["status"] == 0).all()
+    assert _close(a, b), float(np.max(np.abs(a - b)))
+    assert np.array_equal(r["newton_iters"][lanes], ro["newton_iters"])
+    print("C3 full size: 24 seeded lanes max |gpu - oracle|", float(np.max(np.abs(a - b))),
+          "executed lane-steps", int(st["steps_accepted"]), "of", 4000 * 100000, "kernel ms", st["tran_kernel_ms"])
