@@ -471,3 +471,26 @@ def test_bdf_controller_known_answer_and_order_raising():
     t, u = r["t"][0, :T], r["u"][0, :T, 0]
     after = t >= 1e-4 + 1e-9
     assert np.max(np.abs(u[after] - 5.0 * (1.0 - np.exp(-(t[after] - (1e-4 + 0.5e-9)) / 1e-3)))) < 2e-2
+
+
+def test_adaptive_negative_start_time_with_breakpoint_at_t0():
+    """A transient that starts at a NEGATIVE time with a source breakpoint exactly at t0: the breakpoint must be
+    skipped (4 eps(t) dedup, either sign of t), not turned into a zero-length step (h = 0 -> gamma = inf -> NaN)."""
+    def b(params, spec, t=0.0, x=ZERO_VECTOR, ctx=None):
+        ctx = MNAContext() if ctx is None else ctx
+        stamp(VoltageSource(0.0, tran=cb.PulseWave(0.0, 2.0, -1e-6, 1e-7, 1e-7, 4e-7, 1e-6), name="V1"), ctx, "in", 0)
+        stamp(Resistor(1e3, name="R1"), ctx, "in", "out")
+        stamp(Capacitor(1e-10, name="C1"), ctx, "out", 0)
+        return ctx
+    lc = lower_one(b)
+    nl = ora.OracleNetlist(lc.netlist_tables())
+    for method in (1, 3):                                     # trapezoidal + LTE, variable-order BDF
+        o = ora.make_tran_opts(method=method, adaptive=1, dt=1e-9, reltol=1e-5, lte_abstol=1e-8, max_points=20000)
+        r = ora.sweep_tran(nl, ora.make_spec(mode="tran"), -1e-6, 1e-6, o, [lc.index_of("in"), lc.index_of("out")])
+        T = int(r["T"][0])
+        t, u = r["t"][0, :T], r["u"][0, :T]
+        assert r["status"][0] == 0 and np.all(np.isfinite(u))
+        assert t[0] == -1e-6 and t[-1] == 1e-6 and np.all(np.diff(t) > 0)
+        for stop in (-1e-6 + 1e-7, -1e-6 + 5e-7, -1e-6 + 6e-7, 0.0, 1e-7):     # corners, negative and positive
+            assert np.min(np.abs(t - stop)) <= 4e-16 * max(abs(stop), 1e-6)
+        assert u[:, 0].max() == pytest.approx(2.0, abs=1e-12) and 1.5 < u[:, 1].max() <= 2.0 + 1e-9
